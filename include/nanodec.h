@@ -1,0 +1,155 @@
+/*
+ * nanodec.h — C ABI of the B200-native NanoDecoder translate engine (libnanodec.so).
+ *
+ * Drop-in boundary for the reference's translate path (achilles1989/NanoDecoder).  The reference
+ * is pure Python/PyTorch and has NO native interface of its own, so each entry point cites the
+ * reference function whose arithmetic it replaces (paths relative to the reference root):
+ *
+ *   nd_frontend_*        utils/labelop.py:194-243 (extract_fast5_raw: normalise + chunk) and
+ *                        inputters/nano_dataset.py:49-58,81 + inputters/inputter.py:86-95
+ *                        (text -> float -> zero-padded fp32 batch)
+ *   nd_encode            translate/translator.py:542-559 (_run_encoder) ->
+ *                        encoder/nano_encoder.py:79-124, encoder/transformer.py:106-127,
+ *                        encoder/cnn_encoder.py:29-44, encoder/rnn_encoder.py:64-84
+ *   nd_decode_greedy     translate/translator.py:396-503 (_translate_random_sampling, topk 1) with
+ *                        decoder/transformer.py:194-246, onmt/decoders/decoder.py:303-366,
+ *                        onmt/decoders/cnn_decoder.py:74-132, models/model_builder.py:331-334
+ *   nd_decode_beam       translate/translator.py:619-825 (_fast_translate_batch)
+ *   nd_load_weight       models/model_builder.py:343-357 (load_state_dict of checkpoint tensors)
+ *
+ * Conventions
+ *   - Every call returns 0 on success or a negative nd_status; nd_last_error() gives the message.
+ *     No C++ exception crosses the ABI.  CUDA errors are sticky per engine.
+ *   - The caller owns every input/output buffer (plain device pointers unless stated otherwise).
+ *     The engine owns only its weights copy, workspace and KV caches, sized at nd_create.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and no call
+ *     synchronises the host unless documented.
+ *   - Thread-compatible, not re-entrant: one call at a time per engine (the reference drives the
+ *     translator from one result-handler thread, translate.py:100-129).
+ *   - There is no CPU fallback: without a CUDA device nd_create fails with ND_ERR_CUDA.
+ */
+#ifndef NANODEC_H_
+#define NANODEC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ND_API_VERSION 1
+
+typedef enum {
+  ND_OK = 0,
+  ND_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  ND_ERR_CUDA = -2,        /* CUDA runtime or driver error (sticky) */
+  ND_ERR_STATE = -3,       /* call order violated (e.g. decode before encode) */
+  ND_ERR_WEIGHT = -4,      /* missing / mis-shaped checkpoint tensor */
+  ND_ERR_NOMEM = -5
+} nd_status;
+
+enum { ND_ENC_NANO = 0, ND_ENC_TRANSFORMER = 1, ND_ENC_CNN = 2, ND_ENC_RNN = 3, ND_ENC_BRNN = 4 };
+enum { ND_DEC_TRANSFORMER = 0, ND_DEC_RNN = 1, ND_DEC_CNN = 2 };
+enum { ND_ATTN_MLP = 0, ND_ATTN_GENERAL = 1, ND_ATTN_DOT = 2 };
+/* arithmetic of the dense projections */
+enum {
+  ND_GEMM_SIMT_FP32 = 0,   /* fp32 FFMA tiles (bring-up / cross-check path) */
+  ND_GEMM_TC_3XTF32 = 1,   /* tcgen05 kind::tf32, 3-pass split: fp32-parity mode */
+  ND_GEMM_TC_TF32 = 2      /* tcgen05 kind::tf32 single pass: fast mode, ~1e-3 relative error */
+};
+enum { ND_DTYPE_F32 = 0, ND_DTYPE_I64 = 1 };
+enum { ND_NORM_MEDIAN = 0, ND_NORM_MEAN = 1, ND_NORM_NONE = 2 };
+
+typedef struct nd_config {
+  int32_t api_version;        /* ND_API_VERSION */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t encoder_type;       /* ND_ENC_* */
+  int32_t decoder_type;       /* ND_DEC_* */
+  int32_t enc_layers;
+  int32_t dec_layers;
+  int32_t d_model;            /* enc_rnn_size == dec_rnn_size == tgt_word_vec_size */
+  int32_t heads;
+  int32_t d_ff;
+  int32_t vocab_size;         /* 4 specials + bases */
+  int32_t cnn_kernel_width;
+  int32_t enc_pooling[8];     /* per-layer MaxPool1d stride of the nano encoder */
+  int32_t input_feed;
+  int32_t attn_type;          /* ND_ATTN_* (RNN decoder) */
+  int32_t position_encoding;
+  int32_t max_batch;          /* chunks per nd_encode call */
+  int32_t max_src_len;        /* samples per chunk (T) */
+  int32_t max_tgt_len;        /* decode steps (L) */
+  int32_t max_beam;           /* largest beam_size that will be requested (>=1) */
+  int32_t gemm_mode;          /* ND_GEMM_* */
+  int32_t reserved[8];
+} nd_config;
+
+typedef struct nd_engine nd_engine;
+
+/* lifecycle --------------------------------------------------------------------------------- */
+int nd_create(const nd_config* cfg, nd_engine** out);
+int nd_destroy(nd_engine* e);
+const char* nd_last_error(const nd_engine* e);   /* e may be NULL: last create error */
+int nd_api_version(void);
+
+/* weights: `name` is the checkpoint key ("encoder.rnn_0.weight_ih_l0", "generator.0.bias", ...);
+ * `data` may be a host or device pointer (copied synchronously). */
+int nd_load_weight(nd_engine* e, const char* name, const void* data, const int64_t* shape,
+                   int32_t ndim, int32_t dtype);
+int nd_finalize_weights(nd_engine* e);           /* checks completeness, packs kernel layouts */
+
+/* signal front end ---------------------------------------------------------------------------
+ * signal:       int16 raw samples of n_reads reads, concatenated (device)
+ * read_offsets: [n_reads+1] int64 sample offsets (device)
+ * Pass 1 (nd_frontend_stats): exact per-read median and scale (MAD/0.6745 or std) in fp64.
+ * Pass 2 (nd_frontend_chunks): normalise in fp64, round once to fp32, gather fixed-stride chunks
+ *   chunk_read/chunk_start: [n_chunks] which read / first sample of each chunk (device; the chunk
+ *   table is built by the host mirror from read lengths exactly as utils/labelop.py:225-233)
+ *   out_chunks: [n_chunks, chunk_len] fp32 zero padded; out_lengths: [n_chunks] int64            */
+int nd_frontend_stats(nd_engine* e, const int16_t* signal, const int64_t* read_offsets,
+                      int32_t n_reads, int32_t normalization, double* out_center,
+                      double* out_scale, void* stream);
+int nd_frontend_chunks(nd_engine* e, const int16_t* signal, const int64_t* read_offsets,
+                       const double* center, const double* scale, const int32_t* chunk_read,
+                       const int64_t* chunk_start, int32_t n_chunks, int32_t chunk_len,
+                       float* out_chunks, int64_t* out_lengths, void* stream);
+
+/* encoder ------------------------------------------------------------------------------------
+ * src: [B, T] fp32 chunk-major zero padded; lengths: [B] int64 (device).                       */
+int nd_encode(nd_engine* e, const float* src, const int64_t* lengths, int32_t B, int32_t T,
+              void* stream);
+/* copy out the memory bank of the last nd_encode as [T', B, d] (reference layout; for the CNN
+ * encoder [d, B, T]) and its lengths [B]; T' is returned through out_Tp.  For parity tests.      */
+int nd_get_memory_bank(nd_engine* e, float* out, int64_t* out_lengths, int32_t* out_Tp,
+                       void* stream);
+
+/* decode -------------------------------------------------------------------------------------
+ * Greedy: runs exactly max_len steps like the reference (no EOS early exit).
+ *   out_ids    [B, max_len] int64
+ *   out_scores [B] fp32: log-prob of the LAST step's token (translator.py:494)
+ *   out_attn   NULL or [max_len, B, T'] fp32 (head-0 cross attention of the last layer)
+ *   out_logits NULL or [max_len, B, V] fp32 log-probs of every step (parity tests)               */
+int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* out_ids,
+                     float* out_scores, float* out_attn, float* out_logits, void* stream);
+/* Fast batched beam search (--fast).
+ *   out_ids     [B, n_best, max_len] int64, padded with -1 after each hypothesis' last token
+ *   out_lens    [B, n_best] int32 hypothesis lengths (including the final </s> if emitted)
+ *   out_scores  [B, n_best] fp32                                                                 */
+int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len,
+                   int32_t min_len, float alpha, int64_t* out_ids, int32_t* out_lens,
+                   float* out_scores, void* stream);
+
+/* bookkeeping for bench.py: kernels launched by this engine since creation / last reset.        */
+int64_t nd_launch_count(const nd_engine* e);
+int nd_reset_launch_count(nd_engine* e);
+
+/* standalone kernel entry points (unit tests / microbenchmarks) -------------------------------
+ * C[M,N] = act(LN?(A)[M,K] . W[N,K]^T + bias) (+ residual); row-major fp32 device pointers.      */
+int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, const float* bias,
+                 const float* residual, const float* ln_gamma, const float* ln_beta, float* C,
+                 int32_t M, int32_t N, int32_t K, int32_t relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANODEC_H_ */

@@ -1,0 +1,39 @@
+// Dense projection interface shared by the SIMT and tcgen05 GEMM kernels.
+//   C[M,N] = epilogue( prologue(A)[M,K] . W[N,K]^T )
+// A, W, C row-major fp32 (W is an nn.Linear weight: K contiguous).
+#pragma once
+#include "common.cuh"
+
+namespace nd {
+
+enum { PRO_NONE = 0, PRO_LAYERNORM = 1, PRO_AFFINE = 2 };
+
+struct GemmParams {
+  const float* A = nullptr;  int64_t lda = 0;
+  const float* W = nullptr;  int64_t ldw = 0;   // hi part (or the full fp32 weight)
+  const float* W_lo = nullptr;                   // tf32 residual W - tf32(W) (3xTF32 mode only)
+  const float* bias = nullptr;                   // [N]
+  float* C = nullptr;        int64_t ldc = 0;
+  const float* residual = nullptr; int64_t ldr = 0;   // added after the activation
+  int M = 0, N = 0, K = 0;
+  // prologue applied to A while it is staged:
+  //   PRO_LAYERNORM: (a - mean_row) * rstd_row * pg[k] + pb[k]   (nn.LayerNorm, eps)
+  //   PRO_AFFINE:    a * pg[k] + pb[k]                          (eval BatchNorm1d folded to alpha/beta)
+  int prologue = PRO_NONE;
+  const float* pg = nullptr; const float* pb = nullptr; float eps = 1e-6f;
+  int relu = 0;
+  // columns [0, div_ncols) are divided by div_by after the bias (q / sqrt(dh), multi_headed_attn.py:167)
+  float div_by = 1.0f; int div_ncols = 0;
+};
+
+// both return cudaError_t of the launch
+cudaError_t gemm_simt(const GemmParams& p, cudaStream_t stream);
+// npass: 3 = 3xTF32 (fp32 parity), 1 = single TF32
+cudaError_t gemm_tc(const GemmParams& p, int npass, cudaStream_t stream);
+// one-time driver entry-point lookup for tensor-map encoding; returns false if unavailable
+bool gemm_tc_available(const char** why);
+
+// split an fp32 weight into tf32 hi (low 13 mantissa bits cleared) and lo = w - hi
+void split_tf32_host(const float* w, float* hi, float* lo, size_t n);
+
+}  // namespace nd

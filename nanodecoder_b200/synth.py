@@ -1,0 +1,243 @@
+"""Seeded synthetic checkpoints and synthetic signal for tests and benchmarks.
+
+There is no network in the build / GPU environment, so every number in this repo is measured on
+random-init weights of the named architecture and on synthetic raw signal.
+The state dict uses the reference's exact key names and shapes (models/model_builder.py:65-214,
+onmt/models/model_saver.py:105-115) so the same dict loads into the reference's own modules
+(`oracle/make_golden.py` does that with ``load_state_dict``).
+
+Values come from numpy PCG64 streams keyed by (seed, parameter name) so they do not depend on
+generation order, torch version, or device.
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict
+
+import numpy as np
+import torch
+
+from .config import ModelConfig
+
+
+def _rng(seed: int, key: str) -> np.random.Generator:
+    return np.random.default_rng([seed, zlib.crc32(key.encode())])
+
+
+class _Builder:
+    def __init__(self, seed: int):
+        self.seed = seed
+        self.sd: Dict[str, torch.Tensor] = {}
+
+    def normal(self, key, shape, std):
+        x = _rng(self.seed, key).standard_normal(shape).astype(np.float32) * np.float32(std)
+        self.sd[key] = torch.from_numpy(x)
+        return self.sd[key]
+
+    def matrix(self, key, out_f, in_f, gain=1.0, extra=()):
+        return self.normal(key, (out_f, in_f) + tuple(extra), gain / np.sqrt(in_f * max(1, int(np.prod(extra)))))
+
+    def bias(self, key, n, std=0.05):
+        return self.normal(key, (n,), std)
+
+    def affine(self, prefix, n):
+        """LayerNorm / BatchNorm affine: scale around 1, small shift."""
+        w = 1.0 + 0.1 * _rng(self.seed, prefix + ".weight").standard_normal(n)
+        b = 0.05 * _rng(self.seed, prefix + ".bias").standard_normal(n)
+        self.sd[prefix + ".weight"] = torch.from_numpy(w.astype(np.float32))
+        self.sd[prefix + ".bias"] = torch.from_numpy(b.astype(np.float32))
+
+    def linear(self, prefix, out_f, in_f, bias=True, gain=1.0):
+        self.matrix(prefix + ".weight", out_f, in_f, gain)
+        if bias:
+            self.bias(prefix + ".bias", out_f)
+
+    def lstm(self, prefix, suffix, in_f, hidden, gain_ih=1.0):
+        self.matrix("%s.weight_ih%s" % (prefix, suffix), 4 * hidden, in_f, gain_ih)
+        self.matrix("%s.weight_hh%s" % (prefix, suffix), 4 * hidden, hidden, 1.0)
+        self.bias("%s.bias_ih%s" % (prefix, suffix), 4 * hidden)
+        self.bias("%s.bias_hh%s" % (prefix, suffix), 4 * hidden)
+
+    def mha(self, prefix, d, qk_gain=1.0, out_gain=1.0):
+        self.linear(prefix + ".linear_keys", d, d, gain=qk_gain)
+        self.linear(prefix + ".linear_values", d, d)
+        self.linear(prefix + ".linear_query", d, d, gain=qk_gain)
+        self.linear(prefix + ".final_linear", d, d, gain=out_gain)
+
+    def ffn(self, prefix, d, ff, out_gain=1.0):
+        self.linear(prefix + ".w_1", ff, d)
+        self.linear(prefix + ".w_2", d, ff, gain=out_gain)
+        self.affine(prefix + ".layer_norm", d)
+
+    def wnconv(self, prefix, d, width):
+        """WeightNormConv2d (onmt/modules/weight_norm.py:101-169): weight==V, bias==b aliases and
+        the Polyak buffers equal to the live values, as in a trained checkpoint, so the
+        eval-time buffer update is exactly a no-op."""
+        v = self.matrix(prefix + ".V", 2 * d, d, 1.0, extra=(width, 1))
+        g = 1.0 + 0.1 * _rng(self.seed, prefix + ".g").standard_normal(2 * d)
+        g = torch.from_numpy(g.astype(np.float32))
+        b = self.bias(prefix + ".b", 2 * d)
+        self.sd[prefix + ".g"] = g
+        self.sd[prefix + ".weight"] = v.clone()
+        self.sd[prefix + ".bias"] = b.clone()
+        self.sd[prefix + ".V_avg"] = v.clone()
+        self.sd[prefix + ".g_avg"] = g.clone()
+        self.sd[prefix + ".b_avg"] = b.clone()
+
+
+# Gains that make a random-init model signal-sensitive: sharp cross-attention and a weak
+# previous-token embedding, so different chunks decode to different, non-constant sequences
+# (plain 1/sqrt(fan_in) init collapses to one repeated token; SURVEY.md §7 "hard parts").
+DEFAULT_GAINS = dict(emb_std=0.5, attn_qk=2.0, ctx_out=2.0, self_qk=1.0, self_out=1.0, ffn_out=1.0,
+                     gen=3.0, eos_bias=-1.5)
+
+
+# per-family gains found by a small random search (entropy of the greedy token histogram >= 1.4 bits
+# and (nearly) all of 16 chunks decoding to different sequences at d=256, 3+3 layers, seed 2025)
+FAMILY_GAINS = {
+    ("nano", "transformer"): dict(emb_std=0.3, attn_qk=2.0, ctx_out=3.0, self_qk=2.0, self_out=4.0,
+                                  ffn_out=2.0, gen=1.0, eos_bias=-0.07),
+    ("transformer", "transformer"): dict(emb_std=0.3, attn_qk=1.0, ctx_out=1.0, self_qk=2.0,
+                                         self_out=0.5, ffn_out=1.0, gen=2.0, eos_bias=-1.0),
+    ("nano", "rnn"): dict(emb_std=0.1, attn_qk=2.5, ctx_out=6.0, gen=1.0, eos_bias=-0.5),
+    ("brnn", "rnn"): dict(emb_std=1.0, attn_qk=1.5, ctx_out=2.0, gen=3.0, eos_bias=-1.0),
+    ("cnn", "cnn"): dict(emb_std=1.0, attn_qk=2.5, ctx_out=2.0, gen=2.0, eos_bias=-0.5),
+}
+
+
+def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> Dict[str, torch.Tensor]:
+    """Flat state dict: reference ``model.state_dict()`` keys incl. ``generator.0.*``."""
+    b = _Builder(seed)
+    G = dict(DEFAULT_GAINS)
+    G.update(FAMILY_GAINS.get((cfg.encoder_type, cfg.decoder_type), {}))
+    G.update(gains or {})
+    d, V = cfg.d_model, cfg.vocab_size
+    h = d // 2
+
+    # ---------------- encoder
+    if cfg.encoder_type == "nano":              # encoder/nano_encoder.py:26-77
+        b.linear("encoder.W", d, d, bias=False)
+        for l in range(cfg.enc_layers):
+            in_f = 1 if l == 0 else d
+            for sfx in ("_l0", "_l0_reverse"):
+                b.lstm("encoder.rnn_%d" % l, sfx, in_f, h, gain_ih=1.0)
+            p = "encoder.batchnorm_%d" % l
+            b.affine(p, d)
+            b.normal(p + ".running_mean", (d,), 0.05)
+            rv = 0.1 + 0.05 * np.abs(_rng(seed, p + ".running_var").standard_normal(d))
+            b.sd[p + ".running_var"] = torch.from_numpy(rv.astype(np.float32))
+            b.sd[p + ".num_batches_tracked"] = torch.tensor(1000, dtype=torch.int64)
+    elif cfg.encoder_type in ("rnn", "brnn"):   # encoder/rnn_encoder.py:23-62
+        dirs = 2 if cfg.encoder_type == "brnn" else 1
+        hh = d // dirs
+        for l in range(cfg.enc_layers):
+            in_f = 1 if l == 0 else d
+            b.lstm("encoder.rnn", "_l%d" % l, in_f, hh)
+            if dirs == 2:
+                b.lstm("encoder.rnn", "_l%d_reverse" % l, in_f, hh)
+    elif cfg.encoder_type == "transformer":     # encoder/transformer.py:87-104
+        b.linear("encoder.linear", d, 1)
+        for l in range(cfg.enc_layers):
+            p = "encoder.transformer.%d" % l
+            b.mha(p + ".self_attn", d)
+            b.ffn(p + ".feed_forward", d, cfg.d_ff)
+            b.affine(p + ".layer_norm", d)
+        b.affine("encoder.layer_norm", d)
+    elif cfg.encoder_type == "cnn":             # encoder/cnn_encoder.py:18-27
+        b.linear("encoder.linear", d, 1)
+        for l in range(cfg.enc_layers):
+            b.wnconv("encoder.cnn.layers.%d.conv" % l, d, cfg.cnn_kernel_width)
+
+    # ---------------- decoder
+    b.normal("decoder.embeddings.make_embedding.emb_luts.0.weight", (V, d), G["emb_std"])
+    if cfg.decoder_type == "transformer":       # decoder/transformer.py:145-171
+        for l in range(cfg.dec_layers):
+            p = "decoder.transformer_layers.%d" % l
+            b.mha(p + ".self_attn", d, qk_gain=G["self_qk"], out_gain=G["self_out"])
+            b.mha(p + ".context_attn", d, qk_gain=G["attn_qk"], out_gain=G["ctx_out"])
+            b.ffn(p + ".feed_forward", d, cfg.d_ff, out_gain=G["ffn_out"])
+            b.affine(p + ".layer_norm_1", d)
+            b.affine(p + ".layer_norm_2", d)
+        b.affine("decoder.layer_norm", d)
+    elif cfg.decoder_type == "rnn":             # onmt/decoders/decoder.py:57-106,352-366
+        for l in range(cfg.dec_layers):
+            in_f = (2 * d if cfg.input_feed else d) if l == 0 else d
+            p = "decoder.rnn.layers.%d" % l
+            b.matrix(p + ".weight_ih", 4 * d, in_f)
+            b.matrix(p + ".weight_hh", 4 * d, d)
+            b.bias(p + ".bias_ih", 4 * d)
+            b.bias(p + ".bias_hh", 4 * d)
+        # onmt/modules/global_attention.py:71-93
+        if cfg.global_attention == "mlp":
+            b.linear("decoder.attn.linear_context", d, d, bias=False)
+            b.linear("decoder.attn.linear_query", d, d)
+            b.linear("decoder.attn.v", 1, d, bias=False, gain=4.0 * G["attn_qk"])
+            b.linear("decoder.attn.linear_out", d, 2 * d, bias=True, gain=G["ctx_out"])
+        else:
+            if cfg.global_attention == "general":
+                b.linear("decoder.attn.linear_in", d, d, bias=False)
+            b.linear("decoder.attn.linear_out", d, 2 * d, bias=False, gain=G["ctx_out"])
+    elif cfg.decoder_type == "cnn":             # onmt/decoders/cnn_decoder.py:20-49
+        b.linear("decoder.linear", d, d)
+        for l in range(cfg.dec_layers):
+            b.wnconv("decoder.conv_layers.%d.conv" % l, d, cfg.cnn_kernel_width)
+            b.linear("decoder.attn_layers.%d.linear_in" % l, d, d, gain=G["attn_qk"])
+
+    # ---------------- generator (models/model_builder.py:331-334)
+    b.matrix("generator.0.weight", V, d, G["gen"])
+    gb = b.bias("generator.0.bias", V, 0.2)
+    # make the specials (<unk>, <blank>, <s>) unattractive so sequences look like bases + </s>
+    gb[0:3] -= 6.0
+    gb[3] += G["eos_bias"]
+    return b.sd
+
+
+def make_checkpoint(cfg: ModelConfig, seed: int = 2025) -> dict:
+    """Checkpoint dict in the reference layout (onmt/models/model_saver.py:105-115)."""
+    from .checkpoint import make_vocab_entry
+    sd = make_state_dict(cfg, seed)
+    return {
+        "model": {k: v for k, v in sd.items() if not k.startswith("generator.")},
+        "generator": {k[len("generator."):]: v for k, v in sd.items() if k.startswith("generator.")},
+        "vocab": make_vocab_entry(cfg.vocab),
+        "opt": cfg.to_opt(),
+        "optim": None,
+    }
+
+
+# --------------------------------------------------------------------------- synthetic signal
+def make_chunks(n_chunks: int, T: int = 512, seed: int = 1234, ragged: bool = True,
+                read_len: int = 16):
+    """Normalised signal chunks as the front end would emit them.
+
+    -> (src [n_chunks, T] fp32 zero padded, lengths [n_chunks] int64).
+    Values are N(0,1) quantised to 1/64 with 1 % of samples exactly 0.0 and 0.1 % exactly 1.0,
+    so the value-equality attention masks of the reference are exercised
+    (encoder/transformer.py:120-121, decoder/transformer.py:220-221).  With ``ragged`` the last
+    chunk of each synthetic read of ``read_len`` chunks is short (64..T-1 samples).
+    """
+    rng = np.random.default_rng([seed, 7])
+    x = np.round(rng.standard_normal((n_chunks, T)) * 64.0) / 64.0
+    u = rng.random((n_chunks, T))
+    x[u < 0.01] = 0.0
+    x[u > 0.999] = 1.0
+    lengths = np.full((n_chunks,), T, dtype=np.int64)
+    if ragged:
+        last = np.arange(read_len - 1, n_chunks, read_len)
+        lengths[last] = rng.integers(64, T, size=last.shape[0])
+        for i in last:
+            x[i, lengths[i]:] = 0.0
+    return torch.from_numpy(x.astype(np.float32)), torch.from_numpy(lengths)
+
+
+def make_raw_reads(n_reads: int, seed: int = 99, min_len: int = 2000, max_len: int = 200000):
+    """Synthetic int16 raw reads: N ~ U(min_len,max_len), values ~ N(500,80) clipped to [0,2047]."""
+    rng = np.random.default_rng([seed, 11])
+    lens = rng.integers(min_len, max_len + 1, size=n_reads)
+    reads = []
+    for n in lens:
+        # slow level changes + noise, like a squiggle
+        levels = rng.normal(500.0, 80.0, size=int(n) // 9 + 2)
+        sig = np.repeat(levels, 9)[: int(n)] + rng.normal(0.0, 12.0, size=int(n))
+        reads.append(np.clip(np.round(sig), 0, 2047).astype(np.int16))
+    return reads

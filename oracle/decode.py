@@ -1,0 +1,149 @@
+"""ORACLE (test infrastructure): restatement of the reference's decode loops
+(translate/translator.py) over ``oracle.model.OracleModel``.  Citations relative to /root/reference.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+UNK, PAD, BOS, EOS = 0, 1, 2, 3
+
+
+def _run_encoder(model, src, src_lengths):
+    """translate/translator.py:542-559."""
+    enc_states, memory_bank, lengths = model.encoder(src, src_lengths)
+    return src, enc_states, memory_bank, lengths
+
+
+def _decode_and_generate(model, decoder_in, memory_bank, memory_lengths, step):
+    """translate/translator.py:561-617 (no copy attention)."""
+    dec_out, attn = model.decoder(decoder_in, memory_bank, memory_lengths=memory_lengths, step=step)
+    return model.generator(dec_out.squeeze(0)), attn
+
+
+def greedy(model, src, src_lengths, max_length=100, min_length=0, return_attention=False,
+           trace_logits=None):
+    """translate/translator.py:396-503 with keep_topk == 1 (argmax; :371-375).
+    Runs all ``max_length`` steps — the reference has no EOS early exit (:455).
+    -> dict(predictions [B,L] int64, scores [B] (LAST step's log-prob only, :494),
+            attention [L,B,T] or None, memory_bank, memory_lengths)"""
+    with torch.no_grad():
+        B = src.size(1)
+        src, enc_states, memory_bank, memory_lengths = _run_encoder(model, src, src_lengths)
+        model.decoder.init_state(src, memory_bank, enc_states)
+        seq = torch.full([B, 1], BOS, dtype=torch.long)
+        attns = []
+        topk_scores = None
+        for step in range(max_length):
+            decoder_input = seq[:, -1].view(1, -1, 1)
+            log_probs, attn = _decode_and_generate(model, decoder_input, memory_bank,
+                                                   memory_lengths, step)
+            if step < min_length:
+                log_probs[:, EOS] = -1e20                           # :469-470
+            if trace_logits is not None:
+                trace_logits.append(log_probs.clone())
+            topk_scores, topk_ids = log_probs.topk(1, dim=-1)       # :375
+            seq = torch.cat([seq, topk_ids.view(-1, 1)], -1)        # :477
+            if return_attention:
+                attns.append(attn.reshape(-1, attn.size(-1)))
+        return {"predictions": seq[:, 1:].contiguous(), "scores": topk_scores[:, 0].clone(),
+                "attention": torch.stack(attns) if attns else None,
+                "memory_bank": memory_bank, "memory_lengths": memory_lengths}
+
+
+def _tile(x, count, dim=0):
+    """onmt/utils/misc.py:28-47: each batch entry repeated ``count`` times consecutively."""
+    return x.repeat_interleave(count, dim=dim)
+
+
+def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0, n_best=1,
+              alpha=0.0):
+    """translate/translator.py:619-825 (``--fast`` batched beam search, no attention return).
+    -> dict(predictions: list[B] of list[n_best] of LongTensor, scores: list[B] of list[float])"""
+    with torch.no_grad():
+        B, K = src.size(1), beam_size
+        src, enc_states, memory_bank, src_lengths = _run_encoder(model, src, src_lengths)
+        model.decoder.init_state(src, memory_bank, enc_states)
+        model.decoder.map_state(lambda s, dim: _tile(s, K, dim))    # :667-668
+        memory_bank = _tile(memory_bank, K, 1)                      # :673
+        memory_lengths = _tile(src_lengths, K)                      # :676
+        top_beam_finished = torch.zeros([B], dtype=torch.bool)
+        batch_offset = torch.arange(B, dtype=torch.long)
+        beam_offset = torch.arange(0, B * K, step=K, dtype=torch.long)
+        alive_seq = torch.full([B * K, 1], BOS, dtype=torch.long)
+        topk_log_probs = torch.tensor([0.0] + [float("-inf")] * (K - 1)).repeat(B)   # :691-693
+        hypotheses = [[] for _ in range(B)]
+        results = {"predictions": [[] for _ in range(B)], "scores": [[] for _ in range(B)]}
+
+        for step in range(max_length):
+            decoder_input = alive_seq[:, -1].view(1, -1, 1)
+            log_probs, _ = _decode_and_generate(model, decoder_input, memory_bank,
+                                                memory_lengths, step)
+            V = log_probs.size(-1)
+            if step < min_length:
+                log_probs[:, EOS] = -1e20                           # :714-715
+            log_probs = log_probs + topk_log_probs.view(-1).unsqueeze(1)        # :718
+            length_penalty = ((5.0 + (step + 1)) / 6.0) ** alpha    # :720-721
+            curr_scores = (log_probs / length_penalty).reshape(-1, K * V)
+            topk_scores, topk_ids = curr_scores.topk(K, dim=-1)     # :726
+            topk_log_probs = topk_scores * length_penalty           # :729
+            topk_beam_index = torch.div(topk_ids, V, rounding_mode="trunc")    # :732
+            topk_ids = topk_ids.fmod(V)                             # :733
+            batch_index = topk_beam_index + beam_offset[:topk_beam_index.size(0)].unsqueeze(1)
+            select_indices = batch_index.view(-1)
+            alive_seq = torch.cat([alive_seq.index_select(0, select_indices),
+                                   topk_ids.view(-1, 1)], -1)       # :742-744
+            is_finished = topk_ids.eq(EOS)
+            if step + 1 == max_length:
+                is_finished.fill_(True)                             # :754-755
+            if is_finished.any():
+                topk_log_probs = topk_log_probs.masked_fill(is_finished, -1e10)   # :760
+                top_beam_finished |= is_finished[:, 0]
+                predictions = alive_seq.view(-1, K, alive_seq.size(-1))
+                non_finished_batch = []
+                for i in range(is_finished.size(0)):
+                    b = int(batch_offset[i])
+                    for j in is_finished[i].nonzero().view(-1).tolist():
+                        hypotheses[b].append((topk_scores[i, j], predictions[i, j, 1:]))
+                    if top_beam_finished[i] and len(hypotheses[b]) >= n_best:   # :781
+                        best = sorted(hypotheses[b], key=lambda x: x[0], reverse=True)
+                        for n, (score, pred) in enumerate(best):
+                            if n >= n_best:
+                                break
+                            results["scores"][b].append(float(score))
+                            results["predictions"][b].append(pred.clone())
+                    else:
+                        non_finished_batch.append(i)
+                non_finished = torch.tensor(non_finished_batch, dtype=torch.long)
+                if len(non_finished) == 0:
+                    break
+                top_beam_finished = top_beam_finished.index_select(0, non_finished)
+                batch_offset = batch_offset.index_select(0, non_finished)
+                topk_log_probs = topk_log_probs.index_select(0, non_finished)
+                batch_index = batch_index.index_select(0, non_finished)
+                select_indices = batch_index.view(-1)
+                alive_seq = predictions.index_select(0, non_finished).view(-1, alive_seq.size(-1))
+            memory_bank = memory_bank.index_select(1, select_indices)           # :813-817
+            memory_lengths = memory_lengths.index_select(0, select_indices)
+            model.decoder.map_state(lambda s, dim: s.index_select(dim, select_indices))
+        return results
+
+
+def build_target_tokens(pred, itos):
+    """translate/translation.py:31-41: ids -> tokens, cut at the first ``</s>``."""
+    tokens = []
+    for tok in pred.tolist() if hasattr(pred, "tolist") else pred:
+        if itos[tok] == "</s>":
+            break
+        tokens.append(itos[tok])
+    return tokens
+
+
+def count_bases(pred_ids: torch.Tensor) -> int:
+    """Bases = tokens before the first </s> (what translate.py:85-95 counts as len(c_bpread) when
+    stride == length; specials other than </s> are counted as the reference's string join keeps
+    them as tokens too)."""
+    is_eos = pred_ids.eq(EOS)
+    first = torch.where(is_eos.any(1), is_eos.float().argmax(1), torch.full_like(pred_ids[:, 0], pred_ids.size(1)))
+    return int(first.sum())

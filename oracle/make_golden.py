@@ -1,0 +1,248 @@
+"""Generate golden vectors by running the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz
+
+For every model family it
+  1. builds the reference's own model through its factory (models/model_builder.py:236-389),
+  2. loads the seeded synthetic state dict from ``nanodecoder_b200.synth`` with
+     ``load_state_dict`` and checks the key sets agree (pins the checkpoint layout),
+  3. runs the reference's ``Translator.translate_batch`` (greedy and ``--fast`` beam) on seeded
+     synthetic chunks through a fake batch object,
+  4. checks the oracle port (oracle/model.py, oracle/decode.py) against it, and
+  5. stores inputs' seeds + reference outputs as a small .npz fixture.
+
+The fixtures are what ``tests/test_oracle_golden.py`` (CPU) and the ``-m gpu`` parity tests
+compare against on machines where the reference is not available.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim                                   # noqa: E402
+from oracle import decode as odecode                         # noqa: E402
+from oracle import frontend as ofrontend                     # noqa: E402
+from oracle.model import OracleModel                         # noqa: E402
+from nanodecoder_b200.config import ModelConfig              # noqa: E402
+from nanodecoder_b200 import synth                           # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+LOGIT_STEPS = (0, 1, 2, 7, 50, 99)
+
+# name -> (family, kwargs)   full-size d=256 3+3 configs of BASELINE.json plus small variants
+CASES = {
+    "l2t_d256": ("l2t", dict()),
+    "t2t_d256": ("t2t", dict()),
+    "nano2rnn_d256": ("nano2rnn", dict()),
+    "brnn2rnn_d256": ("brnn2rnn", dict()),
+    "cnn2cnn_d256": ("cnn2cnn", dict()),
+    "l2t_d64": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2)),
+    "t2t_d64": ("t2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2)),
+    "t2t_d512_6x6": ("t2t", dict(d_model=512, enc_layers=6, dec_layers=6)),
+}
+
+
+def load_into_reference(model, sd):
+    ref_keys = set(model.state_dict().keys())
+    ours = set(sd.keys())
+    missing = {k for k in ref_keys - ours if not k.endswith(".mask")}
+    extra = ours - ref_keys
+    assert not missing, "synthetic state dict lacks reference keys: %s" % sorted(missing)[:8]
+    assert not extra, "synthetic state dict has unknown keys: %s" % sorted(extra)[:8]
+    for k, v in model.state_dict().items():
+        if k in sd:
+            assert tuple(v.shape) == tuple(sd[k].shape), (k, v.shape, sd[k].shape)
+    model.load_state_dict(sd, strict=False)
+    return model.eval()
+
+
+def run_reference(family, cfg, sd, src, lengths, max_length, beam_size):
+    model, fields, mopt = refshim.build_reference_model(
+        family, d=cfg.d_model, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers,
+        heads=cfg.heads, ff=cfg.d_ff)
+    load_into_reference(model, sd)
+    assert list(fields["tgt"].vocab.itos) == cfg.vocab
+    out = {}
+    # ---- greedy
+    tr = refshim.build_reference_translator(model, fields, mopt, beam_size=1, max_length=max_length)
+    logits = []
+    orig = tr._decode_and_generate
+
+    def spy(*a, **k):
+        lp, attn = orig(*a, **k)
+        logits.append(lp.detach().clone())
+        return lp, attn
+
+    tr._decode_and_generate = spy
+    mb_holder = {}
+    orig_enc = tr._run_encoder
+
+    def enc_spy(batch, data_type):
+        r = orig_enc(batch, data_type)
+        mb_holder["mb"], mb_holder["lens"] = r[2].detach().clone(), r[3].detach().clone()
+        return r
+
+    tr._run_encoder = enc_spy
+    batch = refshim.FakeBatch(src.clone(), lengths.clone())
+    t0 = time.time()
+    res = tr.translate_batch(batch, refshim.FakeData(), False, fast=False)
+    out["greedy_seconds"] = time.time() - t0
+    out["greedy_ids"] = torch.stack([p[0] for p in res["predictions"]])
+    out["greedy_scores"] = torch.stack([s[0] for s in res["scores"]])
+    out["logits"] = torch.stack([logits[s] for s in LOGIT_STEPS if s < max_length])
+    out["memory_bank"] = mb_holder["mb"]
+    out["memory_lengths"] = mb_holder["lens"]
+    # ---- fast beam
+    if beam_size > 1:
+        trb = refshim.build_reference_translator(model, fields, mopt, beam_size=beam_size,
+                                                 fast=True, max_length=max_length)
+        batch = refshim.FakeBatch(src.clone(), lengths.clone())
+        t0 = time.time()
+        resb = trb.translate_batch(batch, refshim.FakeData(), False, fast=True)
+        out["beam_seconds"] = time.time() - t0
+        out["beam_ids"] = [p[0] for p in resb["predictions"]]
+        out["beam_scores"] = torch.tensor([float(s[0]) for s in resb["scores"]])
+    return out
+
+
+def pad_ragged(seqs, L, fill=-1):
+    out = np.full((len(seqs), L), fill, dtype=np.int64)
+    for i, s in enumerate(seqs):
+        out[i, : len(s)] = s.numpy()
+    return out
+
+
+def make_case(name, B=6, T=512, max_length=100, beam_size=5, seed=2025, write=True):
+    family, kw = CASES[name]
+    cfg = ModelConfig.family(family, **kw)
+    sd = synth.make_state_dict(cfg, seed=seed)
+    chunks, lengths = synth.make_chunks(B, T=T, seed=1234, ragged=True, read_len=3)
+    order = torch.argsort(lengths, descending=True, stable=True)      # iterator order
+    chunks, lengths = chunks[order], lengths[order]
+    src = chunks.t().contiguous().unsqueeze(2)                        # [T,B,1]
+
+    ref = run_reference(family, cfg, sd, src, lengths, max_length, beam_size)
+
+    # ---- oracle port vs reference
+    om = OracleModel(sd, cfg)
+    trace = []
+    og = odecode.greedy(om, src, lengths, max_length=max_length, trace_logits=trace)
+    mb_err = (og["memory_bank"] - ref["memory_bank"]).abs().max().item()
+    mb_scale = ref["memory_bank"].abs().max().item()
+    ol = torch.stack([trace[s] for s in LOGIT_STEPS if s < max_length])
+    lg_err = (ol - ref["logits"]).abs().max().item()
+    same_ids = bool((og["predictions"] == ref["greedy_ids"]).all())
+    assert torch.equal(og["memory_lengths"], ref["memory_lengths"])
+    ob = odecode.beam_fast(om, src, lengths, beam_size=beam_size, max_length=max_length)
+    beam_same = all(torch.equal(a[0], b) for a, b in zip(ob["predictions"], ref["beam_ids"]))
+    bs_err = (torch.tensor([s[0] for s in ob["scores"]]) - ref["beam_scores"]).abs().max().item()
+    ids = ref["greedy_ids"]
+    hist = torch.bincount(ids.flatten(), minlength=cfg.vocab_size).float()
+    p = hist / hist.sum()
+    entropy = float(-(p[p > 0] * p[p > 0].log2()).sum())
+    n_eos = int(ids.eq(3).any(1).sum())
+    print("%-16s ref greedy %.1fs beam %.1fs | oracle-vs-ref: mb %.2e (scale %.2f) logits %.2e "
+          "greedy_ids_same=%s beam_same=%s beam_score %.2e | token entropy %.2f bits, "
+          "%d/%d chunks emit </s>" % (name, ref["greedy_seconds"], ref.get("beam_seconds", 0), mb_err,
+                                      mb_scale, lg_err, same_ids, beam_same, bs_err, entropy,
+                                      n_eos, B))
+    assert mb_err <= 2e-5 * max(1.0, mb_scale), "oracle encoder deviates from the reference"
+    assert lg_err <= 2e-4, "oracle logits deviate from the reference"
+    assert same_ids, "oracle greedy ids differ from the reference"
+    assert beam_same and bs_err < 1e-3, "oracle beam output differs from the reference"
+
+    if write:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        mb = ref["memory_bank"]
+        np.savez_compressed(
+            os.path.join(GOLDEN_DIR, name + ".npz"),
+            family=family, cfg_json=np.array(repr(cfg.asdict())), weight_seed=seed, chunk_seed=1234,
+            B=B, T=T, max_length=max_length, beam_size=beam_size, read_len=3,
+            src=src[:, :, 0].t().contiguous().numpy(), lengths=lengths.numpy(),
+            logit_steps=np.array([s for s in LOGIT_STEPS if s < max_length]),
+            logits=ref["logits"].numpy(),
+            greedy_ids=ref["greedy_ids"].numpy(), greedy_scores=ref["greedy_scores"].numpy(),
+            memory_lengths=ref["memory_lengths"].numpy(),
+            memory_shape=np.array(mb.shape),
+            # strided sample of the memory bank + moments of the whole tensor (keeps the file small)
+            memory_sample=mb.flatten()[::97].numpy().copy(),
+            memory_sum=np.float64(mb.double().sum().item()),
+            memory_abs_sum=np.float64(mb.double().abs().sum().item()),
+            beam_ids=pad_ragged(ref["beam_ids"], max_length), beam_scores=ref["beam_scores"].numpy(),
+            token_entropy_bits=entropy,
+        )
+
+
+def make_frontend_golden(write=True):
+    """Front end: run the reference's extract_fast5_raw on '.signal' text files.
+
+    'mean' normalisation is pure numpy inside the reference -> fully pinned.  For 'median' the
+    reference calls statsmodels.robust.mad, which is not installed: the harness injects the
+    oracle's restatement of that one function (documented in oracle/frontend.py), so chunking,
+    the subtraction/division and the text round trip are pinned; mad itself is cross-checked
+    against scipy.stats.median_abs_deviation in the tests."""
+    refshim.install()
+    import tempfile
+    import statsmodels.robust as robust
+    if not hasattr(robust, "mad"):
+        robust.mad = ofrontend.mad
+    import numpy
+    if not hasattr(numpy, "float"):
+        numpy.float = float                                  # np.float was removed in numpy 1.24
+    from utils.labelop import extract_fast5_raw
+    reads = synth.make_raw_reads(4, seed=99, min_len=700, max_len=5000)
+    reads.append(np.array([500, 510, 490, 500, 505], dtype=np.int16))          # 1 short chunk
+    reads.append(synth.make_raw_reads(1, seed=5, min_len=1024, max_len=1024)[0])  # exact multiple
+    store = {}
+    for ri, raw in enumerate(reads):
+        with tempfile.NamedTemporaryFile("w", suffix=".signal", delete=False) as f:
+            f.write(" ".join(str(int(v)) for v in raw))
+            path = f.name
+        for norm in ("median", "mean"):
+            for (L, S) in ((512, 512), (300, 60)):
+                res = extract_fast5_raw(path, "r%d.txt" % ri, norm, L, S, "signal")
+                ref_chunks = [np.array([float(x) for x in s.split()], dtype=np.float64)
+                              for s in res[1:]]
+                mine = ofrontend.chunk(ofrontend.normalise(raw.astype(np.float64), norm), L, S)
+                assert len(mine) == len(ref_chunks), (len(mine), len(ref_chunks))
+                for a, b in zip(mine, ref_chunks):
+                    assert a.shape == b.shape and np.array_equal(a, b), "front end differs"
+                key = "r%d_%s_%d_%d" % (ri, norm, L, S)
+                flat = np.concatenate(ref_chunks).astype(np.float32)
+                store[key + "_lens"] = np.array([len(c) for c in ref_chunks], dtype=np.int64)
+                store[key + "_flat"] = flat if flat.size < 6000 else flat[::7].copy()
+                store[key + "_sum"] = np.float64(np.concatenate(ref_chunks).sum())
+        os.unlink(path)
+        store["raw_%d" % ri] = raw
+    print("frontend: %d reads x 2 normalisations x 2 strides identical to extract_fast5_raw" % len(reads))
+    if write:
+        os.makedirs(GOLDEN_DIR, exist_ok=True)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "frontend.npz"), n_reads=len(reads), **store)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", nargs="*", default=list(CASES))
+    ap.add_argument("--no-write", action="store_true")
+    ap.add_argument("--B", type=int, default=6)
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    make_frontend_golden(write=not args.no_write)
+    for name in args.cases:
+        B = args.B if "d512" not in name else 3
+        make_case(name, B=B, write=not args.no_write)
+
+
+if __name__ == "__main__":
+    main()
