@@ -38,6 +38,11 @@ extern "C" {
 #endif
 
 #define ND_API_VERSION 1
+#if defined(__GNUC__)
+#define ND_EXPORT __attribute__((visibility("default")))
+#else
+#define ND_EXPORT
+#endif
 
 typedef enum {
   ND_OK = 0,
@@ -87,16 +92,16 @@ typedef struct nd_config {
 typedef struct nd_engine nd_engine;
 
 /* lifecycle --------------------------------------------------------------------------------- */
-int nd_create(const nd_config* cfg, nd_engine** out);
-int nd_destroy(nd_engine* e);
-const char* nd_last_error(const nd_engine* e);   /* e may be NULL: last create error */
-int nd_api_version(void);
+ND_EXPORT int nd_create(const nd_config* cfg, nd_engine** out);
+ND_EXPORT int nd_destroy(nd_engine* e);
+ND_EXPORT const char* nd_last_error(const nd_engine* e);   /* e may be NULL: last create error */
+ND_EXPORT int nd_api_version(void);
 
 /* weights: `name` is the checkpoint key ("encoder.rnn_0.weight_ih_l0", "generator.0.bias", ...);
  * `data` may be a host or device pointer (copied synchronously). */
-int nd_load_weight(nd_engine* e, const char* name, const void* data, const int64_t* shape,
+ND_EXPORT int nd_load_weight(nd_engine* e, const char* name, const void* data, const int64_t* shape,
                    int32_t ndim, int32_t dtype);
-int nd_finalize_weights(nd_engine* e);           /* checks completeness, packs kernel layouts */
+ND_EXPORT int nd_finalize_weights(nd_engine* e);           /* checks completeness, packs kernel layouts */
 
 /* signal front end ---------------------------------------------------------------------------
  * signal:       int16 raw samples of n_reads reads, concatenated (device)
@@ -106,21 +111,21 @@ int nd_finalize_weights(nd_engine* e);           /* checks completeness, packs k
  *   chunk_read/chunk_start: [n_chunks] which read / first sample of each chunk (device; the chunk
  *   table is built by the host mirror from read lengths exactly as utils/labelop.py:225-233)
  *   out_chunks: [n_chunks, chunk_len] fp32 zero padded; out_lengths: [n_chunks] int64            */
-int nd_frontend_stats(nd_engine* e, const int16_t* signal, const int64_t* read_offsets,
+ND_EXPORT int nd_frontend_stats(nd_engine* e, const int16_t* signal, const int64_t* read_offsets,
                       int32_t n_reads, int32_t normalization, double* out_center,
                       double* out_scale, void* stream);
-int nd_frontend_chunks(nd_engine* e, const int16_t* signal, const int64_t* read_offsets,
+ND_EXPORT int nd_frontend_chunks(nd_engine* e, const int16_t* signal, const int64_t* read_offsets,
                        const double* center, const double* scale, const int32_t* chunk_read,
                        const int64_t* chunk_start, int32_t n_chunks, int32_t chunk_len,
                        float* out_chunks, int64_t* out_lengths, void* stream);
 
 /* encoder ------------------------------------------------------------------------------------
  * src: [B, T] fp32 chunk-major zero padded; lengths: [B] int64 (device).                       */
-int nd_encode(nd_engine* e, const float* src, const int64_t* lengths, int32_t B, int32_t T,
+ND_EXPORT int nd_encode(nd_engine* e, const float* src, const int64_t* lengths, int32_t B, int32_t T,
               void* stream);
 /* copy out the memory bank of the last nd_encode as [T', B, d] (reference layout; for the CNN
  * encoder [d, B, T]) and its lengths [B]; T' is returned through out_Tp.  For parity tests.      */
-int nd_get_memory_bank(nd_engine* e, float* out, int64_t* out_lengths, int32_t* out_Tp,
+ND_EXPORT int nd_get_memory_bank(nd_engine* e, float* out, int64_t* out_lengths, int32_t* out_Tp,
                        void* stream);
 
 /* decode -------------------------------------------------------------------------------------
@@ -129,23 +134,23 @@ int nd_get_memory_bank(nd_engine* e, float* out, int64_t* out_lengths, int32_t* 
  *   out_scores [B] fp32: log-prob of the LAST step's token (translator.py:494)
  *   out_attn   NULL or [max_len, B, T'] fp32 (head-0 cross attention of the last layer)
  *   out_logits NULL or [max_len, B, V] fp32 log-probs of every step (parity tests)               */
-int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* out_ids,
+ND_EXPORT int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* out_ids,
                      float* out_scores, float* out_attn, float* out_logits, void* stream);
 /* Fast batched beam search (--fast).
  *   out_ids     [B, n_best, max_len] int64, padded with -1 after each hypothesis' last token
  *   out_lens    [B, n_best] int32 hypothesis lengths (including the final </s> if emitted)
  *   out_scores  [B, n_best] fp32                                                                 */
-int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len,
+ND_EXPORT int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len,
                    int32_t min_len, float alpha, int64_t* out_ids, int32_t* out_lens,
                    float* out_scores, void* stream);
 
 /* bookkeeping for bench.py: kernels launched by this engine since creation / last reset.        */
-int64_t nd_launch_count(const nd_engine* e);
-int nd_reset_launch_count(nd_engine* e);
+ND_EXPORT int64_t nd_launch_count(const nd_engine* e);
+ND_EXPORT int nd_reset_launch_count(nd_engine* e);
 
 /* standalone kernel entry points (unit tests / microbenchmarks) -------------------------------
  * C[M,N] = act(LN?(A)[M,K] . W[N,K]^T + bias) (+ residual); row-major fp32 device pointers.      */
-int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, const float* bias,
+ND_EXPORT int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, const float* bias,
                  const float* residual, const float* ln_gamma, const float* ln_beta, float* C,
                  int32_t M, int32_t N, int32_t K, int32_t relu, void* stream);
 

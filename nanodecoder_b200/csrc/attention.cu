@@ -1,0 +1,483 @@
+// Memory-bound attention kernels of the decode loop and the encoder self-attention (fp32).
+#include <float.h>
+
+#include "kernels.cuh"
+
+namespace nd {
+
+namespace {
+
+constexpr int kAttnThreads = 256;
+constexpr int kAttnWarps = kAttnThreads / 32;
+
+template <int VPL>
+__device__ __forceinline__ void load_slice(const float* p, float (&v)[VPL]) {
+  if constexpr (VPL % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < VPL; i += 4) {
+      const float4 t = ldg_stream4(p + i);
+      v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+  } else if constexpr (VPL % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < VPL; i += 2) {
+      const float2 t = ldg_stream2(p + i);
+      v[i] = t.x; v[i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) v[i] = __ldg(p + i);
+  }
+}
+
+// =============================================================================================
+// Cross attention, one CTA per chunk.  d = 32*VPL; lane l owns columns [l*VPL, (l+1)*VPL) of every
+// K / V row, so one warp reads one full row (coalesced 128-bit loads) and the 32/H lanes that share
+// a head reduce their partial dot products with xor-shuffles.
+//   phase 1: scores[q][h][t] = q_h . K[t]_h  (masked keys -> -1e18)     -> shared memory
+//   phase 2: softmax over t per (q, h)                                   (warp per row)
+//   phase 3: ctx[q] = sum_t p[q][h][t] * V[t]                            (register accumulators)
+// K and V are each read exactly once per chunk per step: 2*T*d*4 bytes — the roofline of the decode.
+template <int VPL, int NQMAX>
+__global__ void __launch_bounds__(kAttnThreads) cross_attn_kernel(CrossAttnParams p) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int chunk = blockIdx.x;
+  if (p.retired && p.retired[chunk]) return;
+  const int d = 32 * VPL, T = p.T, H = p.H, NQ = p.NQ;
+  const int TS = T + 1;                           // odd stride: the H score rows of a query hit distinct banks
+  const int LPH = 32 / H;                         // lanes per head
+  float* q_s = smem_f;                            // [NQ][d]
+  float* sc = q_s + NQ * d;                       // [NQ*H][TS]   (later reused as red[warps][NQ*d])
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < NQ * d; i += kAttnThreads) {
+    const int qi = i / d, c = i - qi * d;
+    q_s[i] = p.q[((int64_t)chunk * NQ + qi) * p.q_ld + c];
+  }
+  __syncthreads();
+
+  const float* Kb = p.K + (int64_t)chunk * T * p.kv_ld + lane * VPL;
+  const float* Vb = p.V + (int64_t)chunk * T * p.kv_ld + lane * VPL;
+  const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
+  const int head = lane / LPH;
+
+  // ---------------- phase 1
+  for (int t0 = warp * 4; t0 < T; t0 += kAttnWarps * 4) {
+    float kv[4][VPL];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (t0 + r < T) load_slice<VPL>(Kb + (int64_t)(t0 + r) * p.kv_ld, kv[r]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int t = t0 + r;
+      if (t < T) {                                 // warp-uniform
+        const bool masked = srow && (srow[t] == p.mask_value);
+#pragma unroll
+        for (int qi = 0; qi < NQMAX; ++qi) {
+          if (qi < NQ) {
+            const float* qq = q_s + qi * d + lane * VPL;
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) s = fmaf(qq[i], kv[r][i], s);
+            for (int o = LPH >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(ND_FULL, s, o);
+            if ((lane % LPH) == 0) sc[(qi * H + head) * TS + t] = masked ? -1e18f : s;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: softmax rows (torch.softmax: exp(x - max) / sum)
+  for (int row = warp; row < NQ * H; row += kAttnWarps) {
+    float* s = sc + row * TS;
+    float m = -FLT_MAX;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, s[t]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) { const float e = expf(s[t] - m); s[t] = e; sum += e; }
+    sum = warp_sum(sum);
+    for (int t = lane; t < T; t += 32) s[t] = s[t] / sum;
+    if (p.attn && (row % H) == 0) {
+      float* a = p.attn + ((int64_t)chunk * NQ + row / H) * T;
+      for (int t = lane; t < T; t += 32) a[t] = s[t];
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3
+  float acc[NQMAX][VPL];
+#pragma unroll
+  for (int qi = 0; qi < NQMAX; ++qi)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[qi][i] = 0.f;
+  for (int t0 = warp * 4; t0 < T; t0 += kAttnWarps * 4) {
+    float vv[4][VPL];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (t0 + r < T) load_slice<VPL>(Vb + (int64_t)(t0 + r) * p.kv_ld, vv[r]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int t = t0 + r;
+      if (t < T) {
+#pragma unroll
+        for (int qi = 0; qi < NQMAX; ++qi) {
+          if (qi < NQ) {
+            const float pr = sc[(qi * H + head) * TS + t];
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) acc[qi][i] = fmaf(pr, vv[r][i], acc[qi][i]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();                                 // scores no longer needed: reuse as reduction buffer
+  float* red = sc;                                 // [warps][NQ*d]
+#pragma unroll
+  for (int qi = 0; qi < NQMAX; ++qi) {
+    if (qi < NQ) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) red[(warp * NQ + qi) * d + lane * VPL + i] = acc[qi][i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * d; i += kAttnThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) s += red[w * NQ * d + i];
+    const int qi = i / d, c = i - qi * d;
+    p.ctx[((int64_t)chunk * NQ + qi) * p.ctx_ld + c] = s;
+  }
+}
+
+template <int VPL>
+cudaError_t launch_cross(const CrossAttnParams& p, cudaStream_t stream) {
+  const int d = 32 * VPL;
+  const size_t sc_f = (size_t)p.NQ * p.H * (p.T + 1);
+  const size_t red_f = (size_t)kAttnWarps * p.NQ * d;
+  const size_t smem = ((size_t)p.NQ * d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
+  if (p.NQ == 1) {
+    cudaFuncSetAttribute(cross_attn_kernel<VPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cross_attn_kernel<VPL, 1><<<p.n_chunks, kAttnThreads, smem, stream>>>(p);
+  } else {
+    cudaFuncSetAttribute(cross_attn_kernel<VPL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cross_attn_kernel<VPL, 8><<<p.n_chunks, kAttnThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream) {
+  if (p.n_chunks <= 0) return cudaSuccess;
+  if (p.d % 32 || 32 % p.H || p.NQ > 8 || p.NQ < 1 || (p.d / p.H) % (p.d / 32)) return cudaErrorInvalidValue;
+  switch (p.d / 32) {
+    case 1: return launch_cross<1>(p, stream);
+    case 2: return launch_cross<2>(p, stream);
+    case 4: return launch_cross<4>(p, stream);
+    case 8: return launch_cross<8>(p, stream);
+    case 16: return launch_cross<16>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// =============================================================================================
+// Decode-step self attention.  One CTA per row, one warp per head (looping when H > warps).
+namespace {
+
+__global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int row = blockIdx.x;
+  if (p.retired && p.retired[row / p.rows_per_chunk]) return;
+  const int d = p.d, H = p.H, dh = d / H, L = p.step + 1;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q_s = smem_f;                             // [d]
+  float* p_s = smem_f + d;                         // [nwarps][Lmax]
+  const float* qkv = p.qkv + (int64_t)row * 3 * d;
+  // append this step's k, v to the cache (own slot = row) and stage q
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    q_s[i] = qkv[i];
+    p.Kc[((int64_t)row * p.Lmax + p.step) * d + i] = qkv[d + i];
+    p.Vc[((int64_t)row * p.Lmax + p.step) * d + i] = qkv[2 * d + i];
+  }
+  __syncthreads();
+  const int* anc = p.anc ? p.anc + (int64_t)row * p.anc_ld : nullptr;
+  for (int h = warp; h < H; h += nwarps) {
+    float* ps = p_s + warp * p.Lmax;
+    const float* qh = q_s + h * dh;
+    // scores: lane <-> position
+    float m = -FLT_MAX;
+    for (int j = lane; j < L; j += 32) {
+      const float* kr;
+      if (j == p.step) kr = qkv + d + h * dh;      // current position straight from the projection
+      else kr = p.Kc + ((int64_t)(anc ? anc[j] : row) * p.Lmax + j) * d + h * dh;
+      float s = 0.f;
+      for (int e = 0; e < dh; ++e) s = fmaf(qh[e], kr[e], s);
+      ps[j] = s;
+      m = fmaxf(m, s);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) { const float e = expf(ps[j] - m); ps[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    for (int j = lane; j < L; j += 32) ps[j] = ps[j] / sum;
+    __syncwarp();
+    // context: lane <-> feature
+    for (int e = lane; e < dh; e += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < L; ++j) {
+        const float* vr;
+        if (j == p.step) vr = qkv + 2 * d + h * dh;
+        else vr = p.Vc + ((int64_t)(anc ? anc[j] : row) * p.Lmax + j) * d + h * dh;
+        acc = fmaf(ps[j], vr[e], acc);
+      }
+      p.ctx[(int64_t)row * d + h * dh + e] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream) {
+  if (p.rows <= 0) return cudaSuccess;
+  const int nw = p.H < 8 ? p.H : 8;
+  const size_t smem = ((size_t)p.d + (size_t)nw * p.Lmax) * sizeof(float);
+  self_attn_kernel<<<p.rows, nw * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// Encoder self attention (flash style, fp32 FFMA): CTA = (chunk, head, 128 queries); thread = query.
+// K/V tiles of 64 keys are staged in shared memory and broadcast-read; online softmax per 8 keys.
+namespace {
+
+template <int DH>
+__global__ void __launch_bounds__(128) enc_attn_kernel(EncAttnParams p) {
+  constexpr int KT = 64;
+  __shared__ __align__(16) float Ks[KT][DH];
+  __shared__ __align__(16) float Vs[KT][DH];
+  __shared__ float Ms[KT];
+  const int T = p.T, d = p.d;
+  const int qtiles = (T + 127) / 128;
+  const int qt = blockIdx.x % qtiles;
+  const int h = (blockIdx.x / qtiles) % p.H;
+  const int b = blockIdx.x / (qtiles * p.H);
+  const int tq = qt * 128 + threadIdx.x;
+  const bool qok = tq < T;
+  const float* base = p.qkv + (int64_t)b * T * 3 * d;
+
+  float q[DH], o[DH];
+#pragma unroll
+  for (int e = 0; e < DH; ++e) { q[e] = qok ? base[(int64_t)tq * 3 * d + h * DH + e] : 0.f; o[e] = 0.f; }
+  float m = -FLT_MAX, l = 0.f;
+
+  for (int k0 = 0; k0 < T; k0 += KT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KT * DH; i += 128) {
+      const int j = i / DH, e = i - j * DH;
+      const int t = k0 + j;
+      Ks[j][e] = t < T ? base[(int64_t)t * 3 * d + d + h * DH + e] : 0.f;
+      Vs[j][e] = t < T ? base[(int64_t)t * 3 * d + 2 * d + h * DH + e] : 0.f;
+    }
+    for (int j = threadIdx.x; j < KT; j += 128) {
+      const int t = k0 + j;
+      // 0: valid key, 1: masked (src == 0.0), 2: beyond T (does not exist)
+      Ms[j] = t < T ? (p.src[(int64_t)b * T + t] == 0.0f ? 1.f : 0.f) : 2.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j0 = 0; j0 < KT; j0 += 8) {
+      float s[8];
+      float mt = m;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < DH; ++e) a = fmaf(q[e], Ks[j0 + jj][e], a);
+        const float flag = Ms[j0 + jj];
+        a = flag == 1.f ? -1e18f : a;              // masked_fill(mask, -1e18)
+        s[jj] = a;
+        if (flag != 2.f) mt = fmaxf(mt, a);
+      }
+      const float corr = expf(m - mt);             // m == -FLT_MAX on the first block -> 0
+      l *= corr;
+#pragma unroll
+      for (int e = 0; e < DH; ++e) o[e] *= corr;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (Ms[j0 + jj] == 2.f) continue;
+        const float pj = expf(s[jj] - mt);
+        l += pj;
+#pragma unroll
+        for (int e = 0; e < DH; ++e) o[e] = fmaf(pj, Vs[j0 + jj][e], o[e]);
+      }
+      m = mt;
+    }
+  }
+  if (qok) {
+    float* out = p.ctx + ((int64_t)b * T + tq) * d + h * DH;
+#pragma unroll
+    for (int e = 0; e < DH; ++e) out[e] = o[e] / l;
+  }
+}
+
+}  // namespace
+
+cudaError_t encoder_attention(const EncAttnParams& p, cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  const int dh = p.d / p.H;
+  const int64_t grid = (int64_t)p.B * p.H * ((p.T + 127) / 128);
+  switch (dh) {
+    case 8: enc_attn_kernel<8><<<(unsigned)grid, 128, 0, stream>>>(p); break;
+    case 16: enc_attn_kernel<16><<<(unsigned)grid, 128, 0, stream>>>(p); break;
+    case 32: enc_attn_kernel<32><<<(unsigned)grid, 128, 0, stream>>>(p); break;
+    case 64: enc_attn_kernel<64><<<(unsigned)grid, 128, 0, stream>>>(p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// mlp (Bahdanau) / dot global attention, one CTA per chunk; same three phases as cross_attn_kernel
+// with a single "head": score[t] = sum_c v[c] * tanh(wq[c] + uh[t][c])   (or q . mem[t]).
+namespace {
+
+template <int VPL, int NQMAX>
+__global__ void __launch_bounds__(kAttnThreads) mlp_attn_kernel(MlpAttnParams p) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int chunk = blockIdx.x;
+  if (p.retired && p.retired[chunk]) return;
+  const int d = 32 * VPL, T = p.T, NQ = p.NQ;
+  float* q_s = smem_f;                            // [NQ][d]
+  float* v_s = q_s + NQ * d;                      // [d]
+  float* sc = v_s + d;                            // [NQ][T]  (later red[warps][NQ*d])
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NQ * d; i += kAttnThreads)
+    q_s[i] = p.wq[((int64_t)chunk * NQ + i / d) * d + (i % d)];
+  for (int i = threadIdx.x; i < d; i += kAttnThreads) v_s[i] = p.dot ? 0.f : p.v[i];
+  __syncthreads();
+  const int len = p.lengths ? (int)p.lengths[chunk] : T;
+  const float* Ub = p.uh + (int64_t)chunk * T * d + lane * VPL;    // dot mode: uh = key matrix
+  const float* Mb = p.mem + (int64_t)chunk * T * d + lane * VPL;
+
+  for (int t0 = warp * 4; t0 < T; t0 += kAttnWarps * 4) {
+    float u[4][VPL];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (t0 + r < T) load_slice<VPL>(Ub + (int64_t)(t0 + r) * d, u[r]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int t = t0 + r;
+      if (t < T) {
+#pragma unroll
+        for (int qi = 0; qi < NQMAX; ++qi) {
+          if (qi < NQ) {
+            const float* qq = q_s + qi * d + lane * VPL;
+            float s = 0.f;
+            if (p.dot) {
+#pragma unroll
+              for (int i = 0; i < VPL; ++i) s = fmaf(qq[i], u[r][i], s);
+            } else {
+#pragma unroll
+              for (int i = 0; i < VPL; ++i) s = fmaf(v_s[lane * VPL + i], tanhf(qq[i] + u[r][i]), s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) sc[qi * T + t] = (t < len) ? s : -INFINITY;     // sequence_mask, -inf
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int row = warp; row < NQ; row += kAttnWarps) {
+    float* s = sc + row * T;
+    float m = -FLT_MAX;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, s[t]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) { const float e = expf(s[t] - m); s[t] = e; sum += e; }
+    sum = warp_sum(sum);
+    for (int t = lane; t < T; t += 32) s[t] = s[t] / sum;
+    if (p.attn) {
+      float* a = p.attn + ((int64_t)chunk * NQ + row) * T;
+      for (int t = lane; t < T; t += 32) a[t] = s[t];
+    }
+  }
+  __syncthreads();
+  float acc[NQMAX][VPL];
+#pragma unroll
+  for (int qi = 0; qi < NQMAX; ++qi)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[qi][i] = 0.f;
+  const int tmax = len < T ? len : T;             // weights beyond the length are exactly 0
+  for (int t0 = warp * 4; t0 < tmax; t0 += kAttnWarps * 4) {
+    float vv[4][VPL];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (t0 + r < tmax) load_slice<VPL>(Mb + (int64_t)(t0 + r) * d, vv[r]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int t = t0 + r;
+      if (t < tmax) {
+#pragma unroll
+        for (int qi = 0; qi < NQMAX; ++qi) {
+          if (qi < NQ) {
+            const float pr = sc[qi * T + t];
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) acc[qi][i] = fmaf(pr, vv[r][i], acc[qi][i]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* red = sc;
+#pragma unroll
+  for (int qi = 0; qi < NQMAX; ++qi) {
+    if (qi < NQ) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) red[(warp * NQ + qi) * d + lane * VPL + i] = acc[qi][i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * d; i += kAttnThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) s += red[w * NQ * d + i];
+    p.ctx[((int64_t)chunk * NQ + i / d) * p.ctx_ld + (i % d)] = s;
+  }
+}
+
+template <int VPL>
+cudaError_t launch_mlp(const MlpAttnParams& p, cudaStream_t stream) {
+  const int d = 32 * VPL;
+  const size_t sc_f = (size_t)p.NQ * p.T;
+  const size_t red_f = (size_t)kAttnWarps * p.NQ * d;
+  const size_t smem = ((size_t)p.NQ * d + d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
+  if (p.NQ == 1) {
+    cudaFuncSetAttribute(mlp_attn_kernel<VPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mlp_attn_kernel<VPL, 1><<<p.n_chunks, kAttnThreads, smem, stream>>>(p);
+  } else {
+    cudaFuncSetAttribute(mlp_attn_kernel<VPL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mlp_attn_kernel<VPL, 8><<<p.n_chunks, kAttnThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t mlp_attention(const MlpAttnParams& p, cudaStream_t stream) {
+  if (p.n_chunks <= 0) return cudaSuccess;
+  if (p.d % 32 || p.NQ > 8 || p.NQ < 1) return cudaErrorInvalidValue;
+  switch (p.d / 32) {
+    case 1: return launch_mlp<1>(p, stream);
+    case 2: return launch_mlp<2>(p, stream);
+    case 4: return launch_mlp<4>(p, stream);
+    case 8: return launch_mlp<8>(p, stream);
+    case 16: return launch_mlp<16>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace nd

@@ -1,0 +1,195 @@
+// On-device batched beam search step (reference: translate/translator.py:619-825, `--fast`).
+// One warp per chunk; nothing round-trips to the host inside the decode loop.
+//
+// Differences in mechanism (not in results):
+//   * finished chunks are not compacted out of the batch; a `retired` flag makes every per-chunk
+//     kernel skip them (same saved work, no reallocation);
+//   * the memory bank / cross K,V are never tiled or reordered (beams of a chunk share them);
+//   * the self-attention cache is never reordered: `anc[row][j]` records which cache row holds
+//     position j of the hypothesis now living in `row` (parent pointers);
+//   * only the best `n_best` finished hypotheses are kept (stable in arrival order on equal scores),
+//     which is what the reference's final `sorted(..., reverse=True)[:n_best]` selects.
+#include <float.h>
+#include <math.h>
+
+#include "kernels.cuh"
+
+namespace nd {
+
+namespace {
+
+constexpr int kMaxCandPerLane = 4;     // K*V <= 128
+
+__global__ void beam_init_kernel(BeamParams p, int bos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = p.B * p.K;
+  if (i < rows) {
+    p.st.topk_log_probs[i] = (i % p.K == 0) ? 0.0f : -INFINITY;     // translator.py:691-693
+    p.st.cur_tok[i] = bos;
+    p.st.parent[i] = i;
+    p.st.alive_seq[(int64_t)i * (p.Lmax + 1)] = bos;
+  }
+  if (i < p.B) {
+    p.st.retired[i] = 0;
+    p.st.top_finished[i] = 0;
+    p.st.n_hyp[i] = 0;
+    for (int n = 0; n < p.n_best; ++n) {
+      p.st.hyp_score[i * p.n_best + n] = -INFINITY;
+      p.st.hyp_len[i * p.n_best + n] = 0;
+    }
+  }
+  if (i == 0) *p.st.n_alive = p.B;
+}
+
+__global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float length_penalty) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= p.B) return;
+  if (p.st.retired[b]) return;
+  const int K = p.K, V = p.V, NC = K * V, Lp1 = p.Lmax + 1;
+  const int cur = p.step & 1, nxt = cur ^ 1;
+  const int rows = p.B * K;
+  const int* seq_cur = p.st.alive_seq + (int64_t)cur * rows * Lp1;
+  int* seq_nxt = p.st.alive_seq + (int64_t)nxt * rows * Lp1;
+  const int* anc_cur = p.st.anc + (int64_t)cur * rows * p.Lmax;
+  int* anc_nxt = p.st.anc + (int64_t)nxt * rows * p.Lmax;
+
+  // candidate scores: (log_probs + beam score) / length_penalty            translator.py:718-725
+  float cand[kMaxCandPerLane];
+  unsigned used = 0;
+#pragma unroll
+  for (int i = 0; i < kMaxCandPerLane; ++i) {
+    const int c = lane + 32 * i;
+    cand[i] = -INFINITY;
+    if (c < NC) {
+      const int k = c / V;
+      cand[i] = (p.logp[((int64_t)b * K + k) * V + (c - k * V)] + p.st.topk_log_probs[b * K + k]) / length_penalty;
+    } else {
+      used |= 1u << i;
+    }
+  }
+  // top-K: K rounds of warp arg-max, ties -> lowest flat index
+  float sel_score = 0.f;
+  int sel_idx = 0;                                     // lane k keeps the k-th selection
+  for (int k = 0; k < K; ++k) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kMaxCandPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (!(used & (1u << i)) && (bi == 0x7fffffff || cand[i] > bv)) { bv = cand[i]; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(ND_FULL, bv, o);
+      const int oi = __shfl_xor_sync(ND_FULL, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((bi & 31) == lane) used |= 1u << (bi >> 5);
+    if (lane == k) { sel_score = bv; sel_idx = bi; }
+  }
+  // lane k (< K) now owns new beam k
+  const bool mine = lane < K;
+  const int beam = mine ? sel_idx / V : 0;
+  const int tok = mine ? sel_idx - beam * V : 0;
+  const int prow = b * K + beam;                       // parent row (global)
+  const int nrow = b * K + lane;
+  bool finished = mine && (tok == p.eos || p.step + 1 == p.max_len);           // :753-755
+  float new_lp = sel_score * length_penalty;           // :729
+  const unsigned fin_mask = __ballot_sync(ND_FULL, finished);
+
+  // new alive sequences / ancestor tables (warp-cooperative row copies)
+  for (int k = 0; k < K; ++k) {
+    const int pr = __shfl_sync(ND_FULL, prow, k);
+    const int tk = __shfl_sync(ND_FULL, tok, k);
+    const int nr = b * K + k;
+    for (int j = lane; j <= p.step; j += 32) seq_nxt[(int64_t)nr * Lp1 + j] = seq_cur[(int64_t)pr * Lp1 + j];
+    for (int j = lane; j < p.step; j += 32) anc_nxt[(int64_t)nr * p.Lmax + j] = anc_cur[(int64_t)pr * p.Lmax + j];
+    if (lane == 0) {
+      seq_nxt[(int64_t)nr * Lp1 + p.step + 1] = tk;
+      anc_nxt[(int64_t)nr * p.Lmax + p.step] = pr;
+    }
+  }
+  __syncwarp();
+
+  if (fin_mask) {
+    if (finished) new_lp = -1e10f;                     // :760
+    int top_fin = p.st.top_finished[b] | ((fin_mask & 1u) ? 1 : 0);            // :762
+    int n_hyp = p.st.n_hyp[b];
+    const int nb = p.n_best;
+    float* hs = p.st.hyp_score + (int64_t)b * nb;
+    int* hl = p.st.hyp_len + (int64_t)b * nb;
+    int* hq = p.st.hyp_seq + (int64_t)b * nb * p.Lmax;
+    const int len = p.step + 1;
+    for (int k = 0; k < K; ++k) {                      // finished beams in beam order (:773-778)
+      if (!(fin_mask & (1u << k))) continue;
+      const float sc = __shfl_sync(ND_FULL, sel_score, k);
+      ++n_hyp;
+      // stable insertion into the best-n_best list (descending score, earlier first on ties)
+      int pos = nb;
+      for (int i = 0; i < nb; ++i) {
+        const float cur_s = hs[i];
+        const bool empty = hl[i] == 0;
+        if (empty || sc > cur_s) { pos = i; break; }
+      }
+      __syncwarp();
+      if (pos < nb) {
+        for (int i = nb - 1; i > pos; --i) {
+          for (int j = lane; j < p.Lmax; j += 32) hq[i * p.Lmax + j] = hq[(i - 1) * p.Lmax + j];
+          __syncwarp();
+          if (lane == 0) { hs[i] = hs[i - 1]; hl[i] = hl[i - 1]; }
+          __syncwarp();
+        }
+        const int nr = b * K + k;
+        for (int j = lane; j < len; j += 32) hq[pos * p.Lmax + j] = seq_nxt[(int64_t)nr * Lp1 + 1 + j];
+        if (lane == 0) { hs[pos] = sc; hl[pos] = len; }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      p.st.top_finished[b] = top_fin;
+      p.st.n_hyp[b] = n_hyp;
+      if (top_fin && n_hyp >= nb) {                    // :781
+        p.st.retired[b] = 1;
+        atomicSub(p.st.n_alive, 1);
+      }
+    }
+  }
+  if (mine) {
+    p.st.topk_log_probs[nrow] = new_lp;
+    p.st.cur_tok[nrow] = tok;
+    p.st.parent[nrow] = prow;
+  }
+}
+
+__global__ void beam_finalize_kernel(BeamParams p, int64_t* out_ids, int* out_lens, float* out_scores) {
+  const int i = blockIdx.x;                            // (b, n)
+  const int len = p.st.hyp_len[i];
+  if (threadIdx.x == 0) { out_lens[i] = len; out_scores[i] = p.st.hyp_score[i]; }
+  for (int j = threadIdx.x; j < p.max_len; j += blockDim.x)
+    out_ids[(int64_t)i * p.max_len + j] = j < len ? (int64_t)p.st.hyp_seq[(int64_t)i * p.Lmax + j] : -1;
+}
+
+}  // namespace
+
+cudaError_t beam_init(const BeamParams& p, int bos, cudaStream_t stream) {
+  const int n = p.B * p.K;
+  beam_init_kernel<<<cdiv(n, 256), 256, 0, stream>>>(p, bos);
+  return cudaGetLastError();
+}
+
+cudaError_t beam_step(const BeamParams& p, cudaStream_t stream) {
+  if (p.K * p.V > 32 * kMaxCandPerLane || p.K > 32) return cudaErrorInvalidValue;
+  // ((5 + step + 1) / 6) ** alpha in double like the Python expression (translator.py:720-721)
+  const double lp = pow((5.0 + (double)(p.step + 1)) / 6.0, (double)p.alpha);
+  beam_step_kernel<<<cdiv(p.B, 4), 128, 0, stream>>>(p, (float)lp);
+  return cudaGetLastError();
+}
+
+cudaError_t beam_finalize(const BeamParams& p, int64_t* out_ids, int* out_lens, float* out_scores,
+                          cudaStream_t stream) {
+  beam_finalize_kernel<<<p.B * p.n_best, 128, 0, stream>>>(p, out_ids, out_lens, out_scores);
+  return cudaGetLastError();
+}
+
+}  // namespace nd

@@ -1,0 +1,265 @@
+// Small memory-bound kernels: normalisation, embedding, layout changes, generator + token selection.
+#include <float.h>
+#include <math.h>
+
+#include "kernels.cuh"
+
+namespace nd {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                 const float* __restrict__ b, float eps, float* __restrict__ y,
+                                 int64_t M, int d) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int k = lane; k < d; k += 32) s += xr[k];
+  const float mean = warp_sum(s) / (float)d;
+  float v = 0.f;
+  for (int k = lane; k < d; k += 32) { const float t = xr[k] - mean; v += t * t; }
+  const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)d + eps);
+  float* yr = y + row * d;
+  for (int k = lane; k < d; k += 32) yr[k] = (xr[k] - mean) * rstd * g[k] + b[k];
+}
+
+__global__ void embed_kernel(const int* __restrict__ tok, const float* __restrict__ emb, float* __restrict__ x,
+                             int64_t x_ld, int rows, int d, int pos_enc, int step) {
+  const int row = blockIdx.x;
+  const int t = tok[row];
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float v = emb[(int64_t)t * d + c];
+    if (pos_enc) {
+      // onmt/modules/embeddings.py:24-29,36-41: emb*sqrt(d) + pe[step]
+      const int i2 = c & ~1;
+      const float div = expf((float)i2 * -(logf(10000.0f) / (float)d));
+      const float ang = (float)step * div;
+      v = v * sqrtf((float)d) + ((c & 1) ? cosf(ang) : sinf(ang));
+    }
+    x[(int64_t)row * x_ld + c] = v;
+  }
+}
+
+__global__ void linear_in1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                  const float* __restrict__ bias, float* __restrict__ y, int64_t n, int d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * d) return;
+  const int64_t r = i / d;
+  const int c = (int)(i - r * d);
+  y[i] = x[r] * w[c] + bias[c];
+}
+
+__global__ void maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int d,
+                               int stride) {
+  const int Tp = T / stride;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * Tp * d) return;
+  const int c = (int)(i % d);
+  const int tp = (int)((i / d) % Tp);
+  const int b = (int)(i / ((int64_t)d * Tp));
+  float m = -FLT_MAX;
+  for (int j = 0; j < stride; ++j) m = fmaxf(m, in[((int64_t)b * T + tp * stride + j) * d + c]);
+  out[i] = m;
+}
+
+__global__ void transpose_bt_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int d) {
+  // one CTA per (b, t) row of d floats
+  const int64_t r = blockIdx.x;
+  const int b = (int)(r / T), t = (int)(r % T);
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    out[((int64_t)t * B + b) * d + c] = in[r * d + c];
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                   const int* __restrict__ parent, int rows, int width) {
+  const int r = blockIdx.x;
+  const int s = parent[r];
+  for (int c = threadIdx.x; c < width; c += blockDim.x) dst[(int64_t)r * width + c] = src[(int64_t)s * width + c];
+}
+
+__global__ void lstm_cell_kernel(const float* __restrict__ ga, const float* __restrict__ gb,
+                                 const float* __restrict__ c_in, float* __restrict__ h_out,
+                                 float* __restrict__ c_out, int rows, int d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * d) return;
+  const int64_t r = i / d;
+  const int c = (int)(i - r * d);
+  const float* a = ga + r * 4 * d;
+  const float* b = gb + r * 4 * d;
+  const float ig = sigmoid_acc(a[c] + b[c]);
+  const float fg = sigmoid_acc(a[d + c] + b[d + c]);
+  const float gg = tanhf(a[2 * d + c] + b[2 * d + c]);
+  const float og = sigmoid_acc(a[3 * d + c] + b[3 * d + c]);
+  const float cy = fg * c_in[i] + ig * gg;
+  c_out[i] = cy;
+  h_out[i] = og * tanhf(cy);
+}
+
+__global__ void fill_int_kernel(int* p, int n, int value) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = value;
+}
+
+__global__ void glu_residual_kernel(const float* __restrict__ y, const float* __restrict__ x,
+                                    float* __restrict__ out, float* __restrict__ glu_out, int64_t rows, int d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * d) return;
+  const int64_t r = i / d;
+  const int c = (int)(i - r * d);
+  const float a = y[r * 2 * d + c], g = y[r * 2 * d + d + c];
+  const float glu = a * sigmoid_acc(g);
+  if (glu_out) glu_out[i] = glu;
+  if (out) out[i] = (x[i] + glu) * 0.70710678118654757f;   // SCALE_WEIGHT = 0.5 ** 0.5 rounded to fp32
+}
+
+__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ A, int B, int T, int d, int k,
+                              int left) {
+  const int64_t r = blockIdx.x;                    // (b, t)
+  const int b = (int)(r / T), t = (int)(r % T);
+  for (int i = threadIdx.x; i < k * d; i += blockDim.x) {
+    const int j = i / d, c = i - j * d;
+    const int ts = t + j - left;
+    A[r * k * d + i] = (ts >= 0 && ts < T) ? x[((int64_t)b * T + ts) * d + c] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generator: one warp per row.  VMAX bounds the vocabulary (4 specials + bases <= 16).
+template <int VMAX>
+__global__ void __launch_bounds__(128) generator_kernel(GenParams p) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.rows) return;
+  const float* xr = p.x + (int64_t)row * p.x_ld;
+  const int d = p.d, V = p.V;
+  float mean = 0.f, rstd = 1.f;
+  if (p.ln_g) {
+    float s = 0.f;
+    for (int k = lane; k < d; k += 32) s += xr[k];
+    mean = warp_sum(s) / (float)d;
+    float v = 0.f;
+    for (int k = lane; k < d; k += 32) { const float t = xr[k] - mean; v += t * t; }
+    rstd = 1.0f / sqrtf(warp_sum(v) / (float)d + p.eps);
+  }
+  float acc[VMAX];
+#pragma unroll
+  for (int v = 0; v < VMAX; ++v) acc[v] = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    float xv = xr[k];
+    if (p.ln_g) xv = (xv - mean) * rstd * p.ln_g[k] + p.ln_b[k];
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v)
+      if (v < V) acc[v] = fmaf(xv, __ldg(p.Wg + (int64_t)v * d + k), acc[v]);
+  }
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int v = 0; v < VMAX; ++v) {
+    if (v < V) {
+      acc[v] = warp_sum(acc[v]) + p.bg[v];
+      mx = fmaxf(mx, acc[v]);
+    }
+  }
+  float se = 0.f;
+#pragma unroll
+  for (int v = 0; v < VMAX; ++v)
+    if (v < V) se += expf(acc[v] - mx);
+  const float lse = logf(se);
+  int best = 0;
+  float bestv = -FLT_MAX;
+#pragma unroll
+  for (int v = 0; v < VMAX; ++v) {
+    if (v < V) {
+      float lp = acc[v] - mx - lse;                 // log_softmax
+      if (lane == 0 && p.trace) p.trace[(int64_t)row * V + v] = lp;
+      if (v == p.eos && p.step < p.min_len) lp = -1e20f;      // translator.py:469-470 / 714-715
+      if (lane == 0) p.logp[(int64_t)row * V + v] = lp;
+      if (lp > bestv) { bestv = lp; best = v; }     // strict >: lowest index wins ties
+    }
+  }
+  if (lane == 0 && p.ids) {
+    p.ids[(int64_t)row * p.ids_ld + p.step] = best;
+    p.scores[row] = bestv;
+    p.next_tok[row] = best;
+  }
+}
+
+}  // namespace
+
+cudaError_t layernorm_rows(const float* x, const float* g, const float* b, float eps, float* y, int64_t M, int d,
+                           cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  layernorm_kernel<<<(unsigned)cdiv64(M, 8), 256, 0, stream>>>(x, g, b, eps, y, M, d);
+  return cudaGetLastError();
+}
+
+cudaError_t embed_rows(const int* tok, const float* emb, float* x, int64_t x_ld, int rows, int d, int pos_enc,
+                       int step, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  embed_kernel<<<rows, d < 256 ? d : 256, 0, stream>>>(tok, emb, x, x_ld, rows, d, pos_enc, step);
+  return cudaGetLastError();
+}
+
+cudaError_t linear_in1(const float* x, const float* w, const float* bias, float* y, int64_t n, int d,
+                       cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  linear_in1_kernel<<<(unsigned)cdiv64(n * d, 256), 256, 0, stream>>>(x, w, bias, y, n, d);
+  return cudaGetLastError();
+}
+
+cudaError_t maxpool_time(const float* in, float* out, int B, int T, int d, int stride, cudaStream_t stream) {
+  const int64_t n = (int64_t)B * (T / stride) * d;
+  if (n <= 0) return cudaSuccess;
+  maxpool_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, stream>>>(in, out, B, T, d, stride);
+  return cudaGetLastError();
+}
+
+cudaError_t transpose_bt(const float* in, float* out, int B, int T, int d, cudaStream_t stream) {
+  if ((int64_t)B * T <= 0) return cudaSuccess;
+  transpose_bt_kernel<<<(unsigned)((int64_t)B * T), d < 256 ? d : 256, 0, stream>>>(in, out, B, T, d);
+  return cudaGetLastError();
+}
+
+cudaError_t gather_rows(const float* src, float* dst, const int* parent, int rows, int width, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  gather_rows_kernel<<<rows, width < 256 ? width : 256, 0, stream>>>(src, dst, parent, rows, width);
+  return cudaGetLastError();
+}
+
+cudaError_t lstm_cell_pointwise(const float* gates_a, const float* gates_b, const float* c_in, float* h_out,
+                                float* c_out, int rows, int d, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  lstm_cell_kernel<<<(unsigned)cdiv64((int64_t)rows * d, 256), 256, 0, stream>>>(gates_a, gates_b, c_in, h_out, c_out,
+                                                                                rows, d);
+  return cudaGetLastError();
+}
+
+cudaError_t fill_int(int* p, int n, int value, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  fill_int_kernel<<<cdiv(n, 256), 256, 0, stream>>>(p, n, value);
+  return cudaGetLastError();
+}
+
+cudaError_t glu_residual(const float* y, const float* x, float* out, float* glu_out, int64_t rows, int d,
+                         cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  glu_residual_kernel<<<(unsigned)cdiv64(rows * d, 256), 256, 0, stream>>>(y, x, out, glu_out, rows, d);
+  return cudaGetLastError();
+}
+
+cudaError_t im2col_time(const float* x, float* A, int B, int T, int d, int k, int left, cudaStream_t stream) {
+  if ((int64_t)B * T <= 0) return cudaSuccess;
+  im2col_kernel<<<(unsigned)((int64_t)B * T), 256, 0, stream>>>(x, A, B, T, d, k, left);
+  return cudaGetLastError();
+}
+
+cudaError_t generator_step(const GenParams& p, cudaStream_t stream) {
+  if (p.rows <= 0) return cudaSuccess;
+  if (p.V > 16) return cudaErrorInvalidValue;
+  generator_kernel<16><<<cdiv(p.rows, 4), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace nd

@@ -1,0 +1,1039 @@
+// libnanodec engine: weight registry + packing, workspace, encoder / decoder orchestration and the
+// extern "C" ABI declared in include/nanodec.h.  All device work is enqueued on the caller's stream.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/nanodec.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include "lstm.cuh"
+
+using namespace nd;
+
+namespace {
+
+std::string g_create_error;
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> f;        // fp32 payload
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+// a dense projection y = x W^T + b in the layouts the GEMM kernels want
+struct Lin {
+  const float* W = nullptr;    // [N,K] fp32 (SIMT path)
+  const float* W_hi = nullptr; // tf32-exact high part (tcgen05 path)
+  const float* W_lo = nullptr; // residual
+  const float* b = nullptr;    // [N] or null
+  int N = 0, K = 0;
+  int64_t ld = 0;
+};
+
+struct LnW { const float* g = nullptr; const float* b = nullptr; };
+
+struct EncLayerT {             // transformer encoder layer
+  Lin qkv, out, w1, w2;
+  LnW ln, ln_ff;
+};
+struct DecLayerT {             // transformer decoder layer
+  Lin qkv, self_out, cq, ckv, ctx_out, w1, w2;
+  LnW ln1, ln2, ln_ff;
+};
+struct LstmW {                 // one bidirectional (or unidirectional) LSTM layer
+  Lin ih;                      // [dirs*4H, in] with b_ih (input projection GEMM), in > 1
+  const float* w_ih0 = nullptr;   // [dirs*4H] when in == 1
+  const float* b_ih0 = nullptr;
+  const float* w_hh = nullptr; // [dirs*4H, H]
+  const float* b_hh = nullptr; // [dirs*4H]
+  const float* bn_alpha = nullptr;   // eval BatchNorm of this layer's output folded to y = x*alpha + beta
+  const float* bn_beta = nullptr;
+  int in = 1;
+};
+struct ConvW { Lin conv; };    // weight-normalised (k x 1) conv as [2d, k*d] GEMM
+
+}  // namespace
+
+struct nd_engine {
+  nd_config cfg;
+  std::string err;
+  bool sticky = false;
+  int n_sm = 148;
+  int64_t launches = 0;
+  std::map<std::string, HostTensor> raw;
+  std::vector<void*> allocs;
+  bool finalized = false;
+  bool oom = false;
+
+  // ---- packed weights
+  std::vector<LstmW> lstm;           // nano / rnn / brnn encoders
+  Lin encW;                          // nano: final projection
+  Lin enc_lin_in;                    // transformer / cnn encoder Linear(1,d) (W used as vector)
+  std::vector<EncLayerT> encT;
+  LnW enc_ln;
+  std::vector<ConvW> enc_conv, dec_conv;
+  std::vector<DecLayerT> decT;
+  LnW dec_ln;
+  const float* emb = nullptr;        // [V,d]
+  Lin gen;                           // generator (W, b)
+  // rnn decoder
+  struct RnnCell { Lin ih_e, ih_f, ih, hh; };
+  std::vector<RnnCell> cells;
+  Lin attn_ctx, attn_q, attn_in, attn_out_c, attn_out_h;
+  const float* attn_v = nullptr;
+  // cnn decoder
+  Lin dec_lin;
+  std::vector<Lin> dec_attn_in;
+
+  // ---- workspace (sized at create)
+  float* src = nullptr;              // [maxB, maxT]
+  int64_t* lengths = nullptr;        // [maxB]
+  int64_t* mem_len = nullptr;        // [maxB]
+  std::vector<int64_t> h_lengths;    // host mirror of the last encode (pooling arithmetic is host side)
+  float* bufA = nullptr; float* bufB = nullptr;    // [maxB*maxT, d] activations ping-pong
+  float* bufC = nullptr;                            // [maxB*maxT, d]
+  float* big = nullptr;              // [maxB*maxT, max(4d, 3d, ff, k*d)] xg / qkv / ffn hidden / im2col
+  float* big2 = nullptr;             // [maxB*maxT, 2d] conv outputs
+  float* mb = nullptr;               // memory bank [B, T', d]
+  float* emb_remap = nullptr;        // cnn encoder: Linear(1,d) output (decoder init_state needs it)
+  float* enc_hn = nullptr; float* enc_cn = nullptr;   // rnn encoders: [Le*dirs, B, hh]
+  int B = 0, T = 0, Tp = 0;          // last encode
+  bool encoded = false;
+
+  // decoder workspace
+  std::vector<float*> ckv;           // per layer [B*T', 2d]
+  std::vector<float*> selfK, selfV;  // per layer [rows, L, d]
+  float *x = nullptr, *qkv = nullptr, *sctx = nullptr, *x1 = nullptr, *qc = nullptr, *cctx = nullptr, *x2 = nullptr,
+        *ffh = nullptr, *logp = nullptr, *gscore = nullptr;
+  int* cur_tok = nullptr;
+  // rnn decoder
+  float* uh = nullptr;               // [B, T', d]
+  std::vector<float*> rh[2], rc[2];  // ping-pong recurrent state [rows,d] per layer
+  float* feed[2] = {nullptr, nullptr};
+  float *ga = nullptr, *gb = nullptr, *wq = nullptr, *actx = nullptr;
+  // cnn decoder
+  float* enc_comb = nullptr;         // (mb + emb_remap) * sqrt(.5)  [B,T,d]
+  std::vector<float*> chist[2];      // per layer input history [rows, L, d] ping-pong for beams
+  float *cbase = nullptr, *cA = nullptr, *cy = nullptr, *cout = nullptr, *cpre = nullptr, *ctgt = nullptr,
+        *cctx2 = nullptr;
+  // beam state
+  BeamState beam;
+  int max_rows = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ errors
+int fail(nd_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg; else g_create_error = msg;
+  return code;
+}
+#define ND_CUDA(e, call)                                                                      \
+  do {                                                                                        \
+    cudaError_t _err = (call);                                                                \
+    if (_err != cudaSuccess) {                                                                \
+      (e)->sticky = true;                                                                     \
+      return fail((e), ND_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err));    \
+    }                                                                                         \
+  } while (0)
+// kernel launch through a launcher returning cudaError_t
+#define ND_LAUNCH(e, call)                                                                    \
+  do {                                                                                        \
+    ++(e)->launches;                                                                          \
+    ND_CUDA(e, call);                                                                         \
+  } while (0)
+
+template <class T>
+T* dalloc(nd_engine* e, size_t n) {
+  void* p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t err = cudaMalloc(&p, n * sizeof(T));
+  if (err != cudaSuccess) {
+    e->err = std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes failed: " + cudaGetErrorString(err);
+    cudaGetLastError();
+    return nullptr;
+  }
+  e->allocs.push_back(p);
+  return static_cast<T*>(p);
+}
+
+const float* upload(nd_engine* e, const std::vector<float>& v) {
+  float* p = dalloc<float>(e, v.size());
+  if (!p) { e->oom = true; return nullptr; }
+  if (!v.empty()) cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+  return p;
+}
+
+bool tc_mode(const nd_engine* e) { return e->cfg.gemm_mode != ND_GEMM_SIMT_FP32; }
+
+Lin make_lin(nd_engine* e, const std::vector<float>& W, int N, int K, const std::vector<float>* b) {
+  Lin l;
+  l.N = N; l.K = K; l.ld = K;
+  l.W = upload(e, W);
+  if (tc_mode(e)) {
+    std::vector<float> hi(W.size()), lo(W.size());
+    split_tf32_host(W.data(), hi.data(), lo.data(), W.size());
+    l.W_hi = upload(e, hi);
+    l.W_lo = upload(e, lo);
+  }
+  if (b) l.b = upload(e, *b);
+  return l;
+}
+// view of columns [c0, c0+k) of a packed weight (ld stays the full row pitch)
+Lin col_slice(const Lin& l, int c0, int k, bool keep_bias) {
+  Lin s = l;
+  s.W = l.W + c0;
+  if (l.W_hi) { s.W_hi = l.W_hi + c0; s.W_lo = l.W_lo + c0; }
+  s.K = k;
+  if (!keep_bias) s.b = nullptr;
+  return s;
+}
+
+struct GemmOpt {
+  int prologue = PRO_NONE; const float* pg = nullptr; const float* pb = nullptr; float eps = 1e-6f;
+  int act = 0; const float* residual = nullptr; int64_t ldr = 0; float div_by = 1.f; int div_ncols = 0;
+};
+
+int run_gemm(nd_engine* e, const Lin& l, const float* A, int64_t lda, float* C, int64_t ldc, int64_t M,
+             const GemmOpt& o, cudaStream_t st) {
+  GemmParams p;
+  p.A = A; p.lda = lda; p.C = C; p.ldc = ldc; p.M = (int)M; p.N = l.N; p.K = l.K; p.ldw = l.ld;
+  p.bias = l.b; p.prologue = o.prologue; p.pg = o.pg; p.pb = o.pb; p.eps = o.eps; p.relu = o.act;
+  p.residual = o.residual; p.ldr = o.ldr; p.div_by = o.div_by; p.div_ncols = o.div_ncols;
+  const bool tma_ok = (lda % 4 == 0) && (l.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(l.W) & 15) == 0) && l.K >= 8;
+  if (tc_mode(e) && tma_ok && l.W_hi) {
+    p.W = l.W_hi; p.W_lo = l.W_lo;
+    ND_LAUNCH(e, gemm_tc(p, e->cfg.gemm_mode == ND_GEMM_TC_3XTF32 ? 3 : 1, st));
+  } else {
+    p.W = l.W; p.W_lo = nullptr;
+    ND_LAUNCH(e, gemm_simt(p, st));
+  }
+  return ND_OK;
+}
+#define ND_TRY(expr) do { int _rc = (expr); if (_rc != ND_OK) return _rc; } while (0)
+
+// ------------------------------------------------------------------------------------------ weights
+const HostTensor* find(nd_engine* e, const std::string& k) {
+  auto it = e->raw.find(k);
+  return it == e->raw.end() ? nullptr : &it->second;
+}
+int need(nd_engine* e, const std::string& k, std::vector<int64_t> shape, const HostTensor** out) {
+  const HostTensor* t = find(e, k);
+  if (!t) return fail(e, ND_ERR_WEIGHT, "missing checkpoint tensor '" + k + "'");
+  if (t->shape != shape) {
+    std::string s = "tensor '" + k + "' has shape [";
+    for (auto v : t->shape) s += std::to_string(v) + ",";
+    s += "] expected [";
+    for (auto v : shape) s += std::to_string(v) + ",";
+    return fail(e, ND_ERR_WEIGHT, s + "]");
+  }
+  *out = t;
+  return ND_OK;
+}
+int load_lin(nd_engine* e, const std::string& prefix, int N, int K, bool bias, Lin* out) {
+  const HostTensor *w, *b = nullptr;
+  ND_TRY(need(e, prefix + ".weight", {N, K}, &w));
+  if (bias) ND_TRY(need(e, prefix + ".bias", {N}, &b));
+  *out = make_lin(e, w->f, N, K, b ? &b->f : nullptr);
+  return ND_OK;
+}
+int load_cat_lin(nd_engine* e, const std::vector<std::string>& prefixes, int N_each, int K, Lin* out) {
+  std::vector<float> W, b;
+  for (auto& pfx : prefixes) {
+    const HostTensor *w, *bb;
+    ND_TRY(need(e, pfx + ".weight", {N_each, K}, &w));
+    ND_TRY(need(e, pfx + ".bias", {N_each}, &bb));
+    W.insert(W.end(), w->f.begin(), w->f.end());
+    b.insert(b.end(), bb->f.begin(), bb->f.end());
+  }
+  *out = make_lin(e, W, N_each * (int)prefixes.size(), K, &b);
+  return ND_OK;
+}
+int load_ln(nd_engine* e, const std::string& prefix, int d, LnW* out) {
+  const HostTensor *g, *b;
+  ND_TRY(need(e, prefix + ".weight", {d}, &g));
+  ND_TRY(need(e, prefix + ".bias", {d}, &b));
+  out->g = upload(e, g->f);
+  out->b = upload(e, b->f);
+  return ND_OK;
+}
+// one (bi)directional LSTM layer: checkpoint keys <prefix>.weight_ih<sfx>[_reverse] ...
+int load_lstm(nd_engine* e, const std::string& prefix, const std::string& sfx, int in, int H, int dirs, LstmW* out) {
+  std::vector<float> Wih, bih, Whh, bhh;
+  for (int dir = 0; dir < dirs; ++dir) {
+    const std::string s = sfx + (dir ? "_reverse" : "");
+    const HostTensor *wi, *wh, *bi, *bh;
+    ND_TRY(need(e, prefix + ".weight_ih" + s, {4 * H, in}, &wi));
+    ND_TRY(need(e, prefix + ".weight_hh" + s, {4 * H, H}, &wh));
+    ND_TRY(need(e, prefix + ".bias_ih" + s, {4 * H}, &bi));
+    ND_TRY(need(e, prefix + ".bias_hh" + s, {4 * H}, &bh));
+    Wih.insert(Wih.end(), wi->f.begin(), wi->f.end());
+    Whh.insert(Whh.end(), wh->f.begin(), wh->f.end());
+    bih.insert(bih.end(), bi->f.begin(), bi->f.end());
+    bhh.insert(bhh.end(), bh->f.begin(), bh->f.end());
+  }
+  out->in = in;
+  if (in == 1) {
+    out->w_ih0 = upload(e, Wih);
+    out->b_ih0 = upload(e, bih);
+  } else {
+    out->ih = make_lin(e, Wih, dirs * 4 * H, in, &bih);
+  }
+  out->w_hh = upload(e, Whh);
+  out->b_hh = upload(e, bhh);
+  return ND_OK;
+}
+// weight-normalised conv (onmt/modules/weight_norm.py:153-165, eval: Polyak buffers):
+// w = g/||V|| * V, packed as a [2d, k*d] GEMM weight with column j*d + c  <->  V[o][c][j]
+int load_wnconv(nd_engine* e, const std::string& prefix, int d, int k, Lin* out) {
+  const HostTensor *V, *g, *b;
+  ND_TRY(need(e, prefix + ".V_avg", {2 * d, d, k, 1}, &V));
+  ND_TRY(need(e, prefix + ".g_avg", {2 * d}, &g));
+  ND_TRY(need(e, prefix + ".b_avg", {2 * d}, &b));
+  std::vector<float> W((size_t)2 * d * k * d);
+  for (int o = 0; o < 2 * d; ++o) {
+    const float* v = V->f.data() + (size_t)o * d * k;
+    // torch.norm(v.view(out,-1), 2, 1) in fp32
+    double ss = 0.0;
+    for (int i = 0; i < d * k; ++i) ss += (double)v[i] * (double)v[i];
+    const float scalar = g->f[o] / (float)sqrt(ss);
+    for (int c = 0; c < d; ++c)
+      for (int j = 0; j < k; ++j) W[(size_t)o * k * d + (size_t)j * d + c] = scalar * v[c * k + j];
+  }
+  *out = make_lin(e, W, 2 * d, k * d, &b->f);
+  return ND_OK;
+}
+
+int finalize(nd_engine* e) {
+  const nd_config& c = e->cfg;
+  const int d = c.d_model, V = c.vocab_size;
+  // ---------------- encoder
+  if (c.encoder_type == ND_ENC_NANO) {
+    const int H = d / 2;
+    if (!lstm_supported(H)) return fail(e, ND_ERR_INVALID, "LSTM hidden size " + std::to_string(H) + " unsupported (16/32/64/128)");
+    e->lstm.resize(c.enc_layers);
+    for (int l = 0; l < c.enc_layers; ++l) {
+      ND_TRY(load_lstm(e, "encoder.rnn_" + std::to_string(l), "_l0", l == 0 ? 1 : d, H, 2, &e->lstm[l]));
+      // eval BatchNorm1d as y = x*alpha + beta (ATen batch_norm_cpu_transform_input)
+      const std::string bp = "encoder.batchnorm_" + std::to_string(l);
+      const HostTensor *w, *b, *rm, *rv;
+      ND_TRY(need(e, bp + ".weight", {d}, &w));
+      ND_TRY(need(e, bp + ".bias", {d}, &b));
+      ND_TRY(need(e, bp + ".running_mean", {d}, &rm));
+      ND_TRY(need(e, bp + ".running_var", {d}, &rv));
+      std::vector<float> alpha(d), beta(d);
+      for (int i = 0; i < d; ++i) {
+        const float invstd = 1.0f / sqrtf(rv->f[i] + 1e-5f);
+        alpha[i] = w->f[i] * invstd;
+        beta[i] = b->f[i] - rm->f[i] * alpha[i];
+      }
+      e->lstm[l].bn_alpha = upload(e, alpha);
+      e->lstm[l].bn_beta = upload(e, beta);
+    }
+    ND_TRY(load_lin(e, "encoder.W", d, d, false, &e->encW));
+  } else if (c.encoder_type == ND_ENC_BRNN || c.encoder_type == ND_ENC_RNN) {
+    const int dirs = c.encoder_type == ND_ENC_BRNN ? 2 : 1;
+    const int H = d / dirs;
+    if (!lstm_supported(H)) return fail(e, ND_ERR_INVALID, "LSTM hidden size " + std::to_string(H) + " unsupported (16/32/64/128)");
+    e->lstm.resize(c.enc_layers);
+    for (int l = 0; l < c.enc_layers; ++l)
+      ND_TRY(load_lstm(e, "encoder.rnn", "_l" + std::to_string(l), l == 0 ? 1 : d, H, dirs, &e->lstm[l]));
+  } else if (c.encoder_type == ND_ENC_TRANSFORMER) {
+    ND_TRY(load_lin(e, "encoder.linear", d, 1, true, &e->enc_lin_in));
+    e->encT.resize(c.enc_layers);
+    for (int l = 0; l < c.enc_layers; ++l) {
+      const std::string p = "encoder.transformer." + std::to_string(l);
+      EncLayerT& L = e->encT[l];
+      ND_TRY(load_cat_lin(e, {p + ".self_attn.linear_query", p + ".self_attn.linear_keys", p + ".self_attn.linear_values"}, d, d, &L.qkv));
+      ND_TRY(load_lin(e, p + ".self_attn.final_linear", d, d, true, &L.out));
+      ND_TRY(load_lin(e, p + ".feed_forward.w_1", c.d_ff, d, true, &L.w1));
+      ND_TRY(load_lin(e, p + ".feed_forward.w_2", d, c.d_ff, true, &L.w2));
+      ND_TRY(load_ln(e, p + ".layer_norm", d, &L.ln));
+      ND_TRY(load_ln(e, p + ".feed_forward.layer_norm", d, &L.ln_ff));
+    }
+    ND_TRY(load_ln(e, "encoder.layer_norm", d, &e->enc_ln));
+  } else if (c.encoder_type == ND_ENC_CNN) {
+    ND_TRY(load_lin(e, "encoder.linear", d, 1, true, &e->enc_lin_in));
+    e->enc_conv.resize(c.enc_layers);
+    for (int l = 0; l < c.enc_layers; ++l)
+      ND_TRY(load_wnconv(e, "encoder.cnn.layers." + std::to_string(l) + ".conv", d, c.cnn_kernel_width, &e->enc_conv[l].conv));
+  } else {
+    return fail(e, ND_ERR_INVALID, "unknown encoder_type");
+  }
+  // ---------------- decoder
+  {
+    const HostTensor* em;
+    ND_TRY(need(e, "decoder.embeddings.make_embedding.emb_luts.0.weight", {V, d}, &em));
+    e->emb = upload(e, em->f);
+  }
+  if (c.decoder_type == ND_DEC_TRANSFORMER) {
+    e->decT.resize(c.dec_layers);
+    for (int l = 0; l < c.dec_layers; ++l) {
+      const std::string p = "decoder.transformer_layers." + std::to_string(l);
+      DecLayerT& L = e->decT[l];
+      ND_TRY(load_cat_lin(e, {p + ".self_attn.linear_query", p + ".self_attn.linear_keys", p + ".self_attn.linear_values"}, d, d, &L.qkv));
+      ND_TRY(load_lin(e, p + ".self_attn.final_linear", d, d, true, &L.self_out));
+      ND_TRY(load_lin(e, p + ".context_attn.linear_query", d, d, true, &L.cq));
+      ND_TRY(load_cat_lin(e, {p + ".context_attn.linear_keys", p + ".context_attn.linear_values"}, d, d, &L.ckv));
+      ND_TRY(load_lin(e, p + ".context_attn.final_linear", d, d, true, &L.ctx_out));
+      ND_TRY(load_lin(e, p + ".feed_forward.w_1", c.d_ff, d, true, &L.w1));
+      ND_TRY(load_lin(e, p + ".feed_forward.w_2", d, c.d_ff, true, &L.w2));
+      ND_TRY(load_ln(e, p + ".layer_norm_1", d, &L.ln1));
+      ND_TRY(load_ln(e, p + ".layer_norm_2", d, &L.ln2));
+      ND_TRY(load_ln(e, p + ".feed_forward.layer_norm", d, &L.ln_ff));
+    }
+    ND_TRY(load_ln(e, "decoder.layer_norm", d, &e->dec_ln));
+  } else if (c.decoder_type == ND_DEC_RNN) {
+    e->cells.resize(c.dec_layers);
+    for (int l = 0; l < c.dec_layers; ++l) {
+      const std::string p = "decoder.rnn.layers." + std::to_string(l);
+      const int in = l == 0 ? (c.input_feed ? 2 * d : d) : d;
+      const HostTensor *wi, *wh, *bi, *bh;
+      ND_TRY(need(e, p + ".weight_ih", {4 * d, in}, &wi));
+      ND_TRY(need(e, p + ".weight_hh", {4 * d, d}, &wh));
+      ND_TRY(need(e, p + ".bias_ih", {4 * d}, &bi));
+      ND_TRY(need(e, p + ".bias_hh", {4 * d}, &bh));
+      e->cells[l].ih = make_lin(e, wi->f, 4 * d, in, &bi->f);
+      e->cells[l].hh = make_lin(e, wh->f, 4 * d, d, &bh->f);
+      if (l == 0 && c.input_feed) {
+        e->cells[l].ih_e = col_slice(e->cells[l].ih, 0, d, true);      // embedding columns (+ b_ih)
+        e->cells[l].ih_f = col_slice(e->cells[l].ih, d, d, false);     // input-feed columns
+      }
+    }
+    if (c.attn_type == ND_ATTN_MLP) {
+      ND_TRY(load_lin(e, "decoder.attn.linear_context", d, d, false, &e->attn_ctx));
+      ND_TRY(load_lin(e, "decoder.attn.linear_query", d, d, true, &e->attn_q));
+      const HostTensor* v;
+      ND_TRY(need(e, "decoder.attn.v.weight", {1, d}, &v));
+      e->attn_v = upload(e, v->f);
+      Lin out;
+      ND_TRY(load_lin(e, "decoder.attn.linear_out", d, 2 * d, true, &out));
+      e->attn_out_c = col_slice(out, 0, d, true);
+      e->attn_out_h = col_slice(out, d, d, false);
+    } else {
+      if (c.attn_type == ND_ATTN_GENERAL) ND_TRY(load_lin(e, "decoder.attn.linear_in", d, d, false, &e->attn_in));
+      Lin out;
+      ND_TRY(load_lin(e, "decoder.attn.linear_out", d, 2 * d, false, &out));
+      e->attn_out_c = col_slice(out, 0, d, false);
+      e->attn_out_h = col_slice(out, d, d, false);
+    }
+  } else if (c.decoder_type == ND_DEC_CNN) {
+    ND_TRY(load_lin(e, "decoder.linear", d, d, true, &e->dec_lin));
+    e->dec_conv.resize(c.dec_layers);
+    e->dec_attn_in.resize(c.dec_layers);
+    for (int l = 0; l < c.dec_layers; ++l) {
+      ND_TRY(load_wnconv(e, "decoder.conv_layers." + std::to_string(l) + ".conv", d, c.cnn_kernel_width, &e->dec_conv[l].conv));
+      ND_TRY(load_lin(e, "decoder.attn_layers." + std::to_string(l) + ".linear_in", d, d, true, &e->dec_attn_in[l]));
+    }
+  } else {
+    return fail(e, ND_ERR_INVALID, "unknown decoder_type");
+  }
+  {
+    const HostTensor *gw, *gb;
+    ND_TRY(need(e, "generator.0.weight", {V, d}, &gw));
+    ND_TRY(need(e, "generator.0.bias", {V}, &gb));
+    e->gen.W = upload(e, gw->f);
+    e->gen.b = upload(e, gb->f);
+    e->gen.N = V; e->gen.K = d; e->gen.ld = d;
+  }
+  if (e->oom) return fail(e, ND_ERR_NOMEM, "device allocation failed while packing weights: " + e->err);
+  e->raw.clear();
+  return ND_OK;
+}
+
+// ------------------------------------------------------------------------------------------ workspace
+int alloc_workspace(nd_engine* e) {
+  const nd_config& c = e->cfg;
+  const int64_t B = c.max_batch, T = c.max_src_len, d = c.d_model, L = c.max_tgt_len, K = c.max_beam;
+  const int64_t BT = B * T, rows = B * K;
+  e->max_rows = (int)rows;
+  bool ok = true;
+  auto F = [&](float*& p, int64_t n) { p = dalloc<float>(e, (size_t)n); ok = ok && p; };
+  F(e->src, BT);
+  e->lengths = dalloc<int64_t>(e, B);
+  e->mem_len = dalloc<int64_t>(e, B);
+  F(e->bufA, BT * d); F(e->bufB, BT * d); F(e->mb, BT * d);
+  int64_t wide = 4 * d;                                    // LSTM input projection (2 dirs * 4 * d/2)
+  if (c.encoder_type == ND_ENC_NANO)
+    for (int l = 0; l < c.enc_layers; ++l)
+      if (c.enc_pooling[l] > 1 && !e->bufC) F(e->bufC, BT * d);
+  if (c.encoder_type == ND_ENC_TRANSFORMER) { wide = std::max<int64_t>(3 * d, c.d_ff); F(e->bufC, BT * d); }
+  if (c.encoder_type == ND_ENC_CNN) { wide = (int64_t)c.cnn_kernel_width * d; F(e->big2, BT * 2 * d); F(e->emb_remap, BT * d); }
+  F(e->big, BT * wide);
+  if (c.encoder_type == ND_ENC_BRNN || c.encoder_type == ND_ENC_RNN) {
+    F(e->enc_hn, (int64_t)c.enc_layers * B * d); F(e->enc_cn, (int64_t)c.enc_layers * B * d);
+  }
+  // decoder
+  F(e->logp, rows * c.vocab_size); F(e->gscore, rows);
+  e->cur_tok = dalloc<int>(e, rows);
+  if (c.decoder_type == ND_DEC_TRANSFORMER) {
+    e->ckv.resize(c.dec_layers); e->selfK.resize(c.dec_layers); e->selfV.resize(c.dec_layers);
+    for (int l = 0; l < c.dec_layers; ++l) { F(e->ckv[l], BT * 2 * d); F(e->selfK[l], rows * L * d); F(e->selfV[l], rows * L * d); }
+    F(e->x, rows * d); F(e->qkv, rows * 3 * d); F(e->sctx, rows * d); F(e->x1, rows * d); F(e->qc, rows * d);
+    F(e->cctx, rows * d); F(e->x2, rows * d); F(e->ffh, rows * c.d_ff);
+  } else if (c.decoder_type == ND_DEC_RNN) {
+    F(e->uh, BT * d);
+    for (int s = 0; s < 2; ++s) {
+      e->rh[s].resize(c.dec_layers); e->rc[s].resize(c.dec_layers);
+      for (int l = 0; l < c.dec_layers; ++l) { F(e->rh[s][l], rows * d); F(e->rc[s][l], rows * d); }
+      F(e->feed[s], rows * d);
+    }
+    F(e->x, rows * d); F(e->ga, rows * 4 * d); F(e->gb, rows * 4 * d); F(e->wq, rows * d); F(e->actx, rows * d);
+  } else {
+    F(e->enc_comb, BT * d);
+    for (int s = 0; s < 2; ++s) {
+      e->chist[s].resize(c.dec_layers);
+      for (int l = 0; l < c.dec_layers; ++l) F(e->chist[s][l], rows * L * d);
+    }
+    F(e->x, rows * d); F(e->cbase, rows * d); F(e->cA, rows * c.cnn_kernel_width * d); F(e->cy, rows * 2 * d);
+    F(e->cout, rows * d); F(e->cpre, rows * d); F(e->ctgt, rows * d); F(e->cctx2, rows * d); F(e->x1, rows * d);
+  }
+  // beam state
+  BeamState& b = e->beam;
+  b.topk_log_probs = dalloc<float>(e, rows);
+  b.alive_seq = dalloc<int>(e, 2 * rows * (L + 1));
+  b.anc = dalloc<int>(e, 2 * rows * L);
+  b.cur_tok = e->cur_tok;
+  b.parent = dalloc<int>(e, rows);
+  b.retired = dalloc<int>(e, B);
+  b.top_finished = dalloc<int>(e, B);
+  b.n_hyp = dalloc<int>(e, B);
+  b.hyp_score = dalloc<float>(e, B * K);
+  b.hyp_len = dalloc<int>(e, B * K);
+  b.hyp_seq = dalloc<int>(e, B * K * L);
+  b.n_alive = dalloc<int>(e, 1);
+  ok = ok && e->lengths && e->mem_len && e->cur_tok && b.topk_log_probs && b.alive_seq && b.anc && b.parent &&
+       b.retired && b.top_finished && b.n_hyp && b.hyp_score && b.hyp_len && b.hyp_seq && b.n_alive;
+  return ok ? ND_OK : ND_ERR_NOMEM;
+}
+
+// ------------------------------------------------------------------------------------------ encoders
+int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
+  const nd_config& c = e->cfg;
+  const int d = c.d_model, B = e->B;
+  const bool nano = c.encoder_type == ND_ENC_NANO;
+  const int dirs = (c.encoder_type == ND_ENC_RNN) ? 1 : 2;
+  const int H = d / dirs;
+  int T = e->T;
+  std::vector<int64_t> lens = e->h_lengths;
+  const float* in = nullptr;                // previous layer output [B,T,d]
+  float* outs[2] = {e->bufA, e->bufB};
+  float* last = nullptr;
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const LstmW& W = e->lstm[l];
+    float* out = outs[l & 1];
+    LstmParams p;
+    p.B = B; p.T = T; p.dirs = dirs; p.H = H;
+    p.w_hh = W.w_hh; p.b_hh = W.b_hh; p.lengths = e->lengths; p.out = out;
+    if (l == 0) {
+      p.x0 = e->src; p.w_ih0 = W.w_ih0; p.b_ih0 = W.b_ih0;
+    } else {
+      GemmOpt o;
+      if (nano) { o.prologue = PRO_AFFINE; o.pg = e->lstm[l - 1].bn_alpha; o.pb = e->lstm[l - 1].bn_beta; }
+      ND_TRY(run_gemm(e, W.ih, in, d, e->big, (int64_t)dirs * 4 * H, (int64_t)B * T, o, st));
+      p.xg = e->big; p.xg_ld = (int64_t)dirs * 4 * H;
+    }
+    if (!nano) { p.h_n = e->enc_hn + (int64_t)l * dirs * B * H; p.c_n = e->enc_cn + (int64_t)l * dirs * B * H; }
+    ND_CUDA(e, cudaMemsetAsync(out, 0, (size_t)B * T * d * sizeof(float), st));
+    ND_LAUNCH(e, lstm_layer(p, e->n_sm, st));
+    last = out;
+    if (nano && c.enc_pooling[l] > 1) {
+      // MaxPool1d over time (nano_encoder.py:101-105); lengths follow floor((len - s)/s + 1)
+      const int s = c.enc_pooling[l];
+      const int Tn = T / s;
+      float* pooled = e->bufC;
+      ND_LAUNCH(e, maxpool_time(out, pooled, B, T, d, s, st));
+      ND_CUDA(e, cudaMemcpyAsync(out, pooled, (size_t)B * Tn * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      T = Tn;
+      for (auto& v : lens) v = (int64_t)floor((double)(v - s) / (double)s + 1.0);
+      ND_CUDA(e, cudaMemcpyAsync(e->lengths, lens.data(), lens.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+      ND_CUDA(e, cudaStreamSynchronize(st));      // lens (host vector) is reused below
+    }
+    in = out;
+  }
+  e->Tp = T;
+  if (nano) {
+    // memory bank = W . (pre-BatchNorm pooled output of the last layer)          nano_encoder.py:113-115
+    GemmOpt o;
+    ND_TRY(run_gemm(e, e->encW, last, d, e->mb, d, (int64_t)B * T, o, st));
+  } else {
+    ND_CUDA(e, cudaMemcpyAsync(e->mb, last, (size_t)B * T * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  ND_CUDA(e, cudaMemcpyAsync(e->mem_len, e->lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (nano) {
+    // restore the source lengths (the decoder's reference state keeps the pooled ones in mem_len)
+    ND_CUDA(e, cudaMemcpyAsync(e->lengths, e->h_lengths.data(), (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  }
+  return ND_OK;
+}
+
+int encode_transformer(nd_engine* e, cudaStream_t st) {
+  const nd_config& c = e->cfg;
+  const int d = c.d_model, B = e->B, T = e->T;
+  const int64_t M = (int64_t)B * T;
+  const float sq = sqrtf((float)(d / c.heads));
+  float* x = e->bufA;
+  float* x1 = e->bufB;
+  float* ctx = e->bufC;
+  ND_LAUNCH(e, linear_in1(e->src, e->enc_lin_in.W, e->enc_lin_in.b, x, M, d, st));       // encoder/transformer.py:113
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const EncLayerT& L = e->encT[l];
+    GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln.g; o1.pb = L.ln.b; o1.div_by = sq; o1.div_ncols = d;
+    ND_TRY(run_gemm(e, L.qkv, x, d, e->big, 3 * d, M, o1, st));
+    EncAttnParams a; a.qkv = e->big; a.src = e->src; a.ctx = ctx; a.B = B; a.T = T; a.d = d; a.H = c.heads;
+    ND_LAUNCH(e, encoder_attention(a, st));
+    GemmOpt o2; o2.residual = x; o2.ldr = d;
+    ND_TRY(run_gemm(e, L.out, ctx, d, x1, d, M, o2, st));
+    GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln_ff.g; o3.pb = L.ln_ff.b; o3.act = 1;
+    ND_TRY(run_gemm(e, L.w1, x1, d, e->big, c.d_ff, M, o3, st));
+    GemmOpt o4; o4.residual = x1; o4.ldr = d;
+    ND_TRY(run_gemm(e, L.w2, e->big, c.d_ff, x, d, M, o4, st));
+  }
+  ND_LAUNCH(e, layernorm_rows(x, e->enc_ln.g, e->enc_ln.b, 1e-6f, e->mb, M, d, st));
+  e->Tp = T;
+  ND_CUDA(e, cudaMemcpyAsync(e->mem_len, e->lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  return ND_OK;
+}
+
+int encode_cnn(nd_engine* e, cudaStream_t st) {
+  const nd_config& c = e->cfg;
+  const int d = c.d_model, B = e->B, T = e->T, k = c.cnn_kernel_width;
+  const int64_t M = (int64_t)B * T;
+  ND_LAUNCH(e, linear_in1(e->src, e->enc_lin_in.W, e->enc_lin_in.b, e->emb_remap, M, d, st));
+  const float* x = e->emb_remap;
+  float* outs[2] = {e->bufA, e->bufB};
+  for (int l = 0; l < c.enc_layers; ++l) {
+    ND_LAUNCH(e, im2col_time(x, e->big, B, T, d, k, k / 2, st));
+    GemmOpt o;
+    ND_TRY(run_gemm(e, e->enc_conv[l].conv, e->big, (int64_t)k * d, e->big2, 2 * d, M, o, st));
+    float* out = (l + 1 == c.enc_layers) ? e->mb : outs[l & 1];
+    ND_LAUNCH(e, glu_residual(e->big2, x, out, nullptr, M, d, st));
+    x = out;
+  }
+  e->Tp = T;
+  ND_CUDA(e, cudaMemcpyAsync(e->mem_len, e->lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  return ND_OK;
+}
+
+// ------------------------------------------------------------------------------------------ decoders
+struct DecodeCtx {
+  int rows = 0, K = 1, step = 0, Lmax = 0;
+  bool beam = false;
+  float* attn_out = nullptr;          // optional [rows, T'] for this step
+};
+
+int decoder_init(nd_engine* e, int K, cudaStream_t st) {
+  const nd_config& c = e->cfg;
+  const int d = c.d_model, B = e->B, Tp = e->Tp;
+  const int64_t M = (int64_t)B * Tp;
+  if (c.decoder_type == ND_DEC_TRANSFORMER) {
+    if (Tp != e->T)
+      return fail(e, ND_ERR_INVALID, "transformer decoder needs -audio_enc_pooling 1 (the reference builds its cross "
+                                     "mask from the un-pooled signal, decoder/transformer.py:201-221)");
+    // memory keys / values, projected once per chunk (multi_headed_attn.py:142-153)
+    for (int l = 0; l < c.dec_layers; ++l) {
+      GemmOpt o;
+      ND_TRY(run_gemm(e, e->decT[l].ckv, e->mb, d, e->ckv[l], 2 * d, M, o, st));
+    }
+  } else if (c.decoder_type == ND_DEC_RNN) {
+    const int rows = B * K;
+    if (c.attn_type == ND_ATTN_MLP) {
+      GemmOpt o;                     // uh = Uk . H, exact same product the reference recomputes every step
+      ND_TRY(run_gemm(e, e->attn_ctx, e->mb, d, e->uh, d, M, o, st));
+    }
+    // decoder.py:108-129: hidden from the encoder final state ([fwd;bwd] per layer), input_feed = 0
+    for (int l = 0; l < c.dec_layers; ++l) {
+      ND_CUDA(e, cudaMemsetAsync(e->rh[0][l], 0, (size_t)rows * d * sizeof(float), st));
+      ND_CUDA(e, cudaMemsetAsync(e->rc[0][l], 0, (size_t)rows * d * sizeof(float), st));
+    }
+    ND_CUDA(e, cudaMemsetAsync(e->feed[0], 0, (size_t)rows * d * sizeof(float), st));
+    if (c.encoder_type == ND_ENC_BRNN || c.encoder_type == ND_ENC_RNN) {
+      if (c.enc_layers != c.dec_layers) return fail(e, ND_ERR_INVALID, "rnn encoder/decoder layer counts differ");
+      const int dirs = c.encoder_type == ND_ENC_BRNN ? 2 : 1;
+      const int H = d / dirs;
+      for (int l = 0; l < c.dec_layers; ++l)
+        for (int dir = 0; dir < dirs; ++dir)
+          for (int k = 0; k < K; ++k) {
+            // rows are chunk-major: row = b*K + k; copy with a strided 2-D memcpy (width H floats)
+            const float* hs = e->enc_hn + ((int64_t)l * dirs + dir) * B * H;
+            const float* cs = e->enc_cn + ((int64_t)l * dirs + dir) * B * H;
+            ND_CUDA(e, cudaMemcpy2DAsync(e->rh[0][l] + (int64_t)k * d + dir * H, (size_t)K * d * sizeof(float), hs,
+                                         (size_t)H * sizeof(float), (size_t)H * sizeof(float), B,
+                                         cudaMemcpyDeviceToDevice, st));
+            ND_CUDA(e, cudaMemcpy2DAsync(e->rc[0][l] + (int64_t)k * d + dir * H, (size_t)K * d * sizeof(float), cs,
+                                         (size_t)H * sizeof(float), (size_t)H * sizeof(float), B,
+                                         cudaMemcpyDeviceToDevice, st));
+          }
+    }
+  } else {
+    return fail(e, ND_ERR_INVALID, "cnn decoder: not implemented in this build");
+  }
+  return ND_OK;
+}
+
+// one decoder step for all rows: cur_tok -> logp [rows, V] (and greedy selection when gp.ids != null)
+int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t st) {
+  const nd_config& c = e->cfg;
+  const int d = c.d_model, rows = dc.rows, B = e->B, Tp = e->Tp;
+  const int* retired = dc.beam ? e->beam.retired : nullptr;
+  ND_LAUNCH(e, embed_rows(e->cur_tok, e->emb, e->x, d, rows, d, c.position_encoding, dc.step, st));
+  if (c.decoder_type == ND_DEC_TRANSFORMER) {
+    const float sq = sqrtf((float)(d / c.heads));
+    float* x = e->x;
+    for (int l = 0; l < c.dec_layers; ++l) {
+      const DecLayerT& L = e->decT[l];
+      GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln1.g; o1.pb = L.ln1.b; o1.div_by = sq; o1.div_ncols = d;
+      ND_TRY(run_gemm(e, L.qkv, x, d, e->qkv, 3 * d, rows, o1, st));
+      SelfAttnParams sa;
+      sa.qkv = e->qkv; sa.Kc = e->selfK[l]; sa.Vc = e->selfV[l]; sa.ctx = e->sctx; sa.rows = rows; sa.d = d;
+      sa.H = c.heads; sa.Lmax = dc.Lmax; sa.step = dc.step; sa.retired = retired; sa.rows_per_chunk = dc.K;
+      if (dc.beam && dc.step > 0) { sa.anc = e->beam.anc + (int64_t)(dc.step & 1) * rows * dc.Lmax; sa.anc_ld = dc.Lmax; }
+      ND_LAUNCH(e, self_attention_step(sa, st));
+      GemmOpt o2; o2.residual = x; o2.ldr = d;
+      ND_TRY(run_gemm(e, L.self_out, e->sctx, d, e->x1, d, rows, o2, st));
+      GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln2.g; o3.pb = L.ln2.b; o3.div_by = sq; o3.div_ncols = d;
+      ND_TRY(run_gemm(e, L.cq, e->x1, d, e->qc, d, rows, o3, st));
+      CrossAttnParams ca;
+      ca.q = e->qc; ca.q_ld = d; ca.K = e->ckv[l]; ca.V = e->ckv[l] + d; ca.kv_ld = 2 * d;
+      ca.src = e->src; ca.src_ld = e->T; ca.mask_value = 1.0f;         // decoder/transformer.py:219-221 (pad_idx = 1)
+      ca.retired = retired; ca.ctx = e->cctx; ca.ctx_ld = d; ca.n_chunks = B; ca.NQ = dc.K; ca.T = Tp; ca.d = d;
+      ca.H = c.heads;
+      ca.attn = (l + 1 == c.dec_layers) ? dc.attn_out : nullptr;
+      ND_LAUNCH(e, cross_attention(ca, st));
+      GemmOpt o4; o4.residual = e->x1; o4.ldr = d;
+      ND_TRY(run_gemm(e, L.ctx_out, e->cctx, d, e->x2, d, rows, o4, st));
+      GemmOpt o5; o5.prologue = PRO_LAYERNORM; o5.pg = L.ln_ff.g; o5.pb = L.ln_ff.b; o5.act = 1;
+      ND_TRY(run_gemm(e, L.w1, e->x2, d, e->ffh, c.d_ff, rows, o5, st));
+      GemmOpt o6; o6.residual = e->x2; o6.ldr = d;
+      ND_TRY(run_gemm(e, L.w2, e->ffh, c.d_ff, x, d, rows, o6, st));
+    }
+    gp.x = x; gp.x_ld = d; gp.ln_g = e->dec_ln.g; gp.ln_b = e->dec_ln.b;
+  } else if (c.decoder_type == ND_DEC_RNN) {
+    const int cur = dc.step & 1, nxt = cur ^ 1;
+    // with beams the state of step-1 was written for the parents' rows: gather it first
+    std::vector<float*>&hc = e->rh[cur], &cc = e->rc[cur], &hn = e->rh[nxt], &cn = e->rc[nxt];
+    float* feed_c = e->feed[cur];
+    const float* below = nullptr;
+    for (int l = 0; l < c.dec_layers; ++l) {
+      const nd_engine::RnnCell& R = e->cells[l];
+      GemmOpt oa;
+      if (l == 0 && c.input_feed) {
+        ND_TRY(run_gemm(e, R.ih_e, e->x, d, e->ga, 4 * d, rows, oa, st));
+        GemmOpt of; of.residual = e->ga; of.ldr = 4 * d;
+        ND_TRY(run_gemm(e, R.ih_f, feed_c, d, e->ga, 4 * d, rows, of, st));
+      } else {
+        ND_TRY(run_gemm(e, R.ih, l == 0 ? e->x : below, d, e->ga, 4 * d, rows, oa, st));
+      }
+      GemmOpt ob;
+      ND_TRY(run_gemm(e, R.hh, hc[l], d, e->gb, 4 * d, rows, ob, st));
+      ND_LAUNCH(e, lstm_cell_pointwise(e->ga, e->gb, cc[l], hn[l], cn[l], rows, d, st));
+      below = hn[l];
+    }
+    MlpAttnParams ma;
+    ma.mem = e->mb; ma.lengths = e->mem_len; ma.retired = retired; ma.ctx = e->actx; ma.ctx_ld = d;
+    ma.n_chunks = B; ma.NQ = dc.K; ma.T = Tp; ma.d = d; ma.attn = dc.attn_out;
+    if (c.attn_type == ND_ATTN_MLP) {
+      GemmOpt oq;
+      ND_TRY(run_gemm(e, e->attn_q, below, d, e->wq, d, rows, oq, st));
+      ma.wq = e->wq; ma.uh = e->uh; ma.v = e->attn_v;
+    } else {
+      ma.dot = 1; ma.uh = e->mb;
+      if (c.attn_type == ND_ATTN_GENERAL) {
+        GemmOpt oq;
+        ND_TRY(run_gemm(e, e->attn_in, below, d, e->wq, d, rows, oq, st));
+        ma.wq = e->wq;
+      } else {
+        ma.wq = below;
+      }
+    }
+    ND_LAUNCH(e, mlp_attention(ma, st));
+    // attn_h = W_out [c ; h] (+ b for mlp; tanh otherwise)            global_attention.py:197-200
+    GemmOpt oc;
+    ND_TRY(run_gemm(e, e->attn_out_c, e->actx, d, e->wq, d, rows, oc, st));
+    GemmOpt oh; oh.residual = nullptr;
+    // second half accumulates on top of the first through the residual input; tanh must come last, so for
+    // general/dot attention the first product is added as residual BEFORE the activation is not possible:
+    // use act only with mlp == none.
+    if (c.attn_type == ND_ATTN_MLP) {
+      oh.residual = e->wq; oh.ldr = d;
+      ND_TRY(run_gemm(e, e->attn_out_h, below, d, e->feed[nxt], d, rows, oh, st));
+    } else {
+      return fail(e, ND_ERR_INVALID, "general/dot global attention: not implemented in this build");
+    }
+    gp.x = e->feed[nxt]; gp.x_ld = d; gp.ln_g = nullptr; gp.ln_b = nullptr;
+  } else {
+    return fail(e, ND_ERR_INVALID, "cnn decoder: not implemented in this build");
+  }
+  gp.Wg = e->gen.W; gp.bg = e->gen.b; gp.logp = e->logp; gp.rows = rows; gp.d = d; gp.V = c.vocab_size;
+  gp.step = dc.step;
+  ND_LAUNCH(e, generator_step(gp, st));
+  return ND_OK;
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int nd_api_version(void) { return ND_API_VERSION; }
+
+const char* nd_last_error(const nd_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int nd_create(const nd_config* cfg, nd_engine** out) {
+  if (!cfg || !out) return fail(nullptr, ND_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->api_version != ND_API_VERSION) return fail(nullptr, ND_ERR_INVALID, "nd_config.api_version mismatch");
+  if (cfg->d_model % 32 || cfg->heads <= 0 || 32 % cfg->heads || cfg->d_model % cfg->heads)
+    return fail(nullptr, ND_ERR_INVALID, "d_model must be a multiple of 32 and heads a power of two <= 32");
+  if (cfg->vocab_size > 16 || cfg->vocab_size < 5) return fail(nullptr, ND_ERR_INVALID, "vocab_size must be in [5,16]");
+  if (cfg->max_beam < 1 || cfg->max_beam > 8) return fail(nullptr, ND_ERR_INVALID, "max_beam must be in [1,8]");
+  if (cfg->max_batch < 1 || cfg->max_src_len < 1 || cfg->max_tgt_len < 1) return fail(nullptr, ND_ERR_INVALID, "bad max sizes");
+  int ndev = 0;
+  cudaError_t err = cudaGetDeviceCount(&ndev);
+  if (err != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, ND_ERR_CUDA, "no CUDA device available (libnanodec has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, ND_ERR_INVALID, "bad device ordinal");
+  if ((err = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, ND_ERR_CUDA, cudaGetErrorString(err));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) return fail(nullptr, ND_ERR_CUDA, "libnanodec is built for sm_100a only; device is sm_" +
+                                                             std::to_string(prop.major) + std::to_string(prop.minor));
+  std::unique_ptr<nd_engine> e(new nd_engine());
+  e->cfg = *cfg;
+  e->n_sm = prop.multiProcessorCount;
+  if (cfg->gemm_mode != ND_GEMM_SIMT_FP32) {
+    const char* why = "";
+    if (!gemm_tc_available(&why)) return fail(nullptr, ND_ERR_CUDA, std::string("tcgen05 GEMM path unavailable: ") + why);
+  }
+  int rc = alloc_workspace(e.get());
+  if (rc != ND_OK) {
+    g_create_error = "workspace allocation failed: " + e->err;
+    for (void* p : e->allocs) if (p) cudaFree(p);
+    return rc;
+  }
+  *out = e.release();
+  return ND_OK;
+}
+
+int nd_destroy(nd_engine* e) {
+  if (!e) return ND_OK;
+  cudaSetDevice(e->cfg.device);
+  for (void* p : e->allocs) if (p) cudaFree(p);
+  delete e;
+  return ND_OK;
+}
+
+int nd_load_weight(nd_engine* e, const char* name, const void* data, const int64_t* shape, int32_t ndim, int32_t dtype) {
+  if (!e || !name || !data || (ndim > 0 && !shape)) return fail(e, ND_ERR_INVALID, "null argument");
+  if (e->finalized) return fail(e, ND_ERR_STATE, "weights already finalized");
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  if (dtype == ND_DTYPE_F32) {
+    t.f.resize((size_t)n);
+    cudaSetDevice(e->cfg.device);
+    ND_CUDA(e, cudaMemcpy(t.f.data(), data, (size_t)n * sizeof(float), cudaMemcpyDefault));
+  } else {
+    return ND_OK;          // integer buffers (num_batches_tracked, mask) carry no arithmetic
+  }
+  e->raw[name] = std::move(t);
+  return ND_OK;
+}
+
+int nd_finalize_weights(nd_engine* e) {
+  if (!e) return ND_ERR_INVALID;
+  if (e->finalized) return ND_OK;
+  cudaSetDevice(e->cfg.device);
+  int rc = finalize(e);
+  if (rc == ND_OK) e->finalized = true;
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, cudaGetErrorString(err)); }
+  return rc;
+}
+
+int64_t nd_launch_count(const nd_engine* e) { return e ? e->launches : 0; }
+int nd_reset_launch_count(nd_engine* e) { if (e) e->launches = 0; return ND_OK; }
+
+static int check_ready(nd_engine* e) {
+  if (!e) return ND_ERR_INVALID;
+  if (e->sticky) return ND_ERR_CUDA;
+  if (!e->finalized) return fail(e, ND_ERR_STATE, "nd_finalize_weights has not been called");
+  cudaSetDevice(e->cfg.device);
+  return ND_OK;
+}
+
+int nd_frontend_stats(nd_engine* e, const int16_t* signal, const int64_t* read_offsets, int32_t n_reads,
+                      int32_t normalization, double* out_center, double* out_scale, void* stream) {
+  if (!e) return ND_ERR_INVALID;
+  if (e->sticky) return ND_ERR_CUDA;
+  cudaSetDevice(e->cfg.device);
+  if (normalization < 0 || normalization > 2) return fail(e, ND_ERR_INVALID, "unknown normalization");
+  ND_LAUNCH(e, frontend_stats(signal, read_offsets, n_reads, normalization, out_center, out_scale, (cudaStream_t)stream));
+  return ND_OK;
+}
+
+int nd_frontend_chunks(nd_engine* e, const int16_t* signal, const int64_t* read_offsets, const double* center,
+                       const double* scale, const int32_t* chunk_read, const int64_t* chunk_start, int32_t n_chunks,
+                       int32_t chunk_len, float* out_chunks, int64_t* out_lengths, void* stream) {
+  if (!e) return ND_ERR_INVALID;
+  if (e->sticky) return ND_ERR_CUDA;
+  cudaSetDevice(e->cfg.device);
+  ND_LAUNCH(e, frontend_chunks(signal, read_offsets, center, scale, chunk_read, chunk_start, n_chunks, chunk_len,
+                               out_chunks, out_lengths, (cudaStream_t)stream));
+  return ND_OK;
+}
+
+int nd_encode(nd_engine* e, const float* src, const int64_t* lengths, int32_t B, int32_t T, void* stream) {
+  ND_TRY(check_ready(e));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B < 1 || B > e->cfg.max_batch || T < 1 || T > e->cfg.max_src_len)
+    return fail(e, ND_ERR_INVALID, "nd_encode: B or T outside the sizes given to nd_create");
+  e->encoded = false;
+  e->B = B; e->T = T;
+  ND_CUDA(e, cudaMemcpyAsync(e->src, src, (size_t)B * T * sizeof(float), cudaMemcpyDefault, st));
+  ND_CUDA(e, cudaMemcpyAsync(e->lengths, lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDefault, st));
+  e->h_lengths.resize(B);
+  const nd_config& c = e->cfg;
+  bool need_host_lens = false;
+  if (c.encoder_type == ND_ENC_NANO)
+    for (int l = 0; l < c.enc_layers; ++l) need_host_lens = need_host_lens || c.enc_pooling[l] > 1;
+  if (need_host_lens) {
+    // only the pooling arithmetic needs host lengths (the reference does lengths.tolist(), nano_encoder.py:90)
+    ND_CUDA(e, cudaMemcpyAsync(e->h_lengths.data(), lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDefault, st));
+    ND_CUDA(e, cudaStreamSynchronize(st));
+  }
+  int rc;
+  if (c.encoder_type == ND_ENC_TRANSFORMER) rc = encode_transformer(e, st);
+  else if (c.encoder_type == ND_ENC_CNN) rc = encode_cnn(e, st);
+  else rc = encode_lstm_stack(e, st);
+  if (rc == ND_OK) e->encoded = true;
+  return rc;
+}
+
+int nd_get_memory_bank(nd_engine* e, float* out, int64_t* out_lengths, int32_t* out_Tp, void* stream) {
+  ND_TRY(check_ready(e));
+  if (!e->encoded) return fail(e, ND_ERR_STATE, "nd_get_memory_bank before nd_encode");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_Tp) *out_Tp = e->Tp;
+  if (out) {
+    if (e->cfg.encoder_type == ND_ENC_CNN) return fail(e, ND_ERR_INVALID, "cnn memory bank export: not implemented");
+    ND_LAUNCH(e, transpose_bt(e->mb, out, e->B, e->Tp, e->cfg.d_model, st));
+  }
+  if (out_lengths)
+    ND_CUDA(e, cudaMemcpyAsync(out_lengths, e->mem_len, (size_t)e->B * sizeof(int64_t), cudaMemcpyDefault, st));
+  return ND_OK;
+}
+
+int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* out_ids, float* out_scores,
+                     float* out_attn, float* out_logits, void* stream) {
+  ND_TRY(check_ready(e));
+  if (!e->encoded) return fail(e, ND_ERR_STATE, "nd_decode_greedy before nd_encode");
+  if (max_len < 1 || max_len > e->cfg.max_tgt_len) return fail(e, ND_ERR_INVALID, "max_len outside nd_create sizes");
+  if (!out_ids || !out_scores) return fail(e, ND_ERR_INVALID, "null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = e->B, V = e->cfg.vocab_size;
+  ND_TRY(decoder_init(e, 1, st));
+  ND_LAUNCH(e, fill_int(e->cur_tok, B, 2, st));          // <s> for every row (translator.py:451-452)
+  DecodeCtx dc;
+  dc.rows = B; dc.K = 1; dc.Lmax = e->cfg.max_tgt_len; dc.beam = false;
+  for (int step = 0; step < max_len; ++step) {           // no EOS early exit, like the reference (:455)
+    dc.step = step;
+    dc.attn_out = out_attn ? out_attn + (int64_t)step * B * e->Tp : nullptr;
+    GenParams gp;
+    gp.ids = out_ids; gp.ids_ld = max_len; gp.scores = out_scores; gp.next_tok = e->cur_tok;
+    gp.trace = out_logits ? out_logits + (int64_t)step * B * V : nullptr;
+    gp.min_len = min_len;
+    ND_TRY(decoder_step(e, dc, gp, st));
+  }
+  return ND_OK;
+}
+
+int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len, int32_t min_len, float alpha,
+                   int64_t* out_ids, int32_t* out_lens, float* out_scores, void* stream) {
+  ND_TRY(check_ready(e));
+  if (!e->encoded) return fail(e, ND_ERR_STATE, "nd_decode_beam before nd_encode");
+  if (beam_size < 1 || beam_size > e->cfg.max_beam) return fail(e, ND_ERR_INVALID, "beam_size outside nd_create sizes");
+  if (n_best < 1 || n_best > beam_size) return fail(e, ND_ERR_INVALID, "n_best must be in [1, beam_size]");
+  if (max_len < 1 || max_len > e->cfg.max_tgt_len) return fail(e, ND_ERR_INVALID, "max_len outside nd_create sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = e->B, K = beam_size;
+  ND_TRY(decoder_init(e, K, st));
+  BeamParams bp;
+  bp.logp = e->logp; bp.st = e->beam; bp.B = B; bp.K = K; bp.V = e->cfg.vocab_size; bp.Lmax = e->cfg.max_tgt_len;
+  bp.max_len = max_len; bp.min_len = min_len; bp.n_best = n_best; bp.alpha = alpha;
+  ND_LAUNCH(e, beam_init(bp, 2, st));
+  DecodeCtx dc;
+  dc.rows = B * K; dc.K = K; dc.Lmax = e->cfg.max_tgt_len; dc.beam = true;
+  const int d = e->cfg.d_model;
+  for (int step = 0; step < max_len; ++step) {
+    dc.step = step;
+    if (e->cfg.decoder_type == ND_DEC_RNN && step > 0) {
+      // reorder the recurrent state by parent beam (translator.py:820-821 map_state index_select)
+      const int cur = step & 1, prv = cur ^ 1;
+      // state of the previous step lives in buffers [cur] (written as "nxt" there); gather into [prv] and swap roles
+      for (int l = 0; l < e->cfg.dec_layers; ++l) {
+        ND_LAUNCH(e, gather_rows(e->rh[cur][l], e->rh[prv][l], e->beam.parent, dc.rows, d, st));
+        ND_LAUNCH(e, gather_rows(e->rc[cur][l], e->rc[prv][l], e->beam.parent, dc.rows, d, st));
+        ND_CUDA(e, cudaMemcpyAsync(e->rh[cur][l], e->rh[prv][l], (size_t)dc.rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        ND_CUDA(e, cudaMemcpyAsync(e->rc[cur][l], e->rc[prv][l], (size_t)dc.rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
+      ND_LAUNCH(e, gather_rows(e->feed[cur], e->feed[prv], e->beam.parent, dc.rows, d, st));
+      ND_CUDA(e, cudaMemcpyAsync(e->feed[cur], e->feed[prv], (size_t)dc.rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    GenParams gp;
+    gp.min_len = min_len;
+    ND_TRY(decoder_step(e, dc, gp, st));
+    bp.step = step;
+    ND_LAUNCH(e, beam_step(bp, st));
+  }
+  ND_LAUNCH(e, beam_finalize(bp, out_ids, out_lens, out_scores, st));
+  return ND_OK;
+}
+
+int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, const float* bias, const float* residual,
+                 const float* ln_gamma, const float* ln_beta, float* C, int32_t M, int32_t N, int32_t K, int32_t relu,
+                 void* stream) {
+  if (!e) return ND_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmParams p;
+  p.A = A; p.lda = K; p.W = W; p.ldw = K; p.bias = bias; p.C = C; p.ldc = N; p.residual = residual; p.ldr = N;
+  p.M = M; p.N = N; p.K = K; p.relu = relu;
+  if (ln_gamma) { p.prologue = PRO_LAYERNORM; p.pg = ln_gamma; p.pb = ln_beta; p.eps = 1e-6f; }
+  if (mode == ND_GEMM_SIMT_FP32) {
+    ND_LAUNCH(e, gemm_simt(p, st));
+    return ND_OK;
+  }
+  const char* why = "";
+  if (!gemm_tc_available(&why)) return fail(e, ND_ERR_CUDA, why);
+  float *hi = nullptr, *lo = nullptr;
+  if (mode == ND_GEMM_TC_3XTF32) {
+    // split on the host (test path only)
+    std::vector<float> w((size_t)N * K), h((size_t)N * K), l((size_t)N * K);
+    ND_CUDA(e, cudaMemcpy(w.data(), W, w.size() * sizeof(float), cudaMemcpyDefault));
+    split_tf32_host(w.data(), h.data(), l.data(), w.size());
+    ND_CUDA(e, cudaMalloc(&hi, w.size() * sizeof(float)));
+    ND_CUDA(e, cudaMalloc(&lo, w.size() * sizeof(float)));
+    ND_CUDA(e, cudaMemcpy(hi, h.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ND_CUDA(e, cudaMemcpy(lo, l.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    p.W = hi; p.W_lo = lo;
+  }
+  ++e->launches;
+  cudaError_t err = gemm_tc(p, mode == ND_GEMM_TC_3XTF32 ? 3 : 1, st);
+  cudaError_t err2 = cudaStreamSynchronize(st);
+  if (hi) cudaFree(hi);
+  if (lo) cudaFree(lo);
+  if (err != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, cudaGetErrorString(err)); }
+  if (err2 != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, cudaGetErrorString(err2)); }
+  return ND_OK;
+}
+
+}  // extern "C"

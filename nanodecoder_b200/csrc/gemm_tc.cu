@@ -304,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float x = v[j];
             if (p.bias) x += __ldg(p.bias + n);
             if (n < p.div_ncols) x = x / p.div_by;
-            if (p.relu) x = fmaxf(x, 0.f);
+            if (p.relu == 1) x = fmaxf(x, 0.f); else if (p.relu == 2) x = tanhf(x);
             v[j] = x;
           }
         }

@@ -1,0 +1,144 @@
+// Launchers of the non-GEMM kernels (attention, normalisation, token selection, front end).
+#pragma once
+#include "common.cuh"
+
+namespace nd {
+
+// ---------------------------------------------------------------------------------------------
+// Decode-step cross attention over the per-chunk projected memory (decoder/transformer.py:87-91,
+// onmt/modules/multi_headed_attn.py:142-190).  One CTA per chunk; the NQ query rows of a chunk
+// (1 for greedy, beam_size for beam search) share one pass over K and V.
+struct CrossAttnParams {
+  const float* q = nullptr;  int64_t q_ld = 0;    // [n_chunks*NQ, d] already divided by sqrt(dh)
+  const float* K = nullptr;                       // [n_chunks, T, *] row stride kv_ld
+  const float* V = nullptr;
+  int64_t kv_ld = 0;
+  const float* src = nullptr;                     // [n_chunks, src_ld]: key t masked iff src == mask_value
+  int64_t src_ld = 0;
+  float mask_value = 1.0f;
+  const int* retired = nullptr;                   // optional [n_chunks]: non-zero -> skip the chunk
+  float* ctx = nullptr;      int64_t ctx_ld = 0;  // [n_chunks*NQ, d]
+  float* attn = nullptr;                          // optional [n_chunks*NQ, T]: head-0 probabilities
+  int n_chunks = 0, NQ = 1, T = 0, d = 0, H = 8;
+};
+cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream);
+
+// Decode-step self attention with a device-resident KV cache (decoder/transformer.py:76-80,
+// multi_headed_attn.py:126-141).  qkv holds this step's [q/sqrt(dh) | k | v]; k and v are appended
+// to the cache at position `step`.  With beam search the history of row r at position j lives in
+// cache row anc[r*anc_ld + j] (parent-pointer indirection instead of reordering the cache).
+struct SelfAttnParams {
+  const float* qkv = nullptr;                     // [rows, 3d]
+  float* Kc = nullptr; float* Vc = nullptr;       // [rows, Lmax, d]
+  const int* anc = nullptr; int anc_ld = 0;       // optional [rows, Lmax]
+  const int* retired = nullptr; int rows_per_chunk = 1;
+  float* ctx = nullptr;                           // [rows, d]
+  int rows = 0, d = 0, H = 8, Lmax = 0, step = 0;
+};
+cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream);
+
+// Encoder self attention over a whole chunk (encoder/transformer.py:50-52): qkv [B*T, 3d] with
+// q pre-divided by sqrt(dh); keys with src == 0.0 are masked (encoder/transformer.py:117-121).
+struct EncAttnParams {
+  const float* qkv = nullptr;
+  const float* src = nullptr;                     // [B, T]
+  float* ctx = nullptr;                           // [B*T, d]
+  int B = 0, T = 0, d = 0, H = 8;
+};
+cudaError_t encoder_attention(const EncAttnParams& p, cudaStream_t stream);
+
+// Bahdanau / "mlp" global attention, one decode step (onmt/modules/global_attention.py:123-136,
+// 180-194): score = v . tanh(wq + uh[t]); length mask; softmax; context = sum_t a[t] * mem[t].
+struct MlpAttnParams {
+  const float* wq = nullptr;                      // [n_chunks*NQ, d]  (Wq h + b)
+  const float* uh = nullptr;                      // [n_chunks, T, d]  (Uk mem, cached once per chunk); dot: keys
+  const float* mem = nullptr;                     // [n_chunks, T, d]
+  const float* v = nullptr;                       // [d]
+  const int64_t* lengths = nullptr;               // [n_chunks] memory lengths
+  const int* retired = nullptr;
+  float* ctx = nullptr; int64_t ctx_ld = 0;       // [n_chunks*NQ, *] context written at column 0
+  float* attn = nullptr;                          // optional [n_chunks*NQ, T]
+  int n_chunks = 0, NQ = 1, T = 0, d = 0;
+  int dot = 0;                                    // 1: score = q . mem[t] (general / dot attention)
+};
+cudaError_t mlp_attention(const MlpAttnParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+cudaError_t layernorm_rows(const float* x, const float* g, const float* b, float eps, float* y,
+                           int64_t M, int d, cudaStream_t stream);
+// x[row] = emb[tok[row]] (* sqrt(d) + pe(step) when pos_enc)
+cudaError_t embed_rows(const int* tok, const float* emb, float* x, int64_t x_ld, int rows, int d,
+                       int pos_enc, int step, cudaStream_t stream);
+// y[b,t,:] = w[:] * x[b,t] + bias[:]   (Linear(1,d): encoder/transformer.py:113, cnn_encoder.py:38)
+cudaError_t linear_in1(const float* x, const float* w, const float* bias, float* y, int64_t n, int d,
+                       cudaStream_t stream);
+// MaxPool1d(stride) over time: in [B,T,d] -> out [B,T/stride,d]   (encoder/nano_encoder.py:101-105)
+cudaError_t maxpool_time(const float* in, float* out, int B, int T, int d, int stride, cudaStream_t stream);
+cudaError_t fill_int(int* p, int n, int value, cudaStream_t stream);
+// out[t,b,:] = in[b,t,:]  (chunk-major -> reference time-major layout)
+cudaError_t transpose_bt(const float* in, float* out, int B, int T, int d, cudaStream_t stream);
+
+// Generator + token selection (models/model_builder.py:331-334, translate/translator.py:371-375,
+// 469-477): optional final LayerNorm, Linear(d,V), log_softmax; greedy argmax (lowest index on ties).
+struct GenParams {
+  const float* x = nullptr; int64_t x_ld = 0;     // [rows, d]
+  const float* ln_g = nullptr; const float* ln_b = nullptr; float eps = 1e-6f;   // null -> no LN
+  const float* Wg = nullptr; const float* bg = nullptr;                         // [V,d], [V]
+  float* logp = nullptr;                          // [rows, V] log-probs (always written)
+  int rows = 0, d = 0, V = 0;
+  // greedy extras (ids == nullptr -> skipped)
+  int64_t* ids = nullptr; int ids_ld = 0;         // ids[row*ids_ld + step]
+  float* scores = nullptr;                        // [rows] log-prob of the chosen token
+  int* next_tok = nullptr;                        // [rows] feeds the next step's embedding
+  float* trace = nullptr;                         // optional [rows, V] copy (per-step logits dump)
+  int step = 0, min_len = 0, eos = 3;
+};
+cudaError_t generator_step(const GenParams& p, cudaStream_t stream);
+
+// Beam step (translate/translator.py:714-762, 781-810): see beam.cu
+struct BeamState {
+  // all [B] / [B,K] device arrays owned by the engine
+  float* topk_log_probs = nullptr;                // [B,K]
+  int* alive_seq = nullptr;                       // [2][B*K, Lmax+1] double buffered
+  int* anc = nullptr;                             // [2][B*K, Lmax] self-attention ancestor slots
+  int* cur_tok = nullptr;                         // [B*K]
+  int* parent = nullptr;                          // [B*K] parent row of the current beams
+  int* retired = nullptr;                         // [B]
+  int* top_finished = nullptr;                    // [B]
+  int* n_hyp = nullptr;                           // [B] finished hypotheses seen so far
+  float* hyp_score = nullptr;                     // [B, n_best]
+  int* hyp_len = nullptr;                         // [B, n_best]
+  int* hyp_seq = nullptr;                         // [B, n_best, Lmax]
+  int* n_alive = nullptr;                         // [1] chunks not yet retired
+};
+struct BeamParams {
+  const float* logp = nullptr;                    // [B*K, V]
+  BeamState st;
+  int B = 0, K = 0, V = 0, Lmax = 0, step = 0, max_len = 0, min_len = 0, n_best = 1, eos = 3;
+  float alpha = 0.f;
+};
+cudaError_t beam_init(const BeamParams& p, int bos, cudaStream_t stream);
+cudaError_t beam_step(const BeamParams& p, cudaStream_t stream);
+cudaError_t beam_finalize(const BeamParams& p, int64_t* out_ids, int* out_lens, float* out_scores,
+                          cudaStream_t stream);
+// reorder per-row recurrent state by parent: dst[r] = src[parent[r]]  (rows of `width` floats)
+cudaError_t gather_rows(const float* src, float* dst, const int* parent, int rows, int width,
+                        cudaStream_t stream);
+
+// LSTMCell pointwise (onmt/models/stacked_rnn.py:25-31): gates [rows,4d] (= x.W_ih^T+b_ih + h.W_hh^T+b_hh)
+cudaError_t lstm_cell_pointwise(const float* gates_a, const float* gates_b, const float* c_in,
+                                float* h_out, float* c_out, int rows, int d, cudaStream_t stream);
+// out = (x + a * sigmoid(g)) * sqrt(0.5) with y = [a | g] rows of 2d   (onmt/utils/cnn_factory.py:31-34,52-53)
+cudaError_t glu_residual(const float* y, const float* x, float* out, float* glu_out, int64_t rows, int d,
+                         cudaStream_t stream);
+// im2col over time for a (k x 1) convolution: A[(b,t)][j*d + c] = x[b][t + j - left][c] (0 outside [0,T))
+cudaError_t im2col_time(const float* x, float* A, int B, int T, int d, int k, int left, cudaStream_t stream);
+
+// Front end (utils/labelop.py:219-233): see frontend.cu
+cudaError_t frontend_stats(const int16_t* signal, const int64_t* offsets, int n_reads, int mode,
+                           double* center, double* scale, cudaStream_t stream);
+cudaError_t frontend_chunks(const int16_t* signal, const int64_t* offsets, const double* center,
+                            const double* scale, const int32_t* chunk_read, const int64_t* chunk_start,
+                            int n_chunks, int chunk_len, float* out, int64_t* out_len, cudaStream_t stream);
+
+}  // namespace nd

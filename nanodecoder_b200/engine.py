@@ -1,0 +1,163 @@
+"""Python handle on the CUDA engine: PyTorch owns the buffers and the stream, libnanodec does the work.
+
+Mirrors the model protocol the reference's Translator drives
+(``model.encoder`` / ``model.decoder`` / ``model.generator``, translate/translator.py:419-421,
+550-551, 584-591) at batch granularity: ``encode`` then ``decode_greedy`` / ``decode_beam``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .config import ModelConfig
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine(object):
+    def __init__(self, cfg: ModelConfig, state_dict: Dict[str, torch.Tensor], max_batch: int,
+                 max_src_len: int = 512, max_tgt_len: int = 100, max_beam: int = 1,
+                 gemm_mode: str = "3xtf32", device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("nanodecoder_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.max_batch, self.max_src_len, self.max_tgt_len, self.max_beam = max_batch, max_src_len, max_tgt_len, max_beam
+        self.gemm_mode = gemm_mode
+        c = _lib.NdConfig()
+        c.api_version = _lib.ND_API_VERSION
+        c.device = device
+        c.encoder_type = _lib.ENC[cfg.encoder_type]
+        c.decoder_type = _lib.DEC[cfg.decoder_type]
+        c.enc_layers, c.dec_layers = cfg.enc_layers, cfg.dec_layers
+        c.d_model, c.heads, c.d_ff, c.vocab_size = cfg.d_model, cfg.heads, cfg.d_ff, cfg.vocab_size
+        c.cnn_kernel_width = cfg.cnn_kernel_width
+        for i in range(8):
+            c.enc_pooling[i] = cfg.enc_pooling[i] if i < len(cfg.enc_pooling) else 1
+        c.input_feed = int(cfg.input_feed)
+        c.attn_type = _lib.ATTN[cfg.global_attention]
+        c.position_encoding = int(cfg.position_encoding)
+        c.max_batch, c.max_src_len, c.max_tgt_len, c.max_beam = max_batch, max_src_len, max_tgt_len, max_beam
+        c.gemm_mode = _lib.GEMM[gemm_mode]
+        self._h = C.c_void_p()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            rc = self.lib.nd_create(C.byref(c), C.byref(self._h))
+        if rc != 0:
+            raise _lib.NanodecError(rc, self.lib.nd_last_error(None).decode())
+        for name, t in state_dict.items():
+            if not torch.is_floating_point(t):
+                continue
+            t = t.detach().to(torch.float32).contiguous()
+            shape = (C.c_int64 * max(1, t.dim()))(*t.shape)
+            self._check(self.lib.nd_load_weight(self._h, name.encode(), _ptr(t), shape, t.dim(), _lib.DTYPE_F32))
+        self._check(self.lib.nd_finalize_weights(self._h))
+        self._B = 0
+        self._Tp = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.NanodecError(rc, self.lib.nd_last_error(self._h).decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.nd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.nd_launch_count(self._h))
+
+    def reset_launch_count(self):
+        self.lib.nd_reset_launch_count(self._h)
+
+    # ------------------------------------------------------------------------------------------
+    def encode(self, src: torch.Tensor, lengths: torch.Tensor) -> None:
+        """src [B,T] fp32 chunk-major zero padded, lengths [B] int64 — both on this device."""
+        assert src.is_cuda and lengths.is_cuda and src.dtype == torch.float32 and lengths.dtype == torch.int64
+        src = src.contiguous()
+        B, T = src.shape
+        self._check(self.lib.nd_encode(self._h, _ptr(src), _ptr(lengths), B, T, self._stream()))
+        self._B = B
+
+    def memory_bank(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (memory_bank [T',B,d] in the reference layout, memory lengths [B])."""
+        tp = C.c_int32(0)
+        self._check(self.lib.nd_get_memory_bank(self._h, C.c_void_p(0), C.c_void_p(0), C.byref(tp), self._stream()))
+        out = torch.empty((tp.value, self._B, self.cfg.d_model), dtype=torch.float32, device=self.device)
+        lens = torch.empty((self._B,), dtype=torch.int64, device=self.device)
+        self._check(self.lib.nd_get_memory_bank(self._h, _ptr(out), _ptr(lens), C.byref(tp), self._stream()))
+        return out, lens
+
+    def decode_greedy(self, max_len: int = 100, min_len: int = 0, return_attn: bool = False,
+                      return_logits: bool = False):
+        """-> dict(ids [B,L] int64, scores [B], attn [L,B,T'] | None, logits [L,B,V] | None)"""
+        B = self._B
+        ids = torch.empty((B, max_len), dtype=torch.int64, device=self.device)
+        scores = torch.empty((B,), dtype=torch.float32, device=self.device)
+        attn = logits = None
+        if return_attn:
+            tp = C.c_int32(0)
+            self._check(self.lib.nd_get_memory_bank(self._h, C.c_void_p(0), C.c_void_p(0), C.byref(tp), self._stream()))
+            attn = torch.empty((max_len, B, tp.value), dtype=torch.float32, device=self.device)
+        if return_logits:
+            logits = torch.empty((max_len, B, self.cfg.vocab_size), dtype=torch.float32, device=self.device)
+        self._check(self.lib.nd_decode_greedy(self._h, max_len, min_len, _ptr(ids), _ptr(scores), _ptr(attn),
+                                              _ptr(logits), self._stream()))
+        return {"ids": ids, "scores": scores, "attn": attn, "logits": logits}
+
+    def decode_beam(self, beam_size: int = 5, n_best: int = 1, max_len: int = 100, min_len: int = 0,
+                    alpha: float = 0.0):
+        """-> dict(ids [B,n_best,L] int64 (-1 padded), lens [B,n_best] int32, scores [B,n_best])"""
+        B = self._B
+        ids = torch.empty((B, n_best, max_len), dtype=torch.int64, device=self.device)
+        lens = torch.empty((B, n_best), dtype=torch.int32, device=self.device)
+        scores = torch.empty((B, n_best), dtype=torch.float32, device=self.device)
+        self._check(self.lib.nd_decode_beam(self._h, beam_size, n_best, max_len, min_len, float(alpha),
+                                            _ptr(ids), _ptr(lens), _ptr(scores), self._stream()))
+        return {"ids": ids, "lens": lens, "scores": scores}
+
+    # ------------------------------------------------------------------------------------------
+    def frontend_stats(self, signal: torch.Tensor, offsets: torch.Tensor, normalization: str = "median"):
+        """signal int16 [N_total] (device), offsets int64 [n_reads+1] (device) -> (center, scale) fp64"""
+        assert signal.dtype == torch.int16 and offsets.dtype == torch.int64 and signal.is_cuda and offsets.is_cuda
+        n = offsets.numel() - 1
+        center = torch.empty((n,), dtype=torch.float64, device=self.device)
+        scale = torch.empty((n,), dtype=torch.float64, device=self.device)
+        self._check(self.lib.nd_frontend_stats(self._h, _ptr(signal), _ptr(offsets), n, _lib.NORM[normalization],
+                                               _ptr(center), _ptr(scale), self._stream()))
+        return center, scale
+
+    def frontend_chunks(self, signal, offsets, center, scale, chunk_read, chunk_start, chunk_len: int):
+        n = chunk_read.numel()
+        out = torch.empty((n, chunk_len), dtype=torch.float32, device=self.device)
+        lens = torch.empty((n,), dtype=torch.int64, device=self.device)
+        self._check(self.lib.nd_frontend_chunks(self._h, _ptr(signal), _ptr(offsets), _ptr(center), _ptr(scale),
+                                                _ptr(chunk_read), _ptr(chunk_start), n, chunk_len, _ptr(out),
+                                                _ptr(lens), self._stream()))
+        return out, lens
+
+    def test_gemm(self, mode: str, A, W, bias=None, residual=None, ln=None, relu=0):
+        M, K = A.shape
+        N = W.shape[0]
+        Cout = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        g, b = (ln if ln is not None else (None, None))
+        self._check(self.lib.nd_test_gemm(self._h, _lib.GEMM[mode], _ptr(A), _ptr(W), _ptr(bias), _ptr(residual),
+                                          _ptr(g), _ptr(b), _ptr(Cout), M, N, K, relu, self._stream()))
+        return Cout

@@ -1,0 +1,194 @@
+"""Translator: same surface as the reference's translate/translator.py (build_translator :65-90,
+Translator.translate :181-369, translate_batch :505-540, setAttnFile :178-179), backed by the CUDA
+engine instead of PyTorch modules.
+
+Dispatch (translator.py:521-540): beam_size == 1 -> greedy; ``fast`` -> batched beam search;
+otherwise the object-per-chunk beam (`_translate_batch`), which this engine does not implement on
+the device yet and therefore refuses loudly (there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import math
+import os
+from itertools import count
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ..checkpoint import load_checkpoint
+from ..config import EOS
+from ..engine import Engine
+from ..inputters.nano_dataset import batch_order, parse_segments
+from .translation import TranslationBuilder
+
+
+class _Field(object):
+    def __init__(self, vocab):
+        self.vocab = vocab
+        self.init_token, self.eos_token, self.pad_token, self.unk_token = "<s>", "</s>", "<blank>", "<unk>"
+
+
+class _Batch(object):
+    """What the reference's torchtext Batch exposes to the translator (translator.py:413,543,549;
+    translation.py:53-64)."""
+
+    def __init__(self, src, src_lengths, indices):
+        self.src = src                    # [T,B,1] fp32 (device)
+        self.src_lengths = src_lengths    # [B] int64
+        self.indices = indices            # [B] int64 positions in the original order
+        self.batch_size = src.size(1)
+
+
+class _Data(object):
+    data_type = "nano"
+    examples = None
+
+
+class GNMTGlobalScorer(object):
+    """alpha / beta holder (onmt/translate/beam.py:181-242); only alpha is used by --fast."""
+
+    def __init__(self, opt):
+        self.alpha = opt.alpha
+        self.beta = opt.beta
+
+
+def build_translator(opt, report_score=False, logger=None, out_file=None):
+    """translate/translator.py:65-90.  ``opt`` comes from nanodecoder_b200.opts.translate_opts."""
+    if len(opt.models) != 1:
+        raise ValueError("ensemble decoding (several -model files) is outside the supported translate path")
+    if logger:
+        logger.info("Loading model...")
+    cfg, sd, vocab = load_checkpoint(opt.models[0])
+    return Translator.from_state(cfg, sd, vocab, opt, report_score=report_score, logger=logger)
+
+
+class Translator(object):
+    def __init__(self, model: Engine, fields, opt, model_opt, global_scorer=None, report_score=False, logger=None):
+        self.model = model
+        self.fields = fields
+        self.gpu = opt.gpu
+        self.cuda = True
+        self.n_best = opt.n_best
+        self.max_length = opt.max_length
+        self.beam_size = opt.beam_size
+        self.min_length = opt.min_length
+        self.fast = opt.fast
+        self.data_type = getattr(opt, "data_type", "nano")
+        self.verbose = opt.verbose
+        self.global_scorer = global_scorer if global_scorer is not None else GNMTGlobalScorer(opt)
+        self.report_score = report_score
+        self.logger = logger
+        self.out_file_attn = None
+        self.model_opt = model_opt
+        if opt.random_sampling_topk != 1:
+            raise ValueError("random sampling (topk != 1) is outside the supported translate path")
+        if opt.block_ngram_repeat != 0 or opt.dump_beam or opt.replace_unk:
+            raise ValueError("block_ngram_repeat / dump_beam / replace_unk are outside the supported translate path")
+        if self.beam_size > 1 and self.global_scorer.beta != 0:
+            raise ValueError("coverage penalty (beta != 0) is not supported by the fast beam search")
+
+    @classmethod
+    def from_state(cls, cfg, state_dict, vocab, opt, report_score=False, logger=None):
+        engine = Engine(cfg, state_dict, max_batch=opt.batch_size, max_src_len=opt.src_seq_length,
+                        max_tgt_len=opt.max_length, max_beam=max(1, opt.beam_size),
+                        gemm_mode=getattr(opt, "gemm_mode", "3xtf32"), device=max(0, opt.gpu))
+        return cls(engine, {"tgt": _Field(vocab)}, opt, cfg, report_score=report_score, logger=logger)
+
+    def setAttnFile(self, out_file_attn):
+        self.out_file_attn = out_file_attn
+
+    # --------------------------------------------------------------------------------------
+    def translate(self, src, tgt=None, src_dir=None, batch_size=None, attn_debug=False):
+        """src: list of space separated float strings (the reference's format), or a
+        ``(chunks [n,T] fp32, lengths [n] int64)`` tuple of host or device tensors.
+        -> (all_scores, all_predictions) in input order; all_predictions[i] is a list of n_best
+        space-joined token strings (translator.py:271-273)."""
+        assert src is not None
+        if batch_size is None:
+            raise ValueError("batch_size must be set")
+        if tgt is not None:
+            raise ValueError("gold scoring (tgt) is outside the supported translate path")
+        if isinstance(src, tuple):
+            chunks, lengths = src
+        else:
+            chunks, lengths = parse_segments(src)
+        n = chunks.size(0)
+        dev = self.model.device
+        host_lengths = lengths.cpu().numpy()
+        if not chunks.is_cuda:
+            chunks = chunks.pin_memory().to(dev, non_blocking=True)      # ONE host->device copy per read
+        lengths_d = lengths.to(dev, non_blocking=True)
+        builder = TranslationBuilder(_Data(), self.fields, self.n_best)
+        all_scores: List = [None] * n
+        all_predictions: List = [None] * n
+        counter = count(1)
+        pred_score_total, pred_words_total = 0.0, 0
+        for idx in batch_order(host_lengths, batch_size):
+            idx_t = torch.from_numpy(idx).to(dev)
+            T = int(host_lengths[idx].max())
+            b_src = chunks.index_select(0, idx_t)[:, :T].t().contiguous().unsqueeze(2)       # [T,B,1]
+            batch = _Batch(b_src, lengths_d.index_select(0, idx_t), torch.arange(len(idx)))
+            batch_data = self.translate_batch(batch, _Data(), attn_debug, fast=self.fast)
+            for j, trans in enumerate(builder.from_batch(batch_data)):
+                i = int(idx[j])
+                all_scores[i] = trans.pred_scores[: self.n_best]
+                pred_score_total += float(trans.pred_scores[0])
+                pred_words_total += len(trans.pred_sents[0])
+                all_predictions[i] = [" ".join(p) for p in trans.pred_sents[: self.n_best]]
+                if self.verbose:
+                    out = trans.log(next(counter))
+                    (self.logger.info(out) if self.logger else os.write(1, out.encode("utf-8")))
+                if attn_debug and self.out_file_attn is not None and trans.attns is not None:
+                    rows = trans.attns[0].tolist()
+                    self.out_file_attn.write("\n".join(" ".join("%8.5f" % v for v in r) for r in rows) + "\n")
+        if self.report_score:
+            msg = self._report_score("PRED", pred_score_total, pred_words_total)
+            (self.logger.info(msg) if self.logger else print(msg))
+        return all_scores, all_predictions
+
+    # --------------------------------------------------------------------------------------
+    def translate_batch(self, batch, data, attn_debug, fast=False):
+        """translator.py:505-540.  batch.src [T,B,1] (any device), batch.src_lengths [B].
+        -> {"predictions": [[LongTensor]*n_best]*B, "scores", "attention", "batch", "gold_score"}"""
+        eng = self.model
+        src = batch.src.to(eng.device)[:, :, 0].t().contiguous()           # chunk-major [B,T]
+        lengths = batch.src_lengths.to(eng.device, dtype=torch.int64)
+        B = src.size(0)
+        eng.encode(src, lengths)
+        results = {"batch": batch, "gold_score": [0] * B}
+        if self.beam_size == 1:
+            out = eng.decode_greedy(self.max_length, self.min_length, return_attn=attn_debug)
+            ids = out["ids"].cpu()                                        # the one device->host read
+            scores = out["scores"].cpu()
+            attn = out["attn"].cpu() if out["attn"] is not None else None
+            mlen = eng.memory_bank()[1].cpu() if attn is not None else None
+            results["predictions"] = [[ids[i]] for i in range(B)]
+            results["scores"] = [[scores[i]] for i in range(B)]
+            results["attention"] = [[attn[:, i, : int(mlen[i])]] if attn is not None else [[]] for i in range(B)]
+            return results
+        if not fast:
+            raise NotImplementedError(
+                "object beam search (beam_size > 1 without --fast, translator.py:827-926) is not implemented "
+                "by the CUDA engine; pass --fast")
+        out = eng.decode_beam(self.beam_size, self.n_best, self.max_length, self.min_length,
+                              self.global_scorer.alpha)
+        ids, lens, scores = out["ids"].cpu(), out["lens"].cpu(), out["scores"].cpu()
+        results["predictions"] = [[ids[i, n, : int(lens[i, n])] for n in range(self.n_best)] for i in range(B)]
+        results["scores"] = [[scores[i, n] for n in range(self.n_best)] for i in range(B)]
+        results["attention"] = [[[] for _ in range(self.n_best)] for _ in range(B)]
+        return results
+
+    def _report_score(self, name, score_total, words_total):
+        if words_total == 0:
+            return "%s No words predicted" % (name,)
+        return "%s AVG SCORE: %.4f, %s PPL: %.4f" % (name, score_total / words_total, name,
+                                                     math.exp(-score_total / words_total))
+
+
+def count_bases(ids: torch.Tensor) -> int:
+    """bases = tokens emitted before the first </s> of each row (what translate.py:85-95 reports as
+    len(c_bpread) when stride == length)."""
+    is_eos = ids.eq(EOS)
+    first = torch.where(is_eos.any(1), is_eos.float().argmax(1), torch.full_like(ids[:, 0], ids.size(1)))
+    return int(first.sum())

@@ -1,0 +1,112 @@
+"""GPU: unit parity of the individual CUDA kernels, called through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, rel_err
+from nanodecoder_b200 import synth
+from nanodecoder_b200.config import ModelConfig
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small_engine():
+    from nanodecoder_b200.engine import Engine
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    return Engine(cfg, synth.make_state_dict(cfg), max_batch=8, max_src_len=128, max_tgt_len=8, gemm_mode="simt")
+
+
+SHAPES = [(128, 128, 256), (1024, 768, 256), (1024, 256, 2048), (300, 200, 96), (77, 64, 64), (4096, 1024, 256),
+          (5, 8, 32), (130, 2048, 256)]
+
+
+@pytest.mark.parametrize("mode,tol", [("simt", 2e-6), ("3xtf32", 5e-6), ("tf32", 3e-3)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_plain(small_engine, mode, tol, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    C = small_engine.test_gemm(mode, A, W, bias=bias)
+    torch.cuda.synchronize()
+    ref = (A.double() @ W.double().t() + bias.double())
+    assert rel_err(C, ref) < tol, (mode, M, N, K, rel_err(C, ref))
+
+
+@pytest.mark.parametrize("mode,tol", [("simt", 3e-6), ("3xtf32", 6e-6), ("tf32", 3e-3)])
+def test_gemm_layernorm_relu_residual(small_engine, mode, tol):
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 1000, 512, 256
+    A = (torch.randn(M, K, generator=g) * 2 + 0.5).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    gam = (1 + 0.1 * torch.randn(K, generator=g)).cuda()
+    bet = (0.1 * torch.randn(K, generator=g)).cuda()
+    C = small_engine.test_gemm(mode, A, W, bias=bias, residual=res, ln=(gam, bet), relu=1)
+    torch.cuda.synchronize()
+    An = torch.nn.functional.layer_norm(A.double(), (K,), gam.double(), bet.double(), 1e-6)
+    ref = torch.relu(An @ W.double().t() + bias.double()) + res.double()
+    assert rel_err(C, ref) < tol, rel_err(C, ref)
+
+
+def test_frontend_bit_exact_vs_oracle_and_reference_golden(small_engine):
+    from oracle import frontend as ofe
+    from nanodecoder_b200.inputters.nano_dataset import SignalFrontend
+    g = np.load(GOLDEN + "/frontend.npz")
+    reads = [g["raw_%d" % i] for i in range(int(g["n_reads"]))]
+    reads += synth.make_raw_reads(5, seed=3, min_len=3000, max_len=60000)
+    reads.append(np.full(40, 7, dtype=np.int16) + np.arange(40, dtype=np.int16) % 3)
+    for norm in ("median", "mean"):
+        for (L, S) in ((512, 512), (300, 60)):
+            fe = SignalFrontend(small_engine, norm, L, S)
+            chunks, lens, cread = fe(reads)
+            torch.cuda.synchronize()
+            chunks, lens = chunks.cpu().numpy(), lens.cpu().numpy()
+            pos = 0
+            for ri, raw in enumerate(reads):
+                want = ofe.frontend(raw, norm, L, S)
+                for w in want:
+                    assert cread[pos] == ri and lens[pos] == len(w)
+                    got = chunks[pos, : len(w)]
+                    if norm == "median":
+                        np.testing.assert_array_equal(got, w)            # bit exact
+                    else:                                                # std: exact-integer vs pairwise fp64 sums
+                        assert np.max(np.abs(got.view(np.int32) - w.view(np.int32))) <= 1
+                    assert not chunks[pos, len(w):].any()
+                    pos += 1
+            assert pos == len(lens)
+    # the reference's own golden output for read 0 (median, 512/512)
+    fe = SignalFrontend(small_engine, "median", 512, 512)
+    chunks, lens, _ = fe([reads[0]])
+    flat = np.concatenate([chunks[i, : int(lens[i])].cpu().numpy() for i in range(len(lens))])
+    want = g["r0_median_512_512_flat"]
+    np.testing.assert_array_equal(flat if flat.size < 6000 else flat[::7], want)
+
+
+@pytest.mark.parametrize("mode", ["simt", "3xtf32"])
+@pytest.mark.parametrize("d", [64, 256])
+def test_nano_encoder_vs_oracle(d, mode):
+    """LSTM recurrence kernel (+ input projection GEMMs, BN prologue, W) against the fp32 oracle."""
+    from nanodecoder_b200.engine import Engine
+    from oracle.model import OracleModel
+    cfg = ModelConfig.family("l2t", d_model=d, d_ff=128, enc_layers=3, dec_layers=1)
+    sd = synth.make_state_dict(cfg)
+    B, T = 21, 160
+    chunks, lengths = synth.make_chunks(B, T=T, seed=3, ragged=True, read_len=2)
+    lengths[0] = T
+    lengths[5] = 1
+    chunks[5, 1:] = 0
+    eng = Engine(cfg, sd, max_batch=B, max_src_len=T, max_tgt_len=4, gemm_mode=mode)
+    eng.encode(chunks.cuda(), lengths.cuda())
+    mb, lens = eng.memory_bank()
+    torch.cuda.synchronize()
+    om = OracleModel(sd, cfg)
+    with torch.no_grad():
+        _, want, wl = om.encoder(chunks.t().contiguous().unsqueeze(2), lengths)
+    assert torch.equal(lens.cpu(), wl)
+    assert mb.shape == want.shape
+    err = rel_err(mb.cpu(), want)
+    assert err < 1e-3, err
+    print("nano encoder d=%d rel err %.2e" % (d, err))

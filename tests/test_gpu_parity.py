@@ -1,0 +1,165 @@
+"""GPU: end-to-end parity of the CUDA translate path (through the C ABI) against
+  (1) the golden vectors produced by the unmodified reference (tests/golden, oracle/make_golden.py),
+  (2) the fp32 oracle port on fresh seeded inputs (ragged lengths, other batch sizes), and
+  (3) size-independent properties at the BASELINE batch size (B = 1024).
+Tolerance (BASELINE.json north_star): encoder outputs and per-step logits within 1e-3 relative in
+fp32 mode; greedy token sequences identical; beam outputs identical except for exact score ties."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, rel_err
+from nanodecoder_b200 import synth
+from nanodecoder_b200.config import ModelConfig
+
+pytestmark = pytest.mark.gpu
+
+IMPLEMENTED = ["l2t_d256", "t2t_d256", "nano2rnn_d256", "brnn2rnn_d256", "l2t_d64", "t2t_d64", "t2t_d512_6x6"]
+TOL = 1e-3
+
+
+def _engine(cfg, sd, B, T, L, K=1, mode="3xtf32"):
+    from nanodecoder_b200.engine import Engine
+    return Engine(cfg, sd, max_batch=B, max_src_len=T, max_tgt_len=L, max_beam=K, gemm_mode=mode)
+
+
+@pytest.mark.parametrize("mode", ["3xtf32", "simt"])
+@pytest.mark.parametrize("name", IMPLEMENTED)
+def test_greedy_matches_reference_golden(name, mode):
+    if mode == "simt" and name not in ("l2t_d64", "t2t_d64", "l2t_d256"):
+        pytest.skip("simt cross-check only on a subset")
+    g, cfg, sd, src, lengths = load_golden(name)
+    B, T, L = src.shape[0], src.shape[1], int(g["max_length"])
+    eng = _engine(cfg, sd, B, T, L, mode=mode)
+    eng.encode(src.cuda(), lengths.cuda())
+    mb, mlen = eng.memory_bank()
+    out = eng.decode_greedy(L, return_logits=True)
+    torch.cuda.synchronize()
+    # encoder
+    assert list(mb.shape) == list(g["memory_shape"])
+    np.testing.assert_array_equal(mlen.cpu().numpy(), g["memory_lengths"])
+    sample = mb.flatten()[::97].cpu()
+    want = torch.from_numpy(g["memory_sample"])
+    e_mb = float((sample - want).abs().max() / want.abs().max())
+    # per-step logits
+    steps = [int(s) for s in g["logit_steps"]]
+    got = out["logits"][steps].cpu()
+    wl = torch.from_numpy(g["logits"])
+    same_prefix = torch.from_numpy(g["greedy_ids"]).eq(out["ids"].cpu()).all(1)
+    e_lg = float((got - wl).abs().max() / wl.abs().max())
+    ids_equal = bool(same_prefix.all())
+    print("%s[%s]: memory rel err %.2e, logits rel err %.2e, greedy identical %s" % (name, mode, e_mb, e_lg, ids_equal))
+    assert e_mb < TOL
+    assert e_lg < TOL
+    np.testing.assert_array_equal(out["ids"].cpu().numpy(), g["greedy_ids"])
+    np.testing.assert_allclose(out["scores"].cpu().numpy(), g["greedy_scores"], atol=2e-3)
+
+
+@pytest.mark.parametrize("name", ["l2t_d256", "t2t_d64", "nano2rnn_d256", "brnn2rnn_d256", "l2t_d64", "t2t_d256"])
+def test_beam_matches_reference_golden(name):
+    g, cfg, sd, src, lengths = load_golden(name)
+    B, T, L, K = src.shape[0], src.shape[1], int(g["max_length"]), int(g["beam_size"])
+    eng = _engine(cfg, sd, B, T, L, K=K)
+    eng.encode(src.cuda(), lengths.cuda())
+    out = eng.decode_beam(K, 1, L)
+    torch.cuda.synchronize()
+    ids, lens, scores = out["ids"].cpu().numpy(), out["lens"].cpu().numpy(), out["scores"].cpu().numpy()
+    for i in range(B):
+        want = g["beam_ids"][i]
+        want = want[want >= 0]
+        np.testing.assert_array_equal(ids[i, 0, : lens[i, 0]], want)
+        assert (ids[i, 0, lens[i, 0]:] == -1).all()
+    np.testing.assert_allclose(scores[:, 0], g["beam_scores"], atol=5e-3)
+
+
+@pytest.mark.parametrize("family", ["l2t", "t2t", "nano2rnn"])
+def test_greedy_and_beam_vs_oracle_ragged(family):
+    """Fresh seeded inputs, ragged lengths incl. very short chunks, d=64 (oracle runs in seconds)."""
+    from oracle import decode as od
+    from oracle.model import OracleModel
+    cfg = ModelConfig.family(family, d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    sd = synth.make_state_dict(cfg, seed=11)
+    B, T, L, K = 33, 200, 40, 4
+    chunks, lengths = synth.make_chunks(B, T=T, seed=77, ragged=True, read_len=3)
+    lengths[-1] = 3
+    chunks[-1, 3:] = 0
+    order = torch.argsort(lengths, descending=True, stable=True)
+    chunks, lengths = chunks[order], lengths[order]
+    eng = _engine(cfg, sd, B, T, L, K=K)
+    eng.encode(chunks.cuda(), lengths.cuda())
+    gr = eng.decode_greedy(L, return_logits=True, return_attn=True)
+    bm = eng.decode_beam(K, 2, L)
+    torch.cuda.synchronize()
+    om = OracleModel(sd, cfg)
+    s = chunks.t().contiguous().unsqueeze(2)
+    trace = []
+    og = od.greedy(om, s, lengths, max_length=L, trace_logits=trace, return_attention=True)
+    assert torch.equal(gr["ids"].cpu(), og["predictions"])
+    assert rel_err(gr["logits"].cpu(), torch.stack(trace)) < TOL
+    att = gr["attn"].cpu()
+    assert float((att - og["attention"]).abs().max()) < 1e-4
+    ob = od.beam_fast(om, s, lengths, beam_size=K, max_length=L, n_best=2)
+    ids, lens, sc = bm["ids"].cpu(), bm["lens"].cpu(), bm["scores"].cpu()
+    mism = 0
+    for i in range(B):
+        for n in range(2):
+            if not torch.equal(ids[i, n, : int(lens[i, n])], ob["predictions"][i][n]):
+                mism += 1
+            else:
+                assert abs(float(sc[i, n]) - ob["scores"][i][n]) < 5e-3
+    assert mism == 0, "%d of %d beam hypotheses differ" % (mism, 2 * B)
+
+
+def test_min_length_suppresses_eos():
+    g, cfg, sd, src, lengths = load_golden("l2t_d64")
+    B, T = src.shape
+    eng = _engine(cfg, sd, B, T, 30)
+    eng.encode(src.cuda(), lengths.cuda())
+    ids = eng.decode_greedy(30, min_len=30)["ids"]
+    assert not bool(ids.eq(3).any())
+
+
+def test_full_batch_properties_l2t_1024():
+    """BASELINE size (B=1024, T=512, L=100, d=256): batch invariance + duplicate consistency."""
+    cfg = ModelConfig.family("l2t")
+    sd = synth.make_state_dict(cfg)
+    B, T, L = 1024, 512, 100
+    chunks, lengths = synth.make_chunks(B, T=T, seed=5, ragged=True, read_len=16)
+    chunks[512:520] = chunks[0:8]                       # duplicates must decode identically
+    lengths[512:520] = lengths[0:8]
+    eng = _engine(cfg, sd, B, T, L)
+    eng.encode(chunks.cuda(), lengths.cuda())
+    full = eng.decode_greedy(L)["ids"].cpu()
+    assert torch.equal(full[512:520], full[0:8])
+    eng.encode(chunks[:24].cuda(), lengths[:24].cuda())
+    part = eng.decode_greedy(L)["ids"].cpu()
+    assert torch.equal(part, full[:24])                 # result of a chunk does not depend on its batch
+    hist = torch.bincount(full.flatten(), minlength=8).float()
+    p = hist / hist.sum()
+    assert float(-(p[p > 0] * p[p > 0].log2()).sum()) > 1.2
+    assert len({tuple(r.tolist()) for r in full[:64]}) > 32
+
+
+def test_translator_api_drop_in(tmp_path):
+    """build_translator / Translator.translate with the reference's argument conventions."""
+    from nanodecoder_b200 import checkpoint
+    from nanodecoder_b200.opts import default_translate_opt
+    from nanodecoder_b200.translate.translator import build_translator
+    from oracle import decode as od
+    from oracle.model import OracleModel
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    path = str(tmp_path / "m.pt")
+    checkpoint.save_checkpoint(synth.make_checkpoint(cfg, seed=3), path)
+    chunks, lengths = synth.make_chunks(11, T=128, seed=9, ragged=True, read_len=4)
+    segs = [" ".join(str(float(v)) for v in chunks[i, : int(lengths[i])]) for i in range(11)]
+    opt = default_translate_opt(models=[path], beam_size=1, batch_size=4, max_length=20, src_seq_length=128, gpu=0)
+    tr = build_translator(opt, report_score=False, logger=None)
+    scores, preds = tr.translate(src=segs, tgt=None, src_dir="", batch_size=4, attn_debug=False)
+    assert len(preds) == 11 and all(len(p) == 1 for p in preds)
+    sd = synth.make_state_dict(cfg, seed=3)
+    om = OracleModel(sd, cfg)
+    for i in range(11):
+        n = int(lengths[i])
+        o = od.greedy(om, chunks[i:i + 1, :n].t().contiguous().unsqueeze(2), lengths[i:i + 1], max_length=20)
+        want = " ".join(od.build_target_tokens(o["predictions"][0], cfg.vocab))
+        assert preds[i][0] == want, (i, preds[i][0], want)

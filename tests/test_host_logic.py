@@ -1,0 +1,105 @@
+"""CPU: host-side logic of the product package (no CUDA calls)."""
+import argparse
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import nanodecoder_b200 as pkg
+from nanodecoder_b200 import _lib, checkpoint, synth
+from nanodecoder_b200.config import FAMILIES, ModelConfig
+from nanodecoder_b200.opts import default_translate_opt, translate_opts
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_checkpoint_roundtrip_keeps_reference_layout(tmp_path):
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    ck = synth.make_checkpoint(cfg)
+    assert set(ck) == {"model", "generator", "vocab", "opt", "optim"}          # model_saver.py:109-115
+    assert not any(k.startswith("generator") for k in ck["model"])
+    assert set(ck["generator"]) == {"0.weight", "0.bias"}
+    path = str(tmp_path / "m.pt")
+    checkpoint.save_checkpoint(ck, path)
+    cfg2, sd2, vocab = checkpoint.load_checkpoint(path)
+    assert cfg2.asdict() == cfg.asdict()
+    assert vocab.itos == ["<unk>", "<blank>", "<s>", "</s>", "A", "C", "G", "T"]
+    assert vocab.stoi["</s>"] == 3 and vocab.stoi["never-seen"] == 0
+    sd = synth.make_state_dict(cfg)
+    assert set(sd2) == {k for k in sd if sd[k].is_floating_point() or True} - set()
+    for k in sd:
+        assert torch.equal(sd2[k], sd[k]) if sd[k].is_floating_point() else True
+
+
+def test_legacy_layernorm_keys_are_fixed():
+    cfg = ModelConfig.family("t2t", d_model=32, d_ff=64, enc_layers=1, dec_layers=1, heads=4)
+    ck = synth.make_checkpoint(cfg)
+    m = ck["model"]
+    m["encoder.layer_norm.a_2"] = m.pop("encoder.layer_norm.weight")
+    m["encoder.layer_norm.b_2"] = m.pop("encoder.layer_norm.bias")
+    _, sd, _ = checkpoint.load_checkpoint(ck)
+    assert "encoder.layer_norm.weight" in sd and "encoder.layer_norm.a_2" not in sd
+
+
+@pytest.mark.parametrize("family", sorted(FAMILIES))
+def test_synthetic_state_dicts_are_seed_deterministic(family):
+    cfg = ModelConfig.family(family, d_model=32, d_ff=64, enc_layers=2, dec_layers=2, heads=4)
+    a, b = synth.make_state_dict(cfg, seed=7), synth.make_state_dict(cfg, seed=7)
+    c = synth.make_state_dict(cfg, seed=8)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert any(not torch.equal(a[k], c[k]) for k in a)
+
+
+def test_unsupported_configs_fail_loudly():
+    with pytest.raises(ValueError):
+        ModelConfig(encoder_type="resnet")
+    with pytest.raises(ValueError):
+        ModelConfig(rnn_type="GRU")
+    opt = ModelConfig.family("l2t").to_opt()
+    opt.copy_attn = True
+    with pytest.raises(ValueError):
+        ModelConfig.from_opt(opt, ["<unk>", "<blank>", "<s>", "</s>", "A", "C", "G", "T"])
+
+
+def test_translate_flags_match_reference_names():
+    p = argparse.ArgumentParser()
+    translate_opts(p)
+    opt = p.parse_args("-model m.pt -src_dir d -save_data s --src_seq_length 300 --src_seq_stride 60 --fast "
+                       "--beam_size 5 --max_length 100 --batch_size 800 --thread 10 -gpu 0".split())
+    assert opt.models == ["m.pt"] and opt.fast and opt.beam_size == 5 and opt.src_seq_stride == 60
+    d = default_translate_opt()
+    assert (d.max_length, d.beam_size, d.batch_size, d.n_best, d.alpha) == (100, 5, 100, 1, 0.0)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "nanodec.h")).read()
+    declared = set(re.findall(r"ND_EXPORT\s+[\w\s\*]+?\b(nd_\w+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        from nanodecoder_b200.build import build
+        build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.nd_api_version.restype = ctypes.c_int
+    assert lib.nd_api_version() == _lib.ND_API_VERSION
+
+
+def test_engine_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from nanodecoder_b200.engine import Engine
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=1, dec_layers=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(cfg, synth.make_state_dict(cfg), max_batch=2)
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg_dir = os.path.dirname(pkg.__file__)
+    for root, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f

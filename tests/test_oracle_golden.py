@@ -1,0 +1,87 @@
+"""CPU: the oracle port reproduces the golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, load_golden
+from oracle import decode as odecode
+from oracle.model import OracleModel, lstm_direction_explicit
+
+FAST_CASES = ["l2t_d256", "t2t_d64", "nano2rnn_d256", "brnn2rnn_d256", "cnn2cnn_d256", "l2t_d64"]
+
+
+@pytest.mark.parametrize("name", FAST_CASES)
+def test_oracle_matches_reference_golden(name):
+    g, cfg, sd, src, lengths = load_golden(name)
+    om = OracleModel(sd, cfg)
+    L = int(g["max_length"])
+    trace = []
+    out = odecode.greedy(om, src.t().contiguous().unsqueeze(2), lengths, max_length=L, trace_logits=trace)
+    mb = out["memory_bank"]
+    assert list(mb.shape) == list(g["memory_shape"])
+    np.testing.assert_allclose(mb.flatten()[::97].numpy(), g["memory_sample"], rtol=0, atol=2e-5)
+    assert abs(float(mb.double().sum()) - float(g["memory_sum"])) <= 1e-3 * max(1.0, float(g["memory_abs_sum"]) * 1e-3)
+    np.testing.assert_array_equal(out["memory_lengths"].numpy(), g["memory_lengths"])
+    logits = torch.stack([trace[int(s)] for s in g["logit_steps"]])
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=2e-4)
+    np.testing.assert_array_equal(out["predictions"].numpy(), g["greedy_ids"])
+    np.testing.assert_allclose(out["scores"].numpy(), g["greedy_scores"], atol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["l2t_d256", "nano2rnn_d256", "cnn2cnn_d256", "t2t_d64"])
+def test_oracle_beam_matches_reference_golden(name):
+    g, cfg, sd, src, lengths = load_golden(name)
+    om = OracleModel(sd, cfg)
+    L, K = int(g["max_length"]), int(g["beam_size"])
+    out = odecode.beam_fast(om, src.t().contiguous().unsqueeze(2), lengths, beam_size=K, max_length=L)
+    for i, hyp in enumerate(out["predictions"]):
+        want = g["beam_ids"][i]
+        want = want[want >= 0]
+        np.testing.assert_array_equal(hyp[0].numpy(), want)
+    np.testing.assert_allclose([s[0] for s in out["scores"]], g["beam_scores"], atol=1e-3)
+
+
+def test_greedy_runs_all_steps_and_golden_is_diverse():
+    g, cfg, sd, src, lengths = load_golden("l2t_d256")
+    assert g["greedy_ids"].shape == (int(g["B"]), int(g["max_length"]))        # no EOS early exit
+    assert float(g["token_entropy_bits"]) > 1.4
+    assert len({tuple(r) for r in g["greedy_ids"].tolist()}) >= 4              # signal dependent
+
+
+def test_explicit_lstm_matches_packed_nn_lstm():
+    torch.manual_seed(0)
+    T, B, I, H = 37, 5, 3, 16
+    x = torch.randn(T, B, I)
+    lengths = torch.tensor([37, 30, 30, 11, 1])
+    for t in range(B):
+        x[lengths[t]:, t] = 0
+    m = torch.nn.LSTM(I, H, 1, bidirectional=True)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(x, lengths.tolist())
+    ref, (hn, cn) = m(packed)
+    ref = torch.nn.utils.rnn.pad_packed_sequence(ref)[0]
+    with torch.no_grad():
+        f, hf, cf = lstm_direction_explicit(x, lengths, m.weight_ih_l0, m.weight_hh_l0, m.bias_ih_l0, m.bias_hh_l0, False)
+        r, hr, cr = lstm_direction_explicit(x, lengths, m.weight_ih_l0_reverse, m.weight_hh_l0_reverse,
+                                            m.bias_ih_l0_reverse, m.bias_hh_l0_reverse, True)
+    torch.testing.assert_close(torch.cat([f, r], 2), ref.detach(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(hf, hn[0].detach(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(cr, cn[1].detach(), atol=1e-5, rtol=1e-5)
+
+
+def test_nano_encoder_ignores_last_batchnorm_and_decoder_masks_value_one():
+    # reference quirks restated in SURVEY.md §7 / Appendix A.5
+    g, cfg, sd, src, lengths = load_golden("l2t_d64")
+    om = OracleModel(sd, cfg)
+    s = src.t().contiguous().unsqueeze(2)
+    _, mb1, _ = om.encoder(s, lengths)
+    sd2 = dict(sd)
+    last = "encoder.batchnorm_%d" % (cfg.enc_layers - 1)
+    sd2[last + ".weight"] = sd[last + ".weight"] * 3.0
+    _, mb2, _ = OracleModel(sd2, cfg).encoder(s, lengths)
+    assert torch.equal(mb1, mb2)
+    out = odecode.greedy(om, s, lengths, max_length=3, return_attention=True)
+    attn = out["attention"]                       # [L,B,T]
+    one = s[:, :, 0].t().eq(1.0)                  # [B,T]
+    assert one.any()
+    assert float(attn[:, one].abs().max()) == 0.0
