@@ -144,6 +144,17 @@ ND_EXPORT int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, in
                    int32_t min_len, float alpha, int64_t* out_ids, int32_t* out_lens,
                    float* out_scores, void* stream);
 
+/* per-kernel-category device timing for bench.py's roofline figures: while a category bit is set,
+ * every launch of that category is bracketed by CUDA events on the launching stream;
+ * nd_profile_read synchronises on the last event, returns the summed milliseconds and launch
+ * counts per category (arrays of ND_PROF_NCAT) and clears the log.                                */
+enum {
+  ND_PROF_GEMM = 0, ND_PROF_LSTM = 1, ND_PROF_CROSS_ATTN = 2, ND_PROF_SELF_ATTN = 3, ND_PROF_ENC_ATTN = 4,
+  ND_PROF_MLP_ATTN = 5, ND_PROF_GENERATOR = 6, ND_PROF_BEAM = 7, ND_PROF_OTHER = 8, ND_PROF_NCAT = 9
+};
+ND_EXPORT int nd_profile_enable(nd_engine* e, uint32_t category_mask);
+ND_EXPORT int nd_profile_read(nd_engine* e, double* out_ms, int64_t* out_count);
+
 /* bookkeeping for bench.py: kernels launched by this engine since creation / last reset.        */
 ND_EXPORT int64_t nd_launch_count(const nd_engine* e);
 ND_EXPORT int nd_reset_launch_count(nd_engine* e);

@@ -19,6 +19,7 @@ ATTN = {"mlp": 0, "general": 1, "dot": 2}
 GEMM = {"simt": 0, "3xtf32": 1, "tf32": 2}
 NORM = {"median": 0, "mean": 1, "none": 2, "None": 2}
 DTYPE_F32, DTYPE_I64 = 0, 1
+PROF_CATS = ["gemm", "lstm", "cross_attn", "self_attn", "enc_attn", "mlp_attn", "generator", "beam", "other"]
 
 
 class NdConfig(C.Structure):
@@ -54,6 +55,8 @@ SIGNATURES = {
     "nd_get_memory_bank": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32), _P]),
     "nd_decode_greedy": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "nd_decode_beam": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, _P, _P, _P, _P]),
+    "nd_profile_enable": (C.c_int, [_P, C.c_uint32]),
+    "nd_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "nd_launch_count": (C.c_int64, [_P]),
     "nd_reset_launch_count": (C.c_int, [_P]),
     "nd_test_gemm": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,

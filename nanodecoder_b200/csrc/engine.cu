@@ -69,6 +69,11 @@ struct nd_engine {
   std::vector<void*> allocs;
   bool finalized = false;
   bool oom = false;
+  // per-category CUDA-event timing of kernel launches (nd_profile_enable / nd_profile_read)
+  uint32_t prof_mask = 0;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_used = 0;
+  std::vector<int> prof_cat;           // category of event pair i (events 2i, 2i+1)
 
   // ---- packed weights
   std::vector<LstmW> lstm;           // nano / rnn / brnn encoders
@@ -142,11 +147,32 @@ int fail(nd_engine* e, int code, const std::string& msg) {
     }                                                                                         \
   } while (0)
 // kernel launch through a launcher returning cudaError_t
-#define ND_LAUNCH(e, call)                                                                    \
+#define ND_LAUNCH(e, call) ND_LAUNCH_CAT(e, ND_PROF_OTHER, nullptr, call)
+// same, attributed to a profiling category and (when that category is enabled) bracketed by CUDA events
+#define ND_LAUNCH_CAT(e, cat, st_, call)                                                      \
   do {                                                                                        \
     ++(e)->launches;                                                                          \
+    const bool _prof = ((e)->prof_mask >> (cat)) & 1u;                                        \
+    if (_prof) prof_begin((e), (cat), (cudaStream_t)(st_));                                   \
     ND_CUDA(e, call);                                                                         \
+    if (_prof) prof_end((e), (cudaStream_t)(st_));                                            \
   } while (0)
+
+void prof_begin(nd_engine* e, int cat, cudaStream_t st) {
+  if (e->prof_used + 2 > e->prof_pool.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      e->prof_pool.push_back(ev);
+    }
+  }
+  e->prof_cat.push_back(cat);
+  cudaEventRecord(e->prof_pool[e->prof_used], st);
+}
+void prof_end(nd_engine* e, cudaStream_t st) {
+  cudaEventRecord(e->prof_pool[e->prof_used + 1], st);
+  e->prof_used += 2;
+}
 
 template <class T>
 T* dalloc(nd_engine* e, size_t n) {
@@ -209,10 +235,10 @@ int run_gemm(nd_engine* e, const Lin& l, const float* A, int64_t lda, float* C, 
                       ((reinterpret_cast<uintptr_t>(l.W) & 15) == 0) && l.K >= 8;
   if (tc_mode(e) && tma_ok && l.W_hi) {
     p.W = l.W_hi; p.W_lo = l.W_lo;
-    ND_LAUNCH(e, gemm_tc(p, e->cfg.gemm_mode == ND_GEMM_TC_3XTF32 ? 3 : 1, st));
+    ND_LAUNCH_CAT(e, ND_PROF_GEMM, st, gemm_tc(p, e->cfg.gemm_mode == ND_GEMM_TC_3XTF32 ? 3 : 1, st));
   } else {
     p.W = l.W; p.W_lo = nullptr;
-    ND_LAUNCH(e, gemm_simt(p, st));
+    ND_LAUNCH_CAT(e, ND_PROF_GEMM, st, gemm_simt(p, st));
   }
   return ND_OK;
 }
@@ -541,7 +567,7 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
     }
     if (!nano) { p.h_n = e->enc_hn + (int64_t)l * dirs * B * H; p.c_n = e->enc_cn + (int64_t)l * dirs * B * H; }
     ND_CUDA(e, cudaMemsetAsync(out, 0, (size_t)B * T * d * sizeof(float), st));
-    ND_LAUNCH(e, lstm_layer(p, e->n_sm, st));
+    ND_LAUNCH_CAT(e, ND_PROF_LSTM, st, lstm_layer(p, e->n_sm, st));
     last = out;
     if (nano && c.enc_pooling[l] > 1) {
       // MaxPool1d over time (nano_encoder.py:101-105); lengths follow floor((len - s)/s + 1)
@@ -587,7 +613,7 @@ int encode_transformer(nd_engine* e, cudaStream_t st) {
     GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln.g; o1.pb = L.ln.b; o1.div_by = sq; o1.div_ncols = d;
     ND_TRY(run_gemm(e, L.qkv, x, d, e->big, 3 * d, M, o1, st));
     EncAttnParams a; a.qkv = e->big; a.src = e->src; a.ctx = ctx; a.B = B; a.T = T; a.d = d; a.H = c.heads;
-    ND_LAUNCH(e, encoder_attention(a, st));
+    ND_LAUNCH_CAT(e, ND_PROF_ENC_ATTN, st, encoder_attention(a, st));
     GemmOpt o2; o2.residual = x; o2.ldr = d;
     ND_TRY(run_gemm(e, L.out, ctx, d, x1, d, M, o2, st));
     GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln_ff.g; o3.pb = L.ln_ff.b; o3.act = 1;
@@ -694,7 +720,7 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
       sa.qkv = e->qkv; sa.Kc = e->selfK[l]; sa.Vc = e->selfV[l]; sa.ctx = e->sctx; sa.rows = rows; sa.d = d;
       sa.H = c.heads; sa.Lmax = dc.Lmax; sa.step = dc.step; sa.retired = retired; sa.rows_per_chunk = dc.K;
       if (dc.beam && dc.step > 0) { sa.anc = e->beam.anc + (int64_t)(dc.step & 1) * rows * dc.Lmax; sa.anc_ld = dc.Lmax; }
-      ND_LAUNCH(e, self_attention_step(sa, st));
+      ND_LAUNCH_CAT(e, ND_PROF_SELF_ATTN, st, self_attention_step(sa, st));
       GemmOpt o2; o2.residual = x; o2.ldr = d;
       ND_TRY(run_gemm(e, L.self_out, e->sctx, d, e->x1, d, rows, o2, st));
       GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln2.g; o3.pb = L.ln2.b; o3.div_by = sq; o3.div_ncols = d;
@@ -705,7 +731,7 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
       ca.retired = retired; ca.ctx = e->cctx; ca.ctx_ld = d; ca.n_chunks = B; ca.NQ = dc.K; ca.T = Tp; ca.d = d;
       ca.H = c.heads;
       ca.attn = (l + 1 == c.dec_layers) ? dc.attn_out : nullptr;
-      ND_LAUNCH(e, cross_attention(ca, st));
+      ND_LAUNCH_CAT(e, ND_PROF_CROSS_ATTN, st, cross_attention(ca, st));
       GemmOpt o4; o4.residual = e->x1; o4.ldr = d;
       ND_TRY(run_gemm(e, L.ctx_out, e->cctx, d, e->x2, d, rows, o4, st));
       GemmOpt o5; o5.prologue = PRO_LAYERNORM; o5.pg = L.ln_ff.g; o5.pb = L.ln_ff.b; o5.act = 1;
@@ -752,7 +778,7 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
         ma.wq = below;
       }
     }
-    ND_LAUNCH(e, mlp_attention(ma, st));
+    ND_LAUNCH_CAT(e, ND_PROF_MLP_ATTN, st, mlp_attention(ma, st));
     // attn_h = W_out [c ; h] (+ b for mlp; tanh otherwise)            global_attention.py:197-200
     GemmOpt oc;
     ND_TRY(run_gemm(e, e->attn_out_c, e->actx, d, e->wq, d, rows, oc, st));
@@ -772,7 +798,7 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
   }
   gp.Wg = e->gen.W; gp.bg = e->gen.b; gp.logp = e->logp; gp.rows = rows; gp.d = d; gp.V = c.vocab_size;
   gp.step = dc.step;
-  ND_LAUNCH(e, generator_step(gp, st));
+  ND_LAUNCH_CAT(e, ND_PROF_GENERATOR, st, generator_step(gp, st));
   return ND_OK;
 }
 
@@ -826,6 +852,7 @@ int nd_create(const nd_config* cfg, nd_engine** out) {
 int nd_destroy(nd_engine* e) {
   if (!e) return ND_OK;
   cudaSetDevice(e->cfg.device);
+  for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
   for (void* p : e->allocs) if (p) cudaFree(p);
   delete e;
   return ND_OK;
@@ -857,6 +884,34 @@ int nd_finalize_weights(nd_engine* e) {
   cudaError_t err = cudaDeviceSynchronize();
   if (err != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, cudaGetErrorString(err)); }
   return rc;
+}
+
+int nd_profile_enable(nd_engine* e, uint32_t category_mask) {
+  if (!e) return ND_ERR_INVALID;
+  e->prof_mask = category_mask;
+  e->prof_used = 0;
+  e->prof_cat.clear();
+  return ND_OK;
+}
+
+int nd_profile_read(nd_engine* e, double* out_ms, int64_t* out_count) {
+  if (!e || !out_ms || !out_count) return ND_ERR_INVALID;
+  cudaSetDevice(e->cfg.device);
+  for (int c = 0; c < ND_PROF_NCAT; ++c) { out_ms[c] = 0.0; out_count[c] = 0; }
+  if (e->prof_used) {
+    cudaError_t err = cudaEventSynchronize(e->prof_pool[e->prof_used - 1]);
+    if (err != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, cudaGetErrorString(err)); }
+  }
+  for (size_t i = 0; i < e->prof_cat.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->prof_pool[2 * i], e->prof_pool[2 * i + 1]) == cudaSuccess) {
+      out_ms[e->prof_cat[i]] += ms;
+      out_count[e->prof_cat[i]] += 1;
+    }
+  }
+  e->prof_used = 0;
+  e->prof_cat.clear();
+  return ND_OK;
 }
 
 int64_t nd_launch_count(const nd_engine* e) { return e ? e->launches : 0; }
@@ -992,7 +1047,7 @@ int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_
     gp.min_len = min_len;
     ND_TRY(decoder_step(e, dc, gp, st));
     bp.step = step;
-    ND_LAUNCH(e, beam_step(bp, st));
+    ND_LAUNCH_CAT(e, ND_PROF_BEAM, st, beam_step(bp, st));
   }
   ND_LAUNCH(e, beam_finalize(bp, out_ids, out_lens, out_scores, st));
   return ND_OK;

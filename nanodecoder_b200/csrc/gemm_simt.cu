@@ -125,11 +125,13 @@ cudaError_t gemm_simt(const GemmParams& p, cudaStream_t stream) {
 
 void split_tf32_host(const float* w, float* hi, float* lo, size_t n) {
   for (size_t i = 0; i < n; ++i) {
-    union { float f; uint32_t u; } a, h;
+    union { float f; uint32_t u; } a, h, l;
     a.f = w[i];
-    h.u = a.u & 0xffffe000u;
+    h.u = (a.u + 0x1000u) & 0xffffe000u;      // round to nearest tf32 (unbiased residual)
     hi[i] = h.f;
-    lo[i] = a.f - h.f;      // exact in fp32
+    l.f = a.f - h.f;                          // exact in fp32
+    l.u = (l.u + 0x1000u) & 0xffffe000u;      // and the residual itself rounded to tf32
+    lo[i] = l.f;
   }
 }
 

@@ -270,8 +270,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float h[4], l[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              h[i] = __uint_as_float(__float_as_uint(x[i]) & 0xffffe000u);
-              l[i] = x[i] - h[i];
+              h[i] = __uint_as_float((__float_as_uint(x[i]) + 0x1000u) & 0xffffe000u);     // nearest tf32
+              l[i] = __uint_as_float((__float_as_uint(x[i] - h[i]) + 0x1000u) & 0xffffe000u);
             }
             *reinterpret_cast<float4*>(rh + pc) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4*>(rl + pc) = make_float4(l[0], l[1], l[2], l[3]);

@@ -87,6 +87,21 @@ class Engine(object):
     def reset_launch_count(self):
         self.lib.nd_reset_launch_count(self._h)
 
+    def profile_enable(self, categories=()):
+        """Bracket launches of the named kernel categories with CUDA events (see _lib.PROF_CATS)."""
+        mask = 0
+        for c in categories:
+            mask |= 1 << _lib.PROF_CATS.index(c)
+        self._check(self.lib.nd_profile_enable(self._h, mask))
+
+    def profile_read(self):
+        """-> {category: (total_ms, launches)} since the last read; synchronises the device."""
+        n = len(_lib.PROF_CATS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._check(self.lib.nd_profile_read(self._h, ms, cnt))
+        return {c: (ms[i], int(cnt[i])) for i, c in enumerate(_lib.PROF_CATS) if cnt[i]}
+
     # ------------------------------------------------------------------------------------------
     def encode(self, src: torch.Tensor, lengths: torch.Tensor) -> None:
         """src [B,T] fp32 chunk-major zero padded, lengths [B] int64 — both on this device."""

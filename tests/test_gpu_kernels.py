@@ -21,7 +21,7 @@ SHAPES = [(128, 128, 256), (1024, 768, 256), (1024, 256, 2048), (300, 200, 96), 
           (5, 8, 32), (130, 2048, 256)]
 
 
-@pytest.mark.parametrize("mode,tol", [("simt", 2e-6), ("3xtf32", 5e-6), ("tf32", 3e-3)])
+@pytest.mark.parametrize("mode,tol", [("simt", 2e-6), ("3xtf32", 1e-5), ("tf32", 3e-3)])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_plain(small_engine, mode, tol, M, N, K):
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
@@ -34,7 +34,7 @@ def test_gemm_plain(small_engine, mode, tol, M, N, K):
     assert rel_err(C, ref) < tol, (mode, M, N, K, rel_err(C, ref))
 
 
-@pytest.mark.parametrize("mode,tol", [("simt", 3e-6), ("3xtf32", 6e-6), ("tf32", 3e-3)])
+@pytest.mark.parametrize("mode,tol", [("simt", 3e-6), ("3xtf32", 1e-5), ("tf32", 3e-3)])
 def test_gemm_layernorm_relu_residual(small_engine, mode, tol):
     g = torch.Generator().manual_seed(5)
     M, N, K = 1000, 512, 256
