@@ -205,16 +205,20 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   for (int h = warp; h < H; h += nwarps) {
     float* ps = p_s + warp * p.Lmax;
     const float* qh = q_s + h * dh;
-    // scores: lane <-> position
+    // ---- scores: lane <-> position, 128-bit loads of the key's head slice, 4 partial sums
     float m = -FLT_MAX;
     for (int j = lane; j < L; j += 32) {
-      const float* kr;
-      if (j == p.step) kr = qkv + d + h * dh;      // current position straight from the projection
-      else kr = p.Kc + ((int64_t)(anc ? anc[j] : row) * p.Lmax + j) * d + h * dh;
-      float s = 0.f;
-      for (int e = 0; e < dh; ++e) s = fmaf(qh[e], kr[e], s);
-      ps[j] = s;
-      m = fmaxf(m, s);
+      const float* kr = (j == p.step) ? qkv + d + h * dh
+                                      : p.Kc + ((int64_t)(anc ? anc[j] : row) * p.Lmax + j) * d + h * dh;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int e = 0; e < dh; e += 4) {
+        const float4 kk = *reinterpret_cast<const float4*>(kr + e);
+        const float4 qq = *reinterpret_cast<const float4*>(qh + e);
+        a0 = fmaf(qq.x, kk.x, a0); a1 = fmaf(qq.y, kk.y, a1); a2 = fmaf(qq.z, kk.z, a2); a3 = fmaf(qq.w, kk.w, a3);
+      }
+      const float sc = (a0 + a1) + (a2 + a3);
+      ps[j] = sc;
+      m = fmaxf(m, sc);
     }
     m = warp_max(m);
     float sum = 0.f;
@@ -222,13 +226,25 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
     sum = warp_sum(sum);
     for (int j = lane; j < L; j += 32) ps[j] = ps[j] / sum;
     __syncwarp();
-    // context: lane <-> feature
+    // ---- context: lane <-> feature, 8 positions in flight
     for (int e = lane; e < dh; e += 32) {
       float acc = 0.f;
-      for (int j = 0; j < L; ++j) {
-        const float* vr;
-        if (j == p.step) vr = qkv + 2 * d + h * dh;
-        else vr = p.Vc + ((int64_t)(anc ? anc[j] : row) * p.Lmax + j) * d + h * dh;
+      int j = 0;
+      for (; j + 8 <= L; j += 8) {
+        float vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int jj = j + u;
+          const float* vr = (jj == p.step) ? qkv + 2 * d + h * dh
+                                           : p.Vc + ((int64_t)(anc ? anc[jj] : row) * p.Lmax + jj) * d + h * dh;
+          vv[u] = vr[e];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(ps[j + u], vv[u], acc);
+      }
+      for (; j < L; ++j) {
+        const float* vr = (j == p.step) ? qkv + 2 * d + h * dh
+                                        : p.Vc + ((int64_t)(anc ? anc[j] : row) * p.Lmax + j) * d + h * dh;
         acc = fmaf(ps[j], vr[e], acc);
       }
       p.ctx[(int64_t)row * d + h * dh + e] = acc;

@@ -33,6 +33,10 @@ struct Lin {
   const float* b = nullptr;    // [N] or null
   int N = 0, K = 0;
   int64_t ld = 0;
+  // tcgen05 path with a prologue folded into the weights at pack time (see GemmParams::ln_cvec):
+  int folded = 0;              // 0 none, 1 LayerNorm (W_hi/W_lo hold W*g, cvec/dvec set), 2 column affine
+  const float* cvec = nullptr; // [N] sum_k W[n,k] g[k]
+  const float* dvec = nullptr; // [N] LN: sum_k W[n,k] beta[k] + b[n];  affine: b[n] + sum_k W[n,k] shift[k]
 };
 
 struct LnW { const float* g = nullptr; const float* b = nullptr; };
@@ -197,13 +201,35 @@ const float* upload(nd_engine* e, const std::vector<float>& v) {
 
 bool tc_mode(const nd_engine* e) { return e->cfg.gemm_mode != ND_GEMM_SIMT_FP32; }
 
-Lin make_lin(nd_engine* e, const std::vector<float>& W, int N, int K, const std::vector<float>* b) {
+// fold: 0 none; 1 LayerNorm(fg = gamma, fb = beta) in front of the projection; 2 column affine
+// a*fg[k] + fb[k] (eval BatchNorm) in front of it.  Folding only affects the tcgen05 operands; the
+// SIMT cross-check path keeps the original weight and applies the prologue to A like the reference.
+Lin make_lin(nd_engine* e, const std::vector<float>& W, int N, int K, const std::vector<float>* b, int fold = 0,
+             const std::vector<float>* fg = nullptr, const std::vector<float>* fb = nullptr) {
   Lin l;
   l.N = N; l.K = K; l.ld = K;
   l.W = upload(e, W);
   if (tc_mode(e)) {
+    std::vector<float> Wf(W);
+    if (fold) {
+      std::vector<float> cvec(N), dvec(N);
+      for (int n = 0; n < N; ++n) {
+        double c = 0.0, dsum = 0.0;
+        for (int k = 0; k < K; ++k) {
+          const float w = W[(size_t)n * K + k];
+          Wf[(size_t)n * K + k] = w * (*fg)[k];
+          c += (double)w * (double)(*fg)[k];
+          dsum += (double)w * (double)(*fb)[k];
+        }
+        cvec[n] = (float)c;
+        dvec[n] = (float)(dsum + (b ? (double)(*b)[n] : 0.0));
+      }
+      l.folded = fold;
+      l.cvec = upload(e, cvec);
+      l.dvec = upload(e, dvec);
+    }
     std::vector<float> hi(W.size()), lo(W.size());
-    split_tf32_host(W.data(), hi.data(), lo.data(), W.size());
+    split_tf32_host(Wf.data(), hi.data(), lo.data(), W.size());
     l.W_hi = upload(e, hi);
     l.W_lo = upload(e, lo);
   }
@@ -235,6 +261,15 @@ int run_gemm(nd_engine* e, const Lin& l, const float* A, int64_t lda, float* C, 
                       ((reinterpret_cast<uintptr_t>(l.W) & 15) == 0) && l.K >= 8;
   if (tc_mode(e) && tma_ok && l.W_hi) {
     p.W = l.W_hi; p.W_lo = l.W_lo;
+    if (o.prologue == PRO_LAYERNORM) {
+      if (l.folded != 1) return fail(e, ND_ERR_STATE, "internal: LayerNorm GEMM without folded weights");
+      p.prologue = PRO_NONE; p.ln_cvec = l.cvec; p.ln_dvec = l.dvec; p.bias = nullptr;
+    } else if (o.prologue == PRO_AFFINE) {
+      if (l.folded != 2) return fail(e, ND_ERR_STATE, "internal: affine GEMM without folded weights");
+      p.prologue = PRO_NONE; p.bias = l.dvec;
+    } else if (l.folded) {
+      return fail(e, ND_ERR_STATE, "internal: folded weights used without their prologue");
+    }
     ND_LAUNCH_CAT(e, ND_PROF_GEMM, st, gemm_tc(p, e->cfg.gemm_mode == ND_GEMM_TC_3XTF32 ? 3 : 1, st));
   } else {
     p.W = l.W; p.W_lo = nullptr;
@@ -262,14 +297,23 @@ int need(nd_engine* e, const std::string& k, std::vector<int64_t> shape, const H
   *out = t;
   return ND_OK;
 }
-int load_lin(nd_engine* e, const std::string& prefix, int N, int K, bool bias, Lin* out) {
+int load_lin(nd_engine* e, const std::string& prefix, int N, int K, bool bias, Lin* out,
+             const std::string& ln_prefix = "") {
   const HostTensor *w, *b = nullptr;
   ND_TRY(need(e, prefix + ".weight", {N, K}, &w));
   if (bias) ND_TRY(need(e, prefix + ".bias", {N}, &b));
-  *out = make_lin(e, w->f, N, K, b ? &b->f : nullptr);
+  if (!ln_prefix.empty()) {
+    const HostTensor *g, *bb;
+    ND_TRY(need(e, ln_prefix + ".weight", {K}, &g));
+    ND_TRY(need(e, ln_prefix + ".bias", {K}, &bb));
+    *out = make_lin(e, w->f, N, K, b ? &b->f : nullptr, 1, &g->f, &bb->f);
+  } else {
+    *out = make_lin(e, w->f, N, K, b ? &b->f : nullptr);
+  }
   return ND_OK;
 }
-int load_cat_lin(nd_engine* e, const std::vector<std::string>& prefixes, int N_each, int K, Lin* out) {
+int load_cat_lin(nd_engine* e, const std::vector<std::string>& prefixes, int N_each, int K, Lin* out,
+                 const std::string& ln_prefix = "") {
   std::vector<float> W, b;
   for (auto& pfx : prefixes) {
     const HostTensor *w, *bb;
@@ -278,7 +322,14 @@ int load_cat_lin(nd_engine* e, const std::vector<std::string>& prefixes, int N_e
     W.insert(W.end(), w->f.begin(), w->f.end());
     b.insert(b.end(), bb->f.begin(), bb->f.end());
   }
-  *out = make_lin(e, W, N_each * (int)prefixes.size(), K, &b);
+  if (!ln_prefix.empty()) {
+    const HostTensor *g, *bb;
+    ND_TRY(need(e, ln_prefix + ".weight", {K}, &g));
+    ND_TRY(need(e, ln_prefix + ".bias", {K}, &bb));
+    *out = make_lin(e, W, N_each * (int)prefixes.size(), K, &b, 1, &g->f, &bb->f);
+  } else {
+    *out = make_lin(e, W, N_each * (int)prefixes.size(), K, &b);
+  }
   return ND_OK;
 }
 int load_ln(nd_engine* e, const std::string& prefix, int d, LnW* out) {
@@ -290,7 +341,8 @@ int load_ln(nd_engine* e, const std::string& prefix, int d, LnW* out) {
   return ND_OK;
 }
 // one (bi)directional LSTM layer: checkpoint keys <prefix>.weight_ih<sfx>[_reverse] ...
-int load_lstm(nd_engine* e, const std::string& prefix, const std::string& sfx, int in, int H, int dirs, LstmW* out) {
+int load_lstm(nd_engine* e, const std::string& prefix, const std::string& sfx, int in, int H, int dirs, LstmW* out,
+              const std::vector<float>* in_alpha = nullptr, const std::vector<float>* in_beta = nullptr) {
   std::vector<float> Wih, bih, Whh, bhh;
   for (int dir = 0; dir < dirs; ++dir) {
     const std::string s = sfx + (dir ? "_reverse" : "");
@@ -309,7 +361,8 @@ int load_lstm(nd_engine* e, const std::string& prefix, const std::string& sfx, i
     out->w_ih0 = upload(e, Wih);
     out->b_ih0 = upload(e, bih);
   } else {
-    out->ih = make_lin(e, Wih, dirs * 4 * H, in, &bih);
+    out->ih = in_alpha ? make_lin(e, Wih, dirs * 4 * H, in, &bih, 2, in_alpha, in_beta)
+                       : make_lin(e, Wih, dirs * 4 * H, in, &bih);
   }
   out->w_hh = upload(e, Whh);
   out->b_hh = upload(e, bhh);
@@ -344,8 +397,8 @@ int finalize(nd_engine* e) {
     const int H = d / 2;
     if (!lstm_supported(H)) return fail(e, ND_ERR_INVALID, "LSTM hidden size " + std::to_string(H) + " unsupported (16/32/64/128)");
     e->lstm.resize(c.enc_layers);
+    std::vector<std::vector<float>> alphas(c.enc_layers), betas(c.enc_layers);
     for (int l = 0; l < c.enc_layers; ++l) {
-      ND_TRY(load_lstm(e, "encoder.rnn_" + std::to_string(l), "_l0", l == 0 ? 1 : d, H, 2, &e->lstm[l]));
       // eval BatchNorm1d as y = x*alpha + beta (ATen batch_norm_cpu_transform_input)
       const std::string bp = "encoder.batchnorm_" + std::to_string(l);
       const HostTensor *w, *b, *rm, *rv;
@@ -353,14 +406,19 @@ int finalize(nd_engine* e) {
       ND_TRY(need(e, bp + ".bias", {d}, &b));
       ND_TRY(need(e, bp + ".running_mean", {d}, &rm));
       ND_TRY(need(e, bp + ".running_var", {d}, &rv));
-      std::vector<float> alpha(d), beta(d);
+      alphas[l].resize(d); betas[l].resize(d);
       for (int i = 0; i < d; ++i) {
         const float invstd = 1.0f / sqrtf(rv->f[i] + 1e-5f);
-        alpha[i] = w->f[i] * invstd;
-        beta[i] = b->f[i] - rm->f[i] * alpha[i];
+        alphas[l][i] = w->f[i] * invstd;
+        betas[l][i] = b->f[i] - rm->f[i] * alphas[l][i];
       }
-      e->lstm[l].bn_alpha = upload(e, alpha);
-      e->lstm[l].bn_beta = upload(e, beta);
+    }
+    for (int l = 0; l < c.enc_layers; ++l) {
+      // layer l >= 1 reads BatchNorm_{l-1}(output of layer l-1): folded into its input projection
+      ND_TRY(load_lstm(e, "encoder.rnn_" + std::to_string(l), "_l0", l == 0 ? 1 : d, H, 2, &e->lstm[l],
+                       l ? &alphas[l - 1] : nullptr, l ? &betas[l - 1] : nullptr));
+      e->lstm[l].bn_alpha = upload(e, alphas[l]);
+      e->lstm[l].bn_beta = upload(e, betas[l]);
     }
     ND_TRY(load_lin(e, "encoder.W", d, d, false, &e->encW));
   } else if (c.encoder_type == ND_ENC_BRNN || c.encoder_type == ND_ENC_RNN) {
@@ -376,9 +434,9 @@ int finalize(nd_engine* e) {
     for (int l = 0; l < c.enc_layers; ++l) {
       const std::string p = "encoder.transformer." + std::to_string(l);
       EncLayerT& L = e->encT[l];
-      ND_TRY(load_cat_lin(e, {p + ".self_attn.linear_query", p + ".self_attn.linear_keys", p + ".self_attn.linear_values"}, d, d, &L.qkv));
+      ND_TRY(load_cat_lin(e, {p + ".self_attn.linear_query", p + ".self_attn.linear_keys", p + ".self_attn.linear_values"}, d, d, &L.qkv, p + ".layer_norm"));
       ND_TRY(load_lin(e, p + ".self_attn.final_linear", d, d, true, &L.out));
-      ND_TRY(load_lin(e, p + ".feed_forward.w_1", c.d_ff, d, true, &L.w1));
+      ND_TRY(load_lin(e, p + ".feed_forward.w_1", c.d_ff, d, true, &L.w1, p + ".feed_forward.layer_norm"));
       ND_TRY(load_lin(e, p + ".feed_forward.w_2", d, c.d_ff, true, &L.w2));
       ND_TRY(load_ln(e, p + ".layer_norm", d, &L.ln));
       ND_TRY(load_ln(e, p + ".feed_forward.layer_norm", d, &L.ln_ff));
@@ -403,12 +461,12 @@ int finalize(nd_engine* e) {
     for (int l = 0; l < c.dec_layers; ++l) {
       const std::string p = "decoder.transformer_layers." + std::to_string(l);
       DecLayerT& L = e->decT[l];
-      ND_TRY(load_cat_lin(e, {p + ".self_attn.linear_query", p + ".self_attn.linear_keys", p + ".self_attn.linear_values"}, d, d, &L.qkv));
+      ND_TRY(load_cat_lin(e, {p + ".self_attn.linear_query", p + ".self_attn.linear_keys", p + ".self_attn.linear_values"}, d, d, &L.qkv, p + ".layer_norm_1"));
       ND_TRY(load_lin(e, p + ".self_attn.final_linear", d, d, true, &L.self_out));
-      ND_TRY(load_lin(e, p + ".context_attn.linear_query", d, d, true, &L.cq));
+      ND_TRY(load_lin(e, p + ".context_attn.linear_query", d, d, true, &L.cq, p + ".layer_norm_2"));
       ND_TRY(load_cat_lin(e, {p + ".context_attn.linear_keys", p + ".context_attn.linear_values"}, d, d, &L.ckv));
       ND_TRY(load_lin(e, p + ".context_attn.final_linear", d, d, true, &L.ctx_out));
-      ND_TRY(load_lin(e, p + ".feed_forward.w_1", c.d_ff, d, true, &L.w1));
+      ND_TRY(load_lin(e, p + ".feed_forward.w_1", c.d_ff, d, true, &L.w1, p + ".feed_forward.layer_norm"));
       ND_TRY(load_lin(e, p + ".feed_forward.w_2", d, c.d_ff, true, &L.w2));
       ND_TRY(load_ln(e, p + ".layer_norm_1", d, &L.ln1));
       ND_TRY(load_ln(e, p + ".layer_norm_2", d, &L.ln2));
@@ -1069,12 +1127,35 @@ int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, con
   }
   const char* why = "";
   if (!gemm_tc_available(&why)) return fail(e, ND_ERR_CUDA, why);
-  float *hi = nullptr, *lo = nullptr;
-  if (mode == ND_GEMM_TC_3XTF32) {
-    // split on the host (test path only)
+  float *hi = nullptr, *lo = nullptr, *cv = nullptr, *dv = nullptr;
+  {
+    // host-side weight preparation exactly as the engine's packer does it (test path only)
     std::vector<float> w((size_t)N * K), h((size_t)N * K), l((size_t)N * K);
     ND_CUDA(e, cudaMemcpy(w.data(), W, w.size() * sizeof(float), cudaMemcpyDefault));
+    if (ln_gamma) {
+      std::vector<float> g(K), b(K), bias_h(N, 0.f), cvec(N), dvec(N);
+      ND_CUDA(e, cudaMemcpy(g.data(), ln_gamma, K * sizeof(float), cudaMemcpyDefault));
+      ND_CUDA(e, cudaMemcpy(b.data(), ln_beta, K * sizeof(float), cudaMemcpyDefault));
+      if (bias) ND_CUDA(e, cudaMemcpy(bias_h.data(), bias, N * sizeof(float), cudaMemcpyDefault));
+      for (int n = 0; n < N; ++n) {
+        double c = 0.0, dsum = 0.0;
+        for (int k = 0; k < K; ++k) {
+          const float wv = w[(size_t)n * K + k];
+          c += (double)wv * g[k];
+          dsum += (double)wv * b[k];
+          w[(size_t)n * K + k] = wv * g[k];
+        }
+        cvec[n] = (float)c;
+        dvec[n] = (float)(dsum + bias_h[n]);
+      }
+      ND_CUDA(e, cudaMalloc(&cv, N * sizeof(float)));
+      ND_CUDA(e, cudaMalloc(&dv, N * sizeof(float)));
+      ND_CUDA(e, cudaMemcpy(cv, cvec.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+      ND_CUDA(e, cudaMemcpy(dv, dvec.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+      p.prologue = PRO_NONE; p.ln_cvec = cv; p.ln_dvec = dv; p.bias = nullptr;
+    }
     split_tf32_host(w.data(), h.data(), l.data(), w.size());
+    if (mode != ND_GEMM_TC_3XTF32) h = w;            // single pass: the tensor core truncates the operand itself
     ND_CUDA(e, cudaMalloc(&hi, w.size() * sizeof(float)));
     ND_CUDA(e, cudaMalloc(&lo, w.size() * sizeof(float)));
     ND_CUDA(e, cudaMemcpy(hi, h.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1086,6 +1167,8 @@ int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, con
   cudaError_t err2 = cudaStreamSynchronize(st);
   if (hi) cudaFree(hi);
   if (lo) cudaFree(lo);
+  if (cv) cudaFree(cv);
+  if (dv) cudaFree(dv);
   if (err != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, cudaGetErrorString(err)); }
   if (err2 != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, cudaGetErrorString(err2)); }
   return ND_OK;

@@ -24,6 +24,12 @@ struct GemmParams {
   int relu = 0;                                  // 0 none, 1 ReLU, 2 tanh
   // columns [0, div_ncols) are divided by div_by after the bias (q / sqrt(dh), multi_headed_attn.py:167)
   float div_by = 1.0f; int div_ncols = 0;
+  // tcgen05 path only — LayerNorm folded around the GEMM instead of applied to A:
+  //   LN(a) . W^T + bias = rstd_m * (a . (W*g)^T - mean_m * cvec[n]) + dvec[n]
+  //   with W given as W*g (gamma folded into the columns), cvec[n] = sum_k W[n,k] g[k],
+  //   dvec[n] = sum_k W[n,k] beta[k] + bias[n].  Row mean / rstd are accumulated from the A tiles
+  //   as they stream through shared memory (no extra pass over A).
+  const float* ln_cvec = nullptr; const float* ln_dvec = nullptr;
 };
 
 // both return cudaError_t of the launch

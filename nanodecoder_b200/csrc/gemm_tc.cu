@@ -218,52 +218,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================================================================== converters (warps 0-3)
-    const int row = threadIdx.x;                // one A-tile row per thread
+    const int row = threadIdx.x;                // one A-tile row per thread (and one TMEM lane in the epilogue)
     const int m = m0 + row;
-    if (p.prologue == PRO_LAYERNORM) {
-      // row statistics: each warp walks its 32 rows, lanes stride over K (coalesced, L2 resident)
-      for (int r = warp * 32; r < warp * 32 + 32; ++r) {
-        const int mm = m0 + r;
-        float mean = 0.f, rstd = 1.f;
-        if (mm < p.M) {
-          const float* a = p.A + (int64_t)mm * p.lda;
-          float sacc = 0.f;
-          for (int k = lane; k < p.K; k += 32) sacc += a[k];
-          mean = warp_sum(sacc) / (float)p.K;
-          float vacc = 0.f;
-          for (int k = lane; k < p.K; k += 32) { const float d = a[k] - mean; vacc += d * d; }
-          rstd = 1.0f / sqrtf(warp_sum(vacc) / (float)p.K + p.eps);
-        }
-        if (lane == 0) { s_mean[r] = mean; s_rstd[r] = rstd; }
-      }
-      __syncwarp();
-    }
-    const float mean = (p.prologue == PRO_LAYERNORM) ? s_mean[row] : 0.f;
-    const float rstd = (p.prologue == PRO_LAYERNORM) ? s_rstd[row] : 1.f;
+    const bool fold = p.ln_cvec != nullptr;
     const int sw = row & 7;
+    float x0 = 0.f, s1 = 0.f, s2 = 0.f;         // shifted one-pass row moments for the folded LayerNorm
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % C::kStages;
       const uint32_t it = kb / C::kStages;
       mbar_wait(&raw_full[s], it & 1);
-      if (NPASS == 3 || p.prologue != PRO_NONE) {
+      if (NPASS == 3 || p.prologue != PRO_NONE || fold) {
         uint8_t* rh = a_hi(s) + row * 128;
         uint8_t* rl = a_lo(s) + row * 128;
+        if (fold && kb == 0) x0 = *reinterpret_cast<float*>(rh + (sw << 4));      // logical element k = 0
 #pragma unroll
         for (int c = 0; c < 8; ++c) {           // logical 16-byte chunk c lives at physical chunk c ^ (row & 7)
           const int pc = (c ^ sw) << 4;
           float4 v = *reinterpret_cast<float4*>(rh + pc);
           float x[4] = {v.x, v.y, v.z, v.w};
           const int kbase = kb * BK + c * 4;
-          if (p.prologue != PRO_NONE) {
+          if (fold) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float dlt = (kbase + i < p.K) ? x[i] - x0 : 0.f;
+              s1 += dlt;
+              s2 = fmaf(dlt, dlt, s2);
+            }
+          }
+          if (p.prologue == PRO_AFFINE) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int k = kbase + i;
-              if (k < p.K && m < p.M) {
-                if (p.prologue == PRO_LAYERNORM) x[i] = (x[i] - mean) * rstd * p.pg[k] + p.pb[k];
-                else x[i] = x[i] * p.pg[k] + p.pb[k];
-              } else {
-                x[i] = 0.f;
-              }
+              x[i] = (k < p.K && m < p.M) ? x[i] * p.pg[k] + p.pb[k] : 0.f;
             }
           }
           if (NPASS == 3) {
@@ -275,13 +261,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             *reinterpret_cast<float4*>(rh + pc) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4*>(rl + pc) = make_float4(l[0], l[1], l[2], l[3]);
-          } else {
+          } else if (p.prologue == PRO_AFFINE) {
             *reinterpret_cast<float4*>(rh + pc) = make_float4(x[0], x[1], x[2], x[3]);
           }
         }
-        fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
+        if (NPASS == 3 || p.prologue == PRO_AFFINE)
+          fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
       }
       mbar_arrive(&conv_full[s]);
+    }
+    float ln_mean = 0.f, ln_rstd = 1.f;
+    if (fold) {
+      const float invK = 1.0f / (float)p.K;
+      const float ds = s1 * invK;
+      ln_mean = x0 + ds;
+      const float var = fmaxf(s2 * invK - ds * ds, 0.f);
+      ln_rstd = 1.0f / sqrtf(var + p.eps);
     }
 
     // ===================================================================== epilogue
@@ -297,31 +292,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);     // warp-collective: all lanes participate
       const int nb = n0 + c0;
       if (row_ok && nb < p.N) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = nb + j;
-          if (n < p.N) {
-            float x = v[j];
-            if (p.bias) x += __ldg(p.bias + n);
-            if (n < p.div_ncols) x = x / p.div_by;
-            if (p.relu == 1) x = fmaxf(x, 0.f); else if (p.relu == 2) x = tanhf(x);
-            v[j] = x;
-          }
-        }
         float* crow = p.C + (int64_t)m * p.ldc + nb;
         const float* rrow = p.residual ? p.residual + (int64_t)m * p.ldr + nb : nullptr;
-        if (vec_ok && nb + 32 <= p.N) {
+        if (nb + 32 <= p.N) {
+          // ---- full 32-column block: everything with compile-time register indices
+          if (fold) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (rrow) {
-              const float4 r = *reinterpret_cast<const float4*>(rrow + j);
-              o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_cvec + nb + j));
+              const float4 dv = __ldg(reinterpret_cast<const float4*>(p.ln_dvec + nb + j));
+              v[j] = ln_rstd * (v[j] - ln_mean * cv.x) + dv.x;
+              v[j + 1] = ln_rstd * (v[j + 1] - ln_mean * cv.y) + dv.y;
+              v[j + 2] = ln_rstd * (v[j + 2] - ln_mean * cv.z) + dv.z;
+              v[j + 3] = ln_rstd * (v[j + 3] - ln_mean * cv.w) + dv.w;
             }
-            *reinterpret_cast<float4*>(crow + j) = o;
+          } else if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          }
+          if (nb + 32 <= p.div_ncols) {                       // q / sqrt(dh): IEEE division like the reference
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fdiv_rn(v[j], p.div_by);
+          } else if (nb < p.div_ncols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (nb + j < p.div_ncols) ? __fdiv_rn(v[j], p.div_by) : v[j];
+          }
+          if (p.relu == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.relu == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          }
+          if (vec_ok) {
+            if (rrow) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r = *reinterpret_cast<const float4*>(rrow + j);
+                v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) crow[j] = v[j] + (rrow ? rrow[j] : 0.f);
           }
         } else {
-          for (int j = 0; j < 32 && nb + j < p.N; ++j) crow[j] = v[j] + (rrow ? rrow[j] : 0.f);
+          // ---- ragged tail block (N not a multiple of 32): predicated scalar path, still unrolled
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (n < p.N) {
+              float x = v[j];
+              if (fold) x = ln_rstd * (x - ln_mean * __ldg(p.ln_cvec + n)) + __ldg(p.ln_dvec + n);
+              else if (p.bias) x += __ldg(p.bias + n);
+              if (n < p.div_ncols) x = __fdiv_rn(x, p.div_by);
+              if (p.relu == 1) x = fmaxf(x, 0.f); else if (p.relu == 2) x = tanhf(x);
+              if (rrow) x += rrow[j];
+              crow[j] = x;
+            }
+          }
         }
       }
       __syncwarp();

@@ -3,10 +3,10 @@
 // encoder/rnn_encoder.py:70-78 (cuDNN / ATen LSTM over a PackedSequence).
 //
 // Mapping: one work item = (tile of BT chunks, direction).  An item is executed by a thread-block
-// cluster of C CTAs; CTA `rank` owns hidden units [rank*H/C, (rank+1)*H/C).  Each thread owns ONE
-// gate row of W_hh and keeps it in registers for all T steps (weights-stationary; fp32 exact),
-// the hidden state of the tile lives in shared memory (double buffered) and is exchanged between
-// the CTAs of the cluster through distributed shared memory once per step.
+// cluster of C CTAs; CTA `rank` owns hidden units [rank*H/C, (rank+1)*H/C).  W_hh stays in
+// registers for all T steps (weights-stationary; fp32 exact), the hidden state of the tile lives
+// in shared memory (double buffered) and is exchanged between the CTAs of the cluster through
+// distributed shared memory once per step.
 //   per step:  gates[row][b] = xg[b][t][row] + b_hh[row] + sum_k W_hh[row][k] * h[b][k]
 //              c = sig(f)*c + sig(i)*tanh(g);  h = sig(o)*tanh(c)          (gate order i,f,g,o)
 #include <cooperative_groups.h>
@@ -19,15 +19,22 @@ namespace nd {
 
 namespace {
 
+// Thread layout: tid = u*4 + kq.  Thread (u, kq) holds, for hidden unit u of this CTA, the K-quarter
+// [kq*H/4, (kq+1)*H/4) of all FOUR gate rows (i,f,g,o) in registers (4 * H/4 = H weights), so every
+// hidden-state value fetched from shared memory feeds four FMAs (the shared-memory -> register
+// return path, not the FMA pipe, bounds a one-row-per-thread layout).  The four K-quarter partial
+// sums are combined with a 2-stage reduce-scatter over xor-shuffles, after which lane kq owns the
+// complete gates of chunks [kq*BT/4, (kq+1)*BT/4) of the tile and performs their cell update.
 template <int H, int C, int BT>
 __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
   constexpr int UPC = H / C;          // hidden units owned by this CTA
-  constexpr int NT = 4 * UPC;         // one thread per gate row
-  constexpr int PPT = BT / 4;         // (unit, chunk) pairs per thread in the pointwise phase
-  static_assert(BT % 4 == 0, "BT must be a multiple of 4");
+  constexpr int NT = 4 * UPC;
+  constexpr int KQ = H / 4;           // K elements per thread
+  constexpr int KS = KQ + 4;          // padded quarter stride (floats): conflict-free 128-bit quarter reads
+  constexpr int PPT = BT / 4;         // chunks whose cell update this lane performs
+  static_assert(BT % 4 == 0 && KQ % 4 == 0, "tile shape");
 
-  __shared__ __align__(16) float h_buf[2][BT][H];
-  __shared__ float gates[BT][NT];
+  __shared__ __align__(16) float h_buf[2][BT][4 * KS];
   __shared__ int s_len[BT];
 
   const int tid = threadIdx.x;
@@ -37,23 +44,28 @@ __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
   const int dir = item % p.dirs;
   const int tile = item / p.dirs;
   const int b0 = tile * BT;
+  const int u = tid >> 2, kq = tid & 3;
+  const int ucol = rank * UPC + u;                       // hidden unit index in [0, H)
+  const int64_t gbase = (int64_t)dir * 4 * H + ucol;     // + g*H = row of gate g in the [dirs*4H] dimension
 
-  const int gate = tid / UPC, u = tid % UPC;
-  const int grow = gate * H + rank * UPC + u;                 // row in the [4H] gate dimension
-  const int64_t wrow = (int64_t)dir * 4 * H + grow;
-
-  float w[H];
+  float w[4][KQ];
 #pragma unroll
-  for (int k = 0; k < H; k += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(p.w_hh + wrow * H + k);
-    w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int k = 0; k < KQ; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p.w_hh + (gbase + g * H) * H + kq * KQ + k);
+      w[g][k] = v.x; w[g][k + 1] = v.y; w[g][k + 2] = v.z; w[g][k + 3] = v.w;
+    }
+  float bhh[4], wi0[4], bi0[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    bhh[g] = p.b_hh[gbase + g * H];
+    wi0[g] = p.x0 ? p.w_ih0[gbase + g * H] : 0.f;
+    bi0[g] = p.x0 ? p.b_ih0[gbase + g * H] : 0.f;
   }
-  const float bhh = p.b_hh[wrow];
-  const float wi0 = p.x0 ? p.w_ih0[wrow] : 0.f;
-  const float bi0 = p.x0 ? p.b_ih0[wrow] : 0.f;
 
   if (tid < BT) s_len[tid] = (b0 + tid < p.B) ? (int)p.lengths[b0 + tid] : 0;
-  for (int i = tid; i < 2 * BT * H; i += NT) (&h_buf[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * BT * 4 * KS; i += NT) (&h_buf[0][0][0])[i] = 0.f;
   __syncthreads();
   int maxlen = 0;
 #pragma unroll
@@ -67,57 +79,84 @@ __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
   if constexpr (C > 1) cg::this_cluster().sync();
 
   const int out_ld = p.dirs * H;
+  const int hoff = (ucol / KQ) * KS + (ucol % KQ);       // where unit ucol lives inside a padded h row
+  const bool hi2 = (kq >> 1) != 0, lo1 = (kq & 1) != 0;
   for (int s = 0; s < maxlen; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
-    // ---- input-side gate term (independent of the recurrence: its latency hides behind the FMAs)
-    float xin[BT];
+    // ---- input-side gate terms of the chunks this lane finishes (latency hides behind the FMAs)
+    float xin[4][PPT];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) {
+    for (int j = 0; j < PPT; ++j) {
+      const int b = kq * PPT + j;
       const int len = s_len[b];
       const bool active = s < len;
       const int t = active ? (dir == 0 ? s : len - 1 - s) : 0;
       const int bb = min(b0 + b, p.B - 1);
       if (p.x0) {
-        xin[b] = p.x0[(int64_t)bb * p.T + t] * wi0 + bi0;
+        const float xv = p.x0[(int64_t)bb * p.T + t];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xin[g][j] = xv * wi0[g] + bi0[g];
       } else {
-        xin[b] = p.xg[((int64_t)bb * p.T + t) * p.xg_ld + wrow];
+        const float* xr = p.xg + ((int64_t)bb * p.T + t) * p.xg_ld + gbase;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xin[g][j] = xr[g * H];
       }
     }
-    // ---- recurrent matvec: this thread's gate row against the tile's hidden states
-    float acc[BT];
+    // ---- partial recurrent products over this thread's K-quarter, all BT chunks
+    float acc[4][BT];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = bhh;
+    for (int g = 0; g < 4; ++g)
 #pragma unroll
-    for (int k = 0; k < H; k += 4) {
+      for (int b = 0; b < BT; ++b) acc[g][b] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KQ; k += 4) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
-        const float4 hv = *reinterpret_cast<const float4*>(&h_buf[cur][b][k]);   // warp-broadcast
-        acc[b] = fmaf(w[k], hv.x, acc[b]);
-        acc[b] = fmaf(w[k + 1], hv.y, acc[b]);
-        acc[b] = fmaf(w[k + 2], hv.z, acc[b]);
-        acc[b] = fmaf(w[k + 3], hv.w, acc[b]);
+        const float4 hv = *reinterpret_cast<const float4*>(&h_buf[cur][b][kq * KS + k]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          acc[g][b] = fmaf(w[g][k], hv.x, acc[g][b]);
+          acc[g][b] = fmaf(w[g][k + 1], hv.y, acc[g][b]);
+          acc[g][b] = fmaf(w[g][k + 2], hv.z, acc[g][b]);
+          acc[g][b] = fmaf(w[g][k + 3], hv.w, acc[g][b]);
+        }
       }
     }
+    // ---- reduce-scatter over the 4 K-quarters: lane kq ends up with chunks [kq*PPT, (kq+1)*PPT)
+    float fin[4][PPT];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) gates[b][tid] = xin[b] + acc[b];
-    __syncthreads();
-    // ---- pointwise cell update; thread owns pairs (unit uu, chunk b)
+    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        float half[2];
+#pragma unroll
+        for (int lo = 0; lo < 2; ++lo) {
+          // chunk groups: bq = hi*2 + lo; this lane keeps the groups with hi == (kq >> 1)
+          const float keep = hi2 ? acc[g][(2 + lo) * PPT + j] : acc[g][lo * PPT + j];
+          const float send = hi2 ? acc[g][lo * PPT + j] : acc[g][(2 + lo) * PPT + j];
+          half[lo] = keep + __shfl_xor_sync(ND_FULL, send, 2);
+        }
+        const float keep = lo1 ? half[1] : half[0];
+        const float send = lo1 ? half[0] : half[1];
+        fin[g][j] = keep + __shfl_xor_sync(ND_FULL, send, 1);
+      }
+    }
+    // ---- cell update of (unit ucol, chunk kq*PPT + j)
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      const int pidx = tid + j * NT;
-      const int uu = pidx % UPC, b = pidx / UPC;
+      const int b = kq * PPT + j;
       const int len = s_len[b];
       if (s < len) {
-        const float ig = sigmoid_acc(gates[b][0 * UPC + uu]);
-        const float fg = sigmoid_acc(gates[b][1 * UPC + uu]);
-        const float gg = tanhf(gates[b][2 * UPC + uu]);
-        const float og = sigmoid_acc(gates[b][3 * UPC + uu]);
+        const float ig = sigmoid_acc(xin[0][j] + (fin[0][j] + bhh[0]));
+        const float fg = sigmoid_acc(xin[1][j] + (fin[1][j] + bhh[1]));
+        const float gg = tanhf(xin[2][j] + (fin[2][j] + bhh[2]));
+        const float og = sigmoid_acc(xin[3][j] + (fin[3][j] + bhh[3]));
         c_state[j] = fg * c_state[j] + ig * gg;
         h_state[j] = og * tanhf(c_state[j]);
         const int t = dir == 0 ? s : len - 1 - s;
-        p.out[((int64_t)(b0 + b) * p.T + t) * out_ld + dir * H + rank * UPC + uu] = h_state[j];
+        p.out[((int64_t)(b0 + b) * p.T + t) * out_ld + dir * H + ucol] = h_state[j];
       }
-      float* dst = &h_buf[nxt][b][rank * UPC + uu];
+      float* dst = &h_buf[nxt][b][hoff];
       if constexpr (C > 1) {
         cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
@@ -132,10 +171,9 @@ __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
   if (p.h_n) {
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      const int pidx = tid + j * NT;
-      const int uu = pidx % UPC, b = pidx / UPC;
+      const int b = kq * PPT + j;
       if (b0 + b < p.B) {
-        const int64_t o = ((int64_t)dir * p.B + b0 + b) * H + rank * UPC + uu;
+        const int64_t o = ((int64_t)dir * p.B + b0 + b) * H + ucol;
         p.h_n[o] = h_state[j];
         p.c_n[o] = c_state[j];
       }
