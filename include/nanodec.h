@@ -165,6 +165,10 @@ ND_EXPORT int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const flo
                  const float* residual, const float* ln_gamma, const float* ln_beta, float* C,
                  int32_t M, int32_t N, int32_t K, int32_t relu, void* stream);
 
+/* tuning aid: when non-NULL, CTA 0 of every subsequent tcgen05 GEMM launch writes clock64() stamps of
+ * its pipeline phases into dev_buf32[0..31] (device memory).  NULL switches it off.                 */
+ND_EXPORT int nd_debug_gemm_timeline(int64_t* dev_buf32);
+
 #ifdef __cplusplus
 }
 #endif

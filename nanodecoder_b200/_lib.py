@@ -59,6 +59,7 @@ SIGNATURES = {
     "nd_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "nd_launch_count": (C.c_int64, [_P]),
     "nd_reset_launch_count": (C.c_int, [_P]),
+    "nd_debug_gemm_timeline": (C.c_int, [_P]),
     "nd_test_gemm": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, _P]),
 }

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kAttnThreads) cross_attn_kernel(CrossAttnParam
 
   for (int i = threadIdx.x; i < NQ * d; i += kAttnThreads) {
     const int qi = i / d, c = i - qi * d;
-    q_s[i] = p.q[((int64_t)chunk * NQ + qi) * p.q_ld + c];
+    q_s[i] = p.q[((int64_t)chunk * NQ + qi) * p.q_ld + c] / p.q_div;
   }
   __syncthreads();
 
@@ -185,70 +185,96 @@ cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream) {
 // Decode-step self attention.  One CTA per row, one warp per head (looping when H > warps).
 namespace {
 
+// Cache layout: [slot][head][pos][dh] so that one head's keys / values of consecutive positions are
+// contiguous: dh/4 lanes cover one position with 128-bit loads, 32/(dh/4) positions per warp access.
 __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
   const int row = blockIdx.x;
   if (p.retired && p.retired[row / p.rows_per_chunk]) return;
   const int d = p.d, H = p.H, dh = d / H, L = p.step + 1;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int LPP = dh >> 2;                         // lanes per position (dh = 8/16/32/64 -> 2/4/8/16)
+  const int PPI = 32 / LPP;                        // positions per warp iteration
+  const int sub = lane % LPP, grp = lane / LPP;
   float* q_s = smem_f;                             // [d]
   float* p_s = smem_f + d;                         // [nwarps][Lmax]
   const float* qkv = p.qkv + (int64_t)row * 3 * d;
   // append this step's k, v to the cache (own slot = row) and stage q
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    q_s[i] = qkv[i];
-    p.Kc[((int64_t)row * p.Lmax + p.step) * d + i] = qkv[d + i];
-    p.Vc[((int64_t)row * p.Lmax + p.step) * d + i] = qkv[2 * d + i];
+    const int h = i / dh, e = i - h * dh;
+    const int64_t o = (((int64_t)row * H + h) * p.Lmax + p.step) * dh + e;
+    q_s[i] = qkv[i] / p.q_div;
+    p.Kc[o] = qkv[d + i];
+    p.Vc[o] = qkv[2 * d + i];
   }
   __syncthreads();
   const int* anc = p.anc ? p.anc + (int64_t)row * p.anc_ld : nullptr;
   for (int h = warp; h < H; h += nwarps) {
     float* ps = p_s + warp * p.Lmax;
-    const float* qh = q_s + h * dh;
-    // ---- scores: lane <-> position, 128-bit loads of the key's head slice, 4 partial sums
+    const float4 qq = *reinterpret_cast<const float4*>(q_s + h * dh + sub * 4);
+    // ---- scores: 4 independent 128-bit loads in flight per lane (the kernel is latency bound)
     float m = -FLT_MAX;
-    for (int j = lane; j < L; j += 32) {
-      const float* kr = (j == p.step) ? qkv + d + h * dh
-                                      : p.Kc + ((int64_t)(anc ? anc[j] : row) * p.Lmax + j) * d + h * dh;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int e = 0; e < dh; e += 4) {
-        const float4 kk = *reinterpret_cast<const float4*>(kr + e);
-        const float4 qq = *reinterpret_cast<const float4*>(qh + e);
-        a0 = fmaf(qq.x, kk.x, a0); a1 = fmaf(qq.y, kk.y, a1); a2 = fmaf(qq.z, kk.z, a2); a3 = fmaf(qq.w, kk.w, a3);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < L; j0 += 4 * PPI) {
+      float4 kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * PPI + grp;
+        kk[u] = zero4;
+        if (j < L) {
+          const float* kr = (j == p.step)
+                                ? qkv + d + h * dh
+                                : p.Kc + (((int64_t)(anc ? anc[j] : row) * H + h) * p.Lmax + j) * dh;
+          kk[u] = *reinterpret_cast<const float4*>(kr + sub * 4);
+        }
       }
-      const float sc = (a0 + a1) + (a2 + a3);
-      ps[j] = sc;
-      m = fmaxf(m, sc);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * PPI + grp;
+        float sc = fmaf(qq.x, kk[u].x, fmaf(qq.y, kk[u].y, fmaf(qq.z, kk[u].z, qq.w * kk[u].w)));
+        for (int o = LPP >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(ND_FULL, sc, o);
+        if (j < L) {
+          if (sub == 0) ps[j] = sc;
+          m = fmaxf(m, sc);
+        }
+      }
     }
     m = warp_max(m);
+    __syncwarp();
     float sum = 0.f;
     for (int j = lane; j < L; j += 32) { const float e = expf(ps[j] - m); ps[j] = e; sum += e; }
     sum = warp_sum(sum);
     for (int j = lane; j < L; j += 32) ps[j] = ps[j] / sum;
     __syncwarp();
-    // ---- context: lane <-> feature, 8 positions in flight
-    for (int e = lane; e < dh; e += 32) {
-      float acc = 0.f;
-      int j = 0;
-      for (; j + 8 <= L; j += 8) {
-        float vv[8];
+    // ---- context: each lane accumulates 4 features over its share of the positions
+    float4 acc = zero4;
+    for (int j0 = 0; j0 < L; j0 += 4 * PPI) {
+      float4 vv[4];
+      float pj[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int jj = j + u;
-          const float* vr = (jj == p.step) ? qkv + 2 * d + h * dh
-                                           : p.Vc + ((int64_t)(anc ? anc[jj] : row) * p.Lmax + jj) * d + h * dh;
-          vv[u] = vr[e];
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * PPI + grp;
+        vv[u] = zero4;
+        pj[u] = 0.f;
+        if (j < L) {
+          const float* vr = (j == p.step)
+                                ? qkv + 2 * d + h * dh
+                                : p.Vc + (((int64_t)(anc ? anc[j] : row) * H + h) * p.Lmax + j) * dh;
+          vv[u] = *reinterpret_cast<const float4*>(vr + sub * 4);
+          pj[u] = ps[j];
         }
+      }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc = fmaf(ps[j + u], vv[u], acc);
+      for (int u = 0; u < 4; ++u) {
+        acc.x = fmaf(pj[u], vv[u].x, acc.x); acc.y = fmaf(pj[u], vv[u].y, acc.y);
+        acc.z = fmaf(pj[u], vv[u].z, acc.z); acc.w = fmaf(pj[u], vv[u].w, acc.w);
       }
-      for (; j < L; ++j) {
-        const float* vr = (j == p.step) ? qkv + 2 * d + h * dh
-                                        : p.Vc + ((int64_t)(anc ? anc[j] : row) * p.Lmax + j) * d + h * dh;
-        acc = fmaf(ps[j], vr[e], acc);
-      }
-      p.ctx[(int64_t)row * d + h * dh + e] = acc;
     }
+    for (int o = LPP; o < 32; o <<= 1) {
+      acc.x += __shfl_xor_sync(ND_FULL, acc.x, o); acc.y += __shfl_xor_sync(ND_FULL, acc.y, o);
+      acc.z += __shfl_xor_sync(ND_FULL, acc.z, o); acc.w += __shfl_xor_sync(ND_FULL, acc.w, o);
+    }
+    if (grp == 0) *reinterpret_cast<float4*>(p.ctx + (int64_t)row * d + h * dh + sub * 4) = acc;
     __syncwarp();
   }
 }
@@ -257,6 +283,8 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
 
 cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream) {
   if (p.rows <= 0) return cudaSuccess;
+  const int dh = p.d / p.H;
+  if (dh != 8 && dh != 16 && dh != 32 && dh != 64) return cudaErrorInvalidValue;
   const int nw = p.H < 8 ? p.H : 8;
   const size_t smem = ((size_t)p.d + (size_t)nw * p.Lmax) * sizeof(float);
   self_attn_kernel<<<p.rows, nw * 32, smem, stream>>>(p);
@@ -285,7 +313,7 @@ __global__ void __launch_bounds__(128) enc_attn_kernel(EncAttnParams p) {
 
   float q[DH], o[DH];
 #pragma unroll
-  for (int e = 0; e < DH; ++e) { q[e] = qok ? base[(int64_t)tq * 3 * d + h * DH + e] : 0.f; o[e] = 0.f; }
+  for (int e = 0; e < DH; ++e) { q[e] = qok ? base[(int64_t)tq * 3 * d + h * DH + e] / p.q_div : 0.f; o[e] = 0.f; }
   float m = -FLT_MAX, l = 0.f;
 
   for (int k0 = 0; k0 < T; k0 += KT) {

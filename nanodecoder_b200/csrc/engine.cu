@@ -668,9 +668,9 @@ int encode_transformer(nd_engine* e, cudaStream_t st) {
   ND_LAUNCH(e, linear_in1(e->src, e->enc_lin_in.W, e->enc_lin_in.b, x, M, d, st));       // encoder/transformer.py:113
   for (int l = 0; l < c.enc_layers; ++l) {
     const EncLayerT& L = e->encT[l];
-    GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln.g; o1.pb = L.ln.b; o1.div_by = sq; o1.div_ncols = d;
+    GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln.g; o1.pb = L.ln.b;
     ND_TRY(run_gemm(e, L.qkv, x, d, e->big, 3 * d, M, o1, st));
-    EncAttnParams a; a.qkv = e->big; a.src = e->src; a.ctx = ctx; a.B = B; a.T = T; a.d = d; a.H = c.heads;
+    EncAttnParams a; a.qkv = e->big; a.q_div = sq; a.src = e->src; a.ctx = ctx; a.B = B; a.T = T; a.d = d; a.H = c.heads;
     ND_LAUNCH_CAT(e, ND_PROF_ENC_ATTN, st, encoder_attention(a, st));
     GemmOpt o2; o2.residual = x; o2.ldr = d;
     ND_TRY(run_gemm(e, L.out, ctx, d, x1, d, M, o2, st));
@@ -772,19 +772,19 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
     float* x = e->x;
     for (int l = 0; l < c.dec_layers; ++l) {
       const DecLayerT& L = e->decT[l];
-      GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln1.g; o1.pb = L.ln1.b; o1.div_by = sq; o1.div_ncols = d;
+      GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln1.g; o1.pb = L.ln1.b;
       ND_TRY(run_gemm(e, L.qkv, x, d, e->qkv, 3 * d, rows, o1, st));
       SelfAttnParams sa;
-      sa.qkv = e->qkv; sa.Kc = e->selfK[l]; sa.Vc = e->selfV[l]; sa.ctx = e->sctx; sa.rows = rows; sa.d = d;
+      sa.qkv = e->qkv; sa.q_div = sq; sa.Kc = e->selfK[l]; sa.Vc = e->selfV[l]; sa.ctx = e->sctx; sa.rows = rows; sa.d = d;
       sa.H = c.heads; sa.Lmax = dc.Lmax; sa.step = dc.step; sa.retired = retired; sa.rows_per_chunk = dc.K;
       if (dc.beam && dc.step > 0) { sa.anc = e->beam.anc + (int64_t)(dc.step & 1) * rows * dc.Lmax; sa.anc_ld = dc.Lmax; }
       ND_LAUNCH_CAT(e, ND_PROF_SELF_ATTN, st, self_attention_step(sa, st));
       GemmOpt o2; o2.residual = x; o2.ldr = d;
       ND_TRY(run_gemm(e, L.self_out, e->sctx, d, e->x1, d, rows, o2, st));
-      GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln2.g; o3.pb = L.ln2.b; o3.div_by = sq; o3.div_ncols = d;
+      GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln2.g; o3.pb = L.ln2.b;
       ND_TRY(run_gemm(e, L.cq, e->x1, d, e->qc, d, rows, o3, st));
       CrossAttnParams ca;
-      ca.q = e->qc; ca.q_ld = d; ca.K = e->ckv[l]; ca.V = e->ckv[l] + d; ca.kv_ld = 2 * d;
+      ca.q = e->qc; ca.q_ld = d; ca.q_div = sq; ca.K = e->ckv[l]; ca.V = e->ckv[l] + d; ca.kv_ld = 2 * d;
       ca.src = e->src; ca.src_ld = e->T; ca.mask_value = 1.0f;         // decoder/transformer.py:219-221 (pad_idx = 1)
       ca.retired = retired; ca.ctx = e->cctx; ca.ctx_ld = d; ca.n_chunks = B; ca.NQ = dc.K; ca.T = Tp; ca.d = d;
       ca.H = c.heads;
@@ -1111,6 +1111,11 @@ int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_
   return ND_OK;
 }
 
+int nd_debug_gemm_timeline(int64_t* dev_buf32) {
+  gemm_tc_set_debug(reinterpret_cast<long long*>(dev_buf32));
+  return ND_OK;
+}
+
 int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, const float* bias, const float* residual,
                  const float* ln_gamma, const float* ln_beta, float* C, int32_t M, int32_t N, int32_t K, int32_t relu,
                  void* stream) {
@@ -1122,7 +1127,7 @@ int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, con
   p.M = M; p.N = N; p.K = K; p.relu = relu;
   if (ln_gamma) { p.prologue = PRO_LAYERNORM; p.pg = ln_gamma; p.pb = ln_beta; p.eps = 1e-6f; }
   if (mode == ND_GEMM_SIMT_FP32) {
-    ND_LAUNCH(e, gemm_simt(p, st));
+    ND_LAUNCH_CAT(e, ND_PROF_GEMM, st, gemm_simt(p, st));
     return ND_OK;
   }
   const char* why = "";
@@ -1163,7 +1168,10 @@ int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, con
     p.W = hi; p.W_lo = lo;
   }
   ++e->launches;
+  const bool prof = (e->prof_mask >> ND_PROF_GEMM) & 1u;
+  if (prof) prof_begin(e, ND_PROF_GEMM, st);
   cudaError_t err = gemm_tc(p, mode == ND_GEMM_TC_3XTF32 ? 3 : 1, st);
+  if (prof) prof_end(e, st);
   cudaError_t err2 = cudaStreamSynchronize(st);
   if (hi) cudaFree(hi);
   if (lo) cudaFree(lo);

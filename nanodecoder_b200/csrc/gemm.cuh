@@ -30,12 +30,14 @@ struct GemmParams {
   //   dvec[n] = sum_k W[n,k] beta[k] + bias[n].  Row mean / rstd are accumulated from the A tiles
   //   as they stream through shared memory (no extra pass over A).
   const float* ln_cvec = nullptr; const float* ln_dvec = nullptr;
+  long long* dbg = nullptr;      // optional [32] clock64() timeline written by CTA 0 (tuning aid)
 };
 
 // both return cudaError_t of the launch
 cudaError_t gemm_simt(const GemmParams& p, cudaStream_t stream);
 // npass: 3 = 3xTF32 (fp32 parity), 1 = single TF32
 cudaError_t gemm_tc(const GemmParams& p, int npass, cudaStream_t stream);
+void gemm_tc_set_debug(long long* dev_buf);   // timeline buffer for subsequent gemm_tc launches (nullptr = off)
 // one-time driver entry-point lookup for tensor-map encoding; returns false if unavailable
 bool gemm_tc_available(const char** why);
 

@@ -12,6 +12,13 @@
 //              (tcgen05.ld -> bias / scale / ReLU / residual -> global)
 //   warp 5     TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to mbarriers
 // Pipeline: kStages smem stages, mbarriers raw_full (TMA tx) -> conv_full (128 arrivals) -> empty (commit).
+//
+// Split-K over a thread-block cluster (template S > 1), for the decode-step projections where
+// M = batch rows is small and a 128 x BN tile grid cannot fill 148 SMs: the S CTAs of a cluster
+// each run the pipeline over 1/S of K into their own TMEM accumulator, park the partial tile in
+// shared memory, and after one cluster barrier every CTA reduces 128/S rows over the S partials
+// through distributed shared memory in a FIXED order (deterministic) and applies the epilogue.
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -27,12 +34,16 @@ constexpr int kConvThreads = 128;
 constexpr int kThreads = 192;
 constexpr int A_TILE_BYTES = BM * 128;
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, int S>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_TILE_BYTES * (NPASS == 3 ? 2 : 1) + B_TILE_BYTES * (NPASS == 3 ? 2 : 1);
-  static constexpr int kStages = (200 * 1024) / STAGE_BYTES >= 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BM * 4;
+  static constexpr int PS = BN + 4;                                   // padded pitch of split-K partial rows
+  static constexpr int RECV_BYTES = S > 1 ? BM * PS * 4 : 0;          // peers push their partial rows here
+  static constexpr int kStagesFit = (200 * 1024 - RECV_BYTES) / STAGE_BYTES;
+  static constexpr int kStages = kStagesFit >= 6 ? 6 : kStagesFit;
+  static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BM * 4 /*row moments*/ + 2 * BN * 4 /*epilogue vectors*/;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + RECV_BYTES + 1024 /*align*/ + AUX_BYTES;
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 };
 
@@ -118,29 +129,114 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ------------------------------------------------------------------------------------ epilogue
+// bias / folded LayerNorm, ReLU, residual and store for CH consecutive columns (kept small on purpose:
+// these kernels run for ~10 us, cold instruction fetch of a bulky epilogue costs as much as the math)
+// [nb, nb+CH) of output row m; v[] holds the fp32 accumulators.  All register indices static.
+// cold path: ragged N tail or unaligned C / residual — out of line so it costs no instruction fetch
+template <int CH>
+__device__ __noinline__ void epilogue_store_slow(const GemmParams& p, float (&v)[CH], int m, int nb, bool fold,
+                                                 float ln_mean, float ln_rstd) {
+  float* crow = p.C + (int64_t)m * p.ldc + nb;
+  const float* rrow = p.residual ? p.residual + (int64_t)m * p.ldr + nb : nullptr;
+#pragma unroll 1
+  for (int j = 0; j < CH; ++j) {
+    const int n = nb + j;
+    if (n < p.N) {
+      float x = v[j];
+      if (fold) x = ln_rstd * (x - ln_mean * __ldg(p.ln_cvec + n)) + __ldg(p.ln_dvec + n);
+      else if (p.bias) x += __ldg(p.bias + n);
+      if (p.relu == 1) x = fmaxf(x, 0.f);
+      if (rrow) x += rrow[j];
+      crow[j] = x;
+    }
+  }
+}
+
+// fast path: CH full columns, 16-byte aligned rows.  vec0/vec1 are the CTA's epilogue vectors staged in
+// shared memory at kernel start (bias, or cvec/dvec of the folded LayerNorm) indexed by tile column;
+// res[] holds the residual values prefetched into registers before the accumulator was ready.
+template <int CH>
+__device__ __forceinline__ void epilogue_store_fast(const GemmParams& p, float (&v)[CH], const float4 (&res)[CH / 4],
+                                                    int m, int nb, int col, bool fold, float ln_mean, float ln_rstd,
+                                                    const float* vec0, const float* vec1) {
+  if (fold) {
+#pragma unroll
+    for (int j = 0; j < CH; j += 4) {
+      const float4 cv = *reinterpret_cast<const float4*>(vec0 + col + j);
+      const float4 dv = *reinterpret_cast<const float4*>(vec1 + col + j);
+      v[j] = ln_rstd * (v[j] - ln_mean * cv.x) + dv.x;
+      v[j + 1] = ln_rstd * (v[j + 1] - ln_mean * cv.y) + dv.y;
+      v[j + 2] = ln_rstd * (v[j + 2] - ln_mean * cv.z) + dv.z;
+      v[j + 3] = ln_rstd * (v[j + 3] - ln_mean * cv.w) + dv.w;
+    }
+  } else if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < CH; j += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(vec0 + col + j);
+      v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+    }
+  }
+  if (p.relu == 1) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (p.residual) {
+#pragma unroll
+    for (int j = 0; j < CH; j += 4) {
+      v[j] += res[j / 4].x; v[j + 1] += res[j / 4].y; v[j + 2] += res[j / 4].z; v[j + 3] += res[j / 4].w;
+    }
+  }
+  float* crow = p.C + (int64_t)m * p.ldc + nb;
+#pragma unroll
+  for (int j = 0; j < CH; j += 4)
+    *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+
+template <int CH>
+__device__ __forceinline__ void load_residual(const GemmParams& p, float4 (&res)[CH / 4], int m, int nb, bool ok) {
+  if (p.residual && ok) {
+    const float* rrow = p.residual + (int64_t)m * p.ldr + nb;
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) res[j] = *reinterpret_cast<const float4*>(rrow + 4 * j);
+  }
+}
+
+#define ND_TS(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
+
 // ------------------------------------------------------------------------------------ kernel
-template <int BN, int NPASS>
+template <int BN, int NPASS, int S>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, GemmParams p) {
-  using C = Cfg<BN, NPASS>;
+  using C = Cfg<BN, NPASS, S>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by SWIZZLE_128B operand tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::STAGE_BYTES);
+  float* part = reinterpret_cast<float*>(smem + C::kStages * C::STAGE_BYTES);   // split-K receive buffer [S][BM/S][PS]
+  uint8_t* aux = smem + C::kStages * C::STAGE_BYTES + C::RECV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
   uint64_t* raw_full = bars;
   uint64_t* conv_full = bars + C::kStages;
   uint64_t* empty = bars + 2 * C::kStages;
   uint64_t* tmem_full = bars + 3 * C::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * C::kStages + 1);
-  float* s_mean = reinterpret_cast<float*>(smem + C::kStages * C::STAGE_BYTES + 256);
-  float* s_rstd = s_mean + BM;
+  float* s_stats = reinterpret_cast<float*>(aux + 256);              // [BM][2] (mean, M2) per (source rank, row)
+  float* s_vec0 = s_stats + 2 * BM;                                  // [BN] bias | folded-LN cvec of this tile
+  float* s_vec1 = s_vec0 + BN;                                       // [BN] folded-LN dvec
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) ND_TS(0);
+  int crank = 0;
+  if constexpr (S > 1) crank = (int)cooperative_groups::this_cluster().block_rank();
+  const int tile = blockIdx.x / S;
   const int ntn = (p.N + BN - 1) / BN;
-  const int m0 = (blockIdx.x / ntn) * BM, n0 = (blockIdx.x % ntn) * BN;
-  const int KB = (p.K + BK - 1) / BK;
+  const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+  const int KBtot = (p.K + BK - 1) / BK;
+  const int kb_per = KBtot / S;                       // launcher guarantees KBtot % S == 0
+  const int kb0 = crank * kb_per;
+  const int KB = kb_per;
 
   auto a_hi = [&](int s) { return tiles + s * C::STAGE_BYTES; };
   auto a_lo = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES; };
@@ -161,6 +257,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  "n"(C::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  if (threadIdx.x < BN) {                      // epilogue vectors of this tile's columns -> shared memory
+    const int n = n0 + (int)threadIdx.x;
+    const bool f = p.ln_cvec != nullptr;
+    s_vec0[threadIdx.x] = n < p.N ? (f ? p.ln_cvec[n] : (p.bias ? p.bias[n] : 0.f)) : 0.f;
+    s_vec1[threadIdx.x] = (f && n < p.N) ? p.ln_dvec[n] : 0.f;
+  }
   if (warp == 4 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
@@ -170,30 +272,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) ND_TS(1);
+
+  // epilogue-thread state (warps 0-3; declared here because the split-K reduction below needs it)
+  const int row = threadIdx.x;                  // one A-tile row per converter thread == one TMEM lane
+  const bool fold = p.ln_cvec != nullptr;
+  float ln_mean = 0.f, ln_rstd = 1.f;
+  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                      (!p.residual || (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
+  constexpr int PS = C::PS;
 
   if (warp == 4) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % C::kStages;
-        const uint32_t it = kb / C::kStages;
+      for (int i = 0; i < KB; ++i) {
+        const int s = i % C::kStages;
+        const uint32_t it = i / C::kStages;
         mbar_wait(&empty[s], (it & 1) ^ 1);
         mbar_expect_tx(&raw_full[s], A_TILE_BYTES + C::B_TILE_BYTES * (NPASS == 3 ? 2 : 1));
-        tma_load_2d(a_hi(s), &tmA, &raw_full[s], kb * BK, m0);
-        tma_load_2d(b_hi(s), &tmWhi, &raw_full[s], kb * BK, n0);
-        if (NPASS == 3) tma_load_2d(b_lo(s), &tmWlo, &raw_full[s], kb * BK, n0);
+        const int kc = (kb0 + i) * BK;
+        tma_load_2d(a_hi(s), &tmA, &raw_full[s], kc, m0);
+        tma_load_2d(b_hi(s), &tmWhi, &raw_full[s], kc, n0);
+        if (NPASS == 3) tma_load_2d(b_lo(s), &tmWlo, &raw_full[s], kc, n0);
+        if (i == 0) ND_TS(2);
       }
+      ND_TS(3);
     }
   } else if (warp == 5) {
     // ===================================================================== MMA issuer
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
     // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % C::kStages;
-      const uint32_t it = kb / C::kStages;
+    for (int i = 0; i < KB; ++i) {
+      const int s = i % C::kStages;
+      const uint32_t it = i / C::kStages;
       mbar_wait(&conv_full[s], it & 1);
       tc_fence_after();
+      if (lane == 0 && i == 0) ND_TS(4);
       if (lane == 0) {
         const uint64_t dah = make_desc(smem_u32(a_hi(s)));
         const uint64_t dbh = make_desc(smem_u32(b_hi(s)));
@@ -202,7 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K=8 step inside the swizzle row
-          const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+          const uint32_t first = (i == 0 && k == 0) ? 0u : 1u;
           if (NPASS == 3) {
             umma_tf32(tmem_base, dal + adv, dbh + adv, idesc, first);
             umma_tf32(tmem_base, dah + adv, dbl + adv, idesc, 1u);
@@ -212,155 +327,176 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
-        if (kb == KB - 1) umma_commit(tmem_full);
+        if (i == KB - 1) { umma_commit(tmem_full); ND_TS(5); }
       }
       __syncwarp();
     }
   } else {
     // ===================================================================== converters (warps 0-3)
-    const int row = threadIdx.x;                // one A-tile row per thread (and one TMEM lane in the epilogue)
     const int m = m0 + row;
-    const bool fold = p.ln_cvec != nullptr;
     const int sw = row & 7;
     float x0 = 0.f, s1 = 0.f, s2 = 0.f;         // shifted one-pass row moments for the folded LayerNorm
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % C::kStages;
-      const uint32_t it = kb / C::kStages;
+    for (int i = 0; i < KB; ++i) {
+      const int s = i % C::kStages;
+      const uint32_t it = i / C::kStages;
       mbar_wait(&raw_full[s], it & 1);
-      if (NPASS == 3 || p.prologue != PRO_NONE || fold) {
+      if (threadIdx.x == 0 && i == 0) ND_TS(6);
+      if (NPASS == 3 || fold) {
         uint8_t* rh = a_hi(s) + row * 128;
         uint8_t* rl = a_lo(s) + row * 128;
-        if (fold && kb == 0) x0 = *reinterpret_cast<float*>(rh + (sw << 4));      // logical element k = 0
+        if (fold && i == 0) x0 = *reinterpret_cast<float*>(rh + (sw << 4));       // first element of this K slice
+        // all eight 16-byte chunks of the row first (loads cannot be hoisted over the in-place stores)
+        float4 vin[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) vin[c] = *reinterpret_cast<float4*>(rh + ((c ^ sw) << 4));
 #pragma unroll
         for (int c = 0; c < 8; ++c) {           // logical 16-byte chunk c lives at physical chunk c ^ (row & 7)
           const int pc = (c ^ sw) << 4;
-          float4 v = *reinterpret_cast<float4*>(rh + pc);
-          float x[4] = {v.x, v.y, v.z, v.w};
-          const int kbase = kb * BK + c * 4;
+          const float x[4] = {vin[c].x, vin[c].y, vin[c].z, vin[c].w};
+          const int kbase = (kb0 + i) * BK + c * 4;
           if (fold) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float dlt = (kbase + i < p.K) ? x[i] - x0 : 0.f;
+            for (int q = 0; q < 4; ++q) {
+              const float dlt = (kbase + q < p.K) ? x[q] - x0 : 0.f;
               s1 += dlt;
               s2 = fmaf(dlt, dlt, s2);
-            }
-          }
-          if (p.prologue == PRO_AFFINE) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int k = kbase + i;
-              x[i] = (k < p.K && m < p.M) ? x[i] * p.pg[k] + p.pb[k] : 0.f;
             }
           }
           if (NPASS == 3) {
             float h[4], l[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              h[i] = __uint_as_float((__float_as_uint(x[i]) + 0x1000u) & 0xffffe000u);     // nearest tf32
-              l[i] = __uint_as_float((__float_as_uint(x[i] - h[i]) + 0x1000u) & 0xffffe000u);
+            for (int q = 0; q < 4; ++q) {
+              h[q] = __uint_as_float((__float_as_uint(x[q]) + 0x1000u) & 0xffffe000u);     // nearest tf32
+              l[q] = __uint_as_float((__float_as_uint(x[q] - h[q]) + 0x1000u) & 0xffffe000u);
             }
             *reinterpret_cast<float4*>(rh + pc) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4*>(rl + pc) = make_float4(l[0], l[1], l[2], l[3]);
-          } else if (p.prologue == PRO_AFFINE) {
-            *reinterpret_cast<float4*>(rh + pc) = make_float4(x[0], x[1], x[2], x[3]);
           }
         }
-        if (NPASS == 3 || p.prologue == PRO_AFFINE)
+        if (NPASS == 3)
           fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
       }
       mbar_arrive(&conv_full[s]);
+      if (threadIdx.x == 0 && i == 0) ND_TS(7);
     }
-    float ln_mean = 0.f, ln_rstd = 1.f;
-    if (fold) {
-      const float invK = 1.0f / (float)p.K;
-      const float ds = s1 * invK;
-      ln_mean = x0 + ds;
-      const float var = fmaxf(s2 * invK - ds * ds, 0.f);
-      ln_rstd = 1.0f / sqrtf(var + p.eps);
+    if (threadIdx.x == 0) ND_TS(8);
+    // moments of this CTA's K slice: n_s elements, mean_s, M2_s = sum (x - mean_s)^2
+    const int k_lo = kb0 * BK;
+    const int n_s = max(0, min(p.K, k_lo + KB * BK) - k_lo);
+    float mean_s = 0.f, m2_s = 0.f;
+    if (fold && n_s > 0) {
+      const float ds = s1 / (float)n_s;
+      mean_s = x0 + ds;
+      m2_s = fmaxf(s2 - s1 * ds, 0.f);
     }
 
     // ===================================================================== epilogue
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const bool row_ok = m < p.M;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                        (!p.residual || (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
+    if constexpr (S == 1) {
+      const bool row_ok = m < p.M;
+      // residual of the first column block: in flight while the last MMAs retire
+      float4 res[8];
+      load_residual<32>(p, res, m, n0, row_ok && vec_ok && n0 + 32 <= p.N);
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      if (threadIdx.x == 0) ND_TS(9);
+      if (fold) {
+        ln_mean = mean_s;
+        ln_rstd = 1.0f / sqrtf(m2_s / (float)p.K + p.eps);
+      }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);     // warp-collective: all lanes participate
-      const int nb = n0 + c0;
-      if (row_ok && nb < p.N) {
-        float* crow = p.C + (int64_t)m * p.ldc + nb;
-        const float* rrow = p.residual ? p.residual + (int64_t)m * p.ldr + nb : nullptr;
-        if (nb + 32 <= p.N) {
-          // ---- full 32-column block: everything with compile-time register indices
-          if (fold) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);     // warp-collective: all lanes participate
+        const int nb = n0 + c0;
+        float4 res_next[8];
+        load_residual<32>(p, res_next, m, nb + 32, row_ok && vec_ok && c0 + 32 < BN && nb + 64 <= p.N);
+        if (row_ok && nb < p.N) {
+          if (vec_ok && nb + 32 <= p.N) epilogue_store_fast<32>(p, v, res, m, nb, c0, fold, ln_mean, ln_rstd, s_vec0, s_vec1);
+          else epilogue_store_slow<32>(p, v, m, nb, fold, ln_mean, ln_rstd);
+        }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 cv = __ldg(reinterpret_cast<const float4*>(p.ln_cvec + nb + j));
-              const float4 dv = __ldg(reinterpret_cast<const float4*>(p.ln_dvec + nb + j));
-              v[j] = ln_rstd * (v[j] - ln_mean * cv.x) + dv.x;
-              v[j + 1] = ln_rstd * (v[j + 1] - ln_mean * cv.y) + dv.y;
-              v[j + 2] = ln_rstd * (v[j + 2] - ln_mean * cv.z) + dv.z;
-              v[j + 3] = ln_rstd * (v[j + 3] - ln_mean * cv.w) + dv.w;
-            }
-          } else if (p.bias) {
+        for (int j = 0; j < 8; ++j) res[j] = res_next[j];
+        __syncwarp();
+      }
+    } else {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      if (threadIdx.x == 0) ND_TS(9);
+      // push this row's partial sums (and its partial LayerNorm moments) into the receive buffer of the
+      // CTA that owns the row: remote shared-memory stores are posted, one cluster barrier publishes them
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      constexpr int RPC = BM / S;
+      const int owner = row / RPC, rl = row % RPC;
+      float* dst = cluster.map_shared_rank(part + (size_t)(crank * RPC + rl) * PS, owner);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-            }
-          }
-          if (nb + 32 <= p.div_ncols) {                       // q / sqrt(dh): IEEE division like the reference
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      float* sdst = cluster.map_shared_rank(s_stats + 2 * (crank * RPC + rl), owner);
+      sdst[0] = mean_s;
+      sdst[1] = m2_s;
+    }
+    if (threadIdx.x == 0) ND_TS(10);
+  }
+
+  if constexpr (S > 1) {
+    namespace cg = cooperative_groups;
+    constexpr int RPC = BM / S;                  // rows reduced by this CTA
+    constexpr int CH = BN / S;                   // columns per thread (S threads per row)
+    const int rl = threadIdx.x / S;
+    const int cbeg = (threadIdx.x % S) * CH;
+    const int m = m0 + crank * RPC + rl;
+    const bool fast = vec_ok && n0 + cbeg + CH <= p.N;
+    float4 res[CH / 4];
+    if (warp < 4) load_residual<CH>(p, res, m, n0 + cbeg, m < p.M && fast);     // overlaps the barrier
+    tc_fence_before();
+    cg::this_cluster().sync();                   // every partial row has landed in its owner's shared memory
+    if (threadIdx.x == 0) ND_TS(11);
+    if (warp < 4) {
+      float acc[CH];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fdiv_rn(v[j], p.div_by);
-          } else if (nb < p.div_ncols) {
+      for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+      float mean_all = 0.f, m2_all = 0.f;
+      int n_all = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (nb + j < p.div_ncols) ? __fdiv_rn(v[j], p.div_by) : v[j];
-          }
-          if (p.relu == 1) {
+      for (int s = 0; s < S; ++s) {              // fixed order -> bitwise deterministic
+        const float* rp = part + (size_t)(s * RPC + rl) * PS + cbeg;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.relu == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-          }
-          if (vec_ok) {
-            if (rrow) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r = *reinterpret_cast<const float4*>(rrow + j);
-                v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) crow[j] = v[j] + (rrow ? rrow[j] : 0.f);
-          }
-        } else {
-          // ---- ragged tail block (N not a multiple of 32): predicated scalar path, still unrolled
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            if (n < p.N) {
-              float x = v[j];
-              if (fold) x = ln_rstd * (x - ln_mean * __ldg(p.ln_cvec + n)) + __ldg(p.ln_dvec + n);
-              else if (p.bias) x += __ldg(p.bias + n);
-              if (n < p.div_ncols) x = __fdiv_rn(x, p.div_by);
-              if (p.relu == 1) x = fmaxf(x, 0.f); else if (p.relu == 2) x = tanhf(x);
-              if (rrow) x += rrow[j];
-              crow[j] = x;
-            }
+        for (int j = 0; j < CH; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(rp + j);
+          acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+        }
+        if (fold) {
+          // Chan et al. pairwise update of (n, mean, M2) with K slice s
+          const float* sp = s_stats + 2 * (s * RPC + rl);
+          const int k_lo = s * kb_per * BK;
+          const int nn = max(0, min(p.K, k_lo + kb_per * BK) - k_lo);
+          if (nn > 0) {
+            const float mu = sp[0], mm = sp[1];
+            const float delta = mu - mean_all;
+            const int nt = n_all + nn;
+            mean_all += delta * ((float)nn / (float)nt);
+            m2_all += mm + delta * delta * ((float)n_all * (float)nn / (float)nt);
+            n_all = nt;
           }
         }
       }
-      __syncwarp();
+      if (fold) {
+        ln_mean = mean_all;
+        ln_rstd = 1.0f / sqrtf(m2_all / (float)p.K + p.eps);
+      }
+      if (m < p.M && n0 + cbeg < p.N) {
+        if (fast) epilogue_store_fast<CH>(p, acc, res, m, n0 + cbeg, cbeg, fold, ln_mean, ln_rstd, s_vec0, s_vec1);
+        else epilogue_store_slow<CH>(p, acc, m, n0 + cbeg, fold, ln_mean, ln_rstd);
+      }
     }
+    if (threadIdx.x == 0) ND_TS(12);
   }
 
   tc_fence_before();
@@ -368,10 +504,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 5) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+    if (lane == 0) ND_TS(14);
   }
 }
 
 // ------------------------------------------------------------------------------------ host side
+long long* g_dbg = nullptr;
 PFN_cuTensorMapEncodeTiled g_encode = nullptr;
 bool g_lookup_done = false;
 const char* g_why = "";
@@ -402,12 +540,12 @@ bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, i
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, int S>
 cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN, NPASS>;
+  using C = Cfg<BN, NPASS, S>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -417,11 +555,43 @@ cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
   if (!make_map(&tmWhi, p.W, p.N, p.K, p.ldw, BN)) return cudaErrorInvalidValue;
   if (!make_map(&tmWlo, NPASS == 3 ? p.W_lo : p.W, p.N, p.K, p.ldw, BN)) return cudaErrorInvalidValue;
   const int64_t tiles = (int64_t)cdiv(p.N, BN) * cdiv(p.M, BM);
-  gemm_tc_kernel<BN, NPASS><<<(unsigned)tiles, kThreads, C::SMEM_BYTES, stream>>>(tmA, tmWhi, tmWlo, p);
-  return cudaGetLastError();
+  GemmParams pp = p;
+  pp.dbg = g_dbg;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(tiles * S));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NPASS, S>, tmA, tmWhi, tmWlo, pp);
+}
+
+template <int NPASS>
+cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
+  // tile width: wide tiles when there is plenty of work (encoder-side GEMMs), narrow tiles plus
+  // split-K over a cluster when M is small (decode-step GEMMs) so that ~one wave of the 148 SMs is busy
+  const int KB = cdiv(p.K, BK);
+  const int64_t tiles128 = (int64_t)cdiv(p.N, 128) * cdiv(p.M, BM);
+  if (tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
+  const int64_t tiles64 = (int64_t)cdiv(p.N, 64) * cdiv(p.M, BM);
+  int split = 1;
+  while (split < 4 && KB % (split * 2) == 0 && KB / (split * 2) >= 2 && tiles64 * split * 2 <= 160) split *= 2;
+  switch (split) {
+    case 4: return launch<64, NPASS, 4>(p, stream);
+    case 2: return launch<64, NPASS, 2>(p, stream);
+    default: return launch<64, NPASS, 1>(p, stream);
+  }
 }
 
 }  // namespace
+
+void gemm_tc_set_debug(long long* dev_buf) { g_dbg = dev_buf; }
 
 bool gemm_tc_available(const char** why) {
   const bool ok = lookup();
@@ -432,15 +602,13 @@ bool gemm_tc_available(const char** why) {
 cudaError_t gemm_tc(const GemmParams& p, int npass, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   if (!lookup()) return cudaErrorNotSupported;
+  // the tensor-core kernel keeps a minimal epilogue; prologues are folded into the weights by the caller
+  if (p.prologue != PRO_NONE || p.div_ncols != 0 || p.relu > 1) return cudaErrorInvalidValue;
   // TMA needs 16-byte aligned bases and row pitches
   if ((p.lda & 3) || (p.ldw & 3) || (reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15) ||
       (npass == 3 && (p.W_lo == nullptr || (reinterpret_cast<uintptr_t>(p.W_lo) & 15))))
     return cudaErrorInvalidValue;
-  // tile width: fill the 148 SMs when M is small (decode), wide tiles when M is large (encoder)
-  const int64_t tiles128 = (int64_t)cdiv(p.N, 128) * cdiv(p.M, BM);
-  const bool narrow = (p.N <= 64) || (tiles128 < 148 && p.N % 128 != 0) || (tiles128 < 74);
-  if (npass == 3) return narrow ? launch<64, 3>(p, stream) : launch<128, 3>(p, stream);
-  return narrow ? launch<64, 1>(p, stream) : launch<128, 1>(p, stream);
+  return npass == 3 ? dispatch<3>(p, stream) : dispatch<1>(p, stream);
 }
 
 }  // namespace nd

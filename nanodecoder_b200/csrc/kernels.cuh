@@ -9,7 +9,8 @@ namespace nd {
 // onmt/modules/multi_headed_attn.py:142-190).  One CTA per chunk; the NQ query rows of a chunk
 // (1 for greedy, beam_size for beam search) share one pass over K and V.
 struct CrossAttnParams {
-  const float* q = nullptr;  int64_t q_ld = 0;    // [n_chunks*NQ, d] already divided by sqrt(dh)
+  const float* q = nullptr;  int64_t q_ld = 0;    // [n_chunks*NQ, d] raw projection; divided by q_div here
+  float q_div = 1.0f;                             // sqrt(dh): q / sqrt(dh) as multi_headed_attn.py:167 (IEEE division)
   const float* K = nullptr;                       // [n_chunks, T, *] row stride kv_ld
   const float* V = nullptr;
   int64_t kv_ld = 0;
@@ -24,12 +25,13 @@ struct CrossAttnParams {
 cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream);
 
 // Decode-step self attention with a device-resident KV cache (decoder/transformer.py:76-80,
-// multi_headed_attn.py:126-141).  qkv holds this step's [q/sqrt(dh) | k | v]; k and v are appended
+// multi_headed_attn.py:126-141).  qkv holds this step's [q | k | v]; k and v are appended
 // to the cache at position `step`.  With beam search the history of row r at position j lives in
 // cache row anc[r*anc_ld + j] (parent-pointer indirection instead of reordering the cache).
 struct SelfAttnParams {
-  const float* qkv = nullptr;                     // [rows, 3d]
-  float* Kc = nullptr; float* Vc = nullptr;       // [rows, Lmax, d]
+  const float* qkv = nullptr;                     // [rows, 3d] raw [q | k | v]
+  float q_div = 1.0f;                             // q / sqrt(dh)
+  float* Kc = nullptr; float* Vc = nullptr;       // [rows, H, Lmax, dh] (head-major: contiguous per head)
   const int* anc = nullptr; int anc_ld = 0;       // optional [rows, Lmax]
   const int* retired = nullptr; int rows_per_chunk = 1;
   float* ctx = nullptr;                           // [rows, d]
@@ -38,9 +40,10 @@ struct SelfAttnParams {
 cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream);
 
 // Encoder self attention over a whole chunk (encoder/transformer.py:50-52): qkv [B*T, 3d] with
-// q pre-divided by sqrt(dh); keys with src == 0.0 are masked (encoder/transformer.py:117-121).
+// q divided by sqrt(dh) on load; keys with src == 0.0 are masked (encoder/transformer.py:117-121).
 struct EncAttnParams {
   const float* qkv = nullptr;
+  float q_div = 1.0f;                             // q / sqrt(dh)
   const float* src = nullptr;                     // [B, T]
   float* ctx = nullptr;                           // [B*T, d]
   int B = 0, T = 0, d = 0, H = 8;

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Basecall a directory of reads — same command line as the reference's translate.py
+(translate.py:59-187): -model M -src_dir D -save_data S [--fast] [-beam_size K] ...
+
+Differences in mechanism only: reads are pooled, normalised and chunked on the GPU
+(no multiprocessing.Pool / text round trip), decoded by the CUDA engine, and the per-read
+result/<read>.fasta, segment/<read>.txt and speed.txt files are written in the same formats.
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from nanodecoder_b200 import opts                                        # noqa: E402
+
+
+def write_output(opt, file_src, all_predictions, time_translate):
+    """translate.py:81-98 (same file formats)."""
+    from nanodecoder_b200.utils.labelop import index2base, simple_assembly
+    name = file_src.split(".txt")[0]
+    if opt.src_seq_stride < opt.src_seq_length:
+        c_bpread = index2base(np.argmax(simple_assembly(all_predictions), axis=0))
+    else:
+        c_bpread = simple_assembly(all_predictions, flag_intersection=False)
+    with open(os.path.join(opt.save_data, "result", name + ".fasta"), "w") as f:
+        f.writelines(">%s\n%s" % (name, c_bpread))
+    with open(os.path.join(opt.save_data, "segment", file_src), "w+") as f:
+        for n_best_preds in all_predictions:
+            f.write("\n".join(n_best_preds) + "\n")
+    with open(os.path.join(opt.save_data, "speed.txt"), "a+") as f:
+        f.writelines("%s\t%0.2f\t%d\t%0.2f\n" % (name, float(time_translate), len(c_bpread),
+                                                 len(c_bpread) / float(max(time_translate, 1e-9))))
+
+
+def main(opt, logger):
+    from nanodecoder_b200.inputters.nano_dataset import SignalFrontend
+    from nanodecoder_b200.translate.translator import build_translator
+    from nanodecoder_b200.utils.labelop import read_raw_signal
+    for sub in ("", "result", "segment") + (("attention",) if opt.attn_debug else ()):
+        os.makedirs(os.path.join(opt.save_data, sub), exist_ok=True)
+    opt.tgt = None
+    opt.data_type = "nano"
+    translator = build_translator(opt, report_score=False, logger=logger)
+    frontend = SignalFrontend(translator.model, opt.normalization_raw, opt.src_seq_length, opt.src_seq_stride)
+
+    todo, done = [], 0
+    for fn in sorted(os.listdir(opt.src_dir)):
+        for suffix in ("fast5", "signal"):
+            if fn.endswith(suffix):
+                out = fn[: -len(suffix) - 1] + ".txt"
+                if os.path.exists(os.path.join(opt.save_data, "result", out.split(".txt")[0] + ".fasta")):
+                    done += 1                                    # translate.py:152 (resume semantics)
+                else:
+                    todo.append((fn, suffix, out))
+    logger.info("%d reads have already translated, remains %d read\n" % (done, len(todo)))
+
+    pool_reads = max(1, opt.thread * 8)                          # reads pooled per GPU front-end launch
+    for g0 in range(0, len(todo), pool_reads):
+        group = todo[g0: g0 + pool_reads]
+        start = time.time()
+        reads = [read_raw_signal(os.path.join(opt.src_dir, fn), suffix) for fn, suffix, _ in group]
+        keep = [i for i, r in enumerate(reads) if r.size > 0]
+        if not keep:
+            continue
+        chunks, lengths, chunk_read = frontend([reads[i] for i in keep])
+        _, preds = translator.translate(src=(chunks, lengths), tgt=None, src_dir=opt.save_data,
+                                        batch_size=opt.batch_size, attn_debug=opt.attn_debug)
+        elapsed = time.time() - start
+        total = max(1, len(chunk_read))
+        for j, i in enumerate(keep):
+            sel = np.nonzero(chunk_read == j)[0]
+            try:
+                write_output(opt, group[i][2], [preds[k] for k in sel], elapsed * len(sel) / total)
+            except Exception:                                    # translate.py:97-98
+                print("!!!error!!!data src: " + group[i][2].split(".txt")[0])
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser(description="translate.py", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    opts.translate_opts(parser)
+    opt = parser.parse_args()
+    logging.basicConfig(level=logging.INFO, format="[%(asctime)s %(levelname)s] %(message)s")
+    log = logging.getLogger("translate")
+    if opt.log_file:
+        log.addHandler(logging.FileHandler(opt.log_file))
+    main(opt, log)
