@@ -5,12 +5,12 @@
 //               D += a_lo.w_hi + a_hi.w_lo + a_hi.w_hi   -> ~2^-21 relative error (fp32 parity mode)
 //   npass == 1  single TF32 pass (fast mode, ~2^-11)
 //
-// CTA = 192 threads, one 128 x BN output tile:
-//   warp 4     TMA producer: A (raw fp32), W_hi, W_lo tiles of 128B-swizzled K-major rows (BK = 32)
-//   warps 0-3  converters: apply the prologue (LayerNorm / column affine) to the A tile in place,
-//              split it into tf32 hi/lo, publish to the async proxy; afterwards the epilogue
-//              (tcgen05.ld -> bias / scale / ReLU / residual -> global)
-//   warp 5     TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to mbarriers
+// CTA = 320 threads, one 128 x BN output tile:
+//   warp 8     TMA producer: A (raw fp32), W_hi, W_lo tiles of 128B-swizzled K-major rows (BK = 32)
+//   warps 0-7  converters: split the A tile in place into tf32 hi/lo (and accumulate the LayerNorm row
+//              moments), publish to the async proxy; afterwards the epilogue (tcgen05.ld -> bias /
+//              folded LayerNorm / ReLU -> transpose through shared memory -> residual -> coalesced stores)
+//   warp 9     TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to mbarriers
 // Pipeline: kStages smem stages, mbarriers raw_full (TMA tx) -> conv_full (128 arrivals) -> empty (commit).
 //
 // Split-K over a thread-block cluster (template S > 1), for the decode-step projections where
@@ -30,8 +30,10 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 32;                 // 32 fp32 = one 128-byte swizzle row
-constexpr int kConvThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kConvWarps = 8;
+constexpr int kConvThreads = kConvWarps * 32;
+constexpr int kTmaWarp = kConvWarps, kMmaWarp = kConvWarps + 1;
+constexpr int kThreads = kConvThreads + 64;
 constexpr int A_TILE_BYTES = BM * 128;
 
 template <int BN, int NPASS, int S>
@@ -42,7 +44,8 @@ struct Cfg {
   static constexpr int RECV_BYTES = S > 1 ? BM * PS * 4 : 0;          // peers push their partial rows here
   static constexpr int kStagesFit = (200 * 1024 - RECV_BYTES) / STAGE_BYTES;
   static constexpr int kStages = kStagesFit >= 6 ? 6 : kStagesFit;
-  static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BM * 4 /*row moments*/ + 2 * BN * 4 /*epilogue vectors*/;
+  static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BM * 4 /*row stats*/ + 2 * BN * 4 /*epilogue vectors*/ +
+                                   4 * BM * 4 /*half-row moments*/;
   static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + RECV_BYTES + 1024 /*align*/ + AUX_BYTES;
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 };
@@ -153,13 +156,11 @@ __device__ __noinline__ void epilogue_store_slow(const GemmParams& p, float (&v)
   }
 }
 
-// fast path: CH full columns, 16-byte aligned rows.  vec0/vec1 are the CTA's epilogue vectors staged in
-// shared memory at kernel start (bias, or cvec/dvec of the folded LayerNorm) indexed by tile column;
-// res[] holds the residual values prefetched into registers before the accumulator was ready.
+// row-wise part of the epilogue on CH accumulators of one output row: bias or folded LayerNorm, ReLU.
+// vec0 / vec1: the tile's epilogue vectors staged in shared memory, indexed by tile column `col`.
 template <int CH>
-__device__ __forceinline__ void epilogue_store_fast(const GemmParams& p, float (&v)[CH], const float4 (&res)[CH / 4],
-                                                    int m, int nb, int col, bool fold, float ln_mean, float ln_rstd,
-                                                    const float* vec0, const float* vec1) {
+__device__ __forceinline__ void epilogue_rowwise(const GemmParams& p, float (&v)[CH], int col, bool fold,
+                                                 float ln_mean, float ln_rstd, const float* vec0, const float* vec1) {
   if (fold) {
 #pragma unroll
     for (int j = 0; j < CH; j += 4) {
@@ -181,30 +182,12 @@ __device__ __forceinline__ void epilogue_store_fast(const GemmParams& p, float (
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if (p.residual) {
-#pragma unroll
-    for (int j = 0; j < CH; j += 4) {
-      v[j] += res[j / 4].x; v[j + 1] += res[j / 4].y; v[j + 2] += res[j / 4].z; v[j + 3] += res[j / 4].w;
-    }
-  }
-  float* crow = p.C + (int64_t)m * p.ldc + nb;
-#pragma unroll
-  for (int j = 0; j < CH; j += 4)
-    *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-}
-
-template <int CH>
-__device__ __forceinline__ void load_residual(const GemmParams& p, float4 (&res)[CH / 4], int m, int nb, bool ok) {
-  if (p.residual && ok) {
-    const float* rrow = p.residual + (int64_t)m * p.ldr + nb;
-#pragma unroll
-    for (int j = 0; j < CH / 4; ++j) res[j] = *reinterpret_cast<const float4*>(rrow + 4 * j);
-  }
 }
 
 #define ND_TS(slot) do { if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------ kernel
+// warps 0-7: converters + epilogue, warp 8: TMA producer, warp 9: TMEM owner + MMA issuer
 template <int BN, int NPASS, int S>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
@@ -225,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_stats = reinterpret_cast<float*>(aux + 256);              // [BM][2] (mean, M2) per (source rank, row)
   float* s_vec0 = s_stats + 2 * BM;                                  // [BN] bias | folded-LN cvec of this tile
   float* s_vec1 = s_vec0 + BN;                                       // [BN] folded-LN dvec
+  float* s_mom = s_vec1 + BN;                                        // [2][BM][2] half-row (s1, s2) moments
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) ND_TS(0);
@@ -237,13 +221,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_per = KBtot / S;                       // launcher guarantees KBtot % S == 0
   const int kb0 = crank * kb_per;
   const int KB = kb_per;
+  constexpr int PS = C::PS;
 
   auto a_hi = [&](int s) { return tiles + s * C::STAGE_BYTES; };
   auto a_lo = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES; };
   auto b_hi = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES * (NPASS == 3 ? 2 : 1); };
   auto b_lo = [&](int s) { return b_hi(s) + C::B_TILE_BYTES; };
+  auto issue_tma = [&](int i) {
+    const int s = i % C::kStages;
+    mbar_expect_tx(&raw_full[s], A_TILE_BYTES + C::B_TILE_BYTES * (NPASS == 3 ? 2 : 1));
+    const int kc = (kb0 + i) * BK;
+    tma_load_2d(a_hi(s), &tmA, &raw_full[s], kc, m0);
+    tma_load_2d(b_hi(s), &tmWhi, &raw_full[s], kc, n0);
+    if (NPASS == 3) tma_load_2d(b_lo(s), &tmWlo, &raw_full[s], kc, n0);
+  };
 
-  if (threadIdx.x == 0) {
+  int tma_issued = 0;
+  if (warp == kTmaWarp && lane == 0) {
+    // the producer owns the barriers: initialise them and put the first stages in flight before
+    // the CTA-wide setup barrier, so the first TMA round trip overlaps TMEM allocation and setup
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&raw_full[s], 1);
       mbar_init(&conv_full[s], kConvThreads);
@@ -251,8 +247,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
+    if (NPASS == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+    const int first = KB < C::kStages ? KB : C::kStages;
+    for (; tma_issued < first; ++tma_issued) issue_tma(tma_issued);
+    ND_TS(2);
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(C::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -263,42 +265,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     s_vec0[threadIdx.x] = n < p.N ? (f ? p.ln_cvec[n] : (p.bias ? p.bias[n] : 0.f)) : 0.f;
     s_vec1[threadIdx.x] = (f && n < p.N) ? p.ln_dvec[n] : 0.f;
   }
-  if (warp == 4 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
-    if (NPASS == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) ND_TS(1);
 
-  // epilogue-thread state (warps 0-3; declared here because the split-K reduction below needs it)
-  const int row = threadIdx.x;                  // one A-tile row per converter thread == one TMEM lane
   const bool fold = p.ln_cvec != nullptr;
-  float ln_mean = 0.f, ln_rstd = 1.f;
   const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                       (!p.residual || (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
-  constexpr int PS = C::PS;
 
-  if (warp == 4) {
-    // ===================================================================== TMA producer
+  if (warp == kTmaWarp) {
+    // ===================================================================== TMA producer (remaining stages)
     if (lane == 0) {
-      for (int i = 0; i < KB; ++i) {
+      for (int i = tma_issued; i < KB; ++i) {
         const int s = i % C::kStages;
         const uint32_t it = i / C::kStages;
         mbar_wait(&empty[s], (it & 1) ^ 1);
-        mbar_expect_tx(&raw_full[s], A_TILE_BYTES + C::B_TILE_BYTES * (NPASS == 3 ? 2 : 1));
-        const int kc = (kb0 + i) * BK;
-        tma_load_2d(a_hi(s), &tmA, &raw_full[s], kc, m0);
-        tma_load_2d(b_hi(s), &tmWhi, &raw_full[s], kc, n0);
-        if (NPASS == 3) tma_load_2d(b_lo(s), &tmWlo, &raw_full[s], kc, n0);
-        if (i == 0) ND_TS(2);
+        issue_tma(i);
       }
       ND_TS(3);
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ===================================================================== MMA issuer
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=TF32 [7,10)=2, b=TF32 [10,13)=2,
     // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
@@ -332,10 +320,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
     }
   } else {
-    // ===================================================================== converters (warps 0-3)
+    // ===================================================================== converters (warps 0-7)
+    // thread = (row, half): half h converts 16-byte chunks [4h, 4h+4) of the row's 128-byte k-block slice
+    const int row = threadIdx.x & (BM - 1);
+    const int half = threadIdx.x >> 7;
     const int m = m0 + row;
     const int sw = row & 7;
-    float x0 = 0.f, s1 = 0.f, s2 = 0.f;         // shifted one-pass row moments for the folded LayerNorm
+    float x0 = 0.f, s1 = 0.f, s2 = 0.f;         // shifted one-pass moments for the folded LayerNorm
     for (int i = 0; i < KB; ++i) {
       const int s = i % C::kStages;
       const uint32_t it = i / C::kStages;
@@ -345,15 +336,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* rh = a_hi(s) + row * 128;
         uint8_t* rl = a_lo(s) + row * 128;
         if (fold && i == 0) x0 = *reinterpret_cast<float*>(rh + (sw << 4));       // first element of this K slice
-        // all eight 16-byte chunks of the row first (loads cannot be hoisted over the in-place stores)
-        float4 vin[8];
+        // all four chunks first (loads cannot be hoisted over the in-place stores by the compiler)
+        float4 vin[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) vin[c] = *reinterpret_cast<float4*>(rh + ((c ^ sw) << 4));
+        for (int c = 0; c < 4; ++c) vin[c] = *reinterpret_cast<float4*>(rh + (((4 * half + c) ^ sw) << 4));
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {           // logical 16-byte chunk c lives at physical chunk c ^ (row & 7)
-          const int pc = (c ^ sw) << 4;
+        for (int c = 0; c < 4; ++c) {           // logical 16-byte chunk lc lives at physical chunk lc ^ (row & 7)
+          const int lc = 4 * half + c;
+          const int pc = (lc ^ sw) << 4;
           const float x[4] = {vin[c].x, vin[c].y, vin[c].z, vin[c].w};
-          const int kbase = (kb0 + i) * BK + c * 4;
+          const int kbase = (kb0 + i) * BK + lc * 4;
           if (fold) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -380,49 +372,78 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (threadIdx.x == 0 && i == 0) ND_TS(7);
     }
     if (threadIdx.x == 0) ND_TS(8);
-    // moments of this CTA's K slice: n_s elements, mean_s, M2_s = sum (x - mean_s)^2
-    const int k_lo = kb0 * BK;
-    const int n_s = max(0, min(p.K, k_lo + KB * BK) - k_lo);
+    // combine the two half-row moment sums: this CTA's K slice has n_s elements, mean_s, M2_s
     float mean_s = 0.f, m2_s = 0.f;
-    if (fold && n_s > 0) {
-      const float ds = s1 / (float)n_s;
-      mean_s = x0 + ds;
-      m2_s = fmaxf(s2 - s1 * ds, 0.f);
+    if (fold) {
+      s_mom[(half * BM + row) * 2] = s1;
+      s_mom[(half * BM + row) * 2 + 1] = s2;
+      asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+      const float t1 = s_mom[row * 2] + s_mom[(BM + row) * 2];
+      const float t2 = s_mom[row * 2 + 1] + s_mom[(BM + row) * 2 + 1];
+      const int k_lo = kb0 * BK;
+      const int n_s = max(0, min(p.K, k_lo + KB * BK) - k_lo);
+      if (n_s > 0) {
+        const float ds = t1 / (float)n_s;
+        mean_s = x0 + ds;
+        m2_s = fmaxf(t2 - t1 * ds, 0.f);
+      }
     }
 
-    // ===================================================================== epilogue
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ===================================================================== epilogue (all 8 warps)
+    // warp w reads TMEM lanes 32*(w&3).. (its rows) and the column half (w>>2) of the tile
+    const int lg = warp & 3, chalf = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
+    constexpr int HC = BN / 2;                   // columns per warp
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    if (threadIdx.x == 0) ND_TS(9);
     if constexpr (S == 1) {
-      const bool row_ok = m < p.M;
-      // residual of the first column block: in flight while the last MMAs retire
-      float4 res[8];
-      load_residual<32>(p, res, m, n0, row_ok && vec_ok && n0 + 32 <= p.N);
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-      if (threadIdx.x == 0) ND_TS(9);
+      float ln_mean = 0.f, ln_rstd = 1.f;
       if (fold) {
         ln_mean = mean_s;
         ln_rstd = 1.0f / sqrtf(m2_s / (float)p.K + p.eps);
       }
+      // per-warp staging tile [32 rows][36 floats] in the (now idle) pipeline stages: accumulators are
+      // transposed through it so that global stores / residual loads are 128-byte contiguous per row
+      float* stg = reinterpret_cast<float*>(tiles) + warp * (32 * 36);
+      const int rsub = lane >> 3, cq = lane & 7;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int cb = 0; cb < HC; cb += 32) {
+        const int c0 = chalf * HC + cb;
+        const int nb = n0 + c0;
         float v[32];
         tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);     // warp-collective: all lanes participate
-        const int nb = n0 + c0;
-        float4 res_next[8];
-        load_residual<32>(p, res_next, m, nb + 32, row_ok && vec_ok && c0 + 32 < BN && nb + 64 <= p.N);
-        if (row_ok && nb < p.N) {
-          if (vec_ok && nb + 32 <= p.N) epilogue_store_fast<32>(p, v, res, m, nb, c0, fold, ln_mean, ln_rstd, s_vec0, s_vec1);
-          else epilogue_store_slow<32>(p, v, m, nb, fold, ln_mean, ln_rstd);
-        }
+        if (vec_ok && nb + 32 <= p.N) {
+          // residual rows in flight while the row-wise math runs (4 rows x 128 B per instruction)
+          float4 res[8];
+          if (p.residual) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) res[j] = res_next[j];
+            for (int i = 0; i < 8; ++i) {
+              const int mm = m0 + lg * 32 + 4 * i + rsub;
+              res[i] = mm < p.M ? *reinterpret_cast<const float4*>(p.residual + (int64_t)mm * p.ldr + nb + cq * 4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          epilogue_rowwise<32>(p, v, c0, fold, ln_mean, ln_rstd, s_vec0, s_vec1);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rsub;
+            const int mm = m0 + lg * 32 + r;
+            float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
+            if (p.residual) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+            if (mm < p.M) *reinterpret_cast<float4*>(p.C + (int64_t)mm * p.ldc + nb + cq * 4) = o;
+          }
+          __syncwarp();
+        } else if (m < p.M && nb < p.N) {
+          epilogue_store_slow<32>(p, v, m, nb, fold, ln_mean, ln_rstd);
+        }
         __syncwarp();
       }
     } else {
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-      if (threadIdx.x == 0) ND_TS(9);
       // push this row's partial sums (and its partial LayerNorm moments) into the receive buffer of the
       // CTA that owns the row: remote shared-memory stores are posted, one cluster barrier publishes them
       namespace cg = cooperative_groups;
@@ -431,16 +452,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int owner = row / RPC, rl = row % RPC;
       float* dst = cluster.map_shared_rank(part + (size_t)(crank * RPC + rl) * PS, owner);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int cb = 0; cb < HC; cb += 32) {
+        const int c0 = chalf * HC + cb;
         float v[32];
         tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-      float* sdst = cluster.map_shared_rank(s_stats + 2 * (crank * RPC + rl), owner);
-      sdst[0] = mean_s;
-      sdst[1] = m2_s;
+      if (chalf == 0) {
+        float* sdst = cluster.map_shared_rank(s_stats + 2 * (crank * RPC + rl), owner);
+        sdst[0] = mean_s;
+        sdst[1] = m2_s;
+      }
     }
     if (threadIdx.x == 0) ND_TS(10);
   }
@@ -448,17 +472,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (S > 1) {
     namespace cg = cooperative_groups;
     constexpr int RPC = BM / S;                  // rows reduced by this CTA
-    constexpr int CH = BN / S;                   // columns per thread (S threads per row)
-    const int rl = threadIdx.x / S;
-    const int cbeg = (threadIdx.x % S) * CH;
+    constexpr int TPR = kConvThreads / RPC;      // threads per row (2S)
+    constexpr int CH = BN / TPR;                 // columns per thread
+    static_assert(CH % 4 == 0, "split-K column chunk");
+    const int rl = threadIdx.x / TPR;
+    const int cbeg = (threadIdx.x % TPR) * CH;
     const int m = m0 + crank * RPC + rl;
+    const bool conv = warp < kConvWarps;
     const bool fast = vec_ok && n0 + cbeg + CH <= p.N;
     float4 res[CH / 4];
-    if (warp < 4) load_residual<CH>(p, res, m, n0 + cbeg, m < p.M && fast);     // overlaps the barrier
+    if (conv && p.residual && m < p.M && fast) {      // overlaps the barrier
+      const float* rrow = p.residual + (int64_t)m * p.ldr + n0 + cbeg;
+#pragma unroll
+      for (int j = 0; j < CH / 4; ++j) res[j] = *reinterpret_cast<const float4*>(rrow + 4 * j);
+    }
     tc_fence_before();
     cg::this_cluster().sync();                   // every partial row has landed in its owner's shared memory
     if (threadIdx.x == 0) ND_TS(11);
-    if (warp < 4) {
+    if (conv) {
       float acc[CH];
 #pragma unroll
       for (int j = 0; j < CH; ++j) acc[j] = 0.f;
@@ -487,13 +518,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      float ln_mean = 0.f, ln_rstd = 1.f;
       if (fold) {
         ln_mean = mean_all;
         ln_rstd = 1.0f / sqrtf(m2_all / (float)p.K + p.eps);
       }
       if (m < p.M && n0 + cbeg < p.N) {
-        if (fast) epilogue_store_fast<CH>(p, acc, res, m, n0 + cbeg, cbeg, fold, ln_mean, ln_rstd, s_vec0, s_vec1);
-        else epilogue_store_slow<CH>(p, acc, m, n0 + cbeg, fold, ln_mean, ln_rstd);
+        if (fast) {
+          epilogue_rowwise<CH>(p, acc, cbeg, fold, ln_mean, ln_rstd, s_vec0, s_vec1);
+          float* crow = p.C + (int64_t)m * p.ldc + n0 + cbeg;
+#pragma unroll
+          for (int j = 0; j < CH; j += 4) {
+            float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            if (p.residual) { o.x += res[j / 4].x; o.y += res[j / 4].y; o.z += res[j / 4].z; o.w += res[j / 4].w; }
+            *reinterpret_cast<float4*>(crow + j) = o;
+          }
+        } else {
+          epilogue_store_slow<CH>(p, acc, m, n0 + cbeg, fold, ln_mean, ln_rstd);
+        }
       }
     }
     if (threadIdx.x == 0) ND_TS(12);
@@ -501,7 +543,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
     if (lane == 0) ND_TS(14);
