@@ -144,6 +144,13 @@ ND_EXPORT int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, in
                    int32_t min_len, float alpha, int64_t* out_ids, int32_t* out_lens,
                    float* out_scores, void* stream);
 
+/* integer options (results never depend on them):
+ *   "decode_streams" (default 1, 1..16): engine-owned CUDA streams the decode loop spreads contiguous
+ *                    chunk groups over (chunks are independent);
+ *   "use_graphs"     (default 1): capture the decode loop of a repeated (mode, B, T, L, ...) configuration
+ *                    into a CUDA graph on its second call and replay it afterwards.                    */
+ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);
+
 /* per-kernel-category device timing for bench.py's roofline figures: while a category bit is set,
  * every launch of that category is bracketed by CUDA events on the launching stream;
  * nd_profile_read synchronises on the last event, returns the summed milliseconds and launch

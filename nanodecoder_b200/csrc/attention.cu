@@ -189,7 +189,7 @@ namespace {
 // contiguous: dh/4 lanes cover one position with 128-bit loads, 32/(dh/4) positions per warp access.
 __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
-  const int row = blockIdx.x;
+  const int row = p.row0 + blockIdx.x;
   if (p.retired && p.retired[row / p.rows_per_chunk]) return;
   const int d = p.d, H = p.H, dh = d / H, L = p.step + 1;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -42,9 +42,10 @@ __global__ void beam_init_kernel(BeamParams p, int bos) {
 }
 
 __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float length_penalty) {
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int bl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (b >= p.B) return;
+  if (bl >= p.nb) return;
+  const int b = p.b0 + bl;
   if (p.st.retired[b]) return;
   const int K = p.K, V = p.V, NC = K * V, Lp1 = p.Lmax + 1;
   const int cur = p.step & 1, nxt = cur ^ 1;
@@ -182,7 +183,8 @@ cudaError_t beam_step(const BeamParams& p, cudaStream_t stream) {
   if (p.K * p.V > 32 * kMaxCandPerLane || p.K > 32) return cudaErrorInvalidValue;
   // ((5 + step + 1) / 6) ** alpha in double like the Python expression (translator.py:720-721)
   const double lp = pow((5.0 + (double)(p.step + 1)) / 6.0, (double)p.alpha);
-  beam_step_kernel<<<cdiv(p.B, 4), 128, 0, stream>>>(p, (float)lp);
+  if (p.nb <= 0) return cudaSuccess;
+  beam_step_kernel<<<cdiv(p.nb, 4), 128, 0, stream>>>(p, (float)lp);
   return cudaGetLastError();
 }
 

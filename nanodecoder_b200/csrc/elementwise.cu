@@ -74,8 +74,8 @@ __global__ void transpose_bt_kernel(const float* __restrict__ in, float* __restr
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                   const int* __restrict__ parent, int rows, int width) {
-  const int r = blockIdx.x;
+                                   const int* __restrict__ parent, int row0, int width) {
+  const int r = row0 + blockIdx.x;
   const int s = parent[r];
   for (int c = threadIdx.x; c < width; c += blockDim.x) dst[(int64_t)r * width + c] = src[(int64_t)s * width + c];
 }
@@ -222,9 +222,61 @@ cudaError_t transpose_bt(const float* in, float* out, int B, int T, int d, cudaS
   return cudaGetLastError();
 }
 
-cudaError_t gather_rows(const float* src, float* dst, const int* parent, int rows, int width, cudaStream_t stream) {
+cudaError_t gather_rows(const float* src, float* dst, const int* parent, int row0, int rows, int width,
+                        cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  gather_rows_kernel<<<rows, width < 256 ? width : 256, 0, stream>>>(src, dst, parent, rows, width);
+  gather_rows_kernel<<<rows, width < 256 ? width : 256, 0, stream>>>(src, dst, parent, row0, width);
+  return cudaGetLastError();
+}
+
+namespace {
+__global__ void cnn_window_kernel(const float* __restrict__ x, float* __restrict__ hist, const int* __restrict__ anc,
+                                  int anc_ld, const int* __restrict__ retired, int rows_per_chunk,
+                                  float* __restrict__ A, int row0, int t, int k, int d, int Lmax) {
+  const int r = row0 + blockIdx.x;
+  if (retired && retired[r / rows_per_chunk]) return;     // retired chunks keep stale ancestor tables
+  for (int i = threadIdx.x; i < k * d; i += blockDim.x) {
+    const int j = i / d, c = i - j * d;
+    const int pos = t - (k - 1) + j;
+    float v = 0.f;
+    if (pos == t) {
+      v = x[(int64_t)r * d + c];
+      hist[((int64_t)r * Lmax + t) * d + c] = v;
+    } else if (pos >= 0) {
+      const int slot = anc ? anc[(int64_t)r * anc_ld + pos] : r;
+      v = hist[((int64_t)slot * Lmax + pos) * d + c];
+    }
+    A[(int64_t)r * k * d + i] = v;
+  }
+}
+__global__ void add_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, float s,
+                                 float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a[i] + b[i]) * s;
+}
+__global__ void cnn_combine_kernel(const float* __restrict__ x, const float* __restrict__ c,
+                                   const float* __restrict__ o, float s, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (x[i] + (c[i] + o[i]) * s) * s;
+}
+}  // namespace
+
+cudaError_t cnn_window(const float* x, float* hist, const int* anc, int anc_ld, const int* retired,
+                       int rows_per_chunk, float* A, int row0, int rows, int t, int k, int d, int Lmax,
+                       cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  cnn_window_kernel<<<rows, 256, 0, stream>>>(x, hist, anc, anc_ld, retired, rows_per_chunk, A, row0, t, k, d, Lmax);
+  return cudaGetLastError();
+}
+cudaError_t add_scale(const float* a, const float* b, float s, float* out, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  add_scale_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, stream>>>(a, b, s, out, n);
+  return cudaGetLastError();
+}
+cudaError_t cnn_combine(const float* x, const float* c, const float* o, float s, float* out, int64_t n,
+                        cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  cnn_combine_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, stream>>>(x, c, o, s, out, n);
   return cudaGetLastError();
 }
 
@@ -233,6 +285,35 @@ cudaError_t lstm_cell_pointwise(const float* gates_a, const float* gates_b, cons
   if (rows <= 0) return cudaSuccess;
   lstm_cell_kernel<<<(unsigned)cdiv64((int64_t)rows * d, 256), 256, 0, stream>>>(gates_a, gates_b, c_in, h_out, c_out,
                                                                                 rows, d);
+  return cudaGetLastError();
+}
+
+namespace {
+__global__ void transpose_to_dbt_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int d) {
+  __shared__ float tile[32][33];
+  // in viewed as [B*T, d] -> out [d, B*T]
+  const int64_t R = (int64_t)B * T;
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < d) ? in[r * d + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (r < R && c < d) out[(int64_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+}  // namespace
+
+cudaError_t transpose_to_dbt(const float* in, float* out, int B, int T, int d, cudaStream_t stream) {
+  const int64_t R = (int64_t)B * T;
+  if (R <= 0) return cudaSuccess;
+  dim3 grid((unsigned)cdiv64(R, 32), (unsigned)cdiv(d, 32));
+  transpose_to_dbt_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, out, B, T, d);
   return cudaGetLastError();
 }
 

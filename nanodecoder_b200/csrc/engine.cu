@@ -133,6 +133,26 @@ struct nd_engine {
   // beam state
   BeamState beam;
   int max_rows = 0;
+  // decode-loop concurrency: the batch is cut into `decode_streams` contiguous chunk groups that run the
+  // step loop on their own streams (chunks are independent), so the latency-bound projections of one
+  // group overlap the HBM-bound attention of another
+  int decode_streams = 1;
+  // CUDA graphs: the whole decode loop of a (mode, B, T, L, ...) configuration is captured once (second
+  // call with the same key) and replayed; outputs go to engine-owned buffers and are copied to the caller's
+  int use_graphs = 1;
+  struct GraphEntry {
+    std::vector<int64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+  };
+  std::vector<GraphEntry> graphs;
+  std::vector<int64_t> last_key;
+  cudaStream_t main_stream = nullptr;
+  cudaEvent_t g_in = nullptr, g_out = nullptr;
+  int64_t* o_ids = nullptr; float* o_scores = nullptr; int* o_lens = nullptr;
+  std::vector<cudaStream_t> streams;
+  std::vector<cudaEvent_t> join_ev;
+  cudaEvent_t fork_ev = nullptr;
 };
 
 namespace {
@@ -578,6 +598,10 @@ int alloc_workspace(nd_engine* e) {
     F(e->x, rows * d); F(e->cbase, rows * d); F(e->cA, rows * c.cnn_kernel_width * d); F(e->cy, rows * 2 * d);
     F(e->cout, rows * d); F(e->cpre, rows * d); F(e->ctgt, rows * d); F(e->cctx2, rows * d); F(e->x1, rows * d);
   }
+  e->o_ids = dalloc<int64_t>(e, (size_t)rows * L);
+  e->o_scores = dalloc<float>(e, (size_t)rows);
+  e->o_lens = dalloc<int>(e, (size_t)rows);
+  ok = ok && e->o_ids && e->o_scores && e->o_lens;
   // beam state
   BeamState& b = e->beam;
   b.topk_log_probs = dalloc<float>(e, rows);
@@ -707,9 +731,10 @@ int encode_cnn(nd_engine* e, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------ decoders
 struct DecodeCtx {
-  int rows = 0, K = 1, step = 0, Lmax = 0;
+  int K = 1, step = 0, Lmax = 0;
+  int c0 = 0, nc = 0;                 // chunk range handled by this call; rows = [c0*K, (c0+nc)*K)
   bool beam = false;
-  float* attn_out = nullptr;          // optional [rows, T'] for this step
+  float* attn_out = nullptr;          // optional [rows_total, T'] for this step
 };
 
 int decoder_init(nd_engine* e, int K, cudaStream_t st) {
@@ -756,107 +781,254 @@ int decoder_init(nd_engine* e, int K, cudaStream_t st) {
           }
     }
   } else {
-    return fail(e, ND_ERR_INVALID, "cnn decoder: not implemented in this build");
+    if (c.encoder_type != ND_ENC_CNN)
+      return fail(e, ND_ERR_INVALID, "cnn decoder needs the cnn encoder (its init_state adds the encoder's "
+                                     "input projection, onmt/decoders/cnn_decoder.py:59-64)");
+    // state["src"] = (memory_bank + enc_hidden) * SCALE_WEIGHT                      cnn_decoder.py:63
+    ND_LAUNCH(e, add_scale(e->mb, e->emb_remap, 0.70710678118654757f, e->enc_comb, M * d, st));
   }
   return ND_OK;
 }
 
-// one decoder step for all rows: cur_tok -> logp [rows, V] (and greedy selection when gp.ids != null)
+// one decoder step for the chunk range of dc: cur_tok -> logp [rows, V] (and greedy selection when gp.ids != null)
 int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t st) {
   const nd_config& c = e->cfg;
-  const int d = c.d_model, rows = dc.rows, B = e->B, Tp = e->Tp;
+  const int d = c.d_model, Tp = e->Tp, K = dc.K;
+  const int r0 = dc.c0 * K, rows = dc.nc * K, B_total = e->B;
   const int* retired = dc.beam ? e->beam.retired : nullptr;
-  ND_LAUNCH(e, embed_rows(e->cur_tok, e->emb, e->x, d, rows, d, c.position_encoding, dc.step, st));
+  const int* anc = (dc.beam && dc.step > 0) ? e->beam.anc + (int64_t)(dc.step & 1) * B_total * K * dc.Lmax : nullptr;
+  auto R = [&](float* p, int64_t w) { return p + (int64_t)r0 * w; };            // row-range view
+  const float s2 = 0.70710678118654757f;                                        // SCALE_WEIGHT = 0.5 ** 0.5
+  ND_LAUNCH(e, embed_rows(e->cur_tok + r0, e->emb, R(e->x, d), d, rows, d, c.position_encoding, dc.step, st));
   if (c.decoder_type == ND_DEC_TRANSFORMER) {
     const float sq = sqrtf((float)(d / c.heads));
-    float* x = e->x;
+    float* x = R(e->x, d);
     for (int l = 0; l < c.dec_layers; ++l) {
       const DecLayerT& L = e->decT[l];
       GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln1.g; o1.pb = L.ln1.b;
-      ND_TRY(run_gemm(e, L.qkv, x, d, e->qkv, 3 * d, rows, o1, st));
+      ND_TRY(run_gemm(e, L.qkv, x, d, R(e->qkv, 3 * d), 3 * d, rows, o1, st));
       SelfAttnParams sa;
-      sa.qkv = e->qkv; sa.q_div = sq; sa.Kc = e->selfK[l]; sa.Vc = e->selfV[l]; sa.ctx = e->sctx; sa.rows = rows; sa.d = d;
-      sa.H = c.heads; sa.Lmax = dc.Lmax; sa.step = dc.step; sa.retired = retired; sa.rows_per_chunk = dc.K;
-      if (dc.beam && dc.step > 0) { sa.anc = e->beam.anc + (int64_t)(dc.step & 1) * rows * dc.Lmax; sa.anc_ld = dc.Lmax; }
+      sa.qkv = e->qkv; sa.q_div = sq; sa.Kc = e->selfK[l]; sa.Vc = e->selfV[l]; sa.ctx = e->sctx; sa.row0 = r0;
+      sa.rows = rows; sa.d = d; sa.H = c.heads; sa.Lmax = dc.Lmax; sa.step = dc.step; sa.retired = retired;
+      sa.rows_per_chunk = K; sa.anc = anc; sa.anc_ld = dc.Lmax;
       ND_LAUNCH_CAT(e, ND_PROF_SELF_ATTN, st, self_attention_step(sa, st));
       GemmOpt o2; o2.residual = x; o2.ldr = d;
-      ND_TRY(run_gemm(e, L.self_out, e->sctx, d, e->x1, d, rows, o2, st));
+      ND_TRY(run_gemm(e, L.self_out, R(e->sctx, d), d, R(e->x1, d), d, rows, o2, st));
       GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln2.g; o3.pb = L.ln2.b;
-      ND_TRY(run_gemm(e, L.cq, e->x1, d, e->qc, d, rows, o3, st));
+      ND_TRY(run_gemm(e, L.cq, R(e->x1, d), d, R(e->qc, d), d, rows, o3, st));
       CrossAttnParams ca;
-      ca.q = e->qc; ca.q_ld = d; ca.q_div = sq; ca.K = e->ckv[l]; ca.V = e->ckv[l] + d; ca.kv_ld = 2 * d;
-      ca.src = e->src; ca.src_ld = e->T; ca.mask_value = 1.0f;         // decoder/transformer.py:219-221 (pad_idx = 1)
-      ca.retired = retired; ca.ctx = e->cctx; ca.ctx_ld = d; ca.n_chunks = B; ca.NQ = dc.K; ca.T = Tp; ca.d = d;
-      ca.H = c.heads;
-      ca.attn = (l + 1 == c.dec_layers) ? dc.attn_out : nullptr;
+      ca.q = R(e->qc, d); ca.q_ld = d; ca.q_div = sq;
+      ca.K = e->ckv[l] + (int64_t)dc.c0 * Tp * 2 * d; ca.V = ca.K + d; ca.kv_ld = 2 * d;
+      ca.src = e->src + (int64_t)dc.c0 * e->T; ca.src_ld = e->T; ca.mask_value = 1.0f;   // decoder/transformer.py:219-221
+      ca.retired = retired ? retired + dc.c0 : nullptr; ca.ctx = R(e->cctx, d); ca.ctx_ld = d; ca.n_chunks = dc.nc;
+      ca.NQ = K; ca.T = Tp; ca.d = d; ca.H = c.heads;
+      ca.attn = (l + 1 == c.dec_layers && dc.attn_out) ? dc.attn_out + (int64_t)r0 * Tp : nullptr;
       ND_LAUNCH_CAT(e, ND_PROF_CROSS_ATTN, st, cross_attention(ca, st));
-      GemmOpt o4; o4.residual = e->x1; o4.ldr = d;
-      ND_TRY(run_gemm(e, L.ctx_out, e->cctx, d, e->x2, d, rows, o4, st));
+      GemmOpt o4; o4.residual = R(e->x1, d); o4.ldr = d;
+      ND_TRY(run_gemm(e, L.ctx_out, R(e->cctx, d), d, R(e->x2, d), d, rows, o4, st));
       GemmOpt o5; o5.prologue = PRO_LAYERNORM; o5.pg = L.ln_ff.g; o5.pb = L.ln_ff.b; o5.act = 1;
-      ND_TRY(run_gemm(e, L.w1, e->x2, d, e->ffh, c.d_ff, rows, o5, st));
-      GemmOpt o6; o6.residual = e->x2; o6.ldr = d;
-      ND_TRY(run_gemm(e, L.w2, e->ffh, c.d_ff, x, d, rows, o6, st));
+      ND_TRY(run_gemm(e, L.w1, R(e->x2, d), d, R(e->ffh, c.d_ff), c.d_ff, rows, o5, st));
+      GemmOpt o6; o6.residual = R(e->x2, d); o6.ldr = d;
+      ND_TRY(run_gemm(e, L.w2, R(e->ffh, c.d_ff), c.d_ff, x, d, rows, o6, st));
     }
     gp.x = x; gp.x_ld = d; gp.ln_g = e->dec_ln.g; gp.ln_b = e->dec_ln.b;
   } else if (c.decoder_type == ND_DEC_RNN) {
     const int cur = dc.step & 1, nxt = cur ^ 1;
-    // with beams the state of step-1 was written for the parents' rows: gather it first
-    std::vector<float*>&hc = e->rh[cur], &cc = e->rc[cur], &hn = e->rh[nxt], &cn = e->rc[nxt];
-    float* feed_c = e->feed[cur];
+    if (dc.beam && dc.step > 0) {
+      // reorder the recurrent state by parent beam (translator.py:820-821 map_state index_select): the state
+      // written by step-1 sits in buffers [cur]; gather through the spare [nxt] buffers and copy back
+      for (int l = 0; l < c.dec_layers; ++l) {
+        ND_LAUNCH(e, gather_rows(e->rh[cur][l], e->rh[nxt][l], e->beam.parent, r0, rows, d, st));
+        ND_LAUNCH(e, gather_rows(e->rc[cur][l], e->rc[nxt][l], e->beam.parent, r0, rows, d, st));
+        ND_CUDA(e, cudaMemcpyAsync(R(e->rh[cur][l], d), R(e->rh[nxt][l], d), (size_t)rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        ND_CUDA(e, cudaMemcpyAsync(R(e->rc[cur][l], d), R(e->rc[nxt][l], d), (size_t)rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
+      ND_LAUNCH(e, gather_rows(e->feed[cur], e->feed[nxt], e->beam.parent, r0, rows, d, st));
+      ND_CUDA(e, cudaMemcpyAsync(R(e->feed[cur], d), R(e->feed[nxt], d), (size_t)rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
     const float* below = nullptr;
     for (int l = 0; l < c.dec_layers; ++l) {
-      const nd_engine::RnnCell& R = e->cells[l];
+      const nd_engine::RnnCell& Rc = e->cells[l];
       GemmOpt oa;
       if (l == 0 && c.input_feed) {
-        ND_TRY(run_gemm(e, R.ih_e, e->x, d, e->ga, 4 * d, rows, oa, st));
-        GemmOpt of; of.residual = e->ga; of.ldr = 4 * d;
-        ND_TRY(run_gemm(e, R.ih_f, feed_c, d, e->ga, 4 * d, rows, of, st));
+        ND_TRY(run_gemm(e, Rc.ih_e, R(e->x, d), d, R(e->ga, 4 * d), 4 * d, rows, oa, st));
+        GemmOpt of; of.residual = R(e->ga, 4 * d); of.ldr = 4 * d;
+        ND_TRY(run_gemm(e, Rc.ih_f, R(e->feed[cur], d), d, R(e->ga, 4 * d), 4 * d, rows, of, st));
       } else {
-        ND_TRY(run_gemm(e, R.ih, l == 0 ? e->x : below, d, e->ga, 4 * d, rows, oa, st));
+        ND_TRY(run_gemm(e, Rc.ih, l == 0 ? R(e->x, d) : below, d, R(e->ga, 4 * d), 4 * d, rows, oa, st));
       }
       GemmOpt ob;
-      ND_TRY(run_gemm(e, R.hh, hc[l], d, e->gb, 4 * d, rows, ob, st));
-      ND_LAUNCH(e, lstm_cell_pointwise(e->ga, e->gb, cc[l], hn[l], cn[l], rows, d, st));
-      below = hn[l];
+      ND_TRY(run_gemm(e, Rc.hh, R(e->rh[cur][l], d), d, R(e->gb, 4 * d), 4 * d, rows, ob, st));
+      ND_LAUNCH(e, lstm_cell_pointwise(R(e->ga, 4 * d), R(e->gb, 4 * d), R(e->rc[cur][l], d), R(e->rh[nxt][l], d),
+                                       R(e->rc[nxt][l], d), rows, d, st));
+      below = R(e->rh[nxt][l], d);
     }
     MlpAttnParams ma;
-    ma.mem = e->mb; ma.lengths = e->mem_len; ma.retired = retired; ma.ctx = e->actx; ma.ctx_ld = d;
-    ma.n_chunks = B; ma.NQ = dc.K; ma.T = Tp; ma.d = d; ma.attn = dc.attn_out;
-    if (c.attn_type == ND_ATTN_MLP) {
-      GemmOpt oq;
-      ND_TRY(run_gemm(e, e->attn_q, below, d, e->wq, d, rows, oq, st));
-      ma.wq = e->wq; ma.uh = e->uh; ma.v = e->attn_v;
-    } else {
-      ma.dot = 1; ma.uh = e->mb;
-      if (c.attn_type == ND_ATTN_GENERAL) {
-        GemmOpt oq;
-        ND_TRY(run_gemm(e, e->attn_in, below, d, e->wq, d, rows, oq, st));
-        ma.wq = e->wq;
-      } else {
-        ma.wq = below;
-      }
-    }
-    ND_LAUNCH_CAT(e, ND_PROF_MLP_ATTN, st, mlp_attention(ma, st));
-    // attn_h = W_out [c ; h] (+ b for mlp; tanh otherwise)            global_attention.py:197-200
-    GemmOpt oc;
-    ND_TRY(run_gemm(e, e->attn_out_c, e->actx, d, e->wq, d, rows, oc, st));
-    GemmOpt oh; oh.residual = nullptr;
-    // second half accumulates on top of the first through the residual input; tanh must come last, so for
-    // general/dot attention the first product is added as residual BEFORE the activation is not possible:
-    // use act only with mlp == none.
-    if (c.attn_type == ND_ATTN_MLP) {
-      oh.residual = e->wq; oh.ldr = d;
-      ND_TRY(run_gemm(e, e->attn_out_h, below, d, e->feed[nxt], d, rows, oh, st));
-    } else {
+    ma.mem = e->mb + (int64_t)dc.c0 * Tp * d; ma.lengths = e->mem_len + dc.c0;
+    ma.retired = retired ? retired + dc.c0 : nullptr; ma.ctx = R(e->actx, d); ma.ctx_ld = d;
+    ma.n_chunks = dc.nc; ma.NQ = K; ma.T = Tp; ma.d = d;
+    ma.attn = dc.attn_out ? dc.attn_out + (int64_t)r0 * Tp : nullptr;
+    if (c.attn_type != ND_ATTN_MLP)
       return fail(e, ND_ERR_INVALID, "general/dot global attention: not implemented in this build");
-    }
-    gp.x = e->feed[nxt]; gp.x_ld = d; gp.ln_g = nullptr; gp.ln_b = nullptr;
+    GemmOpt oq;
+    ND_TRY(run_gemm(e, e->attn_q, below, d, R(e->wq, d), d, rows, oq, st));
+    ma.wq = R(e->wq, d); ma.uh = e->uh + (int64_t)dc.c0 * Tp * d; ma.v = e->attn_v;
+    ND_LAUNCH_CAT(e, ND_PROF_MLP_ATTN, st, mlp_attention(ma, st));
+    // attn_h = W_out [c ; h] + b (no tanh for mlp)                           global_attention.py:197-200
+    GemmOpt oc;
+    ND_TRY(run_gemm(e, e->attn_out_c, R(e->actx, d), d, R(e->wq, d), d, rows, oc, st));
+    GemmOpt oh; oh.residual = R(e->wq, d); oh.ldr = d;
+    ND_TRY(run_gemm(e, e->attn_out_h, below, d, R(e->feed[nxt], d), d, rows, oh, st));
+    gp.x = R(e->feed[nxt], d); gp.x_ld = d; gp.ln_g = nullptr; gp.ln_b = nullptr;
   } else {
-    return fail(e, ND_ERR_INVALID, "cnn decoder: not implemented in this build");
+    // CNN decoder, incremental (the reference re-runs the whole prefix each step, cnn_decoder.py:79-80; the
+    // convolutions are causal, so position t only needs the last k inputs of every layer)
+    const int k = c.cnn_kernel_width;
+    GemmOpt ol;
+    ND_TRY(run_gemm(e, e->dec_lin, R(e->x, d), d, R(e->cbase, d), d, rows, ol, st));       // :97-100
+    const float* xl = R(e->cbase, d);
+    float* xbuf[2] = {R(e->x1, d), R(e->x, d)};
+    for (int l = 0; l < c.dec_layers; ++l) {
+      ND_LAUNCH(e, cnn_window(xl - (int64_t)r0 * d, e->chist[0][l], anc, dc.Lmax, retired, K, e->cA, r0, rows,
+                              dc.step, k, d, dc.Lmax, st));
+      GemmOpt ocv;
+      ND_TRY(run_gemm(e, e->dec_conv[l].conv, R(e->cA, (int64_t)k * d), (int64_t)k * d, R(e->cy, 2 * d), 2 * d, rows, ocv, st));
+      ND_LAUNCH(e, glu_residual(R(e->cy, 2 * d), nullptr, nullptr, R(e->cout, d), rows, d, st));       // out = a*sigmoid(g)
+      GemmOpt oi;
+      ND_TRY(run_gemm(e, e->dec_attn_in[l], R(e->cout, d), d, R(e->cpre, d), d, rows, oi, st));
+      ND_LAUNCH(e, add_scale(R(e->cbase, d), R(e->cpre, d), s2, R(e->ctgt, d), (int64_t)rows * d, st));
+      MlpAttnParams ma;
+      ma.dot = 1; ma.wq = R(e->ctgt, d); ma.uh = e->mb + (int64_t)dc.c0 * Tp * d;        // keys: encoder top
+      ma.mem = e->enc_comb + (int64_t)dc.c0 * Tp * d;                                     // values: combined
+      ma.lengths = nullptr; ma.retired = retired ? retired + dc.c0 : nullptr; ma.ctx = R(e->cctx2, d); ma.ctx_ld = d;
+      ma.n_chunks = dc.nc; ma.NQ = K; ma.T = Tp; ma.d = d;
+      ma.attn = (l + 1 == c.dec_layers && dc.attn_out) ? dc.attn_out + (int64_t)r0 * Tp : nullptr;
+      ND_LAUNCH_CAT(e, ND_PROF_MLP_ATTN, st, mlp_attention(ma, st));
+      float* xn = xbuf[l & 1];
+      ND_LAUNCH(e, cnn_combine(xl, R(e->cctx2, d), R(e->cout, d), s2, xn, (int64_t)rows * d, st));      // :116
+      xl = xn;
+    }
+    gp.x = xl; gp.x_ld = d; gp.ln_g = nullptr; gp.ln_b = nullptr;
   }
-  gp.Wg = e->gen.W; gp.bg = e->gen.b; gp.logp = e->logp; gp.rows = rows; gp.d = d; gp.V = c.vocab_size;
-  gp.step = dc.step;
+  gp.Wg = e->gen.W; gp.bg = e->gen.b; gp.logp = R(e->logp, c.vocab_size); gp.rows = rows; gp.d = d;
+  gp.V = c.vocab_size; gp.step = dc.step;
   ND_LAUNCH_CAT(e, ND_PROF_GENERATOR, st, generator_step(gp, st));
+  return ND_OK;
+}
+
+// fork the caller's stream into the engine's decode streams / join them back
+int fork_streams(nd_engine* e, cudaStream_t st, int n) {
+  ND_CUDA(e, cudaEventRecord(e->fork_ev, st));
+  for (int g = 0; g < n; ++g) ND_CUDA(e, cudaStreamWaitEvent(e->streams[g], e->fork_ev, 0));
+  return ND_OK;
+}
+int join_streams(nd_engine* e, cudaStream_t st, int n) {
+  for (int g = 0; g < n; ++g) {
+    ND_CUDA(e, cudaEventRecord(e->join_ev[g], e->streams[g]));
+    ND_CUDA(e, cudaStreamWaitEvent(st, e->join_ev[g], 0));
+  }
+  return ND_OK;
+}
+int n_groups(const nd_engine* e, int B) {
+  int n = e->decode_streams;
+  if (e->prof_mask) n = 1;                       // per-kernel event timing wants kernels that run alone
+  if (n > (int)e->streams.size()) n = (int)e->streams.size();
+  while (n > 1 && B / n < 64) --n;               // tiny groups only add launch overhead
+  return n < 1 ? 1 : n;
+}
+
+int greedy_body(nd_engine* e, int max_len, int min_len, int64_t* out_ids, float* out_scores, float* out_attn,
+                       float* out_logits, cudaStream_t st) {
+  const int B = e->B, V = e->cfg.vocab_size;
+  ND_TRY(decoder_init(e, 1, st));
+  ND_LAUNCH(e, fill_int(e->cur_tok, B, 2, st));          // <s> for every row (translator.py:451-452)
+  const int G = n_groups(e, B);
+  if (G > 1) ND_TRY(fork_streams(e, st, G));
+  for (int step = 0; step < max_len; ++step) {           // no EOS early exit, like the reference (:455)
+    for (int g = 0; g < G; ++g) {
+      DecodeCtx dc;
+      dc.K = 1; dc.Lmax = e->cfg.max_tgt_len; dc.beam = false; dc.step = step;
+      dc.c0 = (int)((int64_t)B * g / G);
+      dc.nc = (int)((int64_t)B * (g + 1) / G) - dc.c0;
+      dc.attn_out = out_attn ? out_attn + (int64_t)step * B * e->Tp : nullptr;
+      GenParams gp;
+      gp.ids = out_ids + (int64_t)dc.c0 * max_len; gp.ids_ld = max_len; gp.scores = out_scores + dc.c0;
+      gp.next_tok = e->cur_tok + dc.c0;
+      gp.trace = out_logits ? out_logits + ((int64_t)step * B + dc.c0) * V : nullptr;
+      gp.min_len = min_len;
+      ND_TRY(decoder_step(e, dc, gp, G > 1 ? e->streams[g] : st));
+    }
+  }
+  if (G > 1) ND_TRY(join_streams(e, st, G));
+  return ND_OK;
+}
+
+int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float alpha, int64_t* out_ids,
+                     int32_t* out_lens, float* out_scores, cudaStream_t st) {
+  const int B = e->B;
+  ND_TRY(decoder_init(e, K, st));
+  BeamParams bp;
+  bp.logp = e->logp; bp.st = e->beam; bp.B = B; bp.K = K; bp.V = e->cfg.vocab_size; bp.Lmax = e->cfg.max_tgt_len;
+  bp.max_len = max_len; bp.min_len = min_len; bp.n_best = n_best; bp.alpha = alpha;
+  ND_LAUNCH(e, beam_init(bp, 2, st));
+  const int G = n_groups(e, B);
+  if (G > 1) ND_TRY(fork_streams(e, st, G));
+  for (int step = 0; step < max_len; ++step) {
+    for (int g = 0; g < G; ++g) {
+      cudaStream_t gs = G > 1 ? e->streams[g] : st;
+      DecodeCtx dc;
+      dc.K = K; dc.Lmax = e->cfg.max_tgt_len; dc.beam = true; dc.step = step;
+      dc.c0 = (int)((int64_t)B * g / G);
+      dc.nc = (int)((int64_t)B * (g + 1) / G) - dc.c0;
+      GenParams gp;
+      gp.min_len = min_len;
+      ND_TRY(decoder_step(e, dc, gp, gs));
+      bp.step = step; bp.b0 = dc.c0; bp.nb = dc.nc;
+      ND_LAUNCH_CAT(e, ND_PROF_BEAM, gs, beam_step(bp, gs));
+    }
+  }
+  if (G > 1) ND_TRY(join_streams(e, st, G));
+  ND_LAUNCH(e, beam_finalize(bp, out_ids, out_lens, out_scores, st));
+  return ND_OK;
+}
+
+// Run `body(stream)` either eagerly on the caller's stream or as a cached CUDA graph on the engine's
+// main stream (bracketed by events so it is ordered inside the caller's stream).
+template <class Body>
+int run_cached(nd_engine* e, const std::vector<int64_t>& key, cudaStream_t st, Body body) {
+  nd_engine::GraphEntry* hit = nullptr;
+  for (auto& g : e->graphs)
+    if (g.key == key) hit = &g;
+  if (!hit) {
+    if (e->last_key != key) {            // first sighting: run eagerly (also warms up lazy kernel attributes)
+      e->last_key = key;
+      return body(st);
+    }
+    // second call with the same configuration: capture
+    cudaGraph_t graph = nullptr;
+    const int64_t before = e->launches;
+    ND_CUDA(e, cudaStreamBeginCapture(e->main_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(e->main_stream);
+    cudaError_t err = cudaStreamEndCapture(e->main_stream, &graph);
+    if (rc != ND_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (err != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(err)); }
+    nd_engine::GraphEntry ge;
+    ge.key = key;
+    ge.launches = e->launches - before;
+    e->launches = before;
+    err = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) { e->sticky = true; return fail(e, ND_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(err)); }
+    if (e->graphs.size() >= 8) { cudaGraphExecDestroy(e->graphs.front().exec); e->graphs.erase(e->graphs.begin()); }
+    e->graphs.push_back(ge);
+    hit = &e->graphs.back();
+  }
+  ND_CUDA(e, cudaEventRecord(e->g_in, st));
+  ND_CUDA(e, cudaStreamWaitEvent(e->main_stream, e->g_in, 0));
+  ND_CUDA(e, cudaGraphLaunch(hit->exec, e->main_stream));
+  ND_CUDA(e, cudaEventRecord(e->g_out, e->main_stream));
+  ND_CUDA(e, cudaStreamWaitEvent(st, e->g_out, 0));
+  e->launches += hit->launches;
   return ND_OK;
 }
 
@@ -903,7 +1075,16 @@ int nd_create(const nd_config* cfg, nd_engine** out) {
     for (void* p : e->allocs) if (p) cudaFree(p);
     return rc;
   }
-  *out = e.release();
+  if (cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->g_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->g_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->main_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(nullptr, ND_ERR_CUDA, "cudaEventCreate / cudaStreamCreate failed");
+  nd_engine* raw = e.release();
+  rc = nd_set_int(raw, "decode_streams", 4);
+  if (rc == ND_OK) raw->decode_streams = 1;   // streams exist, default is the single-stream schedule
+  if (rc != ND_OK) { g_create_error = raw->err; nd_destroy(raw); return rc; }
+  *out = raw;
   return ND_OK;
 }
 
@@ -911,6 +1092,13 @@ int nd_destroy(nd_engine* e) {
   if (!e) return ND_OK;
   cudaSetDevice(e->cfg.device);
   for (cudaEvent_t ev : e->prof_pool) cudaEventDestroy(ev);
+  for (cudaStream_t s2 : e->streams) cudaStreamDestroy(s2);
+  for (cudaEvent_t ev : e->join_ev) cudaEventDestroy(ev);
+  if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+  for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (e->g_in) cudaEventDestroy(e->g_in);
+  if (e->g_out) cudaEventDestroy(e->g_out);
+  if (e->main_stream) cudaStreamDestroy(e->main_stream);
   for (void* p : e->allocs) if (p) cudaFree(p);
   delete e;
   return ND_OK;
@@ -1037,8 +1225,8 @@ int nd_get_memory_bank(nd_engine* e, float* out, int64_t* out_lengths, int32_t* 
   cudaStream_t st = (cudaStream_t)stream;
   if (out_Tp) *out_Tp = e->Tp;
   if (out) {
-    if (e->cfg.encoder_type == ND_ENC_CNN) return fail(e, ND_ERR_INVALID, "cnn memory bank export: not implemented");
-    ND_LAUNCH(e, transpose_bt(e->mb, out, e->B, e->Tp, e->cfg.d_model, st));
+    if (e->cfg.encoder_type == ND_ENC_CNN) ND_LAUNCH(e, transpose_to_dbt(e->mb, out, e->B, e->Tp, e->cfg.d_model, st));
+    else ND_LAUNCH(e, transpose_bt(e->mb, out, e->B, e->Tp, e->cfg.d_model, st));
   }
   if (out_lengths)
     ND_CUDA(e, cudaMemcpyAsync(out_lengths, e->mem_len, (size_t)e->B * sizeof(int64_t), cudaMemcpyDefault, st));
@@ -1052,20 +1240,15 @@ int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* ou
   if (max_len < 1 || max_len > e->cfg.max_tgt_len) return fail(e, ND_ERR_INVALID, "max_len outside nd_create sizes");
   if (!out_ids || !out_scores) return fail(e, ND_ERR_INVALID, "null output");
   cudaStream_t st = (cudaStream_t)stream;
-  const int B = e->B, V = e->cfg.vocab_size;
-  ND_TRY(decoder_init(e, 1, st));
-  ND_LAUNCH(e, fill_int(e->cur_tok, B, 2, st));          // <s> for every row (translator.py:451-452)
-  DecodeCtx dc;
-  dc.rows = B; dc.K = 1; dc.Lmax = e->cfg.max_tgt_len; dc.beam = false;
-  for (int step = 0; step < max_len; ++step) {           // no EOS early exit, like the reference (:455)
-    dc.step = step;
-    dc.attn_out = out_attn ? out_attn + (int64_t)step * B * e->Tp : nullptr;
-    GenParams gp;
-    gp.ids = out_ids; gp.ids_ld = max_len; gp.scores = out_scores; gp.next_tok = e->cur_tok;
-    gp.trace = out_logits ? out_logits + (int64_t)step * B * V : nullptr;
-    gp.min_len = min_len;
-    ND_TRY(decoder_step(e, dc, gp, st));
-  }
+  if (out_attn || out_logits || e->prof_mask || !e->use_graphs)
+    return greedy_body(e, max_len, min_len, out_ids, out_scores, out_attn, out_logits, st);
+  const int B = e->B;
+  const std::vector<int64_t> key = {0, B, e->T, e->Tp, max_len, min_len, 1, 1, 0, n_groups(e, B)};
+  ND_TRY(run_cached(e, key, st, [&](cudaStream_t s2) {
+    return greedy_body(e, max_len, min_len, e->o_ids, e->o_scores, nullptr, nullptr, s2);
+  }));
+  ND_CUDA(e, cudaMemcpyAsync(out_ids, e->o_ids, (size_t)B * max_len * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  ND_CUDA(e, cudaMemcpyAsync(out_scores, e->o_scores, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return ND_OK;
 }
 
@@ -1076,39 +1259,44 @@ int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_
   if (beam_size < 1 || beam_size > e->cfg.max_beam) return fail(e, ND_ERR_INVALID, "beam_size outside nd_create sizes");
   if (n_best < 1 || n_best > beam_size) return fail(e, ND_ERR_INVALID, "n_best must be in [1, beam_size]");
   if (max_len < 1 || max_len > e->cfg.max_tgt_len) return fail(e, ND_ERR_INVALID, "max_len outside nd_create sizes");
+  if (!out_ids || !out_lens || !out_scores) return fail(e, ND_ERR_INVALID, "null output");
   cudaStream_t st = (cudaStream_t)stream;
   const int B = e->B, K = beam_size;
-  ND_TRY(decoder_init(e, K, st));
-  BeamParams bp;
-  bp.logp = e->logp; bp.st = e->beam; bp.B = B; bp.K = K; bp.V = e->cfg.vocab_size; bp.Lmax = e->cfg.max_tgt_len;
-  bp.max_len = max_len; bp.min_len = min_len; bp.n_best = n_best; bp.alpha = alpha;
-  ND_LAUNCH(e, beam_init(bp, 2, st));
-  DecodeCtx dc;
-  dc.rows = B * K; dc.K = K; dc.Lmax = e->cfg.max_tgt_len; dc.beam = true;
-  const int d = e->cfg.d_model;
-  for (int step = 0; step < max_len; ++step) {
-    dc.step = step;
-    if (e->cfg.decoder_type == ND_DEC_RNN && step > 0) {
-      // reorder the recurrent state by parent beam (translator.py:820-821 map_state index_select)
-      const int cur = step & 1, prv = cur ^ 1;
-      // state of the previous step lives in buffers [cur] (written as "nxt" there); gather into [prv] and swap roles
-      for (int l = 0; l < e->cfg.dec_layers; ++l) {
-        ND_LAUNCH(e, gather_rows(e->rh[cur][l], e->rh[prv][l], e->beam.parent, dc.rows, d, st));
-        ND_LAUNCH(e, gather_rows(e->rc[cur][l], e->rc[prv][l], e->beam.parent, dc.rows, d, st));
-        ND_CUDA(e, cudaMemcpyAsync(e->rh[cur][l], e->rh[prv][l], (size_t)dc.rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        ND_CUDA(e, cudaMemcpyAsync(e->rc[cur][l], e->rc[prv][l], (size_t)dc.rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      }
-      ND_LAUNCH(e, gather_rows(e->feed[cur], e->feed[prv], e->beam.parent, dc.rows, d, st));
-      ND_CUDA(e, cudaMemcpyAsync(e->feed[cur], e->feed[prv], (size_t)dc.rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    }
-    GenParams gp;
-    gp.min_len = min_len;
-    ND_TRY(decoder_step(e, dc, gp, st));
-    bp.step = step;
-    ND_LAUNCH_CAT(e, ND_PROF_BEAM, st, beam_step(bp, st));
-  }
-  ND_LAUNCH(e, beam_finalize(bp, out_ids, out_lens, out_scores, st));
+  if (e->prof_mask || !e->use_graphs)
+    return beam_body(e, K, n_best, max_len, min_len, alpha, out_ids, out_lens, out_scores, st);
+  int32_t alpha_bits;
+  memcpy(&alpha_bits, &alpha, sizeof(alpha_bits));
+  const std::vector<int64_t> key = {1, B, e->T, e->Tp, max_len, min_len, K, n_best, alpha_bits, n_groups(e, B)};
+  ND_TRY(run_cached(e, key, st, [&](cudaStream_t s2) {
+    return beam_body(e, K, n_best, max_len, min_len, alpha, e->o_ids, e->o_lens, e->o_scores, s2);
+  }));
+  ND_CUDA(e, cudaMemcpyAsync(out_ids, e->o_ids, (size_t)B * n_best * max_len * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  ND_CUDA(e, cudaMemcpyAsync(out_lens, e->o_lens, (size_t)B * n_best * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  ND_CUDA(e, cudaMemcpyAsync(out_scores, e->o_scores, (size_t)B * n_best * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return ND_OK;
+}
+
+int nd_set_int(nd_engine* e, const char* name, int64_t value) {
+  if (!e || !name) return ND_ERR_INVALID;
+  if (strcmp(name, "decode_streams") == 0) {
+    if (value < 1 || value > 16) return fail(e, ND_ERR_INVALID, "decode_streams must be in [1,16]");
+    cudaSetDevice(e->cfg.device);
+    while ((int64_t)e->streams.size() < value) {
+      cudaStream_t s2;
+      cudaEvent_t ev;
+      ND_CUDA(e, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      ND_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->streams.push_back(s2);
+      e->join_ev.push_back(ev);
+    }
+    e->decode_streams = (int)value;
+    return ND_OK;
+  }
+  if (strcmp(name, "use_graphs") == 0) {
+    e->use_graphs = value != 0;
+    return ND_OK;
+  }
+  return fail(e, ND_ERR_INVALID, std::string("unknown option '") + name + "'");
 }
 
 int nd_debug_gemm_timeline(int64_t* dev_buf32) {

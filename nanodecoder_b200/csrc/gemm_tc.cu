@@ -45,7 +45,7 @@ struct Cfg {
   static constexpr int kStagesFit = (200 * 1024 - RECV_BYTES) / STAGE_BYTES;
   static constexpr int kStages = kStagesFit >= 6 ? 6 : kStagesFit;
   static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BM * 4 /*row stats*/ + 2 * BN * 4 /*epilogue vectors*/ +
-                                   4 * BM * 4 /*half-row moments*/;
+                                   6 * BM * 4 /*half-row moments*/;
   static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + RECV_BYTES + 1024 /*align*/ + AUX_BYTES;
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 };
@@ -208,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_stats = reinterpret_cast<float*>(aux + 256);              // [BM][2] (mean, M2) per (source rank, row)
   float* s_vec0 = s_stats + 2 * BM;                                  // [BN] bias | folded-LN cvec of this tile
   float* s_vec1 = s_vec0 + BN;                                       // [BN] folded-LN dvec
-  float* s_mom = s_vec1 + BN;                                        // [2][BM][2] half-row (s1, s2) moments
+  float* s_mom = s_vec1 + BN;                                        // [2][BM][3] half-row (n, mean, M2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) ND_TS(0);
@@ -327,6 +327,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m = m0 + row;
     const int sw = row & 7;
     float x0 = 0.f, s1 = 0.f, s2 = 0.f;         // shifted one-pass moments for the folded LayerNorm
+    int cnt = 0;
     for (int i = 0; i < KB; ++i) {
       const int s = i % C::kStages;
       const uint32_t it = i / C::kStages;
@@ -335,11 +336,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (NPASS == 3 || fold) {
         uint8_t* rh = a_hi(s) + row * 128;
         uint8_t* rl = a_lo(s) + row * 128;
-        if (fold && i == 0) x0 = *reinterpret_cast<float*>(rh + (sw << 4));       // first element of this K slice
         // all four chunks first (loads cannot be hoisted over the in-place stores by the compiler)
         float4 vin[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) vin[c] = *reinterpret_cast<float4*>(rh + (((4 * half + c) ^ sw) << 4));
+        if (fold && i == 0) x0 = vin[0].x;      // shift = first element of THIS thread's share (race free)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {           // logical 16-byte chunk lc lives at physical chunk lc ^ (row & 7)
           const int lc = 4 * half + c;
@@ -349,7 +350,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (fold) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float dlt = (kbase + q < p.K) ? x[q] - x0 : 0.f;
+              const bool in = kbase + q < p.K;
+              const float dlt = in ? x[q] - x0 : 0.f;
+              cnt += in ? 1 : 0;
               s1 += dlt;
               s2 = fmaf(dlt, dlt, s2);
             }
@@ -372,20 +375,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (threadIdx.x == 0 && i == 0) ND_TS(7);
     }
     if (threadIdx.x == 0) ND_TS(8);
-    // combine the two half-row moment sums: this CTA's K slice has n_s elements, mean_s, M2_s
+    // each thread: (cnt, mean, M2) of its half-row share; combine the two halves (Chan et al.) into the
+    // moments of this CTA's K slice
     float mean_s = 0.f, m2_s = 0.f;
     if (fold) {
-      s_mom[(half * BM + row) * 2] = s1;
-      s_mom[(half * BM + row) * 2 + 1] = s2;
+      float mean_h = 0.f, m2_h = 0.f;
+      if (cnt > 0) {
+        const float ds = s1 / (float)cnt;
+        mean_h = x0 + ds;
+        m2_h = fmaxf(s2 - s1 * ds, 0.f);
+      }
+      float* mo = s_mom + (half * BM + row) * 3;
+      mo[0] = (float)cnt; mo[1] = mean_h; mo[2] = m2_h;
       asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
-      const float t1 = s_mom[row * 2] + s_mom[(BM + row) * 2];
-      const float t2 = s_mom[row * 2 + 1] + s_mom[(BM + row) * 2 + 1];
-      const int k_lo = kb0 * BK;
-      const int n_s = max(0, min(p.K, k_lo + KB * BK) - k_lo);
-      if (n_s > 0) {
-        const float ds = t1 / (float)n_s;
-        mean_s = x0 + ds;
-        m2_s = fmaxf(t2 - t1 * ds, 0.f);
+      const float* a = s_mom + row * 3;
+      const float* b = s_mom + (BM + row) * 3;
+      const float na = a[0], nb = b[0], nt = na + nb;
+      if (nt > 0.f) {
+        const float delta = b[1] - a[1];
+        mean_s = a[1] + delta * (nb / nt);
+        m2_s = a[2] + b[2] + delta * delta * (na * nb / nt);
       }
     }
 
@@ -616,14 +625,18 @@ cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
 
 template <int NPASS>
 cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
-  // tile width: wide tiles when there is plenty of work (encoder-side GEMMs), narrow tiles plus
-  // split-K over a cluster when M is small (decode-step GEMMs) so that ~one wave of the 148 SMs is busy
+  // Tile width follows the amount of work (wide tiles for the encoder-side GEMMs).  The split-K factor
+  // fixes the summation order of every output element, so for the decode-step GEMMs (M < 8192 rows) it
+  // is a function of (N, K) ONLY: the same chunk then produces bit-identical results whatever batch or
+  // stream group it is decoded in.  It is sized so that ~1024 rows fill about one wave of the 148 SMs.
   const int KB = cdiv(p.K, BK);
   const int64_t tiles128 = (int64_t)cdiv(p.N, 128) * cdiv(p.M, BM);
-  if (tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
-  const int64_t tiles64 = (int64_t)cdiv(p.N, 64) * cdiv(p.M, BM);
   int split = 1;
-  while (split < 4 && KB % (split * 2) == 0 && KB / (split * 2) >= 2 && tiles64 * split * 2 <= 160) split *= 2;
+  if (p.M < 8192) {
+    const int ref_tiles = 8 * cdiv(p.N, 64);           // 64-wide tiles of a 1024-row problem
+    while (split < 4 && KB % (split * 2) == 0 && KB / (split * 2) >= 2 && ref_tiles * split * 2 <= 160) split *= 2;
+  }
+  if (split == 1 && tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
   switch (split) {
     case 4: return launch<64, NPASS, 4>(p, stream);
     case 2: return launch<64, NPASS, 2>(p, stream);

@@ -35,6 +35,7 @@ struct SelfAttnParams {
   const int* anc = nullptr; int anc_ld = 0;       // optional [rows, Lmax]
   const int* retired = nullptr; int rows_per_chunk = 1;
   float* ctx = nullptr;                           // [rows, d]
+  int row0 = 0;                                   // first row of the range handled by this launch (all bases global)
   int rows = 0, d = 0, H = 8, Lmax = 0, step = 0;
 };
 cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream);
@@ -78,6 +79,8 @@ cudaError_t linear_in1(const float* x, const float* w, const float* bias, float*
 // MaxPool1d(stride) over time: in [B,T,d] -> out [B,T/stride,d]   (encoder/nano_encoder.py:101-105)
 cudaError_t maxpool_time(const float* in, float* out, int B, int T, int d, int stride, cudaStream_t stream);
 cudaError_t fill_int(int* p, int n, int value, cudaStream_t stream);
+// out[c,b,t] = in[b,t,c]  (the CNN encoder's reference layout, encoder/cnn_encoder.py:43-44)
+cudaError_t transpose_to_dbt(const float* in, float* out, int B, int T, int d, cudaStream_t stream);
 // out[t,b,:] = in[b,t,:]  (chunk-major -> reference time-major layout)
 cudaError_t transpose_bt(const float* in, float* out, int B, int T, int d, cudaStream_t stream);
 
@@ -118,6 +121,7 @@ struct BeamParams {
   const float* logp = nullptr;                    // [B*K, V]
   BeamState st;
   int B = 0, K = 0, V = 0, Lmax = 0, step = 0, max_len = 0, min_len = 0, n_best = 1, eos = 3;
+  int b0 = 0, nb = 0;                             // chunk range [b0, b0+nb) handled by this launch (B = total)
   float alpha = 0.f;
 };
 cudaError_t beam_init(const BeamParams& p, int bos, cudaStream_t stream);
@@ -125,7 +129,7 @@ cudaError_t beam_step(const BeamParams& p, cudaStream_t stream);
 cudaError_t beam_finalize(const BeamParams& p, int64_t* out_ids, int* out_lens, float* out_scores,
                           cudaStream_t stream);
 // reorder per-row recurrent state by parent: dst[r] = src[parent[r]]  (rows of `width` floats)
-cudaError_t gather_rows(const float* src, float* dst, const int* parent, int rows, int width,
+cudaError_t gather_rows(const float* src, float* dst, const int* parent, int row0, int rows, int width,
                         cudaStream_t stream);
 
 // LSTMCell pointwise (onmt/models/stacked_rnn.py:25-31): gates [rows,4d] (= x.W_ih^T+b_ih + h.W_hh^T+b_hh)
@@ -136,6 +140,19 @@ cudaError_t glu_residual(const float* y, const float* x, float* out, float* glu_
                          cudaStream_t stream);
 // im2col over time for a (k x 1) convolution: A[(b,t)][j*d + c] = x[b][t + j - left][c] (0 outside [0,T))
 cudaError_t im2col_time(const float* x, float* A, int B, int T, int d, int k, int left, cudaStream_t stream);
+
+// ---- CNN decoder step helpers (onmt/decoders/cnn_decoder.py:105-116, conv_multi_step_attention.py:66-82)
+// hist[slot][pos][d] keeps every layer input; row r reads position p from slot anc[r][p] (beam) or r.
+// Stores x (this step's layer input) at position t and builds the causal conv window
+// A[r][j*d + c] = layer input at position t-(k-1)+j (zeros before the sequence start).
+cudaError_t cnn_window(const float* x, float* hist, const int* anc, int anc_ld, const int* retired,
+                       int rows_per_chunk, float* A, int row0, int rows, int t, int k, int d, int Lmax,
+                       cudaStream_t stream);
+// out = (a + b) * s
+cudaError_t add_scale(const float* a, const float* b, float s, float* out, int64_t n, cudaStream_t stream);
+// out = (x + (c + o) * s) * s
+cudaError_t cnn_combine(const float* x, const float* c, const float* o, float s, float* out, int64_t n,
+                        cudaStream_t stream);
 
 // Front end (utils/labelop.py:219-233): see frontend.cu
 cudaError_t frontend_stats(const int16_t* signal, const int64_t* offsets, int n_reads, int mode,

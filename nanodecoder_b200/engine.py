@@ -87,6 +87,10 @@ class Engine(object):
     def reset_launch_count(self):
         self.lib.nd_reset_launch_count(self._h)
 
+    def set_option(self, name: str, value: int):
+        """e.g. set_option("decode_streams", 1)"""
+        self._check(self.lib.nd_set_int(self._h, name.encode(), int(value)))
+
     def profile_enable(self, categories=()):
         """Bracket launches of the named kernel categories with CUDA events (see _lib.PROF_CATS)."""
         mask = 0
@@ -112,10 +116,12 @@ class Engine(object):
         self._B = B
 
     def memory_bank(self) -> Tuple[torch.Tensor, torch.Tensor]:
-        """-> (memory_bank [T',B,d] in the reference layout, memory lengths [B])."""
+        """-> (memory_bank [T',B,d] in the reference layout ([d,B,T] for the CNN encoder), memory lengths [B])."""
         tp = C.c_int32(0)
         self._check(self.lib.nd_get_memory_bank(self._h, C.c_void_p(0), C.c_void_p(0), C.byref(tp), self._stream()))
-        out = torch.empty((tp.value, self._B, self.cfg.d_model), dtype=torch.float32, device=self.device)
+        shape = (self.cfg.d_model, self._B, tp.value) if self.cfg.encoder_type == "cnn" else \
+            (tp.value, self._B, self.cfg.d_model)
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
         lens = torch.empty((self._B,), dtype=torch.int64, device=self.device)
         self._check(self.lib.nd_get_memory_bank(self._h, _ptr(out), _ptr(lens), C.byref(tp), self._stream()))
         return out, lens

@@ -17,14 +17,16 @@ B = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 cfg = ModelConfig.family(family)
 sd = synth.make_state_dict(cfg)
 eng = Engine(cfg, sd, max_batch=B, max_src_len=512, max_tgt_len=100, max_beam=beam)
+if os.environ.get("ND_STREAMS"):
+    eng.set_option("decode_streams", int(os.environ["ND_STREAMS"]))
 chunks, lengths = synth.make_chunks(B, T=512, seed=1234, ragged=True, read_len=16)
 order = torch.argsort(lengths, descending=True, stable=True)
 src, lens = chunks[order].cuda(), lengths[order].cuda()
 cats = ["gemm", "lstm", "cross_attn", "self_attn", "enc_attn", "mlp_attn", "generator", "beam", "other"]
-for it in range(2):
+for it in range(4):
     torch.cuda.synchronize()
     eng.reset_launch_count()
-    if it == 1:
+    if it == 3:
         eng.profile_enable(cats)
     t0 = time.perf_counter()
     eng.encode(src, lens)
@@ -33,7 +35,9 @@ for it in range(2):
     out = eng.decode_beam(beam, 1, 100) if beam > 1 else eng.decode_greedy(100)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    print("step %d: encode %.2f ms, decode %.2f ms, %d launches" % (it, 1e3 * (t1 - t0), 1e3 * (t2 - t1), eng.launch_count))
+    print("step %d (%s): encode %.2f ms, decode %.2f ms, %d launches" % (
+        it, ["eager", "graph capture", "graph replay", "profiled, 1 stream"][it], 1e3 * (t1 - t0), 1e3 * (t2 - t1),
+        eng.launch_count))
 prof = eng.profile_read()
 tot = sum(v[0] for v in prof.values())
 for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):

@@ -14,7 +14,8 @@ from nanodecoder_b200.config import ModelConfig
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = ["l2t_d256", "t2t_d256", "nano2rnn_d256", "brnn2rnn_d256", "l2t_d64", "t2t_d64", "t2t_d512_6x6"]
+IMPLEMENTED = ["l2t_d256", "t2t_d256", "nano2rnn_d256", "brnn2rnn_d256", "cnn2cnn_d256", "l2t_d64", "t2t_d64",
+               "t2t_d512_6x6"]
 TOL = 1e-3
 
 
@@ -55,7 +56,8 @@ def test_greedy_matches_reference_golden(name, mode):
     np.testing.assert_allclose(out["scores"].cpu().numpy(), g["greedy_scores"], atol=2e-3)
 
 
-@pytest.mark.parametrize("name", ["l2t_d256", "t2t_d64", "nano2rnn_d256", "brnn2rnn_d256", "l2t_d64", "t2t_d256"])
+@pytest.mark.parametrize("name", ["l2t_d256", "t2t_d64", "nano2rnn_d256", "brnn2rnn_d256", "l2t_d64", "t2t_d256",
+                                  "cnn2cnn_d256"])
 def test_beam_matches_reference_golden(name):
     g, cfg, sd, src, lengths = load_golden(name)
     B, T, L, K = src.shape[0], src.shape[1], int(g["max_length"]), int(g["beam_size"])
@@ -72,7 +74,7 @@ def test_beam_matches_reference_golden(name):
     np.testing.assert_allclose(scores[:, 0], g["beam_scores"], atol=5e-3)
 
 
-@pytest.mark.parametrize("family", ["l2t", "t2t", "nano2rnn"])
+@pytest.mark.parametrize("family", ["l2t", "t2t", "nano2rnn", "cnn2cnn"])
 def test_greedy_and_beam_vs_oracle_ragged(family):
     """Fresh seeded inputs, ragged lengths incl. very short chunks, d=64 (oracle runs in seconds)."""
     from oracle import decode as od
@@ -108,6 +110,36 @@ def test_greedy_and_beam_vs_oracle_ragged(family):
             else:
                 assert abs(float(sc[i, n]) - ob["scores"][i][n]) < 5e-3
     assert mism == 0, "%d of %d beam hypotheses differ" % (mism, 2 * B)
+
+
+def test_decode_streams_and_graphs_do_not_change_results():
+    """Chunk groups on several streams and CUDA-graph replay are scheduling choices only: eager call,
+    graph capture (2nd call) and graph replays (3rd, 4th call) must all return identical results."""
+    g, cfg, sd, src, lengths = load_golden("l2t_d64")
+    chunks, lens = synth.make_chunks(300, T=128, seed=21, ragged=True, read_len=5)
+    eng = _engine(cfg, sd, 300, 128, 24, K=3)
+    outs = []
+    for ns, graphs in ((1, 0), (1, 1), (4, 1), (3, 1)):
+        eng.set_option("decode_streams", ns)
+        eng.set_option("use_graphs", graphs)
+        for rep in range(4):
+            eng.encode(chunks.cuda(), lens.cuda())
+            gr = eng.decode_greedy(24)
+            bm = eng.decode_beam(3, 1, 24)
+            outs.append((gr["ids"].cpu(), gr["scores"].cpu(), bm["ids"].cpu(), bm["scores"].cpu(), bm["lens"].cpu()))
+    names = ["greedy ids", "greedy scores", "beam ids", "beam scores", "beam lens"]
+    for i, o in enumerate(outs[1:]):
+        for nm, a, b in zip(names, outs[0], o):
+            assert torch.equal(a, b), "%s differ between call 0 and call %d (max |diff| %g)" % (
+                nm, i + 1, float((a.double() - b.double()).abs().max()))
+    # a different batch through the cached graphs (same shapes, other data)
+    chunks2, lens2 = synth.make_chunks(300, T=128, seed=22, ragged=True, read_len=5)
+    eng.encode(chunks2.cuda(), lens2.cuda())
+    a = eng.decode_greedy(24)["ids"].cpu()
+    eng.set_option("use_graphs", 0)
+    eng.encode(chunks2.cuda(), lens2.cuda())
+    b = eng.decode_greedy(24)["ids"].cpu()
+    assert torch.equal(a, b)
 
 
 def test_min_length_suppresses_eos():
