@@ -54,15 +54,43 @@ def base_config(n_gpus):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """SM clock / throttle-reason samples DURING the timed region.  NVML from a thread of this process
+    (two cheap queries per sample); falls back to an `nvidia-smi -lms` child when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu):
-        self.gpu = gpu
-        self.proc = None
+    def __init__(self, gpu, interval_s=0.05):
+        self.gpu, self.interval = gpu, interval_s
+        self.proc = self.thread = None
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop = False
+
+    def _nvml_loop(self, nv, h):
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(self.interval)
 
     def start(self):
+        if os.environ.get("ND_BENCH_SAMPLER", "nvml") == "nvml":
+            try:
+                import threading
+                import pynvml as nv
+                nv.nvmlInit()
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+                h = nv.nvmlDeviceGetHandleByIndex(idx)
+                self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+                self._nv = nv
+                self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -70,7 +98,28 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    @staticmethod
+    def _summary(sm, mx, reasons, source):
+        # samples under load = the upper half (idle samples before/after the region drag the median down)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons), "source": source}
+
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv, bits, reasons = self._nv, self.reason_bits, set()
+            for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+                alt = attr.replace("ClocksEventReason", "ClocksThrottleReason")
+                mask = getattr(nv, attr, getattr(nv, alt, 0))
+                if bits & int(mask):
+                    reasons.add(name)
+            return self._summary(self.samples, self.max_mhz, reasons, "nvml")
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,11 +142,7 @@ class ClockSampler(object):
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        # samples under load = the upper half (idle samples before/after the region drag the median down)
-        sm_sorted = sorted(sm)
-        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return self._summary(sm, max(mx) if mx else None, reasons, "nvidia-smi")
 
 
 # ------------------------------------------------------------------------------------------ CPU arm

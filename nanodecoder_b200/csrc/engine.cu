@@ -58,6 +58,7 @@ struct LstmW {                 // one bidirectional (or unidirectional) LSTM lay
   const float* bn_alpha = nullptr;   // eval BatchNorm of this layer's output folded to y = x*alpha + beta
   const float* bn_beta = nullptr;
   int in = 1;
+  bool tc_ok = false;          // |W_hh| within the fp16 range: the tensor-core recurrence may be used
 };
 struct ConvW { Lin conv; };    // weight-normalised (k x 1) conv as [2d, k*d] GEMM
 
@@ -386,6 +387,9 @@ int load_lstm(nd_engine* e, const std::string& prefix, const std::string& sfx, i
   }
   out->w_hh = upload(e, Whh);
   out->b_hh = upload(e, bhh);
+  float wmax = 0.f;
+  for (float v : Whh) wmax = std::max(wmax, fabsf(v));
+  out->tc_ok = wmax < 6.0e4f;
   return ND_OK;
 }
 // weight-normalised conv (onmt/modules/weight_norm.py:153-165, eval: Polyak buffers):
@@ -649,7 +653,8 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
     }
     if (!nano) { p.h_n = e->enc_hn + (int64_t)l * dirs * B * H; p.c_n = e->enc_cn + (int64_t)l * dirs * B * H; }
     ND_CUDA(e, cudaMemsetAsync(out, 0, (size_t)B * T * d * sizeof(float), st));
-    ND_LAUNCH_CAT(e, ND_PROF_LSTM, st, lstm_layer(p, e->n_sm, st));
+    if (tc_mode(e) && lstm_tc_supported(H) && W.tc_ok) ND_LAUNCH_CAT(e, ND_PROF_LSTM, st, lstm_layer_tc(p, st));
+    else ND_LAUNCH_CAT(e, ND_PROF_LSTM, st, lstm_layer(p, e->n_sm, st));
     last = out;
     if (nano && c.enc_pooling[l] > 1) {
       // MaxPool1d over time (nano_encoder.py:101-105); lengths follow floor((len - s)/s + 1)
@@ -674,7 +679,7 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
     ND_CUDA(e, cudaMemcpyAsync(e->mb, last, (size_t)B * T * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   ND_CUDA(e, cudaMemcpyAsync(e->mem_len, e->lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-  if (nano) {
+  if (nano && lens != e->h_lengths) {
     // restore the source lengths (the decoder's reference state keeps the pooled ones in mem_len)
     ND_CUDA(e, cudaMemcpyAsync(e->lengths, e->h_lengths.data(), (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   }
@@ -1292,6 +1297,11 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     e->decode_streams = (int)value;
     return ND_OK;
   }
+  if (strcmp(name, "lstm_variant") == 0) {
+    if (value < 0 || value > 1) return fail(e, ND_ERR_INVALID, "lstm_variant must be 0 (W_hh in TMEM) or 1 (in smem)");
+    lstm_tc_set_variant((int)value);
+    return ND_OK;
+  }
   if (strcmp(name, "use_graphs") == 0) {
     e->use_graphs = value != 0;
     return ND_OK;
@@ -1301,6 +1311,7 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
 
 int nd_debug_gemm_timeline(int64_t* dev_buf32) {
   gemm_tc_set_debug(reinterpret_cast<long long*>(dev_buf32));
+  lstm_tc_set_debug(dev_buf32 ? reinterpret_cast<long long*>(dev_buf32) + 16 : nullptr);   // slots 16..31
   return ND_OK;
 }
 

@@ -18,9 +18,14 @@ struct LstmParams {
   float* h_n = nullptr;           // optional [dirs, B, H]
   float* c_n = nullptr;
   int B = 0, T = 0, dirs = 2, H = 0;
+  long long* dbg = nullptr;       // optional [32] clock64() stamps of step 100 of CTA 0 (tuning aid)
 };
 
 bool lstm_supported(int H);
-cudaError_t lstm_layer(const LstmParams& p, int n_sm, cudaStream_t stream);
+cudaError_t lstm_layer(const LstmParams& p, int n_sm, cudaStream_t stream);       // fp32 FFMA, weights in registers
+bool lstm_tc_supported(int H);
+cudaError_t lstm_layer_tc(const LstmParams& p, cudaStream_t stream);   // tcgen05 fp16x2-split, W_hh on chip; needs |W_hh| < 6e4
+void lstm_tc_set_debug(long long* dev_buf);
+void lstm_tc_set_variant(int v);   // 0: W_hh resident in tensor memory (default), 1: in shared memory
 
 }  // namespace nd
