@@ -76,6 +76,8 @@ class ClockSampler(object):
             time.sleep(self.interval)
 
     def start(self):
+        if os.environ.get("ND_BENCH_SAMPLER", "nvml") == "none":      # experiments only
+            return
         if os.environ.get("ND_BENCH_SAMPLER", "nvml") == "nvml":
             try:
                 import threading

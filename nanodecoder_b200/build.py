@@ -21,7 +21,7 @@ SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm.cu", "lstm_tc.cu", "
            "beam.cu", "frontend.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("ND_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _digest(path):

@@ -42,6 +42,8 @@ template <int VPL, int NQMAX>
 __global__ void __launch_bounds__(kAttnThreads) cross_attn_kernel(CrossAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
   const int chunk = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (p.retired && p.retired[chunk]) return;
   const int d = 32 * VPL, T = p.T, H = p.H, NQ = p.NQ;
   const int TS = T + 1;                           // odd stride: the H score rows of a query hit distinct banks
@@ -158,10 +160,10 @@ cudaError_t launch_cross(const CrossAttnParams& p, cudaStream_t stream) {
   const size_t smem = ((size_t)p.NQ * d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
   if (p.NQ == 1) {
     cudaFuncSetAttribute(cross_attn_kernel<VPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cross_attn_kernel<VPL, 1><<<p.n_chunks, kAttnThreads, smem, stream>>>(p);
+    launch_k(cross_attn_kernel<VPL, 1>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   } else {
     cudaFuncSetAttribute(cross_attn_kernel<VPL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cross_attn_kernel<VPL, 8><<<p.n_chunks, kAttnThreads, smem, stream>>>(p);
+    launch_k(cross_attn_kernel<VPL, 8>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   }
   return cudaGetLastError();
 }
@@ -190,6 +192,8 @@ namespace {
 __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
   const int row = p.row0 + blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (p.retired && p.retired[row / p.rows_per_chunk]) return;
   const int d = p.d, H = p.H, dh = d / H, L = p.step + 1;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -287,7 +291,7 @@ cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream) {
   if (dh != 8 && dh != 16 && dh != 32 && dh != 64) return cudaErrorInvalidValue;
   const int nw = p.H < 8 ? p.H : 8;
   const size_t smem = ((size_t)p.d + (size_t)nw * p.Lmax) * sizeof(float);
-  self_attn_kernel<<<p.rows, nw * 32, smem, stream>>>(p);
+  launch_k(self_attn_kernel, dim3(p.rows), dim3(nw * 32), smem, stream, p);
   return cudaGetLastError();
 }
 
@@ -391,6 +395,8 @@ template <int VPL, int NQMAX>
 __global__ void __launch_bounds__(kAttnThreads) mlp_attn_kernel(MlpAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
   const int chunk = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (p.retired && p.retired[chunk]) return;
   const int d = 32 * VPL, T = p.T, NQ = p.NQ;
   float* q_s = smem_f;                            // [NQ][d]
@@ -501,10 +507,10 @@ cudaError_t launch_mlp(const MlpAttnParams& p, cudaStream_t stream) {
   const size_t smem = ((size_t)p.NQ * d + d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
   if (p.NQ == 1) {
     cudaFuncSetAttribute(mlp_attn_kernel<VPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mlp_attn_kernel<VPL, 1><<<p.n_chunks, kAttnThreads, smem, stream>>>(p);
+    launch_k(mlp_attn_kernel<VPL, 1>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   } else {
     cudaFuncSetAttribute(mlp_attn_kernel<VPL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mlp_attn_kernel<VPL, 8><<<p.n_chunks, kAttnThreads, smem, stream>>>(p);
+    launch_k(mlp_attn_kernel<VPL, 8>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   }
   return cudaGetLastError();
 }

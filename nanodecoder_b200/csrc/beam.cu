@@ -21,6 +21,8 @@ namespace {
 constexpr int kMaxCandPerLane = 4;     // K*V <= 128
 
 __global__ void beam_init_kernel(BeamParams p, int bos) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int rows = p.B * p.K;
   if (i < rows) {
@@ -42,6 +44,8 @@ __global__ void beam_init_kernel(BeamParams p, int bos) {
 }
 
 __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float length_penalty) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int bl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (bl >= p.nb) return;
@@ -164,6 +168,8 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
 }
 
 __global__ void beam_finalize_kernel(BeamParams p, int64_t* out_ids, int* out_lens, float* out_scores) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x;                            // (b, n)
   const int len = p.st.hyp_len[i];
   if (threadIdx.x == 0) { out_lens[i] = len; out_scores[i] = p.st.hyp_score[i]; }
@@ -175,7 +181,7 @@ __global__ void beam_finalize_kernel(BeamParams p, int64_t* out_ids, int* out_le
 
 cudaError_t beam_init(const BeamParams& p, int bos, cudaStream_t stream) {
   const int n = p.B * p.K;
-  beam_init_kernel<<<cdiv(n, 256), 256, 0, stream>>>(p, bos);
+  launch_k(beam_init_kernel, dim3(cdiv(n, 256)), dim3(256), 0, stream, p, bos);
   return cudaGetLastError();
 }
 
@@ -184,13 +190,13 @@ cudaError_t beam_step(const BeamParams& p, cudaStream_t stream) {
   // ((5 + step + 1) / 6) ** alpha in double like the Python expression (translator.py:720-721)
   const double lp = pow((5.0 + (double)(p.step + 1)) / 6.0, (double)p.alpha);
   if (p.nb <= 0) return cudaSuccess;
-  beam_step_kernel<<<cdiv(p.nb, 4), 128, 0, stream>>>(p, (float)lp);
+  launch_k(beam_step_kernel, dim3(cdiv(p.nb, 4)), dim3(128), 0, stream, p, (float)lp);
   return cudaGetLastError();
 }
 
 cudaError_t beam_finalize(const BeamParams& p, int64_t* out_ids, int* out_lens, float* out_scores,
                           cudaStream_t stream) {
-  beam_finalize_kernel<<<p.B * p.n_best, 128, 0, stream>>>(p, out_ids, out_lens, out_scores);
+  launch_k(beam_finalize_kernel, dim3(p.B * p.n_best), dim3(128), 0, stream, p, out_ids, out_lens, out_scores);
   return cudaGetLastError();
 }
 

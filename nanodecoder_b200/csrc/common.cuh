@@ -42,6 +42,46 @@ __device__ __forceinline__ float2 ldg_stream2(const float* p) {
   return r;
 }
 
+// ---- programmatic dependent launch (PDL).  Every kernel of the decode step loop starts with
+// pdl_launch_dependents() (the next kernel of the stream may become resident and run its prologue now) and
+// executes pdl_wait() before its first access to memory another kernel may have written or may still read;
+// pdl_wait() returns once ALL prerequisite grids have completed and flushed.  Both are no-ops when the kernel
+// was launched without the attribute.
+// Measured on B200 (profiles/r01_pdl_experiment.md): triggering at kernel ENTRY makes the decode loop 30 %
+// slower (CTAs of the following kernels become resident on whatever SMs are free at that moment, so the
+// 1024-CTA attention kernels end up badly balanced).  ND_PDL_EARLY=1 re-enables it for experiments.
+#ifndef ND_PDL_EARLY
+#define ND_PDL_EARLY 0
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if ND_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+// trigger used near the END of a kernel's main loop: the next kernel's launch latency and prologue overlap
+// this kernel's epilogue only
+__device__ __forceinline__ void pdl_launch_dependents_late() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern int g_pdl;                       // 1: launch_k adds the programmatic-stream-serialization attribute
+
+// <<<grid, block, smem, stream>>> replacement for kernels that follow the PDL protocol above
+template <class... Params, class... Args>
+static inline cudaError_t launch_k(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

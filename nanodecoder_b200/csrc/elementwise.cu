@@ -28,6 +28,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 
 __global__ void embed_kernel(const int* __restrict__ tok, const float* __restrict__ emb, float* __restrict__ x,
                              int64_t x_ld, int rows, int d, int pos_enc, int step) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const int t = tok[row];
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -75,6 +77,8 @@ __global__ void transpose_bt_kernel(const float* __restrict__ in, float* __restr
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                    const int* __restrict__ parent, int row0, int width) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = row0 + blockIdx.x;
   const int s = parent[r];
   for (int c = threadIdx.x; c < width; c += blockDim.x) dst[(int64_t)r * width + c] = src[(int64_t)s * width + c];
@@ -83,6 +87,8 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, float* __restr
 __global__ void lstm_cell_kernel(const float* __restrict__ ga, const float* __restrict__ gb,
                                  const float* __restrict__ c_in, float* __restrict__ h_out,
                                  float* __restrict__ c_out, int rows, int d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * d) return;
   const int64_t r = i / d;
@@ -99,12 +105,16 @@ __global__ void lstm_cell_kernel(const float* __restrict__ ga, const float* __re
 }
 
 __global__ void fill_int_kernel(int* p, int n, int value) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = value;
 }
 
 __global__ void glu_residual_kernel(const float* __restrict__ y, const float* __restrict__ x,
                                     float* __restrict__ out, float* __restrict__ glu_out, int64_t rows, int d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * d) return;
   const int64_t r = i / d;
@@ -130,6 +140,8 @@ __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ A
 // Generator: one warp per row.  VMAX bounds the vocabulary (4 specials + bases <= 16).
 template <int VMAX>
 __global__ void __launch_bounds__(128) generator_kernel(GenParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= p.rows) return;
@@ -198,7 +210,7 @@ cudaError_t layernorm_rows(const float* x, const float* g, const float* b, float
 cudaError_t embed_rows(const int* tok, const float* emb, float* x, int64_t x_ld, int rows, int d, int pos_enc,
                        int step, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  embed_kernel<<<rows, d < 256 ? d : 256, 0, stream>>>(tok, emb, x, x_ld, rows, d, pos_enc, step);
+  launch_k(embed_kernel, dim3(rows), dim3(d < 256 ? d : 256), 0, stream, tok, emb, x, x_ld, rows, d, pos_enc, step);
   return cudaGetLastError();
 }
 
@@ -225,7 +237,7 @@ cudaError_t transpose_bt(const float* in, float* out, int B, int T, int d, cudaS
 cudaError_t gather_rows(const float* src, float* dst, const int* parent, int row0, int rows, int width,
                         cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  gather_rows_kernel<<<rows, width < 256 ? width : 256, 0, stream>>>(src, dst, parent, row0, width);
+  launch_k(gather_rows_kernel, dim3(rows), dim3(width < 256 ? width : 256), 0, stream, src, dst, parent, row0, width);
   return cudaGetLastError();
 }
 
@@ -233,6 +245,8 @@ namespace {
 __global__ void cnn_window_kernel(const float* __restrict__ x, float* __restrict__ hist, const int* __restrict__ anc,
                                   int anc_ld, const int* __restrict__ retired, int rows_per_chunk,
                                   float* __restrict__ A, int row0, int t, int k, int d, int Lmax) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = row0 + blockIdx.x;
   if (retired && retired[r / rows_per_chunk]) return;     // retired chunks keep stale ancestor tables
   for (int i = threadIdx.x; i < k * d; i += blockDim.x) {
@@ -251,11 +265,15 @@ __global__ void cnn_window_kernel(const float* __restrict__ x, float* __restrict
 }
 __global__ void add_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, float s,
                                  float* __restrict__ out, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (a[i] + b[i]) * s;
 }
 __global__ void cnn_combine_kernel(const float* __restrict__ x, const float* __restrict__ c,
                                    const float* __restrict__ o, float s, float* __restrict__ out, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (x[i] + (c[i] + o[i]) * s) * s;
 }
@@ -265,25 +283,25 @@ cudaError_t cnn_window(const float* x, float* hist, const int* anc, int anc_ld, 
                        int rows_per_chunk, float* A, int row0, int rows, int t, int k, int d, int Lmax,
                        cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  cnn_window_kernel<<<rows, 256, 0, stream>>>(x, hist, anc, anc_ld, retired, rows_per_chunk, A, row0, t, k, d, Lmax);
+  launch_k(cnn_window_kernel, dim3(rows), dim3(256), 0, stream, x, hist, anc, anc_ld, retired, rows_per_chunk, A, row0, t, k, d, Lmax);
   return cudaGetLastError();
 }
 cudaError_t add_scale(const float* a, const float* b, float s, float* out, int64_t n, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  add_scale_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, stream>>>(a, b, s, out, n);
+  launch_k(add_scale_kernel, dim3((unsigned)cdiv64(n, 256)), dim3(256), 0, stream, a, b, s, out, n);
   return cudaGetLastError();
 }
 cudaError_t cnn_combine(const float* x, const float* c, const float* o, float s, float* out, int64_t n,
                         cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  cnn_combine_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, stream>>>(x, c, o, s, out, n);
+  launch_k(cnn_combine_kernel, dim3((unsigned)cdiv64(n, 256)), dim3(256), 0, stream, x, c, o, s, out, n);
   return cudaGetLastError();
 }
 
 cudaError_t lstm_cell_pointwise(const float* gates_a, const float* gates_b, const float* c_in, float* h_out,
                                 float* c_out, int rows, int d, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  lstm_cell_kernel<<<(unsigned)cdiv64((int64_t)rows * d, 256), 256, 0, stream>>>(gates_a, gates_b, c_in, h_out, c_out,
+  launch_k(lstm_cell_kernel, dim3((unsigned)cdiv64((int64_t)rows * d, 256)), dim3(256), 0, stream, gates_a, gates_b, c_in, h_out, c_out,
                                                                                 rows, d);
   return cudaGetLastError();
 }
@@ -319,14 +337,14 @@ cudaError_t transpose_to_dbt(const float* in, float* out, int B, int T, int d, c
 
 cudaError_t fill_int(int* p, int n, int value, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  fill_int_kernel<<<cdiv(n, 256), 256, 0, stream>>>(p, n, value);
+  launch_k(fill_int_kernel, dim3(cdiv(n, 256)), dim3(256), 0, stream, p, n, value);
   return cudaGetLastError();
 }
 
 cudaError_t glu_residual(const float* y, const float* x, float* out, float* glu_out, int64_t rows, int d,
                          cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  glu_residual_kernel<<<(unsigned)cdiv64(rows * d, 256), 256, 0, stream>>>(y, x, out, glu_out, rows, d);
+  launch_k(glu_residual_kernel, dim3((unsigned)cdiv64(rows * d, 256)), dim3(256), 0, stream, y, x, out, glu_out, rows, d);
   return cudaGetLastError();
 }
 
@@ -339,7 +357,7 @@ cudaError_t im2col_time(const float* x, float* A, int B, int T, int d, int k, in
 cudaError_t generator_step(const GenParams& p, cudaStream_t stream) {
   if (p.rows <= 0) return cudaSuccess;
   if (p.V > 16) return cudaErrorInvalidValue;
-  generator_kernel<16><<<cdiv(p.rows, 4), 128, 0, stream>>>(p);
+  launch_k(generator_kernel<16>, dim3(cdiv(p.rows, 4)), dim3(128), 0, stream, p);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,8 @@
 
 using namespace nd;
 
+namespace nd { int g_pdl = 0; }   // programmatic dependent launch: measured slower on this workload, see common.cuh
+
 namespace {
 
 std::string g_create_error;
@@ -1248,7 +1250,7 @@ int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* ou
   if (out_attn || out_logits || e->prof_mask || !e->use_graphs)
     return greedy_body(e, max_len, min_len, out_ids, out_scores, out_attn, out_logits, st);
   const int B = e->B;
-  const std::vector<int64_t> key = {0, B, e->T, e->Tp, max_len, min_len, 1, 1, 0, n_groups(e, B)};
+  const std::vector<int64_t> key = {0, B, e->T, e->Tp, max_len, min_len, 1, 1, 0, n_groups(e, B), g_pdl};
   ND_TRY(run_cached(e, key, st, [&](cudaStream_t s2) {
     return greedy_body(e, max_len, min_len, e->o_ids, e->o_scores, nullptr, nullptr, s2);
   }));
@@ -1271,7 +1273,7 @@ int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_
     return beam_body(e, K, n_best, max_len, min_len, alpha, out_ids, out_lens, out_scores, st);
   int32_t alpha_bits;
   memcpy(&alpha_bits, &alpha, sizeof(alpha_bits));
-  const std::vector<int64_t> key = {1, B, e->T, e->Tp, max_len, min_len, K, n_best, alpha_bits, n_groups(e, B)};
+  const std::vector<int64_t> key = {1, B, e->T, e->Tp, max_len, min_len, K, n_best, alpha_bits, n_groups(e, B), g_pdl};
   ND_TRY(run_cached(e, key, st, [&](cudaStream_t s2) {
     return beam_body(e, K, n_best, max_len, min_len, alpha, e->o_ids, e->o_lens, e->o_scores, s2);
   }));
@@ -1295,6 +1297,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
       e->join_ev.push_back(ev);
     }
     e->decode_streams = (int)value;
+    return ND_OK;
+  }
+  if (strcmp(name, "pdl") == 0) {            // programmatic dependent launch in the decode loop (process-wide)
+    g_pdl = value != 0;
     return ND_OK;
   }
   if (strcmp(name, "lstm_variant") == 0) {

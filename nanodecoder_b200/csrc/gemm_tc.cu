@@ -227,14 +227,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto a_lo = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES; };
   auto b_hi = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES * (NPASS == 3 ? 2 : 1); };
   auto b_lo = [&](int s) { return b_hi(s) + C::B_TILE_BYTES; };
-  auto issue_tma = [&](int i) {
+  auto issue_w = [&](int i) {                  // weight tiles: never written by another kernel of the stream
     const int s = i % C::kStages;
     mbar_expect_tx(&raw_full[s], A_TILE_BYTES + C::B_TILE_BYTES * (NPASS == 3 ? 2 : 1));
     const int kc = (kb0 + i) * BK;
-    tma_load_2d(a_hi(s), &tmA, &raw_full[s], kc, m0);
     tma_load_2d(b_hi(s), &tmWhi, &raw_full[s], kc, n0);
     if (NPASS == 3) tma_load_2d(b_lo(s), &tmWlo, &raw_full[s], kc, n0);
   };
+  auto issue_a = [&](int i) {                  // activation tile: produced by the previous kernel
+    const int s = i % C::kStages;
+    tma_load_2d(a_hi(s), &tmA, &raw_full[s], (kb0 + i) * BK, m0);
+  };
+  auto issue_tma = [&](int i) { issue_w(i); issue_a(i); };
+  pdl_launch_dependents();                     // the next kernel's prologue may overlap this kernel
 
   int tma_issued = 0;
   if (warp == kTmaWarp && lane == 0) {
@@ -250,9 +255,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
     if (NPASS == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+    // programmatic dependent launch: the weight tiles of the first stages are requested while the previous
+    // kernel may still be running; everything that kernel produced (A, residual, C) is touched after pdl_wait
     const int first = KB < C::kStages ? KB : C::kStages;
-    for (; tma_issued < first; ++tma_issued) issue_tma(tma_issued);
+    for (int i = 0; i < first; ++i) issue_w(i);
+    pdl_wait();
+    for (; tma_issued < first; ++tma_issued) issue_a(tma_issued);
     ND_TS(2);
+  } else {
+    pdl_wait();
   }
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -613,13 +624,15 @@ cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = S;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NPASS, S>, tmA, tmWhi, tmWlo, pp);
 }
 
