@@ -69,7 +69,7 @@ class ClockSampler(object):
     def _nvml_loop(self, nv, h):
         while not self._stop:
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))))
                 self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
             except Exception:
                 pass
@@ -108,10 +108,13 @@ class ClockSampler(object):
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx,
                 "samples": len(sm), "reasons": sorted(reasons), "source": source}
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) perf_counter bounds of the timed region: only samples inside it are reported."""
         if self.thread is not None:
             self._stop = True
             self.thread.join(timeout=2)
+            inside = [m for (t, m) in self.samples if window is None or window[0] <= t <= window[1]]
+            self.samples = inside if inside else [m for (_, m) in self.samples]
             nv, bits, reasons = self._nv, self.reason_bits, set()
             for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
                                ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
@@ -148,8 +151,10 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(n_chunks, steps, warmup):
-    """Oracle port (CPU restatement of the reference's translate path) on a bounded sample."""
+def cpu_sample(n_chunks, steps, warmup, target_s=None):
+    """Oracle port (CPU restatement of the reference's translate path) on a bounded sample.  With
+    ``target_s`` the step count is chosen from the warm-up step's duration so the sample takes about that
+    many seconds of CPU work (never fewer than ``steps``, never more than 40)."""
     from nanodecoder_b200 import synth
     from oracle import decode as od
     from oracle.model import OracleModel
@@ -162,11 +167,15 @@ def cpu_sample(n_chunks, steps, warmup):
     lengths = lengths[order]
     om = OracleModel(sd, cfg)
     times, bases = [], 0
-    for i in range(warmup + steps):
+    i = 0
+    while i < warmup + steps:
         t0 = time.perf_counter()
         out = od.greedy(om, src, lengths, max_length=L)
         dt = time.perf_counter() - t0
-        if i >= warmup:
+        if target_s and i == 0:
+            steps = max(steps, min(40, int(target_s / max(dt, 1e-3))))
+        i += 1
+        if i > warmup:
             times.append(dt)
             bases += od.count_bases(out["predictions"])
     total = sum(times)
@@ -246,17 +255,20 @@ def main():
         eng.encode(src_d, len_d)
         return eng.decode_greedy(L)["ids"]
 
+    # the clock sampler runs from before the warm-up (no idle gap in front of the timed region: the GPU
+    # would drop its clocks and the first timed step would pay the ramp); only samples taken inside the
+    # timed region are reported
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         ids = step_device()
     torch.cuda.synchronize()
 
     # ---------------- timed region 1: inputs resident in HBM
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     eng.reset_launch_count()
     barrier()
+    t_region0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     bases_t = torch.zeros((), dtype=torch.int64, device=dev)
     ev0.record()
@@ -267,9 +279,10 @@ def main():
         bases_t += first.sum()
     ev1.record()
     barrier()
+    t_region1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((t_region0, t_region1)) if rank == 0 else None
     # ---------------- per-kernel pass for the roofline entry: same steps with CUDA-event brackets around
     # every launch of the dominant kernel (the engine then runs the decode loop on one stream, eagerly)
     eng.profile_enable(["cross_attn"])
@@ -351,7 +364,7 @@ def main():
                         "api": "Translator.translate(src=(pinned chunks, lengths), batch_size=1024) -> base strings"},
                 "gpu_launches": int(tot[1].item()), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = {k: v for k, v in cpu_sample(32, 2, 1).items()
+            line["cpu_baseline"] = {k: v for k, v in cpu_sample(50, 2, 1, target_s=15.0).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:

@@ -44,6 +44,13 @@ def main(opt, logger):
     from nanodecoder_b200.inputters.nano_dataset import SignalFrontend
     from nanodecoder_b200.translate.translator import build_translator
     from nanodecoder_b200.utils.labelop import read_raw_signal
+    from nanodecoder_b200 import shard
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch
+        import torch.distributed as dist
+        opt.gpu = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(opt.gpu)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", opt.gpu))
     for sub in ("", "result", "segment") + (("attention",) if opt.attn_debug else ()):
         os.makedirs(os.path.join(opt.save_data, sub), exist_ok=True)
     opt.tgt = None
@@ -62,11 +69,18 @@ def main(opt, logger):
                     todo.append((fn, suffix, out))
     logger.info("%d reads have already translated, remains %d read\n" % (done, len(todo)))
 
+    # reads shard across the ranks of a torchrun launch (one process per GPU, no collective inside the step);
+    # every rank derives the same partition from the file sizes
+    rank, ws = shard.world()
+    mine = shard.partition_reads([os.path.getsize(os.path.join(opt.src_dir, t[0])) for t in todo], ws)[rank]
+    todo_mine = [(i, todo[i]) for i in mine]
+
+    records = []                                                 # (global read index, out name, predictions, seconds)
     pool_reads = max(1, opt.thread * 8)                          # reads pooled per GPU front-end launch
-    for g0 in range(0, len(todo), pool_reads):
-        group = todo[g0: g0 + pool_reads]
+    for g0 in range(0, len(todo_mine), pool_reads):
+        group = todo_mine[g0: g0 + pool_reads]
         start = time.time()
-        reads = [read_raw_signal(os.path.join(opt.src_dir, fn), suffix) for fn, suffix, _ in group]
+        reads = [read_raw_signal(os.path.join(opt.src_dir, fn), suffix) for _, (fn, suffix, _) in group]
         keep = [i for i, r in enumerate(reads) if r.size > 0]
         if not keep:
             continue
@@ -77,10 +91,15 @@ def main(opt, logger):
         total = max(1, len(chunk_read))
         for j, i in enumerate(keep):
             sel = np.nonzero(chunk_read == j)[0]
+            records.append((group[i][0], group[i][1][2], [preds[k] for k in sel], elapsed * len(sel) / total))
+    # per-read records travel to rank 0 (NCCL all_gather over NVLink on the GPUs), which writes the files
+    merged = shard.gather_records(records, dst=0)
+    if merged is not None:
+        for _, out_name, preds, seconds in merged:
             try:
-                write_output(opt, group[i][2], [preds[k] for k in sel], elapsed * len(sel) / total)
+                write_output(opt, out_name, preds, seconds)
             except Exception:                                    # translate.py:97-98
-                print("!!!error!!!data src: " + group[i][2].split(".txt")[0])
+                print("!!!error!!!data src: " + out_name.split(".txt")[0])
 
 
 if __name__ == "__main__":
