@@ -15,6 +15,7 @@
  *                        decoder/transformer.py:194-246, onmt/decoders/decoder.py:303-366,
  *                        onmt/decoders/cnn_decoder.py:74-132, models/model_builder.py:331-334
  *   nd_decode_beam       translate/translator.py:619-825 (_fast_translate_batch)
+ *   nd_decode_beam_object translate/translator.py:827-926 (_translate_batch) + onmt/translate/beam.py:74-178
  *   nd_load_weight       models/model_builder.py:343-357 (load_state_dict of checkpoint tensors)
  *
  * Conventions
@@ -143,6 +144,18 @@ ND_EXPORT int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, i
 ND_EXPORT int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len,
                    int32_t min_len, float alpha, int64_t* out_ids, int32_t* out_lens,
                    float* out_scores, void* stream);
+
+/* Object beam search (translate/translator.py:827-926 _translate_batch + onmt/translate/beam.py:74-178, the
+ * reference's default when --fast is absent): rows ending in </s> stay in the beam for one step with all their
+ * children at -1e20; every chunk keeps advancing until EVERY chunk is done (top beam ended and >= n_best
+ * finished) or max_len steps ran; finished hypotheses are ranked by the GNMT global score = beam score /
+ * length penalty (length_penalty: 0 none, 1 wu ((5+len)^alpha / 6^alpha), 2 avg; penalties.py:65-88), stable in
+ * arrival order; chunks with fewer than n_best finished hypotheses are topped up from the live beam
+ * (beam.py:154-168).  Coverage penalty, stepwise penalty and n-gram blocking are not supported.
+ * Outputs as nd_decode_beam.                                                                                 */
+ND_EXPORT int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len,
+                          int32_t min_len, int32_t length_penalty, float alpha, int64_t* out_ids,
+                          int32_t* out_lens, float* out_scores, void* stream);
 
 /* integer options (results never depend on them):
  *   "decode_streams" (default 1, 1..16): engine-owned CUDA streams the decode loop spreads contiguous

@@ -40,9 +40,15 @@ __global__ void beam_init_kernel(BeamParams p, int bos) {
       p.st.hyp_len[i * p.n_best + n] = 0;
     }
   }
-  if (i == 0) *p.st.n_alive = p.B;
+  if (i == 0) {
+    *p.st.n_alive = p.B;
+    *p.st.n_done = 0;
+    *p.st.stop_step = 0x7fffffff;
+  }
 }
 
+// length_penalty: fast mode ((5+step+1)/6)^alpha; object mode: divisor of the global score of hypotheses
+// finishing at this step (beam.py:200-208)
 __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float length_penalty) {
   pdl_launch_dependents();
   pdl_wait();
@@ -51,6 +57,13 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
   if (bl >= p.nb) return;
   const int b = p.b0 + bl;
   if (p.st.retired[b]) return;
+  const bool obj = p.mode == 1;
+  if (obj && p.step >= *p.st.stop_step) {              // every Beam was done before this step (translator.py:883-884)
+    // the loop has ended: from the next step on every per-chunk kernel skips this chunk (its ancestor tables
+    // are no longer extended, so the attention kernels must not walk them)
+    if (lane == 0) p.st.retired[b] = 1;
+    return;
+  }
   const int K = p.K, V = p.V, NC = K * V, Lp1 = p.Lmax + 1;
   const int cur = p.step & 1, nxt = cur ^ 1;
   const int rows = p.B * K;
@@ -68,7 +81,9 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     cand[i] = -INFINITY;
     if (c < NC) {
       const int k = c / V;
-      cand[i] = (p.logp[((int64_t)b * K + k) * V + (c - k * V)] + p.st.topk_log_probs[b * K + k]) / length_penalty;
+      const float lpv = p.logp[((int64_t)b * K + k) * V + (c - k * V)] + p.st.topk_log_probs[b * K + k];
+      if (obj) cand[i] = (p.step > 0 && p.st.cur_tok[b * K + k] == p.eos) ? -1e20f : lpv;   // beam.py:94-100
+      else cand[i] = lpv / length_penalty;
     } else {
       used |= 1u << i;
     }
@@ -99,8 +114,8 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
   const int tok = mine ? sel_idx - beam * V : 0;
   const int prow = b * K + beam;                       // parent row (global)
   const int nrow = b * K + lane;
-  bool finished = mine && (tok == p.eos || p.step + 1 == p.max_len);           // :753-755
-  float new_lp = sel_score * length_penalty;           // :729
+  bool finished = mine && (tok == p.eos || (!obj && p.step + 1 == p.max_len));  // :753-755 | beam.py:140-141
+  float new_lp = obj ? sel_score : sel_score * length_penalty;                 // :729 | beam.py:127
   const unsigned fin_mask = __ballot_sync(ND_FULL, finished);
 
   // new alive sequences / ancestor tables (warp-cooperative row copies)
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
   __syncwarp();
 
   if (fin_mask) {
-    if (finished) new_lp = -1e10f;                     // :760
+    if (finished && !obj) new_lp = -1e10f;             // :760 (object mode keeps the score: beam.py:97-100 blocks the children)
     int top_fin = p.st.top_finished[b] | ((fin_mask & 1u) ? 1 : 0);            // :762
     int n_hyp = p.st.n_hyp[b];
     const int nb = p.n_best;
@@ -128,7 +143,8 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     const int len = p.step + 1;
     for (int k = 0; k < K; ++k) {                      // finished beams in beam order (:773-778)
       if (!(fin_mask & (1u << k))) continue;
-      const float sc = __shfl_sync(ND_FULL, sel_score, k);
+      float sc = __shfl_sync(ND_FULL, sel_score, k);
+      if (obj) sc = sc / length_penalty;               // global score (length penalty none / wu / avg)
       ++n_hyp;
       // stable insertion into the best-n_best list (descending score, earlier first on ties)
       int pos = nb;
@@ -154,9 +170,13 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     if (lane == 0) {
       p.st.top_finished[b] = top_fin;
       p.st.n_hyp[b] = n_hyp;
-      if (top_fin && n_hyp >= nb) {                    // :781
+      if (!obj && top_fin && n_hyp >= nb) {            // :781
         p.st.retired[b] = 1;
         atomicSub(p.st.n_alive, 1);
+      }
+      if (obj && (top_fin & 1) && n_hyp >= nb && !(top_fin & 2)) {      // Beam.done() became true (beam.py:151-152)
+        p.st.top_finished[b] = top_fin | 2;
+        if (atomicAdd(p.st.n_done, 1) + 1 == p.B) atomicMin(p.st.stop_step, p.step + 1);
       }
     }
   }
@@ -165,6 +185,44 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     p.st.cur_tok[nrow] = tok;
     p.st.parent[nrow] = prow;
   }
+}
+
+// Object mode, after the loop: Beam.sort_finished(minimum=n_best) (beam.py:154-168) tops the finished list up
+// from the live beam in beam order; they arrive last, so they rank after equal-score finished entries.
+__global__ void __launch_bounds__(32) beam_object_fill_kernel(BeamParams p, float gs_none, float alpha) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int K = p.K, Lp1 = p.Lmax + 1, nb = p.n_best;
+  int n_hyp = p.st.n_hyp[b];
+  if (n_hyp >= nb) return;
+  const int steps = min(p.max_len, *p.st.stop_step);   // steps actually executed = len(next_ys) - 1
+  const int buf = ((steps - 1) & 1) ^ 1;               // alive_seq buffer written by the last executed step
+  const int* seq = p.st.alive_seq + (int64_t)buf * p.B * K * Lp1;
+  float div = 1.0f;                                    // global score divisor at len(next_ys) = steps + 1
+  if (p.lp_mode == 1) div = (float)(pow(5.0 + (double)(steps + 1), (double)alpha) / pow(6.0, (double)alpha));
+  else if (p.lp_mode == 2) div = (float)(steps + 1);
+  float* hs = p.st.hyp_score + (int64_t)b * nb;
+  int* hl = p.st.hyp_len + (int64_t)b * nb;
+  int* hq = p.st.hyp_seq + (int64_t)b * nb * p.Lmax;
+  for (int i = 0; n_hyp < nb && i < K; ++i, ++n_hyp) {
+    const float sc = p.st.topk_log_probs[b * K + i] / div;
+    int pos = nb;
+    for (int q = 0; q < nb; ++q) {
+      if (hl[q] == 0 || sc > hs[q]) { pos = q; break; }
+    }
+    __syncwarp();
+    if (pos < nb) {
+      for (int q = nb - 1; q > pos; --q) {
+        for (int j = lane; j < p.Lmax; j += 32) hq[q * p.Lmax + j] = hq[(q - 1) * p.Lmax + j];
+        __syncwarp();
+        if (lane == 0) { hs[q] = hs[q - 1]; hl[q] = hl[q - 1]; }
+        __syncwarp();
+      }
+      for (int j = lane; j < steps; j += 32) hq[pos * p.Lmax + j] = seq[(int64_t)(b * K + i) * Lp1 + 1 + j];
+      if (lane == 0) { hs[pos] = sc; hl[pos] = steps; }
+      __syncwarp();
+    }
+  }
+  (void)gs_none;
 }
 
 __global__ void beam_finalize_kernel(BeamParams p, int64_t* out_ids, int* out_lens, float* out_scores) {
@@ -188,7 +246,13 @@ cudaError_t beam_init(const BeamParams& p, int bos, cudaStream_t stream) {
 cudaError_t beam_step(const BeamParams& p, cudaStream_t stream) {
   if (p.K * p.V > 32 * kMaxCandPerLane || p.K > 32) return cudaErrorInvalidValue;
   // ((5 + step + 1) / 6) ** alpha in double like the Python expression (translator.py:720-721)
-  const double lp = pow((5.0 + (double)(p.step + 1)) / 6.0, (double)p.alpha);
+  double lp = pow((5.0 + (double)(p.step + 1)) / 6.0, (double)p.alpha);
+  if (p.mode == 1) {
+    // object mode: divisor of the global score for hypotheses finishing now, len(next_ys) = step + 2
+    // (penalties.py:65-88: wu ((5 + n) ** a) / ((5 + 1) ** a), avg n, none 1)
+    const double n = (double)(p.step + 2);
+    lp = p.lp_mode == 1 ? pow(5.0 + n, (double)p.alpha) / pow(6.0, (double)p.alpha) : (p.lp_mode == 2 ? n : 1.0);
+  }
   if (p.nb <= 0) return cudaSuccess;
   launch_k(beam_step_kernel, dim3(cdiv(p.nb, 4)), dim3(128), 0, stream, p, (float)lp);
   return cudaGetLastError();
@@ -196,6 +260,7 @@ cudaError_t beam_step(const BeamParams& p, cudaStream_t stream) {
 
 cudaError_t beam_finalize(const BeamParams& p, int64_t* out_ids, int* out_lens, float* out_scores,
                           cudaStream_t stream) {
+  if (p.mode == 1) beam_object_fill_kernel<<<p.B, 32, 0, stream>>>(p, 1.0f, p.alpha);
   launch_k(beam_finalize_kernel, dim3(p.B * p.n_best), dim3(128), 0, stream, p, out_ids, out_lens, out_scores);
   return cudaGetLastError();
 }

@@ -622,7 +622,9 @@ int alloc_workspace(nd_engine* e) {
   b.hyp_len = dalloc<int>(e, B * K);
   b.hyp_seq = dalloc<int>(e, B * K * L);
   b.n_alive = dalloc<int>(e, 1);
-  ok = ok && e->lengths && e->mem_len && e->cur_tok && b.topk_log_probs && b.alive_seq && b.anc && b.parent &&
+  b.n_done = dalloc<int>(e, 1);
+  b.stop_step = dalloc<int>(e, 1);
+  ok = ok && b.n_done && b.stop_step && e->lengths && e->mem_len && e->cur_tok && b.topk_log_probs && b.alive_seq && b.anc && b.parent &&
        b.retired && b.top_finished && b.n_hyp && b.hyp_score && b.hyp_len && b.hyp_seq && b.n_alive;
   return ok ? ND_OK : ND_ERR_NOMEM;
 }
@@ -970,13 +972,14 @@ int greedy_body(nd_engine* e, int max_len, int min_len, int64_t* out_ids, float*
   return ND_OK;
 }
 
-int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float alpha, int64_t* out_ids,
-                     int32_t* out_lens, float* out_scores, cudaStream_t st) {
+// mode 0: --fast batched beam (translator.py:619-825); mode 1: object beam (translator.py:827-926 + beam.py)
+int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float alpha, int mode, int lp_mode,
+              int64_t* out_ids, int32_t* out_lens, float* out_scores, cudaStream_t st) {
   const int B = e->B;
   ND_TRY(decoder_init(e, K, st));
   BeamParams bp;
   bp.logp = e->logp; bp.st = e->beam; bp.B = B; bp.K = K; bp.V = e->cfg.vocab_size; bp.Lmax = e->cfg.max_tgt_len;
-  bp.max_len = max_len; bp.min_len = min_len; bp.n_best = n_best; bp.alpha = alpha;
+  bp.max_len = max_len; bp.min_len = min_len; bp.n_best = n_best; bp.alpha = alpha; bp.mode = mode; bp.lp_mode = lp_mode;
   ND_LAUNCH(e, beam_init(bp, 2, st));
   const int G = n_groups(e, B);
   if (G > 1) ND_TRY(fork_streams(e, st, G));
@@ -988,7 +991,9 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
       dc.c0 = (int)((int64_t)B * g / G);
       dc.nc = (int)((int64_t)B * (g + 1) / G) - dc.c0;
       GenParams gp;
-      gp.min_len = min_len;
+      // EOS is suppressed while step < min_length (fast, translator.py:714-715) / while len(next_ys) = step + 1
+      // < min_length (object, beam.py:88-92)
+      gp.min_len = mode == 1 ? (min_len > 0 ? min_len - 1 : 0) : min_len;
       ND_TRY(decoder_step(e, dc, gp, gs));
       bp.step = step; bp.b0 = dc.c0; bp.nb = dc.nc;
       ND_LAUNCH_CAT(e, ND_PROF_BEAM, gs, beam_step(bp, gs));
@@ -1259,28 +1264,45 @@ int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* ou
   return ND_OK;
 }
 
-int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len, int32_t min_len, float alpha,
-                   int64_t* out_ids, int32_t* out_lens, float* out_scores, void* stream) {
+static int decode_beam_any(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len, int32_t min_len,
+                           float alpha, int mode, int lp_mode, int64_t* out_ids, int32_t* out_lens, float* out_scores,
+                           void* stream) {
   ND_TRY(check_ready(e));
   if (!e->encoded) return fail(e, ND_ERR_STATE, "nd_decode_beam before nd_encode");
   if (beam_size < 1 || beam_size > e->cfg.max_beam) return fail(e, ND_ERR_INVALID, "beam_size outside nd_create sizes");
   if (n_best < 1 || n_best > beam_size) return fail(e, ND_ERR_INVALID, "n_best must be in [1, beam_size]");
   if (max_len < 1 || max_len > e->cfg.max_tgt_len) return fail(e, ND_ERR_INVALID, "max_len outside nd_create sizes");
+  if (lp_mode < 0 || lp_mode > 2) return fail(e, ND_ERR_INVALID, "length penalty must be 0 (none), 1 (wu) or 2 (avg)");
+  if (mode == 1 && beam_size > e->cfg.vocab_size)
+    return fail(e, ND_ERR_INVALID, "object beam: beam_size > vocabulary (the reference's step-0 topk fails too)");
   if (!out_ids || !out_lens || !out_scores) return fail(e, ND_ERR_INVALID, "null output");
   cudaStream_t st = (cudaStream_t)stream;
   const int B = e->B, K = beam_size;
   if (e->prof_mask || !e->use_graphs)
-    return beam_body(e, K, n_best, max_len, min_len, alpha, out_ids, out_lens, out_scores, st);
+    return beam_body(e, K, n_best, max_len, min_len, alpha, mode, lp_mode, out_ids, out_lens, out_scores, st);
   int32_t alpha_bits;
   memcpy(&alpha_bits, &alpha, sizeof(alpha_bits));
-  const std::vector<int64_t> key = {1, B, e->T, e->Tp, max_len, min_len, K, n_best, alpha_bits, n_groups(e, B), g_pdl};
+  const std::vector<int64_t> key = {1 + mode * 4 + lp_mode, B, e->T, e->Tp, max_len, min_len, K, n_best, alpha_bits,
+                                    n_groups(e, B), g_pdl};
   ND_TRY(run_cached(e, key, st, [&](cudaStream_t s2) {
-    return beam_body(e, K, n_best, max_len, min_len, alpha, e->o_ids, e->o_lens, e->o_scores, s2);
+    return beam_body(e, K, n_best, max_len, min_len, alpha, mode, lp_mode, e->o_ids, e->o_lens, e->o_scores, s2);
   }));
   ND_CUDA(e, cudaMemcpyAsync(out_ids, e->o_ids, (size_t)B * n_best * max_len * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   ND_CUDA(e, cudaMemcpyAsync(out_lens, e->o_lens, (size_t)B * n_best * sizeof(int), cudaMemcpyDeviceToDevice, st));
   ND_CUDA(e, cudaMemcpyAsync(out_scores, e->o_scores, (size_t)B * n_best * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return ND_OK;
+}
+
+int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len, int32_t min_len, float alpha,
+                   int64_t* out_ids, int32_t* out_lens, float* out_scores, void* stream) {
+  return decode_beam_any(e, beam_size, n_best, max_len, min_len, alpha, 0, 0, out_ids, out_lens, out_scores, stream);
+}
+
+int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len, int32_t min_len,
+                          int32_t length_penalty, float alpha, int64_t* out_ids, int32_t* out_lens,
+                          float* out_scores, void* stream) {
+  return decode_beam_any(e, beam_size, n_best, max_len, min_len, alpha, 1, length_penalty, out_ids, out_lens, out_scores,
+                         stream);
 }
 
 int nd_set_int(nd_engine* e, const char* name, int64_t value) {

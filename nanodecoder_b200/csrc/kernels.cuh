@@ -116,6 +116,8 @@ struct BeamState {
   int* hyp_len = nullptr;                         // [B, n_best]
   int* hyp_seq = nullptr;                         // [B, n_best, Lmax]
   int* n_alive = nullptr;                         // [1] chunks not yet retired
+  int* n_done = nullptr;                          // [1] object mode: chunks whose Beam.done() is true
+  int* stop_step = nullptr;                       // [1] object mode: first step that is NOT executed any more
 };
 struct BeamParams {
   const float* logp = nullptr;                    // [B*K, V]
@@ -123,6 +125,11 @@ struct BeamParams {
   int B = 0, K = 0, V = 0, Lmax = 0, step = 0, max_len = 0, min_len = 0, n_best = 1, eos = 3;
   int b0 = 0, nb = 0;                             // chunk range [b0, b0+nb) handled by this launch (B = total)
   float alpha = 0.f;
+  // mode 1 = object beam (translator.py:827-926 + onmt/translate/beam.py): EOS rows get -1e20 children, every
+  // chunk keeps advancing until ALL chunks are done, finished hypotheses are ranked by the global score
+  // = beam score / gs_div (length penalty none / wu / avg)
+  int mode = 0;
+  int lp_mode = 0;                                // 0 none, 1 wu, 2 avg
 };
 cudaError_t beam_init(const BeamParams& p, int bos, cudaStream_t stream);
 cudaError_t beam_step(const BeamParams& p, cudaStream_t stream);

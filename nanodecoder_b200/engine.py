@@ -154,6 +154,20 @@ class Engine(object):
                                             _ptr(ids), _ptr(lens), _ptr(scores), self._stream()))
         return {"ids": ids, "lens": lens, "scores": scores}
 
+    LENGTH_PENALTY = {"none": 0, "wu": 1, "avg": 2}
+
+    def decode_beam_object(self, beam_size: int = 5, n_best: int = 1, max_len: int = 100, min_len: int = 0,
+                           length_penalty: str = "none", alpha: float = 0.0):
+        """Object beam search (the reference's default without --fast).  Same outputs as decode_beam."""
+        B = self._B
+        ids = torch.empty((B, n_best, max_len), dtype=torch.int64, device=self.device)
+        lens = torch.empty((B, n_best), dtype=torch.int32, device=self.device)
+        scores = torch.empty((B, n_best), dtype=torch.float32, device=self.device)
+        self._check(self.lib.nd_decode_beam_object(self._h, beam_size, n_best, max_len, min_len,
+                                                   self.LENGTH_PENALTY[length_penalty], float(alpha), _ptr(ids),
+                                                   _ptr(lens), _ptr(scores), self._stream()))
+        return {"ids": ids, "lens": lens, "scores": scores}
+
     # ------------------------------------------------------------------------------------------
     def frontend_stats(self, signal: torch.Tensor, offsets: torch.Tensor, normalization: str = "median"):
         """signal int16 [N_total] (device), offsets int64 [n_reads+1] (device) -> (center, scale) fp64"""

@@ -42,6 +42,31 @@ def batch_order(lengths: np.ndarray, batch_size: int) -> List[np.ndarray]:
     return out
 
 
+def reference_pad_lengths(chunk_lengths: Sequence[int], batch_size: int) -> np.ndarray:
+    """Width every chunk of ONE read is zero-padded to by the reference, which translates read by read
+    (translate.py:113-120) in consecutive groups of ``batch_size`` chunks padded to the group's longest
+    (inputter.py:86-95).  The width matters: the Transformer decoder's cross attention also attends the padded
+    positions (decoder/transformer.py:219-221 masks by signal VALUE, not by length).  Pooling chunks of many
+    reads into large GPU batches keeps results identical as long as each chunk is still padded to this width."""
+    lens = np.asarray(chunk_lengths, dtype=np.int64)
+    out = np.empty_like(lens)
+    for b0 in range(0, len(lens), batch_size):
+        out[b0: b0 + batch_size] = lens[b0: b0 + batch_size].max()
+    return out
+
+
+def pooled_batches(lengths: np.ndarray, pad_to: np.ndarray, batch_size: int) -> List[Tuple[np.ndarray, int]]:
+    """Batches for chunks pooled over many reads: chunks are grouped by their reference padding width (stable),
+    each group cut into batches of ``batch_size`` sorted by length descending.  -> [(indices, width)]"""
+    out = []
+    for w in sorted(set(int(v) for v in pad_to), reverse=True):
+        idx = np.nonzero(pad_to == w)[0]
+        for b0 in range(0, len(idx), batch_size):
+            part = idx[b0: b0 + batch_size]
+            out.append((part[np.argsort(-lengths[part], kind="stable")], w))
+    return out
+
+
 def parse_segments(src: Sequence[str]) -> Tuple[torch.Tensor, torch.Tensor]:
     """The reference's wire format between extract_fast5_raw and the translator: one string of
     space separated floats per chunk (labelop.py:231; nano_dataset.py:49-58,81).

@@ -3,8 +3,8 @@ Translator.translate :181-369, translate_batch :505-540, setAttnFile :178-179), 
 engine instead of PyTorch modules.
 
 Dispatch (translator.py:521-540): beam_size == 1 -> greedy; ``fast`` -> batched beam search;
-otherwise the object-per-chunk beam (`_translate_batch`), which this engine does not implement on
-the device yet and therefore refuses loudly (there is no CPU fallback).
+otherwise the object-per-chunk beam (`_translate_batch` + onmt.translate.Beam), which the engine runs as a
+mode of the same on-device beam kernels (nd_decode_beam_object).
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ import torch
 from ..checkpoint import load_checkpoint
 from ..config import EOS
 from ..engine import Engine
-from ..inputters.nano_dataset import batch_order, parse_segments
+from ..inputters.nano_dataset import batch_order, parse_segments, pooled_batches
 from .translation import TranslationBuilder
 
 
@@ -46,11 +46,14 @@ class _Data(object):
 
 
 class GNMTGlobalScorer(object):
-    """alpha / beta holder (onmt/translate/beam.py:181-242); only alpha is used by --fast."""
+    """alpha / beta / penalty names (onmt/translate/beam.py:181-242).  --fast only uses alpha; the object beam
+    ranks finished hypotheses with the length penalty (none | wu | avg); coverage penalties are unsupported."""
 
     def __init__(self, opt):
         self.alpha = opt.alpha
         self.beta = opt.beta
+        self.length_penalty = getattr(opt, "length_penalty", "none")
+        self.coverage_penalty = getattr(opt, "coverage_penalty", "none")
 
 
 def build_translator(opt, report_score=False, logger=None, out_file=None):
@@ -85,8 +88,10 @@ class Translator(object):
             raise ValueError("random sampling (topk != 1) is outside the supported translate path")
         if opt.block_ngram_repeat != 0 or opt.dump_beam or opt.replace_unk:
             raise ValueError("block_ngram_repeat / dump_beam / replace_unk are outside the supported translate path")
-        if self.beam_size > 1 and self.global_scorer.beta != 0:
-            raise ValueError("coverage penalty (beta != 0) is not supported by the fast beam search")
+        if self.beam_size > 1 and (self.global_scorer.beta != 0 or self.global_scorer.coverage_penalty != "none"):
+            raise ValueError("coverage penalty is outside the supported translate path")
+        if self.beam_size > 1 and getattr(opt, "stepwise_penalty", False):
+            raise ValueError("stepwise_penalty is outside the supported translate path")
 
     @classmethod
     def from_state(cls, cfg, state_dict, vocab, opt, report_score=False, logger=None):
@@ -100,8 +105,10 @@ class Translator(object):
 
     # --------------------------------------------------------------------------------------
     def translate(self, src, tgt=None, src_dir=None, batch_size=None, attn_debug=False):
-        """src: list of space separated float strings (the reference's format), or a
-        ``(chunks [n,T] fp32, lengths [n] int64)`` tuple of host or device tensors.
+        """src: list of space separated float strings (the reference's format: the chunks of ONE read), or a
+        ``(chunks [n,T] fp32, lengths [n] int64[, pad_to [n] int64])`` tuple of host or device tensors, possibly
+        pooled over many reads; ``pad_to`` = the width the reference would pad each chunk to
+        (inputters.nano_dataset.reference_pad_lengths) keeps pooled results identical to read-by-read calls.
         -> (all_scores, all_predictions) in input order; all_predictions[i] is a list of n_best
         space-joined token strings (translator.py:271-273)."""
         assert src is not None
@@ -109,8 +116,10 @@ class Translator(object):
             raise ValueError("batch_size must be set")
         if tgt is not None:
             raise ValueError("gold scoring (tgt) is outside the supported translate path")
+        pad_to = None
         if isinstance(src, tuple):
-            chunks, lengths = src
+            chunks, lengths = src[0], src[1]
+            pad_to = np.asarray(src[2], dtype=np.int64) if len(src) > 2 and src[2] is not None else None
         else:
             chunks, lengths = parse_segments(src)
         n = chunks.size(0)
@@ -124,9 +133,12 @@ class Translator(object):
         all_predictions: List = [None] * n
         counter = count(1)
         pred_score_total, pred_words_total = 0.0, 0
-        for idx in batch_order(host_lengths, batch_size):
+        if pad_to is None:
+            plan = [(idx, int(host_lengths[idx].max())) for idx in batch_order(host_lengths, batch_size)]
+        else:
+            plan = pooled_batches(host_lengths, pad_to, batch_size)
+        for idx, T in plan:
             idx_t = torch.from_numpy(idx).to(dev)
-            T = int(host_lengths[idx].max())
             b_src = chunks.index_select(0, idx_t)[:, :T].t().contiguous().unsqueeze(2)       # [T,B,1]
             batch = _Batch(b_src, lengths_d.index_select(0, idx_t), torch.arange(len(idx)))
             batch_data = self.translate_batch(batch, _Data(), attn_debug, fast=self.fast)
@@ -168,11 +180,12 @@ class Translator(object):
             results["attention"] = [[attn[:, i, : int(mlen[i])]] if attn is not None else [[]] for i in range(B)]
             return results
         if not fast:
-            raise NotImplementedError(
-                "object beam search (beam_size > 1 without --fast, translator.py:827-926) is not implemented "
-                "by the CUDA engine; pass --fast")
-        out = eng.decode_beam(self.beam_size, self.n_best, self.max_length, self.min_length,
-                              self.global_scorer.alpha)
+            # object beam (translator.py:827-926): ranking by the GNMT global score (length penalty only)
+            out = eng.decode_beam_object(self.beam_size, self.n_best, self.max_length, self.min_length,
+                                         self.global_scorer.length_penalty, self.global_scorer.alpha)
+        else:
+            out = eng.decode_beam(self.beam_size, self.n_best, self.max_length, self.min_length,
+                                  self.global_scorer.alpha)
         ids, lens, scores = out["ids"].cpu(), out["lens"].cpu(), out["scores"].cpu()
         results["predictions"] = [[ids[i, n, : int(lens[i, n])] for n in range(self.n_best)] for i in range(B)]
         results["scores"] = [[scores[i, n] for n in range(self.n_best)] for i in range(B)]

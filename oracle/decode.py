@@ -130,6 +130,92 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
         return results
 
 
+def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length=0, n_best=1,
+                length_penalty="none", alpha=0.0):
+    """translate/translator.py:827-926 (``_translate_batch``, the default when ``--fast`` is absent) with
+    onmt/translate/beam.py:74-178 (``Beam.advance / done / sort_finished / get_hyp``) and the
+    GNMTGlobalScorer of beam.py:181-208 with coverage penalty "none" (penalties.py:59-63), length penalty
+    none / wu / avg (penalties.py:65-88), no stepwise penalty, no n-gram blocking.
+    -> dict(predictions: list[B] of list[n_best] of LongTensor, scores: list[B] of list[n_best] of float)"""
+    with torch.no_grad():
+        B, K = src.size(1), beam_size
+        src, enc_states, memory_bank, src_lengths = _run_encoder(model, src, src_lengths)
+        model.decoder.init_state(src, memory_bank, enc_states)
+        model.decoder.map_state(lambda s, dim: _tile(s, K, dim))    # :872-873
+        memory_bank = _tile(memory_bank, K, 1)                      # :878
+        memory_lengths = _tile(src_lengths, K)                      # :879
+
+        def global_score(scores, n_ys):                             # beam.py:200-208, penalties.py:65-88
+            if length_penalty == "wu":
+                return scores / (((5 + n_ys) ** alpha) / ((5 + 1) ** alpha))
+            if length_penalty == "avg":
+                return scores / n_ys
+            return scores
+
+        # per chunk Beam state (beam.py:20-60)
+        scores = [torch.zeros(K) for _ in range(B)]
+        prev_ks = [[] for _ in range(B)]
+        next_ys = [[torch.full((K,), PAD, dtype=torch.long)] for _ in range(B)]
+        for b in range(B):
+            next_ys[b][0][0] = BOS
+        eos_top = [False] * B
+        finished = [[] for _ in range(B)]
+
+        for step in range(max_length):
+            if all(eos_top[b] and len(finished[b]) >= n_best for b in range(B)):    # :883-884, beam.py:151-152
+                break
+            inp = torch.stack([next_ys[b][-1] for b in range(B)]).view(1, -1, 1)
+            out, _ = _decode_and_generate(model, inp, memory_bank, memory_lengths, step)
+            out = out.view(B, K, -1)
+            select = []
+            for b in range(B):
+                word_probs = out[b]
+                V = word_probs.size(1)
+                cur_len = len(next_ys[b])
+                if cur_len < min_length:                            # beam.py:89-92
+                    word_probs[:, EOS] = -1e20
+                if len(prev_ks[b]) > 0:
+                    beam_scores = word_probs + scores[b].unsqueeze(1)
+                    for i in range(K):                              # "Don't let EOS have children" :97-100
+                        if next_ys[b][-1][i] == EOS:
+                            beam_scores[i] = -1e20
+                else:
+                    beam_scores = word_probs[0]
+                best_scores, best_id = beam_scores.reshape(-1).topk(K, 0, True, True)
+                scores[b] = best_scores
+                prev_k = torch.div(best_id, V, rounding_mode="trunc")
+                prev_ks[b].append(prev_k)
+                next_ys[b].append(best_id - prev_k * V)
+                for i in range(K):                                  # :140-144
+                    if next_ys[b][-1][i] == EOS:
+                        s_i = global_score(scores[b], len(next_ys[b]))[i]
+                        finished[b].append((float(s_i), len(next_ys[b]) - 1, i))
+                if next_ys[b][-1][0] == EOS:                        # :147-149
+                    eos_top[b] = True
+                select.append(prev_k + b * K)
+            select = torch.cat(select)
+            model.decoder.map_state(lambda s, dim: s.index_select(dim, select))      # :913-914
+
+        results = {"predictions": [], "scores": []}
+        for b in range(B):
+            i = 0
+            while len(finished[b]) < n_best:                        # sort_finished(minimum=n_best) :157-163
+                s_i = global_score(scores[b], len(next_ys[b]))[i]
+                finished[b].append((float(s_i), len(next_ys[b]) - 1, i))
+                i += 1
+            finished[b].sort(key=lambda a: -a[0])                   # stable
+            hyps = []
+            for (sc, t, k) in finished[b][:n_best]:                 # get_hyp :170-178
+                hyp = []
+                for j in range(t - 1, -1, -1):
+                    hyp.append(int(next_ys[b][j + 1][k]))
+                    k = int(prev_ks[b][j][k])
+                hyps.append(torch.tensor(hyp[::-1], dtype=torch.long))
+            results["predictions"].append(hyps)
+            results["scores"].append([sc for sc, _, _ in finished[b][:n_best]])
+        return results
+
+
 def build_target_tokens(pred, itos):
     """translate/translation.py:31-41: ids -> tokens, cut at the first ``</s>``."""
     tokens = []

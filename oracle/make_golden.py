@@ -38,6 +38,7 @@ from nanodecoder_b200 import synth                           # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 LOGIT_STEPS = (0, 1, 2, 7, 50, 99)
+OBJ_N_BEST = 2
 
 # name -> (family, kwargs)   full-size d=256 3+3 configs of BASELINE.json plus small variants
 CASES = {
@@ -112,6 +113,16 @@ def run_reference(family, cfg, sd, src, lengths, max_length, beam_size):
         out["beam_seconds"] = time.time() - t0
         out["beam_ids"] = [p[0] for p in resb["predictions"]]
         out["beam_scores"] = torch.tensor([float(s[0]) for s in resb["scores"]])
+        # ---- object beam (_translate_batch + onmt.translate.Beam: the default without --fast), n_best 2
+        tro = refshim.build_reference_translator(model, fields, mopt, beam_size=beam_size, fast=False,
+                                                 max_length=max_length, n_best=OBJ_N_BEST)
+        batch = refshim.FakeBatch(src.clone(), lengths.clone())
+        t0 = time.time()
+        reso = tro.translate_batch(batch, refshim.FakeData(), False, fast=False)
+        out["obj_seconds"] = time.time() - t0
+        out["obj_ids"] = [[torch.tensor([int(t) for t in h], dtype=torch.long) for h in p[:OBJ_N_BEST]]
+                          for p in reso["predictions"]]
+        out["obj_scores"] = torch.tensor([[float(x) for x in s[:OBJ_N_BEST]] for s in reso["scores"]])
     return out
 
 
@@ -146,6 +157,10 @@ def make_case(name, B=6, T=512, max_length=100, beam_size=5, seed=2025, write=Tr
     ob = odecode.beam_fast(om, src, lengths, beam_size=beam_size, max_length=max_length)
     beam_same = all(torch.equal(a[0], b) for a, b in zip(ob["predictions"], ref["beam_ids"]))
     bs_err = (torch.tensor([s[0] for s in ob["scores"]]) - ref["beam_scores"]).abs().max().item()
+    oo = odecode.beam_object(om, src, lengths, beam_size=beam_size, max_length=max_length, n_best=OBJ_N_BEST)
+    obj_same = all(torch.equal(a, b) for pa, pb in zip(oo["predictions"], ref["obj_ids"]) for a, b in zip(pa, pb))
+    obj_err = (torch.tensor(oo["scores"]) - ref["obj_scores"]).abs().max().item()
+    assert obj_same and obj_err < 1e-3, "oracle object-beam output differs from the reference (%s, %g)" % (obj_same, obj_err)
     ids = ref["greedy_ids"]
     hist = torch.bincount(ids.flatten(), minlength=cfg.vocab_size).float()
     p = hist / hist.sum()
@@ -179,6 +194,9 @@ def make_case(name, B=6, T=512, max_length=100, beam_size=5, seed=2025, write=Tr
             memory_sum=np.float64(mb.double().sum().item()),
             memory_abs_sum=np.float64(mb.double().abs().sum().item()),
             beam_ids=pad_ragged(ref["beam_ids"], max_length), beam_scores=ref["beam_scores"].numpy(),
+            obj_n_best=OBJ_N_BEST,
+            obj_ids=np.stack([pad_ragged(p, max_length) for p in ref["obj_ids"]]),      # [B, n_best, L], -1 padded
+            obj_scores=ref["obj_scores"].numpy(),
             token_entropy_bits=entropy,
         )
 

@@ -5,7 +5,7 @@ import scipy.stats
 
 from helpers import GOLDEN
 from oracle import frontend as ofe
-from nanodecoder_b200.inputters.nano_dataset import batch_order, chunk_table, parse_segments
+from nanodecoder_b200.inputters.nano_dataset import pooled_batches, reference_pad_lengths, batch_order, chunk_table, parse_segments
 
 
 def _golden():
@@ -49,3 +49,16 @@ def test_batch_order_and_parse_segments():
     assert chunks.shape == (2, 3) and l.tolist() == [3, 1] and float(chunks[1, 1]) == 0.0
     src, lengths, idx = ofe.make_batches([np.zeros(5), np.ones(9), np.ones(5)], 3)[0]
     assert idx.tolist() == [1, 0, 2] and src.shape == (9, 3, 1)
+
+
+def test_pooled_batches_keep_reference_padding_width():
+    """Chunks pooled over reads are padded exactly as in the reference's read-by-read batches."""
+    read_a = [128, 128, 128, 128, 128, 60]           # batch_size 5 -> groups [128 x5] and [60]
+    read_b = [128, 77]
+    pad = np.concatenate([reference_pad_lengths(read_a, 5), reference_pad_lengths(read_b, 5)])
+    assert pad.tolist() == [128] * 5 + [60] + [128, 128]
+    lens = np.array(read_a + read_b)
+    plan = pooled_batches(lens, pad, 4)
+    assert [(i.tolist(), w) for i, w in plan] == [([0, 1, 2, 3], 128), ([4, 6, 7], 128), ([5], 60)]
+    for src, l, idx in ofe.make_batches([np.zeros(n) for n in read_a], 5):
+        assert all(src.shape[0] == pad[i] for i in idx)

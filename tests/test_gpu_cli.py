@@ -43,12 +43,13 @@ def test_translate_cli_matches_oracle_chain(tmp_path, stride):
     speed = (out_dir / "speed.txt").read_text().strip().splitlines()
     assert len(speed) == len(reads)
     for name, raw in reads.items():
-        chunks = ofe.frontend(raw, "median", 128, stride)
-        want_preds = []
-        for c in chunks:                                  # one chunk per oracle call: no batching effects
-            src = torch.from_numpy(c).view(-1, 1, 1)
-            o = od.greedy(om, src, torch.tensor([len(c)]), max_length=L)
-            want_preds.append([" ".join(od.build_target_tokens(o["predictions"][0], cfg.vocab))])
+        # the reference translates read by read, in consecutive batches of batch_size chunks (translate.py:113-120)
+        chunks = ofe.chunk(ofe.normalise(raw, "median"), 128, stride)
+        want_preds = [None] * len(chunks)
+        for src, lens, idx in ofe.make_batches(chunks, 5):
+            o = od.greedy(om, torch.from_numpy(src), torch.from_numpy(lens), max_length=L)
+            for j, i in enumerate(idx):
+                want_preds[int(i)] = [" ".join(od.build_target_tokens(o["predictions"][j], cfg.vocab))]
         seg = (out_dir / "segment" / (name + ".txt")).read_text().splitlines()
         assert seg == [p[0] for p in want_preds], name
         if stride < 128:

@@ -74,6 +74,51 @@ def test_beam_matches_reference_golden(name):
     np.testing.assert_allclose(scores[:, 0], g["beam_scores"], atol=5e-3)
 
 
+@pytest.mark.parametrize("name", IMPLEMENTED)
+def test_object_beam_matches_reference_golden(name):
+    """nd_decode_beam_object vs the reference's _translate_batch + onmt.translate.Beam (no --fast), n_best 2."""
+    g, cfg, sd, src, lengths = load_golden(name)
+    B, T, L, K, NB = src.shape[0], src.shape[1], int(g["max_length"]), int(g["beam_size"]), int(g["obj_n_best"])
+    eng = _engine(cfg, sd, B, T, L, K=K)
+    eng.encode(src.cuda(), lengths.cuda())
+    out = eng.decode_beam_object(K, NB, L)
+    torch.cuda.synchronize()
+    ids, lens, scores = out["ids"].cpu().numpy(), out["lens"].cpu().numpy(), out["scores"].cpu().numpy()
+    for i in range(B):
+        for n in range(NB):
+            want = g["obj_ids"][i, n]
+            want = want[want >= 0]
+            np.testing.assert_array_equal(ids[i, n, : lens[i, n]], want, err_msg="chunk %d hyp %d" % (i, n))
+    np.testing.assert_allclose(scores, g["obj_scores"], atol=5e-3)
+
+
+@pytest.mark.parametrize("lp,alpha,min_len", [("none", 0.0, 0), ("wu", 0.6, 0), ("avg", 0.0, 7)])
+def test_object_beam_vs_oracle_penalties_and_min_length(lp, alpha, min_len):
+    from oracle import decode as od
+    from oracle.model import OracleModel
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    sd = synth.make_state_dict(cfg, seed=11)
+    B, T, L, K, NB = 19, 160, 36, 4, 3
+    chunks, lengths = synth.make_chunks(B, T=T, seed=5, ragged=True, read_len=3)
+    order = torch.argsort(lengths, descending=True, stable=True)
+    chunks, lengths = chunks[order], lengths[order]
+    eng = _engine(cfg, sd, B, T, L, K=K)
+    eng.encode(chunks.cuda(), lengths.cuda())
+    out = eng.decode_beam_object(K, NB, L, min_len=min_len, length_penalty=lp, alpha=alpha)
+    torch.cuda.synchronize()
+    want = od.beam_object(OracleModel(sd, cfg), chunks.t().contiguous().unsqueeze(2), lengths, beam_size=K,
+                          max_length=L, min_length=min_len, n_best=NB, length_penalty=lp, alpha=alpha)
+    ids, lens, sc = out["ids"].cpu(), out["lens"].cpu(), out["scores"].cpu()
+    mism = 0
+    for i in range(B):
+        for n in range(NB):
+            if torch.equal(ids[i, n, : int(lens[i, n])], want["predictions"][i][n]):
+                assert abs(float(sc[i, n]) - want["scores"][i][n]) < 5e-3
+            else:
+                mism += 1
+    assert mism == 0, "%d of %d object-beam hypotheses differ" % (mism, NB * B)
+
+
 @pytest.mark.parametrize("family", ["l2t", "t2t", "nano2rnn", "cnn2cnn"])
 def test_greedy_and_beam_vs_oracle_ragged(family):
     """Fresh seeded inputs, ragged lengths incl. very short chunks, d=64 (oracle runs in seconds)."""

@@ -42,6 +42,32 @@ def test_oracle_beam_matches_reference_golden(name):
     np.testing.assert_allclose([s[0] for s in out["scores"]], g["beam_scores"], atol=1e-3)
 
 
+@pytest.mark.parametrize("name", ["l2t_d256", "brnn2rnn_d256", "cnn2cnn_d256", "t2t_d64", "l2t_d64"])
+def test_oracle_object_beam_matches_reference_golden(name):
+    """_translate_batch + onmt.translate.Beam (the default without --fast), n_best 2."""
+    g, cfg, sd, src, lengths = load_golden(name)
+    om = OracleModel(sd, cfg)
+    L, K, NB = int(g["max_length"]), int(g["beam_size"]), int(g["obj_n_best"])
+    out = odecode.beam_object(om, src.t().contiguous().unsqueeze(2), lengths, beam_size=K, max_length=L, n_best=NB)
+    for i, hyps in enumerate(out["predictions"]):
+        for n in range(NB):
+            want = g["obj_ids"][i, n]
+            np.testing.assert_array_equal(hyps[n].numpy(), want[want >= 0])
+    np.testing.assert_allclose(np.array(out["scores"]), g["obj_scores"], atol=1e-3)
+
+
+def test_object_beam_length_penalties_change_ranking_only():
+    """wu / avg length penalties rescale the finished scores (penalties.py:65-88); beams themselves are unchanged."""
+    g, cfg, sd, src, lengths = load_golden("l2t_d64")
+    om = OracleModel(sd, cfg)
+    s = src.t().contiguous().unsqueeze(2)
+    a = odecode.beam_object(om, s, lengths, beam_size=4, max_length=30, n_best=4)
+    b = odecode.beam_object(om, s, lengths, beam_size=4, max_length=30, n_best=4, length_penalty="avg")
+    for ha, hb in zip(a["predictions"], b["predictions"]):
+        assert sorted(tuple(h.tolist()) for h in ha) == sorted(tuple(h.tolist()) for h in hb)
+    assert a["scores"] != b["scores"]
+
+
 def test_greedy_runs_all_steps_and_golden_is_diverse():
     g, cfg, sd, src, lengths = load_golden("l2t_d256")
     assert g["greedy_ids"].shape == (int(g["B"]), int(g["max_length"]))        # no EOS early exit

@@ -41,7 +41,7 @@ def write_output(opt, file_src, all_predictions, time_translate):
 
 
 def main(opt, logger):
-    from nanodecoder_b200.inputters.nano_dataset import SignalFrontend
+    from nanodecoder_b200.inputters.nano_dataset import SignalFrontend, reference_pad_lengths
     from nanodecoder_b200.translate.translator import build_translator
     from nanodecoder_b200.utils.labelop import read_raw_signal
     from nanodecoder_b200 import shard
@@ -85,7 +85,13 @@ def main(opt, logger):
         if not keep:
             continue
         chunks, lengths, chunk_read = frontend([reads[i] for i in keep])
-        _, preds = translator.translate(src=(chunks, lengths), tgt=None, src_dir=opt.save_data,
+        # chunks of many reads share GPU batches; each keeps the padding width of its read-by-read reference batch
+        h_len = lengths.cpu().numpy()
+        pad_to = np.empty_like(h_len)
+        for j in range(len(keep)):
+            sel = np.nonzero(chunk_read == j)[0]
+            pad_to[sel] = reference_pad_lengths(h_len[sel], opt.batch_size)
+        _, preds = translator.translate(src=(chunks, lengths, pad_to), tgt=None, src_dir=opt.save_data,
                                         batch_size=opt.batch_size, attn_debug=opt.attn_debug)
         elapsed = time.time() - start
         total = max(1, len(chunk_read))
