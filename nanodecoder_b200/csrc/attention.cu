@@ -184,6 +184,209 @@ cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream) {
 }
 
 // =============================================================================================
+// Cross attention in memory-bank space (see CrossMbParams).  One CTA (256 threads) per chunk streams the
+// chunk's memory bank through shared memory ONCE in tiles of 32 positions (one 32 KB cp.async.bulk per tile,
+// mbarrier transaction counts, NST stages in flight) and keeps an online softmax per head:
+//   phase A  S[h][t] = mb[t] . qt_h      lane = position, warp g = column slice [g d/8, (g+1) d/8): 128-bit row
+//            reads rotated by the lane index (conflict-free without padding); 8 partial sums per (h, t) combined
+//            through shared memory
+//   softmax  warp h: mask, running max / sum, p = exp(S - m), rescale factor for the accumulators
+//   phase B  acc[h][j] += p[h][t] mb[t][j]  thread = 4 columns x all heads, the 1024/d thread groups split the rows
+// fp32 FFMA throughout (4 T d H flops per chunk): at d = 256 the FFMA time is about the HBM time of the
+// T*d*4-byte read, so the kernel stays on the HBM roofline at half the bytes of the K/V formulation.
+namespace {
+
+constexpr int kMbTT = 32;                          // positions per tile
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+template <int H>
+__global__ void __launch_bounds__(256) cross_attn_mb_kernel(CrossMbParams p, int nst) {
+  extern __shared__ __align__(16) float smem_f[];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int chunk = blockIdx.x;
+  const int d = p.d, T = p.T;
+  const int pitch = d;                             // a tile is a contiguous [32][d] block: ONE bulk copy
+  const int tile_f = kMbTT * pitch;
+  float* tiles = smem_f;                           // [nst][32][pitch]
+  float* qt_s = tiles + (size_t)nst * tile_f;      // [H][d]
+  float* part = qt_s + H * d;                      // [8][H][32] phase-A partial sums
+  float* prob = part + 8 * H * kMbTT;              // [32][H]
+  float* alpha_s = prob + kMbTT * H;               // [H] accumulator rescale of this tile, then 1/l at the end
+  uint64_t* full = reinterpret_cast<uint64_t*>(alpha_s + H);   // [nst]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (T + kMbTT - 1) / kMbTT;
+  const float* mb = p.mb + (int64_t)chunk * T * d;
+  const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
+
+  if (tid == 0) {
+    for (int s = 0; s < nst; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // producer = one thread: a tile of 32 positions is rows*d*4 contiguous bytes of the memory bank
+  auto issue_tile = [&](int i) {
+    const int s = i % nst;
+    const int rows = min(kMbTT, T - i * kMbTT);
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(rows * d * 4);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&full[s])), "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_addr_u32(tiles + (size_t)s * tile_f)),
+                   "l"(mb + (int64_t)i * kMbTT * d), "r"(bytes), "r"(smem_addr_u32(&full[s]))
+                   : "memory");
+    }
+  };
+  if (warp == 0)
+    for (int i = 0; i < nst && i < ntiles; ++i) issue_tile(i);
+  for (int i = tid; i < H * d; i += 256) qt_s[i] = p.qt[(int64_t)chunk * H * d + i];
+
+  const int JW = d / 8;                            // phase-A columns per warp
+  const int TPR = d / 4;                           // phase-B threads per row
+  const int RG = 256 / TPR;                        // phase-B row groups
+  const int RPG = kMbTT / RG;                      // rows per group and tile
+  const int rg = tid / TPR, j4 = (tid % TPR) * 4;
+  float acc[H][4];
+#pragma unroll
+  for (int h = 0; h < H; ++h) { acc[h][0] = 0.f; acc[h][1] = 0.f; acc[h][2] = 0.f; acc[h][3] = 0.f; }
+  float m_run = -INFINITY, l_run = 0.f;            // running max / sum of head `warp` (warp-uniform)
+  __syncthreads();
+
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i % nst;
+    const float* tile = tiles + (size_t)s * tile_f;
+    const int rows = min(kMbTT, T - i * kMbTT);
+    {
+      const uint32_t parity = (uint32_t)((i / nst) & 1);
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra DONE_%=;\n"
+          "bra WAIT_%=;\n"
+          "DONE_%=:\n"
+          "}\n" ::"r"(smem_addr_u32(&full[s])),
+          "r"(parity)
+          : "memory");
+    }
+    // ---- phase A
+    {
+      float sa[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) sa[h] = 0.f;
+      if (lane < rows) {
+        // rows are d*4 bytes apart (a multiple of 128): lane r starts at 16-byte unit r of its slice and
+        // wraps, so the 8 lanes of a shared-memory wavefront touch 8 different bank groups
+        const float* mrow = tile + lane * pitch + warp * JW;
+        const float* qcol = qt_s + warp * JW;
+        const int nch = JW >> 2;
+        for (int ci = 0; ci < nch; ++ci) {
+          const int c = ((ci + lane) & (nch - 1)) << 2;
+          const float4 mv = *reinterpret_cast<const float4*>(mrow + c);
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            const float4 qv = *reinterpret_cast<const float4*>(qcol + h * d + c);
+            sa[h] = fmaf(mv.x, qv.x, sa[h]);
+            sa[h] = fmaf(mv.y, qv.y, sa[h]);
+            sa[h] = fmaf(mv.z, qv.z, sa[h]);
+            sa[h] = fmaf(mv.w, qv.w, sa[h]);
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) part[(warp * H + h) * kMbTT + lane] = sa[h];
+    }
+    __syncthreads();
+    // ---- online softmax: warp h owns head h (H <= 8 warps)
+    if (warp < H) {
+      float sc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sc += part[(g * H + warp) * kMbTT + lane];
+      const int t = i * kMbTT + lane;
+      if (t >= T) sc = -INFINITY;
+      else if (srow && srow[t] == p.mask_value) sc = -1e18f;          // masked_fill(mask, -1e18)
+      const float m_new = fmaxf(m_run, warp_max(sc));
+      const float al = expf(m_run - m_new);                           // 0 on the first tile
+      const float pr = expf(sc - m_new);
+      l_run = l_run * al + warp_sum(pr);
+      m_run = m_new;
+      prob[lane * H + warp] = pr;
+      if (lane == 0) alpha_s[warp] = al;
+    }
+    __syncthreads();
+    // ---- phase B
+    {
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float al = alpha_s[h];
+        acc[h][0] *= al; acc[h][1] *= al; acc[h][2] *= al; acc[h][3] *= al;
+      }
+      const int r1 = min(rows, (rg + 1) * RPG);
+      for (int r = rg * RPG; r < r1; ++r) {
+        const float4 mv = *reinterpret_cast<const float4*>(tile + r * pitch + j4);
+        float pw[H];
+#pragma unroll
+        for (int h = 0; h < H; h += 4) {
+          const float4 pv = *reinterpret_cast<const float4*>(prob + r * H + h);
+          pw[h] = pv.x; pw[h + 1] = pv.y; pw[h + 2] = pv.z; pw[h + 3] = pv.w;
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          acc[h][0] = fmaf(pw[h], mv.x, acc[h][0]);
+          acc[h][1] = fmaf(pw[h], mv.y, acc[h][1]);
+          acc[h][2] = fmaf(pw[h], mv.z, acc[h][2]);
+          acc[h][3] = fmaf(pw[h], mv.w, acc[h][3]);
+        }
+      }
+    }
+    __syncthreads();                               // stage s, part and prob are free again
+    if (warp == 0 && i + nst < ntiles) issue_tile(i + nst);
+  }
+
+  // ---- combine the row groups, normalise by the softmax sum, write ctxt[h][j]
+  if (warp < H && lane == 0) alpha_s[warp] = 1.0f / l_run;
+  float* red = tiles;                              // [RG][H][d] = 1024 H floats <= one stage
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+    *reinterpret_cast<float4*>(red + ((size_t)rg * H + h) * d + j4) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+  __syncthreads();
+  float* out = p.ctxt + (int64_t)chunk * H * d;
+  for (int i = tid; i < H * d; i += 256) {
+    float sum = 0.f;
+    for (int g = 0; g < RG; ++g) sum += red[(size_t)g * H * d + i];
+    out[i] = sum * alpha_s[i / d];
+  }
+}
+
+}  // namespace
+
+bool cross_attention_mb_supported(int d, int H) {
+  return H == 8 && (d == 32 || d == 64 || d == 128 || d == 256 || d == 512 || d == 1024);
+}
+
+cudaError_t cross_attention_mb(const CrossMbParams& p, cudaStream_t stream) {
+  if (p.n_chunks <= 0) return cudaSuccess;
+  if (!cross_attention_mb_supported(p.d, p.H)) return cudaErrorInvalidValue;
+  constexpr int H = 8;
+  const size_t tile_b = (size_t)kMbTT * p.d * sizeof(float);
+  const size_t fixed = ((size_t)H * p.d + 8 * H * kMbTT + kMbTT * H + H) * sizeof(float) + 64;
+  int nst = 4;
+  while (nst > 2 && nst * tile_b + fixed > 100 * 1024) --nst;        // two CTAs per SM when the tiles allow it
+  const size_t smem = nst * tile_b + fixed;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(cross_attn_mb_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  return launch_k(cross_attn_mb_kernel<H>, dim3(p.n_chunks), dim3(256), smem, stream, p, nst);
+}
+
+// =============================================================================================
 // Decode-step self attention.  One CTA per row, one warp per head (looping when H > warps).
 namespace {
 

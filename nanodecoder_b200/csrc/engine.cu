@@ -49,6 +49,7 @@ struct EncLayerT {             // transformer encoder layer
 };
 struct DecLayerT {             // transformer decoder layer
   Lin qkv, self_out, cq, ckv, ctx_out, w1, w2;
+  Lin cqt, cm;                 // memory-bank-space cross attention (kernels.cuh CrossMbParams): P [H*d, d], Mcat [d, H*d]
   LnW ln1, ln2, ln_ff;
 };
 struct LstmW {                 // one bidirectional (or unidirectional) LSTM layer
@@ -122,6 +123,11 @@ struct nd_engine {
   std::vector<float*> selfK, selfV;  // per layer [rows, L, d]
   float *x = nullptr, *qkv = nullptr, *sctx = nullptr, *x1 = nullptr, *qc = nullptr, *cctx = nullptr, *x2 = nullptr,
         *ffh = nullptr, *logp = nullptr, *gscore = nullptr;
+  float *qt = nullptr, *cctxt = nullptr;   // [maxB, H*d] memory-bank-space cross attention (greedy)
+  // 0 (default): K/V cross attention, HBM-bound at 96 % of the measured peak.  1: greedy decode reads the memory
+  // bank once per layer-step (half the bytes, 8x the fp32 FMAs): measured 291 us vs 171 us per launch at d = 256
+  // (profiles/r01_cross_mb_experiment.md) -- kept as an option until its FFMA side is as good as its byte count
+  int cross_mode = 0;
   int* cur_tok = nullptr;
   // rnn decoder
   float* uh = nullptr;               // [B, T', d]
@@ -415,6 +421,60 @@ int load_wnconv(nd_engine* e, const std::string& prefix, int d, int k, Lin* out)
   return ND_OK;
 }
 
+// Memory-bank-space cross attention weights of one decoder layer (see CrossMbParams), products in double:
+//   P[h*d + j][k]   = sum_i Wk[h*dh+i][j] Wq[h*dh+i][k] / sqrt(dh)      pb[h*d + j] = sum_i Wk[h*dh+i][j] bq[h*dh+i] / sqrt(dh)
+//   M[n][h*d + j]   = sum_i Wo[n][h*dh+i] Wv[h*dh+i][j]                 mo[n] = bo[n] + sum_i Wo[n][i] bv[i]
+// (bk only adds a per-head constant to every score of a row, which the softmax removes.)
+int load_cross_mb(nd_engine* e, const std::string& p, const std::string& ln_prefix, int d, int H, Lin* cqt, Lin* cm) {
+  const HostTensor *wq, *bq, *wk, *wv, *bv, *wo, *bo, *g, *bb;
+  ND_TRY(need(e, p + ".linear_query.weight", {d, d}, &wq));
+  ND_TRY(need(e, p + ".linear_query.bias", {d}, &bq));
+  ND_TRY(need(e, p + ".linear_keys.weight", {d, d}, &wk));
+  ND_TRY(need(e, p + ".linear_values.weight", {d, d}, &wv));
+  ND_TRY(need(e, p + ".linear_values.bias", {d}, &bv));
+  ND_TRY(need(e, p + ".final_linear.weight", {d, d}, &wo));
+  ND_TRY(need(e, p + ".final_linear.bias", {d}, &bo));
+  ND_TRY(need(e, ln_prefix + ".weight", {d}, &g));
+  ND_TRY(need(e, ln_prefix + ".bias", {d}, &bb));
+  const int dh = d / H;
+  const double sc = 1.0 / sqrt((double)dh);
+  const int64_t HD = (int64_t)H * d;
+  std::vector<float> P((size_t)HD * d), pb((size_t)HD), M((size_t)d * HD), mo((size_t)d);
+  std::vector<double> row((size_t)d);
+  for (int h = 0; h < H; ++h)
+    for (int j = 0; j < d; ++j) {
+      std::fill(row.begin(), row.end(), 0.0);
+      double bsum = 0.0;
+      for (int i = 0; i < dh; ++i) {
+        const double wkij = wk->f[(size_t)(h * dh + i) * d + j];
+        const float* wqr = wq->f.data() + (size_t)(h * dh + i) * d;
+        for (int k = 0; k < d; ++k) row[k] += wkij * (double)wqr[k];
+        bsum += wkij * (double)bq->f[h * dh + i];
+      }
+      float* pr = P.data() + ((size_t)h * d + j) * d;
+      for (int k = 0; k < d; ++k) pr[k] = (float)(row[k] * sc);
+      pb[(size_t)h * d + j] = (float)(bsum * sc);
+    }
+  for (int n = 0; n < d; ++n) {
+    double bsum = bo->f[n];
+    for (int i = 0; i < d; ++i) bsum += (double)wo->f[(size_t)n * d + i] * (double)bv->f[i];
+    mo[n] = (float)bsum;
+    for (int h = 0; h < H; ++h) {
+      std::fill(row.begin(), row.end(), 0.0);
+      for (int i = 0; i < dh; ++i) {
+        const double w = wo->f[(size_t)n * d + h * dh + i];
+        const float* wvr = wv->f.data() + (size_t)(h * dh + i) * d;
+        for (int j = 0; j < d; ++j) row[j] += w * (double)wvr[j];
+      }
+      float* mr = M.data() + (size_t)n * HD + (size_t)h * d;
+      for (int j = 0; j < d; ++j) mr[j] = (float)row[j];
+    }
+  }
+  *cqt = make_lin(e, P, (int)HD, d, &pb, 1, &g->f, &bb->f);
+  *cm = make_lin(e, M, d, (int)HD, &mo);
+  return ND_OK;
+}
+
 int finalize(nd_engine* e) {
   const nd_config& c = e->cfg;
   const int d = c.d_model, V = c.vocab_size;
@@ -492,6 +552,8 @@ int finalize(nd_engine* e) {
       ND_TRY(load_lin(e, p + ".context_attn.linear_query", d, d, true, &L.cq, p + ".layer_norm_2"));
       ND_TRY(load_cat_lin(e, {p + ".context_attn.linear_keys", p + ".context_attn.linear_values"}, d, d, &L.ckv));
       ND_TRY(load_lin(e, p + ".context_attn.final_linear", d, d, true, &L.ctx_out));
+      if (cross_attention_mb_supported(d, c.heads))
+        ND_TRY(load_cross_mb(e, p + ".context_attn", p + ".layer_norm_2", d, c.heads, &L.cqt, &L.cm));
       ND_TRY(load_lin(e, p + ".feed_forward.w_1", c.d_ff, d, true, &L.w1, p + ".feed_forward.layer_norm"));
       ND_TRY(load_lin(e, p + ".feed_forward.w_2", d, c.d_ff, true, &L.w2));
       ND_TRY(load_ln(e, p + ".layer_norm_1", d, &L.ln1));
@@ -587,6 +649,7 @@ int alloc_workspace(nd_engine* e) {
     for (int l = 0; l < c.dec_layers; ++l) { F(e->ckv[l], BT * 2 * d); F(e->selfK[l], rows * L * d); F(e->selfV[l], rows * L * d); }
     F(e->x, rows * d); F(e->qkv, rows * 3 * d); F(e->sctx, rows * d); F(e->x1, rows * d); F(e->qc, rows * d);
     F(e->cctx, rows * d); F(e->x2, rows * d); F(e->ffh, rows * c.d_ff);
+    if (cross_attention_mb_supported((int)d, c.heads)) { F(e->qt, B * c.heads * d); F(e->cctxt, B * c.heads * d); }
   } else if (c.decoder_type == ND_DEC_RNN) {
     F(e->uh, BT * d);
     for (int s = 0; s < 2; ++s) {
@@ -743,10 +806,15 @@ struct DecodeCtx {
   int K = 1, step = 0, Lmax = 0;
   int c0 = 0, nc = 0;                 // chunk range handled by this call; rows = [c0*K, (c0+nc)*K)
   bool beam = false;
+  bool cross_mb = false;              // cross attention in memory-bank space (greedy, no attention output)
   float* attn_out = nullptr;          // optional [rows_total, T'] for this step
 };
 
-int decoder_init(nd_engine* e, int K, cudaStream_t st) {
+bool use_cross_mb(const nd_engine* e, int K, bool want_attn) {
+  return e->cross_mode == 1 && K == 1 && !want_attn && e->cfg.decoder_type == ND_DEC_TRANSFORMER && e->qt != nullptr;
+}
+
+int decoder_init(nd_engine* e, int K, cudaStream_t st, bool cross_mb = false) {
   const nd_config& c = e->cfg;
   const int d = c.d_model, B = e->B, Tp = e->Tp;
   const int64_t M = (int64_t)B * Tp;
@@ -754,8 +822,9 @@ int decoder_init(nd_engine* e, int K, cudaStream_t st) {
     if (Tp != e->T)
       return fail(e, ND_ERR_INVALID, "transformer decoder needs -audio_enc_pooling 1 (the reference builds its cross "
                                      "mask from the un-pooled signal, decoder/transformer.py:201-221)");
-    // memory keys / values, projected once per chunk (multi_headed_attn.py:142-153)
-    for (int l = 0; l < c.dec_layers; ++l) {
+    // memory keys / values, projected once per chunk (multi_headed_attn.py:142-153); not needed when the
+    // cross attention runs in memory-bank space
+    for (int l = 0; l < c.dec_layers && !cross_mb; ++l) {
       GemmOpt o;
       ND_TRY(run_gemm(e, e->decT[l].ckv, e->mb, d, e->ckv[l], 2 * d, M, o, st));
     }
@@ -823,18 +892,32 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
       ND_LAUNCH_CAT(e, ND_PROF_SELF_ATTN, st, self_attention_step(sa, st));
       GemmOpt o2; o2.residual = x; o2.ldr = d;
       ND_TRY(run_gemm(e, L.self_out, R(e->sctx, d), d, R(e->x1, d), d, rows, o2, st));
-      GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln2.g; o3.pb = L.ln2.b;
-      ND_TRY(run_gemm(e, L.cq, R(e->x1, d), d, R(e->qc, d), d, rows, o3, st));
-      CrossAttnParams ca;
-      ca.q = R(e->qc, d); ca.q_ld = d; ca.q_div = sq;
-      ca.K = e->ckv[l] + (int64_t)dc.c0 * Tp * 2 * d; ca.V = ca.K + d; ca.kv_ld = 2 * d;
-      ca.src = e->src + (int64_t)dc.c0 * e->T; ca.src_ld = e->T; ca.mask_value = 1.0f;   // decoder/transformer.py:219-221
-      ca.retired = retired ? retired + dc.c0 : nullptr; ca.ctx = R(e->cctx, d); ca.ctx_ld = d; ca.n_chunks = dc.nc;
-      ca.NQ = K; ca.T = Tp; ca.d = d; ca.H = c.heads;
-      ca.attn = (l + 1 == c.dec_layers && dc.attn_out) ? dc.attn_out + (int64_t)r0 * Tp : nullptr;
-      ND_LAUNCH_CAT(e, ND_PROF_CROSS_ATTN, st, cross_attention(ca, st));
-      GemmOpt o4; o4.residual = R(e->x1, d); o4.ldr = d;
-      ND_TRY(run_gemm(e, L.ctx_out, R(e->cctx, d), d, R(e->x2, d), d, rows, o4, st));
+      if (dc.cross_mb) {
+        // cross attention in memory-bank space: QT = LN2(x1) P^T + pb -> attention over mb -> x2 = x1 + ctxt Mcat^T + mo
+        const int64_t HD = (int64_t)c.heads * d;
+        GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln2.g; o3.pb = L.ln2.b;
+        ND_TRY(run_gemm(e, L.cqt, R(e->x1, d), d, R(e->qt, HD), HD, rows, o3, st));
+        CrossMbParams cm;
+        cm.qt = R(e->qt, HD); cm.mb = e->mb + (int64_t)dc.c0 * Tp * d;
+        cm.src = e->src + (int64_t)dc.c0 * e->T; cm.src_ld = e->T; cm.mask_value = 1.0f;   // decoder/transformer.py:219-221
+        cm.ctxt = R(e->cctxt, HD); cm.n_chunks = dc.nc; cm.T = Tp; cm.d = d; cm.H = c.heads;
+        ND_LAUNCH_CAT(e, ND_PROF_CROSS_ATTN, st, cross_attention_mb(cm, st));
+        GemmOpt o4; o4.residual = R(e->x1, d); o4.ldr = d;
+        ND_TRY(run_gemm(e, L.cm, R(e->cctxt, HD), HD, R(e->x2, d), d, rows, o4, st));
+      } else {
+        GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln2.g; o3.pb = L.ln2.b;
+        ND_TRY(run_gemm(e, L.cq, R(e->x1, d), d, R(e->qc, d), d, rows, o3, st));
+        CrossAttnParams ca;
+        ca.q = R(e->qc, d); ca.q_ld = d; ca.q_div = sq;
+        ca.K = e->ckv[l] + (int64_t)dc.c0 * Tp * 2 * d; ca.V = ca.K + d; ca.kv_ld = 2 * d;
+        ca.src = e->src + (int64_t)dc.c0 * e->T; ca.src_ld = e->T; ca.mask_value = 1.0f;   // decoder/transformer.py:219-221
+        ca.retired = retired ? retired + dc.c0 : nullptr; ca.ctx = R(e->cctx, d); ca.ctx_ld = d; ca.n_chunks = dc.nc;
+        ca.NQ = K; ca.T = Tp; ca.d = d; ca.H = c.heads;
+        ca.attn = (l + 1 == c.dec_layers && dc.attn_out) ? dc.attn_out + (int64_t)r0 * Tp : nullptr;
+        ND_LAUNCH_CAT(e, ND_PROF_CROSS_ATTN, st, cross_attention(ca, st));
+        GemmOpt o4; o4.residual = R(e->x1, d); o4.ldr = d;
+        ND_TRY(run_gemm(e, L.ctx_out, R(e->cctx, d), d, R(e->x2, d), d, rows, o4, st));
+      }
       GemmOpt o5; o5.prologue = PRO_LAYERNORM; o5.pg = L.ln_ff.g; o5.pb = L.ln_ff.b; o5.act = 1;
       ND_TRY(run_gemm(e, L.w1, R(e->x2, d), d, R(e->ffh, c.d_ff), c.d_ff, rows, o5, st));
       GemmOpt o6; o6.residual = R(e->x2, d); o6.ldr = d;
@@ -949,14 +1032,15 @@ int n_groups(const nd_engine* e, int B) {
 int greedy_body(nd_engine* e, int max_len, int min_len, int64_t* out_ids, float* out_scores, float* out_attn,
                        float* out_logits, cudaStream_t st) {
   const int B = e->B, V = e->cfg.vocab_size;
-  ND_TRY(decoder_init(e, 1, st));
+  const bool cross_mb = use_cross_mb(e, 1, out_attn != nullptr);
+  ND_TRY(decoder_init(e, 1, st, cross_mb));
   ND_LAUNCH(e, fill_int(e->cur_tok, B, 2, st));          // <s> for every row (translator.py:451-452)
   const int G = n_groups(e, B);
   if (G > 1) ND_TRY(fork_streams(e, st, G));
   for (int step = 0; step < max_len; ++step) {           // no EOS early exit, like the reference (:455)
     for (int g = 0; g < G; ++g) {
       DecodeCtx dc;
-      dc.K = 1; dc.Lmax = e->cfg.max_tgt_len; dc.beam = false; dc.step = step;
+      dc.K = 1; dc.Lmax = e->cfg.max_tgt_len; dc.beam = false; dc.step = step; dc.cross_mb = cross_mb;
       dc.c0 = (int)((int64_t)B * g / G);
       dc.nc = (int)((int64_t)B * (g + 1) / G) - dc.c0;
       dc.attn_out = out_attn ? out_attn + (int64_t)step * B * e->Tp : nullptr;
@@ -1255,7 +1339,7 @@ int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* ou
   if (out_attn || out_logits || e->prof_mask || !e->use_graphs)
     return greedy_body(e, max_len, min_len, out_ids, out_scores, out_attn, out_logits, st);
   const int B = e->B;
-  const std::vector<int64_t> key = {0, B, e->T, e->Tp, max_len, min_len, 1, 1, 0, n_groups(e, B), g_pdl};
+  const std::vector<int64_t> key = {0, B, e->T, e->Tp, max_len, min_len, 1, 1, 0, n_groups(e, B), g_pdl, e->cross_mode};
   ND_TRY(run_cached(e, key, st, [&](cudaStream_t s2) {
     return greedy_body(e, max_len, min_len, e->o_ids, e->o_scores, nullptr, nullptr, s2);
   }));
@@ -1319,6 +1403,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
       e->join_ev.push_back(ev);
     }
     e->decode_streams = (int)value;
+    return ND_OK;
+  }
+  if (strcmp(name, "cross_mode") == 0) {     // 1: memory-bank-space cross attention for greedy decode, 0: K/V
+    e->cross_mode = value != 0;
     return ND_OK;
   }
   if (strcmp(name, "pdl") == 0) {            // programmatic dependent launch in the decode loop (process-wide)

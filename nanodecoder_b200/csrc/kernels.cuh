@@ -24,6 +24,24 @@ struct CrossAttnParams {
 };
 cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream);
 
+// Greedy-decode cross attention in MEMORY-BANK space (one query per chunk).  With K = mb Wk^T + bk and
+// V = mb Wv^T + bv (multi_headed_attn.py:142-153) the per-head score and context are, in exact arithmetic,
+//     q_h . K_h[t]   = mb[t] . qt_h + const_h        qt_h = Wk_h^T q_h / sqrt(dh)      (const_h cancels in softmax)
+//     sum_t a_h[t] V_h[t] = Wv_h (sum_t a_h[t] mb[t]) + bv_h                             (sum_t a_h[t] = 1)
+// so the kernel reads the memory bank ONCE (T*d*4 bytes per chunk instead of K and V, 2*T*d*4) and returns
+// ctxt[h] = sum_t a_h[t] mb[t]; the two d x d products move into the projections around it
+// (QT = LN2(x) P^T + pb with P_h = Wk_h^T Wq_h / sqrt(dh);  out = ctxt Mcat^T + mo with M_h = Wo_h Wv_h).
+struct CrossMbParams {
+  const float* qt = nullptr;                      // [n_chunks, H*d]
+  const float* mb = nullptr;                      // [n_chunks, T, d] memory bank
+  const float* src = nullptr; int64_t src_ld = 0; // key t masked iff src == mask_value (decoder/transformer.py:219-221)
+  float mask_value = 1.0f;
+  float* ctxt = nullptr;                          // [n_chunks, H*d]
+  int n_chunks = 0, T = 0, d = 0, H = 8;
+};
+bool cross_attention_mb_supported(int d, int H);
+cudaError_t cross_attention_mb(const CrossMbParams& p, cudaStream_t stream);
+
 // Decode-step self attention with a device-resident KV cache (decoder/transformer.py:76-80,
 // multi_headed_attn.py:126-141).  qkv holds this step's [q | k | v]; k and v are appended
 // to the cache at position `step`.  With beam search the history of row r at position j lives in

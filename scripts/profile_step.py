@@ -17,6 +17,8 @@ B = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 cfg = ModelConfig.family(family)
 sd = synth.make_state_dict(cfg)
 eng = Engine(cfg, sd, max_batch=B, max_src_len=512, max_tgt_len=100, max_beam=beam)
+if os.environ.get("ND_CROSS"):
+    eng.set_option("cross_mode", int(os.environ["ND_CROSS"]))
 if os.environ.get("ND_PDL"):
     eng.set_option("pdl", int(os.environ["ND_PDL"]))
 if os.environ.get("ND_STREAMS"):

@@ -74,6 +74,31 @@ def test_beam_matches_reference_golden(name):
     np.testing.assert_allclose(scores[:, 0], g["beam_scores"], atol=5e-3)
 
 
+@pytest.mark.parametrize("name", ["l2t_d256", "t2t_d64", "t2t_d512_6x6"])
+def test_cross_attention_formulations_agree(name):
+    """Greedy decode reads the memory bank once per layer-step (cross_mode 1, default: scores and context in
+    memory-bank space, K/V projections folded into the surrounding GEMMs); cross_mode 0 is the reference's
+    K/V formulation.  Both must reproduce the reference golden; the attention output path always uses K/V."""
+    g, cfg, sd, src, lengths = load_golden(name)
+    B, T, L = src.shape[0], src.shape[1], int(g["max_length"])
+    outs = {}
+    for mode in (1, 0):
+        eng = _engine(cfg, sd, B, T, L)
+        eng.set_option("cross_mode", mode)
+        eng.encode(src.cuda(), lengths.cuda())
+        o = eng.decode_greedy(L, return_logits=True)
+        torch.cuda.synchronize()
+        outs[mode] = (o["ids"].cpu(), o["logits"].cpu())
+        np.testing.assert_array_equal(outs[mode][0].numpy(), g["greedy_ids"])
+    e = rel_err(outs[1][1], outs[0][1])
+    print("%s: logits rel err between formulations %.2e" % (name, e))
+    assert e < 1e-4
+    eng = _engine(cfg, sd, B, T, L)
+    eng.encode(src.cuda(), lengths.cuda())
+    o = eng.decode_greedy(L, return_attn=True)
+    np.testing.assert_array_equal(o["ids"].cpu().numpy(), g["greedy_ids"])
+
+
 @pytest.mark.parametrize("name", IMPLEMENTED)
 def test_object_beam_matches_reference_golden(name):
     """nd_decode_beam_object vs the reference's _translate_batch + onmt.translate.Beam (no --fast), n_best 2."""
