@@ -1405,6 +1405,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     e->decode_streams = (int)value;
     return ND_OK;
   }
+  if (strcmp(name, "gemm_persistent") == 0) {   // process-wide: large-M GEMMs as a persistent kernel (default 1)
+    gemm_tc_set_persistent(value != 0);
+    return ND_OK;
+  }
   if (strcmp(name, "cross_mode") == 0) {     // 1: memory-bank-space cross attention for greedy decode, 0: K/V
     e->cross_mode = value != 0;
     return ND_OK;
@@ -1481,6 +1485,7 @@ int nd_test_gemm(nd_engine* e, int32_t mode, const float* A, const float* W, con
     ND_CUDA(e, cudaMemcpy(hi, h.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
     ND_CUDA(e, cudaMemcpy(lo, l.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
     p.W = hi; p.W_lo = lo;
+
   }
   ++e->launches;
   const bool prof = (e->prof_mask >> ND_PROF_GEMM) & 1u;

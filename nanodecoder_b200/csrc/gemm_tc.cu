@@ -570,6 +570,308 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------ persistent kernel
+// Same arithmetic and epilogue as gemm_tc_kernel<BN, NPASS, 1>, for the large-M projections of the encoder side
+// (input projections of the LSTM layers, memory K/V, Transformer encoder): one CTA per SM walks the tile list
+// (n fastest, so the CTAs running at any moment share their A rows in L2), the TMA / converter / MMA pipeline
+// never drains between tiles, and the accumulator is double buffered in tensor memory so that the epilogue of
+// tile i (4 dedicated warps) overlaps the main loop of tile i+1.  The one-tile-per-CTA kernel spends ~7 us per
+// tile outside the MMAs (launch, TMEM allocation, pipeline fill, epilogue); here only the MMA time remains.
+//   warps 0-7  converters (tf32 hi/lo split in place, LayerNorm row moments)
+//   warps 8-11 epilogue (tcgen05.ld -> bias / folded LayerNorm / ReLU -> smem transpose -> residual -> stores)
+//   warp 12    TMA producer        warp 13  TMEM owner + MMA issuer
+constexpr int kPEpiWarps = 4;
+constexpr int kPEpiThreads = kPEpiWarps * 32;
+constexpr int kPTmaWarp = kConvWarps + kPEpiWarps, kPMmaWarp = kPTmaWarp + 1;
+constexpr int kPThreads = (kPMmaWarp + 1) * 32;
+
+template <int BN, int NPASS>
+struct PCfg {
+  static constexpr int B_TILE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES * (NPASS == 3 ? 2 : 1) + B_TILE_BYTES * (NPASS == 3 ? 2 : 1);
+  static constexpr int STG_BYTES = kPEpiWarps * 32 * 36 * 4;
+  static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BM * 2 * 4 /*row stats x2*/ + 2 * 2 * BN * 4 /*vectors x2*/ +
+                                   2 * BM * 3 * 4 /*half-row moments*/;
+  static constexpr int kStagesFit = (222 * 1024 - STG_BYTES - AUX_BYTES - 1024) / STAGE_BYTES;
+  static constexpr int kStages = kStagesFit >= 6 ? 6 : kStagesFit;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + STG_BYTES + AUX_BYTES + 1024 /*align*/;
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static_assert(kStages >= 2, "pipeline needs two stages");
+};
+
+// Measured limits (profiles/r01_gemm_persistent.md): at 150 TFLOP/s fp32-equivalent the kernel moves 7 TB/s of
+// operand tiles from L2 and ~190 KB of shared-memory traffic per k-block (the three passes re-read the hi / lo tiles).
+// Fetching ONE fp32 weight tile and splitting it on chip like the activations was tried: a third less L2 traffic,
+// but the extra converter traffic on shared memory made it 15 % slower.
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kPThreads, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
+                       const __grid_constant__ CUtensorMap tmWlo, GemmParams p, int n_tiles) {
+  using C = PCfg<BN, NPASS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* stg_base = reinterpret_cast<float*>(smem + C::kStages * C::STAGE_BYTES);
+  uint8_t* aux = smem + C::kStages * C::STAGE_BYTES + C::STG_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* raw_full = bars;
+  uint64_t* conv_full = bars + C::kStages;
+  uint64_t* empty = bars + 2 * C::kStages;
+  uint64_t* acc_full = bars + 3 * C::kStages;          // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;                  // [2] epilogue -> MMA / converters (stats buffer)
+  uint64_t* stat_full = acc_empty + 2;                 // [2] converters -> epilogue (LayerNorm row moments)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 2);
+  float* s_stats = reinterpret_cast<float*>(aux + 256);        // [2][BM][2] (mean, M2)
+  float* s_vec = s_stats + 2 * BM * 2;                          // [2][2][BN]
+  float* s_mom = s_vec + 2 * 2 * BN;                            // [2][BM][3]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntn = (p.N + BN - 1) / BN;
+  const int KB = (p.K + BK - 1) / BK;
+  const bool fold = p.ln_cvec != nullptr;
+
+  auto a_hi = [&](int s) { return tiles + s * C::STAGE_BYTES; };
+  auto a_lo = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES; };
+  auto b_hi = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES * (NPASS == 3 ? 2 : 1); };
+  auto b_lo = [&](int s) { return b_hi(s) + C::B_TILE_BYTES; };
+
+  if (warp == kPTmaWarp && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&conv_full[s], kConvThreads);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kPEpiThreads);
+      mbar_init(&stat_full[b], BM);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWhi) : "memory");
+    if (NPASS == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
+  }
+  if (warp == kPMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kPTmaWarp) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % C::kStages;
+          mbar_wait(&empty[s], ((it / C::kStages) & 1) ^ 1);
+          mbar_expect_tx(&raw_full[s], A_TILE_BYTES + C::B_TILE_BYTES * (NPASS == 3 ? 2 : 1));
+          tma_load_2d(a_hi(s), &tmA, &raw_full[s], kb * BK, m0);
+          tma_load_2d(b_hi(s), &tmWhi, &raw_full[s], kb * BK, n0);
+          if (NPASS == 3) tma_load_2d(b_lo(s), &tmWlo, &raw_full[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == kPMmaWarp) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    uint32_t it = 0, j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const uint32_t buf = j & 1;
+      mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % C::kStages;
+        mbar_wait(&conv_full[s], (it / C::kStages) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t dah = make_desc(smem_u32(a_hi(s)));
+          const uint64_t dbh = make_desc(smem_u32(b_hi(s)));
+          const uint64_t dal = make_desc(smem_u32(a_lo(s)));
+          const uint64_t dbl = make_desc(smem_u32(b_lo(s)));
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+            if (NPASS == 3) {
+              umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, first);
+              umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+              umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+            } else {
+              umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, first);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (kb == KB - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < kConvWarps) {
+    // ===================================================================== converters
+    // thread = (row, half): half h converts 16-byte chunks [4h, 4h+4) of the row's 128-byte k-block slice
+    const int row = threadIdx.x & (BM - 1);
+    const int half = threadIdx.x >> 7;
+    const int sw = row & 7;
+    uint32_t it = 0, j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      float x0 = 0.f, s1 = 0.f, s2 = 0.f;
+      int cnt = 0;
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % C::kStages;
+        mbar_wait(&raw_full[s], (it / C::kStages) & 1);
+        if (NPASS == 3 || fold) {
+          uint8_t* rh = a_hi(s) + row * 128;
+          uint8_t* rl = a_lo(s) + row * 128;
+          float4 vin[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) vin[c] = *reinterpret_cast<float4*>(rh + (((4 * half + c) ^ sw) << 4));
+          if (fold && kb == 0) x0 = vin[0].x;     // shift = first element of THIS thread's share
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {           // logical 16-byte chunk lc lives at physical chunk lc ^ (row & 7)
+            const int lc = 4 * half + c;
+            const int pc = (lc ^ sw) << 4;
+            const float x[4] = {vin[c].x, vin[c].y, vin[c].z, vin[c].w};
+            const int kbase = kb * BK + lc * 4;
+            if (fold) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const bool in = kbase + q < p.K;
+                const float dlt = in ? x[q] - x0 : 0.f;
+                cnt += in ? 1 : 0;
+                s1 += dlt;
+                s2 = fmaf(dlt, dlt, s2);
+              }
+            }
+            if (NPASS == 3) {
+              float h[4], l[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                h[q] = __uint_as_float((__float_as_uint(x[q]) + 0x1000u) & 0xffffe000u);
+                l[q] = __uint_as_float((__float_as_uint(x[q] - h[q]) + 0x1000u) & 0xffffe000u);
+              }
+              *reinterpret_cast<float4*>(rh + pc) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(rl + pc) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+          }
+          if (NPASS == 3) fence_proxy_async();
+        }
+        mbar_arrive(&conv_full[s]);
+      }
+      if (fold) {
+        // (cnt, mean, M2) of this thread's half row; combine the halves (Chan et al.) and hand the row moments
+        // of this tile to the epilogue through the double-buffered stats array
+        float mean_h = 0.f, m2_h = 0.f;
+        if (cnt > 0) {
+          const float ds = s1 / (float)cnt;
+          mean_h = x0 + ds;
+          m2_h = fmaxf(s2 - s1 * ds, 0.f);
+        }
+        float* mo = s_mom + (half * BM + row) * 3;
+        mo[0] = (float)cnt; mo[1] = mean_h; mo[2] = m2_h;
+        asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+        if (half == 0) {
+          const float* a = s_mom + row * 3;
+          const float* b = s_mom + (BM + row) * 3;
+          const float na = a[0], nb = b[0], nt = na + nb;
+          float mean_s = 0.f, m2_s = 0.f;
+          if (nt > 0.f) {
+            const float delta = b[1] - a[1];
+            mean_s = a[1] + delta * (nb / nt);
+            m2_s = a[2] + b[2] + delta * delta * (na * nb / nt);
+          }
+          const uint32_t buf = j & 1;
+          mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);      // the epilogue two tiles back has read its moments
+          s_stats[(buf * BM + row) * 2] = mean_s;
+          s_stats[(buf * BM + row) * 2 + 1] = m2_s;
+          mbar_arrive(&stat_full[buf]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 8-11)
+    const int lg = warp - kConvWarps;                 // == warp % 4: the TMEM lane quadrant this warp may read
+    const int et = threadIdx.x - kConvThreads;        // 0..127
+    const uint32_t lane_base = (uint32_t)(lg * 32) << 16;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        (!p.residual || (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)));
+    float* stg = stg_base + lg * (32 * 36);
+    const int rsub = lane >> 3, cq = lane & 7;
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+      const uint32_t buf = j & 1;
+      const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+      const int m = m0 + lg * 32 + lane;
+      float* v0 = s_vec + (buf * 2) * BN;
+      float* v1 = v0 + BN;
+      for (int i = et; i < BN; i += kPEpiThreads) {
+        const int n = n0 + i;
+        v0[i] = n < p.N ? (fold ? p.ln_cvec[n] : (p.bias ? p.bias[n] : 0.f)) : 0.f;
+        v1[i] = (fold && n < p.N) ? p.ln_dvec[n] : 0.f;
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kPEpiThreads) : "memory");
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (fold) {
+        mbar_wait(&stat_full[buf], (j >> 1) & 1);
+        ln_mean = s_stats[(buf * BM + lg * 32 + lane) * 2];
+        ln_rstd = 1.0f / sqrtf(s_stats[(buf * BM + lg * 32 + lane) * 2 + 1] / (float)p.K + p.eps);
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int nb = n0 + c0;
+        float v[32];
+        tmem_ld32(tmem_base + lane_base + buf * BN + (uint32_t)c0, v);
+        if (vec_ok && nb + 32 <= p.N) {
+          float4 res[8];
+          if (p.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int mm = m0 + lg * 32 + 4 * i + rsub;
+              res[i] = mm < p.M ? *reinterpret_cast<const float4*>(p.residual + (int64_t)mm * p.ldr + nb + cq * 4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          epilogue_rowwise<32>(p, v, c0, fold, ln_mean, ln_rstd, v0, v1);
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4)
+            *reinterpret_cast<float4*>(stg + lane * 36 + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rsub;
+            const int mm = m0 + lg * 32 + r;
+            float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
+            if (p.residual) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+            if (mm < p.M) *reinterpret_cast<float4*>(p.C + (int64_t)mm * p.ldc + nb + cq * 4) = o;
+          }
+          __syncwarp();
+        } else if (m < p.M && nb < p.N) {
+          epilogue_store_slow<32>(p, v, m, nb, fold, ln_mean, ln_rstd);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);                   // accumulator (and its stats / vectors) may be reused
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kPMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS));
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
 long long* g_dbg = nullptr;
 PFN_cuTensorMapEncodeTiled g_encode = nullptr;
@@ -636,6 +938,34 @@ cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
   return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NPASS, S>, tmA, tmWhi, tmWlo, pp);
 }
 
+int g_persist = 1;       // 0: always one tile per CTA (experiments / cross-check)
+int g_n_sm = 0;
+
+template <int BN, int NPASS>
+cudaError_t launch_persist(const GemmParams& p, cudaStream_t stream) {
+  using C = PCfg<BN, NPASS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (g_n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  CUtensorMap tmA, tmWhi, tmWlo;
+  if (!make_map(&tmA, p.A, p.M, p.K, p.lda, BM)) return cudaErrorInvalidValue;
+  if (!make_map(&tmWhi, p.W, p.N, p.K, p.ldw, BN)) return cudaErrorInvalidValue;
+  if (!make_map(&tmWlo, NPASS == 3 ? p.W_lo : p.W, p.N, p.K, p.ldw, BN)) return cudaErrorInvalidValue;
+  const int64_t tiles = (int64_t)cdiv(p.N, BN) * cdiv(p.M, BM);
+  const int grid = (int)(tiles < g_n_sm ? tiles : g_n_sm);
+  gemm_tc_persist_kernel<BN, NPASS><<<grid, kPThreads, C::SMEM_BYTES, stream>>>(tmA, tmWhi, tmWlo, p, (int)tiles);
+  return cudaGetLastError();
+}
+
 template <int NPASS>
 cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
   // Tile width follows the amount of work (wide tiles for the encoder-side GEMMs).  The split-K factor
@@ -649,6 +979,8 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
     const int ref_tiles = 8 * cdiv(p.N, 64);           // 64-wide tiles of a 1024-row problem
     while (split < 4 && KB % (split * 2) == 0 && KB / (split * 2) >= 2 && ref_tiles * split * 2 <= 160) split *= 2;
   }
+  // many tiles per SM: the persistent kernel (pipeline never drains, epilogue overlapped)
+  if (g_persist && split == 1 && p.N > 64 && tiles128 >= 4 * 148) return launch_persist<128, NPASS>(p, stream);
   if (split == 1 && tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
   switch (split) {
     case 4: return launch<64, NPASS, 4>(p, stream);
@@ -660,6 +992,7 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
 }  // namespace
 
 void gemm_tc_set_debug(long long* dev_buf) { g_dbg = dev_buf; }
+void gemm_tc_set_persistent(int on) { g_persist = on; }
 
 bool gemm_tc_available(const char** why) {
   const bool ok = lookup();

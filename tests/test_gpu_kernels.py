@@ -34,6 +34,34 @@ def test_gemm_plain(small_engine, mode, tol, M, N, K):
     assert rel_err(C, ref) < tol, (mode, M, N, K, rel_err(C, ref))
 
 
+@pytest.mark.parametrize("mode,tol", [("3xtf32", 1e-5), ("tf32", 3e-3)])
+@pytest.mark.parametrize("M,N,K,ln", [(20000, 1024, 256, False), (19999, 520, 96, True), (40000, 256, 512, True),
+                                      (16384, 2048, 256, True)])
+def test_gemm_persistent_kernel(small_engine, mode, tol, M, N, K, ln):
+    """Large tile counts run as the persistent kernel (double-buffered TMEM accumulator, dedicated epilogue warps):
+    ragged M and N, LayerNorm folding, ReLU and residual must match the one-tile-per-CTA kernel and fp64."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 1.5 + 0.25).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    gam = (1 + 0.1 * torch.randn(K, generator=g)).cuda()
+    bet = (0.1 * torch.randn(K, generator=g)).cuda()
+    kw = dict(bias=bias, residual=res, ln=(gam, bet) if ln else None, relu=1 if ln else 0)
+    C = small_engine.test_gemm(mode, A, W, **kw)
+    small_engine.set_option("gemm_persistent", 0)
+    try:
+        C1 = small_engine.test_gemm(mode, A, W, **kw)
+    finally:
+        small_engine.set_option("gemm_persistent", 1)
+    torch.cuda.synchronize()
+    An = torch.nn.functional.layer_norm(A.double(), (K,), gam.double(), bet.double(), 1e-6) if ln else A.double()
+    ref = An @ W.double().t() + bias.double()
+    ref = (torch.relu(ref) if ln else ref) + res.double()
+    assert rel_err(C, ref) < tol, rel_err(C, ref)
+    assert rel_err(C, C1.double()) < (5e-6 if mode == "3xtf32" else 1e-5)   # LayerNorm moments are grouped differently
+
+
 @pytest.mark.parametrize("mode,tol", [("simt", 3e-6), ("3xtf32", 1e-5), ("tf32", 3e-3)])
 def test_gemm_layernorm_relu_residual(small_engine, mode, tol):
     g = torch.Generator().manual_seed(5)
