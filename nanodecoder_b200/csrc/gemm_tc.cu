@@ -980,7 +980,7 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
     while (split < 4 && KB % (split * 2) == 0 && KB / (split * 2) >= 2 && ref_tiles * split * 2 <= 160) split *= 2;
   }
   // many tiles per SM: the persistent kernel (pipeline never drains, epilogue overlapped)
-  if (g_persist && split == 1 && p.N > 64 && tiles128 >= 4 * 148) return launch_persist<128, NPASS>(p, stream);
+  if (g_persist && split == 1 && p.N > 64 && tiles128 >= 200) return launch_persist<128, NPASS>(p, stream);
   if (split == 1 && tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
   switch (split) {
     case 4: return launch<64, NPASS, 4>(p, stream);
