@@ -265,3 +265,30 @@ def test_translator_api_drop_in(tmp_path):
         o = od.greedy(om, chunks[i:i + 1, :n].t().contiguous().unsqueeze(2), lengths[i:i + 1], max_length=20)
         want = " ".join(od.build_target_tokens(o["predictions"][0], cfg.vocab))
         assert preds[i][0] == want, (i, preds[i][0], want)
+
+
+@pytest.mark.parametrize("beam,fast", [(1, False), (4, True), (4, False)])
+def test_translate_host_paths_agree(beam, fast):
+    """Translator.translate builds its strings with array ops; the reference-shaped path
+    (translate_batch -> TranslationBuilder.from_batch, translation.py:31-105) must give the same strings."""
+    from nanodecoder_b200.checkpoint import Vocab
+    from nanodecoder_b200.engine import Engine
+    from nanodecoder_b200.opts import default_translate_opt
+    from nanodecoder_b200.translate.translation import TranslationBuilder
+    from nanodecoder_b200.translate.translator import Translator, _Batch, _Data, _Field
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    sd = synth.make_state_dict(cfg, seed=3)
+    NB = 1 if beam == 1 else 2
+    opt = default_translate_opt(beam_size=beam, n_best=NB, batch_size=16, max_length=30, src_seq_length=128, gpu=0, fast=fast)
+    eng = Engine(cfg, sd, max_batch=16, max_src_len=128, max_tgt_len=30, max_beam=beam)
+    tr = Translator(eng, {"tgt": _Field(Vocab(cfg.vocab))}, opt, cfg)
+    chunks, lengths = synth.make_chunks(16, T=128, seed=4, ragged=True, read_len=4)
+    scores, preds = tr.translate(src=(chunks, lengths), batch_size=16)
+    order = torch.argsort(lengths, descending=True, stable=True)
+    batch = _Batch(chunks[order].t().contiguous().unsqueeze(2).cuda(), lengths[order].cuda(), torch.arange(16))
+    res = tr.translate_batch(batch, _Data(), False, fast=fast)
+    trans = TranslationBuilder(_Data(), tr.fields, NB).from_batch(res)
+    for j, t in enumerate(trans):
+        i = int(order[j])
+        assert preds[i] == [" ".join(p) for p in t.pred_sents[:NB]]
+        assert [float(x) for x in scores[i]] == [float(x) for x in t.pred_scores[:NB]]
