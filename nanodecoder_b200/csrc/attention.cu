@@ -38,8 +38,13 @@ __device__ __forceinline__ void load_slice(const float* p, float (&v)[VPL]) {
 //   phase 2: softmax over t per (q, h)                                   (warp per row)
 //   phase 3: ctx[q] = sum_t p[q][h][t] * V[t]                            (register accumulators)
 // K and V are each read exactly once per chunk per step: 2*T*d*4 bytes — the roofline of the decode.
+// rows of K / V a warp keeps in flight per iteration: 4 x VPL floats per lane; at VPL = 16 (d = 512) that costs 93
+// registers and two CTAs per SM, measured 4.4 TB/s -- two rows and three CTAs per SM there
+template <int VPL> struct CrossRows { static constexpr int R = VPL >= 16 ? 2 : 4; static constexpr int MINB = VPL >= 16 ? 3 : 1; };
+
 template <int VPL, int NQMAX>
-__global__ void __launch_bounds__(kAttnThreads) cross_attn_kernel(CrossAttnParams p) {
+__global__ void __launch_bounds__(kAttnThreads, (NQMAX == 1 ? CrossRows<VPL>::MINB : 1)) cross_attn_kernel(CrossAttnParams p) {
+  constexpr int R = NQMAX == 1 ? CrossRows<VPL>::R : 4;
   extern __shared__ __align__(16) float smem_f[];
   const int chunk = blockIdx.x;
   pdl_launch_dependents();
@@ -64,13 +69,13 @@ __global__ void __launch_bounds__(kAttnThreads) cross_attn_kernel(CrossAttnParam
   const int head = lane / LPH;
 
   // ---------------- phase 1
-  for (int t0 = warp * 4; t0 < T; t0 += kAttnWarps * 4) {
-    float kv[4][VPL];
+  for (int t0 = warp * R; t0 < T; t0 += kAttnWarps * R) {
+    float kv[R][VPL];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
       if (t0 + r < T) load_slice<VPL>(Kb + (int64_t)(t0 + r) * p.kv_ld, kv[r]);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
       const int t = t0 + r;
       if (t < T) {                                 // warp-uniform
         const bool masked = srow && (srow[t] == p.mask_value);
@@ -113,13 +118,13 @@ __global__ void __launch_bounds__(kAttnThreads) cross_attn_kernel(CrossAttnParam
   for (int qi = 0; qi < NQMAX; ++qi)
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[qi][i] = 0.f;
-  for (int t0 = warp * 4; t0 < T; t0 += kAttnWarps * 4) {
-    float vv[4][VPL];
+  for (int t0 = warp * R; t0 < T; t0 += kAttnWarps * R) {
+    float vv[R][VPL];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
       if (t0 + r < T) load_slice<VPL>(Vb + (int64_t)(t0 + r) * p.kv_ld, vv[r]);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
       const int t = t0 + r;
       if (t < T) {
 #pragma unroll

@@ -14,7 +14,8 @@ from nanodecoder_b200.engine import Engine
 family = sys.argv[1] if len(sys.argv) > 1 else "l2t"
 beam = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
-cfg = ModelConfig.family(family)
+kw = eval(os.environ["ND_KW"]) if os.environ.get("ND_KW") else {}     # e.g. ND_KW="dict(d_model=512,enc_layers=6,dec_layers=6)"
+cfg = ModelConfig.family(family, **kw)
 sd = synth.make_state_dict(cfg)
 eng = Engine(cfg, sd, max_batch=B, max_src_len=512, max_tgt_len=100, max_beam=beam)
 if os.environ.get("ND_CROSS"):
