@@ -367,15 +367,212 @@ __global__ void __launch_bounds__(256) cross_attn_mb_kernel(CrossMbParams p, int
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2 for d = 256, H = 8: register-resident query and accumulators, packed fp32 FMAs (FFMA2).
+//   lane  = column slice [8 lane, 8 lane + 8)      warp w = positions 4w .. 4w+3 of every 32-position tile
+//   qt[8 heads][8 cols] and acc[8][8] live in registers for the whole chunk; the 4 x 8 tile values a thread
+//   loads (two LDS.128 per row, conflict free) feed both the scores and the context, so each memory-bank
+//   element crosses shared memory once.  Per tile: 256 FFMA2 per thread, one 32-value butterfly reduce-scatter
+//   (lane L ends with the score of position L>>3, head L&7), ONE CTA barrier; every warp recomputes the
+//   per-head running max / sum of the online softmax from the 8 x 32 score tile in shared memory.
+constexpr int kMb2D = 256, kMb2H = 8;
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+__global__ void __launch_bounds__(256, 1) cross_attn_mb2_kernel(CrossMbParams p, int nst) {
+  extern __shared__ __align__(16) float smem_f[];
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int D = kMb2D, H = kMb2H;
+  const int chunk = blockIdx.x, T = p.T;
+  const int tile_f = kMbTT * D;
+  float* tiles = smem_f;                              // [nst][32][256]
+  float* sbuf = tiles + (size_t)nst * tile_f;         // [2][H][32] scores of the current / next tile
+  float* l_s = sbuf + 2 * H * kMbTT;                  // [H] 1 / softmax sum
+  uint64_t* full = reinterpret_cast<uint64_t*>(l_s + H);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (T + kMbTT - 1) / kMbTT;
+  const float* mb = p.mb + (int64_t)chunk * T * D;
+  const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
+
+  if (tid == 0) {
+    for (int s = 0; s < nst; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue_tile = [&](int i) {                      // one thread: rows*1 KB contiguous bytes of the memory bank
+    const int s = i % nst;
+    const uint32_t bytes = (uint32_t)(min(kMbTT, T - i * kMbTT) * D * 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&full[s])), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr_u32(tiles + (size_t)s * tile_f)),
+                 "l"(mb + (int64_t)i * kMbTT * D), "r"(bytes), "r"(smem_addr_u32(&full[s]))
+                 : "memory");
+  };
+  if (tid == 0)
+    for (int i = 0; i < nst && i < ntiles; ++i) issue_tile(i);
+
+  // query (already projected into memory-bank space) of this thread's 8 columns, all heads
+  float2 qt[H][4], acc[H][4];
+  {
+    const float* q = p.qt + (int64_t)chunk * H * D + 8 * lane;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const float4 a = *reinterpret_cast<const float4*>(q + h * D), b = *reinterpret_cast<const float4*>(q + h * D + 4);
+      qt[h][0] = make_float2(a.x, a.y); qt[h][1] = make_float2(a.z, a.w);
+      qt[h][2] = make_float2(b.x, b.y); qt[h][3] = make_float2(b.z, b.w);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[h][c] = make_float2(0.f, 0.f);
+    }
+  }
+  const int hh = lane & 7, rq = lane >> 3;            // this lane's (head, position-in-warp / row quarter) after the reduce-scatter
+  float m_run = -INFINITY, l_run = 0.f;               // running max / sum of head hh (replicated in every warp)
+
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i % nst, buf = i & 1;
+    const float* tile = tiles + (size_t)s * tile_f;
+    const int rows = min(kMbTT, T - i * kMbTT);
+    // mask of this lane's position (prefetched before the wait)
+    const int t_own = i * kMbTT + 4 * warp + rq;
+    const float src_own = (srow && t_own < T) ? srow[t_own] : 0.f;
+    {
+      const uint32_t parity = (uint32_t)((i / nst) & 1);
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra DONE_%=;\n"
+          "bra WAIT_%=;\n"
+          "DONE_%=:\n"
+          "}\n" ::"r"(smem_addr_u32(&full[s])),
+          "r"(parity)
+          : "memory");
+    }
+    // ---- this thread's 4 positions x 8 columns (zero beyond the end of the chunk)
+    float2 mv[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = 4 * warp + r;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (row < rows) {
+        a = *reinterpret_cast<const float4*>(tile + row * D + 8 * lane);
+        b = *reinterpret_cast<const float4*>(tile + row * D + 8 * lane + 4);
+      }
+      mv[r][0] = make_float2(a.x, a.y); mv[r][1] = make_float2(a.z, a.w);
+      mv[r][2] = make_float2(b.x, b.y); mv[r][3] = make_float2(b.z, b.w);
+    }
+    // ---- partial scores of (position r, head h) over this lane's columns
+    float v[32];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a2 = ffma2(mv[r][c], qt[h][c], a2);
+        v[r * 8 + h] = a2.x + a2.y;
+      }
+    // ---- butterfly reduce-scatter over the 32 lanes: lane L ends with the full sum of value L
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int k = 0; k < off; ++k) {
+        const float keep = up ? v[k + off] : v[k];
+        const float send = up ? v[k] : v[k + off];
+        v[k] = keep + __shfl_xor_sync(ND_FULL, send, off);
+      }
+    }
+    float sc = v[0];                                  // position 4 warp + rq, head hh
+    if (t_own >= T) sc = -INFINITY;
+    else if (srow && src_own == p.mask_value) sc = -1e18f;          // masked_fill(mask, -1e18)
+    sbuf[(buf * H + hh) * kMbTT + 4 * warp + rq] = sc;
+    __syncthreads();                                  // scores of the tile complete; stage s fully read
+    if (tid == 0 && i + nst < ntiles) issue_tile(i + nst);
+    // ---- online softmax of head hh (every warp, redundantly): lanes (hh, rq) cover positions 8 rq .. 8 rq + 7
+    float pr_own;
+    {
+      const float4 s0 = *reinterpret_cast<const float4*>(sbuf + (buf * H + hh) * kMbTT + 8 * rq);
+      const float4 s1 = *reinterpret_cast<const float4*>(sbuf + (buf * H + hh) * kMbTT + 8 * rq + 4);
+      float tm = fmaxf(fmaxf(fmaxf(s0.x, s0.y), fmaxf(s0.z, s0.w)), fmaxf(fmaxf(s1.x, s1.y), fmaxf(s1.z, s1.w)));
+      tm = fmaxf(tm, __shfl_xor_sync(ND_FULL, tm, 8));
+      tm = fmaxf(tm, __shfl_xor_sync(ND_FULL, tm, 16));
+      const float m_new = fmaxf(m_run, tm);
+      float ts = expf(s0.x - m_new) + expf(s0.y - m_new) + expf(s0.z - m_new) + expf(s0.w - m_new) +
+                 expf(s1.x - m_new) + expf(s1.y - m_new) + expf(s1.z - m_new) + expf(s1.w - m_new);
+      ts += __shfl_xor_sync(ND_FULL, ts, 8);
+      ts += __shfl_xor_sync(ND_FULL, ts, 16);
+      const float al = expf(m_run - m_new);           // 0 on the first tile
+      l_run = l_run * al + ts;
+      m_run = m_new;
+      pr_own = expf(sc - m_new);
+      // rescale the accumulators when a running max moved (rare after the first tiles)
+      if (__any_sync(ND_FULL, al != 1.0f)) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float a = __shfl_sync(ND_FULL, al, h);
+          const float2 a2 = make_float2(a, a);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[h][c] = make_float2(acc[h][c].x * a2.x, acc[h][c].y * a2.y);
+        }
+      }
+    }
+    // ---- context: acc[h][cols] += p[position r][h] * mb[position r][cols]
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float pw = __shfl_sync(ND_FULL, pr_own, r * 8 + h);
+        const float2 p2 = make_float2(pw, pw);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[h][c] = ffma2(p2, mv[r][c], acc[h][c]);
+      }
+  }
+
+  // ---- combine the 8 warps (each saw a quarter... an eighth of the positions), normalise, write ctxt[h][col]
+  if (warp == 0 && lane < H) l_s[lane] = 1.0f / l_run;           // lane = hh for lanes 0..7
+  __syncthreads();                                    // every warp is done with the tiles
+  float* red = tiles;                                 // [8 warps][H][256] = 64 KB
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    float* o = red + ((size_t)warp * H + h) * D + 8 * lane;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[h][0].x, acc[h][0].y, acc[h][1].x, acc[h][1].y);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[h][2].x, acc[h][2].y, acc[h][3].x, acc[h][3].y);
+  }
+  __syncthreads();
+  float* out = p.ctxt + (int64_t)chunk * H * D;
+  for (int i = tid; i < H * D; i += 256) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[(size_t)w * H * D + i];
+    out[i] = sum * l_s[i / D];
+  }
+}
+
 }  // namespace
 
 bool cross_attention_mb_supported(int d, int H) {
   return H == 8 && (d == 32 || d == 64 || d == 128 || d == 256 || d == 512 || d == 1024);
 }
 
+int g_cross_mb_version = 2;        // 2: register-resident v2 when d = 256; 1: always the generic v1 (experiments)
+void cross_attention_mb_set_version(int v) { g_cross_mb_version = v; }
+
 cudaError_t cross_attention_mb(const CrossMbParams& p, cudaStream_t stream) {
   if (p.n_chunks <= 0) return cudaSuccess;
   if (!cross_attention_mb_supported(p.d, p.H)) return cudaErrorInvalidValue;
+  if (g_cross_mb_version == 2 && p.d == kMb2D && p.H == kMb2H) {
+    const int nst = 5;                                 // 5 x 32 KB tiles in flight per SM (one CTA per SM)
+    const size_t smem = (size_t)nst * kMbTT * kMb2D * 4 + (2 * kMb2H * kMbTT + kMb2H) * 4 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(cross_attn_mb2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    return launch_k(cross_attn_mb2_kernel, dim3(p.n_chunks), dim3(256), smem, stream, p, nst);
+  }
   constexpr int H = 8;
   const size_t tile_b = (size_t)kMbTT * p.d * sizeof(float);
   const size_t fixed = ((size_t)H * p.d + 8 * H * kMbTT + kMbTT * H + H) * sizeof(float) + 64;

@@ -125,7 +125,7 @@ struct nd_engine {
         *ffh = nullptr, *logp = nullptr, *gscore = nullptr;
   float *qt = nullptr, *cctxt = nullptr;   // [maxB, H*d] memory-bank-space cross attention (greedy)
   // 0 (default): K/V cross attention, HBM-bound at 96 % of the measured peak.  1: greedy decode reads the memory
-  // bank once per layer-step (half the bytes, 8x the fp32 FMAs): measured 291 us vs 171 us per launch at d = 256
+  // bank once per layer-step (half the bytes, 8x the fp32 FMAs): measured 253 us (v2) vs 171 us per launch at d = 256
   // (profiles/r01_cross_mb_experiment.md) -- kept as an option until its FFMA side is as good as its byte count
   int cross_mode = 0;
   int* cur_tok = nullptr;
@@ -1411,6 +1411,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
   }
   if (strcmp(name, "cross_mode") == 0) {     // 1: memory-bank-space cross attention for greedy decode, 0: K/V
     e->cross_mode = value != 0;
+    return ND_OK;
+  }
+  if (strcmp(name, "cross_mb_version") == 0) {
+    cross_attention_mb_set_version((int)value);
     return ND_OK;
   }
   if (strcmp(name, "pdl") == 0) {            // programmatic dependent launch in the decode loop (process-wide)

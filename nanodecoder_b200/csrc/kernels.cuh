@@ -41,6 +41,7 @@ struct CrossMbParams {
 };
 bool cross_attention_mb_supported(int d, int H);
 cudaError_t cross_attention_mb(const CrossMbParams& p, cudaStream_t stream);
+void cross_attention_mb_set_version(int v);
 
 // Decode-step self attention with a device-resident KV cache (decoder/transformer.py:76-80,
 // multi_headed_attn.py:126-141).  qkv holds this step's [q | k | v]; k and v are appended
