@@ -38,13 +38,12 @@ __device__ __forceinline__ void load_slice(const float* p, float (&v)[VPL]) {
 //   phase 2: softmax over t per (q, h)                                   (warp per row)
 //   phase 3: ctx[q] = sum_t p[q][h][t] * V[t]                            (register accumulators)
 // K and V are each read exactly once per chunk per step: 2*T*d*4 bytes — the roofline of the decode.
-// rows of K / V a warp keeps in flight per iteration: 4 x VPL floats per lane; at VPL = 16 (d = 512) that costs 93
-// registers and two CTAs per SM, measured 4.4 TB/s -- two rows and three CTAs per SM there
-template <int VPL> struct CrossRows { static constexpr int R = VPL >= 16 ? 2 : 4; static constexpr int MINB = VPL >= 16 ? 3 : 1; };
-
 template <int VPL, int NQMAX>
-__global__ void __launch_bounds__(kAttnThreads, (NQMAX == 1 ? CrossRows<VPL>::MINB : 1)) cross_attn_kernel(CrossAttnParams p) {
-  constexpr int R = NQMAX == 1 ? CrossRows<VPL>::R : 4;
+__global__ void __launch_bounds__(kAttnThreads) cross_attn_kernel(CrossAttnParams p) {
+  // four rows of K / V in flight per warp iteration.  (Two rows and a minimum-blocks launch bound were tried for
+  // d = 512: 485 -> 469 us there, but any second __launch_bounds__ argument changes the register allocation of the
+  // d = 256 instance (64 -> 80/86 registers, 171 -> 177/214 us), so the plain form stays.)
+  constexpr int R = 4;
   extern __shared__ __align__(16) float smem_f[];
   const int chunk = blockIdx.x;
   pdl_launch_dependents();

@@ -128,6 +128,7 @@ struct nd_engine {
   // bank once per layer-step (half the bytes, 8x the fp32 FMAs): measured 253 us (v2) vs 171 us per launch at d = 256
   // (profiles/r01_cross_mb_experiment.md) -- kept as an option until its FFMA side is as good as its byte count
   int cross_mode = 0;
+  int enc_attn_tc = 1;                     // Transformer-encoder self attention on the tensor cores when dh = 32
   int* cur_tok = nullptr;
   // rnn decoder
   float* uh = nullptr;               // [B, T', d]
@@ -767,7 +768,10 @@ int encode_transformer(nd_engine* e, cudaStream_t st) {
     GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln.g; o1.pb = L.ln.b;
     ND_TRY(run_gemm(e, L.qkv, x, d, e->big, 3 * d, M, o1, st));
     EncAttnParams a; a.qkv = e->big; a.q_div = sq; a.src = e->src; a.ctx = ctx; a.B = B; a.T = T; a.d = d; a.H = c.heads;
-    ND_LAUNCH_CAT(e, ND_PROF_ENC_ATTN, st, encoder_attention(a, st));
+    if (tc_mode(e) && e->enc_attn_tc && encoder_attention_tc_supported(a))
+      ND_LAUNCH_CAT(e, ND_PROF_ENC_ATTN, st, encoder_attention_tc(a, st));
+    else
+      ND_LAUNCH_CAT(e, ND_PROF_ENC_ATTN, st, encoder_attention(a, st));
     GemmOpt o2; o2.residual = x; o2.ldr = d;
     ND_TRY(run_gemm(e, L.out, ctx, d, x1, d, M, o2, st));
     GemmOpt o3; o3.prologue = PRO_LAYERNORM; o3.pg = L.ln_ff.g; o3.pb = L.ln_ff.b; o3.act = 1;
@@ -1411,6 +1415,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
   }
   if (strcmp(name, "cross_mode") == 0) {     // 1: memory-bank-space cross attention for greedy decode, 0: K/V
     e->cross_mode = value != 0;
+    return ND_OK;
+  }
+  if (strcmp(name, "enc_attn_tc") == 0) {
+    e->enc_attn_tc = value != 0;
     return ND_OK;
   }
   if (strcmp(name, "cross_mb_version") == 0) {

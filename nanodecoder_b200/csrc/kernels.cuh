@@ -68,7 +68,9 @@ struct EncAttnParams {
   float* ctx = nullptr;                           // [B*T, d]
   int B = 0, T = 0, d = 0, H = 8;
 };
-cudaError_t encoder_attention(const EncAttnParams& p, cudaStream_t stream);
+cudaError_t encoder_attention(const EncAttnParams& p, cudaStream_t stream);        // fp32 FFMA, one query per thread
+bool encoder_attention_tc_supported(const EncAttnParams& p);                        // head size 32, T <= 512
+cudaError_t encoder_attention_tc(const EncAttnParams& p, cudaStream_t stream);     // tcgen05, fp16 two-term split
 
 // Bahdanau / "mlp" global attention, one decode step (onmt/modules/global_attention.py:123-136,
 // 180-194): score = v . tanh(wq + uh[t]); length mask; softmax; context = sum_t a[t] * mem[t].
