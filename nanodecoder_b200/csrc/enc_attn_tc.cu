@@ -29,7 +29,7 @@ constexpr int KOP_BYTES = TMAX * 128;                          // key rows [K_hi
 constexpr int VKB_BYTES = 64 * 128;                            // one 64-key k-block: [V_hi: 32 rows][V_lo: 32 rows] x 128 B
 constexpr int VOP_BYTES = (TMAX / 64) * VKB_BYTES;
 constexpr int QOP_BYTES = 2 * TQ * 128;                        // A1 = [Q_hi | Q_hi], A2 = [Q_lo | 0]
-constexpr int SMEM_BYTES = KOP_BYTES + VOP_BYTES + QOP_BYTES + TMAX * 4 /*flags*/ + 2 * TQ * 4 /*max exchange*/ + 128 + 1024;
+constexpr int SMEM_BYTES = KOP_BYTES + VOP_BYTES + QOP_BYTES + TMAX * 4 /*flags*/ + 6 * TQ * 4 /*max (x2) and sum exchange*/ + 128 + 1024;
 // tensor memory columns
 constexpr uint32_t kColS = 0, kColPhi = 128, kColPlo = 192, kColO = 256, kTmemCols = 512;
 
@@ -124,10 +124,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 // x = hi + lo in fp16; element 0 in the low half of the packed word
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-  const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-  hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-  lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  const __half2 h = __floats2half2_rn(x0, x1);                 // one packed conversion per pair
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_tc_kernel(EncAttnParams 
   uint8_t* vop = kop + KOP_BYTES;                        // [8 k-blocks][64 rows][128 B]
   uint8_t* qop = vop + VOP_BYTES;                        // A1, A2: [128 rows][128 B] each
   float* kflag = reinterpret_cast<float*>(qop + QOP_BYTES);        // [TMAX] 0 valid, 1 masked, 2 beyond T
-  float* mx = kflag + TMAX;                              // [2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mx + 2 * TQ);
+  float* mx = kflag + TMAX;                              // [2 parities][2 halves][128 rows] max, then [2][128] sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mx + 6 * TQ);
   uint64_t* go = bars;                                   // softmax warps -> MMA: Q operand ready / O_j consumed
   uint64_t* s_full = bars + 1;
   uint64_t* p_full = bars + 2;
@@ -307,9 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_tc_kernel(EncAttnParams 
           s[i + 3] = f.w == 0.f ? s[i + 3] : (f.w == 1.f ? -1e18f : -INFINITY);
           mloc = fmaxf(fmaxf(mloc, fmaxf(s[i], s[i + 1])), fmaxf(s[i + 2], s[i + 3]));
         }
-        mx[hf * TQ + row] = mloc;
+        float* mxb = mx + (it & 1) * 2 * TQ;               // double buffered by block parity: one barrier per block
+        mxb[hf * TQ + row] = mloc;
         asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");
-        const float m_j = fmaxf(mloc, mx[(hf ^ 1) * TQ + row]);            // block max of the row (finite: key 0 exists)
+        const float m_j = fmaxf(mloc, mxb[(hf ^ 1) * TQ + row]);           // block max of the row (finite: a key exists)
         // ---- P = exp(S - m_j) in (0, 1], fp16 hi / lo, packed pairs -> tensor memory (A operand of P.V)
         float lsum = 0.f;
         uint32_t phi[32], plo[32];
@@ -324,18 +326,13 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_tc_kernel(EncAttnParams 
         tmem_st32(tmem_base + lane_base + kColPhi + 32 * hf, phi);
         tmem_st32(tmem_base + lane_base + kColPlo + 32 * hf, plo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        // the two halves of a row need each other's sum: exchange through shared memory (second slot set)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(p_full);
-        asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");     // everyone has read mx: reuse it for the sums
-        mx[hf * TQ + row] = lsum;
-        asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");
-        const float l_j = lsum + mx[(hf ^ 1) * TQ + row];
-        // ---- fold block j into the running state
+        // ---- fold block j into the running state (l_run: this thread's HALF of the keys; halves meet at the end)
         const float m_new = fmaxf(m_run, m_j);
         const float a_old = ex2_approx((m_run - m_new) * kLog2e);          // 0 on the first block
         const float a_blk = ex2_approx((m_j - m_new) * kLog2e);
-        l_run = l_run * a_old + l_j * a_blk;
+        l_run = l_run * a_old + lsum * a_blk;
         m_run = m_new;
         mbar_wait(o_full, it & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -347,9 +344,14 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_tc_kernel(EncAttnParams 
           for (int i = 0; i < 16; ++i) o_run[i] = o_run[i] * a_old + (oa[i] + ob[i]) * a_blk;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");     // sums read by everyone before mx is rewritten
         if (j + 1 < nkb) mbar_arrive(go);                  // S, P and O of this block are consumed
       }
+      // the two halves of a row share m_run; their partial sums meet once per tile
+      float* lx = mx + 4 * TQ;
+      lx[hf * TQ + row] = l_run;
+      asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");
+      l_run += lx[(hf ^ 1) * TQ + row];
+      asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");       // read before the next tile rewrites lx
       const int tq = qt * TQ + row;
       if (tq < T) {
         const float inv = 1.0f / l_run;
