@@ -157,6 +157,15 @@ ND_EXPORT int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_b
                           int32_t min_len, int32_t length_penalty, float alpha, int64_t* out_ids,
                           int32_t* out_lens, float* out_scores, void* stream);
 
+/* Read assembly helpers (host code, no GPU work; utils/labelop.py:320-352).
+ * nd_longest_match: difflib.SequenceMatcher(None, a, b).find_longest_match(0, na, 0, nb), i.e. the longest block of
+ *   get_matching_blocks() the reference's simple_assembly() selects (CPython's autojunk rule included; the sentinel
+ *   {na, nb, 0} when nothing matches) -> out3 = {i, j, size}.
+ * nd_assembly_offsets: chunks i = text[offsets[i] : offsets[i+1]], i < n; disp[i] = i_match - j_match between chunk
+ *   i-1 and chunk i (disp[0] = 0): the displacement simple_assembly() accumulates.                              */
+ND_EXPORT int nd_longest_match(const char* a, int32_t na, const char* b, int32_t nb, int32_t* out3);
+ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int32_t n, int32_t* disp);
+
 /* integer options (results never depend on them):
  *   "decode_streams" (default 1, 1..16): engine-owned CUDA streams the decode loop spreads contiguous
  *                    chunk groups over (chunks are independent);

@@ -248,6 +248,59 @@ def make_frontend_golden(write=True):
         np.savez_compressed(os.path.join(GOLDEN_DIR, "frontend.npz"), n_reads=len(reads), **store)
 
 
+def assembly_cases():
+    """Seeded inputs for the read-assembly golden: overlapping windows of a random genome with substitution / indel
+    noise, repeats (longest-block ties), empty chunks, and base strings >= 200 (difflib's autojunk rule)."""
+    rng = np.random.RandomState(7)
+    cases = []
+    for case in range(10):
+        n = int(rng.randint(300, 2500))
+        genome = "".join(rng.choice(list("ACGT"), size=n))
+        if case == 3:
+            genome = ("ACGTTGCA" * 40) + genome[:200]                  # periodic: many maximal blocks
+        n = len(genome)
+        win, stride = [(60, 20), (100, 30), (250, 80), (40, 10), (90, 45)][case % 5]
+        chunks = []
+        for s0 in range(0, max(1, n - win + 1), stride):
+            seg = list(genome[s0: s0 + win])
+            for _ in range(int(rng.randint(0, 4))):                     # noise
+                k = int(rng.randint(0, len(seg)))
+                r = rng.rand()
+                if r < 0.5:
+                    seg[k] = "ACGT"[int(rng.randint(4))]
+                elif r < 0.75:
+                    del seg[k]
+                else:
+                    seg.insert(k, "ACGT"[int(rng.randint(4))])
+            chunks.append(" ".join(seg))
+            if rng.rand() < 0.05:
+                chunks.append("")                                       # a chunk that decoded to nothing
+        cases.append([[c] for c in chunks])
+    return cases
+
+
+def make_assembly_golden(write=True):
+    """Run the reference's own simple_assembly / index2base (utils/labelop.py:295-352) on seeded chunk lists."""
+    refshim.install()
+    import numpy
+    if not hasattr(numpy, "float"):
+        numpy.float = float
+    if not hasattr(numpy.lib, "pad"):
+        numpy.lib.pad = numpy.pad                            # np.lib.pad (labelop.py:341) left numpy's namespace in 2.0
+    from utils.labelop import simple_assembly, index2base
+    store = {}
+    cases = assembly_cases()
+    for ci, bpreads in enumerate(cases):
+        votes = simple_assembly(bpreads)
+        store["case%d_input" % ci] = np.array("\n".join(x[0] for x in bpreads))
+        store["case%d_votes" % ci] = votes.astype(np.int32)
+        store["case%d_fasta" % ci] = np.array(index2base(np.argmax(votes, axis=0)))
+        store["case%d_concat" % ci] = np.array(simple_assembly(bpreads, flag_intersection=False))
+    print("assembly: %d cases through the reference's simple_assembly" % len(cases))
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "assembly.npz"), n_cases=len(cases), **store)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", nargs="*", default=list(CASES))
@@ -257,6 +310,7 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     make_frontend_golden(write=not args.no_write)
+    make_assembly_golden(write=not args.no_write)
     for name in args.cases:
         B = args.B if "d512" not in name else 3
         make_case(name, B=B, write=not args.no_write)
