@@ -43,27 +43,28 @@ __device__ __forceinline__ float2 ldg_stream2(const float* p) {
 }
 
 // ---- programmatic dependent launch (PDL).  Every kernel of the decode step loop starts with
-// pdl_launch_dependents() (the next kernel of the stream may become resident and run its prologue now) and
-// executes pdl_wait() before its first access to memory another kernel may have written or may still read;
-// pdl_wait() returns once ALL prerequisite grids have completed and flushed.  Both are no-ops when the kernel
-// was launched without the attribute.
-// Measured on B200 (profiles/r01_pdl_experiment.md): triggering at kernel ENTRY makes the decode loop 30 %
-// slower (CTAs of the following kernels become resident on whatever SMs are free at that moment, so the
-// 1024-CTA attention kernels end up badly balanced).  ND_PDL_EARLY=1 re-enables it for experiments.
+// pdl_launch_dependents() (a dependent launch that follows in the stream may become resident and run its prologue
+// now) and executes pdl_wait() before its first access to memory another kernel may have written or may still
+// read; pdl_wait() returns once ALL prerequisite grids have completed and flushed.  Both are no-ops for a kernel
+// launched without the attribute / without a dependent behind it.
+// Which launches carry the attribute is decided by g_pdl (measured, profiles/r01_pdl_experiment.md):
+//   2 (default)  only the tcgen05 GEMMs: they need a whole SM each (200 KB of shared memory), so they trickle onto
+//                SMs as the preceding kernel frees them and overlap their launch latency, TMEM allocation and
+//                weight-tile prefetch with its tail: decode 85.6 -> 83.3 ms
+//   1            every step kernel: the 1024-CTA attention kernels become resident next to a running GEMM on the
+//                SMs it leaves free and stay badly balanced: 85.4 -> 112 ms
+//   0            plain stream order
 #ifndef ND_PDL_EARLY
-#define ND_PDL_EARLY 0
+#define ND_PDL_EARLY 1
 #endif
 __device__ __forceinline__ void pdl_launch_dependents() {
 #if ND_PDL_EARLY
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
-// trigger used near the END of a kernel's main loop: the next kernel's launch latency and prologue overlap
-// this kernel's epilogue only
-__device__ __forceinline__ void pdl_launch_dependents_late() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-extern int g_pdl;                       // 1: launch_k adds the programmatic-stream-serialization attribute
+extern int g_pdl;
 
 // <<<grid, block, smem, stream>>> replacement for kernels that follow the PDL protocol above
 template <class... Params, class... Args>
@@ -78,7 +79,7 @@ static inline cudaError_t launch_k(void (*kernel)(Params...), dim3 grid, dim3 bl
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = g_pdl == 1 ? 1 : 0;              // g_pdl == 2: only the tcgen05 GEMM launches are dependent launches
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 

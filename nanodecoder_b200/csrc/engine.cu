@@ -15,7 +15,7 @@
 
 using namespace nd;
 
-namespace nd { int g_pdl = 0; }   // programmatic dependent launch: measured slower on this workload, see common.cuh
+namespace nd { int g_pdl = 2; }   // programmatic dependent launch for the tcgen05 GEMMs only, see common.cuh
 
 namespace {
 
@@ -1426,7 +1426,7 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     return ND_OK;
   }
   if (strcmp(name, "pdl") == 0) {            // programmatic dependent launch in the decode loop (process-wide)
-    g_pdl = value != 0;
+    g_pdl = (int)value;
     return ND_OK;
   }
   if (strcmp(name, "lstm_variant") == 0) {
