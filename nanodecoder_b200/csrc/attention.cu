@@ -12,7 +12,10 @@ constexpr int kAttnWarps = kAttnThreads / 32;
 
 template <int VPL>
 __device__ __forceinline__ void load_slice(const float* p, float (&v)[VPL]) {
-  if constexpr (VPL % 4 == 0) {
+  if constexpr (VPL % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < VPL; i += 8) ldg_stream8(p + i, &v[i]);
+  } else if constexpr (VPL % 4 == 0) {
 #pragma unroll
     for (int i = 0; i < VPL; i += 4) {
       const float4 t = ldg_stream4(p + i);
