@@ -166,11 +166,19 @@ ND_EXPORT int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_b
 ND_EXPORT int nd_longest_match(const char* a, int32_t na, const char* b, int32_t nb, int32_t* out3);
 ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int32_t n, int32_t* disp);
 
-/* integer options (results never depend on them):
+/* integer options.  Scheduling only (results never depend on them):
  *   "decode_streams" (default 1, 1..16): engine-owned CUDA streams the decode loop spreads contiguous
  *                    chunk groups over (chunks are independent);
  *   "use_graphs"     (default 1): capture the decode loop of a repeated (mode, B, T, L, ...) configuration
- *                    into a CUDA graph on its second call and replay it afterwards.                    */
+ *                    into a CUDA graph on its second call and replay it afterwards;
+ *   "pdl"            (default 2, process-wide): 2 = the tcgen05 GEMMs of the step loop are programmatic dependent
+ *                    launches, 1 = every step kernel, 0 = plain stream order.
+ * Kernel selection (same arithmetic contract, results agree to fp32 rounding; all are covered by parity tests):
+ *   "gemm_persistent" (default 1, process-wide): large-M projections as the persistent tcgen05 kernel;
+ *   "enc_attn_tc"    (default 1): Transformer-encoder self attention on the tensor cores (head size 32), 0 = FFMA;
+ *   "lstm_variant"   (default 0, process-wide): tensor-core LSTM keeps W_hh in tensor memory (0) or shared memory (1);
+ *   "cross_mode"     (default 0): 1 = greedy decode runs the cross attention in memory-bank space (opt-in, slower);
+ *   "cross_mb_version" (default 2, process-wide): implementation used by cross_mode 1.                          */
 ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);
 
 /* per-kernel-category device timing for bench.py's roofline figures: while a category bit is set,
