@@ -263,6 +263,12 @@ __global__ void cnn_window_kernel(const float* __restrict__ x, float* __restrict
     A[(int64_t)r * k * d + i] = v;
   }
 }
+__global__ void tanh_kernel(float* __restrict__ x, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = tanhf(x[i]);
+}
 __global__ void add_scale_kernel(const float* __restrict__ a, const float* __restrict__ b, float s,
                                  float* __restrict__ out, int64_t n) {
   pdl_launch_dependents();
@@ -286,6 +292,12 @@ cudaError_t cnn_window(const float* x, float* hist, const int* anc, int anc_ld, 
   launch_k(cnn_window_kernel, dim3(rows), dim3(256), 0, stream, x, hist, anc, anc_ld, retired, rows_per_chunk, A, row0, t, k, d, Lmax);
   return cudaGetLastError();
 }
+cudaError_t tanh_inplace(float* x, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  launch_k(tanh_kernel, dim3((unsigned)cdiv64(n, 256)), dim3(256), 0, stream, x, n);
+  return cudaGetLastError();
+}
+
 cudaError_t add_scale(const float* a, const float* b, float s, float* out, int64_t n, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   launch_k(add_scale_kernel, dim3((unsigned)cdiv64(n, 256)), dim3(256), 0, stream, a, b, s, out, n);

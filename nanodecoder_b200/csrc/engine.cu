@@ -964,17 +964,29 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
     ma.retired = retired ? retired + dc.c0 : nullptr; ma.ctx = R(e->actx, d); ma.ctx_ld = d;
     ma.n_chunks = dc.nc; ma.NQ = K; ma.T = Tp; ma.d = d;
     ma.attn = dc.attn_out ? dc.attn_out + (int64_t)r0 * Tp : nullptr;
-    if (c.attn_type != ND_ATTN_MLP)
-      return fail(e, ND_ERR_INVALID, "general/dot global attention: not implemented in this build");
-    GemmOpt oq;
-    ND_TRY(run_gemm(e, e->attn_q, below, d, R(e->wq, d), d, rows, oq, st));
-    ma.wq = R(e->wq, d); ma.uh = e->uh + (int64_t)dc.c0 * Tp * d; ma.v = e->attn_v;
+    if (c.attn_type == ND_ATTN_MLP) {
+      GemmOpt oq;                    // wq = W_q h + b; uh = U_k H was cached by decoder_init   global_attention.py:123-136
+      ND_TRY(run_gemm(e, e->attn_q, below, d, R(e->wq, d), d, rows, oq, st));
+      ma.wq = R(e->wq, d); ma.uh = e->uh + (int64_t)dc.c0 * Tp * d; ma.v = e->attn_v;
+    } else {
+      // "general": score = (W_in h) . H_s; "dot": score = h . H_s                             global_attention.py:113-122
+      ma.dot = 1;
+      if (c.attn_type == ND_ATTN_GENERAL) {
+        GemmOpt oq;
+        ND_TRY(run_gemm(e, e->attn_in, below, d, R(e->wq, d), d, rows, oq, st));
+        ma.wq = R(e->wq, d);
+      } else {
+        ma.wq = below;
+      }
+      ma.uh = e->mb + (int64_t)dc.c0 * Tp * d;
+    }
     ND_LAUNCH_CAT(e, ND_PROF_MLP_ATTN, st, mlp_attention(ma, st));
-    // attn_h = W_out [c ; h] + b (no tanh for mlp)                           global_attention.py:197-200
+    // attn_h = W_out [c ; h] (+ b, no tanh, for mlp; tanh, no bias, for general / dot)   global_attention.py:197-203
     GemmOpt oc;
     ND_TRY(run_gemm(e, e->attn_out_c, R(e->actx, d), d, R(e->wq, d), d, rows, oc, st));
     GemmOpt oh; oh.residual = R(e->wq, d); oh.ldr = d;
     ND_TRY(run_gemm(e, e->attn_out_h, below, d, R(e->feed[nxt], d), d, rows, oh, st));
+    if (c.attn_type != ND_ATTN_MLP) ND_LAUNCH(e, tanh_inplace(R(e->feed[nxt], d), (int64_t)rows * d, st));
     gp.x = R(e->feed[nxt], d); gp.x_ld = d; gp.ln_g = nullptr; gp.ln_b = nullptr;
   } else {
     // CNN decoder, incremental (the reference re-runs the whole prefix each step, cnn_decoder.py:79-80; the

@@ -160,6 +160,9 @@ cudaError_t beam_finalize(const BeamParams& p, int64_t* out_ids, int* out_lens, 
 cudaError_t gather_rows(const float* src, float* dst, const int* parent, int row0, int rows, int width,
                         cudaStream_t stream);
 
+// x = tanh(x) (accurate tanhf): output stage of the general / dot global attention (global_attention.py:201-203)
+cudaError_t tanh_inplace(float* x, int64_t n, cudaStream_t stream);
+
 // LSTMCell pointwise (onmt/models/stacked_rnn.py:25-31): gates [rows,4d] (= x.W_ih^T+b_ih + h.W_hh^T+b_hh)
 cudaError_t lstm_cell_pointwise(const float* gates_a, const float* gates_b, const float* c_in,
                                 float* h_out, float* c_out, int rows, int d, cudaStream_t stream);

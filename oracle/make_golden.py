@@ -50,6 +50,10 @@ CASES = {
     "l2t_d64": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2)),
     "t2t_d64": ("t2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2)),
     "t2t_d512_6x6": ("t2t", dict(d_model=512, enc_layers=6, dec_layers=6)),
+    # the RNN decoder's other global-attention scorers (onmt/modules/global_attention.py:95-136; "general" is the
+    # reference's command-line default)
+    "nano2rnn_general_d64": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, global_attention="general")),
+    "brnn2rnn_dot_d64": ("brnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, global_attention="dot")),
 }
 
 
@@ -70,7 +74,7 @@ def load_into_reference(model, sd):
 def run_reference(family, cfg, sd, src, lengths, max_length, beam_size):
     model, fields, mopt = refshim.build_reference_model(
         family, d=cfg.d_model, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers,
-        heads=cfg.heads, ff=cfg.d_ff)
+        heads=cfg.heads, ff=cfg.d_ff, extra=["-global_attention", cfg.global_attention])
     load_into_reference(model, sd)
     assert list(fields["tgt"].vocab.itos) == cfg.vocab
     out = {}
