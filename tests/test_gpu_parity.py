@@ -292,3 +292,54 @@ def test_translate_host_paths_agree(beam, fast):
         i = int(order[j])
         assert preds[i] == [" ".join(p) for p in t.pred_sents[:NB]]
         assert [float(x) for x in scores[i]] == [float(x) for x in t.pred_scores[:NB]]
+
+
+@pytest.mark.parametrize("family", ["l2t", "t2t", "nano2rnn", "brnn2rnn", "cnn2cnn"])
+@pytest.mark.parametrize("B,T,L", [(1, 1, 1), (1, 9, 3), (3, 7, 2), (2, 130, 5)])
+def test_edge_shapes_vs_oracle(family, B, T, L):
+    """Smallest batches, one-sample chunks, a single decode step, T just past a tile boundary."""
+    from oracle import decode as od
+    from oracle.model import OracleModel
+    cfg = ModelConfig.family(family, d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    sd = synth.make_state_dict(cfg, seed=13)
+    g = torch.Generator().manual_seed(B * 100 + T)
+    chunks = (torch.randn(B, T, generator=g) * 64).round() / 64
+    lengths = torch.tensor(sorted([max(1, T - 3 * i) for i in range(B)], reverse=True), dtype=torch.int64)
+    for i in range(B):
+        chunks[i, int(lengths[i]):] = 0
+    eng = _engine(cfg, sd, B, T, L, K=2)
+    eng.encode(chunks.cuda(), lengths.cuda())
+    gr = eng.decode_greedy(L, return_logits=True)
+    bm = eng.decode_beam(2, 1, L)
+    ob_dev = eng.decode_beam_object(2, 1, L)
+    torch.cuda.synchronize()
+    om = OracleModel(sd, cfg)
+    s = chunks.t().contiguous().unsqueeze(2)
+    trace = []
+    og = od.greedy(om, s, lengths, max_length=L, trace_logits=trace)
+    assert torch.equal(gr["ids"].cpu(), og["predictions"])
+    assert rel_err(gr["logits"].cpu(), torch.stack(trace)) < TOL
+    of = od.beam_fast(om, s, lengths, beam_size=2, max_length=L)
+    oo = od.beam_object(om, s, lengths, beam_size=2, max_length=L)
+    for i in range(B):
+        assert torch.equal(bm["ids"][i, 0, : int(bm["lens"][i, 0])].cpu(), of["predictions"][i][0])
+        assert torch.equal(ob_dev["ids"][i, 0, : int(ob_dev["lens"][i, 0])].cpu(), oo["predictions"][i][0])
+
+
+def test_engine_rejects_out_of_range_calls():
+    from nanodecoder_b200._lib import NanodecError
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=1, dec_layers=1)
+    eng = _engine(cfg, synth.make_state_dict(cfg), 4, 32, 8, K=2)
+    with pytest.raises(NanodecError):
+        eng.decode_greedy(4)                                   # decode before encode
+    x, l = torch.zeros(5, 32).cuda(), torch.full((5,), 32, dtype=torch.int64).cuda()
+    with pytest.raises(NanodecError):
+        eng.encode(x, l)                                       # batch above max_batch
+    eng.encode(x[:4], l[:4])
+    with pytest.raises(NanodecError):
+        eng.decode_greedy(9)                                   # max_len above max_tgt_len
+    with pytest.raises(NanodecError):
+        eng.decode_beam(3, 1, 8)                               # beam above max_beam
+    with pytest.raises(NanodecError):
+        eng.decode_beam_object(2, 3, 8)                        # n_best above beam_size
+    assert eng.decode_greedy(8)["ids"].shape == (4, 8)         # the engine is still usable afterwards
