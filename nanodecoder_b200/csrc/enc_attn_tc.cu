@@ -1,4 +1,4 @@
-// Transformer-encoder self attention on the 5th-generation tensor cores (head size 32, T <= 512).
+// Transformer-encoder self attention on the 5th-generation tensor cores (head size 32 or 64, T <= 512).
 // Reference: encoder/transformer.py:36-54 -> onmt/modules/multi_headed_attn.py:69-192 (q / sqrt(dh) before
 // Q.K^T, masked_fill(-1e18) of the keys whose SIGNAL VALUE is 0.0, softmax in fp32, context = P.V).
 //
@@ -371,10 +371,262 @@ __global__ void __launch_bounds__(kThreads, 1) enc_attn_tc_kernel(EncAttnParams 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Head size 64 (d = 512, 8 heads).  Same scheme; the operand tiles of all 512 keys would take 256 KB, so the keys
+// are processed in two halves of 256 and the K / V operand tiles of a half (64 + 64 KB) are rebuilt for every
+// query tile (8 conversions of 256 keys per CTA instead of 2: ~15 % of the CTA's time).
+//   K half:  two planes [K_hi | K_lo], each [256 keys][128 B = 64 fp16]
+//   V half:  4 k-blocks of 64 keys, each [V_hi: 64 feature rows][V_lo: 64 rows] x 128 B
+//   S = Q_hi.K_hi + Q_hi.K_lo + Q_lo.K_hi (12 MMAs, N 128); O_j = P_hi.[V_hi ; V_lo] (N 128) + P_lo.V_hi (N 64)
+constexpr int DH64 = 64, KHALF = 256;
+constexpr int K64_PLANE = KHALF * 128;                         // 32 KB
+constexpr int V64_KB = 128 * 128;                              // 16 KB per 64-key k-block
+constexpr int Q64_BYTES = 2 * TQ * 128;                        // A_hi, A_lo
+constexpr int SMEM64_BYTES = 2 * K64_PLANE + (KHALF / 64) * V64_KB + Q64_BYTES + TMAX * 4 + 6 * TQ * 4 + 128 + 1024;
+constexpr uint32_t kColO64 = 256;                              // O: 128 columns [hh + lh | hl]
+
+__global__ void __launch_bounds__(kThreads, 1) enc_attn_tc64_kernel(EncAttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* kop = smem;                                   // [2 planes][256 keys][128 B]
+  uint8_t* vop = kop + 2 * K64_PLANE;                    // [4 k-blocks][128 rows][128 B]
+  uint8_t* qop = vop + (KHALF / 64) * V64_KB;            // A_hi, A_lo: [128 rows][128 B]
+  float* kflag = reinterpret_cast<float*>(qop + Q64_BYTES);
+  float* mx = kflag + TMAX;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mx + 6 * TQ);
+  uint64_t* go = bars;
+  uint64_t* s_full = bars + 1;
+  uint64_t* p_full = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int T = p.T, d = p.d;
+  const float* base = p.qkv + (int64_t)b * T * 3 * d + h * DH64;
+  const int nkb = (T + TK - 1) / TK;
+  const int nqt = (T + TQ - 1) / TQ;
+
+  if (tid == 0) {
+    mbar_init(go, kSmThreads);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, kSmThreads);
+    mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kSmWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp < kSmWarps)
+    for (int t = tid; t < TMAX; t += kSmThreads)
+      kflag[t] = t < T ? (p.src[(int64_t)b * T + t] == 0.0f ? 1.f : 0.f) : 2.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  if (warp == kSmWarps) {
+    // ===================================================================== MMA issuer
+    uint32_t it = 0;
+    for (int qt = 0; qt < nqt; ++qt)
+      for (int j = 0; j < nkb; ++j, ++it) {
+        const int jb = j & 1;                              // key block inside the resident half
+        mbar_wait(go, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint64_t dah = make_desc(smem_u32(qop));
+          const uint64_t dal = make_desc(smem_u32(qop + TQ * 128));
+          const uint64_t dkh = make_desc(smem_u32(kop + jb * TK * 128));
+          const uint64_t dkl = make_desc(smem_u32(kop + K64_PLANE + jb * TK * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + kColS, dah + 2 * k, dkh + 2 * k, idesc128, k ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + kColS, dah + 2 * k, dkl + 2 * k, idesc128, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + kColS, dal + 2 * k, dkh + 2 * k, idesc128, 1u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+        mbar_wait(p_full, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t dbv = make_desc(smem_u32(vop + (2 * jb + (ks >> 2)) * V64_KB)) + (uint64_t)(2 * (ks & 3));
+            umma_ts(tmem_base + kColO64, tmem_base + kColPhi + ks * 8, dbv, idesc128, ks ? 1u : 0u);   // [V_hi ; V_lo]
+            umma_ts(tmem_base + kColO64, tmem_base + kColPlo + ks * 8, dbv, idesc64, 1u);              // V_hi
+          }
+          umma_commit(o_full);
+        }
+        __syncwarp();
+      }
+  } else {
+    // ===================================================================== softmax / conversion warps
+    const int lq = warp & 3, hf = warp >> 2;
+    const int row = lq * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
+    const float kLog2e = 1.4426950408889634f;
+    // K and V of keys [256 kh, 256 kh + 256) -> operand tiles (task = (key, 8-feature chunk), lanes = consecutive keys)
+    auto convert_half = [&](int kh) {
+      for (int i = tid; i < KHALF * 8; i += kSmThreads) {
+        const int c = i / KHALF, tl = i - c * KHALF;
+        const int t = kh * KHALF + tl;
+        float kf[8], vf[8];
+        if (t < T) {
+          const float4 k0 = *reinterpret_cast<const float4*>(base + (int64_t)t * 3 * d + d + 8 * c);
+          const float4 k1 = *reinterpret_cast<const float4*>(base + (int64_t)t * 3 * d + d + 8 * c + 4);
+          const float4 v0 = *reinterpret_cast<const float4*>(base + (int64_t)t * 3 * d + 2 * d + 8 * c);
+          const float4 v1 = *reinterpret_cast<const float4*>(base + (int64_t)t * 3 * d + 2 * d + 8 * c + 4);
+          kf[0] = k0.x; kf[1] = k0.y; kf[2] = k0.z; kf[3] = k0.w; kf[4] = k1.x; kf[5] = k1.y; kf[6] = k1.z; kf[7] = k1.w;
+          vf[0] = v0.x; vf[1] = v0.y; vf[2] = v0.z; vf[3] = v0.w; vf[4] = v1.x; vf[5] = v1.y; vf[6] = v1.z; vf[7] = v1.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { kf[q] = 0.f; vf[q] = 0.f; }
+        }
+        uint4 hi4, lo4;
+        split2(kf[0], kf[1], hi4.x, lo4.x); split2(kf[2], kf[3], hi4.y, lo4.y);
+        split2(kf[4], kf[5], hi4.z, lo4.z); split2(kf[6], kf[7], hi4.w, lo4.w);
+        const int ko = tl * 128 + ((c ^ (tl & 7)) << 4);
+        *reinterpret_cast<uint4*>(kop + ko) = hi4;
+        *reinterpret_cast<uint4*>(kop + K64_PLANE + ko) = lo4;
+        uint8_t* vkb = vop + (tl >> 6) * V64_KB;
+        const int kk = tl & 63;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = 8 * c + q;
+          const __half vh = __float2half_rn(vf[q]);
+          const __half vl = __float2half_rn(vf[q] - __half2float(vh));
+          const int vo = (((kk >> 3) ^ (e & 7)) << 4) + ((kk & 7) << 1);
+          *reinterpret_cast<__half*>(vkb + e * 128 + vo) = vh;
+          *reinterpret_cast<__half*>(vkb + (64 + e) * 128 + vo) = vl;
+        }
+      }
+    };
+    uint32_t it = 0;
+    int resident = -1;                                     // which key half the operand tiles hold
+    for (int qt = 0; qt < nqt; ++qt) {
+      // ---- Q tile -> A operands (task = (row, 8-feature chunk): 1024 tasks, four per thread)
+      for (int i = tid; i < TQ * 8; i += kSmThreads) {
+        const int r = i >> 3, c = i & 7;
+        const int tq = qt * TQ + r;
+        float qf[8];
+        if (tq < T) {
+          const float4 q0 = *reinterpret_cast<const float4*>(base + (int64_t)tq * 3 * d + 8 * c);
+          const float4 q1 = *reinterpret_cast<const float4*>(base + (int64_t)tq * 3 * d + 8 * c + 4);
+          qf[0] = q0.x / p.q_div; qf[1] = q0.y / p.q_div; qf[2] = q0.z / p.q_div; qf[3] = q0.w / p.q_div;
+          qf[4] = q1.x / p.q_div; qf[5] = q1.y / p.q_div; qf[6] = q1.z / p.q_div; qf[7] = q1.w / p.q_div;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) qf[q] = 0.f;
+        }
+        uint4 hi4, lo4;
+        split2(qf[0], qf[1], hi4.x, lo4.x); split2(qf[2], qf[3], hi4.y, lo4.y);
+        split2(qf[4], qf[5], hi4.z, lo4.z); split2(qf[6], qf[7], hi4.w, lo4.w);
+        const int qo = r * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(qop + qo) = hi4;
+        *reinterpret_cast<uint4*>(qop + TQ * 128 + qo) = lo4;
+      }
+      float m_run = -INFINITY, l_run = 0.f;
+      float o_run[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_run[i] = 0.f;
+
+      for (int j = 0; j < nkb; ++j, ++it) {
+        // operands of this block: rebuild the key half when it is not the resident one (every MMA that read the
+        // tiles has completed: this thread has seen o_full of the previous block)
+        if ((j >> 1) != resident) {
+          convert_half(j >> 1);
+          resident = j >> 1;
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_arrive(go);                                   // Q / K / V operands in place, S, P, O of the last block consumed
+        mbar_wait(s_full, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float s[64];
+        {
+          float v0[32], v1[32];
+          tmem_ld32(tmem_base + lane_base + kColS + 64 * hf, v0);
+          tmem_ld32(tmem_base + lane_base + kColS + 64 * hf + 32, v1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s[i] = v0[i]; s[32 + i] = v1[i]; }
+        }
+        const float* fl = kflag + j * TK + 64 * hf;
+        float mloc = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(fl + i);
+          s[i] = f.x == 0.f ? s[i] : (f.x == 1.f ? -1e18f : -INFINITY);
+          s[i + 1] = f.y == 0.f ? s[i + 1] : (f.y == 1.f ? -1e18f : -INFINITY);
+          s[i + 2] = f.z == 0.f ? s[i + 2] : (f.z == 1.f ? -1e18f : -INFINITY);
+          s[i + 3] = f.w == 0.f ? s[i + 3] : (f.w == 1.f ? -1e18f : -INFINITY);
+          mloc = fmaxf(fmaxf(mloc, fmaxf(s[i], s[i + 1])), fmaxf(s[i + 2], s[i + 3]));
+        }
+        float* mxb = mx + (it & 1) * 2 * TQ;
+        mxb[hf * TQ + row] = mloc;
+        asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");
+        const float m_j = fmaxf(mloc, mxb[(hf ^ 1) * TQ + row]);
+        float lsum = 0.f;
+        uint32_t phi[32], plo[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          const float p0 = ex2_approx((s[i] - m_j) * kLog2e);
+          const float p1 = ex2_approx((s[i + 1] - m_j) * kLog2e);
+          lsum += p0 + p1;
+          split2(p0, p1, phi[i >> 1], plo[i >> 1]);
+        }
+        tmem_st32(tmem_base + lane_base + kColPhi + 32 * hf, phi);
+        tmem_st32(tmem_base + lane_base + kColPlo + 32 * hf, plo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(p_full);
+        const float m_new = fmaxf(m_run, m_j);
+        const float a_old = ex2_approx((m_run - m_new) * kLog2e);
+        const float a_blk = ex2_approx((m_j - m_new) * kLog2e);
+        l_run = l_run * a_old + lsum * a_blk;
+        m_run = m_new;
+        mbar_wait(o_full, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+          float oa[32], ob[32];                            // features 32 hf + [0,32): P_hi.V_hi + P_lo.V_hi | P_hi.V_lo
+          tmem_ld32(tmem_base + lane_base + kColO64 + 32 * hf, oa);
+          tmem_ld32(tmem_base + lane_base + kColO64 + 64 + 32 * hf, ob);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_run[i] = o_run[i] * a_old + (oa[i] + ob[i]) * a_blk;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+      float* lx = mx + 4 * TQ;
+      lx[hf * TQ + row] = l_run;
+      asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");
+      l_run += lx[(hf ^ 1) * TQ + row];
+      asm volatile("bar.sync 1, %0;" ::"n"(kSmThreads) : "memory");
+      const int tq = qt * TQ + row;
+      if (tq < T) {
+        const float inv = 1.0f / l_run;
+        float* out = p.ctx + ((int64_t)b * T + tq) * d + h * DH64 + 32 * hf;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(out + i) = make_float4(o_run[i] * inv, o_run[i + 1] * inv, o_run[i + 2] * inv, o_run[i + 3] * inv);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kSmWarps) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
 }  // namespace
 
 bool encoder_attention_tc_supported(const EncAttnParams& p) {
-  return p.H > 0 && p.d / p.H == DH && p.T <= TMAX && (p.d % 4) == 0;
+  return p.H > 0 && (p.d / p.H == DH || p.d / p.H == DH64) && p.d % p.H == 0 && p.T <= TMAX && (p.d % 4) == 0;
 }
 
 cudaError_t encoder_attention_tc(const EncAttnParams& p, cudaStream_t stream) {
@@ -383,10 +635,13 @@ cudaError_t encoder_attention_tc(const EncAttnParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(enc_attn_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM64_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  enc_attn_tc_kernel<<<p.B * p.H, kThreads, SMEM_BYTES, stream>>>(p);
+  if (p.d / p.H == DH64) enc_attn_tc64_kernel<<<p.B * p.H, kThreads, SMEM64_BYTES, stream>>>(p);
+  else enc_attn_tc_kernel<<<p.B * p.H, kThreads, SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }
 

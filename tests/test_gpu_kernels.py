@@ -140,13 +140,14 @@ def test_nano_encoder_vs_oracle(d, mode):
     print("nano encoder d=%d rel err %.2e" % (d, err))
 
 
+@pytest.mark.parametrize("d", [256, 512])
 @pytest.mark.parametrize("T", [512, 333, 128])
-def test_transformer_encoder_attention_tensor_core_vs_ffma_and_oracle(T):
+def test_transformer_encoder_attention_tensor_core_vs_ffma_and_oracle(T, d):
     """Encoder self attention on tcgen05 (fp16 two-term split, P in tensor memory) against the fp32 FFMA kernel
     and the oracle: ragged T, keys masked by value (src == 0.0), several chunks."""
     from nanodecoder_b200.engine import Engine
     from oracle.model import OracleModel
-    cfg = ModelConfig.family("t2t", d_model=256, d_ff=512, enc_layers=2, dec_layers=1)
+    cfg = ModelConfig.family("t2t", d_model=d, d_ff=512, enc_layers=2, dec_layers=1)     # head size 32 | 64
     sd = synth.make_state_dict(cfg, seed=4)
     B = 9
     chunks, lengths = synth.make_chunks(B, T=T, seed=8, ragged=True, read_len=3)
@@ -162,5 +163,5 @@ def test_transformer_encoder_attention_tensor_core_vs_ffma_and_oracle(T):
     with torch.no_grad():
         _, want, _ = OracleModel(sd, cfg).encoder(chunks.t().contiguous().unsqueeze(2), lengths)
     e_tc, e_ff, e_x = rel_err(outs[0], want), rel_err(outs[1], want), rel_err(outs[0], outs[1].double())
-    print("T=%d: tensor-core vs oracle %.2e, FFMA vs oracle %.2e, tensor-core vs FFMA %.2e" % (T, e_tc, e_ff, e_x))
+    print("T=%d d=%d: tensor-core vs oracle %.2e, FFMA vs oracle %.2e, tensor-core vs FFMA %.2e" % (T, d, e_tc, e_ff, e_x))
     assert e_tc < 1e-4 and e_ff < 1e-4 and e_x < 1e-4
