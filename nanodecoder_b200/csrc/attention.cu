@@ -567,7 +567,8 @@ cudaError_t cross_attention_mb(const CrossMbParams& p, cudaStream_t stream) {
   if (g_cross_mb_version == 2 && p.d == kMb2D && p.H == kMb2H) {
     const int nst = 5;                                 // 5 x 32 KB tiles in flight per SM (one CTA per SM)
     const size_t smem = (size_t)nst * kMbTT * kMb2D * 4 + (2 * kMb2H * kMbTT + kMb2H) * 4 + 64;
-    static bool attr_set = false;
+    static PerDeviceFlag attr_flag;
+  bool& attr_set = attr_flag.cur();
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(cross_attn_mb2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
@@ -581,7 +582,10 @@ cudaError_t cross_attention_mb(const CrossMbParams& p, cudaStream_t stream) {
   int nst = 4;
   while (nst > 2 && nst * tile_b + fixed > 100 * 1024) --nst;        // two CTAs per SM when the tiles allow it
   const size_t smem = nst * tile_b + fixed;
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[64] = {};
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  size_t& attr_smem = attr_smem_dev[dev_ & 63];
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(cross_attn_mb_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

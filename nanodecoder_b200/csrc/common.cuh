@@ -90,6 +90,18 @@ static inline cudaError_t launch_k(void (*kernel)(Params...), dim3 grid, dim3 bl
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 
+// Function attributes (dynamic shared-memory limit) are per DEVICE: a launcher's "already set" flag must be too, or the
+// second GPU used by one process launches with the default 48 KB limit.  -> slot of the current device in a static
+// per-launcher table (returns a reference the launcher flips after cudaFuncSetAttribute succeeded).
+struct PerDeviceFlag {
+  bool set[64] = {};
+  bool& cur() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return set[dev & 63];
+  }
+};
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

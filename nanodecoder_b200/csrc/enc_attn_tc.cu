@@ -632,7 +632,8 @@ bool encoder_attention_tc_supported(const EncAttnParams& p) {
 cudaError_t encoder_attention_tc(const EncAttnParams& p, cudaStream_t stream) {
   if (p.B <= 0) return cudaSuccess;
   if (!encoder_attention_tc_supported(p)) return cudaErrorInvalidValue;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;
+  bool& attr_set = attr_flag.cur();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(enc_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess)

@@ -907,7 +907,8 @@ bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, i
 template <int BN, int NPASS, int S>
 cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN, NPASS, S>;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;
+  bool& attr_set = attr_flag.cur();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
@@ -944,7 +945,8 @@ int g_n_sm = 0;
 template <int BN, int NPASS>
 cudaError_t launch_persist(const GemmParams& p, cudaStream_t stream) {
   using C = PCfg<BN, NPASS>;
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;
+  bool& attr_set = attr_flag.cur();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);

@@ -462,7 +462,8 @@ int g_variant = 0;                                            // 0: W_hh in tens
 
 template <bool A_TMEM>
 cudaError_t launch(const LstmParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;
+  bool& attr_set = attr_flag.cur();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(lstm_tc_kernel<A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<A_TMEM>());
     if (e != cudaSuccess) return e;

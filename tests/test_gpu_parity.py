@@ -343,3 +343,19 @@ def test_engine_rejects_out_of_range_calls():
     with pytest.raises(NanodecError):
         eng.decode_beam_object(2, 3, 8)                        # n_best above beam_size
     assert eng.decode_greedy(8)["ids"].shape == (4, 8)         # the engine is still usable afterwards
+
+
+def test_two_devices_in_one_process():
+    """Engines on two GPUs of one process (function attributes and tensor maps are per device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from nanodecoder_b200.engine import Engine
+    g, cfg, sd, src, lengths = load_golden("l2t_d256")
+    B, T, L = src.shape[0], src.shape[1], int(g["max_length"])
+    for dev in (1, 0, 1):
+        with torch.cuda.device(dev):
+            eng = Engine(cfg, sd, max_batch=B, max_src_len=T, max_tgt_len=L, device=dev)
+            eng.encode(src.cuda(dev), lengths.cuda(dev))
+            ids = eng.decode_greedy(L)["ids"]
+            torch.cuda.synchronize(dev)
+            np.testing.assert_array_equal(ids.cpu().numpy(), g["greedy_ids"])
