@@ -165,3 +165,25 @@ def test_transformer_encoder_attention_tensor_core_vs_ffma_and_oracle(T, d):
     e_tc, e_ff, e_x = rel_err(outs[0], want), rel_err(outs[1], want), rel_err(outs[0], outs[1].double())
     print("T=%d d=%d: tensor-core vs oracle %.2e, FFMA vs oracle %.2e, tensor-core vs FFMA %.2e" % (T, d, e_tc, e_ff, e_x))
     assert e_tc < 1e-4 and e_ff < 1e-4 and e_x < 1e-4
+
+
+@pytest.mark.parametrize("N,K,ln", [(256, 256, True), (256, 256, False), (256, 2048, False), (512, 512, True)])
+def test_gemm_split_k_many_row_tiles_is_batch_invariant(small_engine, N, K, ln):
+    """Split-K shapes with many rows (beam search: M = 5 x batch): a cluster walks several row tiles.  The split factor
+    and the summation order depend on (N, K) only, so the first 1024 rows must be BIT-identical to a 1024-row call."""
+    g = torch.Generator().manual_seed(N + K)
+    M = 5121
+    A = (torch.randn(M, K, generator=g) * 1.3 + 0.2).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    res = torch.randn(M, N, generator=g).cuda()
+    gam = (1 + 0.1 * torch.randn(K, generator=g)).cuda()
+    bet = (0.1 * torch.randn(K, generator=g)).cuda()
+    lnp = (gam, bet) if ln else None
+    full = small_engine.test_gemm("3xtf32", A, W, bias=bias, residual=res, ln=lnp)
+    part = small_engine.test_gemm("3xtf32", A[:1024].contiguous(), W, bias=bias, residual=res[:1024].contiguous(), ln=lnp)
+    torch.cuda.synchronize()
+    An = torch.nn.functional.layer_norm(A.double(), (K,), gam.double(), bet.double(), 1e-6) if ln else A.double()
+    ref = An @ W.double().t() + bias.double() + res.double()
+    assert rel_err(full, ref) < 1e-5, rel_err(full, ref)
+    assert torch.equal(full[:1024], part)
