@@ -33,23 +33,49 @@ import torch  # noqa: E402
 
 METRIC = "basecalled_bases_per_sec"
 UNIT = "bases/s"
-WORKLOAD = "l2t_greedy_b1024"       # BASELINE.json configs[1]
+WORKLOAD = "l2t_greedy_b1024"       # BASELINE.json configs[1]: the default and the contract's bench line
 B_PER_GPU, T, L = 1024, 512, 100
-FAMILY = "l2t"
+# the other BASELINE.json configs (parity-test cases; measured with --workload for the record, profiles/)
+WORKLOADS = {
+    # name: (family, config kwargs, beam size, model description, roofline kernel category)
+    "l2t_greedy_b1024": ("l2t", {}, 1, "NanoDecoder LSTM2Transformer enc3(biLSTM)+dec3, d=256, heads=8, ff=2048", "cross_attn"),
+    "l2t_beam5_b1024": ("l2t", {}, 5, "NanoDecoder LSTM2Transformer enc3(biLSTM)+dec3, d=256, --fast beam 5", "cross_attn"),
+    "t2t_greedy_b1024": ("t2t", {}, 1, "Transformer2Transformer 3+3, d=256, heads=8, ff=2048", "cross_attn"),
+    "t2t512_greedy_b1024": ("t2t", dict(d_model=512, enc_layers=6, dec_layers=6), 1,
+                            "Transformer2Transformer 6+6, d=512, heads=8, ff=2048", "cross_attn"),
+    "nano2rnn_greedy_b1024": ("nano2rnn", {}, 1, "NanoDecoder LSTM enc3 -> InputFeed LSTM dec3, mlp attention, d=256", "mlp_attn"),
+    "brnn2rnn_greedy_b1024": ("brnn2rnn", {}, 1, "brnn enc3 -> InputFeed LSTM dec3, mlp attention, d=256", "mlp_attn"),
+    "cnn2cnn_greedy_b1024": ("cnn2cnn", {}, 1, "Conv2Conv 3+3, kernel width 3, d=256", "mlp_attn"),
+}
+FAMILY, FAMILY_KW, BEAM, MODEL_DESC, ROOF_CAT = WORKLOADS[WORKLOAD]
+
+
+def min_length():
+    """Beam workloads: with random-init weights the best hypothesis is "</s>" at step 0 (every further token only
+    lowers the cumulative log-prob), every chunk would retire at once and the metric would be 0 bases/s.
+    min_length = max_length - 1 (the reference's own -min_length flag) keeps all beams alive for the whole loop."""
+    return L - 1 if BEAM > 1 else 0
+
+
+def select_workload(name):
+    global WORKLOAD, FAMILY, FAMILY_KW, BEAM, MODEL_DESC, ROOF_CAT
+    WORKLOAD = name
+    FAMILY, FAMILY_KW, BEAM, MODEL_DESC, ROOF_CAT = WORKLOADS[name]
 
 
 def model_and_weights():
     from nanodecoder_b200 import synth
     from nanodecoder_b200.config import ModelConfig
-    cfg = ModelConfig.family(FAMILY)
+    cfg = ModelConfig.family(FAMILY, **FAMILY_KW)
     return cfg, synth.make_state_dict(cfg, seed=2025)
 
 
 def base_config(n_gpus):
-    return {"workload": WORKLOAD, "model": "NanoDecoder LSTM2Transformer enc3(biLSTM)+dec3, d=256, heads=8, ff=2048",
-            "decode": "greedy", "chunks_per_step_per_gpu": B_PER_GPU, "chunk_len": T, "max_length": L,
+    return {"workload": WORKLOAD, "model": MODEL_DESC,
+            "decode": "greedy" if BEAM == 1 else "--fast beam %d" % BEAM, "chunks_per_step_per_gpu": B_PER_GPU,
+            "chunk_len": T, "max_length": L, "min_length": min_length(),
             "global_chunks_per_step": B_PER_GPU * n_gpus, "parallelism": "read-sharded x%d" % n_gpus,
-            "l2_policy": "working set (3.2 GB of cross K/V per step) >> 126 MB L2; no flush needed"}
+            "l2_policy": "working set (GBs of attention keys / values per step) >> 126 MB L2; no flush needed"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -177,14 +203,19 @@ def cpu_sample(n_chunks, steps, warmup, target_s=None):
     i = 0
     while i < warmup + steps:
         t0 = time.perf_counter()
-        out = od.greedy(om, src, lengths, max_length=L)
+        if BEAM == 1:
+            out = od.greedy(om, src, lengths, max_length=L)
+            n_bases = od.count_bases(out["predictions"])
+        else:
+            out = od.beam_fast(om, src, lengths, beam_size=BEAM, max_length=L, min_length=min_length())
+            n_bases = sum(int((p[0] != 3).sum()) for p in out["predictions"])
         dt = time.perf_counter() - t0
         if target_s and i == 0:
             steps = max(steps, min(40, int(target_s / max(dt, 1e-3))))
         i += 1
         if i > warmup:
             times.append(dt)
-            bases += od.count_bases(out["predictions"])
+            bases += n_bases
     total = sum(times)
     return {"value": bases / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d chunks x %d steps of the same workload (oracle/ CPU port of translate_batch, fp32, "
@@ -193,6 +224,7 @@ def cpu_sample(n_chunks, steps, warmup, target_s=None):
 
 
 def run_reference(args):
+    select_workload(getattr(args, "workload", WORKLOAD))
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -220,7 +252,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gemm-mode", default="3xtf32", choices=["3xtf32", "tf32", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default=WORKLOAD, choices=sorted(WORKLOADS),
+                    help="default = BASELINE.json configs[1]; the others are the remaining BASELINE configs")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -245,7 +280,7 @@ def main():
 
     cfg, sd = model_and_weights()
     B = B_PER_GPU
-    eng = Engine(cfg, sd, max_batch=B, max_src_len=T, max_tgt_len=L, max_beam=1, gemm_mode=args.gemm_mode,
+    eng = Engine(cfg, sd, max_batch=B, max_src_len=T, max_tgt_len=L, max_beam=BEAM, gemm_mode=args.gemm_mode,
                  device=local)
     # every rank decodes its own shard of reads (different seed -> different chunks)
     chunks, lengths = synth.make_chunks(B, T=T, seed=1234 + rank, ragged=True, read_len=16)
@@ -260,7 +295,9 @@ def main():
 
     def step_device():
         eng.encode(src_d, len_d)
-        return eng.decode_greedy(L)["ids"]
+        if BEAM == 1:
+            return eng.decode_greedy(L)["ids"]
+        return eng.decode_beam(BEAM, 1, L, min_len=min_length())["ids"][:, 0, :]   # best hypothesis, -1 padded after </s>
 
     # the clock sampler runs from before the warm-up (no idle gap in front of the timed region: the GPU
     # would drop its clocks and the first timed step would pay the ramp); only samples taken inside the
@@ -269,7 +306,7 @@ def main():
     if rank == 0:
         sampler.start()
     def count_bases_dev(ids):
-        is_eos = ids.eq(3)
+        is_eos = ids.eq(3) | ids.lt(0)
         first = torch.where(is_eos.any(1), is_eos.float().argmax(1), torch.full_like(ids[:, 0], L))
         return first.sum()
 
@@ -306,7 +343,7 @@ def main():
     clocks = sampler.stop((t_region0, t_region1)) if rank == 0 else None
     # ---------------- per-kernel pass for the roofline entry: same steps with CUDA-event brackets around
     # every launch of the dominant kernel (the engine then runs the decode loop on one stream, eagerly)
-    eng.profile_enable(["cross_attn"])
+    eng.profile_enable([ROOF_CAT])
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record()
     for _ in range(max(1, min(args.steps, 3))):
@@ -327,8 +364,8 @@ def main():
     value = bases_total / (ms_max / 1e3)
 
     # ---------------- timed region 2: end to end through the public API with HOST buffers
-    opt = default_translate_opt(beam_size=1, batch_size=B, max_length=L, src_seq_length=T, gpu=local,
-                                gemm_mode=args.gemm_mode)
+    opt = default_translate_opt(beam_size=BEAM, fast=BEAM > 1, batch_size=B, max_length=L, min_length=min_length(),
+                                src_seq_length=T, gpu=local, gemm_mode=args.gemm_mode)
     tr = Translator(eng, {"tgt": _Field(Vocab(cfg.vocab))}, opt, cfg)
     h_chunks, h_len = chunks.pin_memory(), lengths
     tr.translate(src=(h_chunks, h_len), batch_size=B)               # warm
@@ -355,17 +392,21 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        ca_ms, ca_n = prof.get("cross_attn", (0.0, 0))
+        ca_ms, ca_n = prof.get(ROOF_CAT, (0.0, 0))
         d = cfg.d_model
-        # algorithmic bytes per launch: K and V of every chunk once (2*T*d*4) + q in + ctx out
-        bytes_per_launch = B * (2 * T * d * 4 + 2 * d * 4)
+        # algorithmic bytes per launch: K and V (or uh and H, or keys and values of the conv attention) of every
+        # chunk once (2*T*d*4) + query in + context out per row; beams of a chunk share the K/V pass
+        bytes_per_launch = B * (2 * T * d * 4 + 2 * BEAM * d * 4)
         achieved = bytes_per_launch / (ca_ms / max(ca_n, 1) * 1e-3) / 1e9 if ca_n else None
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "cross_attn_traffic.json")))["dram_bytes_per_launch"]
+            if WORKLOAD == "l2t_greedy_b1024":
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "cross_attn_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
-        roofline = {"kernel": "cross_attn_kernel<8,1> (decode cross-attention, fp32 K/V)", "bound": "hbm",
+        kname = {"cross_attn": "cross_attn_kernel<%d,%d> (decode cross-attention, fp32 K/V)" % (d // 32, 1 if BEAM == 1 else 8),
+                 "mlp_attn": "mlp_attn_kernel<%d,1> (decode global / conv attention, fp32)" % (d // 32)}[ROOF_CAT]
+        roofline = {"kernel": kname, "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
@@ -383,6 +424,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * T * 4 + B * 8),
                         "d2h_bytes_per_step": int(B * L * 8 + B * 4),
                         "api": "Translator.translate(src=(pinned chunks, lengths), batch_size=1024) -> base strings"},
+                "n_model_params": int(sum(v.numel() for v in sd.values() if torch.is_floating_point(v))),
                 "gpu_launches": int(tot[1].item()), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_sample(50, 2, 1, target_s=15.0).items()

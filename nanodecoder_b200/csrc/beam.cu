@@ -61,7 +61,10 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
   if (obj && p.step >= *p.st.stop_step) {              // every Beam was done before this step (translator.py:883-884)
     // the loop has ended: from the next step on every per-chunk kernel skips this chunk (its ancestor tables
     // are no longer extended, so the attention kernels must not walk them)
-    if (lane == 0) p.st.retired[b] = 1;
+    if (lane == 0) {
+      p.st.retired[b] = 1;
+      if (bl == 0) *p.st.n_alive = 0;                // the projections of the remaining steps return at once
+    }
     return;
   }
   const int K = p.K, V = p.V, NC = K * V, Lp1 = p.Lmax + 1;

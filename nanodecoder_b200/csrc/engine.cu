@@ -127,6 +127,7 @@ struct nd_engine {
   // 0 (default): K/V cross attention, HBM-bound at 96 % of the measured peak.  1: greedy decode reads the memory
   // bank once per layer-step (half the bytes, 8x the fp32 FMAs): measured 253 us (v2) vs 171 us per launch at d = 256
   // (profiles/r01_cross_mb_experiment.md) -- kept as an option until its FFMA side is as good as its byte count
+  const int* gemm_alive = nullptr;         // set while a beam search runs: GEMMs return at once when it reads 0
   int cross_mode = 0;
   int enc_attn_tc = 1;                     // Transformer-encoder self attention on the tensor cores when dh = 32
   int* cur_tok = nullptr;
@@ -287,6 +288,7 @@ int run_gemm(nd_engine* e, const Lin& l, const float* A, int64_t lda, float* C, 
   p.A = A; p.lda = lda; p.C = C; p.ldc = ldc; p.M = (int)M; p.N = l.N; p.K = l.K; p.ldw = l.ld;
   p.bias = l.b; p.prologue = o.prologue; p.pg = o.pg; p.pb = o.pb; p.eps = o.eps; p.relu = o.act;
   p.residual = o.residual; p.ldr = o.ldr; p.div_by = o.div_by; p.div_ncols = o.div_ncols;
+  p.alive = e->gemm_alive;
   const bool tma_ok = (lda % 4 == 0) && (l.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(l.W) & 15) == 0) && l.K >= 8;
   if (tc_mode(e) && tma_ok && l.W_hi) {
@@ -1083,6 +1085,9 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
   ND_LAUNCH(e, beam_init(bp, 2, st));
   const int G = n_groups(e, B);
   if (G > 1) ND_TRY(fork_streams(e, st, G));
+  // once every chunk has retired (fast) / every Beam is done (object) the remaining steps only cost their launches
+  struct AliveScope { nd_engine* e; ~AliveScope() { e->gemm_alive = nullptr; } } alive_scope{e};
+  e->gemm_alive = e->beam.n_alive;
   for (int step = 0; step < max_len; ++step) {
     for (int g = 0; g < G; ++g) {
       cudaStream_t gs = G > 1 ? e->streams[g] : st;

@@ -30,6 +30,9 @@ struct GemmParams {
   //   dvec[n] = sum_k W[n,k] beta[k] + bias[n].  Row mean / rstd are accumulated from the A tiles
   //   as they stream through shared memory (no extra pass over A).
   const float* ln_cvec = nullptr; const float* ln_dvec = nullptr;
+  // optional device counter: when it reads 0 the whole GEMM returns at once (beam search: every chunk of the batch
+  // has retired, the remaining steps of the captured loop only cost their launches)
+  const int* alive = nullptr;
   long long* dbg = nullptr;      // optional [32] clock64() timeline written by CTA 0 (tuning aid)
 };
 

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmParams p) {
   __shared__ float s_mean[BM], s_rstd[BM];
 
   const int tid = threadIdx.x;
+  if (p.alive && *p.alive == 0) return;          // uniform over the grid (see GemmParams::alive)
   // 1-D grid, n-tile fastest: CTAs that share an A row block run in the same wave (L2 reuse)
   const int ntn = (p.N + BN - 1) / BN;
   const int m0 = (blockIdx.x / ntn) * BM, n0 = (blockIdx.x % ntn) * BN;

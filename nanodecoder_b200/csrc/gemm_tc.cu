@@ -240,6 +240,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
   auto issue_tma = [&](int i) { issue_w(i); issue_a(i); };
   pdl_launch_dependents();                     // the next kernel's prologue may overlap this kernel
+  if (p.alive) {                               // uniform over the grid: nothing has been set up yet
+    pdl_wait();
+    if (*p.alive == 0) return;
+  }
 
   int tma_issued = 0;
   if (warp == kTmaWarp && lane == 0) {
@@ -629,6 +633,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int ntn = (p.N + BN - 1) / BN;
   const int KB = (p.K + BK - 1) / BK;
   const bool fold = p.ln_cvec != nullptr;
+  if (p.alive && *p.alive == 0) return;        // uniform over the grid (see GemmParams::alive)
 
   auto a_hi = [&](int s) { return tiles + s * C::STAGE_BYTES; };
   auto a_lo = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES; };
