@@ -159,6 +159,168 @@ __global__ void __launch_bounds__(kAttnThreads) cross_attn_kernel(CrossAttnParam
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Beam-search variant for d = 256, H = 8 (the K beams of a chunk share ONE pass over its K / V).  The generic kernel
+// above re-reads the queries from shared memory for every row and all-reduces every (query, row) score over the 4
+// lanes of a head (606 us at K = 5 vs 171 us for one query).  Here a warp works on blocks of 4 rows:
+//   * the next block's K (or V) rows are requested before the current block is consumed (register double buffer),
+//   * per query the 4 x 4 (lane, row) partial sums are reduce-scattered with 3 shuffles: lane j of a head group ends
+//     with the complete score of row j and writes it (every lane stores, no predication),
+//   * the probabilities of a block come back as one LDS.128 per query.
+template <int NQT>
+__global__ void __launch_bounds__(kAttnThreads) cross_attn_beam_kernel(CrossAttnParams p) {
+  constexpr int VPL = 8, d = 256, H = 8, LPH = 4;
+  extern __shared__ __align__(16) float smem_f[];
+  const int chunk = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (p.retired && p.retired[chunk]) return;
+  const int T = p.T, NQ = p.NQ;
+  const int TS = (T + 7) & ~3;                     // row stride of the score matrix: multiple of 4 (LDS.128), >= T + 4
+  float* q_s = smem_f;                             // [NQ][d]
+  float* sc = q_s + NQ * d;                        // [NQ*H][TS]   (later reused as red[warps][NQ*d])
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = lane / LPH, j4 = lane & 3;
+
+  for (int i = threadIdx.x; i < NQ * d; i += kAttnThreads) {
+    const int qi = i / d, c = i - qi * d;
+    q_s[i] = p.q[((int64_t)chunk * NQ + qi) * p.q_ld + c] / p.q_div;
+  }
+  __syncthreads();
+  const float* Kb = p.K + (int64_t)chunk * T * p.kv_ld + lane * VPL;
+  const float* Vb = p.V + (int64_t)chunk * T * p.kv_ld + lane * VPL;
+  const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
+  const int nblk = (T + 3) >> 2;                   // blocks of 4 rows; block b belongs to warp b % 8
+
+  auto load_block = [&](const float* base, int blk, float (&r)[4][VPL]) {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int t = blk * 4 + rr;
+      if (t < T) {
+        ldg_stream8(base + (int64_t)t * p.kv_ld, r[rr]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) r[rr][i] = 0.f;
+      }
+    }
+  };
+
+  // ---------------- phase 1: scores
+  {
+    float cur[4][VPL], nxt[4][VPL];
+    int blk = warp;
+    if (blk < nblk) load_block(Kb, blk, cur);
+    for (; blk < nblk; blk += kAttnWarps) {
+      const int nb = blk + kAttnWarps;
+      if (nb < nblk) load_block(Kb, nb, nxt);
+      const int t = blk * 4 + j4;                  // the row whose complete scores this lane ends up with
+      const bool masked = srow && t < T && (srow[t] == p.mask_value);
+#pragma unroll
+      for (int qi = 0; qi < NQT; ++qi) {
+        if (qi < NQ) {
+          const float4 qa = *reinterpret_cast<const float4*>(q_s + qi * d + lane * VPL);
+          const float4 qb = *reinterpret_cast<const float4*>(q_s + qi * d + lane * VPL + 4);
+          float v[4];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+            v[rr] = fmaf(qa.x, cur[rr][0], fmaf(qa.y, cur[rr][1], fmaf(qa.z, cur[rr][2], fmaf(qa.w, cur[rr][3],
+                    fmaf(qb.x, cur[rr][4], fmaf(qb.y, cur[rr][5], fmaf(qb.z, cur[rr][6], qb.w * cur[rr][7])))))));
+          // reduce-scatter over the 4 lanes of the head: lane j4 keeps row j4
+          const bool up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+          const float a0 = (up2 ? v[2] : v[0]) + __shfl_xor_sync(ND_FULL, up2 ? v[0] : v[2], 2);
+          const float a1 = (up2 ? v[3] : v[1]) + __shfl_xor_sync(ND_FULL, up2 ? v[1] : v[3], 2);
+          const float sres = (up1 ? a1 : a0) + __shfl_xor_sync(ND_FULL, up1 ? a0 : a1, 1);
+          if (t < T) sc[(qi * H + head) * TS + t] = masked ? -1e18f : sres;
+        }
+      }
+      if (nb < nblk) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) cur[rr][i] = nxt[rr][i];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: softmax rows (torch.softmax: exp(x - max) / sum); pad the tail of each row with zeros
+  for (int row = warp; row < NQ * H; row += kAttnWarps) {
+    float* srw = sc + row * TS;
+    float m = -FLT_MAX;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, srw[t]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) { const float e = expf(srw[t] - m); srw[t] = e; sum += e; }
+    sum = warp_sum(sum);
+    for (int t = lane; t < T; t += 32) srw[t] = srw[t] / sum;
+    for (int t = T + lane; t < TS; t += 32) srw[t] = 0.f;
+    if (p.attn && (row % H) == 0) {
+      float* a = p.attn + ((int64_t)chunk * NQ + row / H) * T;
+      for (int t = lane; t < T; t += 32) a[t] = srw[t];
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3: context
+  float acc[NQT][VPL];
+#pragma unroll
+  for (int qi = 0; qi < NQT; ++qi)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[qi][i] = 0.f;
+  {
+    float cur[4][VPL], nxt[4][VPL];
+    int blk = warp;
+    if (blk < nblk) load_block(Vb, blk, cur);
+    for (; blk < nblk; blk += kAttnWarps) {
+      const int nb = blk + kAttnWarps;
+      if (nb < nblk) load_block(Vb, nb, nxt);
+#pragma unroll
+      for (int qi = 0; qi < NQT; ++qi) {
+        if (qi < NQ) {
+          const float4 pr = *reinterpret_cast<const float4*>(sc + (qi * H + head) * TS + blk * 4);
+#pragma unroll
+          for (int i = 0; i < VPL; ++i)
+            acc[qi][i] = fmaf(pr.x, cur[0][i], fmaf(pr.y, cur[1][i], fmaf(pr.z, cur[2][i], fmaf(pr.w, cur[3][i], acc[qi][i]))));
+        }
+      }
+      if (nb < nblk) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) cur[rr][i] = nxt[rr][i];
+      }
+    }
+  }
+  __syncthreads();                                 // scores no longer needed: reuse as reduction buffer
+  float* red = sc;                                 // [warps][NQ*d]
+#pragma unroll
+  for (int qi = 0; qi < NQT; ++qi) {
+    if (qi < NQ) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) red[(warp * NQ + qi) * d + lane * VPL + i] = acc[qi][i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * d; i += kAttnThreads) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) sum += red[w * NQ * d + i];
+    const int qi = i / d, c = i - qi * d;
+    p.ctx[((int64_t)chunk * NQ + qi) * p.ctx_ld + c] = sum;
+  }
+}
+
+template <int NQT>
+cudaError_t launch_cross_beam(const CrossAttnParams& p, cudaStream_t stream) {
+  const int TS = (p.T + 7) & ~3;
+  const size_t sc_f = (size_t)p.NQ * 8 * TS;
+  const size_t red_f = (size_t)kAttnWarps * p.NQ * 256;
+  const size_t smem = ((size_t)p.NQ * 256 + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
+  cudaFuncSetAttribute(cross_attn_beam_kernel<NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  launch_k(cross_attn_beam_kernel<NQT>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
+  return cudaGetLastError();
+}
+
 template <int VPL>
 cudaError_t launch_cross(const CrossAttnParams& p, cudaStream_t stream) {
   const int d = 32 * VPL;
@@ -177,9 +339,18 @@ cudaError_t launch_cross(const CrossAttnParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+int g_cross_beam_kernel = 1;      // 0: the generic kernel also for several queries per chunk (cross-check)
+void cross_attention_set_beam_kernel(int on) { g_cross_beam_kernel = on; }
+
 cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream) {
   if (p.n_chunks <= 0) return cudaSuccess;
   if (p.d % 32 || 32 % p.H || p.NQ > 8 || p.NQ < 1 || (p.d / p.H) % (p.d / 32)) return cudaErrorInvalidValue;
+  if (g_cross_beam_kernel && p.NQ > 1 && p.d == 256 && p.H == 8 && (p.kv_ld % 8) == 0 &&
+      (reinterpret_cast<uintptr_t>(p.K) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.V) & 31) == 0) {
+    if (p.NQ <= 4) return launch_cross_beam<4>(p, stream);
+    if (p.NQ == 5) return launch_cross_beam<5>(p, stream);
+    return launch_cross_beam<8>(p, stream);
+  }
   switch (p.d / 32) {
     case 1: return launch_cross<1>(p, stream);
     case 2: return launch_cross<2>(p, stream);

@@ -1434,6 +1434,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     e->cross_mode = value != 0;
     return ND_OK;
   }
+  if (strcmp(name, "cross_beam_kernel") == 0) {   // process-wide
+    cross_attention_set_beam_kernel(value != 0);
+    return ND_OK;
+  }
   if (strcmp(name, "enc_attn_tc") == 0) {
     e->enc_attn_tc = value != 0;
     return ND_OK;

@@ -23,6 +23,7 @@ struct CrossAttnParams {
   int n_chunks = 0, NQ = 1, T = 0, d = 0, H = 8;
 };
 cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream);
+void cross_attention_set_beam_kernel(int on);   // 1 (default): block-of-4-rows kernel for several queries per chunk at d = 256
 
 // Greedy-decode cross attention in MEMORY-BANK space (one query per chunk).  With K = mb Wk^T + bk and
 // V = mb Wv^T + bv (multi_headed_attn.py:142-153) the per-head score and context are, in exact arithmetic,
