@@ -374,7 +374,7 @@ def main():
     e2e_bases = 0
     for _ in range(args.steps):
         _, preds = tr.translate(src=(h_chunks, h_len), batch_size=B)
-        e2e_bases += sum(len(p[0].split()) for p in preds)
+        e2e_bases += sum((p[0].count(" ") + 1) if p[0] else 0 for p in preds)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

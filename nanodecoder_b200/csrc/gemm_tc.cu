@@ -36,7 +36,7 @@ constexpr int kTmaWarp = kConvWarps, kMmaWarp = kConvWarps + 1;
 constexpr int kThreads = kConvThreads + 64;
 constexpr int A_TILE_BYTES = BM * 128;
 
-template <int BN, int NPASS, int S>
+template <int BN, int NPASS, int S, int Q = 1>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_TILE_BYTES * (NPASS == 3 ? 2 : 1) + B_TILE_BYTES * (NPASS == 3 ? 2 : 1);
@@ -45,9 +45,12 @@ struct Cfg {
   static constexpr int kStagesFit = (200 * 1024 - RECV_BYTES) / STAGE_BYTES;
   static constexpr int kStages = kStagesFit >= 6 ? 6 : kStagesFit;
   static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BM * 4 /*row stats*/ + 2 * BN * 4 /*epilogue vectors*/ +
-                                   6 * BM * 4 /*half-row moments*/;
+                                   Q * 6 * BM * 4 /*half-row moments (per serial K slice)*/;
   static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + RECV_BYTES + 1024 /*align*/ + AUX_BYTES;
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int ACC_COLS = Q * BN;                            // one accumulator per serial K slice
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
+  static_assert(Q == 1 || S == 1, "serial K slices replace the cluster split");
+  static_assert(ACC_COLS <= 512, "tensor memory");
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -188,11 +191,15 @@ __device__ __forceinline__ void epilogue_rowwise(const GemmParams& p, float (&v)
 
 // ------------------------------------------------------------------------------------ kernel
 // warps 0-7: converters + epilogue, warp 8: TMA producer, warp 9: TMEM owner + MMA issuer
-template <int BN, int NPASS, int S>
+// Q > 1 ("serial split", S == 1): ONE CTA walks the whole K range but keeps the Q K-slices of the cluster split in Q
+// separate accumulators (and Q separate sets of LayerNorm moments) and adds them in the cluster kernel's order, so
+// the result is bit-identical to gemm_tc_kernel<*, NPASS, Q> whatever the tile width.  Used when there are enough
+// rows (beam search: beam x batch) that the cluster split would run several waves of short CTAs.
+template <int BN, int NPASS, int S, int Q = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, GemmParams p) {
-  using C = Cfg<BN, NPASS, S>;
+  using C = Cfg<BN, NPASS, S, Q>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by SWIZZLE_128B operand tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -221,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_per = KBtot / S;                       // launcher guarantees KBtot % S == 0
   const int kb0 = crank * kb_per;
   const int KB = kb_per;
+  const int kb_q = KB / Q;                            // k-blocks per serial slice (launcher: KBtot % Q == 0)
   constexpr int PS = C::PS;
 
   auto a_hi = [&](int s) { return tiles + s * C::STAGE_BYTES; };
@@ -320,13 +328,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K=8 step inside the swizzle row
-          const uint32_t first = (i == 0 && k == 0) ? 0u : 1u;
+          const uint32_t first = ((Q > 1 ? i % kb_q : i) == 0 && k == 0) ? 0u : 1u;
+          const uint32_t acc_t = Q > 1 ? tmem_base + (uint32_t)((i / kb_q) * BN) : tmem_base;
           if (NPASS == 3) {
-            umma_tf32(tmem_base, dal + adv, dbh + adv, idesc, first);
-            umma_tf32(tmem_base, dah + adv, dbl + adv, idesc, 1u);
-            umma_tf32(tmem_base, dah + adv, dbh + adv, idesc, 1u);
+            umma_tf32(acc_t, dal + adv, dbh + adv, idesc, first);
+            umma_tf32(acc_t, dah + adv, dbl + adv, idesc, 1u);
+            umma_tf32(acc_t, dah + adv, dbh + adv, idesc, 1u);
           } else {
-            umma_tf32(tmem_base, dah + adv, dbh + adv, idesc, first);
+            umma_tf32(acc_t, dah + adv, dbh + adv, idesc, first);
           }
         }
         umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
@@ -355,7 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4 vin[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) vin[c] = *reinterpret_cast<float4*>(rh + (((4 * half + c) ^ sw) << 4));
-        if (fold && i == 0) x0 = vin[0].x;      // shift = first element of THIS thread's share (race free)
+        if (fold && (Q > 1 ? i % kb_q : i) == 0) x0 = vin[0].x;   // shift = first element of THIS thread's share (race free)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {           // logical 16-byte chunk lc lives at physical chunk lc ^ (row & 7)
           const int lc = 4 * half + c;
@@ -388,12 +397,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       mbar_arrive(&conv_full[s]);
       if (threadIdx.x == 0 && i == 0) ND_TS(7);
+      if constexpr (Q > 1) {
+        if (fold && (i + 1) % kb_q == 0) {      // end of a serial K slice: park its half-row moments, start afresh
+          float mean_h = 0.f, m2_h = 0.f;
+          if (cnt > 0) {
+            const float ds = s1 / (float)cnt;
+            mean_h = x0 + ds;
+            m2_h = fmaxf(s2 - s1 * ds, 0.f);
+          }
+          float* mo = s_mom + (((i / kb_q) * 2 + half) * BM + row) * 3;
+          mo[0] = (float)cnt; mo[1] = mean_h; mo[2] = m2_h;
+          cnt = 0; s1 = 0.f; s2 = 0.f;
+        }
+      }
     }
     if (threadIdx.x == 0) ND_TS(8);
     // each thread: (cnt, mean, M2) of its half-row share; combine the two halves (Chan et al.) into the
     // moments of this CTA's K slice
     float mean_s = 0.f, m2_s = 0.f;
-    if (fold) {
+    if constexpr (Q > 1) {
+      if (fold) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kConvThreads) : "memory");
+        float mean_all = 0.f, m2_all = 0.f;
+        int n_all = 0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {            // same two-level combination as the cluster kernel (halves, then slices)
+          const float* a = s_mom + ((q * 2 + 0) * BM + row) * 3;
+          const float* b = s_mom + ((q * 2 + 1) * BM + row) * 3;
+          const float na = a[0], nb = b[0], nt = na + nb;
+          float mu = 0.f, mm = 0.f;
+          if (nt > 0.f) {
+            const float delta = b[1] - a[1];
+            mu = a[1] + delta * (nb / nt);
+            mm = a[2] + b[2] + delta * delta * (na * nb / nt);
+          }
+          const int k_lo = q * kb_q * BK;
+          const int nn = max(0, min(p.K, k_lo + kb_q * BK) - k_lo);
+          if (nn > 0) {
+            const float delta = mu - mean_all;
+            const int ntot = n_all + nn;
+            mean_all += delta * ((float)nn / (float)ntot);
+            m2_all += mm + delta * delta * ((float)n_all * (float)nn / (float)ntot);
+            n_all = ntot;
+          }
+        }
+        mean_s = mean_all;
+        m2_s = m2_all;
+      }
+    } else if (fold) {
       float mean_h = 0.f, m2_h = 0.f;
       if (cnt > 0) {
         const float ds = s1 / (float)cnt;
@@ -436,7 +487,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c0 = chalf * HC + cb;
         const int nb = n0 + c0;
         float v[32];
-        tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);     // warp-collective: all lanes participate
+        if constexpr (Q == 1) {
+          tmem_ld32(tmem_base + lane_base + (uint32_t)c0, v);   // warp-collective: all lanes participate
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {          // slice order of the cluster reduction -> bitwise the same sum
+            float t[32];
+            tmem_ld32(tmem_base + lane_base + (uint32_t)(q * BN + c0), t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += t[j];
+          }
+        }
         if (vec_ok && nb + 32 <= p.N) {
           // residual rows in flight while the row-wise math runs (4 rows x 128 B per instruction)
           float4 res[8];
@@ -909,13 +972,13 @@ bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, i
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int NPASS, int S>
+template <int BN, int NPASS, int S, int Q = 1>
 cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN, NPASS, S>;
+  using C = Cfg<BN, NPASS, S, Q>;
   static PerDeviceFlag attr_flag;
   bool& attr_set = attr_flag.cur();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, S, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -941,10 +1004,11 @@ cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NPASS, S>, tmA, tmWhi, tmWlo, pp);
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NPASS, S, Q>, tmA, tmWhi, tmWlo, pp);
 }
 
 int g_persist = 1;       // 0: always one tile per CTA (experiments / cross-check)
+int g_serial_split = 1;  // 0: cluster split-K also for many rows (cross-check: results are bit-identical)
 int g_n_sm = 0;
 
 template <int BN, int NPASS>
@@ -989,6 +1053,10 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
   // many tiles per SM: the persistent kernel (pipeline never drains, epilogue overlapped)
   if (g_persist && split == 1 && p.N > 64 && tiles128 >= 200) return launch_persist<128, NPASS>(p, stream);
   if (split == 1 && tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
+  // many rows (beam x batch): the cluster split would run several waves of short CTAs; one CTA per 128 x 128 tile
+  // with the K slices in separate accumulators gives the same bits in one wave
+  if (g_serial_split && split > 1 && p.M >= 2048)
+    return split == 4 ? launch<128, NPASS, 1, 4>(p, stream) : launch<128, NPASS, 1, 2>(p, stream);
   switch (split) {
     case 4: return launch<64, NPASS, 4>(p, stream);
     case 2: return launch<64, NPASS, 2>(p, stream);
@@ -1000,6 +1068,7 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
 
 void gemm_tc_set_debug(long long* dev_buf) { g_dbg = dev_buf; }
 void gemm_tc_set_persistent(int on) { g_persist = on; }
+void gemm_tc_set_serial_split(int on) { g_serial_split = on; }
 
 bool gemm_tc_available(const char** why) {
   const bool ok = lookup();

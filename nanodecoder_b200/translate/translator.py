@@ -56,6 +56,27 @@ class GNMTGlobalScorer(object):
         self.coverage_penalty = getattr(opt, "coverage_penalty", "none")
 
 
+def join_tokens(ids: np.ndarray, cut: np.ndarray, itos) -> List[List[str]]:
+    """ids [B,n_best,L] token ids, cut [B,n_best] hypothesis lengths -> [[" ".join(tokens)] * n_best] * B, the strings
+    ``TranslationBuilder`` produces (translation.py:27-41 + translator.py:271-273).  When every emitted token is a
+    single character (the bases) the whole batch is laid out as ONE byte buffer "A C G T ..." and sliced; any other
+    token inside a hypothesis (<unk>, <s> ...) takes the per-hypothesis join."""
+    B, N, L = ids.shape
+    codes = np.array([ord(t) if len(t) == 1 and ord(t) < 128 else 0 for t in itos], dtype=np.uint8)
+    c = codes[ids]
+    live = np.arange(L)[None, None, :] < cut[:, :, None]
+    if L == 0 or bool(((c == 0) & live).any()):
+        itos_a = np.array(list(itos), dtype=object)
+        return [[" ".join(itos_a[ids[j, n, : cut[j, n]]]) for n in range(N)] for j in range(B)]
+    buf = np.full((B, N, 2 * L), 32, dtype=np.uint8)
+    buf[:, :, 0::2] = np.where(live, c, 32)
+    raw = buf.tobytes().decode("ascii")
+    W = 2 * L
+    cl = cut.reshape(-1).tolist()
+    flat = [raw[i * W: i * W + max(2 * cl[i] - 1, 0)] for i in range(B * N)]
+    return [flat[j * N: (j + 1) * N] for j in range(B)]
+
+
 def build_translator(opt, report_score=False, logger=None, out_file=None):
     """translate/translator.py:65-90.  ``opt`` comes from nanodecoder_b200.opts.translate_opts."""
     if len(opt.models) != 1:
@@ -151,10 +172,11 @@ class Translator(object):
                 pos = np.arange(ids.shape[2])[None, None, :]
                 is_end = is_eos | (pos >= lens[:, :, None])
                 cut = np.where(is_end.any(2), is_end.argmax(2), ids.shape[2])
-                for j in range(len(idx)):
-                    i = int(idx[j])
-                    all_scores[i] = [scores[j, n] for n in range(self.n_best)]
-                    all_predictions[i] = [" ".join(itos[ids[j, n, : cut[j, n]]]) for n in range(self.n_best)]
+                strings = join_tokens(ids[:, : self.n_best], cut[:, : self.n_best], itos)
+                score_rows = scores[:, : self.n_best].unbind(0)     # per chunk: n_best 0-d tensors when iterated
+                for j, i in enumerate(idx.tolist()):
+                    all_scores[i] = score_rows[j]
+                    all_predictions[i] = strings[j]
                 pred_score_total += float(scores[:, 0].sum())
                 pred_words_total += int(cut[:, 0].sum())
                 continue

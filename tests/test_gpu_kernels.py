@@ -169,8 +169,9 @@ def test_transformer_encoder_attention_tensor_core_vs_ffma_and_oracle(T, d):
 
 @pytest.mark.parametrize("N,K,ln", [(256, 256, True), (256, 256, False), (256, 2048, False), (512, 512, True)])
 def test_gemm_split_k_many_row_tiles_is_batch_invariant(small_engine, N, K, ln):
-    """Split-K shapes with many rows (beam search: M = 5 x batch): a cluster walks several row tiles.  The split factor
-    and the summation order depend on (N, K) only, so the first 1024 rows must be BIT-identical to a 1024-row call."""
+    """Split-K shapes with many rows (beam search: M = 5 x batch) run the K slices of the cluster split as separate
+    accumulators of ONE CTA per 128 x 128 tile.  The summation order depends on (N, K) only, so the first 1024 rows must
+    be BIT-identical to a 1024-row call (cluster split-K kernel) and to the cluster kernel run on all rows."""
     g = torch.Generator().manual_seed(N + K)
     M = 5121
     A = (torch.randn(M, K, generator=g) * 1.3 + 0.2).cuda()
@@ -182,8 +183,14 @@ def test_gemm_split_k_many_row_tiles_is_batch_invariant(small_engine, N, K, ln):
     lnp = (gam, bet) if ln else None
     full = small_engine.test_gemm("3xtf32", A, W, bias=bias, residual=res, ln=lnp)
     part = small_engine.test_gemm("3xtf32", A[:1024].contiguous(), W, bias=bias, residual=res[:1024].contiguous(), ln=lnp)
+    small_engine.set_option("gemm_serial_split", 0)
+    try:
+        clus = small_engine.test_gemm("3xtf32", A, W, bias=bias, residual=res, ln=lnp)
+    finally:
+        small_engine.set_option("gemm_serial_split", 1)
     torch.cuda.synchronize()
     An = torch.nn.functional.layer_norm(A.double(), (K,), gam.double(), bet.double(), 1e-6) if ln else A.double()
     ref = An @ W.double().t() + bias.double() + res.double()
     assert rel_err(full, ref) < 1e-5, rel_err(full, ref)
     assert torch.equal(full[:1024], part)
+    assert torch.equal(full, clus)
