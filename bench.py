@@ -404,7 +404,10 @@ def main():
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "cross_attn_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
-        kname = {"cross_attn": "cross_attn_kernel<%d,%d> (decode cross-attention, fp32 K/V)" % (d // 32, 1 if BEAM == 1 else 8),
+        ca_name = ("cross_attn_kernel<%d,1>" % (d // 32) if BEAM == 1 else
+                   ("cross_attn_ring_kernel<%d,%d>" % ((4 if BEAM <= 4 else 5), 2) if d == 256 and BEAM <= 5 else
+                    "cross_attn_ring_kernel<8,1>" if d == 256 else "cross_attn_kernel<%d,8>" % (d // 32)))
+        kname = {"cross_attn": ca_name + " (decode cross-attention, fp32 K/V)",
                  "mlp_attn": "mlp_attn_kernel<%d,1> (decode global / conv attention, fp32)" % (d // 32)}[ROOF_CAT]
         roofline = {"kernel": kname, "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s",

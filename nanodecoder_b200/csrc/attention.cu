@@ -339,12 +339,15 @@ cudaError_t launch_cross(const CrossAttnParams& p, cudaStream_t stream) {
 
 }  // namespace
 
-int g_cross_beam_kernel = 1;      // 0: the generic kernel also for several queries per chunk (cross-check)
+// several queries per chunk at d = 256: 2 = persistent shared-memory-ring kernel (cross_attn_ring.cu), 1 = register
+// prefetch kernel above, 0 = the generic kernel (cross-checks)
+int g_cross_beam_kernel = 2;
 void cross_attention_set_beam_kernel(int on) { g_cross_beam_kernel = on; }
 
 cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream) {
   if (p.n_chunks <= 0) return cudaSuccess;
   if (p.d % 32 || 32 % p.H || p.NQ > 8 || p.NQ < 1 || (p.d / p.H) % (p.d / 32)) return cudaErrorInvalidValue;
+  if (g_cross_beam_kernel == 2 && cross_attention_ring_supported(p)) return cross_attention_ring(p, stream);
   if (g_cross_beam_kernel && p.NQ > 1 && p.d == 256 && p.H == 8 && (p.kv_ld % 8) == 0 &&
       (reinterpret_cast<uintptr_t>(p.K) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.V) & 31) == 0) {
     if (p.NQ <= 4) return launch_cross_beam<4>(p, stream);

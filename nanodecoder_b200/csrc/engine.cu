@@ -1438,8 +1438,12 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     gemm_tc_set_serial_split(value != 0);
     return ND_OK;
   }
+  if (strcmp(name, "cross_ring_groups") == 0) {   // process-wide: 1 or 2 groups of 8 consumer warps
+    cross_attention_ring_set_groups(value == 1 ? 1 : 2);
+    return ND_OK;
+  }
   if (strcmp(name, "cross_beam_kernel") == 0) {   // process-wide
-    cross_attention_set_beam_kernel(value != 0);
+    cross_attention_set_beam_kernel(value);
     return ND_OK;
   }
   if (strcmp(name, "enc_attn_tc") == 0) {

@@ -2,6 +2,8 @@
 //   C[M,N] = epilogue( prologue(A)[M,K] . W[N,K]^T )
 // A, W, C row-major fp32 (W is an nn.Linear weight: K contiguous).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace nd {
@@ -45,6 +47,11 @@ void gemm_tc_set_serial_split(int on);         // 1 (default): >= 2048 rows run 
 void gemm_tc_set_debug(long long* dev_buf);   // timeline buffer for subsequent gemm_tc launches (nullptr = off)
 // one-time driver entry-point lookup for tensor-map encoding; returns false if unavailable
 bool gemm_tc_available(const char** why);
+
+// un-swizzled 2-D tensor map over row-major fp32 [rows, cols] (row pitch ld elements) with a [box_rows, box_cols] box:
+// rows land densely in shared memory (box_cols * 4 bytes apart).  Used by the ring-fed attention kernel.
+bool make_plain_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    int box_cols);
 
 // split an fp32 weight into tf32 hi (low 13 mantissa bits cleared) and lo = w - hi
 void split_tf32_host(const float* w, float* hi, float* lo, size_t n);

@@ -1066,6 +1066,19 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+bool make_plain_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    int box_cols) {
+  if (!lookup()) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 void gemm_tc_set_debug(long long* dev_buf) { g_dbg = dev_buf; }
 void gemm_tc_set_persistent(int on) { g_persist = on; }
 void gemm_tc_set_serial_split(int on) { g_serial_split = on; }

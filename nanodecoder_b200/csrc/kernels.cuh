@@ -23,7 +23,12 @@ struct CrossAttnParams {
   int n_chunks = 0, NQ = 1, T = 0, d = 0, H = 8;
 };
 cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream);
-void cross_attention_set_beam_kernel(int on);   // 1 (default): block-of-4-rows kernel for several queries per chunk at d = 256
+// several queries per chunk (beam search) at d = 256, H = 8: 2 (default) persistent CTAs fed by a cp.async.bulk ring
+// (cross_attn_ring.cu), 1 register-prefetch kernel, 0 generic kernel
+void cross_attention_set_beam_kernel(int mode);
+bool cross_attention_ring_supported(const CrossAttnParams& p);
+cudaError_t cross_attention_ring(const CrossAttnParams& p, cudaStream_t stream);
+void cross_attention_ring_set_groups(int g);    // consumer warp groups of the ring kernel (2 default, 1 for > 5 queries)
 
 // Greedy-decode cross attention in MEMORY-BANK space (one query per chunk).  With K = mb Wk^T + bk and
 // V = mb Wv^T + bv (multi_headed_attn.py:142-153) the per-head score and context are, in exact arithmetic,

@@ -24,6 +24,9 @@ if os.environ.get("ND_PDL"):
     eng.set_option("pdl", int(os.environ["ND_PDL"]))
 if os.environ.get("ND_STREAMS"):
     eng.set_option("decode_streams", int(os.environ["ND_STREAMS"]))
+for kv in filter(None, os.environ.get("ND_OPTS", "").split(",")):      # e.g. ND_OPTS="cross_beam_kernel=1,pdl=0"
+    eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+MINLEN = int(os.environ.get("ND_MINLEN", "0"))
 chunks, lengths = synth.make_chunks(B, T=512, seed=1234, ragged=True, read_len=16)
 order = torch.argsort(lengths, descending=True, stable=True)
 src, lens = chunks[order].cuda(), lengths[order].cuda()
@@ -37,7 +40,7 @@ for it in range(4):
     eng.encode(src, lens)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    out = eng.decode_beam(beam, 1, 100) if beam > 1 else eng.decode_greedy(100)
+    out = eng.decode_beam(beam, 1, 100, MINLEN) if beam > 1 else eng.decode_greedy(100)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print("step %d (%s): encode %.2f ms, decode %.2f ms, %d launches" % (

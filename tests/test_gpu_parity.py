@@ -99,6 +99,34 @@ def test_cross_attention_formulations_agree(name):
     np.testing.assert_array_equal(o["ids"].cpu().numpy(), g["greedy_ids"])
 
 
+@pytest.mark.parametrize("K,T,B", [(5, 96, 70), (3, 77, 70), (8, 130, 70), (5, 512, 6), (5, 256, 300)])
+def test_beam_cross_attention_kernels_agree(K, T, B):
+    """Beam search cross attention at d = 256 has three implementations: 2 = persistent CTAs fed by a cp.async.bulk ring
+    (default), 1 = register-prefetch kernel, 0 = the generic kernel.  Same hypotheses, scores within fp32 reassociation
+    noise, for beam widths hitting each template bucket (<= 4, 5, <= 8), T not a multiple of the 32-row stage, a handful
+    of chunks (ring refills served from L2 at once: a stage released before its rows were consumed showed up here as
+    1e-3 errors) and several chunks per CTA."""
+    cfg = ModelConfig.family("l2t")
+    sd = synth.make_state_dict(cfg, seed=K + T)
+    L = 12 if T < 200 else 4
+    chunks, lengths = synth.make_chunks(B, T=T, seed=5, ragged=True, read_len=7)
+    outs = {}
+    for mode in (2, 1, 0):
+        eng = _engine(cfg, sd, B, T, L, K=K)
+        eng.set_option("cross_beam_kernel", mode)
+        try:
+            eng.encode(chunks.cuda(), lengths.cuda())
+            o = eng.decode_beam(K, K, L, L - 1)
+            torch.cuda.synchronize()
+        finally:
+            eng.set_option("cross_beam_kernel", 2)
+        outs[mode] = (o["ids"].cpu().numpy(), o["lens"].cpu().numpy(), o["scores"].cpu().numpy())
+    for mode in (2, 1):
+        np.testing.assert_array_equal(outs[mode][0], outs[0][0])
+        np.testing.assert_array_equal(outs[mode][1], outs[0][1])
+        np.testing.assert_allclose(outs[mode][2], outs[0][2], rtol=1e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("name", IMPLEMENTED)
 def test_object_beam_matches_reference_golden(name):
     """nd_decode_beam_object vs the reference's _translate_batch + onmt.translate.Beam (no --fast), n_best 2."""
