@@ -29,5 +29,7 @@ echo "=== ncu full: cross_attn, lstm, decode gemm" | tee -a $S
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cross_attn -s 310 -c 3 -o $O/${TAG}_prof_cross_attn -f python scripts/profile_step.py l2t 1 > $O/ncu_full1.log 2>&1; echo "exit $?" | tee -a $S
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lstm_tc -s 3 -c 3 -o $O/${TAG}_prof_lstm -f python scripts/profile_step.py l2t 1 > $O/ncu_full2.log 2>&1; echo "exit $?" | tee -a $S
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 1212 -c 6 -o $O/${TAG}_prof_gemm -f python scripts/profile_step.py l2t 1 > $O/ncu_full3.log 2>&1; echo "exit $?" | tee -a $S
+echo "=== ncu full: beam ring cross attention (beam 5, min_length 99)" | tee -a $S
+ND_MINLEN=99 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cross_attn_ring -s 20 -c 2 -o $O/${TAG}_prof_cross_ring -f python scripts/profile_step.py l2t 5 > $O/ncu_full4.log 2>&1; echo "exit $?" | tee -a $S
 fi
 ls -la $O | tail -25

@@ -54,7 +54,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
         "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
-for k in ("cross_attn", "lstm", "gemm", "self_attn", "generator"):
+for k in ("cross_attn", "lstm", "gemm", "self_attn", "generator", "cross_ring"):
     rep = os.path.join(G, "%s_prof_%s.ncu-rep" % (tag, k))
     if not os.path.exists(rep):
         continue
