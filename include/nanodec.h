@@ -178,7 +178,12 @@ ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int3
  *   "enc_attn_tc"    (default 1): Transformer-encoder self attention on the tensor cores (head size 32), 0 = FFMA;
  *   "lstm_variant"   (default 0, process-wide): tensor-core LSTM keeps W_hh in tensor memory (0) or shared memory (1);
  *   "cross_mode"     (default 0): 1 = greedy decode runs the cross attention in memory-bank space (opt-in, slower);
- *   "cross_mb_version" (default 2, process-wide): implementation used by cross_mode 1.                          */
+ *   "cross_mb_version" (default 2, process-wide): implementation used by cross_mode 1;
+ *   "cross_beam_kernel" (default 2, process-wide): cross attention with several beams per chunk at d = 256:
+ *                    2 = persistent TMA-ring kernel, 1 = register-prefetch kernel, 0 = generic kernel (cross-checks);
+ *   "cross_ring_groups" (default 2, process-wide): consumer warp groups of the ring kernel (2 for <= 5 beams);
+ *   "gemm_serial_split" (default 1, process-wide): projections with >= 2048 rows run the split-K sum inside one CTA
+ *                    (bit-identical to the cluster split), 0 = always the cluster split.                        */
 ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);
 
 /* per-kernel-category device timing for bench.py's roofline figures: while a category bit is set,

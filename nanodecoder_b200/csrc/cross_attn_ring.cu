@@ -93,7 +93,8 @@ cross_attn_ring_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)n_stages * kStageBytes);
   uint64_t* empty = full + kMaxStages;
   uint32_t* sink = reinterpret_cast<uint32_t*>(empty + kMaxStages);       // see release_stage (16 bytes reserved)
-  float* q_s = reinterpret_cast<float*>(empty + kMaxStages) + 4;          // [NQ][d]
+  float* msk_s = reinterpret_cast<float*>(empty + kMaxStages) + 4;        // [TS] 1.0 = masked key of this chunk
+  float* q_s = msk_s + TS;                                                // [NQ][d]
   float* sc = q_s + NQ * kD;                                   // [NQ*H][TS], later red[8 warps][NQ*d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -146,8 +147,13 @@ cross_attn_ring_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
       const int qi = i / kD, c = i - qi * kD;
       q_s[i] = p.q[((int64_t)chunk * NQ + qi) * p.q_ld + c] / p.q_div;
     }
+    {
+      // key mask of the chunk staged once: a global load per stage sat on the critical path of phase 1 (228 -> 207 us).
+      // (Requesting the NEXT chunk's queries and mask during the V pass was tried on top: no gain, 207 -> 213 us.)
+      const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
+      for (int i = threadIdx.x; i < T; i += kConsThreads) msk_s[i] = (srow && srow[i] == p.mask_value) ? 1.f : 0.f;
+    }
     cons_sync();
-    const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
 
     // ---------------- phase 1: scores
     {
@@ -165,7 +171,7 @@ cross_attn_ring_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_con
         const uint32_t c = cnt + (uint32_t)it;
         const int s = (int)(c & smask);
         const int t = it * kStageRows + ws * 4 + j4;     // the row whose finished scores this lane stores
-        const bool masked = srow && t < T && (srow[t] == p.mask_value);     // requested before the wait
+        const bool masked = msk_s[t] != 0.f;             // t < TS always; rows >= T are never stored
         mbar_wait(&full[s], (c >> sshift) & 1);
         const uint8_t* rows = ring + (size_t)s * kStageBytes + (size_t)(ws * 4) * kRowBytes + 32 * lane;
         float2 k2[4][4];
@@ -321,7 +327,7 @@ RingPlan plan(const CrossAttnParams& p, int groups) {
   const int nit = (p.T + kStageRows - 1) / kStageRows;
   const size_t TS = (size_t)nit * kStageRows + 4;
   const size_t sc_f = (size_t)p.NQ * kH * TS, red_f = (size_t)kConsWarps * p.NQ * kD;
-  const size_t fixed = 2 * kMaxStages * sizeof(uint64_t) + 16 + ((size_t)p.NQ * kD + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
+  const size_t fixed = 2 * kMaxStages * sizeof(uint64_t) + 16 + TS * sizeof(float) + ((size_t)p.NQ * kD + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
   const size_t budget = 227 * 1024 - 128;
   if (fixed + 2 * (size_t)kStageBytes > budget) return r;
   const int st = (int)((budget - fixed) / kStageBytes);
