@@ -8,9 +8,12 @@ from nanodecoder_b200.engine import Engine
 
 cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=1, dec_layers=1)
 eng = Engine(cfg, synth.make_state_dict(cfg), max_batch=8, max_src_len=64, max_tgt_len=4, gemm_mode="3xtf32")
+import os
 shapes = [(1024, 768, 256, True), (1024, 256, 256, False), (1024, 2048, 256, True), (1024, 256, 2048, False),
           (5120, 768, 256, True), (5120, 256, 256, False), (5120, 2048, 256, True), (5120, 256, 2048, False),
           (524288, 1024, 256, False), (524288, 512, 256, False), (524288, 256, 256, False)]
+if os.environ.get("ND_M"):      # e.g. ND_M=5120: only the decode shapes at that row count
+    shapes = [(int(os.environ["ND_M"]), n, k, l) for (n, k, l) in ((768, 256, True), (256, 256, False), (2048, 256, True), (256, 2048, False))]
 for (M, N, K, ln) in shapes:
     A = torch.randn(M, K, device="cuda")
     W = torch.randn(N, K, device="cuda") / K ** 0.5
