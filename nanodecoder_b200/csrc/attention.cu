@@ -317,7 +317,7 @@ cudaError_t launch_cross_beam(const CrossAttnParams& p, cudaStream_t stream) {
   const size_t red_f = (size_t)kAttnWarps * p.NQ * 256;
   const size_t smem = ((size_t)p.NQ * 256 + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
   cudaFuncSetAttribute(cross_attn_beam_kernel<NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  launch_k(cross_attn_beam_kernel<NQT>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
+  launch_k_heavy(cross_attn_beam_kernel<NQT>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   return cudaGetLastError();
 }
 
@@ -329,10 +329,10 @@ cudaError_t launch_cross(const CrossAttnParams& p, cudaStream_t stream) {
   const size_t smem = ((size_t)p.NQ * d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
   if (p.NQ == 1) {
     cudaFuncSetAttribute(cross_attn_kernel<VPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_k(cross_attn_kernel<VPL, 1>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
+    launch_k_heavy(cross_attn_kernel<VPL, 1>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   } else {
     cudaFuncSetAttribute(cross_attn_kernel<VPL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_k(cross_attn_kernel<VPL, 8>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
+    launch_k_heavy(cross_attn_kernel<VPL, 8>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   }
   return cudaGetLastError();
 }
@@ -748,7 +748,7 @@ cudaError_t cross_attention_mb(const CrossMbParams& p, cudaStream_t stream) {
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    return launch_k(cross_attn_mb2_kernel, dim3(p.n_chunks), dim3(256), smem, stream, p, nst);
+    return launch_k_heavy(cross_attn_mb2_kernel, dim3(p.n_chunks), dim3(256), smem, stream, p, nst);
   }
   constexpr int H = 8;
   const size_t tile_b = (size_t)kMbTT * p.d * sizeof(float);
@@ -765,7 +765,7 @@ cudaError_t cross_attention_mb(const CrossMbParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  return launch_k(cross_attn_mb_kernel<H>, dim3(p.n_chunks), dim3(256), smem, stream, p, nst);
+  return launch_k_heavy(cross_attn_mb_kernel<H>, dim3(p.n_chunks), dim3(256), smem, stream, p, nst);
 }
 
 // =============================================================================================
@@ -1102,10 +1102,10 @@ cudaError_t launch_mlp(const MlpAttnParams& p, cudaStream_t stream) {
   const size_t smem = ((size_t)p.NQ * d + d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
   if (p.NQ == 1) {
     cudaFuncSetAttribute(mlp_attn_kernel<VPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_k(mlp_attn_kernel<VPL, 1>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
+    launch_k_heavy(mlp_attn_kernel<VPL, 1>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   } else {
     cudaFuncSetAttribute(mlp_attn_kernel<VPL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_k(mlp_attn_kernel<VPL, 8>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
+    launch_k_heavy(mlp_attn_kernel<VPL, 8>, dim3(p.n_chunks), dim3(kAttnThreads), smem, stream, p);
   }
   return cudaGetLastError();
 }

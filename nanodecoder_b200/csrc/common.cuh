@@ -60,6 +60,8 @@ __device__ __forceinline__ float2 ldg_stream2(const float* p) {
 //                weight-tile prefetch with its tail: decode 85.6 -> 83.3 ms
 //   1            every step kernel: the 1024-CTA attention kernels become resident next to a running GEMM on the
 //                SMs it leaves free and stay badly balanced: 85.4 -> 112 ms
+//   3            the GEMMs and the small step kernels (self attention, generator, embedding, beam step, element-wise),
+//                not the chunk-per-CTA cross / MLP attention kernels
 //   0            plain stream order
 #ifndef ND_PDL_EARLY
 #define ND_PDL_EARLY 1
@@ -86,7 +88,23 @@ static inline cudaError_t launch_k(void (*kernel)(Params...), dim3 grid, dim3 bl
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl == 1 ? 1 : 0;              // g_pdl == 2: only the tcgen05 GEMM launches are dependent launches
+  cfg.numAttrs = (g_pdl == 1 || g_pdl == 3) ? 1 : 0;   // g_pdl == 2: only the tcgen05 GEMM launches are dependent launches
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+// the big HBM-bound attention kernels (one CTA per chunk): dependent launches only under g_pdl == 1
+template <class... Params, class... Args>
+static inline cudaError_t launch_k_heavy(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl == 1 ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 

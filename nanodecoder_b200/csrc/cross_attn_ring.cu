@@ -357,7 +357,7 @@ cudaError_t launch_ring(const CrossAttnParams& p, const RingPlan& pl, cudaStream
   const int64_t rows = (int64_t)p.n_chunks * p.T;
   if (!make_plain_map(&tmK, p.K, rows, kD, p.kv_ld, kStageRows, kD)) return cudaErrorInvalidValue;
   if (!make_plain_map(&tmV, p.V, rows, kD, p.kv_ld, kStageRows, kD)) return cudaErrorInvalidValue;
-  launch_k(cross_attn_ring_kernel<NQT, G>, dim3(grid), dim3(G * 256 + 32), pl.smem, stream, tmK, tmV, p, pl.stages);
+  launch_k_heavy(cross_attn_ring_kernel<NQT, G>, dim3(grid), dim3(G * 256 + 32), pl.smem, stream, tmK, tmV, p, pl.stages);
   return cudaGetLastError();
 }
 
