@@ -174,7 +174,8 @@ ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int3
  *   "pdl"            (default 2, process-wide): 2 = the tcgen05 GEMMs of the step loop are programmatic dependent
  *                    launches, 1 = every step kernel, 0 = plain stream order.
  * Kernel selection (same arithmetic contract, results agree to fp32 rounding; all are covered by parity tests):
- *   "gemm_persistent" (default 1, process-wide): large-M projections as the persistent tcgen05 kernel;
+ *   "gemm_persistent" (default 2, process-wide): large-M projections as the persistent tcgen05 kernel with the
+ *                    A operand (tf32 hi / lo parts) in tensor memory; 1 = A in shared memory, 0 = one tile per CTA;
  *   "enc_attn_tc"    (default 1): Transformer-encoder self attention on the tensor cores (head size 32), 0 = FFMA;
  *   "lstm_variant"   (default 0, process-wide): tensor-core LSTM keeps W_hh in tensor memory (0) or shared memory (1);
  *   "cross_mode"     (default 0): 1 = greedy decode runs the cross attention in memory-bank space (opt-in, slower);

@@ -1427,7 +1427,7 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     return ND_OK;
   }
   if (strcmp(name, "gemm_persistent") == 0) {   // process-wide: large-M GEMMs as a persistent kernel (default 1)
-    gemm_tc_set_persistent(value != 0);
+    gemm_tc_set_persistent(value < 0 ? 0 : (value > 2 ? 2 : (int)value));   // 2: A operand in tensor memory
     return ND_OK;
   }
   if (strcmp(name, "cross_mode") == 0) {     // 1: memory-bank-space cross attention for greedy decode, 0: K/V

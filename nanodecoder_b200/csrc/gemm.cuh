@@ -42,7 +42,8 @@ struct GemmParams {
 cudaError_t gemm_simt(const GemmParams& p, cudaStream_t stream);
 // npass: 3 = 3xTF32 (fp32 parity), 1 = single TF32
 cudaError_t gemm_tc(const GemmParams& p, int npass, cudaStream_t stream);
-void gemm_tc_set_persistent(int on);           // 1 (default): large tile counts use the persistent kernel
+void gemm_tc_set_persistent(int mode);         // large tile counts: 2 (default) persistent kernel with A in tensor memory,
+                                               // 1 persistent kernel with A in shared memory, 0 one tile per CTA
 void gemm_tc_set_serial_split(int on);         // 1 (default): >= 2048 rows run the split-K sum inside one CTA (same bits)
 void gemm_tc_set_debug(long long* dev_buf);   // timeline buffer for subsequent gemm_tc launches (nullptr = off)
 // one-time driver entry-point lookup for tensor-map encoding; returns false if unavailable

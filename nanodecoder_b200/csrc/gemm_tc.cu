@@ -115,6 +115,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (lane = row, one 32-bit column per k element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -652,29 +671,38 @@ constexpr int kPEpiThreads = kPEpiWarps * 32;
 constexpr int kPTmaWarp = kConvWarps + kPEpiWarps, kPMmaWarp = kPTmaWarp + 1;
 constexpr int kPThreads = (kPMmaWarp + 1) * 32;
 
-template <int BN, int NPASS>
+// ATM (3xTF32 only): the converters write the tf32 hi / lo parts of the A tile into TENSOR MEMORY (tcgen05.st, 64
+// columns per stage) instead of back to shared memory, and the MMAs take A from there: a third less shared-memory
+// traffic per k-block, no generic->async proxy fence, cheaper MMAs (A is not fetched through the shared-memory port).
+template <int BN, int NPASS, bool ATM = false>
 struct PCfg {
+  static_assert(!ATM || NPASS == 3, "A in tensor memory is the 3xTF32 variant");
   static constexpr int B_TILE_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES * (NPASS == 3 ? 2 : 1) + B_TILE_BYTES * (NPASS == 3 ? 2 : 1);
+  static constexpr int A_BYTES = A_TILE_BYTES * ((NPASS == 3 && !ATM) ? 2 : 1);
+  static constexpr int STAGE_BYTES = A_BYTES + B_TILE_BYTES * (NPASS == 3 ? 2 : 1);
   static constexpr int STG_BYTES = kPEpiWarps * 32 * 36 * 4;
   static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BM * 2 * 4 /*row stats x2*/ + 2 * 2 * BN * 4 /*vectors x2*/ +
                                    2 * BM * 3 * 4 /*half-row moments*/;
   static constexpr int kStagesFit = (222 * 1024 - STG_BYTES - AUX_BYTES - 1024) / STAGE_BYTES;
-  static constexpr int kStages = kStagesFit >= 6 ? 6 : kStagesFit;
+  static constexpr int kStagesCap = ATM ? (512 - 2 * BN) / 64 : 6;       // ATM: 64 tensor-memory columns per stage
+  static constexpr int kStages = kStagesFit >= kStagesCap ? kStagesCap : kStagesFit;
   static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + STG_BYTES + AUX_BYTES + 1024 /*align*/;
-  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int ACC_COLS = 2 * BN;                                 // A stages start here
+  static constexpr int NEED_COLS = ACC_COLS + (ATM ? kStages * 64 : 0);
+  static constexpr int TMEM_COLS = NEED_COLS <= 32 ? 32 : (NEED_COLS <= 64 ? 64 : (NEED_COLS <= 128 ? 128 : (NEED_COLS <= 256 ? 256 : 512)));
   static_assert(kStages >= 2, "pipeline needs two stages");
+  static_assert(NEED_COLS <= 512, "tensor memory");
 };
 
 // Measured limits (profiles/r01_gemm_persistent.md): at 150 TFLOP/s fp32-equivalent the kernel moves 7 TB/s of
 // operand tiles from L2 and ~190 KB of shared-memory traffic per k-block (the three passes re-read the hi / lo tiles).
 // Fetching ONE fp32 weight tile and splitting it on chip like the activations was tried: a third less L2 traffic,
 // but the extra converter traffic on shared memory made it 15 % slower.
-template <int BN, int NPASS>
+template <int BN, int NPASS, bool ATM = false>
 __global__ void __launch_bounds__(kPThreads, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                        const __grid_constant__ CUtensorMap tmWlo, GemmParams p, int n_tiles) {
-  using C = PCfg<BN, NPASS>;
+  using C = PCfg<BN, NPASS, ATM>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
@@ -699,8 +727,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (p.alive && *p.alive == 0) return;        // uniform over the grid (see GemmParams::alive)
 
   auto a_hi = [&](int s) { return tiles + s * C::STAGE_BYTES; };
-  auto a_lo = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES; };
-  auto b_hi = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES * (NPASS == 3 ? 2 : 1); };
+  auto a_lo = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES; };      // unused with ATM
+  auto b_hi = [&](int s) { return tiles + s * C::STAGE_BYTES + C::A_BYTES; };
   auto b_lo = [&](int s) { return b_hi(s) + C::B_TILE_BYTES; };
 
   if (warp == kPTmaWarp && lane == 0) {
@@ -767,7 +795,12 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int k = 0; k < BK / 8; ++k) {
             const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
             const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
-            if (NPASS == 3) {
+            if constexpr (ATM) {
+              const uint32_t ah = tmem_base + (uint32_t)(C::ACC_COLS + s * 64 + k * 8), al = ah + 32;
+              umma_tf32_ts(tmem_d, al, dbh + adv, idesc, first);
+              umma_tf32_ts(tmem_d, ah, dbl + adv, idesc, 1u);
+              umma_tf32_ts(tmem_d, ah, dbh + adv, idesc, 1u);
+            } else if (NPASS == 3) {
               umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, first);
               umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
               umma_tf32(tmem_d, dah + adv, dbh + adv, idesc, 1u);
@@ -801,6 +834,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
           for (int c = 0; c < 4; ++c) vin[c] = *reinterpret_cast<float4*>(rh + (((4 * half + c) ^ sw) << 4));
           if (fold && kb == 0) x0 = vin[0].x;     // shift = first element of THIS thread's share
+          uint32_t th[16], tl[16];                // ATM: this thread's 16 columns of the hi / lo tile
 #pragma unroll
           for (int c = 0; c < 4; ++c) {           // logical 16-byte chunk lc lives at physical chunk lc ^ (row & 7)
             const int lc = 4 * half + c;
@@ -824,11 +858,25 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 h[q] = __uint_as_float((__float_as_uint(x[q]) + 0x1000u) & 0xffffe000u);
                 l[q] = __uint_as_float((__float_as_uint(x[q] - h[q]) + 0x1000u) & 0xffffe000u);
               }
-              *reinterpret_cast<float4*>(rh + pc) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(rl + pc) = make_float4(l[0], l[1], l[2], l[3]);
+              if constexpr (ATM) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { th[4 * c + q] = __float_as_uint(h[q]); tl[4 * c + q] = __float_as_uint(l[q]); }
+              } else {
+                *reinterpret_cast<float4*>(rh + pc) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(rl + pc) = make_float4(l[0], l[1], l[2], l[3]);
+              }
             }
           }
-          if (NPASS == 3) fence_proxy_async();
+          if constexpr (ATM) {
+            // warp w owns tensor-memory lanes 32*(w & 3)..: exactly its rows; columns [16*half, 16*half + 16) of the stage
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(C::ACC_COLS + s * 64 + half * 16);
+            tmem_st16(ta, th);
+            tmem_st16(ta + 32, tl);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+          } else if (NPASS == 3) {
+            fence_proxy_async();
+          }
         }
         mbar_arrive(&conv_full[s]);
       }
@@ -1007,17 +1055,17 @@ cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
   return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NPASS, S, Q>, tmA, tmWhi, tmWlo, pp);
 }
 
-int g_persist = 1;       // 0: always one tile per CTA (experiments / cross-check)
+int g_persist = 2;       // 0: always one tile per CTA (cross-check), 1: persistent kernel, 2 (default): ... with A in tensor memory
 int g_serial_split = 1;  // 0: cluster split-K also for many rows (cross-check: results are bit-identical)
 int g_n_sm = 0;
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, bool ATM = false>
 cudaError_t launch_persist(const GemmParams& p, cudaStream_t stream) {
-  using C = PCfg<BN, NPASS>;
+  using C = PCfg<BN, NPASS, ATM>;
   static PerDeviceFlag attr_flag;
   bool& attr_set = attr_flag.cur();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_persist_kernel<BN, NPASS, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -1033,7 +1081,7 @@ cudaError_t launch_persist(const GemmParams& p, cudaStream_t stream) {
   if (!make_map(&tmWlo, NPASS == 3 ? p.W_lo : p.W, p.N, p.K, p.ldw, BN)) return cudaErrorInvalidValue;
   const int64_t tiles = (int64_t)cdiv(p.N, BN) * cdiv(p.M, BM);
   const int grid = (int)(tiles < g_n_sm ? tiles : g_n_sm);
-  gemm_tc_persist_kernel<BN, NPASS><<<grid, kPThreads, C::SMEM_BYTES, stream>>>(tmA, tmWhi, tmWlo, p, (int)tiles);
+  gemm_tc_persist_kernel<BN, NPASS, ATM><<<grid, kPThreads, C::SMEM_BYTES, stream>>>(tmA, tmWhi, tmWlo, p, (int)tiles);
   return cudaGetLastError();
 }
 
@@ -1051,7 +1099,12 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
     while (split < 4 && KB % (split * 2) == 0 && KB / (split * 2) >= 2 && ref_tiles * split * 2 <= 160) split *= 2;
   }
   // many tiles per SM: the persistent kernel (pipeline never drains, epilogue overlapped)
-  if (g_persist && split == 1 && p.N > 64 && tiles128 >= 200) return launch_persist<128, NPASS>(p, stream);
+  if (g_persist && split == 1 && p.N > 64 && tiles128 >= 200) {
+    if constexpr (NPASS == 3) {
+      if (g_persist == 2) return launch_persist<128, 3, true>(p, stream);      // A operand in tensor memory
+    }
+    return launch_persist<128, NPASS>(p, stream);
+  }
   if (split == 1 && tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
   // many rows (beam x batch): the cluster split would run several waves of short CTAs; one CTA per 128 x 128 tile
   // with the K slices in separate accumulators gives the same bits in one wave

@@ -34,6 +34,9 @@ def test_gemm_plain(small_engine, mode, tol, M, N, K):
     assert rel_err(C, ref) < tol, (mode, M, N, K, rel_err(C, ref))
 
 
+DEFAULT_PERSISTENT = 2
+
+
 @pytest.mark.parametrize("mode,tol", [("3xtf32", 1e-5), ("tf32", 3e-3)])
 @pytest.mark.parametrize("M,N,K,ln", [(20000, 1024, 256, False), (19999, 520, 96, True), (40000, 256, 512, True),
                                       (16384, 2048, 256, True)])
@@ -52,9 +55,19 @@ def test_gemm_persistent_kernel(small_engine, mode, tol, M, N, K, ln):
     small_engine.set_option("gemm_persistent", 0)
     try:
         C1 = small_engine.test_gemm(mode, A, W, **kw)
+        small_engine.set_option("gemm_persistent", 2)          # A operand (tf32 hi / lo) in tensor memory
+        C2 = small_engine.test_gemm(mode, A, W, **kw)
     finally:
-        small_engine.set_option("gemm_persistent", 1)
+        small_engine.set_option("gemm_persistent", DEFAULT_PERSISTENT)
     torch.cuda.synchronize()
+    if mode == "3xtf32":
+        small_engine.set_option("gemm_persistent", 1)
+        try:
+            C3 = small_engine.test_gemm(mode, A, W, **kw)
+            torch.cuda.synchronize()
+        finally:
+            small_engine.set_option("gemm_persistent", DEFAULT_PERSISTENT)
+        assert torch.equal(C2, C3)                               # same tf32 operands, same MMA order: same bits
     An = torch.nn.functional.layer_norm(A.double(), (K,), gam.double(), bet.double(), 1e-6) if ln else A.double()
     ref = An @ W.double().t() + bias.double()
     ref = (torch.relu(ref) if ln else ref) + res.double()
