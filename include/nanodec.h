@@ -183,6 +183,8 @@ ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int3
  *   "cross_beam_kernel" (default 2, process-wide): cross attention with several beams per chunk at d = 256:
  *                    2 = persistent TMA-ring kernel, 1 = register-prefetch kernel, 0 = generic kernel (cross-checks);
  *   "cross_ring_groups" (default 2, process-wide): consumer warp groups of the ring kernel (2 for <= 5 beams);
+ *   "gemm_a_tmem"    (default 1, process-wide): the 64-wide one-tile-per-CTA 3xTF32 kernels (decode step) keep the
+ *                    A operand in tensor memory like the persistent kernel; 0 = shared memory (same bits);
  *   "gemm_serial_split" (default 1, process-wide): projections with >= 2048 rows run the split-K sum inside one CTA
  *                    (bit-identical to the cluster split), 0 = always the cluster split.                        */
 ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);

@@ -36,21 +36,26 @@ constexpr int kTmaWarp = kConvWarps, kMmaWarp = kConvWarps + 1;
 constexpr int kThreads = kConvThreads + 64;
 constexpr int A_TILE_BYTES = BM * 128;
 
-template <int BN, int NPASS, int S, int Q = 1>
+// ATM (3xTF32, Q == 1): tf32 hi / lo parts of the A tile go to tensor memory (64 columns per stage) instead of back
+// to shared memory; see gemm_tc_persist_kernel.
+template <int BN, int NPASS, int S, int Q = 1, bool ATM = false>
 struct Cfg {
+  static_assert(!ATM || (NPASS == 3 && Q == 1), "A in tensor memory: 3xTF32, one accumulator");
   static constexpr int B_TILE_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES * (NPASS == 3 ? 2 : 1) + B_TILE_BYTES * (NPASS == 3 ? 2 : 1);
+  static constexpr int A_BYTES = A_TILE_BYTES * ((NPASS == 3 && !ATM) ? 2 : 1);
+  static constexpr int STAGE_BYTES = A_BYTES + B_TILE_BYTES * (NPASS == 3 ? 2 : 1);
   static constexpr int PS = BN + 4;                                   // padded pitch of split-K partial rows
   static constexpr int RECV_BYTES = S > 1 ? BM * PS * 4 : 0;          // peers push their partial rows here
   static constexpr int kStagesFit = (200 * 1024 - RECV_BYTES) / STAGE_BYTES;
-  static constexpr int kStages = kStagesFit >= 6 ? 6 : kStagesFit;
+  static constexpr int kStages = kStagesFit >= 6 ? 6 : kStagesFit;       // 6 x 64 A columns + BN <= 512 for ATM
   static constexpr int AUX_BYTES = 256 /*barriers*/ + 2 * BM * 4 /*row stats*/ + 2 * BN * 4 /*epilogue vectors*/ +
                                    Q * 6 * BM * 4 /*half-row moments (per serial K slice)*/;
   static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + RECV_BYTES + 1024 /*align*/ + AUX_BYTES;
   static constexpr int ACC_COLS = Q * BN;                            // one accumulator per serial K slice
-  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
+  static constexpr int NEED_COLS = ACC_COLS + (ATM ? kStages * 64 : 0);
+  static constexpr int TMEM_COLS = NEED_COLS <= 32 ? 32 : (NEED_COLS <= 64 ? 64 : (NEED_COLS <= 128 ? 128 : (NEED_COLS <= 256 ? 256 : 512)));
   static_assert(Q == 1 || S == 1, "serial K slices replace the cluster split");
-  static_assert(ACC_COLS <= 512, "tensor memory");
+  static_assert(NEED_COLS <= 512, "tensor memory");
 };
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -214,11 +219,11 @@ __device__ __forceinline__ void epilogue_rowwise(const GemmParams& p, float (&v)
 // separate accumulators (and Q separate sets of LayerNorm moments) and adds them in the cluster kernel's order, so
 // the result is bit-identical to gemm_tc_kernel<*, NPASS, Q> whatever the tile width.  Used when there are enough
 // rows (beam search: beam x batch) that the cluster split would run several waves of short CTAs.
-template <int BN, int NPASS, int S, int Q = 1>
+template <int BN, int NPASS, int S, int Q = 1, bool ATM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmWhi,
                const __grid_constant__ CUtensorMap tmWlo, GemmParams p) {
-  using C = Cfg<BN, NPASS, S, Q>;
+  using C = Cfg<BN, NPASS, S, Q, ATM>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by SWIZZLE_128B operand tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -252,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   auto a_hi = [&](int s) { return tiles + s * C::STAGE_BYTES; };
   auto a_lo = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES; };
-  auto b_hi = [&](int s) { return tiles + s * C::STAGE_BYTES + A_TILE_BYTES * (NPASS == 3 ? 2 : 1); };
+  auto b_hi = [&](int s) { return tiles + s * C::STAGE_BYTES + C::A_BYTES; };
   auto b_lo = [&](int s) { return b_hi(s) + C::B_TILE_BYTES; };
   auto issue_w = [&](int i) {                  // weight tiles: never written by another kernel of the stream
     const int s = i % C::kStages;
@@ -349,7 +354,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 32 bytes per K=8 step inside the swizzle row
           const uint32_t first = ((Q > 1 ? i % kb_q : i) == 0 && k == 0) ? 0u : 1u;
           const uint32_t acc_t = Q > 1 ? tmem_base + (uint32_t)((i / kb_q) * BN) : tmem_base;
-          if (NPASS == 3) {
+          if constexpr (ATM) {
+            const uint32_t ah = tmem_base + (uint32_t)(C::ACC_COLS + s * 64 + k * 8), al = ah + 32;
+            umma_tf32_ts(acc_t, al, dbh + adv, idesc, first);
+            umma_tf32_ts(acc_t, ah, dbl + adv, idesc, 1u);
+            umma_tf32_ts(acc_t, ah, dbh + adv, idesc, 1u);
+          } else if (NPASS == 3) {
             umma_tf32(acc_t, dal + adv, dbh + adv, idesc, first);
             umma_tf32(acc_t, dah + adv, dbl + adv, idesc, 1u);
             umma_tf32(acc_t, dah + adv, dbh + adv, idesc, 1u);
@@ -384,6 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < 4; ++c) vin[c] = *reinterpret_cast<float4*>(rh + (((4 * half + c) ^ sw) << 4));
         if (fold && (Q > 1 ? i % kb_q : i) == 0) x0 = vin[0].x;   // shift = first element of THIS thread's share (race free)
+        uint32_t th[16], tl[16];                // ATM: this thread's 16 columns of the hi / lo tile
 #pragma unroll
         for (int c = 0; c < 4; ++c) {           // logical 16-byte chunk lc lives at physical chunk lc ^ (row & 7)
           const int lc = 4 * half + c;
@@ -407,12 +418,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               h[q] = __uint_as_float((__float_as_uint(x[q]) + 0x1000u) & 0xffffe000u);     // nearest tf32
               l[q] = __uint_as_float((__float_as_uint(x[q] - h[q]) + 0x1000u) & 0xffffe000u);
             }
-            *reinterpret_cast<float4*>(rh + pc) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(rl + pc) = make_float4(l[0], l[1], l[2], l[3]);
+            if constexpr (ATM) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { th[4 * c + q] = __float_as_uint(h[q]); tl[4 * c + q] = __float_as_uint(l[q]); }
+            } else {
+              *reinterpret_cast<float4*>(rh + pc) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(rl + pc) = make_float4(l[0], l[1], l[2], l[3]);
+            }
           }
         }
-        if (NPASS == 3)
+        if constexpr (ATM) {
+          // warp w owns tensor-memory lanes 32*(w & 3)..: its rows; columns [16*half, 16*half + 16) of the stage
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(C::ACC_COLS + s * 64 + half * 16);
+          tmem_st16(ta, th);
+          tmem_st16(ta + 32, tl);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        } else if (NPASS == 3) {
           fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+        }
       }
       mbar_arrive(&conv_full[s]);
       if (threadIdx.x == 0 && i == 0) ND_TS(7);
@@ -1020,13 +1044,13 @@ bool make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, i
   return r == CUDA_SUCCESS;
 }
 
-template <int BN, int NPASS, int S, int Q = 1>
+template <int BN, int NPASS, int S, int Q = 1, bool ATM = false>
 cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN, NPASS, S, Q>;
+  using C = Cfg<BN, NPASS, S, Q, ATM>;
   static PerDeviceFlag attr_flag;
   bool& attr_set = attr_flag.cur();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, S, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, S, Q, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -1052,11 +1076,12 @@ cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NPASS, S, Q>, tmA, tmWhi, tmWlo, pp);
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, NPASS, S, Q, ATM>, tmA, tmWhi, tmWlo, pp);
 }
 
 int g_persist = 2;       // 0: always one tile per CTA (cross-check), 1: persistent kernel, 2 (default): ... with A in tensor memory
 int g_serial_split = 1;  // 0: cluster split-K also for many rows (cross-check: results are bit-identical)
+int g_atm = 1;           // one-tile-per-CTA kernels: A operand in tensor memory (0: shared memory; same bits)
 int g_n_sm = 0;
 
 template <int BN, int NPASS, bool ATM = false>
@@ -1105,6 +1130,17 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
     }
     return launch_persist<128, NPASS>(p, stream);
   }
+  if constexpr (NPASS == 3) {
+    // A operand in tensor memory (same bits) for the 64-wide tiles: decode 81.2 -> 80.7 ms.  The one-tile 128-wide
+    // kernel (N = 2048 at M = 1024) measured slower with it (26.8 -> 29.0 us) and keeps A in shared memory.
+    if (g_atm && !(g_serial_split && split > 1 && p.M >= 2048) && !(split == 1 && tiles128 >= 120 && p.N > 64)) {
+      switch (split) {
+        case 4: return launch<64, 3, 4, 1, true>(p, stream);
+        case 2: return launch<64, 3, 2, 1, true>(p, stream);
+        default: return launch<64, 3, 1, 1, true>(p, stream);
+      }
+    }
+  }
   if (split == 1 && tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
   // many rows (beam x batch): the cluster split would run several waves of short CTAs; one CTA per 128 x 128 tile
   // with the K slices in separate accumulators gives the same bits in one wave
@@ -1135,6 +1171,7 @@ bool make_plain_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 void gemm_tc_set_debug(long long* dev_buf) { g_dbg = dev_buf; }
 void gemm_tc_set_persistent(int on) { g_persist = on; }
 void gemm_tc_set_serial_split(int on) { g_serial_split = on; }
+void gemm_tc_set_a_tmem(int on) { g_atm = on; }
 
 bool gemm_tc_available(const char** why) {
   const bool ok = lookup();

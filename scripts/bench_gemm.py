@@ -12,6 +12,8 @@ import os
 shapes = [(1024, 768, 256, True), (1024, 256, 256, False), (1024, 2048, 256, True), (1024, 256, 2048, False),
           (5120, 768, 256, True), (5120, 256, 256, False), (5120, 2048, 256, True), (5120, 256, 2048, False),
           (524288, 1024, 256, False), (524288, 512, 256, False), (524288, 256, 256, False)]
+if os.environ.get("ND_ATM"):
+    eng.set_option("gemm_a_tmem", int(os.environ["ND_ATM"]))
 if os.environ.get("ND_PERSIST"):
     eng.set_option("gemm_persistent", int(os.environ["ND_PERSIST"]))
 if os.environ.get("ND_M"):      # e.g. ND_M=5120: only the decode shapes at that row count

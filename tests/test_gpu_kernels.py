@@ -90,6 +90,23 @@ def test_gemm_layernorm_relu_residual(small_engine, mode, tol):
     An = torch.nn.functional.layer_norm(A.double(), (K,), gam.double(), bet.double(), 1e-6)
     ref = torch.relu(An @ W.double().t() + bias.double()) + res.double()
     assert rel_err(C, ref) < tol, rel_err(C, ref)
+    if mode == "3xtf32":
+        # A operand in tensor memory (default) vs in shared memory: same tf32 operands, same MMA order -> same bits,
+        # for the cluster split-K shapes of the decode step as well
+        for (M2, N2, K2) in ((M, N, K), (1024, 256, 256), (1024, 256, 2048), (300, 768, 256)):
+            A2 = (torch.randn(M2, K2, generator=g) * 2 + 0.5).cuda()
+            W2 = (torch.randn(N2, K2, generator=g) / K2 ** 0.5).cuda()
+            b2 = torch.randn(N2, generator=g).cuda()
+            g2 = (1 + 0.1 * torch.randn(K2, generator=g)).cuda()
+            be2 = (0.1 * torch.randn(K2, generator=g)).cuda()
+            c_t = small_engine.test_gemm(mode, A2, W2, bias=b2, ln=(g2, be2))
+            small_engine.set_option("gemm_a_tmem", 0)
+            try:
+                c_s = small_engine.test_gemm(mode, A2, W2, bias=b2, ln=(g2, be2))
+                torch.cuda.synchronize()
+            finally:
+                small_engine.set_option("gemm_a_tmem", 1)
+            assert torch.equal(c_t, c_s), (M2, N2, K2)
 
 
 def test_frontend_bit_exact_vs_oracle_and_reference_golden(small_engine):
