@@ -172,7 +172,8 @@ ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int3
  *   "use_graphs"     (default 1): capture the decode loop of a repeated (mode, B, T, L, ...) configuration
  *                    into a CUDA graph on its second call and replay it afterwards;
  *   "pdl"            (default 2, process-wide): 2 = the tcgen05 GEMMs of the step loop are programmatic dependent
- *                    launches, 1 = every step kernel, 0 = plain stream order.
+ *                    launches, 1 = every step kernel, 3 = the GEMMs and the small step kernels (not the chunk-per-CTA
+ *                    attention kernels), 0 = plain stream order.
  * Kernel selection (same arithmetic contract, results agree to fp32 rounding; all are covered by parity tests):
  *   "gemm_persistent" (default 2, process-wide): large-M projections as the persistent tcgen05 kernel with the
  *                    A operand (tf32 hi / lo parts) in tensor memory; 1 = A in shared memory, 0 = one tile per CTA;
