@@ -103,3 +103,18 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+
+
+def test_every_documented_option_is_handled_and_vice_versa():
+    """The integer options listed above nd_set_int in include/nanodec.h are exactly the names engine.cu compares
+    against (an undocumented switch, or a documented one that silently does nothing, is an ABI bug)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "nanodec.h")).read()
+    block = header[header.index("integer options."): header.index("nd_set_int(")]
+    documented = set(re.findall(r'^\s*\*\s+"([a-z_0-9]+)"', block, flags=re.M))
+    src = open(os.path.join(root, "nanodecoder_b200", "csrc", "engine.cu")).read()
+    body = src[src.index("int nd_set_int("):]
+    body = body[: body.index("\n}\n")]
+    handled = set(re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', body))
+    assert documented == handled, (sorted(documented - handled), sorted(handled - documented))
