@@ -146,7 +146,7 @@ class Translator(object):
         n = chunks.size(0)
         dev = self.model.device
         host_lengths = lengths.cpu().numpy()
-        if not chunks.is_cuda:
+        if not chunks.is_cuda and torch.device(dev).type == "cuda":
             chunks = chunks.pin_memory().to(dev, non_blocking=True)      # ONE host->device copy per read
         lengths_d = lengths.to(dev, non_blocking=True)
         builder = TranslationBuilder(_Data(), self.fields, self.n_best)
