@@ -161,24 +161,35 @@ class Translator(object):
         fast_host = not (self.verbose or attn_debug)
         itos = np.array(self.fields["tgt"].vocab.itos, dtype=object)
         eos_id = list(itos).index(self.fields["tgt"].eos_token)
-        for idx, T in plan:
+        totals = [0.0, 0]
+
+        def finish(job):
+            # same results as the TranslationBuilder path below, without one Python object per chunk / token:
+            # ids come back as ONE array, hypotheses are cut at the first </s> with array ops
+            idx, (ids, lens, scores) = job[0], self._collect_arrays(job[1])
+            is_eos = ids == eos_id
+            pos = np.arange(ids.shape[2])[None, None, :]
+            is_end = is_eos | (pos >= lens[:, :, None])
+            cut = np.where(is_end.any(2), is_end.argmax(2), ids.shape[2])
+            strings = join_tokens(ids[:, : self.n_best], cut[:, : self.n_best], itos)
+            score_rows = scores[:, : self.n_best].unbind(0)         # per chunk: n_best 0-d tensors when iterated
+            for j, i in enumerate(idx.tolist()):
+                all_scores[i] = score_rows[j]
+                all_predictions[i] = strings[j]
+            totals[0] += float(scores[:, 0].sum())
+            totals[1] += int(cut[:, 0].sum())
+
+        pending = None
+        for k, (idx, T) in enumerate(plan):
             idx_t = torch.from_numpy(idx).to(dev)
             if fast_host:
-                # same results as the TranslationBuilder path below, without one Python object per chunk / token:
-                # ids come back as ONE array, hypotheses are cut at the first </s> with array ops
-                ids, lens, scores = self._decode_arrays(chunks.index_select(0, idx_t)[:, :T].contiguous(),
-                                                        lengths_d.index_select(0, idx_t))
-                is_eos = ids == eos_id
-                pos = np.arange(ids.shape[2])[None, None, :]
-                is_end = is_eos | (pos >= lens[:, :, None])
-                cut = np.where(is_end.any(2), is_end.argmax(2), ids.shape[2])
-                strings = join_tokens(ids[:, : self.n_best], cut[:, : self.n_best], itos)
-                score_rows = scores[:, : self.n_best].unbind(0)     # per chunk: n_best 0-d tensors when iterated
-                for j, i in enumerate(idx.tolist()):
-                    all_scores[i] = score_rows[j]
-                    all_predictions[i] = strings[j]
-                pred_score_total += float(scores[:, 0].sum())
-                pred_words_total += int(cut[:, 0].sum())
+                # the device work of batch k and the copy of its results are only ENQUEUED here; the host side of
+                # batch k-1 (strings) runs while the GPU works on batch k
+                job = (idx, self._launch_arrays(chunks.index_select(0, idx_t)[:, :T].contiguous(),
+                                                lengths_d.index_select(0, idx_t), slot=k & 1))
+                if pending is not None:
+                    finish(pending)
+                pending = job
                 continue
             b_src = chunks.index_select(0, idx_t)[:, :T].t().contiguous().unsqueeze(2)       # [T,B,1]
             batch = _Batch(b_src, lengths_d.index_select(0, idx_t), torch.arange(len(idx)))
@@ -195,6 +206,10 @@ class Translator(object):
                 if attn_debug and self.out_file_attn is not None and trans.attns is not None:
                     rows = trans.attns[0].tolist()
                     self.out_file_attn.write("\n".join(" ".join("%8.5f" % v for v in r) for r in rows) + "\n")
+        if pending is not None:
+            finish(pending)
+        pred_score_total += totals[0]
+        pred_words_total += totals[1]
         if self.report_score:
             msg = self._report_score("PRED", pred_score_total, pred_words_total)
             (self.logger.info(msg) if self.logger else print(msg))
@@ -233,22 +248,54 @@ class Translator(object):
         results["attention"] = [[[] for _ in range(self.n_best)] for _ in range(B)]
         return results
 
-    def _decode_arrays(self, src, lengths):
-        """src [B,T] fp32 chunk-major on the device -> (ids [B,n_best,L] int64 numpy (-1 padded), lens [B,n_best],
-        scores [B,n_best] torch cpu); same dispatch as translate_batch."""
+    def _launch_arrays(self, src, lengths, slot=0):
+        """src [B,T] fp32 chunk-major on the device: enqueue encode + decode (same dispatch as translate_batch) and the
+        device->host copy of the results into pinned buffers of `slot` (two slots: the copy of batch k may still be
+        in flight while batch k+1 is enqueued).  Nothing here waits for the GPU.  -> handle for _collect_arrays."""
         eng = self.model
         eng.encode(src, lengths)
         if self.beam_size == 1:
             out = eng.decode_greedy(self.max_length, self.min_length)
-            ids = out["ids"].cpu().numpy()[:, None, :]
-            lens = np.full((ids.shape[0], 1), ids.shape[2], dtype=np.int64)
-            return ids, lens, out["scores"].cpu()[:, None]
-        if self.fast:
-            out = eng.decode_beam(self.beam_size, self.n_best, self.max_length, self.min_length, self.global_scorer.alpha)
+            dev_t = {"ids": out["ids"], "scores": out["scores"]}
         else:
-            out = eng.decode_beam_object(self.beam_size, self.n_best, self.max_length, self.min_length,
-                                         self.global_scorer.length_penalty, self.global_scorer.alpha)
-        return out["ids"].cpu().numpy(), out["lens"].cpu().numpy().astype(np.int64), out["scores"].cpu()
+            if self.fast:
+                out = eng.decode_beam(self.beam_size, self.n_best, self.max_length, self.min_length,
+                                      self.global_scorer.alpha)
+            else:
+                out = eng.decode_beam_object(self.beam_size, self.n_best, self.max_length, self.min_length,
+                                             self.global_scorer.length_penalty, self.global_scorer.alpha)
+            dev_t = {"ids": out["ids"], "lens": out["lens"], "scores": out["scores"]}
+        if not dev_t["ids"].is_cuda:
+            return dev_t, None
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        host = {}
+        for name, t in dev_t.items():
+            key = (slot, name, tuple(t.shape), t.dtype)
+            buf = self._pinned.get(key)
+            if buf is None:
+                buf = self._pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host[name] = buf.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev_t["ids"].device))
+        return host, ev
+
+    def _collect_arrays(self, handle):
+        """-> (ids [B,n_best,L] int64 numpy (-1 padded), lens [B,n_best] int64 numpy, scores [B,n_best] torch cpu);
+        waits for the batch's copy only.  The arrays are copies: the pinned buffers are reused two batches later."""
+        host, ev = handle
+        if ev is not None:
+            ev.synchronize()
+        ids = host["ids"].numpy()
+        scores = host["scores"].clone() if ev is not None else host["scores"]
+        if "lens" not in host:                                   # greedy: one hypothesis of max_length tokens
+            ids = ids[:, None, :]
+            return ids, np.full((ids.shape[0], 1), ids.shape[2], dtype=np.int64), scores[:, None]
+        return ids, host["lens"].numpy().astype(np.int64), scores
+
+    def _decode_arrays(self, src, lengths):
+        """one batch, synchronously (see _launch_arrays / _collect_arrays)"""
+        return self._collect_arrays(self._launch_arrays(src, lengths))
 
     def _report_score(self, name, score_total, words_total):
         if words_total == 0:
