@@ -149,3 +149,27 @@ def test_gold_scoring_and_missing_batch_size_are_refused():
         tr.translate(src=(chunks, lengths))
     with pytest.raises(ValueError):
         tr.translate(src=(chunks, lengths), tgt=["A C"], batch_size=2)
+
+
+class _Log(object):
+    def __init__(self):
+        self.lines = []
+
+    def info(self, msg):
+        self.lines.append(msg)
+
+
+@pytest.mark.parametrize("beam,n_best", [(1, 1), (5, 2)])
+def test_array_path_equals_the_translation_builder_path(beam, n_best):
+    """translate() builds the strings with array operations; with -verbose it goes through translate_batch and the
+    TranslationBuilder mirror (translate/translation.py:27-41,62-119) one object per chunk.  Same predictions, scores."""
+    L = 15
+    chunks, lengths = _make(13, 36, seed=7)
+    tr, _ = _translator(L, beam=beam, n_best=n_best, batch_size=8)
+    s_fast, p_fast = tr.translate(src=(chunks, lengths), batch_size=8)
+    tr2, _ = _translator(L, beam=beam, n_best=n_best, batch_size=8)
+    tr2.verbose, tr2.logger = True, _Log()
+    s_slow, p_slow = tr2.translate(src=(chunks, lengths), batch_size=8)
+    assert p_fast == p_slow
+    assert [[float(x) for x in s] for s in s_fast] == [[float(x) for x in s] for s in s_slow]
+    assert len(tr2.logger.lines) == 13 and "PRED" in tr2.logger.lines[0]
