@@ -165,6 +165,13 @@ ND_EXPORT int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_b
  *   i-1 and chunk i (disp[0] = 0): the displacement simple_assembly() accumulates.                              */
 ND_EXPORT int nd_longest_match(const char* a, int32_t na, const char* b, int32_t nb, int32_t* out3);
 ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int32_t n, int32_t* disp);
+/* nd_simple_assembly: the whole of simple_assembly() + add_count() (utils/labelop.py:311-352) for one read: chunk i is
+ *   text[offsets[i] : offsets[i+1]]; counts[code][column] (caller-zeroed int32 [n_codes][cap], cap >= total bytes +
+ *   2000) receives one vote per base, lut[byte] = row of that base or -1; *length = columns in use (the reference
+ *   returns concensus[:, :length]).  *err: 0 ok, 1 = the reference would raise IndexError (err_args = index, matrix
+ *   width: it grows by 1000 at most once per chunk), 2 = KeyError (err_args = byte, chunk index).                  */
+ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32_t n, const int8_t* lut,
+                                 int32_t* counts, int64_t cap, int64_t* length, int32_t* err, int64_t* err_args);
 
 /* integer options.  Scheduling only (results never depend on them):
  *   "decode_streams" (default 1, 1..16): engine-owned CUDA streams the decode loop spreads contiguous

@@ -46,6 +46,9 @@ SIGNATURES = {
     "nd_api_version": (C.c_int, []),
     "nd_longest_match": (C.c_int, [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int32)]),
     "nd_assembly_offsets": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32)]),
+    "nd_simple_assembly": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int8),
+                                     C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int64)]),
     "nd_create": (C.c_int, [C.POINTER(NdConfig), C.POINTER(_P)]),
     "nd_destroy": (C.c_int, [_P]),
     "nd_last_error": (C.c_char_p, [_P]),

@@ -55,39 +55,35 @@ def assembly_offsets(segments):
 
 def simple_assembly(bpreads, flag_intersection=True):
     """utils/labelop.py:320-352.  ``bpreads``: list (per chunk) of n_best lists of space-joined tokens.
-    Same result as the reference (vote matrix [5, length]); the difflib longest-block search of every chunk pair
-    runs in libnanodec and the per-base Python loop of add_count is a numpy scatter."""
+    Same result as the reference (vote matrix [5, length], float64): the difflib longest-block search of every chunk
+    pair AND the votes of add_count (:311-318) run in libnanodec (nd_simple_assembly, host C++), one call per read."""
+    import ctypes as C
+    from .. import _lib
     valid = [x[0].replace(" ", "") for x in bpreads if x[0] != ""]
     if not flag_intersection:
         return "".join(valid)
-    lut = np.full(256, -1, dtype=np.int64)
+    lut = np.full(256, -1, dtype=np.int8)
     for k, v in base_dict.items():
         lut[ord(k)] = v
         lut[ord(k.lower())] = v
-    concensus = np.zeros([len(base_keys), 1000])
-    pos, length, census_len = 0, 0, 1000
-    disps = assembly_offsets(valid) if len(valid) > 1 else np.zeros(len(valid), dtype=np.int32)
-    for indx, bpread in enumerate(valid):
-        disp = 0 if indx == 0 else int(disps[indx])
-        if indx > 0 and disp + pos + len(bpread) > census_len:
-            concensus = np.pad(concensus, ((0, 0), (0, 1000)), mode="constant", constant_values=0)
-            census_len += 1000
-        # add_count (labelop.py:311-318): a negative start trims the head of the segment
-        start = pos + disp
-        seg = bpread
-        if start < 0:
-            seg = seg[-start:]
-            start = 0
-        codes = lut[np.frombuffer(seg.encode("latin-1"), dtype=np.uint8)]
-        if (codes < 0).any():
-            raise KeyError(seg[int(np.argmax(codes < 0))])            # base_dict[base.upper()] in the reference
-        if start + len(seg) > census_len:
-            raise IndexError("index %d is out of bounds for axis 1 with size %d" % (start + len(seg) - 1, census_len))
-        np.add.at(concensus, (codes, start + np.arange(len(seg))), 1)
-        if indx > 0:
-            pos += disp
-            length = max(length, pos + len(bpread))
-    return concensus[:, :length]
+    enc = [x.encode("latin-1") for x in valid]
+    offs = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        offs[1:] = np.cumsum([len(x) for x in enc])
+    cap = int(offs[-1]) + 2000
+    counts = np.zeros((len(base_keys), cap), dtype=np.int32)
+    length, err, args = C.c_int64(0), C.c_int32(0), (C.c_int64 * 2)()
+    rc = _lib.load().nd_simple_assembly(b"".join(enc) + b"\0", offs.ctypes.data_as(C.POINTER(C.c_int64)), len(enc),
+                                        lut.ctypes.data_as(C.POINTER(C.c_int8)),
+                                        counts.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(length), C.byref(err),
+                                        args)
+    if rc != 0:
+        raise RuntimeError("nd_simple_assembly failed (%d)" % rc)
+    if err.value == 2:
+        raise KeyError(chr(args[0]))                                      # base_dict[base.upper()] in the reference
+    if err.value == 1:
+        raise IndexError("index %d is out of bounds for axis 1 with size %d" % (args[0], args[1]))
+    return counts[:, : length.value].astype(np.float64)
 
 
 def read_raw_signal(path, suffix):
