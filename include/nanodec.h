@@ -170,6 +170,12 @@ ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int3
  *   2000) receives one vote per base, lut[byte] = row of that base or -1; *length = columns in use (the reference
  *   returns concensus[:, :length]).  *err: 0 ok, 1 = the reference would raise IndexError (err_args = index, matrix
  *   width: it grows by 1000 at most once per chunk), 2 = KeyError (err_args = byte, chunk index).                  */
+/* nd_parse_signal_text: one `.signal` file (whitespace separated integer DAC samples = the fast5 `Signal` dataset that
+ *   extract_fast5_raw reads, utils/labelop.py:199-219, as text) -> int16 samples ready for nd_frontend_stats.
+ *   *status: 0 ok, 1 = some token is not a plain integer (nothing decided: use a float parser), 2 = value outside
+ *   int16, 3 = more than cap samples; *count = samples written so far.                                            */
+ND_EXPORT int nd_parse_signal_text(const char* text, int64_t nbytes, int16_t* out, int64_t cap, int64_t* count,
+                                   int32_t* status);
 ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32_t n, const int8_t* lut,
                                  int32_t* counts, int64_t cap, int64_t* length, int32_t* err, int64_t* err_args);
 

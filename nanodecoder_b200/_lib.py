@@ -46,6 +46,8 @@ SIGNATURES = {
     "nd_api_version": (C.c_int, []),
     "nd_longest_match": (C.c_int, [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int32)]),
     "nd_assembly_offsets": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32)]),
+    "nd_parse_signal_text": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_int16), C.c_int64, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int32)]),
     "nd_simple_assembly": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int8),
                                      C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int64)]),

@@ -143,4 +143,38 @@ int nd_simple_assembly(const char* text, const int64_t* offsets, int32_t n, cons
   return ND_OK;
 }
 
+// `.signal` text files (one read: whitespace separated integer DAC samples, the text form of the fast5 `Signal` dataset
+// that utils/labelop.py:199-219 reads): straight to int16.  status: 0 ok (*count samples written), 1 = a token is not a
+// plain integer (caller falls back to a float parser and its own checks), 2 = value outside int16, 3 = more than cap.
+int nd_parse_signal_text(const char* text, int64_t nbytes, int16_t* out, int64_t cap, int64_t* count, int32_t* status) {
+  if ((!text && nbytes > 0) || !out || !count || !status || nbytes < 0 || cap < 0) return ND_ERR_INVALID;
+  int64_t n = 0, i = 0;
+  *status = 0;
+  while (i < nbytes) {
+    const char c = text[i];
+    if (c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\f' || c == '\v') { ++i; continue; }
+    bool neg = false;
+    if (c == '-' || c == '+') { neg = c == '-'; ++i; }
+    if (i >= nbytes || text[i] < '0' || text[i] > '9') { *status = 1; *count = n; return ND_OK; }
+    int64_t v = 0;
+    while (i < nbytes && text[i] >= '0' && text[i] <= '9') {
+      v = v * 10 + (text[i] - '0');
+      if (v > 1000000) v = 1000000;                // saturate: range is checked below
+      ++i;
+    }
+    if (i < nbytes) {
+      const char e = text[i];
+      if (!(e == ' ' || e == '\n' || e == '\t' || e == '\r' || e == '\f' || e == '\v')) {   // "1.0", "1e3", "12a"
+        *status = 1; *count = n; return ND_OK;
+      }
+    }
+    if (neg) v = -v;
+    if (v < -32768 || v > 32767) { *status = 2; *count = n; return ND_OK; }
+    if (n >= cap) { *status = 3; *count = n; return ND_OK; }
+    out[n++] = (int16_t)v;
+  }
+  *count = n;
+  return ND_OK;
+}
+
 }  // extern "C"

@@ -1,11 +1,15 @@
 """Post-processing helpers with the reference's names (utils/labelop.py:295-352).
 
-Same algorithm as the reference (difflib longest matching block + per-column vote); the
-longest-block search runs in libnanodec (host C++), the vote is a numpy scatter.
+Same algorithm as the reference (difflib longest matching block + per-column vote); both run in
+libnanodec (host C++, nd_simple_assembly), as does the parsing of `.signal` text files (nd_parse_signal_text).
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
+
+from .. import _lib
 
 base_keys = ["A", "C", "G", "T", "M"]
 base_dict = {"A": 0, "C": 1, "G": 2, "T": 3, "M": 4}
@@ -97,7 +101,14 @@ def read_raw_signal(path, suffix):
         with h5py.File(path, "r") as f:
             raw = list(f["/Raw/Reads/"].values())[0]["Signal"][()]
         return np.asarray(raw, dtype=np.int16)
-    vals = np.array(open(path, "r").read().split(), dtype=np.float64)
+    raw = open(path, "rb").read()
+    out = np.empty(len(raw) // 2 + 1, dtype=np.int16)           # every sample takes at least a digit and a separator
+    count, status = C.c_int64(0), C.c_int32(0)
+    rc = _lib.load().nd_parse_signal_text(raw, len(raw), out.ctypes.data_as(C.POINTER(C.c_int16)), out.size,
+                                          C.byref(count), C.byref(status))
+    if rc == 0 and status.value == 0:                           # plain integers: parsed in libnanodec (17x numpy)
+        return out[: count.value].copy()
+    vals = np.array(raw.decode("latin-1").split(), dtype=np.float64)      # floats / exponents: the general parser
     ints = np.round(vals)
     if vals.size and (np.abs(vals - ints).max() > 0 or ints.min() < -32768 or ints.max() > 32767):
         raise ValueError("%s: the GPU front end takes raw int16 DAC samples; got non-integer values" % path)
