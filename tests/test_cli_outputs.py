@@ -1,0 +1,79 @@
+"""CPU: the output side of the translate.py CLI (reference translate.py:81-98): per-read result/<read>.fasta,
+segment/<read>.txt and speed.txt, written by one process and by two ranks (gloo) of a read-sharded run."""
+import importlib.util
+import os
+import types
+
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cli():
+    spec = importlib.util.spec_from_file_location("nd_translate_cli", os.path.join(ROOT, "translate.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _opt(save, stride=512, length=512):
+    for sub in ("", "result", "segment"):
+        os.makedirs(os.path.join(save, sub), exist_ok=True)
+    return types.SimpleNamespace(save_data=save, src_seq_stride=stride, src_seq_length=length)
+
+
+def _records():
+    # (global read index, out name, predictions per chunk (n_best lists), seconds)
+    return [(0, "readA.txt", [["A C G T A C"], ["T A C G G"]], 0.5),
+            (1, "readB.txt", [["G G G"], [""], ["T T"]], 0.25),
+            (2, "readC.txt", [["A C G T T G C A"], ["T T G C A A A"]], 1.0),
+            (3, "readD.txt", [["C"]], 0.125)]
+
+
+def _read(path):
+    with open(path) as f:
+        return f.read()
+
+
+def test_single_process_files_have_the_reference_formats(tmp_path):
+    cli = _cli()
+    opt = _opt(str(tmp_path))
+    cli.finish_records(opt, list(reversed(_records())))               # written in global read order anyway
+    assert _read(tmp_path / "result" / "readA.fasta") == ">readA\nACGTACTACGG"      # stride == length: concatenation
+    assert _read(tmp_path / "result" / "readB.fasta") == ">readB\nGGGTT"
+    assert _read(tmp_path / "segment" / "readB.txt") == "G G G\n\nT T\n"
+    speed = _read(tmp_path / "speed.txt").splitlines()
+    assert speed == ["readA\t0.50\t11\t22.00", "readB\t0.25\t5\t20.00", "readC\t1.00\t15\t15.00", "readD\t0.12\t1\t8.00"]
+
+
+def test_overlapping_windows_go_through_the_assembly(tmp_path):
+    cli = _cli()
+    opt = _opt(str(tmp_path), stride=60, length=300)
+    cli.finish_records(opt, _records()[2:3])
+    # chunks ACGTTGCA and TTGCAAA overlap on TTGCA: consensus ACGTTGCAAA
+    assert _read(tmp_path / "result" / "readC.fasta") == ">readC\nACGTTGCAAA"
+    assert _read(tmp_path / "speed.txt") == "readC\t1.00\t10\t10.00\n"
+
+
+def _worker(rank, ws, init_file, save):
+    os.environ["RANK"], os.environ["WORLD_SIZE"] = str(rank), str(ws)
+    dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=ws)
+    try:
+        cli = _cli()
+        recs = [r for r in _records() if r[0] % ws == (1 - rank)]     # rank 0 holds reads 1, 3; rank 1 holds 0, 2
+        cli.finish_records(_opt(save), recs)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_write_their_own_reads_and_rank0_the_speed_file(tmp_path):
+    ws = 2
+    mp.spawn(_worker, args=(ws, str(tmp_path / "rdv"), str(tmp_path / "out")), nprocs=ws, join=True)
+    ref = tmp_path / "ref"
+    _cli().finish_records(_opt(str(ref)), _records())
+    for sub, names in (("result", ["readA.fasta", "readB.fasta", "readC.fasta", "readD.fasta"]),
+                       ("segment", ["readA.txt", "readB.txt", "readC.txt", "readD.txt"])):
+        for n in names:
+            assert _read(tmp_path / "out" / sub / n) == _read(ref / sub / n)
+    assert _read(tmp_path / "out" / "speed.txt") == _read(ref / "speed.txt")      # global read order, each read once

@@ -22,8 +22,8 @@ sys.path.insert(0, ROOT)
 from nanodecoder_b200 import opts                                        # noqa: E402
 
 
-def write_output(opt, file_src, all_predictions, time_translate):
-    """translate.py:81-98 (same file formats)."""
+def write_read_files(opt, file_src, all_predictions):
+    """result/<read>.fasta and segment/<read>.txt of one read (translate.py:81-93, same formats) -> assembled length."""
     from nanodecoder_b200.utils.labelop import index2base, simple_assembly
     name = file_src.split(".txt")[0]
     if opt.src_seq_stride < opt.src_seq_length:
@@ -35,9 +35,46 @@ def write_output(opt, file_src, all_predictions, time_translate):
     with open(os.path.join(opt.save_data, "segment", file_src), "w+") as f:
         for n_best_preds in all_predictions:
             f.write("\n".join(n_best_preds) + "\n")
+    return len(c_bpread)
+
+
+def speed_line(file_src, time_translate, n_bases):
+    """one line of speed.txt (translate.py:94-96)."""
+    return "%s\t%0.2f\t%d\t%0.2f\n" % (file_src.split(".txt")[0], float(time_translate), n_bases,
+                                        n_bases / float(max(time_translate, 1e-9)))
+
+
+def write_output(opt, file_src, all_predictions, time_translate):
+    """translate.py:81-98 (same file formats)."""
+    n_bases = write_read_files(opt, file_src, all_predictions)
     with open(os.path.join(opt.save_data, "speed.txt"), "a+") as f:
-        f.writelines("%s\t%0.2f\t%d\t%0.2f\n" % (name, float(time_translate), len(c_bpread),
-                                                 len(c_bpread) / float(max(time_translate, 1e-9))))
+        f.writelines(speed_line(file_src, time_translate, n_bases))
+
+
+def finish_records(opt, records):
+    """records of THIS rank: (global read index, out name, predictions, seconds).  One process: the reference's
+    writeOutPut per read, in order.  Several ranks (torchrun): every rank assembles and writes the per-read files of its
+    own reads (they are independent files; assembling everything on rank 0 would make one host core the bottleneck of 8
+    GPUs) and only the speed.txt lines travel to rank 0, which appends them in global read order."""
+    from nanodecoder_b200 import shard
+    _, ws = shard.world()
+    if ws == 1:
+        for _, out_name, preds, seconds in sorted(records, key=lambda r: r[0]):
+            try:
+                write_output(opt, out_name, preds, seconds)
+            except Exception:                                    # translate.py:97-98
+                print("!!!error!!!data src: " + out_name.split(".txt")[0])
+        return
+    lines = []
+    for idx, out_name, preds, seconds in records:
+        try:
+            lines.append((idx, speed_line(out_name, seconds, write_read_files(opt, out_name, preds))))
+        except Exception:
+            print("!!!error!!!data src: " + out_name.split(".txt")[0])
+    merged = shard.gather_records(lines, dst=0)
+    if merged is not None:
+        with open(os.path.join(opt.save_data, "speed.txt"), "a+") as f:
+            f.writelines(line for _, line in merged)
 
 
 def main(opt, logger):
@@ -98,14 +135,7 @@ def main(opt, logger):
         for j, i in enumerate(keep):
             sel = np.nonzero(chunk_read == j)[0]
             records.append((group[i][0], group[i][1][2], [preds[k] for k in sel], elapsed * len(sel) / total))
-    # per-read records travel to rank 0 (NCCL all_gather over NVLink on the GPUs), which writes the files
-    merged = shard.gather_records(records, dst=0)
-    if merged is not None:
-        for _, out_name, preds, seconds in merged:
-            try:
-                write_output(opt, out_name, preds, seconds)
-            except Exception:                                    # translate.py:97-98
-                print("!!!error!!!data src: " + out_name.split(".txt")[0])
+    finish_records(opt, records)
 
 
 if __name__ == "__main__":
