@@ -77,3 +77,60 @@ def test_two_ranks_write_their_own_reads_and_rank0_the_speed_file(tmp_path):
         for n in names:
             assert _read(tmp_path / "out" / sub / n) == _read(ref / sub / n)
     assert _read(tmp_path / "out" / "speed.txt") == _read(ref / "speed.txt")      # global read order, each read once
+
+
+def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path):
+    """run_reads (the CLI's per-rank loop) end to end on CPU: real `.signal` parsing, the reference's chunk table, the
+    real Translator mirror over a recording stub engine; host threads prefetch the next group's files and write the
+    previous reads.  Every non-empty read gets its files, chunks keep their order and their read's padding width."""
+    import numpy as np
+    import torch
+    from nanodecoder_b200.inputters.nano_dataset import chunk_table, reference_pad_lengths
+    from nanodecoder_b200.utils.labelop import read_raw_signal
+    from test_translator_host import EOS, VOCAB, _tokens, _translator
+
+    cli = _cli()
+    T, L, B = 64, 12, 8
+    src = tmp_path / "reads"
+    src.mkdir()
+    rng = np.random.default_rng(11)
+    sizes = [200, 0, 64, 333, 65, 700, 1, 129, 500, 90, 260]            # one empty read, several ragged tails
+    raws = []
+    for i, n in enumerate(sizes):
+        x = rng.integers(300, 900, size=n)
+        (src / ("r%02d.signal" % i)).write_text(" ".join(map(str, x)))
+        raws.append(x.astype(np.int16))
+    opt = _opt(str(tmp_path / "out"), stride=T, length=T)
+    opt.src_dir, opt.thread, opt.batch_size, opt.attn_debug = str(src), 1, B, False      # groups of 8 reads
+
+    def frontend(reads):                                                 # chunking only: samples / 1024 as "signal"
+        cr, cs = chunk_table([r.size for r in reads], T, T)
+        chunks = np.zeros((len(cr), T), np.float32)
+        lens = np.zeros(len(cr), np.int64)
+        for k, (r, s) in enumerate(zip(cr, cs)):
+            seg = reads[r][s: s + T].astype(np.float32) / 1024.0
+            chunks[k, : seg.size] = seg
+            lens[k] = seg.size
+        return torch.from_numpy(chunks), torch.from_numpy(lens), cr
+
+    tr, eng = _translator(L, batch_size=B)
+    todo = [(i, ("r%02d.signal" % i, "signal", "r%02d.txt" % i)) for i in range(len(sizes))]
+    lines = cli.run_reads(opt, todo, read_raw_signal, frontend, tr)
+    cli.finish_lines(opt, lines)
+
+    live = [i for i, n in enumerate(sizes) if n > 0]
+    assert [l[0] for l in lines] == live
+    speed = _read(tmp_path / "out" / "speed.txt").splitlines()
+    assert [s.split("\t")[0] for s in speed] == ["r%02d" % i for i in live]
+    assert not (tmp_path / "out" / "result" / "r01.fasta").exists()
+    for i in live:
+        chunks, lens, _ = frontend([raws[i]])
+        widths = reference_pad_lengths(lens.numpy(), B)
+        want = []
+        for k in range(len(lens)):
+            ids = _tokens(chunks[k].numpy(), int(lens[k]), int(widths[k]), L)
+            want.append(" ".join(VOCAB[t] for t in ids[: int((ids != EOS).sum())]))
+        assert _read(tmp_path / "out" / "segment" / ("r%02d.txt" % i)) == "".join(w + "\n" for w in want)
+        fasta = _read(tmp_path / "out" / "result" / ("r%02d.fasta" % i))
+        assert fasta == ">r%02d\n%s" % (i, "".join(w.replace(" ", "") for w in want))
+        assert int(speed[live.index(i)].split("\t")[2]) == sum(len(w.split()) for w in want)

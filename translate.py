@@ -51,34 +51,82 @@ def write_output(opt, file_src, all_predictions, time_translate):
         f.writelines(speed_line(file_src, time_translate, n_bases))
 
 
-def finish_records(opt, records):
-    """records of THIS rank: (global read index, out name, predictions, seconds).  One process: the reference's
-    writeOutPut per read, in order.  Several ranks (torchrun): every rank assembles and writes the per-read files of its
-    own reads (they are independent files; assembling everything on rank 0 would make one host core the bottleneck of 8
-    GPUs) and only the speed.txt lines travel to rank 0, which appends them in global read order."""
-    from nanodecoder_b200 import shard
-    _, ws = shard.world()
-    if ws == 1:
-        for _, out_name, preds, seconds in sorted(records, key=lambda r: r[0]):
-            try:
-                write_output(opt, out_name, preds, seconds)
-            except Exception:                                    # translate.py:97-98
-                print("!!!error!!!data src: " + out_name.split(".txt")[0])
-        return
-    lines = []
-    for idx, out_name, preds, seconds in records:
+def run_reads(opt, todo_mine, read_signal, frontend, translator):
+    """The read loop of one rank.  todo_mine: [(global read index, (file name, suffix, out name))]; read_signal(path,
+    suffix) -> int16 samples; frontend(list of reads) -> (chunks, lengths, chunk_read); translator.translate as in the
+    reference.  While the GPU works on a group of reads, `opt.thread` host threads parse the files of the NEXT group and
+    assemble / write the per-read files of the PREVIOUS ones (file I/O and the libnanodec calls release the GIL).
+    -> [(global read index, speed.txt line)] of the reads written."""
+    from concurrent.futures import ThreadPoolExecutor
+    from nanodecoder_b200.inputters.nano_dataset import reference_pad_lengths
+    pool_reads = max(1, opt.thread * 8)                          # reads pooled per GPU front-end launch
+    groups = [todo_mine[g0: g0 + pool_reads] for g0 in range(0, len(todo_mine), pool_reads)]
+
+    def write_one(idx, out_name, preds, seconds):
         try:
-            lines.append((idx, speed_line(out_name, seconds, write_read_files(opt, out_name, preds))))
-        except Exception:
+            return idx, speed_line(out_name, seconds, write_read_files(opt, out_name, preds))
+        except Exception:                                        # translate.py:97-98
             print("!!!error!!!data src: " + out_name.split(".txt")[0])
+            return None
+
+    writes = []
+    with ThreadPoolExecutor(max_workers=max(1, opt.thread)) as ex:
+        def load(group):
+            return [ex.submit(read_signal, os.path.join(opt.src_dir, fn), suffix) for _, (fn, suffix, _) in group]
+
+        nxt = load(groups[0]) if groups else None
+        for gi, group in enumerate(groups):
+            start = time.time()
+            futs, nxt = nxt, (load(groups[gi + 1]) if gi + 1 < len(groups) else None)
+            reads = [f.result() for f in futs]
+            keep = [i for i, r in enumerate(reads) if r.size > 0]
+            if not keep:
+                continue
+            chunks, lengths, chunk_read = frontend([reads[i] for i in keep])
+            # chunks of many reads share GPU batches; each keeps the padding width of its read-by-read reference batch
+            h_len = lengths.cpu().numpy()
+            pad_to = np.empty_like(h_len)
+            sels = [np.nonzero(chunk_read == j)[0] for j in range(len(keep))]
+            for sel in sels:
+                pad_to[sel] = reference_pad_lengths(h_len[sel], opt.batch_size)
+            _, preds = translator.translate(src=(chunks, lengths, pad_to), tgt=None, src_dir=opt.save_data,
+                                            batch_size=opt.batch_size, attn_debug=opt.attn_debug)
+            elapsed = time.time() - start
+            total = max(1, len(chunk_read))
+            for j, i in enumerate(keep):
+                sel = sels[j]
+                writes.append(ex.submit(write_one, group[i][0], group[i][1][2], [preds[k] for k in sel],
+                                        elapsed * len(sel) / total))
+        lines = [w.result() for w in writes]
+    return sorted((l for l in lines if l is not None), key=lambda l: l[0])
+
+
+def finish_lines(opt, lines):
+    """speed.txt: one process appends its lines in global read order; under torchrun the lines of all ranks travel to
+    rank 0 (the only collective of a run), which appends them in global read order.  The per-read files were written
+    by the rank that decoded the read (independent files; assembling everything on rank 0 would make one host core
+    the bottleneck of 8 GPUs)."""
+    from nanodecoder_b200 import shard
     merged = shard.gather_records(lines, dst=0)
     if merged is not None:
         with open(os.path.join(opt.save_data, "speed.txt"), "a+") as f:
             f.writelines(line for _, line in merged)
 
 
+def finish_records(opt, records):
+    """records of THIS rank: (global read index, out name, predictions, seconds) -> files (synchronous form of what
+    run_reads does with its thread pool)."""
+    lines = []
+    for idx, out_name, preds, seconds in sorted(records, key=lambda r: r[0]):
+        try:
+            lines.append((idx, speed_line(out_name, seconds, write_read_files(opt, out_name, preds))))
+        except Exception:                                        # translate.py:97-98
+            print("!!!error!!!data src: " + out_name.split(".txt")[0])
+    finish_lines(opt, lines)
+
+
 def main(opt, logger):
-    from nanodecoder_b200.inputters.nano_dataset import SignalFrontend, reference_pad_lengths
+    from nanodecoder_b200.inputters.nano_dataset import SignalFrontend
     from nanodecoder_b200.translate.translator import build_translator
     from nanodecoder_b200.utils.labelop import read_raw_signal
     from nanodecoder_b200 import shard
@@ -110,32 +158,7 @@ def main(opt, logger):
     # every rank derives the same partition from the file sizes
     rank, ws = shard.world()
     mine = shard.partition_reads([os.path.getsize(os.path.join(opt.src_dir, t[0])) for t in todo], ws)[rank]
-    todo_mine = [(i, todo[i]) for i in mine]
-
-    records = []                                                 # (global read index, out name, predictions, seconds)
-    pool_reads = max(1, opt.thread * 8)                          # reads pooled per GPU front-end launch
-    for g0 in range(0, len(todo_mine), pool_reads):
-        group = todo_mine[g0: g0 + pool_reads]
-        start = time.time()
-        reads = [read_raw_signal(os.path.join(opt.src_dir, fn), suffix) for _, (fn, suffix, _) in group]
-        keep = [i for i, r in enumerate(reads) if r.size > 0]
-        if not keep:
-            continue
-        chunks, lengths, chunk_read = frontend([reads[i] for i in keep])
-        # chunks of many reads share GPU batches; each keeps the padding width of its read-by-read reference batch
-        h_len = lengths.cpu().numpy()
-        pad_to = np.empty_like(h_len)
-        for j in range(len(keep)):
-            sel = np.nonzero(chunk_read == j)[0]
-            pad_to[sel] = reference_pad_lengths(h_len[sel], opt.batch_size)
-        _, preds = translator.translate(src=(chunks, lengths, pad_to), tgt=None, src_dir=opt.save_data,
-                                        batch_size=opt.batch_size, attn_debug=opt.attn_debug)
-        elapsed = time.time() - start
-        total = max(1, len(chunk_read))
-        for j, i in enumerate(keep):
-            sel = np.nonzero(chunk_read == j)[0]
-            records.append((group[i][0], group[i][1][2], [preds[k] for k in sel], elapsed * len(sel) / total))
-    finish_records(opt, records)
+    finish_lines(opt, run_reads(opt, [(i, todo[i]) for i in mine], read_raw_signal, frontend, translator))
 
 
 if __name__ == "__main__":
