@@ -146,7 +146,7 @@ class Translator(object):
         n = chunks.size(0)
         dev = self.model.device
         host_lengths = lengths.cpu().numpy()
-        if not chunks.is_cuda and torch.device(dev).type == "cuda":
+        if not chunks.is_cuda and torch.device(dev).type == "cuda":       # (a cpu `dev` only exists in the stub tests)
             chunks = chunks.pin_memory().to(dev, non_blocking=True)      # ONE host->device copy per read
         lengths_d = lengths.to(dev, non_blocking=True)
         builder = TranslationBuilder(_Data(), self.fields, self.n_best)
@@ -266,6 +266,8 @@ class Translator(object):
                                              self.global_scorer.length_penalty, self.global_scorer.alpha)
             dev_t = {"ids": out["ids"], "lens": out["lens"], "scores": out["scores"]}
         if not dev_t["ids"].is_cuda:
+            # only reachable with the recording stub of tests/test_translator_host.py (host-logic tests without a GPU);
+            # Engine itself refuses to exist without CUDA and always returns device tensors — there is no CPU decode
             return dev_t, None
         if not hasattr(self, "_pinned"):
             self._pinned = {}
