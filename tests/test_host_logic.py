@@ -118,3 +118,30 @@ def test_every_documented_option_is_handled_and_vice_versa():
     body = body[: body.index("\n}\n")]
     handled = set(re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', body))
     assert documented == handled, (sorted(documented - handled), sorted(handled - documented))
+
+
+def test_library_sass_is_blackwell_native():
+    """cuobjdump -sass of the built library (no GPU needed): the GEMMs, the LSTM and the encoder attention issue
+    tcgen05.mma (UTC*MMA) with tensor-memory loads / stores (LDTM / STTM), operands arrive by TMA (UTMALDG), the ring
+    cross attention is TMA-fed with packed fp32 FMAs, and no legacy tensor-core path (HMMA) is compiled in."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import sass_inventory as si
+    inv = si.inventory()
+    names = si.demangle(list(inv))
+    by = {}
+    for n, c in zip(names, inv.values()):
+        for prefix in ("gemm_tc_kernel", "gemm_tc_persist_kernel", "lstm_tc_kernel", "enc_attn_tc_kernel",
+                       "enc_attn_tc64_kernel", "cross_attn_ring_kernel"):
+            if n.startswith(prefix + "<") or n == prefix:
+                by.setdefault(prefix, []).append(c)
+    for k in ("gemm_tc_kernel", "gemm_tc_persist_kernel"):
+        assert by[k] and all(c["UTC*MMA"] and c["UTMALDG"] and c["LDTM"] for c in by[k]), k
+    assert any(c["STTM"] for c in by["gemm_tc_persist_kernel"])           # A operand written to tensor memory
+    assert all(c["UTC*MMA"] and c["LDTM"] and c["STAS"] for c in by["lstm_tc_kernel"])
+    assert all(c["UTC*MMA"] and c["LDTM"] and c["STTM"] for c in by["enc_attn_tc_kernel"] + by["enc_attn_tc64_kernel"])
+    assert all(c["UTMALDG"] and c["FFMA2"] for c in by["cross_attn_ring_kernel"])
+    assert sum(c["HMMA"] for c in inv.values()) == 0
