@@ -79,7 +79,11 @@ def test_two_ranks_write_their_own_reads_and_rank0_the_speed_file(tmp_path):
     assert _read(tmp_path / "out" / "speed.txt") == _read(ref / "speed.txt")      # global read order, each read once
 
 
-def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path, threads):
     """run_reads (the CLI's per-rank loop) end to end on CPU: real `.signal` parsing, the reference's chunk table, the
     real Translator mirror over a recording stub engine; host threads prefetch the next group's files and write the
     previous reads.  Every non-empty read gets its files, chunks keep their order and their read's padding width."""
@@ -101,7 +105,7 @@ def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path):
         (src / ("r%02d.signal" % i)).write_text(" ".join(map(str, x)))
         raws.append(x.astype(np.int16))
     opt = _opt(str(tmp_path / "out"), stride=T, length=T)
-    opt.src_dir, opt.thread, opt.batch_size, opt.attn_debug = str(src), 1, B, False      # groups of 8 reads
+    opt.src_dir, opt.thread, opt.batch_size, opt.attn_debug = str(src), threads, B, False   # groups of 8 * threads reads
 
     def frontend(reads):                                                 # chunking only: samples / 1024 as "signal"
         cr, cs = chunk_table([r.size for r in reads], T, T)
