@@ -33,7 +33,7 @@ def demangle(names):
     for n in r:
         n = re.sub(r"(nd::)?\(anonymous namespace\)::", "", n)
         n = re.sub(r"^void ", "", n)
-        n = re.sub(r"\((CUtensorMap_st|nd::|float|int|long|unsigned|const|__).*$", "", n)
+        n = re.sub(r"\(.*$", "", n)                       # argument list (the namespace parenthesis is gone already)
         short.append(n.replace("nd::", ""))
     return short
 
