@@ -205,6 +205,71 @@ def make_case(name, B=6, T=512, max_length=100, beam_size=5, seed=2025, write=Tr
         )
 
 
+# ---- non-degenerate --fast beam cases --------------------------------------------------------------------------
+# With seeded random weights "</s>" is the best step-0 token, so the default-flag beam goldens above hold one-token
+# hypotheses.  The reference's own -min_length flag (translate/translator.py:714-715) keeps "</s>" at -1e20 until
+# step >= min_length: 99 = the bench workload's setting (all beams live for the whole loop), 20 = hypotheses that
+# finish at different steps (retirement, the -1e10 penalty and the n_best bookkeeping of :753-810 are exercised).
+BEAM_CASES = {
+    # file name -> (CASES key, min_length, n_best, alpha)
+    "beam_l2t_d256_min99": ("l2t_d256", 99, 2, 0.0),
+    "beam_l2t_d256_min20": ("l2t_d256", 20, 2, 0.0),
+    "beam_l2t_d256_min20_alpha": ("l2t_d256", 20, 2, 0.7),
+    "beam_t2t_d256_min99": ("t2t_d256", 99, 2, 0.0),
+    "beam_t2t_d256_min20": ("t2t_d256", 20, 2, 0.0),
+    "beam_nano2rnn_d256_min99": ("nano2rnn_d256", 99, 2, 0.0),
+    "beam_nano2rnn_d256_min20": ("nano2rnn_d256", 20, 2, 0.0),
+    "beam_brnn2rnn_d256_min99": ("brnn2rnn_d256", 99, 2, 0.0),
+    "beam_brnn2rnn_d256_min20": ("brnn2rnn_d256", 20, 2, 0.0),
+    "beam_cnn2cnn_d256_min99": ("cnn2cnn_d256", 99, 2, 0.0),
+    "beam_cnn2cnn_d256_min20": ("cnn2cnn_d256", 20, 2, 0.0),
+    "beam_t2t_d512_6x6_min20": ("t2t_d512_6x6", 20, 2, 0.0),
+}
+
+
+def make_beam_case(fname, B=6, T=512, max_length=100, beam_size=5, seed=2025, write=True):
+    """--fast beam of the UNMODIFIED reference with -min_length / -n_best / -alpha; the oracle port must agree."""
+    case, min_length, n_best, alpha = BEAM_CASES[fname]
+    family, kw = CASES[case]
+    if "d512" in case:
+        B = 3
+    cfg = ModelConfig.family(family, **kw)
+    sd = synth.make_state_dict(cfg, seed=seed)
+    chunks, lengths = synth.make_chunks(B, T=T, seed=1234, ragged=True, read_len=3)
+    order = torch.argsort(lengths, descending=True, stable=True)
+    chunks, lengths = chunks[order], lengths[order]
+    src = chunks.t().contiguous().unsqueeze(2)
+    model, fields, mopt = refshim.build_reference_model(
+        family, d=cfg.d_model, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers,
+        heads=cfg.heads, ff=cfg.d_ff, extra=["-global_attention", cfg.global_attention])
+    load_into_reference(model, sd)
+    trb = refshim.build_reference_translator(model, fields, mopt, beam_size=beam_size, fast=True,
+                                             max_length=max_length, min_length=min_length, n_best=n_best, alpha=alpha)
+    t0 = time.time()
+    res = trb.translate_batch(refshim.FakeBatch(src.clone(), lengths.clone()), refshim.FakeData(), False, fast=True)
+    secs = time.time() - t0
+    ref_ids = [[torch.tensor([int(t) for t in h], dtype=torch.long) for h in p[:n_best]] for p in res["predictions"]]
+    ref_scores = torch.tensor([[float(x) for x in s[:n_best]] for s in res["scores"]])
+    ob = odecode.beam_fast(OracleModel(sd, cfg), src, lengths, beam_size=beam_size, max_length=max_length,
+                           min_length=min_length, n_best=n_best, alpha=alpha)
+    same = all(torch.equal(a, b) for pa, pb in zip(ob["predictions"], ref_ids) for a, b in zip(pa, pb))
+    err = (torch.tensor([s[:n_best] for s in ob["scores"]]) - ref_scores).abs().max().item()
+    lens = [[len(h) for h in p] for p in ref_ids]
+    print("%-28s ref --fast beam %.1fs | hypothesis lengths %s | oracle == reference: %s, score err %.2e"
+          % (fname, secs, lens, same, err))
+    assert same and err < 1e-3, "oracle --fast beam differs from the reference"
+    assert min(min(l) for l in lens) > 1, "degenerate hypotheses"
+    if write:
+        np.savez_compressed(
+            os.path.join(GOLDEN_DIR, fname + ".npz"),
+            family=family, cfg_json=np.array(repr(cfg.asdict())), weight_seed=seed, chunk_seed=1234,
+            B=B, T=T, max_length=max_length, beam_size=beam_size, read_len=3, min_length=min_length,
+            n_best=n_best, alpha=np.float32(alpha),
+            src=src[:, :, 0].t().contiguous().numpy(), lengths=lengths.numpy(),
+            beam_ids=np.stack([pad_ragged(p, max_length) for p in ref_ids]),          # [B, n_best, L], -1 padded
+            beam_scores=ref_scores.numpy())
+
+
 def make_frontend_golden(write=True):
     """Front end: run the reference's extract_fast5_raw on '.signal' text files.
 
@@ -310,11 +375,18 @@ def main():
     ap.add_argument("--cases", nargs="*", default=list(CASES))
     ap.add_argument("--no-write", action="store_true")
     ap.add_argument("--B", type=int, default=6)
+    ap.add_argument("--beam-cases", nargs="*", default=None, help="only the non-degenerate --fast beam cases named")
     args = ap.parse_args()
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if args.beam_cases is not None:
+        for name in (args.beam_cases or list(BEAM_CASES)):
+            make_beam_case(name, B=args.B, write=not args.no_write)
+        return
     make_frontend_golden(write=not args.no_write)
     make_assembly_golden(write=not args.no_write)
+    for name in BEAM_CASES:
+        make_beam_case(name, B=args.B, write=not args.no_write)
     for name in args.cases:
         B = args.B if "d512" not in name else 3
         make_case(name, B=B, write=not args.no_write)

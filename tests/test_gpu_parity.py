@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import load_golden, rel_err
+from helpers import BEAM_GOLDEN_CASES, check_beam_against_golden, load_golden, rel_err
 from nanodecoder_b200 import synth
 from nanodecoder_b200.config import ModelConfig
 
@@ -72,6 +72,21 @@ def test_beam_matches_reference_golden(name):
         np.testing.assert_array_equal(ids[i, 0, : lens[i, 0]], want)
         assert (ids[i, 0, lens[i, 0]:] == -1).all()
     np.testing.assert_allclose(scores[:, 0], g["beam_scores"], atol=5e-3)
+
+
+@pytest.mark.parametrize("name", BEAM_GOLDEN_CASES)
+def test_fast_beam_matches_nondegenerate_reference_golden(name):
+    """nd_decode_beam(5, 2, 100, min_len) at d = 256 / 512 against --fast beam outputs of the UNMODIFIED reference run
+    with -min_length 99 (the beam-5 bench workload: every beam lives for 100 steps) and 20 (chunks retire at different
+    steps; -alpha 0.7 in one case): hypotheses of 21 ... 100 tokens, both n_best entries, scores."""
+    g, cfg, sd, src, lengths = load_golden(name)
+    B, T, L, K, NB = src.shape[0], src.shape[1], int(g["max_length"]), int(g["beam_size"]), int(g["n_best"])
+    eng = _engine(cfg, sd, B, T, L, K=K)
+    for rep in range(3):                       # eager, graph capture, graph replay
+        eng.encode(src.cuda(), lengths.cuda())
+        out = eng.decode_beam(K, NB, L, min_len=int(g["min_length"]), alpha=float(g["alpha"]))
+        torch.cuda.synchronize()
+        check_beam_against_golden(g, out["ids"].cpu().numpy(), out["lens"].cpu().numpy(), out["scores"].cpu().numpy())
 
 
 @pytest.mark.parametrize("name", ["l2t_d256", "t2t_d64", "t2t_d512_6x6"])

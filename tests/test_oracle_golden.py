@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, load_golden
+from helpers import GOLDEN_CASES, check_beam_against_golden, load_golden
 from oracle import decode as odecode
 from oracle.model import OracleModel, lstm_direction_explicit
 
@@ -40,6 +40,24 @@ def test_oracle_beam_matches_reference_golden(name):
         want = want[want >= 0]
         np.testing.assert_array_equal(hyp[0].numpy(), want)
     np.testing.assert_allclose([s[0] for s in out["scores"]], g["beam_scores"], atol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["beam_l2t_d256_min20_alpha", "beam_nano2rnn_d256_min20", "beam_cnn2cnn_d256_min20",
+                                  "beam_t2t_d256_min99"])
+def test_oracle_fast_beam_matches_nondegenerate_reference_golden(name):
+    """--fast beam of the unmodified reference with -min_length 99 / 20, -n_best 2 (and -alpha 0.7): hypotheses of
+    21 ... 100 tokens, chunks retiring at different steps (translate/translator.py:714-810)."""
+    g, cfg, sd, src, lengths = load_golden(name)
+    L, K, NB = int(g["max_length"]), int(g["beam_size"]), int(g["n_best"])
+    out = odecode.beam_fast(OracleModel(sd, cfg), src.t().contiguous().unsqueeze(2), lengths, beam_size=K,
+                            max_length=L, min_length=int(g["min_length"]), n_best=NB, alpha=float(g["alpha"]))
+    ids = np.full((len(out["predictions"]), NB, L), -1, dtype=np.int64)
+    lens = np.zeros((ids.shape[0], NB), dtype=np.int64)
+    for i, hyps in enumerate(out["predictions"]):
+        for n in range(NB):
+            lens[i, n] = len(hyps[n])
+            ids[i, n, : lens[i, n]] = hyps[n].numpy()
+    check_beam_against_golden(g, ids, lens, np.array([s[:NB] for s in out["scores"]]), atol=1e-3)
 
 
 @pytest.mark.parametrize("name", ["l2t_d256", "brnn2rnn_d256", "cnn2cnn_d256", "t2t_d64", "l2t_d64"])
