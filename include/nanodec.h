@@ -200,7 +200,15 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *   "gemm_a_tmem"    (default 1, process-wide): the 64-wide one-tile-per-CTA 3xTF32 kernels (decode step) keep the
  *                    A operand in tensor memory like the persistent kernel; 0 = shared memory (same bits);
  *   "gemm_serial_split" (default 1, process-wide): projections with >= 2048 rows run the split-K sum inside one CTA
- *                    (bit-identical to the cluster split), 0 = always the cluster split.                        */
+ *                    (bit-identical to the cluster split), 0 = always the cluster split.
+ * Storage format (changes the stored precision of one intermediate; bounds in DESIGN.md, measured in profiles/):
+ *   "kv_mode"        (default 1): how the Transformer decoder's projected memory keys / values
+ *                    (onmt/modules/multi_headed_attn.py:142-153) are kept between the decode steps of a greedy batch:
+ *                    0 = fp32 rows; 1 = 24-bit fixed point with one power-of-two step per row part (3 bytes per
+ *                    element, absolute error <= the fp32 rounding error of the part's largest element; parity mode);
+ *                    2 = 16-bit fixed point (2 bytes per element; the reduced-precision mode, never the default).
+ *                    Beam search always reads fp32 rows.
+ * Any nd_set_int call drops the engine's captured CUDA graphs (they are re-captured on the following calls).  */
 ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);
 
 /* per-kernel-category device timing for bench.py's roofline figures: while a category bit is set,

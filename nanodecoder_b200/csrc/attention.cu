@@ -346,6 +346,7 @@ void cross_attention_set_beam_kernel(int on) { g_cross_beam_kernel = on; }
 
 cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream) {
   if (p.n_chunks <= 0) return cudaSuccess;
+  if (p.kv_fmt != KV_F32) return cross_attention_packed(p, stream);
   if (p.d % 32 || 32 % p.H || p.NQ > 8 || p.NQ < 1 || (p.d / p.H) % (p.d / 32)) return cudaErrorInvalidValue;
   if (g_cross_beam_kernel == 2 && cross_attention_ring_supported(p)) return cross_attention_ring(p, stream);
   if (g_cross_beam_kernel && p.NQ > 1 && p.d == 256 && p.H == 8 && (p.kv_ld % 8) == 0 &&

@@ -1,0 +1,309 @@
+// Decode-step cross attention over FIXED-POINT memory keys / values (kernels.cuh: KV_Q24 / KV_Q16) and the packer.
+//
+// Reference rows: onmt/modules/multi_headed_attn.py:142-190 through decoder/transformer.py:87-91 (context attention
+// of the Transformer decoder).  The fp32 kernel (attention.cu, cross_attn_kernel) already runs at 98 % of the measured
+// HBM bandwidth and is 55 % of the translate step, so the only way down is fewer bytes: the projected keys / values
+// of a chunk are written ONCE per batch and then re-read dec_layers * max_length (300 ... 600) times, so they are
+// stored as 24-bit fixed point with one power-of-two step per row part (3 bytes per element, the same absolute
+// rounding error fp32 has on the part's largest element) or, as the reduced-precision mode, as 16-bit fixed point.
+//
+// Kernel structure = cross_attn_kernel: one CTA per chunk, lane l owns columns [l*VPL, (l+1)*VPL) of every row, the
+// 32/H lanes of a head combine their partial dot products with xor-shuffles; phases scores / softmax / context.
+// The integers are rebuilt with one PRMT per element (int16 pair register + uint8 quad register -> sign-extended int32),
+// converted with I2F and used UNSCALED: the row's step multiplies the finished score (keys) or the probability
+// (values) once per row instead of once per element.
+#include <float.h>
+
+#include "kernels.cuh"
+
+namespace nd {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// ---- loads: NB contiguous bytes per lane (32 / 16 / 8 / 4 / 2), streaming (read once per step)
+template <int NB>
+__device__ __forceinline__ void load_bytes(const uint8_t* p, uint32_t* r) {
+  if constexpr (NB == 32) {
+    float f[8];
+    ldg_stream8(reinterpret_cast<const float*>(p), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(f[i]);
+  } else if constexpr (NB == 16) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+  } else if constexpr (NB == 8) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
+  } else if constexpr (NB == 4) {
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r[0]) : "l"(p));
+  } else {
+    uint16_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    r[0] = v;
+  }
+}
+
+__device__ __forceinline__ int prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  int d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// element j of a lane's slice as a float holding the (unscaled) integer.  hi: int16 pairs, lo: uint8 quads.
+// prmt selector nibbles: 0-3 = bytes of a (hi pair register), 4-7 = bytes of b (lo quad register), +8 = replicate
+// the sign bit of the selected byte.
+template <int FMT>
+__device__ __forceinline__ float unpack_elem(const uint32_t* hi, const uint32_t* lo, int j) {
+  const uint32_t k = 2u * (j & 1);                                 // byte index of the int16 inside its register
+  if constexpr (FMT == KV_Q24) {
+    const uint32_t sel = (4u + (j & 3)) | (k << 4) | ((k + 1) << 8) | (((k + 1) | 8u) << 12);
+    return __int2float_rn(prmt(hi[j >> 1], lo[j >> 2], sel));
+  } else {
+    const uint32_t sel = k | ((k + 1) << 4) | (((k + 1) | 8u) << 8) | (((k + 1) | 8u) << 12);
+    return __int2float_rn(prmt(hi[j >> 1], 0u, sel));
+  }
+}
+
+template <int VPL, int FMT>
+struct RowRegs {
+  static constexpr int NHI = VPL >= 2 ? VPL / 2 : 1;
+  static constexpr int NLO = VPL >= 4 ? VPL / 4 : 1;
+  uint32_t hi[NHI];
+  uint32_t lo[FMT == KV_Q24 ? NLO : 1];
+  __device__ __forceinline__ void load(const uint8_t* hi_p, const uint8_t* lo_p) {
+    load_bytes<2 * VPL>(hi_p, hi);
+    if constexpr (FMT == KV_Q24) load_bytes<VPL>(lo_p, lo);
+  }
+  __device__ __forceinline__ float get(int j) const { return unpack_elem<FMT>(hi, lo, j); }
+};
+
+// =============================================================================================
+template <int VPL, int NQMAX, int FMT>
+__global__ void __launch_bounds__(kThreads) cross_attn_packed_kernel(CrossAttnParams p) {
+  constexpr int R = VPL >= 16 ? 4 : 8;             // rows in flight per warp iteration (6-12 registers per row)
+  extern __shared__ __align__(16) float smem_f[];
+  const int chunk = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (p.retired && p.retired[chunk]) return;
+  const int d = 32 * VPL, T = p.T, H = p.H, NQ = p.NQ;
+  const int TS = T + 1;
+  const int LPH = 32 / H;
+  float* q_s = smem_f;                            // [NQ][d]
+  float* sc = q_s + NQ * d;                       // [NQ*H][TS]   (later reused as red[warps][NQ*d])
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < NQ * d; i += kThreads) {
+    const int qi = i / d, c = i - qi * d;
+    q_s[i] = p.q[((int64_t)chunk * NQ + qi) * p.q_ld + c] / p.q_div;
+  }
+  __syncthreads();
+
+  const int64_t row0 = (int64_t)chunk * T;
+  const uint8_t* hiK = reinterpret_cast<const uint8_t*>(p.kv_hi) + row0 * (4 * d) + lane * (2 * VPL);
+  const uint8_t* loK = reinterpret_cast<const uint8_t*>(p.kv_lo) + row0 * (2 * d) + lane * VPL;
+  const float* stp = p.kv_scale + row0 * 2;
+  const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
+  const int head = lane / LPH;
+
+  // ---------------- phase 1: scores
+  for (int t0 = warp * R; t0 < T; t0 += kWarps * R) {
+    RowRegs<VPL, FMT> kv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (t0 + r < T) kv[r].load(hiK + (int64_t)(t0 + r) * (4 * d), loK + (int64_t)(t0 + r) * (2 * d));
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = t0 + r;
+      if (t < T) {                                 // warp-uniform
+        const bool masked = srow && (srow[t] == p.mask_value);
+        const float step = stp[2 * t];
+        float kf[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) kf[i] = kv[r].get(i);
+#pragma unroll
+        for (int qi = 0; qi < NQMAX; ++qi) {
+          if (qi < NQ) {
+            const float* qq = q_s + qi * d + lane * VPL;
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) s = fmaf(qq[i], kf[i], s);
+            for (int o = LPH >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(ND_FULL, s, o);
+            if ((lane % LPH) == 0) sc[(qi * H + head) * TS + t] = masked ? -1e18f : s * step;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: softmax rows (torch.softmax: exp(x - max) / sum); the value step of row t is folded
+  // into the probability AFTER the normalisation (and after the optional attention output)
+  for (int row = warp; row < NQ * H; row += kWarps) {
+    float* s = sc + row * TS;
+    float m = -FLT_MAX;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, s[t]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) { const float e = expf(s[t] - m); s[t] = e; sum += e; }
+    sum = warp_sum(sum);
+    float* a = (p.attn && (row % H) == 0) ? p.attn + ((int64_t)chunk * NQ + row / H) * T : nullptr;
+    for (int t = lane; t < T; t += 32) {
+      const float pr = s[t] / sum;
+      if (a) a[t] = pr;
+      s[t] = pr * stp[2 * t + 1];
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3: context
+  float acc[NQMAX][VPL];
+#pragma unroll
+  for (int qi = 0; qi < NQMAX; ++qi)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[qi][i] = 0.f;
+  const uint8_t* hiV = hiK + 2 * d;                // V = columns [d, 2d) of the planes
+  const uint8_t* loV = loK + d;
+  for (int t0 = warp * R; t0 < T; t0 += kWarps * R) {
+    RowRegs<VPL, FMT> vv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (t0 + r < T) vv[r].load(hiV + (int64_t)(t0 + r) * (4 * d), loV + (int64_t)(t0 + r) * (2 * d));
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = t0 + r;
+      if (t < T) {
+        float vf[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) vf[i] = vv[r].get(i);
+#pragma unroll
+        for (int qi = 0; qi < NQMAX; ++qi) {
+          if (qi < NQ) {
+            const float pr = sc[(qi * H + head) * TS + t];
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) acc[qi][i] = fmaf(pr, vf[i], acc[qi][i]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();                                 // scores no longer needed: reuse as reduction buffer
+  float* red = sc;                                 // [warps][NQ*d]
+#pragma unroll
+  for (int qi = 0; qi < NQMAX; ++qi) {
+    if (qi < NQ) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) red[(warp * NQ + qi) * d + lane * VPL + i] = acc[qi][i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * d; i += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w * NQ * d + i];
+    const int qi = i / d, c = i - qi * d;
+    p.ctx[((int64_t)chunk * NQ + qi) * p.ctx_ld + c] = s;
+  }
+}
+
+template <int VPL, int NQMAX, int FMT>
+cudaError_t launch_one(const CrossAttnParams& p, size_t smem, cudaStream_t stream) {
+  static PerDeviceFlag attr_set;
+  bool& set = attr_set.cur();
+  if (!set) {
+    cudaError_t err = cudaFuncSetAttribute(cross_attn_packed_kernel<VPL, NQMAX, FMT>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (err != cudaSuccess) return err;
+    set = true;
+  }
+  launch_k_heavy(cross_attn_packed_kernel<VPL, NQMAX, FMT>, dim3(p.n_chunks), dim3(kThreads), smem, stream, p);
+  return cudaGetLastError();
+}
+
+template <int VPL>
+cudaError_t launch_packed(const CrossAttnParams& p, cudaStream_t stream) {
+  const int d = 32 * VPL;
+  const size_t sc_f = (size_t)p.NQ * p.H * (p.T + 1);
+  const size_t red_f = (size_t)kWarps * p.NQ * d;
+  const size_t smem = ((size_t)p.NQ * d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (p.kv_fmt == KV_Q24)
+    return p.NQ == 1 ? launch_one<VPL, 1, KV_Q24>(p, smem, stream) : launch_one<VPL, 8, KV_Q24>(p, smem, stream);
+  return p.NQ == 1 ? launch_one<VPL, 1, KV_Q16>(p, smem, stream) : launch_one<VPL, 8, KV_Q16>(p, smem, stream);
+}
+
+// =============================================================================================
+// Packer: one warp per (row, part); lane l quantises columns [l*VPL, (l+1)*VPL) of the part.
+template <int VPL>
+__global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ kv, int64_t rows, int fmt,
+                                                      int16_t* __restrict__ hi, uint8_t* __restrict__ lo,
+                                                      float* __restrict__ scale) {
+  constexpr int d = 32 * VPL;
+  const int lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);       // row * 2 + part
+  if (item >= rows * 2) return;
+  const int64_t row = item >> 1;
+  const int part = (int)(item & 1);
+  const float* src = kv + row * (2 * d) + part * d + lane * VPL;
+  float x[VPL];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { x[i] = src[i]; amax = fmaxf(amax, fabsf(x[i])); }
+  amax = warp_max(amax);
+  // 2^e > amax (amax = f * 2^e, f in [0.5, 1)); clamp the exponent so the step stays a normal fp32 number
+  int e = 0;
+  if (amax > 0.f) frexpf(amax, &e);
+  e = max(e, -90);
+  const int bits = fmt == KV_Q24 ? 23 : 15;
+  const float step = ldexpf(1.0f, e - bits);
+  const float inv = ldexpf(1.0f, bits - e);
+  const float lim = fmt == KV_Q24 ? 8388607.0f : 32767.0f;
+  if (lane == 0) scale[row * 2 + part] = step;
+  int16_t* hp = hi + row * (2 * d) + part * d + lane * VPL;
+  uint8_t* lp = lo ? lo + row * (2 * d) + part * d + lane * VPL : nullptr;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int m = (int)fminf(fmaxf(rintf(x[i] * inv), -lim), lim);           // x * 2^k is exact; rint ties to even
+    if (fmt == KV_Q24) {
+      hp[i] = (int16_t)(m >> 8);
+      lp[i] = (uint8_t)(m & 255);
+    } else {
+      hp[i] = (int16_t)m;
+    }
+  }
+}
+
+}  // namespace
+
+bool kv_pack_supported(int d) { return d == 64 || d == 128 || d == 256 || d == 512; }
+
+cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
+                    cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (!kv_pack_supported(d) || (fmt != KV_Q24 && fmt != KV_Q16) || (fmt == KV_Q24 && !lo)) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)cdiv64(rows * 2, 8);
+  switch (d / 32) {
+    case 2: kv_pack_kernel<2><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
+    case 4: kv_pack_kernel<4><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
+    case 8: kv_pack_kernel<8><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
+    default: kv_pack_kernel<16><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream) {
+  if (p.n_chunks <= 0) return cudaSuccess;
+  if (!kv_pack_supported(p.d) || 32 % p.H || p.NQ > 8 || p.NQ < 1 || (p.d / p.H) % (p.d / 32) || !p.kv_hi ||
+      !p.kv_scale || (p.kv_fmt == KV_Q24 && !p.kv_lo))
+    return cudaErrorInvalidValue;
+  switch (p.d / 32) {
+    case 2: return launch_packed<2>(p, stream);
+    case 4: return launch_packed<4>(p, stream);
+    case 8: return launch_packed<8>(p, stream);
+    default: return launch_packed<16>(p, stream);
+  }
+}
+
+}  // namespace nd

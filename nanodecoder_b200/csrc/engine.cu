@@ -129,6 +129,10 @@ struct nd_engine {
   // (profiles/r01_cross_mb_experiment.md) -- kept as an option until its FFMA side is as good as its byte count
   const int* gemm_alive = nullptr;         // set while a beam search runs: GEMMs return at once when it reads 0
   int cross_mode = 0;
+  // storage of the projected memory keys / values (kernels.cuh): KV_F32, KV_Q24 (default: 24-bit fixed point, the
+  // absolute error fp32 has on a row's largest element, 3/4 of the bytes), KV_Q16 (reduced precision, half the bytes)
+  int kv_mode = KV_F32;
+  bool kv_packed = false;                  // set by decoder_init: this decode reads the packed planes
   int enc_attn_tc = 1;                     // Transformer-encoder self attention on the tensor cores when dh = 32
   int* cur_tok = nullptr;
   // rnn decoder
@@ -816,6 +820,18 @@ struct DecodeCtx {
   float* attn_out = nullptr;          // optional [rows_total, T'] for this step
 };
 
+// planes of layer l inside its K/V buffer (sized for fp32 [maxB*maxT, 2d]); offsets follow the LAST encode's B*T'
+struct KvPlanes { int16_t* hi; uint8_t* lo; float* scale; };
+KvPlanes kv_planes(const nd_engine* e, int l) {
+  const size_t n = (size_t)e->B * e->Tp * 2 * e->cfg.d_model;
+  uint8_t* base = reinterpret_cast<uint8_t*>(e->ckv[l]);
+  KvPlanes p;
+  p.hi = reinterpret_cast<int16_t*>(base);
+  p.lo = base + 2 * n;
+  p.scale = reinterpret_cast<float*>(base + 3 * n);
+  return p;
+}
+
 bool use_cross_mb(const nd_engine* e, int K, bool want_attn) {
   return e->cross_mode == 1 && K == 1 && !want_attn && e->cfg.decoder_type == ND_DEC_TRANSFORMER && e->qt != nullptr;
 }
@@ -830,9 +846,19 @@ int decoder_init(nd_engine* e, int K, cudaStream_t st, bool cross_mb = false) {
                                      "mask from the un-pooled signal, decoder/transformer.py:201-221)");
     // memory keys / values, projected once per chunk (multi_headed_attn.py:142-153); not needed when the
     // cross attention runs in memory-bank space
+    // Packed planes: greedy decode only (the beam kernels of cross_attn_ring.cu read fp32 rows); the GEMM writes the
+    // fp32 projection into the encoder's scratch (free once the memory bank exists), the packer re-writes it as
+    // [int16 plane | uint8 plane | steps] into the layer's K/V buffer (3/4 or 1/2 of it).
+    e->kv_packed = !cross_mb && e->kv_mode != KV_F32 && K == 1 && kv_pack_supported(d);
     for (int l = 0; l < c.dec_layers && !cross_mb; ++l) {
       GemmOpt o;
-      ND_TRY(run_gemm(e, e->decT[l].ckv, e->mb, d, e->ckv[l], 2 * d, M, o, st));
+      if (!e->kv_packed) {
+        ND_TRY(run_gemm(e, e->decT[l].ckv, e->mb, d, e->ckv[l], 2 * d, M, o, st));
+        continue;
+      }
+      ND_TRY(run_gemm(e, e->decT[l].ckv, e->mb, d, e->big, 2 * d, M, o, st));
+      KvPlanes pl = kv_planes(e, l);
+      ND_LAUNCH(e, kv_pack(e->big, M, d, e->kv_mode, pl.hi, pl.lo, pl.scale, st));
     }
   } else if (c.decoder_type == ND_DEC_RNN) {
     const int rows = B * K;
@@ -916,6 +942,11 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
         CrossAttnParams ca;
         ca.q = R(e->qc, d); ca.q_ld = d; ca.q_div = sq;
         ca.K = e->ckv[l] + (int64_t)dc.c0 * Tp * 2 * d; ca.V = ca.K + d; ca.kv_ld = 2 * d;
+        if (e->kv_packed) {
+          const KvPlanes pl = kv_planes(e, l);
+          const int64_t r0k = (int64_t)dc.c0 * Tp;
+          ca.kv_fmt = e->kv_mode; ca.kv_hi = pl.hi + r0k * 2 * d; ca.kv_lo = pl.lo + r0k * 2 * d; ca.kv_scale = pl.scale + r0k * 2;
+        }
         ca.src = e->src + (int64_t)dc.c0 * e->T; ca.src_ld = e->T; ca.mask_value = 1.0f;   // decoder/transformer.py:219-221
         ca.retired = retired ? retired + dc.c0 : nullptr; ca.ctx = R(e->cctx, d); ca.ctx_ld = d; ca.n_chunks = dc.nc;
         ca.NQ = K; ca.T = Tp; ca.d = d; ca.H = c.heads;
@@ -1083,7 +1114,9 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
   bp.logp = e->logp; bp.st = e->beam; bp.B = B; bp.K = K; bp.V = e->cfg.vocab_size; bp.Lmax = e->cfg.max_tgt_len;
   bp.max_len = max_len; bp.min_len = min_len; bp.n_best = n_best; bp.alpha = alpha; bp.mode = mode; bp.lp_mode = lp_mode;
   ND_LAUNCH(e, beam_init(bp, 2, st));
-  const int G = n_groups(e, B);
+  // object mode: stop_step / n_done are shared by all chunks (every Beam advances until ALL are done), so chunk
+  // groups on independent streams would see the stop at different steps: one stream
+  const int G = mode == 1 ? 1 : n_groups(e, B);
   if (G > 1) ND_TRY(fork_streams(e, st, G));
   // once every chunk has retired (fast) / every Beam is done (object) the remaining steps only cost their launches
   struct AliveScope { nd_engine* e; ~AliveScope() { e->gemm_alive = nullptr; } } alive_scope{e};
@@ -1360,7 +1393,7 @@ int nd_decode_greedy(nd_engine* e, int32_t max_len, int32_t min_len, int64_t* ou
   if (out_attn || out_logits || e->prof_mask || !e->use_graphs)
     return greedy_body(e, max_len, min_len, out_ids, out_scores, out_attn, out_logits, st);
   const int B = e->B;
-  const std::vector<int64_t> key = {0, B, e->T, e->Tp, max_len, min_len, 1, 1, 0, n_groups(e, B), g_pdl, e->cross_mode};
+  const std::vector<int64_t> key = {0, B, e->T, e->Tp, max_len, min_len, 1, 1, 0, n_groups(e, B), g_pdl, e->cross_mode, e->kv_mode};
   ND_TRY(run_cached(e, key, st, [&](cudaStream_t s2) {
     return greedy_body(e, max_len, min_len, e->o_ids, e->o_scores, nullptr, nullptr, s2);
   }));
@@ -1412,6 +1445,11 @@ int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_best, int32
 
 int nd_set_int(nd_engine* e, const char* name, int64_t value) {
   if (!e || !name) return ND_ERR_INVALID;
+  // captured decode loops bake in the kernel choices of the moment (several switches are process-wide and not part
+  // of the graph key): any option change drops them, the next two calls run eagerly and re-capture
+  for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+  e->last_key.clear();
   if (strcmp(name, "decode_streams") == 0) {
     if (value < 1 || value > 16) return fail(e, ND_ERR_INVALID, "decode_streams must be in [1,16]");
     cudaSetDevice(e->cfg.device);
@@ -1432,6 +1470,11 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
   }
   if (strcmp(name, "cross_mode") == 0) {     // 1: memory-bank-space cross attention for greedy decode, 0: K/V
     e->cross_mode = value != 0;
+    return ND_OK;
+  }
+  if (strcmp(name, "kv_mode") == 0) {        // storage of the memory keys / values: 0 fp32, 1 q24, 2 q16 (kernels.cuh)
+    if (value < 0 || value > 2) return fail(e, ND_ERR_INVALID, "kv_mode must be 0 (fp32), 1 (q24) or 2 (q16)");
+    e->kv_mode = (int)value;
     return ND_OK;
   }
   if (strcmp(name, "gemm_a_tmem") == 0) {         // process-wide

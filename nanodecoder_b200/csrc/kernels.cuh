@@ -21,8 +21,30 @@ struct CrossAttnParams {
   float* ctx = nullptr;      int64_t ctx_ld = 0;  // [n_chunks*NQ, d]
   float* attn = nullptr;                          // optional [n_chunks*NQ, T]: head-0 probabilities
   int n_chunks = 0, NQ = 1, T = 0, d = 0, H = 8;
+  // Packed memory keys / values (kv_fmt != 0; K / V / kv_ld are then unused), see kv_pack below:
+  //   hi [n_chunks*T, 2d] int16 and (q24 only) lo [n_chunks*T, 2d] uint8, K in columns [0,d), V in [d,2d);
+  //   scale [n_chunks*T, 2] = the power-of-two step of the row's K part and V part
+  int kv_fmt = 0;
+  const int16_t* kv_hi = nullptr;
+  const uint8_t* kv_lo = nullptr;
+  const float* kv_scale = nullptr;
 };
 cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream);
+
+// Fixed-point storage of the projected memory keys / values (multi_headed_attn.py:142-153 computes them once per
+// chunk; the decode loop then re-reads them L * Ld times: the bytes that bound the whole translate path).
+//   KV_Q24: every row part (the d keys, or the d values, of one memory position) is stored as 24-bit signed integers
+//           m = rint(x / step), step = 2^(e-23) with 2^e > max|x| of that part: int16 high plane + uint8 low plane
+//           + one fp32 step per part.  |x - m*step| <= step/2 = 2^-24 * 2^e: the absolute rounding error fp32 itself has
+//           on the part's largest element; 3 bytes per element instead of 4.
+//   KV_Q16: m = rint(x / 2^(e-15)) in one int16 plane: |error| <= 2^-16 * 2^e (a bf16 element has 2^-9 |x|);
+//           2 bytes per element.  Reduced-precision mode with a stated, measured bound, never the default.
+enum { KV_F32 = 0, KV_Q24 = 1, KV_Q16 = 2 };
+bool kv_pack_supported(int d);
+// kv [rows, 2d] fp32 (row pitch 2d) -> planes as described in CrossAttnParams
+cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
+                    cudaStream_t stream);
+cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream);   // kv_fmt != 0 (cross_attn_packed.cu)
 // several queries per chunk (beam search) at d = 256, H = 8: 2 (default) persistent CTAs fed by a cp.async.bulk ring
 // (cross_attn_ring.cu), 1 register-prefetch kernel, 0 generic kernel
 void cross_attention_set_beam_kernel(int mode);

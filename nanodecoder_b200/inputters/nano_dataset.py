@@ -91,12 +91,19 @@ class SignalFrontend(object):
     def __call__(self, reads: Sequence[np.ndarray]):
         """reads: list of int16 arrays -> (chunks [n,T] fp32 cuda, lengths [n] int64 cuda,
         chunk_read int32 numpy [n])"""
-        dev = self.engine.device
         lens = np.array([r.size for r in reads], dtype=np.int64)
-        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         flat = np.concatenate([np.ascontiguousarray(r, dtype=np.int16) for r in reads]) if len(reads) else \
             np.zeros((0,), np.int16)
-        sig = torch.from_numpy(flat).to(dev, non_blocking=True)
+        return self.from_flat(torch.from_numpy(flat), lens)
+
+    def from_flat(self, flat: torch.Tensor, read_lengths: Sequence[int]):
+        """flat: the int16 samples of all reads back to back (host tensor, ideally pinned: ONE host->device copy, or
+        already on the device); read_lengths: samples per read.  Same outputs as __call__."""
+        dev = self.engine.device
+        lens = np.asarray(read_lengths, dtype=np.int64)
+        offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        assert flat.dtype == torch.int16 and flat.numel() == int(offsets[-1])
+        sig = flat.to(dev, non_blocking=True)
         off = torch.from_numpy(offsets).to(dev, non_blocking=True)
         center, scale = self.engine.frontend_stats(sig, off, self.normalization)
         cr, cs = chunk_table(lens, self.max_length, self.stride)
