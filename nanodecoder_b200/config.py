@@ -109,6 +109,16 @@ class ModelConfig:
             raise ValueError("-context_gate is outside the supported translate path")
         if g("self_attn_type", "scaled-dot") != "scaled-dot":
             raise ValueError("-self_attn_type average is outside the supported translate path")
+        # flags that change the arithmetic and would otherwise load and decode to wrong bases without an error
+        if g("bridge", False):
+            raise ValueError("-bridge (Linear+ReLU on the encoder final state, encoder/rnn_encoder.py:82-83) is "
+                             "outside the supported translate path")
+        for flag in ("global_attention_function", "generator_function"):
+            if g(flag, "softmax") not in ("softmax", None):
+                raise ValueError("-%s %s is outside the supported translate path (softmax only)" % (flag, g(flag)))
+        if list(vocab_itos[:4]) != SPECIALS:
+            raise ValueError("target vocabulary must start with %s (the engine's <s> / </s> / <blank> ids), got %s"
+                             % (SPECIALS, list(vocab_itos[:4])))
         enc = g("encoder_type", "rnn")
         if enc == "rnn" and g("brnn", False):
             enc = "brnn"

@@ -54,15 +54,30 @@ __device__ __forceinline__ int prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // element j of a lane's slice as a float holding the (unscaled) integer.  hi: int16 pairs, lo: uint8 quads.
 // prmt selector nibbles: 0-3 = bytes of a (hi pair register), 4-7 = bytes of b (lo quad register), +8 = replicate
 // the sign bit of the selected byte.
+// Integer -> float without a conversion instruction: for |m| < 2^22 the bit pattern 0x4B400000 + m is the float
+// 1.5 * 2^23 + m exactly (one IADD on the integer pipe), and subtracting 1.5 * 2^23 is exact (one FADD).
+__device__ __forceinline__ float magic_i2f(int m) { return __int_as_float(m + 0x4B400000) - 12582912.0f; }
+
+__host__ __device__ constexpr bool fmt_has_lo(int fmt) { return fmt == KV_Q24 || fmt == KV_Q23M || fmt == KV_FP24; }
+__host__ __device__ constexpr bool fmt_scaled(int fmt) { return fmt != KV_FP24; }
+
 template <int FMT>
 __device__ __forceinline__ float unpack_elem(const uint32_t* hi, const uint32_t* lo, int j) {
   const uint32_t k = 2u * (j & 1);                                 // byte index of the int16 inside its register
-  if constexpr (FMT == KV_Q24) {
+  if constexpr (FMT == KV_FP24) {
+    // the top 24 bits of an fp32: [hi_b1 | hi_b0 | lo | (byte 0 cleared)]
+    const uint32_t sel = (4u + (j & 3)) | ((4u + (j & 3)) << 4) | (k << 8) | ((k + 1) << 12);
+    return __uint_as_float((uint32_t)prmt(hi[j >> 1], lo[j >> 2], sel) & 0xffffff00u);
+  } else if constexpr (fmt_has_lo(FMT)) {
     const uint32_t sel = (4u + (j & 3)) | (k << 4) | ((k + 1) << 8) | (((k + 1) | 8u) << 12);
-    return __int2float_rn(prmt(hi[j >> 1], lo[j >> 2], sel));
+    const int m = prmt(hi[j >> 1], lo[j >> 2], sel);
+    if constexpr (FMT == KV_Q24) return __int2float_rn(m);
+    return magic_i2f(m);
   } else {
     const uint32_t sel = k | ((k + 1) << 4) | (((k + 1) | 8u) << 8) | (((k + 1) | 8u) << 12);
-    return __int2float_rn(prmt(hi[j >> 1], 0u, sel));
+    const int m = prmt(hi[j >> 1], 0u, sel);
+    if constexpr (FMT == KV_Q16) return __int2float_rn(m);
+    return magic_i2f(m);
   }
 }
 
@@ -71,10 +86,10 @@ struct RowRegs {
   static constexpr int NHI = VPL >= 2 ? VPL / 2 : 1;
   static constexpr int NLO = VPL >= 4 ? VPL / 4 : 1;
   uint32_t hi[NHI];
-  uint32_t lo[FMT == KV_Q24 ? NLO : 1];
+  uint32_t lo[fmt_has_lo(FMT) ? NLO : 1];
   __device__ __forceinline__ void load(const uint8_t* hi_p, const uint8_t* lo_p) {
     load_bytes<2 * VPL>(hi_p, hi);
-    if constexpr (FMT == KV_Q24) load_bytes<VPL>(lo_p, lo);
+    if constexpr (fmt_has_lo(FMT)) load_bytes<VPL>(lo_p, lo);
   }
   __device__ __forceinline__ float get(int j) const { return unpack_elem<FMT>(hi, lo, j); }
 };
@@ -119,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) cross_attn_packed_kernel(CrossAttnPa
       const int t = t0 + r;
       if (t < T) {                                 // warp-uniform
         const bool masked = srow && (srow[t] == p.mask_value);
-        const float step = stp[2 * t];
+        const float step = fmt_scaled(FMT) ? stp[2 * t] : 1.0f;
         float kf[VPL];
 #pragma unroll
         for (int i = 0; i < VPL; ++i) kf[i] = kv[r].get(i);
@@ -153,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) cross_attn_packed_kernel(CrossAttnPa
     for (int t = lane; t < T; t += 32) {
       const float pr = s[t] / sum;
       if (a) a[t] = pr;
-      s[t] = pr * stp[2 * t + 1];
+      s[t] = fmt_scaled(FMT) ? pr * stp[2 * t + 1] : pr;
     }
   }
   __syncthreads();
@@ -229,9 +244,14 @@ cudaError_t launch_packed(const CrossAttnParams& p, cudaStream_t stream) {
   const size_t red_f = (size_t)kWarps * p.NQ * d;
   const size_t smem = ((size_t)p.NQ * d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  if (p.kv_fmt == KV_Q24)
-    return p.NQ == 1 ? launch_one<VPL, 1, KV_Q24>(p, smem, stream) : launch_one<VPL, 8, KV_Q24>(p, smem, stream);
-  return p.NQ == 1 ? launch_one<VPL, 1, KV_Q16>(p, smem, stream) : launch_one<VPL, 8, KV_Q16>(p, smem, stream);
+  switch (p.kv_fmt) {
+    case KV_Q24: return p.NQ == 1 ? launch_one<VPL, 1, KV_Q24>(p, smem, stream) : launch_one<VPL, 8, KV_Q24>(p, smem, stream);
+    case KV_Q16: return p.NQ == 1 ? launch_one<VPL, 1, KV_Q16>(p, smem, stream) : launch_one<VPL, 8, KV_Q16>(p, smem, stream);
+    case KV_Q23M: return p.NQ == 1 ? launch_one<VPL, 1, KV_Q23M>(p, smem, stream) : launch_one<VPL, 8, KV_Q23M>(p, smem, stream);
+    case KV_Q15M: return p.NQ == 1 ? launch_one<VPL, 1, KV_Q15M>(p, smem, stream) : launch_one<VPL, 8, KV_Q15M>(p, smem, stream);
+    case KV_FP24: return p.NQ == 1 ? launch_one<VPL, 1, KV_FP24>(p, smem, stream) : launch_one<VPL, 8, KV_FP24>(p, smem, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 // =============================================================================================
@@ -256,17 +276,25 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
   int e = 0;
   if (amax > 0.f) frexpf(amax, &e);
   e = max(e, -90);
-  const int bits = fmt == KV_Q24 ? 23 : 15;
+  const int bits = fmt == KV_Q24 ? 23 : (fmt == KV_Q23M ? 22 : 15);
   const float step = ldexpf(1.0f, e - bits);
   const float inv = ldexpf(1.0f, bits - e);
-  const float lim = fmt == KV_Q24 ? 8388607.0f : 32767.0f;
-  if (lane == 0) scale[row * 2 + part] = step;
+  const float lim = ldexpf(1.0f, bits) - 1.0f;
+  if (lane == 0) scale[row * 2 + part] = fmt == KV_FP24 ? 1.0f : step;
   int16_t* hp = hi + row * (2 * d) + part * d + lane * VPL;
   uint8_t* lp = lo ? lo + row * (2 * d) + part * d + lane * VPL : nullptr;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
+    if (fmt == KV_FP24) {
+      // fp32 rounded to nearest-even at 16 significant bits: the top 24 bits of the pattern
+      const uint32_t b = __float_as_uint(x[i]);
+      const uint32_t r = (b + 0x7fu + ((b >> 8) & 1u)) >> 8;
+      hp[i] = (int16_t)(r >> 8);
+      lp[i] = (uint8_t)(r & 255u);
+      continue;
+    }
     const int m = (int)fminf(fmaxf(rintf(x[i] * inv), -lim), lim);           // x * 2^k is exact; rint ties to even
-    if (fmt == KV_Q24) {
+    if (fmt == KV_Q24 || fmt == KV_Q23M) {
       hp[i] = (int16_t)(m >> 8);
       lp[i] = (uint8_t)(m & 255);
     } else {
@@ -282,7 +310,7 @@ bool kv_pack_supported(int d) { return d == 64 || d == 128 || d == 256 || d == 5
 cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
                     cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  if (!kv_pack_supported(d) || (fmt != KV_Q24 && fmt != KV_Q16) || (fmt == KV_Q24 && !lo)) return cudaErrorInvalidValue;
+  if (!kv_pack_supported(d) || fmt < KV_Q24 || fmt > KV_FP24 || (fmt_has_lo(fmt) && !lo)) return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)cdiv64(rows * 2, 8);
   switch (d / 32) {
     case 2: kv_pack_kernel<2><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
@@ -296,7 +324,7 @@ cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, 
 cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream) {
   if (p.n_chunks <= 0) return cudaSuccess;
   if (!kv_pack_supported(p.d) || 32 % p.H || p.NQ > 8 || p.NQ < 1 || (p.d / p.H) % (p.d / 32) || !p.kv_hi ||
-      !p.kv_scale || (p.kv_fmt == KV_Q24 && !p.kv_lo))
+      !p.kv_scale || (fmt_has_lo(p.kv_fmt) && !p.kv_lo))
     return cudaErrorInvalidValue;
   switch (p.d / 32) {
     case 2: return launch_packed<2>(p, stream);

@@ -5,6 +5,7 @@
 
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -74,6 +75,7 @@ struct nd_engine {
   int n_sm = 148;
   int64_t launches = 0;
   std::map<std::string, HostTensor> raw;
+  std::set<std::string> used;          // checkpoint tensors the packer consumed (finalize() rejects leftovers)
   std::vector<void*> allocs;
   bool finalized = false;
   bool oom = false;
@@ -318,6 +320,7 @@ int run_gemm(nd_engine* e, const Lin& l, const float* A, int64_t lda, float* C, 
 // ------------------------------------------------------------------------------------------ weights
 const HostTensor* find(nd_engine* e, const std::string& k) {
   auto it = e->raw.find(k);
+  if (it != e->raw.end()) e->used.insert(k);
   return it == e->raw.end() ? nullptr : &it->second;
 }
 int need(nd_engine* e, const std::string& k, std::vector<int64_t> shape, const HostTensor** out) {
@@ -622,6 +625,21 @@ int finalize(nd_engine* e) {
     e->gen.N = V; e->gen.K = d; e->gen.ld = d;
   }
   if (e->oom) return fail(e, ND_ERR_NOMEM, "device allocation failed while packing weights: " + e->err);
+  // A floating-point tensor nothing consumed means the checkpoint holds a module this engine does not run (e.g.
+  // encoder.bridge.*): decoding would silently produce other bases than the reference.  Known aliases / dead weights:
+  // the weight-norm convs' training copies (eval uses the *_avg buffers, onmt/modules/weight_norm.py:154-156).
+  std::string left;
+  int n_left = 0;
+  for (auto& kv : e->raw) {
+    const std::string& k = kv.first;
+    if (e->used.count(k)) continue;
+    auto ends = [&](const char* sfx) { const size_t n = strlen(sfx); return k.size() >= n && k.compare(k.size() - n, n, sfx) == 0; };
+    if (ends(".conv.weight") || ends(".conv.bias") || ends(".conv.V") || ends(".conv.g") || ends(".conv.b")) continue;
+    if (n_left++ < 6) left += (left.empty() ? "" : ", ") + k;
+  }
+  if (n_left)
+    return fail(e, ND_ERR_WEIGHT, "checkpoint holds " + std::to_string(n_left) + " tensor(s) this engine does not use (" +
+                                      left + (n_left > 6 ? ", ..." : "") + "): unsupported model variant");
   e->raw.clear();
   return ND_OK;
 }
@@ -1473,7 +1491,7 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     return ND_OK;
   }
   if (strcmp(name, "kv_mode") == 0) {        // storage of the memory keys / values: 0 fp32, 1 q24, 2 q16 (kernels.cuh)
-    if (value < 0 || value > 2) return fail(e, ND_ERR_INVALID, "kv_mode must be 0 (fp32), 1 (q24) or 2 (q16)");
+    if (value < 0 || value > KV_FP24) return fail(e, ND_ERR_INVALID, "kv_mode must be in [0, 5] (nanodec.h)");
     e->kv_mode = (int)value;
     return ND_OK;
   }

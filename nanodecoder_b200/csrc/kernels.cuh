@@ -39,7 +39,9 @@ cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream);
 //           on the part's largest element; 3 bytes per element instead of 4.
 //   KV_Q16: m = rint(x / 2^(e-15)) in one int16 plane: |error| <= 2^-16 * 2^e (a bf16 element has 2^-9 |x|);
 //           2 bytes per element.  Reduced-precision mode with a stated, measured bound, never the default.
-enum { KV_F32 = 0, KV_Q24 = 1, KV_Q16 = 2 };
+//   KV_Q23M / KV_Q15M: the same with one bit less and the integers rebuilt as floats by exponent arithmetic instead
+//           of a conversion instruction; KV_FP24: the top 24 bits of the fp32 value (16 significant bits, no step).
+enum { KV_F32 = 0, KV_Q24 = 1, KV_Q16 = 2, KV_Q23M = 3, KV_Q15M = 4, KV_FP24 = 5 };
 bool kv_pack_supported(int d);
 // kv [rows, 2d] fp32 (row pitch 2d) -> planes as described in CrossAttnParams
 cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,

@@ -81,6 +81,16 @@ def gather_bytes(payload: bytes, dst: int = 0, group=None) -> Optional[List[byte
     return [bytes(bufs[r][: sizes[r]].cpu().numpy().tobytes()) for r in range(ws)]
 
 
+def broadcast_object(obj, src: int = 0, group=None):
+    """The same picklable object on every rank (the job's read table, built once on `src`)."""
+    rank, ws = world()
+    if ws == 1:
+        return obj
+    box = [obj if rank == src else None]
+    dist.broadcast_object_list(box, src=src, group=group, device=_comm_device(group))
+    return box[0]
+
+
 def gather_records(records: Sequence[tuple], dst: int = 0, group=None) -> Optional[List[tuple]]:
     """Per-read result records, e.g. (read_index, name, fasta_text, segment_lines, seconds, n_bases), from
     every rank -> one list on `dst`, sorted by the first field (the global read index)."""

@@ -41,6 +41,15 @@ def chunks_for(n, seed):
     return chunks[order].contiguous(), lengths[order].contiguous()
 
 
+def oracle_slices(n, slice_b):
+    """The GPU decodes all n chunks (sorted by length, longest first) as ONE batch padded to T; the CPU oracle takes
+    them in slices.  A slice must be padded to the same width (the Transformer decoder attends the padding,
+    decoder/transformer.py:219-221, and the reference pads a batch to its longest chunk), so every slice is a strided
+    pick i, i + k, i + 2k ... of the sorted list: it starts with a full-length chunk and stays sorted."""
+    k = (n + slice_b - 1) // slice_b
+    return [torch.arange(i, n, k) for i in range(k)]
+
+
 def greedy_case(family, kw, n, slice_b, opts_list):
     """-> one row per engine option set (the oracle runs once)"""
     cfg = ModelConfig.family(family, **kw)
@@ -59,24 +68,23 @@ def greedy_case(family, kw, n, slice_b, opts_list):
     om = OracleModel(sd, cfg)
     acc = [dict(same=0, worst=0.0, explain=[]) for _ in opts_list]
     t0 = time.time()
-    for s in range(0, n, slice_b):
-        e = min(n, s + slice_b)
+    for sel in oracle_slices(n, slice_b):
         trace = []
-        want = od.greedy(om, chunks[s:e].t().contiguous().unsqueeze(2), lengths[s:e], max_length=L, trace_logits=trace)
+        want = od.greedy(om, chunks[sel].t().contiguous().unsqueeze(2), lengths[sel], max_length=L, trace_logits=trace)
         tr = torch.stack(trace)                                      # [L, b, V]
         for (ids, logits), a in zip(gpu, acc):
-            for j in range(e - s):
-                if torch.equal(ids[s + j], want["predictions"][j]):
+            for j, c in enumerate(sel.tolist()):
+                if torch.equal(ids[c], want["predictions"][j]):
                     a["same"] += 1
-                    rel = float((logits[:, s + j] - tr[:, j]).abs().max() / tr[:, j].abs().max())
+                    rel = float((logits[:, c] - tr[:, j]).abs().max() / tr[:, j].abs().max())
                     a["worst"] = max(a["worst"], rel)
                 else:
-                    t = int((ids[s + j] != want["predictions"][j]).nonzero()[0])
+                    t = int((ids[c] != want["predictions"][j]).nonzero()[0])
                     lp = tr[t, j]
-                    x, y = int(want["predictions"][j][t]), int(ids[s + j, t])
-                    a["explain"].append({"chunk": s + j, "step": t, "oracle_tok": x, "gpu_tok": y,
+                    x, y = int(want["predictions"][j][t]), int(ids[c, t])
+                    a["explain"].append({"chunk": c, "step": t, "oracle_tok": x, "gpu_tok": y,
                                          "oracle_logp_gap": float(lp[x] - lp[y]),
-                                         "gpu_logp_gap": float(logits[t, s + j, x] - logits[t, s + j, y])})
+                                         "gpu_logp_gap": float(logits[t, c, x] - logits[t, c, y])})
     secs = round(time.time() - t0, 1)
     return [{"family": family, "cfg": kw, "mode": "greedy", "engine_opts": opts, "chunks": n, "identical": a["same"],
              "rate": a["same"] / n, "max_rel_logit_err_identical_chunks": a["worst"], "n_mismatch": len(a["explain"]),
@@ -98,20 +106,19 @@ def beam_case(family, kw, min_len, n, slice_b, opts, K=5, NB=1):
     om = OracleModel(sd, cfg)
     same, explain, hist = 0, [], []
     t0 = time.time()
-    for s in range(0, n, slice_b):
-        e = min(n, s + slice_b)
-        want = od.beam_fast(om, chunks[s:e].t().contiguous().unsqueeze(2), lengths[s:e], beam_size=K, max_length=L,
+    for sel in oracle_slices(n, slice_b):
+        want = od.beam_fast(om, chunks[sel].t().contiguous().unsqueeze(2), lengths[sel], beam_size=K, max_length=L,
                             min_length=min_len, n_best=NB)
-        for j in range(e - s):
+        for j, c in enumerate(sel.tolist()):
             w = want["predictions"][j][0]
-            g = ids[s + j, 0, : int(lens[s + j, 0])]
+            g = ids[c, 0, : int(lens[c, 0])]
             hist.append(len(w))
             if torch.equal(g, w):
                 same += 1
             else:
-                explain.append({"chunk": s + j, "oracle_len": len(w), "gpu_len": int(lens[s + j, 0]),
-                                "oracle_score": float(want["scores"][j][0]), "gpu_score": float(sc[s + j, 0]),
-                                "score_gap": float(want["scores"][j][0]) - float(sc[s + j, 0])})
+                explain.append({"chunk": c, "oracle_len": len(w), "gpu_len": int(lens[c, 0]),
+                                "oracle_score": float(want["scores"][j][0]), "gpu_score": float(sc[c, 0]),
+                                "score_gap": float(want["scores"][j][0]) - float(sc[c, 0])})
     return {"family": family, "cfg": kw, "mode": "--fast beam %d, min_length %d" % (K, min_len), "chunks": n,
             "identical": same, "rate": same / n, "hyp_len_min": min(hist), "hyp_len_mean": sum(hist) / len(hist),
             "mismatches": explain[:20], "oracle_cpu_seconds": round(time.time() - t0, 1)}

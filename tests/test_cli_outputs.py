@@ -104,6 +104,8 @@ def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path, threads):
         x = rng.integers(300, 900, size=n)
         (src / ("r%02d.signal" % i)).write_text(" ".join(map(str, x)))
         raws.append(x.astype(np.int16))
+    (src / "r11.signal").write_text("512 garbage 7")                     # a corrupt read: reported and skipped, per read
+    sizes.append(0)
     opt = _opt(str(tmp_path / "out"), stride=T, length=T)
     opt.src_dir, opt.thread, opt.batch_size, opt.attn_debug = str(src), threads, B, False   # groups of 8 * threads reads
 

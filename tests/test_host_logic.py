@@ -145,3 +145,21 @@ def test_library_sass_is_blackwell_native():
     assert all(c["UTC*MMA"] and c["LDTM"] and c["STTM"] for c in by["enc_attn_tc_kernel"] + by["enc_attn_tc64_kernel"])
     assert all(c["UTMALDG"] and c["FFMA2"] for c in by["cross_attn_ring_kernel"])
     assert sum(c["HMMA"] for c in inv.values()) == 0
+
+
+def test_model_flags_that_change_the_arithmetic_are_refused():
+    """ModelConfig.from_opt (models/model_builder.py:65-214): a checkpoint trained with a module the engine does not run
+    must fail at load, not decode to other bases."""
+    import pytest
+    from nanodecoder_b200.config import ModelConfig, SPECIALS
+    vocab = SPECIALS + ["A", "C", "G", "T"]
+    base = ModelConfig.family("brnn2rnn").to_opt()
+    assert ModelConfig.from_opt(base, vocab).encoder_type == "brnn"
+    for flag, value in (("bridge", True), ("global_attention_function", "sparsemax"), ("generator_function", "sparsemax"),
+                        ("copy_attn", True), ("context_gate", "both"), ("self_attn_type", "average")):
+        opt = ModelConfig.family("brnn2rnn").to_opt()
+        setattr(opt, flag, value)
+        with pytest.raises(ValueError):
+            ModelConfig.from_opt(opt, vocab)
+    with pytest.raises(ValueError):
+        ModelConfig.from_opt(base, ["<unk>", "<s>", "<blank>", "</s>", "A", "C", "G", "T"])     # specials out of order

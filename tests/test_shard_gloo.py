@@ -44,6 +44,9 @@ def _worker(rank, ws, init_file, out_dir):
         merged = shard.gather_records(recs, dst=0)
         raw = shard.gather_bytes(b"" if rank == 1 else b"\x00\x01rank0", dst=0)
         units, secs = shard.reduce_throughput(sum(sizes[i] for i in mine), 1.0 + rank)
+        # the job's read table exists once (rank 0's listing): ranks never partition from their own directory listing
+        table = shard.broadcast_object(([("a.signal", "signal", "a.txt")], [7], 3) if rank == 0 else None, src=0)
+        assert table == ([("a.signal", "signal", "a.txt")], [7], 3)
         if rank == 0:
             assert [r[0] for r in merged] == list(range(len(sizes)))
             assert all(r[2] == "ACGT"[r[0] % 4] * sizes[r[0]] for r in merged)
@@ -68,3 +71,4 @@ def test_single_process_paths_need_no_process_group():
     assert shard.gather_bytes(b"abc") == [b"abc"]
     assert shard.gather_records([(1, "b"), (0, "a")]) == [(0, "a"), (1, "b")]
     assert shard.reduce_throughput(10, 2.0) == (10.0, 2.0)
+    assert shard.broadcast_object({"x": 1}) == {"x": 1}

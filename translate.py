@@ -59,8 +59,21 @@ def run_reads(opt, todo_mine, read_signal, frontend, translator):
     -> [(global read index, speed.txt line)] of the reads written."""
     from concurrent.futures import ThreadPoolExecutor
     from nanodecoder_b200.inputters.nano_dataset import reference_pad_lengths
-    pool_reads = max(1, opt.thread * 8)                          # reads pooled per GPU front-end launch
+    # reads pooled per GPU front-end launch; -attn_debug writes attention/<read>.txt per read (translate.py:110-111
+    # of the reference opens the file and calls setAttnFile before every translate call), so reads go one by one
+    pool_reads = 1 if opt.attn_debug else max(1, opt.thread * 8)
     groups = [todo_mine[g0: g0 + pool_reads] for g0 in range(0, len(todo_mine), pool_reads)]
+
+    def load_one(path, suffix, name):
+        # a read that cannot be loaded (corrupt file, unsupported content) is reported and skipped like the
+        # reference does per read (its pool.apply_async swallows the worker's exception, translate.py:154-161;
+        # the writer prints '!!!error!!!', :97-98) -- it must not take the run (or, under torchrun, the other
+        # ranks waiting in the final gather) down
+        try:
+            return read_signal(path, suffix)
+        except Exception as e:                                   # noqa: BLE001
+            print("!!!error!!!data src: %s (%s: %s)" % (name.split(".txt")[0], type(e).__name__, e))
+            return np.zeros((0,), dtype=np.int16)
 
     def write_one(idx, out_name, preds, seconds):
         try:
@@ -72,7 +85,7 @@ def run_reads(opt, todo_mine, read_signal, frontend, translator):
     writes = []
     with ThreadPoolExecutor(max_workers=max(1, opt.thread)) as ex:
         def load(group):
-            return [ex.submit(read_signal, os.path.join(opt.src_dir, fn), suffix) for _, (fn, suffix, _) in group]
+            return [ex.submit(load_one, os.path.join(opt.src_dir, fn), suffix, out) for _, (fn, suffix, out) in group]
 
         nxt = load(groups[0]) if groups else None
         for gi, group in enumerate(groups):
@@ -89,8 +102,17 @@ def run_reads(opt, todo_mine, read_signal, frontend, translator):
             sels = [np.nonzero(chunk_read == j)[0] for j in range(len(keep))]
             for sel in sels:
                 pad_to[sel] = reference_pad_lengths(h_len[sel], opt.batch_size)
-            _, preds = translator.translate(src=(chunks, lengths, pad_to), tgt=None, src_dir=opt.save_data,
-                                            batch_size=opt.batch_size, attn_debug=opt.attn_debug)
+            attn_file = None
+            if opt.attn_debug:
+                attn_file = open(os.path.join(opt.save_data, "attention", group[keep[0]][1][2]), "w")
+                translator.setAttnFile(attn_file)
+            try:
+                _, preds = translator.translate(src=(chunks, lengths, pad_to), tgt=None, src_dir=opt.save_data,
+                                                batch_size=opt.batch_size, attn_debug=opt.attn_debug)
+            finally:
+                if attn_file is not None:
+                    translator.setAttnFile(None)
+                    attn_file.close()
             elapsed = time.time() - start
             total = max(1, len(chunk_read))
             for j, i in enumerate(keep):
@@ -125,6 +147,20 @@ def finish_records(opt, records):
     finish_lines(opt, lines)
 
 
+def list_reads(opt):
+    """-> (todo [(file name, suffix, out name)], file sizes, number of reads that already have a result)."""
+    todo, done = [], 0
+    for fn in sorted(os.listdir(opt.src_dir)):
+        for suffix in ("fast5", "signal"):
+            if fn.endswith(suffix):
+                out = fn[: -len(suffix) - 1] + ".txt"
+                if os.path.exists(os.path.join(opt.save_data, "result", out.split(".txt")[0] + ".fasta")):
+                    done += 1                                    # translate.py:152 (resume semantics)
+                else:
+                    todo.append((fn, suffix, out))
+    return todo, [os.path.getsize(os.path.join(opt.src_dir, t[0])) for t in todo], done
+
+
 def main(opt, logger):
     from nanodecoder_b200.inputters.nano_dataset import SignalFrontend
     from nanodecoder_b200.translate.translator import build_translator
@@ -143,22 +179,20 @@ def main(opt, logger):
     translator = build_translator(opt, report_score=False, logger=logger)
     frontend = SignalFrontend(translator.model, opt.normalization_raw, opt.src_seq_length, opt.src_seq_stride)
 
-    todo, done = [], 0
-    for fn in sorted(os.listdir(opt.src_dir)):
-        for suffix in ("fast5", "signal"):
-            if fn.endswith(suffix):
-                out = fn[: -len(suffix) - 1] + ".txt"
-                if os.path.exists(os.path.join(opt.save_data, "result", out.split(".txt")[0] + ".fasta")):
-                    done += 1                                    # translate.py:152 (resume semantics)
-                else:
-                    todo.append((fn, suffix, out))
-    logger.info("%d reads have already translated, remains %d read\n" % (done, len(todo)))
-
-    # reads shard across the ranks of a torchrun launch (one process per GPU, no collective inside the step);
-    # every rank derives the same partition from the file sizes
     rank, ws = shard.world()
-    mine = shard.partition_reads([os.path.getsize(os.path.join(opt.src_dir, t[0])) for t in todo], ws)[rank]
-    finish_lines(opt, run_reads(opt, [(i, todo[i]) for i in mine], read_raw_signal, frontend, translator))
+    todo, sizes, done = list_reads(opt) if rank == 0 else ([], [], 0)
+    # ONE listing for the whole job: rank 0 lists the directory (and applies the "already has result/<read>.fasta"
+    # resume rule) and broadcasts the table.  Ranks listing on their own race with faster ranks that already write
+    # .fasta files: the tables differ, the index-based partitions diverge and reads are skipped or decoded twice.
+    todo, sizes, done = shard.broadcast_object((todo, sizes, done), src=0)
+    logger.info("%d reads have already translated, remains %d read\n" % (done, len(todo)))
+    # reads shard across the ranks of a torchrun launch (one process per GPU, no collective inside the step)
+    mine = shard.partition_reads(sizes, ws)[rank]
+    lines = []
+    try:
+        lines = run_reads(opt, [(i, todo[i]) for i in mine], read_raw_signal, frontend, translator)
+    finally:
+        finish_lines(opt, lines)                                 # every rank always enters the final gather
 
 
 if __name__ == "__main__":
