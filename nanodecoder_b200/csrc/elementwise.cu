@@ -27,20 +27,14 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 }
 
 __global__ void embed_kernel(const int* __restrict__ tok, const float* __restrict__ emb, float* __restrict__ x,
-                             int64_t x_ld, int rows, int d, int pos_enc, int step) {
+                             int64_t x_ld, int rows, int d, const float* __restrict__ pe_row, float emb_scale) {
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x;
   const int t = tok[row];
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     float v = emb[(int64_t)t * d + c];
-    if (pos_enc) {
-      // onmt/modules/embeddings.py:24-29,36-41: emb*sqrt(d) + pe[step]
-      const int i2 = c & ~1;
-      const float div = expf((float)i2 * -(logf(10000.0f) / (float)d));
-      const float ang = (float)step * div;
-      v = v * sqrtf((float)d) + ((c & 1) ? cosf(ang) : sinf(ang));
-    }
+    if (pe_row) v = v * emb_scale + pe_row[c];     // onmt/modules/embeddings.py:36-41: emb * sqrt(d) + pe[step]
     x[(int64_t)row * x_ld + c] = v;
   }
 }
@@ -207,10 +201,10 @@ cudaError_t layernorm_rows(const float* x, const float* g, const float* b, float
   return cudaGetLastError();
 }
 
-cudaError_t embed_rows(const int* tok, const float* emb, float* x, int64_t x_ld, int rows, int d, int pos_enc,
-                       int step, cudaStream_t stream) {
+cudaError_t embed_rows(const int* tok, const float* emb, float* x, int64_t x_ld, int rows, int d, const float* pe_row,
+                       float emb_scale, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  launch_k(embed_kernel, dim3(rows), dim3(d < 256 ? d : 256), 0, stream, tok, emb, x, x_ld, rows, d, pos_enc, step);
+  launch_k(embed_kernel, dim3(rows), dim3(d < 256 ? d : 256), 0, stream, tok, emb, x, x_ld, rows, d, pe_row, emb_scale);
   return cudaGetLastError();
 }
 

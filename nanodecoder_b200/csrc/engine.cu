@@ -95,6 +95,7 @@ struct nd_engine {
   std::vector<DecLayerT> decT;
   LnW dec_ln;
   const float* emb = nullptr;        // [V,d]
+  const float* pe = nullptr;         // [max_tgt_len, d] rows of the checkpoint's PositionalEncoding buffer (or null)
   Lin gen;                           // generator (W, b)
   // rnn decoder
   struct RnnCell { Lin ih_e, ih_f, ih, hh; };
@@ -551,6 +552,16 @@ int finalize(nd_engine* e) {
     const HostTensor* em;
     ND_TRY(need(e, "decoder.embeddings.make_embedding.emb_luts.0.weight", {V, d}, &em));
     e->emb = upload(e, em->f);
+    if (c.position_encoding) {
+      // the sinusoid table is a registered buffer of the reference's PositionalEncoding (onmt/modules/embeddings.py:
+      // 21-32) and travels in the checkpoint: use ITS values (no re-derivation with other sin / cos / exp roundings)
+      const HostTensor* pe = find(e, "decoder.embeddings.make_embedding.pe.pe");
+      if (!pe || pe->shape.size() != 3 || pe->shape[1] != 1 || pe->shape[2] != d)
+        return fail(e, ND_ERR_WEIGHT, "position_encoding: checkpoint lacks decoder.embeddings.make_embedding.pe.pe [n,1,d]");
+      if (pe->shape[0] < c.max_tgt_len)
+        return fail(e, ND_ERR_WEIGHT, "position_encoding table is shorter than max_tgt_len");
+      e->pe = upload(e, std::vector<float>(pe->f.begin(), pe->f.begin() + (size_t)c.max_tgt_len * d));
+    }
   }
   if (c.decoder_type == ND_DEC_TRANSFORMER) {
     e->decT.resize(c.dec_layers);
@@ -927,7 +938,12 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
   const int* anc = (dc.beam && dc.step > 0) ? e->beam.anc + (int64_t)(dc.step & 1) * B_total * K * dc.Lmax : nullptr;
   auto R = [&](float* p, int64_t w) { return p + (int64_t)r0 * w; };            // row-range view
   const float s2 = 0.70710678118654757f;                                        // SCALE_WEIGHT = 0.5 ** 0.5
-  ND_LAUNCH(e, embed_rows(e->cur_tok + r0, e->emb, R(e->x, d), d, rows, d, c.position_encoding, dc.step, st));
+  // position of this step's token in the sinusoid table: the Transformer decoder passes `step` (decoder/transformer.py:
+  // 214), the CNN decoder embeds the whole prefix (position = index, cnn_decoder.py:89), the RNN decoders call the
+  // embeddings WITHOUT a step on a one-token input, i.e. every token gets row 0 (onmt/decoders/decoder.py:323)
+  const int pe_pos = c.decoder_type == ND_DEC_RNN ? 0 : dc.step;
+  ND_LAUNCH(e, embed_rows(e->cur_tok + r0, e->emb, R(e->x, d), d, rows, d, e->pe ? e->pe + (int64_t)pe_pos * d : nullptr,
+                          (float)sqrt((double)d), st));
   if (c.decoder_type == ND_DEC_TRANSFORMER) {
     const float sq = sqrtf((float)(d / c.heads));
     float* x = R(e->x, d);

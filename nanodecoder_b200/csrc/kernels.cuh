@@ -121,9 +121,9 @@ cudaError_t mlp_attention(const MlpAttnParams& p, cudaStream_t stream);
 // ---------------------------------------------------------------------------------------------
 cudaError_t layernorm_rows(const float* x, const float* g, const float* b, float eps, float* y,
                            int64_t M, int d, cudaStream_t stream);
-// x[row] = emb[tok[row]] (* sqrt(d) + pe(step) when pos_enc)
+// x[row] = emb[tok[row]] (* emb_scale + pe_row[:] when pe_row: the checkpoint's positional-encoding row of this step)
 cudaError_t embed_rows(const int* tok, const float* emb, float* x, int64_t x_ld, int rows, int d,
-                       int pos_enc, int step, cudaStream_t stream);
+                       const float* pe_row, float emb_scale, cudaStream_t stream);
 // y[b,t,:] = w[:] * x[b,t] + bias[:]   (Linear(1,d): encoder/transformer.py:113, cnn_encoder.py:38)
 cudaError_t linear_in1(const float* x, const float* w, const float* bias, float* y, int64_t n, int d,
                        cudaStream_t stream);

@@ -105,6 +105,18 @@ FAMILY_GAINS = {
 }
 
 
+def positional_encoding_table(dim: int, max_len: int = 5000) -> torch.Tensor:
+    """The registered buffer ``pe`` of the reference's PositionalEncoding (onmt/modules/embeddings.py:21-32), built
+    with the same fp32 torch ops, so a synthetic checkpoint carries what a trained one would: [max_len, 1, dim]."""
+    import math
+    pe = torch.zeros(max_len, dim)
+    position = torch.arange(0, max_len).unsqueeze(1)
+    div_term = torch.exp((torch.arange(0, dim, 2, dtype=torch.float) * -(math.log(10000.0) / dim)))
+    pe[:, 0::2] = torch.sin(position.float() * div_term)
+    pe[:, 1::2] = torch.cos(position.float() * div_term)
+    return pe.unsqueeze(1)
+
+
 def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> Dict[str, torch.Tensor]:
     """Flat state dict: reference ``model.state_dict()`` keys incl. ``generator.0.*``."""
     b = _Builder(seed)
@@ -150,6 +162,8 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
 
     # ---------------- decoder
     b.normal("decoder.embeddings.make_embedding.emb_luts.0.weight", (V, d), G["emb_std"])
+    if cfg.position_encoding:
+        b.sd["decoder.embeddings.make_embedding.pe.pe"] = positional_encoding_table(d)
     if cfg.decoder_type == "transformer":       # decoder/transformer.py:145-171
         for l in range(cfg.dec_layers):
             p = "decoder.transformer_layers.%d" % l

@@ -54,7 +54,19 @@ CASES = {
     # reference's command-line default)
     "nano2rnn_general_d64": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, global_attention="general")),
     "brnn2rnn_dot_d64": ("brnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, global_attention="dot")),
+    # -position_encoding (onmt/modules/embeddings.py:36-43): the three decoders pass different positions
+    "t2t_pe_d64": ("t2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2, position_encoding=True)),
+    "nano2rnn_pe_d64": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, position_encoding=True)),
+    "cnn2cnn_pe_d64": ("cnn2cnn", dict(d_model=64, enc_layers=2, dec_layers=2, position_encoding=True)),
 }
+
+
+def ref_extra(cfg):
+    """command-line flags of the reference for the config fields beyond the family defaults"""
+    extra = ["-global_attention", cfg.global_attention]
+    if cfg.position_encoding:
+        extra.append("-position_encoding")
+    return extra
 
 
 def load_into_reference(model, sd):
@@ -74,7 +86,7 @@ def load_into_reference(model, sd):
 def run_reference(family, cfg, sd, src, lengths, max_length, beam_size):
     model, fields, mopt = refshim.build_reference_model(
         family, d=cfg.d_model, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers,
-        heads=cfg.heads, ff=cfg.d_ff, extra=["-global_attention", cfg.global_attention])
+        heads=cfg.heads, ff=cfg.d_ff, extra=ref_extra(cfg))
     load_into_reference(model, sd)
     assert list(fields["tgt"].vocab.itos) == cfg.vocab
     out = {}
@@ -241,7 +253,7 @@ def make_beam_case(fname, B=6, T=512, max_length=100, beam_size=5, seed=2025, wr
     src = chunks.t().contiguous().unsqueeze(2)
     model, fields, mopt = refshim.build_reference_model(
         family, d=cfg.d_model, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers,
-        heads=cfg.heads, ff=cfg.d_ff, extra=["-global_attention", cfg.global_attention])
+        heads=cfg.heads, ff=cfg.d_ff, extra=ref_extra(cfg))
     load_into_reference(model, sd)
     trb = refshim.build_reference_translator(model, fields, mopt, beam_size=beam_size, fast=True,
                                              max_length=max_length, min_length=min_length, n_best=n_best, alpha=alpha)

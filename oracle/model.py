@@ -219,7 +219,7 @@ class TransformerDecoder(object):
                                         self_values=None) for _ in range(cfg.dec_layers)]
         emb = F.embedding(tgt[:, :, 0], sd["decoder.embeddings.make_embedding.emb_luts.0.weight"])
         if cfg.position_encoding:                                   # onmt/modules/embeddings.py:36-43
-            emb = emb * math.sqrt(cfg.d_model) + _positional_encoding(cfg.d_model, step, emb)
+            emb = emb * math.sqrt(cfg.d_model) + _positional_encoding(cfg.d_model, step, emb, sd.get("decoder.embeddings.make_embedding.pe.pe"))
         out = emb.transpose(0, 1).contiguous()                      # [B',1,d]
         mem = memory_bank.transpose(0, 1).contiguous()              # [B',T,d]
         # pad_idx is the TARGET <blank> id (1) compared against the raw signal value   :219-221
@@ -240,7 +240,10 @@ class TransformerDecoder(object):
         return out.transpose(0, 1).contiguous(), attn.transpose(0, 1).contiguous()
 
 
-def _positional_encoding(dim, step, like):
+def _positional_encoding(dim, step, like, table=None):
+    """onmt/modules/embeddings.py:21-32,36-41: row `step` of the registered buffer when the checkpoint carries it."""
+    if table is not None:
+        return table[step].to(like)
     pos = torch.tensor([[float(step)]])
     div = torch.exp(torch.arange(0, dim, 2, dtype=torch.float) * -(math.log(10000.0) / dim))
     pe = torch.zeros(1, dim)
@@ -296,6 +299,9 @@ class InputFeedRNNDecoder(object):
     def __call__(self, tgt, memory_bank, memory_lengths=None, step=None):
         sd, cfg = self.sd, self.cfg
         emb_t = F.embedding(tgt[0, :, 0], sd["decoder.embeddings.make_embedding.emb_luts.0.weight"])
+        if cfg.position_encoding:       # decoder.py:323 calls the embeddings without a step: a one-token input gets pe[0]
+            emb_t = emb_t * math.sqrt(cfg.d_model) + _positional_encoding(
+                cfg.d_model, 0, emb_t, sd.get("decoder.embeddings.make_embedding.pe.pe")).view(1, -1)
         x = torch.cat([emb_t, self.state["input_feed"].squeeze(0)], 1) if cfg.input_feed else emb_t
         h0, c0 = self.state["hidden"]
         h1, c1 = [], []
@@ -338,6 +344,10 @@ class CNNDecoder(object):
         if prev is not None:
             tgt = torch.cat([prev, tgt], 0)                         # :79-80
         emb = F.embedding(tgt[:, :, 0], sd["decoder.embeddings.make_embedding.emb_luts.0.weight"])
+        if cfg.position_encoding:       # cnn_decoder.py:89: the whole prefix is embedded, position = index
+            emb = emb * math.sqrt(cfg.d_model) + torch.stack([_positional_encoding(
+                cfg.d_model, t, emb, sd.get("decoder.embeddings.make_embedding.pe.pe")).view(1, -1)
+                for t in range(emb.size(0))])
         tgt_emb = emb.transpose(0, 1).contiguous()                  # [B',t,d]
         enc_top = memory_bank.transpose(0, 1).contiguous()          # [B',d,T]
         enc_comb = self.state["src"].transpose(0, 1).contiguous()   # [B',d,T]

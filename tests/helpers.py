@@ -10,7 +10,8 @@ from nanodecoder_b200.config import ModelConfig
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["l2t_d256", "t2t_d256", "nano2rnn_d256", "brnn2rnn_d256", "cnn2cnn_d256", "l2t_d64", "t2t_d64",
-                "t2t_d512_6x6", "nano2rnn_general_d64", "brnn2rnn_dot_d64"]
+                "t2t_d512_6x6", "nano2rnn_general_d64", "brnn2rnn_dot_d64", "t2t_pe_d64", "nano2rnn_pe_d64",
+                "cnn2cnn_pe_d64"]
 
 
 def load_golden(name):
@@ -33,13 +34,25 @@ BEAM_GOLDEN_CASES = ["beam_l2t_d256_min99", "beam_l2t_d256_min20", "beam_l2t_d25
                      "beam_cnn2cnn_d256_min20", "beam_t2t_d512_6x6_min20"]
 
 
-def check_beam_against_golden(g, ids, lens, scores, atol=5e-3):
-    """ids [B,n_best,L], lens [B,n_best], scores [B,n_best] (numpy) vs a beam_* golden of the reference's --fast beam."""
+def check_beam_against_golden(g, ids, lens, scores, atol=5e-3, tie=1e-4):
+    """ids [B,n_best,L], lens [B,n_best], scores [B,n_best] (numpy) vs a beam_* golden of the reference's --fast beam.
+    north_star: "beam outputs match ... any divergence explained by a logit tie": a hypothesis may differ from the
+    reference's only if its cumulative score equals the reference's to within `tie` (a few fp32 ulps of a score of
+    ~ -130: e.g. the reference's own 2nd and 3rd hypotheses of beam_nano2rnn_d256_min99 chunk 2 are -131.399216 and
+    -131.399231, one ulp apart, and swap places under any reassociation).  -> number of such tie swaps."""
     B, NB = g["beam_ids"].shape[:2]
+    swaps = 0
     for i in range(B):
         for n in range(NB):
             want = g["beam_ids"][i, n]
             want = want[want >= 0]
             assert len(want) > 1                                  # the point of these cases: non-degenerate hypotheses
-            np.testing.assert_array_equal(ids[i, n, : int(lens[i, n])], want, err_msg="chunk %d hyp %d" % (i, n))
+            got = ids[i, n, : int(lens[i, n])]
+            if len(got) == len(want) and (got == want).all():
+                continue
+            gap = abs(float(scores[i, n]) - float(g["beam_scores"][i, n]))
+            assert gap <= tie, "chunk %d hyp %d differs and is no tie (score gap %.3g):\n%s\n%s" % (i, n, gap, got, want)
+            swaps += 1
     np.testing.assert_allclose(scores[:, :NB], g["beam_scores"], atol=atol)
+    assert swaps <= max(1, (B * NB) // 10), "%d of %d hypotheses are tie swaps" % (swaps, B * NB)
+    return swaps
