@@ -201,13 +201,17 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *                    A operand in tensor memory like the persistent kernel; 0 = shared memory (same bits);
  *   "gemm_serial_split" (default 1, process-wide): projections with >= 2048 rows run the split-K sum inside one CTA
  *                    (bit-identical to the cluster split), 0 = always the cluster split.
+ *   "cross_packed_fast" (default 1, process-wide): greedy cross attention over fixed-point keys / values at d = 256 /
+ *                    512 as the 256-column-slice kernel (1: 2 CTAs per SM, 2: 3 CTAs per SM), 0 = generic kernel.
  * Storage format (changes the stored precision of one intermediate; bounds in DESIGN.md, measured in profiles/):
- *   "kv_mode"        (default 1): how the Transformer decoder's projected memory keys / values
+ *   "kv_mode"        (default 3): how the Transformer decoder's projected memory keys / values
  *                    (onmt/modules/multi_headed_attn.py:142-153) are kept between the decode steps of a greedy batch:
- *                    0 = fp32 rows; 1 = 24-bit fixed point with one power-of-two step per row part (3 bytes per
- *                    element, absolute error <= the fp32 rounding error of the part's largest element; parity mode);
- *                    2 = 16-bit fixed point (2 bytes per element; the reduced-precision mode, never the default).
- *                    Beam search always reads fp32 rows.
+ *                    0 = fp32 rows; 3 = 23-bit fixed point with one power-of-two step per row part (3 bytes per
+ *                    element, absolute error <= 2^-23 of the part's largest element; parity mode: identical greedy
+ *                    sequences and identity rates to fp32 storage, profiles/r02_identity_rates.md);
+ *                    4 = 15-bit fixed point (2 bytes per element; the reduced-precision mode, never the default);
+ *                    5 = the top 24 bits of the fp32 value; 1 / 2 = 24 / 16-bit fixed point decoded with conversion
+ *                    instructions (cross-checks).  Beam search always reads fp32 rows.
  * Any nd_set_int call drops the engine's captured CUDA graphs (they are re-captured on the following calls).  */
 ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);
 

@@ -223,6 +223,221 @@ __global__ void __launch_bounds__(kThreads) cross_attn_packed_kernel(CrossAttnPa
   }
 }
 
+
+// =============================================================================================
+// Fast path: one query per chunk (greedy), 256-column slices.  The generic kernel above spends ~12 instructions per
+// element (run-time lanes-per-head modulo and shuffle loop, 64-bit address arithmetic and predicates per row, the
+// query re-read from shared memory per row): at 3 bytes per element it is issue-bound (58 % issue-active at 32 %
+// occupancy, profiles/r02_kv_formats.md) and no faster than the fp32 kernel.  Here
+//   * a CTA owns ONE 256-column slice of a chunk (d = 256: the chunk; d = 512: heads 0-3 or 4-7 -- heads are
+//     independent, so the slices need no exchange and the grid doubles),
+//   * lane l owns columns [8l, 8l+8) of the slice, LPH = 4 (d = 256) or 8 (d = 512) lanes share a head; all of that is
+//     compile-time,
+//   * the query lives in 8 registers, the row steps and the key mask (sign of the step) in shared memory,
+//   * rows go in blocks of LPH: the LPH x LPH (lane, row) partial sums are reduce-scattered with LPH - 1 shuffles, lane j
+//     finishes row j and every lane stores one score (no predicates),
+//   * 8 rows (6 KB per warp) are requested before the first is consumed; <= 80 registers -> 3 CTAs (24 warps, 144 KB of
+//     loads in flight) per SM; a 64-register build spills the row registers.
+// one stage of the reduce-scatter: lanes whose bit W is set keep the upper W values, the others the lower W
+template <int W>
+__device__ __forceinline__ void rs_stage(float* v, int lane) {
+  const bool up = (lane & W) != 0;
+#pragma unroll
+  for (int r = 0; r < W; ++r) {
+    const float keep = up ? v[r + W] : v[r];
+    const float send = up ? v[r] : v[r + W];
+    v[r] = keep + __shfl_xor_sync(ND_FULL, send, W);
+  }
+}
+
+template <int LPH, int FMT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(CrossAttnParams p, int split) {
+  constexpr int VPL = 8, DS = 256, HP = 32 / LPH, RB = 8;       // slice width, heads per slice, rows per iteration
+  extern __shared__ __align__(16) float smem_f[];
+  const int chunk = blockIdx.x / split, part = blockIdx.x - chunk * split;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (p.retired && p.retired[chunk]) return;
+  const int T = p.T, d = p.d;
+  const int Tup = (T + RB - 1) & ~(RB - 1);
+  const int TS = Tup + LPH;                      // score pitch: lanes of a block hit 32 distinct banks, 16-byte multiple
+  float* sc = smem_f;                            // [HP][TS]   (later red[warps][DS])
+  float* kstep = sc + (HP * TS > kWarps * DS ? HP * TS : kWarps * DS);   // [Tup] key step, negative = masked key
+  float* vstep = kstep + Tup;                    // [Tup]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = lane / LPH, j = lane % LPH;
+  const int64_t row0 = (int64_t)chunk * T;
+
+  float qr[VPL];
+  {
+    const float* qp = p.q + (int64_t)chunk * p.q_ld + part * DS + lane * VPL;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) qr[i] = qp[i] / p.q_div;
+  }
+  {
+    const float* stp = p.kv_scale + row0 * 2;
+    const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
+    for (int t = threadIdx.x; t < Tup; t += kThreads) {
+      float ks = 1.0f, vs = 1.0f;
+      if (t < T) {
+        if (fmt_scaled(FMT)) { ks = stp[2 * t]; vs = stp[2 * t + 1]; }
+        if (srow && srow[t] == p.mask_value) ks = -ks;
+      }
+      kstep[t] = ks;
+      vstep[t] = vs;
+    }
+  }
+  __syncthreads();
+
+  const uint32_t hi_pitch = 4u * d, lo_pitch = 2u * d;          // bytes per row of the planes ([K | V] columns)
+  const uint8_t* hiK = reinterpret_cast<const uint8_t*>(p.kv_hi) + row0 * hi_pitch + part * (2 * DS) + lane * (2 * VPL);
+  const uint8_t* loK = reinterpret_cast<const uint8_t*>(p.kv_lo) + row0 * lo_pitch + part * DS + lane * VPL;
+  const int nit = Tup / RB;
+
+  // ---------------- phase 1: scores
+  for (int it = warp; it < nit; it += kWarps) {
+    const int t0 = it * RB;
+    RowRegs<VPL, FMT> rr[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (t0 + r < T) {
+        rr[r].load(hiK + (uint32_t)(t0 + r) * hi_pitch, loK + (uint32_t)(t0 + r) * lo_pitch);
+      } else {
+#pragma unroll
+        for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[r].hi[i] = 0u;
+        rr[r].lo[0] = 0u;
+        if (fmt_has_lo(FMT)) rr[r].lo[RowRegs<VPL, FMT>::NLO - 1] = 0u;
+      }
+    }
+#pragma unroll
+    for (int b0 = 0; b0 < RB; b0 += LPH) {
+      float v[LPH];
+#pragma unroll
+      for (int r = 0; r < LPH; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], rr[b0 + r].get(i), s);
+        v[r] = s;
+      }
+      // reduce-scatter over the LPH lanes of the head: lane j ends with the complete sum of row j
+      if constexpr (LPH == 8) rs_stage<4>(v, lane);
+      rs_stage<2>(v, lane);
+      rs_stage<1>(v, lane);
+      const int t = t0 + b0 + j;
+      const float ks = kstep[t];
+      sc[head * TS + t] = ks < 0.f ? -1e18f : v[0] * ks;         // rows >= T: finite junk, never read by the softmax
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: softmax rows (torch.softmax: exp(x - max) / sum); afterwards the row holds
+  // probability * value step, zero beyond T
+  for (int row = warp; row < HP; row += kWarps) {
+    float* s = sc + row * TS;
+    float m = -FLT_MAX;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, s[t]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) { const float e = expf(s[t] - m); s[t] = e; sum += e; }
+    sum = warp_sum(sum);
+    float* a = (p.attn && part == 0 && row == 0) ? p.attn + (int64_t)chunk * T : nullptr;
+    for (int t = lane; t < Tup; t += 32) {
+      float pr = 0.f;
+      if (t < T) {
+        pr = s[t] / sum;
+        if (a) a[t] = pr;
+        pr *= vstep[t];
+      }
+      s[t] = pr;
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3: context
+  float acc[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
+  const uint8_t* hiV = hiK + 2 * d;                // V = columns [d, 2d) of the planes
+  const uint8_t* loV = loK + d;
+  for (int it = warp; it < nit; it += kWarps) {
+    const int t0 = it * RB;
+    RowRegs<VPL, FMT> rr[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (t0 + r < T) {
+        rr[r].load(hiV + (uint32_t)(t0 + r) * hi_pitch, loV + (uint32_t)(t0 + r) * lo_pitch);
+      } else {
+#pragma unroll
+        for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[r].hi[i] = 0u;
+        rr[r].lo[0] = 0u;
+        if (fmt_has_lo(FMT)) rr[r].lo[RowRegs<VPL, FMT>::NLO - 1] = 0u;
+      }
+    }
+    const float4 pa = *reinterpret_cast<const float4*>(sc + head * TS + t0);
+    const float4 pb = *reinterpret_cast<const float4*>(sc + head * TS + t0 + 4);
+    const float pr[RB] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) acc[i] = fmaf(pr[r], rr[r].get(i), acc[i]);
+  }
+  __syncthreads();                                 // scores no longer needed: reuse as reduction buffer
+  float* red = sc;                                 // [warps][DS]
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) red[warp * DS + lane * VPL + i] = acc[i];
+  __syncthreads();
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w * DS + threadIdx.x];
+    p.ctx[(int64_t)chunk * p.ctx_ld + part * DS + threadIdx.x] = s;
+  }
+}
+
+template <int LPH, int FMT, int MINB>
+cudaError_t launch_fast(const CrossAttnParams& p, cudaStream_t stream) {
+  const int split = p.d / 256;
+  const int Tup = (p.T + 7) & ~7, HP = 32 / LPH;
+  const size_t sc_f = (size_t)HP * (Tup + LPH), red_f = (size_t)kWarps * 256;
+  const size_t smem = ((sc_f > red_f ? sc_f : red_f) + 2 * (size_t)Tup) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static PerDeviceFlag attr_set;
+  bool& set = attr_set.cur();
+  if (!set) {
+    cudaError_t err = cudaFuncSetAttribute(cross_attn_packed_fast_kernel<LPH, FMT, MINB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (err != cudaSuccess) return err;
+    set = true;
+  }
+  launch_k_heavy(cross_attn_packed_fast_kernel<LPH, FMT, MINB>, dim3(p.n_chunks * split), dim3(kThreads), smem, stream, p, split);
+  return cudaGetLastError();
+}
+
+// one query per chunk, 8 heads, d = 256 or 512, planes 32-byte aligned
+bool fast_supported(const CrossAttnParams& p) {
+  return p.NQ == 1 && p.H == 8 && (p.d == 256 || p.d == 512) && p.kv_fmt >= KV_Q23M && p.kv_fmt <= KV_FP24 &&
+         (reinterpret_cast<uintptr_t>(p.kv_hi) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.kv_lo) & 15) == 0 &&
+         (int64_t)p.T * 4 * p.d < (int64_t)1 << 31;
+}
+
+int g_packed_fast = 1;     // 1: <= 128 registers, 2 CTAs per SM; 2: <= 80 registers (some row registers spill), 3 CTAs; 0: generic kernel
+
+template <int LPH>
+cudaError_t launch_fast_fmt(const CrossAttnParams& p, cudaStream_t stream) {
+  if (g_packed_fast == 2) {
+    switch (p.kv_fmt) {
+      case KV_Q23M: return launch_fast<LPH, KV_Q23M, 3>(p, stream);
+      case KV_Q15M: return launch_fast<LPH, KV_Q15M, 3>(p, stream);
+      default: return launch_fast<LPH, KV_FP24, 3>(p, stream);
+    }
+  }
+  switch (p.kv_fmt) {
+    case KV_Q23M: return launch_fast<LPH, KV_Q23M, 2>(p, stream);
+    case KV_Q15M: return launch_fast<LPH, KV_Q15M, 2>(p, stream);
+    default: return launch_fast<LPH, KV_FP24, 2>(p, stream);
+  }
+}
+
 template <int VPL, int NQMAX, int FMT>
 cudaError_t launch_one(const CrossAttnParams& p, size_t smem, cudaStream_t stream) {
   static PerDeviceFlag attr_set;
@@ -305,6 +520,8 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
 
 }  // namespace
 
+void cross_attention_packed_set_fast(int on) { g_packed_fast = on; }
+
 bool kv_pack_supported(int d) { return d == 64 || d == 128 || d == 256 || d == 512; }
 
 cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
@@ -326,6 +543,7 @@ cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream
   if (!kv_pack_supported(p.d) || 32 % p.H || p.NQ > 8 || p.NQ < 1 || (p.d / p.H) % (p.d / 32) || !p.kv_hi ||
       !p.kv_scale || (fmt_has_lo(p.kv_fmt) && !p.kv_lo))
     return cudaErrorInvalidValue;
+  if (g_packed_fast && fast_supported(p)) return p.d == 256 ? launch_fast_fmt<4>(p, stream) : launch_fast_fmt<8>(p, stream);
   switch (p.d / 32) {
     case 2: return launch_packed<2>(p, stream);
     case 4: return launch_packed<4>(p, stream);

@@ -1511,6 +1511,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     e->kv_mode = (int)value;
     return ND_OK;
   }
+  if (strcmp(name, "cross_packed_fast") == 0) {   // process-wide
+    cross_attention_packed_set_fast((int)value);
+    return ND_OK;
+  }
   if (strcmp(name, "gemm_a_tmem") == 0) {         // process-wide
     gemm_tc_set_a_tmem(value != 0);
     return ND_OK;
