@@ -61,6 +61,11 @@ __global__ void maxpool_kernel(const float* __restrict__ in, float* __restrict__
   out[i] = m;
 }
 
+__global__ void pool_lengths_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int B, int stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) out[i] = (int64_t)floor((double)(in[i] - stride) / (double)stride + 1.0);      // nano_encoder.py:103-104
+}
+
 __global__ void transpose_bt_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int d) {
   // one CTA per (b, t) row of d floats
   const int64_t r = blockIdx.x;
@@ -219,6 +224,12 @@ cudaError_t maxpool_time(const float* in, float* out, int B, int T, int d, int s
   const int64_t n = (int64_t)B * (T / stride) * d;
   if (n <= 0) return cudaSuccess;
   maxpool_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, stream>>>(in, out, B, T, d, stride);
+  return cudaGetLastError();
+}
+
+cudaError_t pool_lengths(const int64_t* in, int64_t* out, int B, int stride, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  pool_lengths_kernel<<<cdiv(B, 256), 256, 0, stream>>>(in, out, B, stride);
   return cudaGetLastError();
 }
 

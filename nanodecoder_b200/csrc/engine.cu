@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/nanodec.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -110,7 +112,6 @@ struct nd_engine {
   float* src = nullptr;              // [maxB, maxT]
   int64_t* lengths = nullptr;        // [maxB]
   int64_t* mem_len = nullptr;        // [maxB]
-  std::vector<int64_t> h_lengths;    // host mirror of the last encode (pooling arithmetic is host side)
   float* bufA = nullptr; float* bufB = nullptr;    // [maxB*maxT, d] activations ping-pong
   float* bufC = nullptr;                            // [maxB*maxT, d]
   float* big = nullptr;              // [maxB*maxT, max(4d, 3d, ff, k*d)] xg / qkv / ffn hidden / im2col
@@ -317,6 +318,13 @@ int run_gemm(nd_engine* e, const Lin& l, const float* A, int64_t lda, float* C, 
   return ND_OK;
 }
 #define ND_TRY(expr) do { int _rc = (expr); if (_rc != ND_OK) return _rc; } while (0)
+
+// NVTX range over the host-side enqueue of one phase (encode / memory K,V / decode loop): nsys and ncu --nvtx group the
+// kernels of a phase by it; header-only NVTX v3 resolves its injection library lazily, so without a tool it is a no-op
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------ weights
 const HostTensor* find(nd_engine* e, const std::string& k) {
@@ -585,13 +593,16 @@ int finalize(nd_engine* e) {
   } else if (c.decoder_type == ND_DEC_RNN) {
     e->cells.resize(c.dec_layers);
     for (int l = 0; l < c.dec_layers; ++l) {
-      const std::string p = "decoder.rnn.layers." + std::to_string(l);
+      // InputFeedRNNDecoder: StackedLSTM of LSTMCells "decoder.rnn.layers.<l>.weight_ih" (stacked_rnn.py:15-20);
+      // StdRNNDecoder (-input_feed 0, decoder.py:187-262): one multi-layer nn.LSTM "decoder.rnn.weight_ih_l<l>"
+      const std::string p = c.input_feed ? "decoder.rnn.layers." + std::to_string(l) + "." : "decoder.rnn.";
+      const std::string sfx = c.input_feed ? "" : "_l" + std::to_string(l);
       const int in = l == 0 ? (c.input_feed ? 2 * d : d) : d;
       const HostTensor *wi, *wh, *bi, *bh;
-      ND_TRY(need(e, p + ".weight_ih", {4 * d, in}, &wi));
-      ND_TRY(need(e, p + ".weight_hh", {4 * d, d}, &wh));
-      ND_TRY(need(e, p + ".bias_ih", {4 * d}, &bi));
-      ND_TRY(need(e, p + ".bias_hh", {4 * d}, &bh));
+      ND_TRY(need(e, p + "weight_ih" + sfx, {4 * d, in}, &wi));
+      ND_TRY(need(e, p + "weight_hh" + sfx, {4 * d, d}, &wh));
+      ND_TRY(need(e, p + "bias_ih" + sfx, {4 * d}, &bi));
+      ND_TRY(need(e, p + "bias_hh" + sfx, {4 * d}, &bh));
       e->cells[l].ih = make_lin(e, wi->f, 4 * d, in, &bi->f);
       e->cells[l].hh = make_lin(e, wh->f, 4 * d, d, &bh->f);
       if (l == 0 && c.input_feed) {
@@ -736,7 +747,9 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
   const int dirs = (c.encoder_type == ND_ENC_RNN) ? 1 : 2;
   const int H = d / dirs;
   int T = e->T;
-  std::vector<int64_t> lens = e->h_lengths;
+  // lengths the layers see: the source lengths until a pooling layer shortens them -- on the device (the reference
+  // does lengths.tolist() and the arithmetic in Python, nano_encoder.py:90,103-104; here nothing leaves the stream)
+  const int64_t* lens_dev = e->lengths;
   const float* in = nullptr;                // previous layer output [B,T,d]
   float* outs[2] = {e->bufA, e->bufB};
   float* last = nullptr;
@@ -745,7 +758,7 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
     float* out = outs[l & 1];
     LstmParams p;
     p.B = B; p.T = T; p.dirs = dirs; p.H = H;
-    p.w_hh = W.w_hh; p.b_hh = W.b_hh; p.lengths = e->lengths; p.out = out;
+    p.w_hh = W.w_hh; p.b_hh = W.b_hh; p.lengths = lens_dev; p.out = out;
     if (l == 0) {
       p.x0 = e->src; p.w_ih0 = W.w_ih0; p.b_ih0 = W.b_ih0;
     } else {
@@ -767,9 +780,8 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
       ND_LAUNCH(e, maxpool_time(out, pooled, B, T, d, s, st));
       ND_CUDA(e, cudaMemcpyAsync(out, pooled, (size_t)B * Tn * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
       T = Tn;
-      for (auto& v : lens) v = (int64_t)floor((double)(v - s) / (double)s + 1.0);
-      ND_CUDA(e, cudaMemcpyAsync(e->lengths, lens.data(), lens.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-      ND_CUDA(e, cudaStreamSynchronize(st));      // lens (host vector) is reused below
+      ND_LAUNCH(e, pool_lengths(lens_dev, e->mem_len, B, s, st));       // mem_len doubles as the working copy
+      lens_dev = e->mem_len;
     }
     in = out;
   }
@@ -781,11 +793,8 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
   } else {
     ND_CUDA(e, cudaMemcpyAsync(e->mb, last, (size_t)B * T * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
-  ND_CUDA(e, cudaMemcpyAsync(e->mem_len, e->lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-  if (nano && lens != e->h_lengths) {
-    // restore the source lengths (the decoder's reference state keeps the pooled ones in mem_len)
-    ND_CUDA(e, cudaMemcpyAsync(e->lengths, e->h_lengths.data(), (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  }
+  if (lens_dev != e->mem_len)
+    ND_CUDA(e, cudaMemcpyAsync(e->mem_len, e->lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   return ND_OK;
 }
 
@@ -866,6 +875,7 @@ bool use_cross_mb(const nd_engine* e, int K, bool want_attn) {
 }
 
 int decoder_init(nd_engine* e, int K, cudaStream_t st, bool cross_mb = false) {
+  NvtxRange nvtx("nd:decoder_init (memory keys/values, attention pre-projection, state)");
   const nd_config& c = e->cfg;
   const int d = c.d_model, B = e->B, Tp = e->Tp;
   const int64_t M = (int64_t)B * Tp;
@@ -1118,6 +1128,7 @@ int greedy_body(nd_engine* e, int max_len, int min_len, int64_t* out_ids, float*
   const bool cross_mb = use_cross_mb(e, 1, out_attn != nullptr);
   ND_TRY(decoder_init(e, 1, st, cross_mb));
   ND_LAUNCH(e, fill_int(e->cur_tok, B, 2, st));          // <s> for every row (translator.py:451-452)
+  NvtxRange nvtx("nd:greedy decode loop");
   const int G = n_groups(e, B);
   if (G > 1) ND_TRY(fork_streams(e, st, G));
   for (int step = 0; step < max_len; ++step) {           // no EOS early exit, like the reference (:455)
@@ -1148,6 +1159,7 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
   bp.logp = e->logp; bp.st = e->beam; bp.B = B; bp.K = K; bp.V = e->cfg.vocab_size; bp.Lmax = e->cfg.max_tgt_len;
   bp.max_len = max_len; bp.min_len = min_len; bp.n_best = n_best; bp.alpha = alpha; bp.mode = mode; bp.lp_mode = lp_mode;
   ND_LAUNCH(e, beam_init(bp, 2, st));
+  NvtxRange nvtx(mode == 1 ? "nd:object beam decode loop" : "nd:fast beam decode loop");
   // object mode: stop_step / n_done are shared by all chunks (every Beam advances until ALL are done), so chunk
   // groups on independent streams would see the stop at different steps: one stream
   const int G = mode == 1 ? 1 : n_groups(e, B);
@@ -1385,17 +1397,9 @@ int nd_encode(nd_engine* e, const float* src, const int64_t* lengths, int32_t B,
   e->B = B; e->T = T;
   ND_CUDA(e, cudaMemcpyAsync(e->src, src, (size_t)B * T * sizeof(float), cudaMemcpyDefault, st));
   ND_CUDA(e, cudaMemcpyAsync(e->lengths, lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDefault, st));
-  e->h_lengths.resize(B);
   const nd_config& c = e->cfg;
-  bool need_host_lens = false;
-  if (c.encoder_type == ND_ENC_NANO)
-    for (int l = 0; l < c.enc_layers; ++l) need_host_lens = need_host_lens || c.enc_pooling[l] > 1;
-  if (need_host_lens) {
-    // only the pooling arithmetic needs host lengths (the reference does lengths.tolist(), nano_encoder.py:90)
-    ND_CUDA(e, cudaMemcpyAsync(e->h_lengths.data(), lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDefault, st));
-    ND_CUDA(e, cudaStreamSynchronize(st));
-  }
   int rc;
+  NvtxRange nvtx("nd:encode");
   if (c.encoder_type == ND_ENC_TRANSFORMER) rc = encode_transformer(e, st);
   else if (c.encoder_type == ND_ENC_CNN) rc = encode_cnn(e, st);
   else rc = encode_lstm_stack(e, st);

@@ -130,6 +130,8 @@ cudaError_t linear_in1(const float* x, const float* w, const float* bias, float*
                        cudaStream_t stream);
 // MaxPool1d(stride) over time: in [B,T,d] -> out [B,T/stride,d]   (encoder/nano_encoder.py:101-105)
 cudaError_t maxpool_time(const float* in, float* out, int B, int T, int d, int stride, cudaStream_t stream);
+// lengths after MaxPool1d(stride): out[i] = floor((in[i] - stride) / stride + 1) (in == out allowed)
+cudaError_t pool_lengths(const int64_t* in, int64_t* out, int B, int stride, cudaStream_t stream);
 cudaError_t fill_int(int* p, int n, int value, cudaStream_t stream);
 // out[c,b,t] = in[b,t,c]  (the CNN encoder's reference layout, encoder/cnn_encoder.py:43-44)
 cudaError_t transpose_to_dbt(const float* in, float* out, int B, int T, int d, cudaStream_t stream);

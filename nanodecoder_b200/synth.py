@@ -105,6 +105,14 @@ FAMILY_GAINS = {
 }
 
 
+def rnn_decoder_keys(layer: int, input_feed) -> tuple:
+    """(weight_ih, weight_hh, bias_ih, bias_hh) state-dict keys of decoder layer `layer`."""
+    if input_feed:
+        p = "decoder.rnn.layers.%d" % layer
+        return (p + ".weight_ih", p + ".weight_hh", p + ".bias_ih", p + ".bias_hh")
+    return tuple("decoder.rnn.%s_l%d" % (n, layer) for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+
+
 def positional_encoding_table(dim: int, max_len: int = 5000) -> torch.Tensor:
     """The registered buffer ``pe`` of the reference's PositionalEncoding (onmt/modules/embeddings.py:21-32), built
     with the same fp32 torch ops, so a synthetic checkpoint carries what a trained one would: [max_len, 1, dim]."""
@@ -176,11 +184,13 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
     elif cfg.decoder_type == "rnn":             # onmt/decoders/decoder.py:57-106,352-366
         for l in range(cfg.dec_layers):
             in_f = (2 * d if cfg.input_feed else d) if l == 0 else d
-            p = "decoder.rnn.layers.%d" % l
-            b.matrix(p + ".weight_ih", 4 * d, in_f)
-            b.matrix(p + ".weight_hh", 4 * d, d)
-            b.bias(p + ".bias_ih", 4 * d)
-            b.bias(p + ".bias_hh", 4 * d)
+            # InputFeedRNNDecoder: StackedLSTM of LSTMCells (stacked_rnn.py:15-20); StdRNNDecoder (-input_feed 0):
+            # one multi-layer nn.LSTM (decoder.py:264-266 via rnn_factory) -- same arithmetic, other parameter names
+            names = rnn_decoder_keys(l, cfg.input_feed)
+            b.matrix(names[0], 4 * d, in_f)
+            b.matrix(names[1], 4 * d, d)
+            b.bias(names[2], 4 * d)
+            b.bias(names[3], 4 * d)
         # onmt/modules/global_attention.py:71-93
         if cfg.global_attention == "mlp":
             b.linear("decoder.attn.linear_context", d, d, bias=False)

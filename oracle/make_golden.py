@@ -58,6 +58,10 @@ CASES = {
     "t2t_pe_d64": ("t2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2, position_encoding=True)),
     "nano2rnn_pe_d64": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, position_encoding=True)),
     "cnn2cnn_pe_d64": ("cnn2cnn", dict(d_model=64, enc_layers=2, dec_layers=2, position_encoding=True)),
+    # StdRNNDecoder (-input_feed 0, onmt/decoders/decoder.py:187-262)
+    "brnn2rnn_std_general_d64": ("brnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, input_feed=0,
+                                                  global_attention="general")),
+    "brnn2rnn_std_d256": ("brnn2rnn", dict(input_feed=0)),
 }
 
 
@@ -66,6 +70,8 @@ def ref_extra(cfg):
     extra = ["-global_attention", cfg.global_attention]
     if cfg.position_encoding:
         extra.append("-position_encoding")
+    if cfg.decoder_type == "rnn":
+        extra += ["-input_feed", str(int(cfg.input_feed))]
     return extra
 
 

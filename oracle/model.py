@@ -306,9 +306,14 @@ class InputFeedRNNDecoder(object):
         h0, c0 = self.state["hidden"]
         h1, c1 = [], []
         for l in range(cfg.dec_layers):                             # stacked_rnn.py:25-31
-            p = "decoder.rnn.layers.%d" % l
-            g = F.linear(x, sd[p + ".weight_ih"], sd[p + ".bias_ih"]) + \
-                F.linear(h0[l], sd[p + ".weight_hh"], sd[p + ".bias_hh"])
+            # InputFeedRNNDecoder: StackedLSTM of LSTMCells; StdRNNDecoder (decoder.py:203-262, -input_feed 0): one
+            # multi-layer nn.LSTM fed one token -- the same cell arithmetic under nn.LSTM's parameter names
+            if cfg.input_feed:
+                p = "decoder.rnn.layers.%d" % l
+                wi, wh, bi, bh = p + ".weight_ih", p + ".weight_hh", p + ".bias_ih", p + ".bias_hh"
+            else:
+                wi, wh, bi, bh = ("decoder.rnn.%s_l%d" % (n, l) for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+            g = F.linear(x, sd[wi], sd[bi]) + F.linear(h0[l], sd[wh], sd[bh])
             i, f, gg, o = g.chunk(4, 1)
             c = torch.sigmoid(f) * c0[l] + torch.sigmoid(i) * torch.tanh(gg)
             h = torch.sigmoid(o) * torch.tanh(c)

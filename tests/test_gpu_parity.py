@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 IMPLEMENTED = ["l2t_d256", "t2t_d256", "nano2rnn_d256", "brnn2rnn_d256", "cnn2cnn_d256", "l2t_d64", "t2t_d64",
                "t2t_d512_6x6", "nano2rnn_general_d64", "brnn2rnn_dot_d64", "t2t_pe_d64", "nano2rnn_pe_d64",
-               "cnn2cnn_pe_d64"]
+               "cnn2cnn_pe_d64", "brnn2rnn_std_d256", "brnn2rnn_std_general_d64"]
 TOL = 1e-3
 
 
@@ -59,7 +59,8 @@ def test_greedy_matches_reference_golden(name, mode):
 
 @pytest.mark.parametrize("name", ["l2t_d256", "t2t_d64", "nano2rnn_d256", "brnn2rnn_d256", "l2t_d64", "t2t_d256",
                                   "cnn2cnn_d256", "nano2rnn_general_d64", "brnn2rnn_dot_d64", "t2t_pe_d64",
-                                  "nano2rnn_pe_d64", "cnn2cnn_pe_d64"])
+                                  "nano2rnn_pe_d64", "cnn2cnn_pe_d64", "brnn2rnn_std_d256",
+                                  "brnn2rnn_std_general_d64"])
 def test_beam_matches_reference_golden(name):
     g, cfg, sd, src, lengths = load_golden(name)
     B, T, L, K = src.shape[0], src.shape[1], int(g["max_length"]), int(g["beam_size"])
@@ -260,6 +261,42 @@ def test_greedy_and_beam_vs_oracle_ragged(family):
             else:
                 assert abs(float(sc[i, n]) - ob["scores"][i][n]) < 5e-3
     assert mism == 0, "%d of %d beam hypotheses differ" % (mism, 2 * B)
+
+
+@pytest.mark.parametrize("pooling", [[2, 1], [1, 3], [2, 2]])
+def test_nano_encoder_time_pooling_vs_oracle(pooling):
+    """-audio_enc_pooling > 1 (nano_encoder.py:101-105): MaxPool1d over time between the LSTM layers; the pooled
+    lengths are computed on the device (no host round trip inside nd_encode) and bound the RNN decoder's attention."""
+    from oracle import decode as od
+    from oracle.model import OracleModel
+    cfg = ModelConfig.family("nano2rnn", d_model=64, enc_layers=2, dec_layers=2, enc_pooling=pooling)
+    sd = synth.make_state_dict(cfg, seed=17)
+    B, T, L = 9, 130, 12
+    chunks, lengths = synth.make_chunks(B, T=T, seed=31, ragged=True, read_len=2)
+    lengths[-1] = 7
+    chunks[-1, 7:] = 0
+    order = torch.argsort(lengths, descending=True, stable=True)
+    chunks, lengths = chunks[order], lengths[order]
+    Tmax = int(lengths.max())
+    chunks = chunks[:, :Tmax].contiguous()
+    eng = _engine(cfg, sd, B, Tmax, L, K=3)
+    eng.encode(chunks.cuda(), lengths.cuda())
+    mb, mlen = eng.memory_bank()
+    gr = eng.decode_greedy(L, return_logits=True)
+    bm = eng.decode_beam(3, 1, L, min_len=4)
+    torch.cuda.synchronize()
+    om = OracleModel(sd, cfg)
+    s = chunks.t().contiguous().unsqueeze(2)
+    trace = []
+    og = od.greedy(om, s, lengths, max_length=L, trace_logits=trace)
+    assert list(mb.shape) == list(og["memory_bank"].shape)
+    assert torch.equal(mlen.cpu(), og["memory_lengths"])
+    assert rel_err(mb.cpu(), og["memory_bank"]) < TOL
+    assert torch.equal(gr["ids"].cpu(), og["predictions"])
+    assert rel_err(gr["logits"].cpu(), torch.stack(trace)) < TOL
+    ob = od.beam_fast(om, s, lengths, beam_size=3, max_length=L, min_length=4)
+    for i in range(B):
+        assert torch.equal(bm["ids"][i, 0, : int(bm["lens"][i, 0])].cpu(), ob["predictions"][i][0])
 
 
 def test_decode_streams_and_graphs_do_not_change_results():
