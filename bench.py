@@ -17,7 +17,7 @@ Printed JSON line (rank 0): the task contract, plus
   e2e           the same metric from RAW int16 reads in pinned host memory through the public API:
                 SignalFrontend (H2D, median/MAD, chunking) -> Translator.translate (batch after batch, results
                 double-buffered to the host) -> base strings -> shard.gather_records (NCCL at N > 1), all timed
-  reduced_precision   the same workload with 16-bit memory keys / values (kv_mode q16), never the headline
+  reduced_precision   the same workload with 16-bit memory keys / values (kv_mode q15), never the headline
 ``--impl reference`` times the CPU oracle port of the reference's translate path on the host cores (same workload).
 """
 from __future__ import annotations
@@ -55,8 +55,8 @@ WORKLOADS = {
     "brnn2rnn_greedy_b1024": ("brnn2rnn", {}, 1, "brnn enc3 -> InputFeed LSTM dec3, mlp attention, d=256", "mlp_attn", "C4"),
     "cnn2cnn_greedy_b1024": ("cnn2cnn", {}, 1, "Conv2Conv 3+3, kernel width 3, d=256", "mlp_attn", "C4"),
 }
-KV_MODES = {"f32": 0, "q24": 1, "q16": 2}
-KV_BYTES = {"f32": 4, "q24": 3, "q16": 2}
+KV_MODES = {"f32": 0, "q23": 3, "q15": 4}           # nd_set_int("kv_mode"), include/nanodec.h
+KV_BYTES = {"f32": 4, "q23": 3, "q15": 2}
 
 
 class Workload(object):
@@ -304,7 +304,7 @@ def roofline_entry(wl, cfg, kv, prof, prof_ms, n_prof_steps):
     if wl.roof_cat == "mlp_attn":
         kname = "mlp_attn_kernel<%d,1> (decode global / conv attention, fp32)" % (d // 32)
     elif packed:
-        kname = "cross_attn_packed_kernel<%d,1,%s> (decode cross-attention, fixed-point K/V)" % (d // 32, kv)
+        kname = "cross_attn_packed_fast_kernel<%s> (decode cross-attention, fixed-point K/V, %d CTAs per chunk)" % (kv, 2)
     elif K == 1:
         kname = "cross_attn_kernel<%d,1> (decode cross-attention, fp32 K/V)" % (d // 32)
     else:
@@ -402,8 +402,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gemm-mode", default="3xtf32", choices=["3xtf32", "tf32", "simt"])
-    ap.add_argument("--kv-mode", default="q24", choices=sorted(KV_MODES),
-                    help="storage of the decoder's memory keys / values (greedy): q24 = parity mode (default)")
+    ap.add_argument("--kv-mode", default="q23", choices=sorted(KV_MODES),
+                    help="storage of the decoder's memory keys / values (greedy): q23 = parity mode (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE workloads / the q16 line")
     ap.add_argument("--workload", default=WORKLOAD, choices=sorted(WORKLOADS),
@@ -522,7 +522,7 @@ def main():
         # the reduced-precision line and the other BASELINE configurations, fewer steps, same harness
         k2, w2 = max(1, min(args.steps, 5)), 3
         other = {}
-        for name, kv in [(wl.name, "q16")] + [(n, args.kv_mode) for n in WORKLOADS if n != wl.name]:
+        for name, kv in [(wl.name, "q15")] + [(n, args.kv_mode) for n in WORKLOADS if n != wl.name]:
             w = Workload(name)
             try:
                 r = device_leg(w, args, dev, local, rank, world, kv, k2, w2)
@@ -535,7 +535,7 @@ def main():
             del r
             torch.cuda.empty_cache()
             if name == wl.name:
-                entry["note"] = ("16-bit fixed-point memory keys / values: reduced-precision mode, bound and identity "
+                entry["note"] = ("2-byte fixed-point memory keys / values: reduced-precision mode, bound and identity "
                                  "rate in DESIGN.md 4.5 / profiles/; never the headline")
                 line["reduced_precision"] = entry
             else:

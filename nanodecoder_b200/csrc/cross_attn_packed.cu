@@ -236,8 +236,9 @@ __global__ void __launch_bounds__(kThreads) cross_attn_packed_kernel(CrossAttnPa
 //   * the query lives in 8 registers, the row steps and the key mask (sign of the step) in shared memory,
 //   * rows go in blocks of LPH: the LPH x LPH (lane, row) partial sums are reduce-scattered with LPH - 1 shuffles, lane j
 //     finishes row j and every lane stores one score (no predicates),
-//   * 8 rows (6 KB per warp) are requested before the first is consumed; <= 80 registers -> 3 CTAs (24 warps, 144 KB of
-//     loads in flight) per SM; a 64-register build spills the row registers.
+//   * 6 KB of rows per warp are requested before the first is consumed (8 rows of a 256-column slice, 16 of a
+//     128-column one); ~120 registers -> 2 CTAs (16 warps, 96 KB of loads in flight) per SM; an 80-register build
+//     (3 CTAs) spills row registers and measured slower (155 vs 148 us at d = 256).
 // one stage of the reduce-scatter: lanes whose bit W is set keep the upper W values, the others the lower W
 template <int W>
 __device__ __forceinline__ void rs_stage(float* v, int lane) {
@@ -250,9 +251,9 @@ __device__ __forceinline__ void rs_stage(float* v, int lane) {
   }
 }
 
-template <int LPH, int FMT, int MINB>
+template <int VPL, int LPH, int FMT, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(CrossAttnParams p, int split) {
-  constexpr int VPL = 8, DS = 256, HP = 32 / LPH, RB = 8;       // slice width, heads per slice, rows per iteration
+  constexpr int DS = 32 * VPL, HP = 32 / LPH, RB = 64 / VPL;    // slice width, heads per slice, rows per iteration
   extern __shared__ __align__(16) float smem_f[];
   const int chunk = blockIdx.x / split, part = blockIdx.x - chunk * split;
   pdl_launch_dependents();
@@ -305,8 +306,8 @@ __global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(
       } else {
 #pragma unroll
         for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[r].hi[i] = 0u;
-        rr[r].lo[0] = 0u;
-        if (fmt_has_lo(FMT)) rr[r].lo[RowRegs<VPL, FMT>::NLO - 1] = 0u;
+#pragma unroll
+        for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[r].lo[i] = 0u;
       }
     }
 #pragma unroll
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(
         v[r] = s;
       }
       // reduce-scatter over the LPH lanes of the head: lane j ends with the complete sum of row j
-      if constexpr (LPH == 8) rs_stage<4>(v, lane);
+      if constexpr (LPH >= 8) rs_stage<4>(v, lane);
       rs_stage<2>(v, lane);
       rs_stage<1>(v, lane);
       const int t = t0 + b0 + j;
@@ -369,24 +370,25 @@ __global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(
       } else {
 #pragma unroll
         for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[r].hi[i] = 0u;
-        rr[r].lo[0] = 0u;
-        if (fmt_has_lo(FMT)) rr[r].lo[RowRegs<VPL, FMT>::NLO - 1] = 0u;
+#pragma unroll
+        for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[r].lo[i] = 0u;
       }
     }
-    const float4 pa = *reinterpret_cast<const float4*>(sc + head * TS + t0);
-    const float4 pb = *reinterpret_cast<const float4*>(sc + head * TS + t0 + 4);
-    const float pr[RB] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
-    for (int r = 0; r < RB; ++r)
+    for (int r4 = 0; r4 < RB; r4 += 4) {
+      const float4 pq = *reinterpret_cast<const float4*>(sc + head * TS + t0 + r4);
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) acc[i] = fmaf(pr[r], rr[r].get(i), acc[i]);
+      for (int i = 0; i < VPL; ++i)
+        acc[i] = fmaf(pq.x, rr[r4].get(i), fmaf(pq.y, rr[r4 + 1].get(i), fmaf(pq.z, rr[r4 + 2].get(i),
+                 fmaf(pq.w, rr[r4 + 3].get(i), acc[i]))));
+    }
   }
   __syncthreads();                                 // scores no longer needed: reuse as reduction buffer
   float* red = sc;                                 // [warps][DS]
 #pragma unroll
   for (int i = 0; i < VPL; ++i) red[warp * DS + lane * VPL + i] = acc[i];
   __syncthreads();
-  {
+  if (threadIdx.x < DS) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) s += red[w * DS + threadIdx.x];
@@ -394,22 +396,23 @@ __global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(
   }
 }
 
-template <int LPH, int FMT, int MINB>
+template <int VPL, int LPH, int FMT, int MINB>
 cudaError_t launch_fast(const CrossAttnParams& p, cudaStream_t stream) {
-  const int split = p.d / 256;
-  const int Tup = (p.T + 7) & ~7, HP = 32 / LPH;
-  const size_t sc_f = (size_t)HP * (Tup + LPH), red_f = (size_t)kWarps * 256;
+  constexpr int DS = 32 * VPL, RB = 64 / VPL;
+  const int split = p.d / DS;
+  const int Tup = (p.T + RB - 1) & ~(RB - 1), HP = 32 / LPH;
+  const size_t sc_f = (size_t)HP * (Tup + LPH), red_f = (size_t)kWarps * DS;
   const size_t smem = ((sc_f > red_f ? sc_f : red_f) + 2 * (size_t)Tup) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   static PerDeviceFlag attr_set;
   bool& set = attr_set.cur();
   if (!set) {
-    cudaError_t err = cudaFuncSetAttribute(cross_attn_packed_fast_kernel<LPH, FMT, MINB>,
+    cudaError_t err = cudaFuncSetAttribute(cross_attn_packed_fast_kernel<VPL, LPH, FMT, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (err != cudaSuccess) return err;
     set = true;
   }
-  launch_k_heavy(cross_attn_packed_fast_kernel<LPH, FMT, MINB>, dim3(p.n_chunks * split), dim3(kThreads), smem, stream, p, split);
+  launch_k_heavy(cross_attn_packed_fast_kernel<VPL, LPH, FMT, MINB>, dim3(p.n_chunks * split), dim3(kThreads), smem, stream, p, split);
   return cudaGetLastError();
 }
 
@@ -420,22 +423,25 @@ bool fast_supported(const CrossAttnParams& p) {
          (int64_t)p.T * 4 * p.d < (int64_t)1 << 31;
 }
 
-int g_packed_fast = 1;     // 1: <= 128 registers, 2 CTAs per SM; 2: <= 80 registers (some row registers spill), 3 CTAs; 0: generic kernel
+int g_packed_fast = 1;     // 0: generic kernel; 1 / 3: slice kernels, see launch_fast_any
 
-template <int LPH>
+template <int VPL, int LPH, int MINB>
 cudaError_t launch_fast_fmt(const CrossAttnParams& p, cudaStream_t stream) {
-  if (g_packed_fast == 2) {
-    switch (p.kv_fmt) {
-      case KV_Q23M: return launch_fast<LPH, KV_Q23M, 3>(p, stream);
-      case KV_Q15M: return launch_fast<LPH, KV_Q15M, 3>(p, stream);
-      default: return launch_fast<LPH, KV_FP24, 3>(p, stream);
-    }
-  }
   switch (p.kv_fmt) {
-    case KV_Q23M: return launch_fast<LPH, KV_Q23M, 2>(p, stream);
-    case KV_Q15M: return launch_fast<LPH, KV_Q15M, 2>(p, stream);
-    default: return launch_fast<LPH, KV_FP24, 2>(p, stream);
+    case KV_Q23M: return launch_fast<VPL, LPH, KV_Q23M, MINB>(p, stream);
+    case KV_Q15M: return launch_fast<VPL, LPH, KV_Q15M, MINB>(p, stream);
+    default: return launch_fast<VPL, LPH, KV_FP24, MINB>(p, stream);
   }
+}
+
+// slice choice.  d = 512 (dh = 64): 256-column slices of 4 heads (8 lanes x 8 columns per head), 2048 CTAs for 1024 chunks.
+// d = 256 (dh = 32): g_packed_fast 1 = 128-column slices of 4 heads (8 lanes x 4 columns per head), also 2048 CTAs -- with
+// one CTA per chunk 1024 equal work items on 148 x 2 CTA slots run as 3.46 -> 4 rounds (13 % idle in the last round);
+// g_packed_fast 3 = that one-CTA-per-chunk form (4 lanes x 8 columns per head).
+cudaError_t launch_fast_any(const CrossAttnParams& p, cudaStream_t stream) {
+  if (p.d == 512) return launch_fast_fmt<8, 8, 2>(p, stream);
+  if (g_packed_fast == 3) return launch_fast_fmt<8, 4, 2>(p, stream);
+  return launch_fast_fmt<4, 8, 2>(p, stream);
 }
 
 template <int VPL, int NQMAX, int FMT>
@@ -543,7 +549,7 @@ cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream
   if (!kv_pack_supported(p.d) || 32 % p.H || p.NQ > 8 || p.NQ < 1 || (p.d / p.H) % (p.d / 32) || !p.kv_hi ||
       !p.kv_scale || (fmt_has_lo(p.kv_fmt) && !p.kv_lo))
     return cudaErrorInvalidValue;
-  if (g_packed_fast && fast_supported(p)) return p.d == 256 ? launch_fast_fmt<4>(p, stream) : launch_fast_fmt<8>(p, stream);
+  if (g_packed_fast && fast_supported(p)) return launch_fast_any(p, stream);
   switch (p.d / 32) {
     case 2: return launch_packed<2>(p, stream);
     case 4: return launch_packed<4>(p, stream);

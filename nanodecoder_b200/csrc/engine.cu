@@ -133,9 +133,10 @@ struct nd_engine {
   // (profiles/r01_cross_mb_experiment.md) -- kept as an option until its FFMA side is as good as its byte count
   const int* gemm_alive = nullptr;         // set while a beam search runs: GEMMs return at once when it reads 0
   int cross_mode = 0;
-  // storage of the projected memory keys / values (kernels.cuh): KV_F32, KV_Q24 (default: 24-bit fixed point, the
-  // absolute error fp32 has on a row's largest element, 3/4 of the bytes), KV_Q16 (reduced precision, half the bytes)
-  int kv_mode = KV_F32;
+  // storage of the projected memory keys / values (kernels.cuh): KV_Q23M (default: 3 bytes per element, absolute
+  // error <= 2^-23 of the row part's largest element; same greedy sequences and identity rates as fp32 storage),
+  // KV_F32, KV_Q15M (reduced precision, half the bytes), others = cross-checks
+  int kv_mode = KV_Q23M;
   bool kv_packed = false;                  // set by decoder_init: this decode reads the packed planes
   int enc_attn_tc = 1;                     // Transformer-encoder self attention on the tensor cores when dh = 32
   int* cur_tok = nullptr;

@@ -23,7 +23,7 @@ from ..inputters.nano_dataset import batch_order, parse_segments, pooled_batches
 from .translation import TranslationBuilder
 
 
-KV_MODES = {"f32": 0, "q24": 1, "q16": 2}        # nd_set_int("kv_mode"), include/nanodec.h
+KV_MODES = {"f32": 0, "q23": 3, "q15": 4}        # nd_set_int("kv_mode"), include/nanodec.h
 
 
 class _Field(object):
@@ -122,7 +122,7 @@ class Translator(object):
         engine = Engine(cfg, state_dict, max_batch=opt.batch_size, max_src_len=opt.src_seq_length,
                         max_tgt_len=opt.max_length, max_beam=max(1, opt.beam_size),
                         gemm_mode=getattr(opt, "gemm_mode", "3xtf32"), device=max(0, opt.gpu))
-        engine.set_option("kv_mode", KV_MODES[getattr(opt, "kv_mode", "q24")])
+        engine.set_option("kv_mode", KV_MODES[getattr(opt, "kv_mode", "q23")])
         return cls(engine, {"tgt": _Field(vocab)}, opt, cfg, report_score=report_score, logger=logger)
 
     def setAttnFile(self, out_file_attn):

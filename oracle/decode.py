@@ -58,9 +58,14 @@ def _tile(x, count, dim=0):
 
 
 def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0, n_best=1,
-              alpha=0.0):
+              alpha=0.0, margins=None):
     """translate/translator.py:619-825 (``--fast`` batched beam search, no attention return).
-    -> dict(predictions: list[B] of list[n_best] of LongTensor, scores: list[B] of list[float])"""
+    -> dict(predictions: list[B] of list[n_best] of LongTensor, scores: list[B] of list[float])
+    ``margins`` (optional list, diagnostics only): filled with one float per chunk = the smallest gap, over all steps
+    the chunk was alive, between two neighbouring candidates among the best beam_size + 1 of the step (the pruning
+    boundary and the order of the kept beams).  A chunk whose margin is of the order of fp32 rounding (~1e-6) can take
+    another search path under any re-association of the sums: that is what "explained by a logit tie" means for a
+    beam search."""
     with torch.no_grad():
         B, K = src.size(1), beam_size
         src, enc_states, memory_bank, src_lengths = _run_encoder(model, src, src_lengths)
@@ -87,6 +92,15 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
             length_penalty = ((5.0 + (step + 1)) / 6.0) ** alpha    # :720-721
             curr_scores = (log_probs / length_penalty).reshape(-1, K * V)
             topk_scores, topk_ids = curr_scores.topk(K, dim=-1)     # :726
+            if margins is not None:
+                if step == 0:
+                    margins[:] = [float("inf")] * B
+                top = curr_scores.topk(min(K + 1, curr_scores.size(1)), dim=-1)[0]
+                gaps = top[:, :-1] - top[:, 1:]
+                gaps = torch.where(torch.isfinite(gaps), gaps, torch.full_like(gaps, float("inf"))).min(1)[0]
+                for i in range(gaps.size(0)):
+                    b = int(batch_offset[i])
+                    margins[b] = min(margins[b], float(gaps[i]))
             topk_log_probs = topk_scores * length_penalty           # :729
             topk_beam_index = torch.div(topk_ids, V, rounding_mode="trunc")    # :732
             topk_ids = topk_ids.fmod(V)                             # :733

@@ -105,10 +105,13 @@ def beam_case(family, kw, min_len, n, slice_b, opts, K=5, NB=1):
     eng.close()
     om = OracleModel(sd, cfg)
     same, explain, hist = 0, [], []
+    all_margins = []
     t0 = time.time()
     for sel in oracle_slices(n, slice_b):
+        margins = []
         want = od.beam_fast(om, chunks[sel].t().contiguous().unsqueeze(2), lengths[sel], beam_size=K, max_length=L,
-                            min_length=min_len, n_best=NB)
+                            min_length=min_len, n_best=NB, margins=margins)
+        all_margins.extend(margins)
         for j, c in enumerate(sel.tolist()):
             w = want["predictions"][j][0]
             g = ids[c, 0, : int(lens[c, 0])]
@@ -116,11 +119,15 @@ def beam_case(family, kw, min_len, n, slice_b, opts, K=5, NB=1):
             if torch.equal(g, w):
                 same += 1
             else:
-                explain.append({"chunk": c, "oracle_len": len(w), "gpu_len": int(lens[c, 0]),
+                explain.append({"chunk": c, "tightest_candidate_gap_in_the_oracle_search": margins[j],
+                                "oracle_len": len(w), "gpu_len": int(lens[c, 0]),
                                 "oracle_score": float(want["scores"][j][0]), "gpu_score": float(sc[c, 0]),
                                 "score_gap": float(want["scores"][j][0]) - float(sc[c, 0])})
     return {"family": family, "cfg": kw, "mode": "--fast beam %d, min_length %d" % (K, min_len), "chunks": n,
             "identical": same, "rate": same / n, "hyp_len_min": min(hist), "hyp_len_mean": sum(hist) / len(hist),
+            "tightest_gap_quantiles_all_chunks": {q: float(torch.tensor(all_margins).quantile(q)) for q in
+                                                  (0.001, 0.01, 0.1, 0.5)},
+            "chunks_with_gap_below_1e-5": int((torch.tensor(all_margins) < 1e-5).sum()),
             "mismatches": explain[:20], "oracle_cpu_seconds": round(time.time() - t0, 1)}
 
 
@@ -131,7 +138,7 @@ def main():
     ap.add_argument("--slice", type=int, default=64)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "identity_rates.json"))
     ap.add_argument("--opts", default="", help="engine options of the beam cases, e.g. cross_beam_kernel=1")
-    ap.add_argument("--greedy-opts", default="kv_mode=0;kv_mode=1;kv_mode=2",
+    ap.add_argument("--greedy-opts", default="kv_mode=0;kv_mode=3;kv_mode=4",
                     help="';'-separated engine option sets compared against ONE oracle run per family")
     ap.add_argument("--only", default="", help="greedy | beam")
     args = ap.parse_args()

@@ -34,12 +34,13 @@ BEAM_GOLDEN_CASES = ["beam_l2t_d256_min99", "beam_l2t_d256_min20", "beam_l2t_d25
                      "beam_cnn2cnn_d256_min20", "beam_t2t_d512_6x6_min20"]
 
 
-def check_beam_against_golden(g, ids, lens, scores, atol=5e-3, tie=1e-4):
+def check_beam_against_golden(g, ids, lens, scores, atol=5e-3, tie=1e-3):
     """ids [B,n_best,L], lens [B,n_best], scores [B,n_best] (numpy) vs a beam_* golden of the reference's --fast beam.
     north_star: "beam outputs match ... any divergence explained by a logit tie": a hypothesis may differ from the
-    reference's only if its cumulative score equals the reference's to within `tie` (a few fp32 ulps of a score of
-    ~ -130: e.g. the reference's own 2nd and 3rd hypotheses of beam_nano2rnn_d256_min99 chunk 2 are -131.399216 and
-    -131.399231, one ulp apart, and swap places under any reassociation).  -> number of such tie swaps."""
+    reference's only if its cumulative score equals the reference's to within `tie` = 1e-3: a 100-token score of ~ -130
+    carries ~2e-4 of accumulated fp32 rounding (per-step log-probs agree to ~2e-6), and e.g. the reference's own 2nd and
+    3rd hypotheses of beam_nano2rnn_d256_min99 chunk 2 are -131.399216 and -131.399231 -- ONE ulp apart, they swap places
+    under any reassociation of the sums -- while distinct hypotheses are >= 0.05 apart.  -> number of such tie swaps."""
     B, NB = g["beam_ids"].shape[:2]
     swaps = 0
     for i in range(B):
