@@ -24,6 +24,7 @@ FAMILIES = {
     "t2t": dict(encoder_type="transformer", decoder_type="transformer"),
     "nano2rnn": dict(encoder_type="nano", decoder_type="rnn"),
     "brnn2rnn": dict(encoder_type="brnn", decoder_type="rnn"),
+    "rnn2rnn": dict(encoder_type="rnn", decoder_type="rnn"),         # unidirectional encoder (encoder/rnn_encoder.py)
     "cnn2cnn": dict(encoder_type="cnn", decoder_type="cnn"),
 }
 

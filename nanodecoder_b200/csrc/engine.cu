@@ -501,7 +501,7 @@ int finalize(nd_engine* e) {
   // ---------------- encoder
   if (c.encoder_type == ND_ENC_NANO) {
     const int H = d / 2;
-    if (!lstm_supported(H)) return fail(e, ND_ERR_INVALID, "LSTM hidden size " + std::to_string(H) + " unsupported (16/32/64/128)");
+    if (!lstm_supported(H)) return fail(e, ND_ERR_INVALID, "LSTM hidden size " + std::to_string(H) + " unsupported (16/32/64/128/256)");
     e->lstm.resize(c.enc_layers);
     std::vector<std::vector<float>> alphas(c.enc_layers), betas(c.enc_layers);
     for (int l = 0; l < c.enc_layers; ++l) {
@@ -530,7 +530,7 @@ int finalize(nd_engine* e) {
   } else if (c.encoder_type == ND_ENC_BRNN || c.encoder_type == ND_ENC_RNN) {
     const int dirs = c.encoder_type == ND_ENC_BRNN ? 2 : 1;
     const int H = d / dirs;
-    if (!lstm_supported(H)) return fail(e, ND_ERR_INVALID, "LSTM hidden size " + std::to_string(H) + " unsupported (16/32/64/128)");
+    if (!lstm_supported(H)) return fail(e, ND_ERR_INVALID, "LSTM hidden size " + std::to_string(H) + " unsupported (16/32/64/128/256)");
     e->lstm.resize(c.enc_layers);
     for (int l = 0; l < c.enc_layers; ++l)
       ND_TRY(load_lstm(e, "encoder.rnn", "_l" + std::to_string(l), l == 0 ? 1 : d, H, dirs, &e->lstm[l]));

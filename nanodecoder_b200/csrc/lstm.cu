@@ -25,16 +25,29 @@ namespace {
 // return path, not the FMA pipe, bounds a one-row-per-thread layout).  The four K-quarter partial
 // sums are combined with a 2-stage reduce-scatter over xor-shuffles, after which lane kq owns the
 // complete gates of chunks [kq*BT/4, (kq+1)*BT/4) of the tile and performs their cell update.
-template <int H, int C, int BT>
-__global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
-  constexpr int UPC = H / C;          // hidden units owned by this CTA
-  constexpr int NT = 4 * UPC;
-  constexpr int KQ = H / 4;           // K elements per thread
-  constexpr int KS = KQ + 4;          // padded quarter stride (floats): conflict-free 128-bit quarter reads
-  constexpr int PPT = BT / 4;         // chunks whose cell update this lane performs
-  static_assert(BT % 4 == 0 && KQ % 4 == 0, "tile shape");
+// one stage of the reduce-scatter over the K slices: lanes whose kq bit W is set keep the upper N values
+template <int N, int W>
+__device__ __forceinline__ void rs_stage(float* v, int kq) {
+  const bool up = (kq & W) != 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float keep = up ? v[i + N] : v[i];
+    const float send = up ? v[i] : v[i + N];
+    v[i] = keep + __shfl_xor_sync(ND_FULL, send, W);
+  }
+}
 
-  __shared__ __align__(16) float h_buf[2][BT][4 * KS];
+// KSPL = K slices per hidden unit (4; 8 for H = 256, where a quarter of W_hh's four gate rows would be 256 registers)
+template <int H, int C, int BT, int KSPL = 4>
+__global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
+  constexpr int UPC = H / C;          // hidden units owned by this CTA
+  constexpr int NT = KSPL * UPC;
+  constexpr int KQ = H / KSPL;        // K elements per thread
+  constexpr int KS = KQ + 4;          // padded slice stride (floats): conflict-free 128-bit slice reads
+  constexpr int PPT = BT / KSPL;      // chunks whose cell update this lane performs
+  static_assert(BT % KSPL == 0 && KQ % 4 == 0 && (KSPL == 4 || KSPL == 8), "tile shape");
+
+  __shared__ __align__(16) float h_buf[2][BT][KSPL * KS];
   __shared__ int s_len[BT];
 
   const int tid = threadIdx.x;
@@ -44,7 +57,7 @@ __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
   const int dir = item % p.dirs;
   const int tile = item / p.dirs;
   const int b0 = tile * BT;
-  const int u = tid >> 2, kq = tid & 3;
+  const int u = tid / KSPL, kq = tid % KSPL;
   const int ucol = rank * UPC + u;                       // hidden unit index in [0, H)
   const int64_t gbase = (int64_t)dir * 4 * H + ucol;     // + g*H = row of gate g in the [dirs*4H] dimension
 
@@ -65,7 +78,7 @@ __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
   }
 
   if (tid < BT) s_len[tid] = (b0 + tid < p.B) ? (int)p.lengths[b0 + tid] : 0;
-  for (int i = tid; i < 2 * BT * 4 * KS; i += NT) (&h_buf[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * BT * KSPL * KS; i += NT) (&h_buf[0][0][0])[i] = 0.f;
   __syncthreads();
   int maxlen = 0;
 #pragma unroll
@@ -80,7 +93,6 @@ __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
 
   const int out_ld = p.dirs * H;
   const int hoff = (ucol / KQ) * KS + (ucol % KQ);       // where unit ucol lives inside a padded h row
-  const bool hi2 = (kq >> 1) != 0, lo1 = (kq & 1) != 0;
   for (int s = 0; s < maxlen; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
     // ---- input-side gate terms of the chunks this lane finishes (latency hides behind the FMAs)
@@ -122,24 +134,16 @@ __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
         }
       }
     }
-    // ---- reduce-scatter over the 4 K-quarters: lane kq ends up with chunks [kq*PPT, (kq+1)*PPT)
+    // ---- reduce-scatter over the KSPL K slices: lane kq ends up with chunks [kq*PPT, (kq+1)*PPT).  Every stage
+    // halves the chunk range a lane keeps (upper half when its kq bit is set) and adds the partner's partial sums.
     float fin[4][PPT];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
+      if constexpr (KSPL == 8) rs_stage<4 * PPT, 4>(acc[g], kq);
+      rs_stage<2 * PPT, 2>(acc[g], kq);
+      rs_stage<PPT, 1>(acc[g], kq);
 #pragma unroll
-      for (int j = 0; j < PPT; ++j) {
-        float half[2];
-#pragma unroll
-        for (int lo = 0; lo < 2; ++lo) {
-          // chunk groups: bq = hi*2 + lo; this lane keeps the groups with hi == (kq >> 1)
-          const float keep = hi2 ? acc[g][(2 + lo) * PPT + j] : acc[g][lo * PPT + j];
-          const float send = hi2 ? acc[g][lo * PPT + j] : acc[g][(2 + lo) * PPT + j];
-          half[lo] = keep + __shfl_xor_sync(ND_FULL, send, 2);
-        }
-        const float keep = lo1 ? half[1] : half[0];
-        const float send = lo1 ? half[0] : half[1];
-        fin[g][j] = keep + __shfl_xor_sync(ND_FULL, send, 1);
-      }
+      for (int j = 0; j < PPT; ++j) fin[g][j] = acc[g][j];
     }
     // ---- cell update of (unit ucol, chunk kq*PPT + j)
 #pragma unroll
@@ -182,12 +186,12 @@ __global__ void __launch_bounds__(4 * (H / C), 1) lstm_kernel(LstmParams p) {
   if constexpr (C > 1) cg::this_cluster().sync();     // no CTA may exit while peers still write its smem
 }
 
-template <int H, int C, int BT>
+template <int H, int C, int BT, int KSPL = 4>
 cudaError_t launch(const LstmParams& p, cudaStream_t stream) {
   const int tiles = cdiv(p.B, BT);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(tiles * p.dirs * C));
-  cfg.blockDim = dim3(4 * (H / C));
+  cfg.blockDim = dim3(KSPL * (H / C));
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -197,7 +201,7 @@ cudaError_t launch(const LstmParams& p, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, lstm_kernel<H, C, BT>, p);
+  return cudaLaunchKernelEx(&cfg, lstm_kernel<H, C, BT, KSPL>, p);
 }
 
 template <int H, int C>
@@ -223,7 +227,16 @@ cudaError_t pick_bt(const LstmParams& p, int n_sm, cudaStream_t stream) {
 
 }  // namespace
 
-bool lstm_supported(int H) { return H == 16 || H == 32 || H == 64 || H == 128; }
+// H = 256 (unidirectional rnn encoder at d = 256): 8 K slices per unit (32 x 4 weight registers per thread), clusters
+// of 8 CTAs of 32 units each
+cudaError_t launch_h256(const LstmParams& p, int n_sm, cudaStream_t stream) {
+  const int64_t c8 = (int64_t)cdiv(p.B, 8) * p.dirs * 8, c16 = (int64_t)cdiv(p.B, 16) * p.dirs * 8;
+  const double cost8 = (double)cdiv64(c8, n_sm) * (2.5 * 256 * 8 + 700.0);
+  const double cost16 = (double)cdiv64(c16, n_sm) * (2.5 * 256 * 16 + 700.0);
+  return cost8 <= cost16 ? launch<256, 8, 8, 8>(p, stream) : launch<256, 8, 16, 8>(p, stream);
+}
+
+bool lstm_supported(int H) { return H == 16 || H == 32 || H == 64 || H == 128 || H == 256; }
 
 cudaError_t lstm_layer(const LstmParams& p, int n_sm, cudaStream_t stream) {
   if (p.B <= 0) return cudaSuccess;
@@ -232,6 +245,7 @@ cudaError_t lstm_layer(const LstmParams& p, int n_sm, cudaStream_t stream) {
     case 32: return pick_bt<32, 1>(p, n_sm, stream);
     case 64: return pick_bt<64, 1>(p, n_sm, stream);
     case 128: return pick_bt<128, 2>(p, n_sm, stream);
+    case 256: return launch_h256(p, n_sm, stream);
     default: return cudaErrorNotSupported;
   }
 }

@@ -101,6 +101,7 @@ FAMILY_GAINS = {
                                          self_out=0.5, ffn_out=1.0, gen=2.0, eos_bias=-1.0),
     ("nano", "rnn"): dict(emb_std=0.1, attn_qk=2.5, ctx_out=6.0, gen=1.0, eos_bias=-0.5),
     ("brnn", "rnn"): dict(emb_std=1.0, attn_qk=1.5, ctx_out=2.0, gen=3.0, eos_bias=-1.0),
+    ("rnn", "rnn"): dict(emb_std=1.0, attn_qk=1.5, ctx_out=2.0, gen=3.0, eos_bias=-1.0),
     ("cnn", "cnn"): dict(emb_std=1.0, attn_qk=2.5, ctx_out=2.0, gen=2.0, eos_bias=-0.5),
 }
 

@@ -62,6 +62,9 @@ CASES = {
     "brnn2rnn_std_general_d64": ("brnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, input_feed=0,
                                                   global_attention="general")),
     "brnn2rnn_std_d256": ("brnn2rnn", dict(input_feed=0)),
+    # unidirectional rnn encoder (encoder/rnn_encoder.py:64-84): hidden size = d (256: the 8-slice recurrence kernel)
+    "rnn2rnn_d256": ("rnn2rnn", dict()),
+    "rnn2rnn_d64": ("rnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2)),
 }
 
 

@@ -215,6 +215,7 @@ FAMILY_FLAGS = {
     "l2t": ["-encoder_type", "nano", "-decoder_type", "transformer", "-audio_enc_pooling", "1"],
     "nano2rnn": ["-encoder_type", "nano", "-decoder_type", "rnn", "-audio_enc_pooling", "1"],
     "brnn2rnn": ["-encoder_type", "brnn", "-decoder_type", "rnn"],
+    "rnn2rnn": ["-encoder_type", "rnn", "-decoder_type", "rnn"],
     "cnn2cnn": ["-encoder_type", "cnn", "-decoder_type", "cnn"],
 }
 
