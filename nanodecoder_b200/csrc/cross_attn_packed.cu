@@ -239,25 +239,28 @@ __global__ void __launch_bounds__(kThreads) cross_attn_packed_kernel(CrossAttnPa
 //   * 6 KB of rows per warp are requested before the first is consumed (8 rows of a 256-column slice, 16 of a
 //     128-column one); ~120 registers -> 2 CTAs (16 warps, 96 KB of loads in flight) per SM; an 80-register build
 //     (3 CTAs) spills row registers and measured slower (155 vs 148 us at d = 256).
-// one stage of the reduce-scatter: lanes whose bit W is set keep the upper W values, the others the lower W
-template <int W>
+// one stage of a reduce-scatter over lanes W apart: lanes whose bit W is set keep the upper N values, the others the lower N
+template <int N, int W>
 __device__ __forceinline__ void rs_stage(float* v, int lane) {
   const bool up = (lane & W) != 0;
 #pragma unroll
-  for (int r = 0; r < W; ++r) {
-    const float keep = up ? v[r + W] : v[r];
-    const float send = up ? v[r] : v[r + W];
+  for (int r = 0; r < N; ++r) {
+    const float keep = up ? v[r + N] : v[r];
+    const float send = up ? v[r] : v[r + N];
     v[r] = keep + __shfl_xor_sync(ND_FULL, send, W);
   }
 }
 
-template <int VPL, int LPH, int FMT, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(CrossAttnParams p, int split) {
-  constexpr int DS = 32 * VPL, HP = 32 / LPH, RB = 64 / VPL;    // slice width, heads per slice, rows per iteration
+// CHAIN (the 128-column tail CTAs of d = 256, VPL = 4, LPH = 8): the lane pair (2k, 2k+1) holds the 8 columns ONE lane
+// of the whole-chunk form (VPL = 8, LPH = 4) holds; the even lane's 4-product fma chain is handed to the odd lane, which
+// continues it, and the four pair sums are then combined over the odd lanes in the order of the 4-lane reduce-scatter.
+// With 8 rows per iteration and the same row -> warp assignment every sum is formed in the same order as in the
+// whole-chunk CTA: a chunk gets the same bits whether it is decoded by one CTA or by two tail CTAs.
+template <int VPL, int LPH, int FMT, bool CHAIN>
+__device__ __forceinline__ void fast_body(const CrossAttnParams& p, const int chunk, const int part) {
+  constexpr int DS = 32 * VPL, HP = 32 / LPH, RB = CHAIN ? 8 : 64 / VPL;   // slice width, heads per slice, rows per iteration
+  static_assert(!CHAIN || (VPL == 4 && LPH == 8), "pair chaining is the 128-column form of d = 256");
   extern __shared__ __align__(16) float smem_f[];
-  const int chunk = blockIdx.x / split, part = blockIdx.x - chunk * split;
-  pdl_launch_dependents();
-  pdl_wait();
   if (p.retired && p.retired[chunk]) return;
   const int T = p.T, d = p.d;
   const int Tup = (T + RB - 1) & ~(RB - 1);
@@ -310,23 +313,48 @@ __global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(
         for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[r].lo[i] = 0u;
       }
     }
+    if constexpr (CHAIN) {
 #pragma unroll
-    for (int b0 = 0; b0 < RB; b0 += LPH) {
-      float v[LPH];
+      for (int b0 = 0; b0 < RB; b0 += 4) {
+        float v[4];
 #pragma unroll
-      for (int r = 0; r < LPH; ++r) {
-        float s = 0.f;
+        for (int r = 0; r < 4; ++r) {
+          float kf[VPL];
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], rr[b0 + r].get(i), s);
-        v[r] = s;
+          for (int i = 0; i < VPL; ++i) kf[i] = rr[b0 + r].get(i);
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], kf[i], s);
+          s = __shfl_up_sync(ND_FULL, s, 1);                       // odd lanes: the even partner's chain
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], kf[i], s);
+          v[r] = s;                                                // complete 8-column chain in the odd lanes
+        }
+        rs_stage<2, 4>(v, lane);
+        rs_stage<1, 2>(v, lane);
+        const int t = t0 + b0 + ((lane >> 1) & 3);
+        const float ks = kstep[t];
+        if (lane & 1) sc[head * TS + t] = ks < 0.f ? -1e18f : v[0] * ks;
       }
-      // reduce-scatter over the LPH lanes of the head: lane j ends with the complete sum of row j
-      if constexpr (LPH >= 8) rs_stage<4>(v, lane);
-      rs_stage<2>(v, lane);
-      rs_stage<1>(v, lane);
-      const int t = t0 + b0 + j;
-      const float ks = kstep[t];
-      sc[head * TS + t] = ks < 0.f ? -1e18f : v[0] * ks;         // rows >= T: finite junk, never read by the softmax
+    } else {
+#pragma unroll
+      for (int b0 = 0; b0 < RB; b0 += LPH) {
+        float v[LPH];
+#pragma unroll
+        for (int r = 0; r < LPH; ++r) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], rr[b0 + r].get(i), s);
+          v[r] = s;
+        }
+        // reduce-scatter over the LPH lanes of the head: lane j ends with the complete sum of row j
+        if constexpr (LPH >= 8) rs_stage<4, 4>(v, lane);
+        rs_stage<2, 2>(v, lane);
+        rs_stage<1, 1>(v, lane);
+        const int t = t0 + b0 + j;
+        const float ks = kstep[t];
+        sc[head * TS + t] = ks < 0.f ? -1e18f : v[0] * ks;       // rows >= T: finite junk, never read by the softmax
+      }
     }
   }
   __syncthreads();
@@ -397,6 +425,52 @@ __global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(
 }
 
 template <int VPL, int LPH, int FMT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) cross_attn_packed_fast_kernel(CrossAttnParams p, int split) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int chunk = blockIdx.x / split;
+  fast_body<VPL, LPH, FMT, false>(p, chunk, blockIdx.x - chunk * split);
+}
+
+// d = 256 with a split tail.  One CTA per chunk leaves the last round of CTAs partly empty (1024 chunks on 148 x 2
+// slots = 3.46 rounds: the 4th is 46 % full); two 128-column CTAs per chunk fill the rounds but run 7 % slower overall
+// (8-byte loads).  So the first n_full chunks (whole rounds) take one CTA each and the rest -- dispatched last -- two
+// 128-column CTAs each, which need ~0.6 of a whole-chunk CTA's time: 3 + 0.6 rounds instead of 4.  The tail CTAs form
+// every sum in the order of the whole-chunk CTA (see CHAIN above), so a chunk's result does not depend on its position.
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 2) cross_attn_packed_tail_kernel(CrossAttnParams p, int n_full) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if ((int)blockIdx.x < n_full) {
+    fast_body<8, 4, FMT, false>(p, blockIdx.x, 0);
+  } else {
+    const int i = blockIdx.x - n_full;
+    fast_body<4, 8, FMT, true>(p, n_full + (i >> 1), i & 1);
+  }
+}
+
+template <int FMT>
+cudaError_t launch_tail(const CrossAttnParams& p, int n_full, cudaStream_t stream) {
+  const int Tup = (p.T + 7) & ~7;
+  const size_t a = (size_t)8 * (Tup + 4), b = (size_t)4 * (Tup + 8), red_f = (size_t)kWarps * 256;
+  size_t sc_f = a > b ? a : b;
+  if (red_f > sc_f) sc_f = red_f;
+  const size_t smem = (sc_f + 2 * (size_t)Tup) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static PerDeviceFlag attr_set;
+  bool& set = attr_set.cur();
+  if (!set) {
+    cudaError_t err = cudaFuncSetAttribute(cross_attn_packed_tail_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024);
+    if (err != cudaSuccess) return err;
+    set = true;
+  }
+  launch_k_heavy(cross_attn_packed_tail_kernel<FMT>, dim3(n_full + 2 * (p.n_chunks - n_full)), dim3(kThreads), smem, stream,
+                 p, n_full);
+  return cudaGetLastError();
+}
+
+template <int VPL, int LPH, int FMT, int MINB>
 cudaError_t launch_fast(const CrossAttnParams& p, cudaStream_t stream) {
   constexpr int DS = 32 * VPL, RB = 64 / VPL;
   const int split = p.d / DS;
@@ -423,7 +497,7 @@ bool fast_supported(const CrossAttnParams& p) {
          (int64_t)p.T * 4 * p.d < (int64_t)1 << 31;
 }
 
-int g_packed_fast = 1;     // 0: generic kernel; 1 / 3: slice kernels, see launch_fast_any
+int g_packed_fast = 1;     // 0: generic kernel; 1 / 2 / 3: slice kernels, see launch_fast_any
 
 template <int VPL, int LPH, int MINB>
 cudaError_t launch_fast_fmt(const CrossAttnParams& p, cudaStream_t stream) {
@@ -435,13 +509,29 @@ cudaError_t launch_fast_fmt(const CrossAttnParams& p, cudaStream_t stream) {
 }
 
 // slice choice.  d = 512 (dh = 64): 256-column slices of 4 heads (8 lanes x 8 columns per head), 2048 CTAs for 1024 chunks.
-// d = 256 (dh = 32): g_packed_fast 1 = 128-column slices of 4 heads (8 lanes x 4 columns per head), also 2048 CTAs -- with
-// one CTA per chunk 1024 equal work items on 148 x 2 CTA slots run as 3.46 -> 4 rounds (13 % idle in the last round);
-// g_packed_fast 3 = that one-CTA-per-chunk form (4 lanes x 8 columns per head).
+// d = 256 (dh = 32): g_packed_fast 1 (default) = one CTA per chunk with a split tail (cross_attn_packed_tail_kernel),
+// 3 = one CTA per chunk throughout (4 lanes x 8 columns per head; 147.7 us at B = 1024),
+// 2 = two 128-column CTAs per chunk throughout (8 lanes x 4 columns per head; 158.3 us).
 cudaError_t launch_fast_any(const CrossAttnParams& p, cudaStream_t stream) {
   if (p.d == 512) return launch_fast_fmt<8, 8, 2>(p, stream);
   if (g_packed_fast == 3) return launch_fast_fmt<8, 4, 2>(p, stream);
-  return launch_fast_fmt<4, 8, 2>(p, stream);
+  if (g_packed_fast == 2) return launch_fast_fmt<4, 8, 2>(p, stream);
+  // default: whole rounds of one-CTA chunks, the remainder as two 128-column CTAs per chunk when that fits one round
+  static int slots[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!slots[dev & 63]) {
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    slots[dev & 63] = 2 * n_sm;
+  }
+  const int sl = slots[dev & 63], rem = p.n_chunks % sl;
+  const int n_full = (rem > 0 && 2 * rem <= sl && p.n_chunks > sl) ? p.n_chunks - rem : p.n_chunks;
+  switch (p.kv_fmt) {
+    case KV_Q23M: return launch_tail<KV_Q23M>(p, n_full, stream);
+    case KV_Q15M: return launch_tail<KV_Q15M>(p, n_full, stream);
+    default: return launch_tail<KV_FP24>(p, n_full, stream);
+  }
 }
 
 template <int VPL, int NQMAX, int FMT>

@@ -350,10 +350,16 @@ def test_full_batch_properties_l2t_1024():
     chunks, lengths = synth.make_chunks(B, T=T, seed=5, ragged=True, read_len=16)
     chunks[512:520] = chunks[0:8]                       # duplicates must decode identically
     lengths[512:520] = lengths[0:8]
+    # ... also when they sit in the split tail of the fixed-point cross attention (chunks >= 888 of 1024 are decoded by
+    # two 128-column CTAs each, which form every sum in the order of the whole-chunk CTA): same BITS, not just tokens
+    chunks[1000:1008] = chunks[0:8]
+    lengths[1000:1008] = lengths[0:8]
     eng = _engine(cfg, sd, B, T, L)
     eng.encode(chunks.cuda(), lengths.cuda())
+    lg = eng.decode_greedy(8, return_logits=True)["logits"].cpu()
+    assert torch.equal(lg[:, 1000:1008], lg[:, 0:8]) and torch.equal(lg[:, 512:520], lg[:, 0:8])
     full = eng.decode_greedy(L)["ids"].cpu()
-    assert torch.equal(full[512:520], full[0:8])
+    assert torch.equal(full[512:520], full[0:8]) and torch.equal(full[1000:1008], full[0:8])
     eng.encode(chunks[:24].cuda(), lengths[:24].cuda())
     part = eng.decode_greedy(L)["ids"].cpu()
     assert torch.equal(part, full[:24])                 # result of a chunk does not depend on its batch
