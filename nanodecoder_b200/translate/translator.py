@@ -80,6 +80,20 @@ def join_tokens(ids: np.ndarray, cut: np.ndarray, itos) -> List[List[str]]:
     return [flat[j * N: (j + 1) * N] for j in range(B)]
 
 
+def format_attention(src_raw, pred_tokens, attn_rows) -> str:
+    """The text block the reference writes per chunk under -attn_debug (translate/translator.py:284-335): a header of the
+    source samples and of the predicted tokens (+ "</s>") on ONE line, then one line of attention weights per decode
+    step.  src_raw: the chunk's samples (1-D), attn_rows: [steps][src_len] floats."""
+    preds = list(pred_tokens) + ["</s>"]
+    srcs = [str(x) for x in np.asarray(src_raw, dtype=np.float32).reshape(-1)]
+    row_format = "{:>8.5f} " * len(srcs)
+    out = ("{:>8.7} " + "{:>8.7} " * len(srcs)).format(">", *srcs)
+    out += ("{:>8.7} " + "{:>8.7} " * len(preds)).format("|", *preds) + "\n"
+    for row in attn_rows:
+        out += row_format.format(*row) + "\n"
+    return out
+
+
 def build_translator(opt, report_score=False, logger=None, out_file=None):
     """translate/translator.py:65-90.  ``opt`` comes from nanodecoder_b200.opts.translate_opts."""
     if len(opt.models) != 1:
@@ -184,6 +198,7 @@ class Translator(object):
             totals[1] += int(cut[:, 0].sum())
 
         pending = None
+        chunks_host = None
         for k, (idx, T) in enumerate(plan):
             idx_t = torch.from_numpy(idx).to(dev)
             if fast_host:
@@ -207,9 +222,15 @@ class Translator(object):
                 if self.verbose:
                     out = trans.log(next(counter))
                     (self.logger.info(out) if self.logger else os.write(1, out.encode("utf-8")))
-                if attn_debug and self.out_file_attn is not None and trans.attns is not None:
-                    rows = trans.attns[0].tolist()
-                    self.out_file_attn.write("\n".join(" ".join("%8.5f" % v for v in r) for r in rows) + "\n")
+                if attn_debug:
+                    if self.beam_size > 1:
+                        raise ValueError("-attn_debug with beam search: the engine keeps no per-beam attention history; "
+                                         "use -beam_size 1")
+                    if self.out_file_attn is not None:
+                        if chunks_host is None:
+                            chunks_host = chunks.cpu().numpy()
+                        self.out_file_attn.write(format_attention(chunks_host[i, : int(host_lengths[i])],
+                                                                  trans.pred_sents[0], trans.attns[0].tolist()))
         if pending is not None:
             finish(pending)
         pred_score_total += totals[0]

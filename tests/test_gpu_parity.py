@@ -394,6 +394,40 @@ def test_translator_api_drop_in(tmp_path):
         assert preds[i][0] == want, (i, preds[i][0], want)
 
 
+def test_attn_debug_writes_the_reference_block_per_chunk():
+    """Translator.setAttnFile + translate(attn_debug=True) (reference translate/translator.py:178-179, 284-335): one
+    block per chunk in input order -- header line, then max_length rows of head-0 cross-attention weights over the
+    chunk's own samples -- equal to the oracle's attention."""
+    import io
+    from nanodecoder_b200.checkpoint import Vocab
+    from nanodecoder_b200.engine import Engine
+    from nanodecoder_b200.opts import default_translate_opt
+    from nanodecoder_b200.translate.translator import Translator, _Field
+    from oracle import decode as od
+    from oracle.model import OracleModel
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    sd = synth.make_state_dict(cfg, seed=3)
+    L = 7
+    opt = default_translate_opt(beam_size=1, batch_size=4, max_length=L, src_seq_length=40, gpu=0)
+    eng = Engine(cfg, sd, max_batch=4, max_src_len=40, max_tgt_len=L)
+    tr = Translator(eng, {"tgt": _Field(Vocab(cfg.vocab))}, opt, cfg)
+    chunks, lengths = synth.make_chunks(6, T=40, seed=4, ragged=False)
+    buf = io.StringIO()
+    tr.setAttnFile(buf)
+    tr.translate(src=(chunks, lengths), batch_size=4, attn_debug=True)
+    lines = buf.getvalue().splitlines()
+    assert len(lines) == 6 * (1 + L)
+    om = OracleModel(sd, cfg)
+    for i in range(6):
+        head = lines[i * (1 + L)]
+        assert head.startswith("       > ") and "       | " in head and head.rstrip().endswith("</s>")
+        og = od.greedy(om, chunks[i:i + 1].t().contiguous().unsqueeze(2), lengths[i:i + 1], max_length=L,
+                       return_attention=True)
+        rows = np.array([[float(x) for x in ln.split()] for ln in lines[i * (1 + L) + 1: (i + 1) * (1 + L)]])
+        assert rows.shape == (L, 40)
+        np.testing.assert_allclose(rows, og["attention"][:, 0, :].numpy(), atol=2e-5)
+
+
 @pytest.mark.parametrize("beam,fast", [(1, False), (4, True), (4, False)])
 def test_translate_host_paths_agree(beam, fast):
     """Translator.translate builds its strings with array ops; the reference-shaped path

@@ -173,3 +173,12 @@ def test_array_path_equals_the_translation_builder_path(beam, n_best):
     assert p_fast == p_slow
     assert [[float(x) for x in s] for s in s_fast] == [[float(x) for x in s] for s in s_slow]
     assert len(tr2.logger.lines) == 13 and "PRED" in tr2.logger.lines[0]
+
+
+def test_attention_dump_has_the_reference_layout():
+    """-attn_debug block of one chunk (reference translate/translator.py:284-335): "{:>8.7} " cells for the source
+    samples and the predicted tokens (both headers on one line, as the reference writes them), "{:>8.5f} " weights."""
+    from nanodecoder_b200.translate.translator import format_attention
+    txt = format_attention([0.5, -1.234375, 12.0], ["A", "C"], [[0.25, 0.75, 0.0], [1.0, 0.0, 0.0]])
+    assert txt == ("       >      0.5  -1.2343     12.0 " "       |        A        C     </s> \n"
+                   " 0.25000  0.75000  0.00000 \n" " 1.00000  0.00000  0.00000 \n")
