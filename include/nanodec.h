@@ -120,6 +120,17 @@ ND_EXPORT int nd_frontend_chunks(nd_engine* e, const int16_t* signal, const int6
                        const int64_t* chunk_start, int32_t n_chunks, int32_t chunk_len,
                        float* out_chunks, int64_t* out_lengths, void* stream);
 
+/* the same two passes for float-valued reads: fp64 samples (a `.signal` file with non-integer tokens; the reference
+ * parses every token with float(), utils/labelop.py:216-217).  Median / MAD by radix select over the doubles, std with
+ * numpy's pairwise summation order (= the double np.std returns).                                  */
+ND_EXPORT int nd_frontend_stats_f64(nd_engine* e, const double* signal, const int64_t* read_offsets,
+                          int32_t n_reads, int32_t normalization, double* out_center,
+                          double* out_scale, void* stream);
+ND_EXPORT int nd_frontend_chunks_f64(nd_engine* e, const double* signal, const int64_t* read_offsets,
+                           const double* center, const double* scale, const int32_t* chunk_read,
+                           const int64_t* chunk_start, int32_t n_chunks, int32_t chunk_len,
+                           float* out_chunks, int64_t* out_lengths, void* stream);
+
 /* encoder ------------------------------------------------------------------------------------
  * src: [B, T] fp32 chunk-major zero padded; lengths: [B] int64 (device).                       */
 ND_EXPORT int nd_encode(nd_engine* e, const float* src, const int64_t* lengths, int32_t B, int32_t T,

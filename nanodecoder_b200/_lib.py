@@ -58,6 +58,8 @@ SIGNATURES = {
     "nd_finalize_weights": (C.c_int, [_P]),
     "nd_frontend_stats": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "nd_frontend_chunks": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "nd_frontend_stats_f64": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "nd_frontend_chunks_f64": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "nd_encode": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "nd_get_memory_bank": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32), _P]),
     "nd_decode_greedy": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),

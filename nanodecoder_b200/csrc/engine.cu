@@ -1389,6 +1389,27 @@ int nd_frontend_chunks(nd_engine* e, const int16_t* signal, const int64_t* read_
   return ND_OK;
 }
 
+int nd_frontend_stats_f64(nd_engine* e, const double* signal, const int64_t* read_offsets, int32_t n_reads,
+                          int32_t normalization, double* out_center, double* out_scale, void* stream) {
+  if (!e) return ND_ERR_INVALID;
+  if (e->sticky) return ND_ERR_CUDA;
+  cudaSetDevice(e->cfg.device);
+  if (normalization < 0 || normalization > 2) return fail(e, ND_ERR_INVALID, "unknown normalization");
+  ND_LAUNCH(e, frontend_stats_f64(signal, read_offsets, n_reads, normalization, out_center, out_scale, (cudaStream_t)stream));
+  return ND_OK;
+}
+
+int nd_frontend_chunks_f64(nd_engine* e, const double* signal, const int64_t* read_offsets, const double* center,
+                           const double* scale, const int32_t* chunk_read, const int64_t* chunk_start, int32_t n_chunks,
+                           int32_t chunk_len, float* out_chunks, int64_t* out_lengths, void* stream) {
+  if (!e) return ND_ERR_INVALID;
+  if (e->sticky) return ND_ERR_CUDA;
+  cudaSetDevice(e->cfg.device);
+  ND_LAUNCH(e, frontend_chunks_f64(signal, read_offsets, center, scale, chunk_read, chunk_start, n_chunks, chunk_len,
+                                   out_chunks, out_lengths, (cudaStream_t)stream));
+  return ND_OK;
+}
+
 int nd_encode(nd_engine* e, const float* src, const int64_t* lengths, int32_t B, int32_t T, void* stream) {
   ND_TRY(check_ready(e));
   cudaStream_t st = (cudaStream_t)stream;

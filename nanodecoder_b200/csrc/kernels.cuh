@@ -225,4 +225,11 @@ cudaError_t frontend_chunks(const int16_t* signal, const int64_t* offsets, const
                             const double* scale, const int32_t* chunk_read, const int64_t* chunk_start,
                             int n_chunks, int chunk_len, float* out, int64_t* out_len, cudaStream_t stream);
 
+// the same for float-valued reads (fp64 samples): see frontend.cu
+cudaError_t frontend_stats_f64(const double* signal, const int64_t* offsets, int n_reads, int mode,
+                               double* center, double* scale, cudaStream_t stream);
+cudaError_t frontend_chunks_f64(const double* signal, const int64_t* offsets, const double* center,
+                                const double* scale, const int32_t* chunk_read, const int64_t* chunk_start,
+                                int n_chunks, int chunk_len, float* out, int64_t* out_len, cudaStream_t stream);
+
 }  // namespace nd

@@ -170,22 +170,25 @@ class Engine(object):
 
     # ------------------------------------------------------------------------------------------
     def frontend_stats(self, signal: torch.Tensor, offsets: torch.Tensor, normalization: str = "median"):
-        """signal int16 [N_total] (device), offsets int64 [n_reads+1] (device) -> (center, scale) fp64"""
-        assert signal.dtype == torch.int16 and offsets.dtype == torch.int64 and signal.is_cuda and offsets.is_cuda
+        """signal int16 (raw DAC samples) or float64 (float-valued `.signal` files) [N_total] (device), offsets int64
+        [n_reads+1] (device) -> (center, scale) fp64"""
+        assert signal.dtype in (torch.int16, torch.float64) and offsets.dtype == torch.int64
+        assert signal.is_cuda and offsets.is_cuda
         n = offsets.numel() - 1
         center = torch.empty((n,), dtype=torch.float64, device=self.device)
         scale = torch.empty((n,), dtype=torch.float64, device=self.device)
-        self._check(self.lib.nd_frontend_stats(self._h, _ptr(signal), _ptr(offsets), n, _lib.NORM[normalization],
-                                               _ptr(center), _ptr(scale), self._stream()))
+        fn = self.lib.nd_frontend_stats if signal.dtype == torch.int16 else self.lib.nd_frontend_stats_f64
+        self._check(fn(self._h, _ptr(signal), _ptr(offsets), n, _lib.NORM[normalization], _ptr(center), _ptr(scale),
+                       self._stream()))
         return center, scale
 
     def frontend_chunks(self, signal, offsets, center, scale, chunk_read, chunk_start, chunk_len: int):
         n = chunk_read.numel()
         out = torch.empty((n, chunk_len), dtype=torch.float32, device=self.device)
         lens = torch.empty((n,), dtype=torch.int64, device=self.device)
-        self._check(self.lib.nd_frontend_chunks(self._h, _ptr(signal), _ptr(offsets), _ptr(center), _ptr(scale),
-                                                _ptr(chunk_read), _ptr(chunk_start), n, chunk_len, _ptr(out),
-                                                _ptr(lens), self._stream()))
+        fn = self.lib.nd_frontend_chunks if signal.dtype == torch.int16 else self.lib.nd_frontend_chunks_f64
+        self._check(fn(self._h, _ptr(signal), _ptr(offsets), _ptr(center), _ptr(scale), _ptr(chunk_read),
+                       _ptr(chunk_start), n, chunk_len, _ptr(out), _ptr(lens), self._stream()))
         return out, lens
 
     def test_gemm(self, mode: str, A, W, bias=None, residual=None, ln=None, relu=0):

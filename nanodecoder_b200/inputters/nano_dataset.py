@@ -92,8 +92,10 @@ class SignalFrontend(object):
         """reads: list of int16 arrays -> (chunks [n,T] fp32 cuda, lengths [n] int64 cuda,
         chunk_read int32 numpy [n])"""
         lens = np.array([r.size for r in reads], dtype=np.int64)
-        flat = np.concatenate([np.ascontiguousarray(r, dtype=np.int16) for r in reads]) if len(reads) else \
-            np.zeros((0,), np.int16)
+        # raw DAC samples are int16; a float-valued `.signal` file arrives as float64 and takes the fp64 kernels (int16
+        # reads pooled with it are widened: exact, and the statistics of both paths agree on integer samples)
+        dt = np.float64 if any(np.asarray(r).dtype != np.int16 for r in reads) else np.int16
+        flat = np.concatenate([np.ascontiguousarray(r, dtype=dt) for r in reads]) if len(reads) else np.zeros((0,), dt)
         return self.from_flat(torch.from_numpy(flat), lens)
 
     def from_flat(self, flat: torch.Tensor, read_lengths: Sequence[int]):
@@ -102,7 +104,7 @@ class SignalFrontend(object):
         dev = self.engine.device
         lens = np.asarray(read_lengths, dtype=np.int64)
         offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        assert flat.dtype == torch.int16 and flat.numel() == int(offsets[-1])
+        assert flat.dtype in (torch.int16, torch.float64) and flat.numel() == int(offsets[-1])
         sig = flat.to(dev, non_blocking=True)
         off = torch.from_numpy(offsets).to(dev, non_blocking=True)
         center, scale = self.engine.frontend_stats(sig, off, self.normalization)

@@ -91,7 +91,8 @@ def simple_assembly(bpreads, flag_intersection=True):
 
 
 def read_raw_signal(path, suffix):
-    """Raw int16 samples of one read (utils/labelop.py:199-219 without the normalisation)."""
+    """Raw samples of one read (utils/labelop.py:199-219 without the normalisation): int16 for DAC values (fast5 `Signal`
+    datasets, integer `.signal` files), float64 for a `.signal` file with non-integer values."""
     if suffix == "fast5":
         try:
             import h5py
@@ -108,8 +109,9 @@ def read_raw_signal(path, suffix):
                                           C.byref(count), C.byref(status))
     if rc == 0 and status.value == 0:                           # plain integers: parsed in libnanodec (17x numpy)
         return out[: count.value].copy()
-    vals = np.array(raw.decode("latin-1").split(), dtype=np.float64)      # floats / exponents: the general parser
+    # floats / exponents: the reference's own parse, [float(x) for x in text.split()] (utils/labelop.py:216-217)
+    vals = np.array([float(x) for x in raw.decode("latin-1").split()], dtype=np.float64)
     ints = np.round(vals)
     if vals.size and (np.abs(vals - ints).max() > 0 or ints.min() < -32768 or ints.max() > 32767):
-        raise ValueError("%s: the GPU front end takes raw int16 DAC samples; got non-integer values" % path)
+        return vals                                             # float-valued read: the fp64 front-end kernels
     return ints.astype(np.int16)

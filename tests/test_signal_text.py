@@ -31,12 +31,13 @@ def test_float_formatted_integers_take_the_general_parser(tmp_path):
     np.testing.assert_array_equal(got, [512, 481, -3])
 
 
-def test_non_integer_or_out_of_range_samples_are_refused(tmp_path):
+def test_float_valued_samples_come_back_as_float64(tmp_path):
+    """The reference takes any float token (utils/labelop.py:216-217); non-integer or out-of-int16 values go to the fp64
+    front-end kernels as float64, parsed by Python's float() like the reference does."""
+    got = read_raw_signal(_write(tmp_path, "1 2.5 3"), "signal")
+    assert got.dtype == np.float64
+    np.testing.assert_array_equal(got, [1.0, 2.5, 3.0])
+    got = read_raw_signal(_write(tmp_path, "1 40000 -3e-7"), "signal")
+    assert got.dtype == np.float64 and got[1] == 40000.0 and got[2] == float("-3e-7")
     with pytest.raises(ValueError):
-        read_raw_signal(_write(tmp_path, "1 2.5 3"), "signal")        # normalised floats are not raw DAC samples
-    with pytest.raises(ValueError):
-        read_raw_signal(_write(tmp_path, "1 40000 3"), "signal")
-    with pytest.raises(ValueError):
-        read_raw_signal(_write(tmp_path, "1 99999999999999999999 3"), "signal")
-    with pytest.raises(ValueError):
-        read_raw_signal(_write(tmp_path, "12a 3"), "signal")
+        read_raw_signal(_write(tmp_path, "12a 3"), "signal")              # float("12a") fails in the reference too
