@@ -775,6 +775,9 @@ namespace {
 
 // Cache layout: [slot][head][pos][dh] so that one head's keys / values of consecutive positions are
 // contiguous: dh/4 lanes cover one position with 128-bit loads, 32/(dh/4) positions per warp access.
+// U = independent 128-bit loads in flight per lane (the kernel is latency bound: head size 64 covers only 2 positions
+// per warp access, so it keeps 8 loads = 16 positions in flight; smaller heads 4)
+template <int U>
 __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
   const int row = p.row0 + blockIdx.x;
@@ -802,13 +805,13 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   for (int h = warp; h < H; h += nwarps) {
     float* ps = p_s + warp * p.Lmax;
     const float4 qq = *reinterpret_cast<const float4*>(q_s + h * dh + sub * 4);
-    // ---- scores: 4 independent 128-bit loads in flight per lane (the kernel is latency bound)
+    // ---- scores: U independent 128-bit loads in flight per lane (the kernel is latency bound)
     float m = -FLT_MAX;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j0 = 0; j0 < L; j0 += 4 * PPI) {
-      float4 kk[4];
+    for (int j0 = 0; j0 < L; j0 += U * PPI) {
+      float4 kk[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int j = j0 + u * PPI + grp;
         kk[u] = zero4;
         if (j < L) {
@@ -819,7 +822,7 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int j = j0 + u * PPI + grp;
         float sc = fmaf(qq.x, kk[u].x, fmaf(qq.y, kk[u].y, fmaf(qq.z, kk[u].z, qq.w * kk[u].w)));
         for (int o = LPP >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(ND_FULL, sc, o);
@@ -838,11 +841,11 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
     __syncwarp();
     // ---- context: each lane accumulates 4 features over its share of the positions
     float4 acc = zero4;
-    for (int j0 = 0; j0 < L; j0 += 4 * PPI) {
-      float4 vv[4];
-      float pj[4];
+    for (int j0 = 0; j0 < L; j0 += U * PPI) {
+      float4 vv[U];
+      float pj[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int j = j0 + u * PPI + grp;
         vv[u] = zero4;
         pj[u] = 0.f;
@@ -855,7 +858,7 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         acc.x = fmaf(pj[u], vv[u].x, acc.x); acc.y = fmaf(pj[u], vv[u].y, acc.y);
         acc.z = fmaf(pj[u], vv[u].z, acc.z); acc.w = fmaf(pj[u], vv[u].w, acc.w);
       }
@@ -877,7 +880,8 @@ cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream) {
   if (dh != 8 && dh != 16 && dh != 32 && dh != 64) return cudaErrorInvalidValue;
   const int nw = p.H < 8 ? p.H : 8;
   const size_t smem = ((size_t)p.d + (size_t)nw * p.Lmax) * sizeof(float);
-  launch_k(self_attn_kernel, dim3(p.rows), dim3(nw * 32), smem, stream, p);
+  if (dh == 64) launch_k(self_attn_kernel<8>, dim3(p.rows), dim3(nw * 32), smem, stream, p);
+  else launch_k(self_attn_kernel<4>, dim3(p.rows), dim3(nw * 32), smem, stream, p);
   return cudaGetLastError();
 }
 

@@ -298,62 +298,72 @@ __device__ __forceinline__ void fast_body(const CrossAttnParams& p, const int ch
   const uint8_t* loK = reinterpret_cast<const uint8_t*>(p.kv_lo) + row0 * lo_pitch + part * DS + lane * VPL;
   const int nit = Tup / RB;
 
-  // ---------------- phase 1: scores
-  for (int it = warp; it < nit; it += kWarps) {
-    const int t0 = it * RB;
-    RowRegs<VPL, FMT> rr[RB];
+  // ---------------- phase 1: scores.  UNR iterations' rows are requested together (the tail CTAs own 4 columns per
+  // lane: two 8-row iterations = the 6 KB per warp the 8-column form has in flight); they are consumed in order.
+  constexpr int UNR = CHAIN ? 2 : 1;
+  for (int it = warp; it < nit; it += UNR * kWarps) {
+    RowRegs<VPL, FMT> rr[UNR][RB];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      if (t0 + r < T) {
-        rr[r].load(hiK + (uint32_t)(t0 + r) * hi_pitch, loK + (uint32_t)(t0 + r) * lo_pitch);
-      } else {
+    for (int u = 0; u < UNR; ++u) {
+      const int t0 = (it + u * kWarps) * RB;
 #pragma unroll
-        for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[r].hi[i] = 0u;
+      for (int r = 0; r < RB; ++r) {
+        if (t0 + r < T) {
+          rr[u][r].load(hiK + (uint32_t)(t0 + r) * hi_pitch, loK + (uint32_t)(t0 + r) * lo_pitch);
+        } else {
 #pragma unroll
-        for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[r].lo[i] = 0u;
+          for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[u][r].hi[i] = 0u;
+#pragma unroll
+          for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[u][r].lo[i] = 0u;
+        }
       }
     }
-    if constexpr (CHAIN) {
 #pragma unroll
-      for (int b0 = 0; b0 < RB; b0 += 4) {
-        float v[4];
+    for (int u = 0; u < UNR; ++u) {
+      const int t0 = (it + u * kWarps) * RB;
+      if (t0 >= Tup) break;                                          // warp-uniform
+      if constexpr (CHAIN) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          float kf[VPL];
+        for (int b0 = 0; b0 < RB; b0 += 4) {
+          float v[4];
 #pragma unroll
-          for (int i = 0; i < VPL; ++i) kf[i] = rr[b0 + r].get(i);
-          float s = 0.f;
+          for (int r = 0; r < 4; ++r) {
+            float kf[VPL];
 #pragma unroll
-          for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], kf[i], s);
-          s = __shfl_up_sync(ND_FULL, s, 1);                       // odd lanes: the even partner's chain
+            for (int i = 0; i < VPL; ++i) kf[i] = rr[u][b0 + r].get(i);
+            float s = 0.f;
 #pragma unroll
-          for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], kf[i], s);
-          v[r] = s;                                                // complete 8-column chain in the odd lanes
+            for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], kf[i], s);
+            s = __shfl_up_sync(ND_FULL, s, 1);                       // odd lanes: the even partner's chain
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], kf[i], s);
+            v[r] = s;                                                // complete 8-column chain in the odd lanes
+          }
+          rs_stage<2, 4>(v, lane);
+          rs_stage<1, 2>(v, lane);
+          const int t = t0 + b0 + ((lane >> 1) & 3);
+          const float ks = kstep[t];
+          if (lane & 1) sc[head * TS + t] = ks < 0.f ? -1e18f : v[0] * ks;
         }
-        rs_stage<2, 4>(v, lane);
-        rs_stage<1, 2>(v, lane);
-        const int t = t0 + b0 + ((lane >> 1) & 3);
-        const float ks = kstep[t];
-        if (lane & 1) sc[head * TS + t] = ks < 0.f ? -1e18f : v[0] * ks;
-      }
-    } else {
+      } else {
 #pragma unroll
-      for (int b0 = 0; b0 < RB; b0 += LPH) {
-        float v[LPH];
+        for (int b0 = 0; b0 < RB; b0 += LPH) {
+          float v[LPH];
 #pragma unroll
-        for (int r = 0; r < LPH; ++r) {
-          float s = 0.f;
+          for (int r = 0; r < LPH; ++r) {
+            float s = 0.f;
 #pragma unroll
-          for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], rr[b0 + r].get(i), s);
-          v[r] = s;
+            for (int i = 0; i < VPL; ++i) s = fmaf(qr[i], rr[u][b0 + r].get(i), s);
+            v[r] = s;
+          }
+          // reduce-scatter over the LPH lanes of the head: lane j ends with the complete sum of row j
+          if constexpr (LPH >= 8) rs_stage<4, 4>(v, lane);
+          rs_stage<2, 2>(v, lane);
+          rs_stage<1, 1>(v, lane);
+          const int t = t0 + b0 + j;
+          const float ks = kstep[t];
+          sc[head * TS + t] = ks < 0.f ? -1e18f : v[0] * ks;     // rows >= T: finite junk, never read by the softmax
         }
-        // reduce-scatter over the LPH lanes of the head: lane j ends with the complete sum of row j
-        if constexpr (LPH >= 8) rs_stage<4, 4>(v, lane);
-        rs_stage<2, 2>(v, lane);
-        rs_stage<1, 1>(v, lane);
-        const int t = t0 + b0 + j;
-        const float ks = kstep[t];
-        sc[head * TS + t] = ks < 0.f ? -1e18f : v[0] * ks;       // rows >= T: finite junk, never read by the softmax
       }
     }
   }
@@ -388,27 +398,35 @@ __device__ __forceinline__ void fast_body(const CrossAttnParams& p, const int ch
   for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
   const uint8_t* hiV = hiK + 2 * d;                // V = columns [d, 2d) of the planes
   const uint8_t* loV = loK + d;
-  for (int it = warp; it < nit; it += kWarps) {
-    const int t0 = it * RB;
-    RowRegs<VPL, FMT> rr[RB];
+  for (int it = warp; it < nit; it += UNR * kWarps) {
+    RowRegs<VPL, FMT> rr[UNR][RB];
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      if (t0 + r < T) {
-        rr[r].load(hiV + (uint32_t)(t0 + r) * hi_pitch, loV + (uint32_t)(t0 + r) * lo_pitch);
-      } else {
+    for (int u = 0; u < UNR; ++u) {
+      const int t0 = (it + u * kWarps) * RB;
 #pragma unroll
-        for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[r].hi[i] = 0u;
+      for (int r = 0; r < RB; ++r) {
+        if (t0 + r < T) {
+          rr[u][r].load(hiV + (uint32_t)(t0 + r) * hi_pitch, loV + (uint32_t)(t0 + r) * lo_pitch);
+        } else {
 #pragma unroll
-        for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[r].lo[i] = 0u;
+          for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[u][r].hi[i] = 0u;
+#pragma unroll
+          for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[u][r].lo[i] = 0u;
+        }
       }
     }
 #pragma unroll
-    for (int r4 = 0; r4 < RB; r4 += 4) {
-      const float4 pq = *reinterpret_cast<const float4*>(sc + head * TS + t0 + r4);
+    for (int u = 0; u < UNR; ++u) {
+      const int t0 = (it + u * kWarps) * RB;
+      if (t0 >= Tup) break;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i)
-        acc[i] = fmaf(pq.x, rr[r4].get(i), fmaf(pq.y, rr[r4 + 1].get(i), fmaf(pq.z, rr[r4 + 2].get(i),
-                 fmaf(pq.w, rr[r4 + 3].get(i), acc[i]))));
+      for (int r4 = 0; r4 < RB; r4 += 4) {
+        const float4 pq = *reinterpret_cast<const float4*>(sc + head * TS + t0 + r4);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+          acc[i] = fmaf(pq.x, rr[u][r4].get(i), fmaf(pq.y, rr[u][r4 + 1].get(i), fmaf(pq.z, rr[u][r4 + 2].get(i),
+                   fmaf(pq.w, rr[u][r4 + 3].get(i), acc[i]))));
+      }
     }
   }
   __syncthreads();                                 // scores no longer needed: reuse as reduction buffer
@@ -566,7 +584,24 @@ cudaError_t launch_packed(const CrossAttnParams& p, cudaStream_t stream) {
 }
 
 // =============================================================================================
-// Packer: one warp per (row, part); lane l quantises columns [l*VPL, (l+1)*VPL) of the part.
+// Packer: one warp per (row, part); lane l quantises columns [l*VPL, (l+1)*VPL) of the part.  128-bit loads, the
+// integers are packed in registers and leave as one or two vector stores per plane (per-element 2-byte / 1-byte stores
+// made this kernel 5 ms per layer at d = 512: more than the projection GEMM in front of it).
+template <int NB>
+__device__ __forceinline__ void store_bytes(uint8_t* p, const uint32_t* r) {
+  if constexpr (NB >= 16) {
+#pragma unroll
+    for (int i = 0; i < NB / 16; ++i)
+      *reinterpret_cast<uint4*>(p + 16 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  } else if constexpr (NB == 8) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(r[0], r[1]);
+  } else if constexpr (NB == 4) {
+    *reinterpret_cast<uint32_t*>(p) = r[0];
+  } else {
+    *reinterpret_cast<uint16_t*>(p) = (uint16_t)r[0];
+  }
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ kv, int64_t rows, int fmt,
                                                       int16_t* __restrict__ hi, uint8_t* __restrict__ lo,
@@ -579,9 +614,19 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
   const int part = (int)(item & 1);
   const float* src = kv + row * (2 * d) + part * d + lane * VPL;
   float x[VPL];
+  if constexpr (VPL % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < VPL; i += 4) {
+      const float4 t = ldg_stream4(src + i);
+      x[i] = t.x; x[i + 1] = t.y; x[i + 2] = t.z; x[i + 3] = t.w;
+    }
+  } else {
+    const float2 t = ldg_stream2(src);
+    x[0] = t.x; x[1] = t.y;
+  }
   float amax = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) { x[i] = src[i]; amax = fmaxf(amax, fabsf(x[i])); }
+  for (int i = 0; i < VPL; ++i) amax = fmaxf(amax, fabsf(x[i]));
   amax = warp_max(amax);
   // 2^e > amax (amax = f * 2^e, f in [0.5, 1)); clamp the exponent so the step stays a normal fp32 number
   int e = 0;
@@ -592,26 +637,34 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
   const float inv = ldexpf(1.0f, bits - e);
   const float lim = ldexpf(1.0f, bits) - 1.0f;
   if (lane == 0) scale[row * 2 + part] = fmt == KV_FP24 ? 1.0f : step;
-  int16_t* hp = hi + row * (2 * d) + part * d + lane * VPL;
-  uint8_t* lp = lo ? lo + row * (2 * d) + part * d + lane * VPL : nullptr;
+  uint32_t hw[VPL >= 2 ? VPL / 2 : 1], lw[VPL >= 4 ? VPL / 4 : 1];
+#pragma unroll
+  for (int i = 0; i < (VPL >= 2 ? VPL / 2 : 1); ++i) hw[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < (VPL >= 4 ? VPL / 4 : 1); ++i) lw[i] = 0u;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
+    uint32_t h16, l8 = 0u;
     if (fmt == KV_FP24) {
       // fp32 rounded to nearest-even at 16 significant bits: the top 24 bits of the pattern
       const uint32_t b = __float_as_uint(x[i]);
       const uint32_t r = (b + 0x7fu + ((b >> 8) & 1u)) >> 8;
-      hp[i] = (int16_t)(r >> 8);
-      lp[i] = (uint8_t)(r & 255u);
-      continue;
-    }
-    const int m = (int)fminf(fmaxf(rintf(x[i] * inv), -lim), lim);           // x * 2^k is exact; rint ties to even
-    if (fmt == KV_Q24 || fmt == KV_Q23M) {
-      hp[i] = (int16_t)(m >> 8);
-      lp[i] = (uint8_t)(m & 255);
+      h16 = r >> 8;
+      l8 = r & 255u;
     } else {
-      hp[i] = (int16_t)m;
+      const int m = (int)fminf(fmaxf(rintf(x[i] * inv), -lim), lim);         // x * 2^k is exact; rint ties to even
+      if (fmt == KV_Q24 || fmt == KV_Q23M) {
+        h16 = (uint32_t)(m >> 8) & 0xffffu;
+        l8 = (uint32_t)m & 255u;
+      } else {
+        h16 = (uint32_t)m & 0xffffu;
+      }
     }
+    hw[i >> 1] |= h16 << (16 * (i & 1));
+    lw[i >> 2] |= l8 << (8 * (i & 3));
   }
+  store_bytes<2 * VPL>(reinterpret_cast<uint8_t*>(hi + row * (2 * d) + part * d + lane * VPL), hw);
+  if (lo) store_bytes<VPL>(lo + row * (2 * d) + part * d + lane * VPL, lw);
 }
 
 }  // namespace
