@@ -775,8 +775,7 @@ namespace {
 
 // Cache layout: [slot][head][pos][dh] so that one head's keys / values of consecutive positions are
 // contiguous: dh/4 lanes cover one position with 128-bit loads, 32/(dh/4) positions per warp access.
-// U = independent 128-bit loads in flight per lane (the kernel is latency bound: head size 64 covers only 2 positions
-// per warp access, so it keeps 8 loads = 16 positions in flight; smaller heads 4)
+// U = independent 128-bit loads in flight per lane (the kernel is latency bound)
 template <int U>
 __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
@@ -880,8 +879,8 @@ cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream) {
   if (dh != 8 && dh != 16 && dh != 32 && dh != 64) return cudaErrorInvalidValue;
   const int nw = p.H < 8 ? p.H : 8;
   const size_t smem = ((size_t)p.d + (size_t)nw * p.Lmax) * sizeof(float);
-  if (dh == 64) launch_k(self_attn_kernel<8>, dim3(p.rows), dim3(nw * 32), smem, stream, p);
-  else launch_k(self_attn_kernel<4>, dim3(p.rows), dim3(nw * 32), smem, stream, p);
+  // U = 8 at head size 64 measured slower (64.7 vs 56.1 us per launch at d = 512, B = 1024, call r02f): 4 everywhere
+  launch_k(self_attn_kernel<4>, dim3(p.rows), dim3(nw * 32), smem, stream, p);
   return cudaGetLastError();
 }
 
