@@ -210,6 +210,8 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *   "cross_ring_groups" (default 2, process-wide): consumer warp groups of the ring kernel (2 for <= 5 beams);
  *   "gemm_a_tmem"    (default 1, process-wide): the 64-wide one-tile-per-CTA 3xTF32 kernels (decode step) keep the
  *                    A operand in tensor memory like the persistent kernel; 0 = shared memory (same bits);
+ *   "gemm_wide_wave" (default 1, process-wide): decode-step projections whose 64-wide tiles would not fit one wave of SMs
+ *                    (N = 1536 at d = 512) use 128-wide tiles; same bits;
  *   "gemm_serial_split" (default 1, process-wide): projections with >= 2048 rows run the split-K sum inside one CTA
  *                    (bit-identical to the cluster split), 0 = always the cluster split.
  *   "cross_packed_fast" (default 1, process-wide): greedy cross attention over fixed-point keys / values at d = 256 /

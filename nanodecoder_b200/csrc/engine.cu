@@ -1545,6 +1545,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     gemm_tc_set_a_tmem(value != 0);
     return ND_OK;
   }
+  if (strcmp(name, "gemm_wide_wave") == 0) {      // process-wide
+    gemm_tc_set_wide_wave(value != 0);
+    return ND_OK;
+  }
   if (strcmp(name, "gemm_serial_split") == 0) {   // process-wide
     gemm_tc_set_serial_split(value != 0);
     return ND_OK;

@@ -45,6 +45,7 @@ cudaError_t gemm_tc(const GemmParams& p, int npass, cudaStream_t stream);
 void gemm_tc_set_persistent(int mode);         // large tile counts: 2 (default) persistent kernel with A in tensor memory,
                                                // 1 persistent kernel with A in shared memory, 0 one tile per CTA
 void gemm_tc_set_serial_split(int on);         // 1 (default): >= 2048 rows run the split-K sum inside one CTA (same bits)
+void gemm_tc_set_wide_wave(int on);            // 1 (default): 128-wide tiles when 64-wide ones would need a second, mostly empty wave
 void gemm_tc_set_a_tmem(int on);               // 1 (default): one-tile-per-CTA 3xTF32 kernels keep the A operand in tensor memory
 void gemm_tc_set_debug(long long* dev_buf);   // timeline buffer for subsequent gemm_tc launches (nullptr = off)
 // one-time driver entry-point lookup for tensor-map encoding; returns false if unavailable

@@ -1082,6 +1082,7 @@ cudaError_t launch(const GemmParams& p, cudaStream_t stream) {
 int g_persist = 2;       // 0: always one tile per CTA (cross-check), 1: persistent kernel, 2 (default): ... with A in tensor memory
 int g_serial_split = 1;  // 0: cluster split-K also for many rows (cross-check: results are bit-identical)
 int g_atm = 1;           // one-tile-per-CTA kernels: A operand in tensor memory (0: shared memory; same bits)
+int g_wide_wave = 1;     // 128-wide tiles when the 64-wide tiles of a 1024-row problem exceed one wave (see dispatch)
 int g_n_sm = 0;
 
 template <int BN, int NPASS, bool ATM = false>
@@ -1133,7 +1134,8 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
   if constexpr (NPASS == 3) {
     // A operand in tensor memory (same bits) for the 64-wide tiles: decode 81.2 -> 80.7 ms.  The one-tile 128-wide
     // kernel (N = 2048 at M = 1024) measured slower with it (26.8 -> 29.0 us) and keeps A in shared memory.
-    if (g_atm && !(g_serial_split && split > 1 && p.M >= 2048) && !(split == 1 && tiles128 >= 120 && p.N > 64)) {
+    const bool wide_for_wave = g_wide_wave && split == 1 && p.M < 8192 && 8 * cdiv(p.N, 64) > 148 && p.N >= 256;
+    if (g_atm && !(g_serial_split && split > 1 && p.M >= 2048) && !(split == 1 && (tiles128 >= 120 || wide_for_wave) && p.N > 64)) {
       switch (split) {
         case 4: return launch<64, 3, 4, 1, true>(p, stream);
         case 2: return launch<64, 3, 2, 1, true>(p, stream);
@@ -1141,7 +1143,10 @@ cudaError_t dispatch(const GemmParams& p, cudaStream_t stream) {
       }
     }
   }
-  if (split == 1 && tiles128 >= 120 && p.N > 64) return launch<128, NPASS, 1>(p, stream);
+  // 64-wide tiles of a 1024-row problem that do not fit one wave of SMs (N = 1536: 192 CTAs, the second wave 30 % full):
+  // 128-wide tiles instead (96 CTAs).  A function of N only, and the tile width never changes the summation order.
+  const bool wide_for_wave = g_wide_wave && split == 1 && p.M < 8192 && 8 * cdiv(p.N, 64) > 148 && p.N >= 256;
+  if (split == 1 && (tiles128 >= 120 || wide_for_wave) && p.N > 64) return launch<128, NPASS, 1>(p, stream);
   // many rows (beam x batch): the cluster split would run several waves of short CTAs; one CTA per 128 x 128 tile
   // with the K slices in separate accumulators gives the same bits in one wave
   if (g_serial_split && split > 1 && p.M >= 2048)
@@ -1172,6 +1177,7 @@ void gemm_tc_set_debug(long long* dev_buf) { g_dbg = dev_buf; }
 void gemm_tc_set_persistent(int on) { g_persist = on; }
 void gemm_tc_set_serial_split(int on) { g_serial_split = on; }
 void gemm_tc_set_a_tmem(int on) { g_atm = on; }
+void gemm_tc_set_wide_wave(int on) { g_wide_wave = on; }
 
 bool gemm_tc_available(const char** why) {
   const bool ok = lookup();

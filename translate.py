@@ -193,6 +193,9 @@ def main(opt, logger):
         lines = run_reads(opt, [(i, todo[i]) for i in mine], read_raw_signal, frontend, translator)
     finally:
         finish_lines(opt, lines)                                 # every rank always enters the final gather
+        if ws > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
