@@ -210,6 +210,9 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *   "cross_ring_groups" (default 2, process-wide): consumer warp groups of the ring kernel (2 for <= 5 beams);
  *   "gemm_a_tmem"    (default 1, process-wide): the 64-wide one-tile-per-CTA 3xTF32 kernels (decode step) keep the
  *                    A operand in tensor memory like the persistent kernel; 0 = shared memory (same bits);
+ *   "frontend_fast"  (default 1, process-wide): per-read statistics from one shared-memory histogram (reads whose value
+ *                    range exceeds 16384 fall back to the radix select) and the 8-samples-per-thread chunk gather;
+ *                    0 = the general kernels; same bits;
  *   "gemm_wide_wave" (default 1, process-wide): decode-step projections whose 64-wide tiles would not fit one wave of SMs
  *                    (N = 1536 at d = 512) use 128-wide tiles; same bits;
  *   "gemm_serial_split" (default 1, process-wide): projections with >= 2048 rows run the split-K sum inside one CTA

@@ -119,6 +119,7 @@ struct nd_engine {
   float* mb = nullptr;               // memory bank [B, T', d]
   float* emb_remap = nullptr;        // cnn encoder: Linear(1,d) output (decoder init_state needs it)
   float* enc_hn = nullptr; float* enc_cn = nullptr;   // rnn encoders: [Le*dirs, B, hh]
+  int* fe_todo = nullptr; int fe_todo_cap = 0;     // front end: reads left for the radix-select kernel
   int B = 0, T = 0, Tp = 0;          // last encode
   bool encoded = false;
 
@@ -1374,7 +1375,15 @@ int nd_frontend_stats(nd_engine* e, const int16_t* signal, const int64_t* read_o
   if (e->sticky) return ND_ERR_CUDA;
   cudaSetDevice(e->cfg.device);
   if (normalization < 0 || normalization > 2) return fail(e, ND_ERR_INVALID, "unknown normalization");
-  ND_LAUNCH(e, frontend_stats(signal, read_offsets, n_reads, normalization, out_center, out_scale, (cudaStream_t)stream));
+  if (n_reads > e->fe_todo_cap) {                     // scratch of the histogram path: grows with the largest call seen
+    int* p = nullptr;
+    ND_CUDA(e, cudaMalloc(&p, (size_t)n_reads * sizeof(int)));
+    e->allocs.push_back(p);                           // (the old block is freed with the engine)
+    e->fe_todo = p;
+    e->fe_todo_cap = n_reads;
+  }
+  ND_LAUNCH(e, frontend_stats(signal, read_offsets, n_reads, normalization, out_center, out_scale, e->fe_todo,
+                              (cudaStream_t)stream));
   return ND_OK;
 }
 
@@ -1543,6 +1552,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
   }
   if (strcmp(name, "gemm_a_tmem") == 0) {         // process-wide
     gemm_tc_set_a_tmem(value != 0);
+    return ND_OK;
+  }
+  if (strcmp(name, "frontend_fast") == 0) {       // process-wide
+    frontend_set_fast(value != 0);
     return ND_OK;
   }
   if (strcmp(name, "gemm_wide_wave") == 0) {      // process-wide

@@ -102,13 +102,16 @@ __device__ double pairwise_sum(F f, int64_t lo, int64_t n) {
   return pairwise_sum(f, lo, n2) + pairwise_sum(f, lo + n2, n - n2);
 }
 
+// todo != nullptr: only the reads the histogram kernel left (todo[r] != 0)
 __global__ void __launch_bounds__(kStatThreads) stats_kernel(const int16_t* __restrict__ signal,
                                                              const int64_t* __restrict__ offsets, int mode,
                                                              double* __restrict__ center,
-                                                             double* __restrict__ scale) {
+                                                             double* __restrict__ scale,
+                                                             const int* __restrict__ todo) {
   __shared__ unsigned hist[1024];
   __shared__ int sel[8];
   const int r = blockIdx.x;
+  if (todo && !todo[r]) return;
   const int16_t* x = signal + offsets[r];
   const int64_t n = offsets[r + 1] - offsets[r];
   if (n <= 0) {
@@ -145,7 +148,202 @@ __global__ void __launch_bounds__(kStatThreads) stats_kernel(const int16_t* __re
   if (threadIdx.x == 0) { center[r] = c; scale[r] = s; }
 }
 
-// 4 samples per thread: coalesced 2-byte loads, one 128-bit store
+
+// ---------------------------------------------------------------------------------------------
+// Fast path of the statistics: ONE histogram per read.  Raw DAC samples span a few thousand distinct values, so after
+// a min / max pass (which also pulls the read into L2) the whole read is histogrammed into shared memory (bins
+// x - min, up to kHistBins) with 128-bit loads, and both the median and the MAD come out of that histogram: the MAD's
+// order statistics of |2x - 2*median| are found by walking outwards from the median over the bins.  Two vectorised
+// passes (one from HBM, one from L2) instead of four scalar ones; reads with a wider value range take stats_kernel.
+constexpr int kHistBins = 16384;
+
+// f(v) for every sample of x[0, n): 8 samples per 128-bit load on the 16-byte aligned body, scalars at both ends
+template <class F>
+__device__ __forceinline__ void for_each_sample(const int16_t* x, int64_t n, F f) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  int64_t head = (int64_t)(((16 - (reinterpret_cast<uintptr_t>(x) & 15)) & 15) >> 1);
+  if (head > n) head = n;
+  if (tid < head) f((int)x[tid]);
+  const int64_t nvec = (n - head) >> 3;
+  const int4* xv = reinterpret_cast<const int4*>(x + head);
+  for (int64_t i = tid; i < nvec; i += nt) {
+    const int4 q = __ldg(xv + i);
+    const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f((int)(short)(w[k] & 0xffff));
+      f(w[k] >> 16);
+    }
+  }
+  const int64_t done = head + (nvec << 3);
+  if (tid < n - done) f((int)x[done + tid]);
+}
+
+__global__ void __launch_bounds__(kStatThreads) stats_hist_kernel(const int16_t* __restrict__ signal,
+                                                                  const int64_t* __restrict__ offsets, int mode,
+                                                                  double* __restrict__ center,
+                                                                  double* __restrict__ scale, int* __restrict__ todo) {
+  extern __shared__ unsigned hist_s[];                // [kHistBins]
+  __shared__ int s_red[2][kStatThreads / 32];
+  __shared__ unsigned long long s_scan[kStatThreads];
+  __shared__ int s_val[2];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int16_t* x = signal + offsets[r];
+  const int64_t n = offsets[r + 1] - offsets[r];
+  if (tid == 0) todo[r] = 0;
+  if (n <= 0 || mode == 2) {
+    if (tid == 0) { center[r] = 0.0; scale[r] = 1.0; }
+    return;
+  }
+  // ---- pass A: value range
+  int lo = 32767, hi = -32768;
+  for_each_sample(x, n, [&](int v) { lo = min(lo, v); hi = max(hi, v); });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(ND_FULL, lo, o));
+    hi = max(hi, __shfl_xor_sync(ND_FULL, hi, o));
+  }
+  if ((tid & 31) == 0) { s_red[0][tid >> 5] = lo; s_red[1][tid >> 5] = hi; }
+  __syncthreads();
+  lo = s_red[0][0]; hi = s_red[1][0];
+#pragma unroll
+  for (int w = 1; w < kStatThreads / 32; ++w) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); }
+  const int range = hi - lo + 1;
+  if (range > kHistBins) {                            // wide value range: the radix-select kernel takes this read
+    if (tid == 0) todo[r] = 1;
+    return;
+  }
+  // ---- pass B: histogram
+  for (int i = tid; i < range; i += kStatThreads) hist_s[i] = 0u;
+  __syncthreads();
+  for_each_sample(x, n, [&](int v) { atomicAdd(&hist_s[v - lo], 1u); });
+  __syncthreads();
+  // ---- the two middle order statistics: per-thread bin groups, block scan of the group counts, local walk
+  const int64_t k1 = (n - 1) / 2, k2 = n / 2;
+  const int bpt = (range + kStatThreads - 1) / kStatThreads;
+  const int b0 = tid * bpt, b1 = min(range, b0 + bpt);
+  unsigned long long mine = 0;
+  for (int b = b0; b < b1; ++b) mine += hist_s[b];
+  s_scan[tid] = mine;
+  __syncthreads();
+  for (int o = 1; o < kStatThreads; o <<= 1) {        // inclusive Hillis-Steele scan (512 values)
+    const unsigned long long add = tid >= o ? s_scan[tid - o] : 0ull;
+    __syncthreads();
+    s_scan[tid] += add;
+    __syncthreads();
+  }
+  const unsigned long long before = s_scan[tid] - mine;
+  for (int q = 0; q < 2; ++q) {
+    const unsigned long long k = (unsigned long long)(q ? k2 : k1);
+    if (k >= before && k < before + mine) {
+      unsigned long long cum = before;
+      for (int b = b0; b < b1; ++b) {
+        cum += hist_s[b];
+        if (k < cum) { s_val[q] = lo + b; break; }
+      }
+    }
+  }
+  __syncthreads();
+  const int med2 = s_val[0] + s_val[1];               // 2 * median, exact
+  if (tid != 0) return;
+  const double c = 0.5 * (double)med2;
+  double s = 1.0;
+  if (mode == 0) {
+    // order statistics k1, k2 of d = |2x - med2|: merge the bins below the median (descending x) and above it
+    // (ascending x) by increasing d
+    int a = (int)floor(0.5 * (double)med2);           // largest x with 2x <= med2
+    int b = a + 1;                                    // smallest x with 2x > med2
+    long long cum = 0;
+    int d1 = 0, d2 = 0;
+    bool f1 = false, f2 = false;
+    while (!(f1 && f2)) {
+      const int da = a >= lo ? med2 - 2 * a : 0x7fffffff;
+      const int db = b <= hi ? 2 * b - med2 : 0x7fffffff;
+      int d;
+      long long cnt;
+      if (da <= db) { d = da; cnt = hist_s[a - lo]; --a; if (da == db) { cnt += hist_s[b - lo]; ++b; } }
+      else { d = db; cnt = hist_s[b - lo]; ++b; }
+      if (!f1 && k1 < cum + cnt) { d1 = d; f1 = true; }
+      if (!f2 && k2 < cum + cnt) { d2 = d; f2 = true; }
+      cum += cnt;
+    }
+    const double m1 = (0.5 * (double)d1) / kMadC;
+    const double m2 = (0.5 * (double)d2) / kMadC;
+    s = (k1 == k2) ? m1 : (m1 + m2) / 2.0;
+  } else {
+    const double mean = pairwise_sum([&](int64_t i) { return (double)x[i]; }, 0, n) / (double)n;
+    const double ss = pairwise_sum([&](int64_t i) { const double t = (double)x[i] - mean; return t * t; }, 0, n);
+    s = sqrt(ss / (double)n);
+  }
+  center[r] = c;
+  scale[r] = s;
+}
+
+// Chunk gather, 8 samples per thread: the chunk's samples are staged in shared memory with 128-bit loads of the aligned
+// segments that cover them (reads start at arbitrary sample offsets), normalised in fp64 and stored as two 128-bit
+// vectors.  (x - center) * (1 / scale) replaces the fp64 division (20+ instructions per sample, the kernel's former
+// bound) wherever that is provably the same float: the true quotient and its fp64 rounding both lie within 2^-52
+// relative of the product, so if the product's neighbours at +-2^-50 round to the same float, so does the reference's
+// float(float64 quotient); otherwise (about one sample in 10^8) the division is done.
+__global__ void __launch_bounds__(128) chunks_vec_kernel(const int16_t* __restrict__ signal,
+                                                         const int64_t* __restrict__ offsets,
+                                                         const double* __restrict__ center,
+                                                         const double* __restrict__ scale,
+                                                         const int32_t* __restrict__ chunk_read,
+                                                         const int64_t* __restrict__ chunk_start, int chunk_len,
+                                                         float* __restrict__ out, int64_t* __restrict__ out_len) {
+  extern __shared__ __align__(16) int16_t stage[];    // [chunk_len + 16]
+  const int c = blockIdx.x;
+  const int r = chunk_read[c];
+  const int64_t start = chunk_start[c];
+  const int64_t n = offsets[r + 1] - offsets[r];
+  int64_t len64 = n - start;
+  if (len64 > chunk_len) len64 = chunk_len;
+  if (len64 < 0) len64 = 0;
+  const int len = (int)len64;
+  if (threadIdx.x == 0) out_len[c] = len;
+  const int16_t* x = signal + offsets[r] + start;
+  const int mis = (int)((reinterpret_cast<uintptr_t>(x) & 15) >> 1);         // samples before x in its 16-byte segment
+  const int4* seg = reinterpret_cast<const int4*>(x - mis);
+  const int nseg = (mis + len + 7) >> 3;
+  // the last segment may reach past the read (and, for the last read, past the buffer): guard it with scalar loads
+  const int16_t* buf_end = signal + offsets[r + 1];
+  for (int i = threadIdx.x; i < nseg; i += blockDim.x) {
+    const int16_t* p = reinterpret_cast<const int16_t*>(seg + i);
+    if (p + 8 <= buf_end) {                           // (p >= signal: the buffer base is 16-byte aligned)
+      reinterpret_cast<int4*>(stage)[i] = __ldg(seg + i);
+    } else {
+      for (int k = 0; k < 8; ++k) stage[i * 8 + k] = (p + k < buf_end) ? p[k] : (int16_t)0;
+    }
+  }
+  __syncthreads();
+  const double ctr = center[r], scl = scale[r];
+  const double rcp = 1.0 / scl;
+  float* o = out + (int64_t)c * chunk_len;
+  for (int j0 = threadIdx.x * 8; j0 < chunk_len; j0 += blockDim.x * 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = j0 + i;
+      float f = 0.f;
+      if (j < len) {
+        const double num = (double)stage[mis + j] - ctr;
+        const double q = num * rcp;
+        f = (float)q;
+        if ((float)(q * (1.0 - 0x1p-50)) != (float)(q * (1.0 + 0x1p-50))) f = (float)(num / scl);
+      }
+      v[i] = f;
+    }
+    if (j0 + 8 <= chunk_len) {
+      *reinterpret_cast<float4*>(o + j0) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + j0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      for (int i = 0; i < 8 && j0 + i < chunk_len; ++i) o[j0 + i] = v[i];
+    }
+  }
+}
+
+// general form (any chunk_len / alignment): 4 samples per thread, 2-byte loads, fp64 division
 __global__ void __launch_bounds__(128) chunks_kernel(const int16_t* __restrict__ signal,
                                                      const int64_t* __restrict__ offsets,
                                                      const double* __restrict__ center,
@@ -314,11 +512,28 @@ cudaError_t frontend_chunks_f64(const double* signal, const int64_t* offsets, co
   return cudaGetLastError();
 }
 
+int g_frontend_fast = 1;
+void frontend_set_fast(int on) { g_frontend_fast = on; }
+
 cudaError_t frontend_stats(const int16_t* signal, const int64_t* offsets, int n_reads, int mode, double* center,
-                           double* scale, cudaStream_t stream) {
+                           double* scale, int* todo, cudaStream_t stream) {
   if (n_reads <= 0) return cudaSuccess;
   ensure_stack();
-  stats_kernel<<<n_reads, kStatThreads, 0, stream>>>(signal, offsets, mode, center, scale);
+  if (todo && g_frontend_fast) {
+    static PerDeviceFlag attr_set;
+    bool& set = attr_set.cur();
+    if (!set) {
+      cudaError_t err = cudaFuncSetAttribute(stats_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kHistBins * (int)sizeof(unsigned));
+      if (err != cudaSuccess) return err;
+      set = true;
+    }
+    stats_hist_kernel<<<n_reads, kStatThreads, kHistBins * sizeof(unsigned), stream>>>(signal, offsets, mode, center, scale,
+                                                                                      todo);
+    stats_kernel<<<n_reads, kStatThreads, 0, stream>>>(signal, offsets, mode, center, scale, todo);   // wide-range reads
+    return cudaGetLastError();
+  }
+  stats_kernel<<<n_reads, kStatThreads, 0, stream>>>(signal, offsets, mode, center, scale, nullptr);
   return cudaGetLastError();
 }
 
@@ -326,6 +541,13 @@ cudaError_t frontend_chunks(const int16_t* signal, const int64_t* offsets, const
                             const int32_t* chunk_read, const int64_t* chunk_start, int n_chunks, int chunk_len,
                             float* out, int64_t* out_len, cudaStream_t stream) {
   if (n_chunks <= 0) return cudaSuccess;
+  if (g_frontend_fast && (chunk_len & 7) == 0 && chunk_len <= 8192 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(signal) & 15) == 0) {
+    chunks_vec_kernel<<<n_chunks, 128, (chunk_len + 16) * sizeof(int16_t), stream>>>(signal, offsets, center, scale,
+                                                                                     chunk_read, chunk_start, chunk_len,
+                                                                                     out, out_len);
+    return cudaGetLastError();
+  }
   chunks_kernel<<<n_chunks, 128, 0, stream>>>(signal, offsets, center, scale, chunk_read, chunk_start, chunk_len, out,
                                              out_len);
   return cudaGetLastError();

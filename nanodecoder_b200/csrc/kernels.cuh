@@ -219,8 +219,11 @@ cudaError_t cnn_combine(const float* x, const float* c, const float* o, float s,
                         cudaStream_t stream);
 
 // Front end (utils/labelop.py:219-233): see frontend.cu
+// todo: optional int[n_reads] scratch: with it the histogram kernel runs first and the radix-select kernel only takes the
+// reads whose value range exceeds the histogram (todo[r] != 0)
 cudaError_t frontend_stats(const int16_t* signal, const int64_t* offsets, int n_reads, int mode,
-                           double* center, double* scale, cudaStream_t stream);
+                           double* center, double* scale, int* todo, cudaStream_t stream);
+void frontend_set_fast(int on);     // 1 (default): histogram statistics + vectorised chunk gather; 0: the general kernels
 cudaError_t frontend_chunks(const int16_t* signal, const int64_t* offsets, const double* center,
                             const double* scale, const int32_t* chunk_read, const int64_t* chunk_start,
                             int n_chunks, int chunk_len, float* out, int64_t* out_len, cudaStream_t stream);

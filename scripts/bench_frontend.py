@@ -18,7 +18,9 @@ lens = rng.randint(2000, 200001, size=n_reads).astype(np.int64)
 N = int(lens.sum())
 sig = torch.from_numpy(np.clip(np.round(rng.normal(500, 80, size=N)), 0, 2047).astype(np.int16)).cuda()
 off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).cuda()
-for (L, S) in ((512, 512), (300, 60)):
+for (fast, L, S) in ((1, 512, 512), (1, 300, 60), (1, 304, 64), (0, 512, 512)):
+    eng.set_option("frontend_fast", fast)
+    print("frontend_fast =", fast)
     cr, cs = chunk_table(lens, L, S)
     crd, csd = torch.from_numpy(cr).cuda(), torch.from_numpy(cs).cuda()
     for rep in range(3):

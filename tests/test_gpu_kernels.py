@@ -116,15 +116,25 @@ def test_frontend_bit_exact_vs_oracle_and_reference_golden(small_engine):
     reads = [g["raw_%d" % i] for i in range(int(g["n_reads"]))]
     reads += synth.make_raw_reads(5, seed=3, min_len=3000, max_len=60000)
     reads.append(np.full(40, 7, dtype=np.int16) + np.arange(40, dtype=np.int16) % 3)
+    rng = np.random.default_rng(12)
+    reads.append(rng.integers(-30000, 30000, size=5003).astype(np.int16))     # value range > histogram: radix-select path
+    reads.append(rng.integers(-32768, 32768, size=9).astype(np.int16))
+    reads.append(np.array([5, 5, 5, 9], dtype=np.int16))                       # MAD = 0 -> inf / nan like numpy
     for norm in ("median", "mean"):
-        for (L, S) in ((512, 512), (300, 60)):
+        for (L, S) in ((512, 512), (300, 60), (128, 64)):
             fe = SignalFrontend(small_engine, norm, L, S)
             chunks, lens, cread = fe(reads)
+            small_engine.set_option("frontend_fast", 0)                       # the general kernels: same bits
+            chunks_g, lens_g, _ = fe(reads)
+            small_engine.set_option("frontend_fast", 1)
             torch.cuda.synchronize()
+            assert torch.equal(lens, lens_g)
+            np.testing.assert_array_equal(chunks.cpu().numpy(), chunks_g.cpu().numpy())
             chunks, lens = chunks.cpu().numpy(), lens.cpu().numpy()
             pos = 0
             for ri, raw in enumerate(reads):
-                want = ofe.frontend(raw, norm, L, S)
+                with np.errstate(all="ignore"):
+                    want = ofe.frontend(raw, norm, L, S)
                 for w in want:
                     assert cread[pos] == ri and lens[pos] == len(w)
                     got = chunks[pos, : len(w)]
