@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(kStatThreads) stats_kernel(const int16_t* __re
 
 
 // ---------------------------------------------------------------------------------------------
-// Fast path of the statistics: ONE histogram per read.  Raw DAC samples span a few thousand distinct values, so after
-// a min / max pass (which also pulls the read into L2) the whole read is histogrammed into shared memory (bins
-// x - min, up to kHistBins) with 128-bit loads, and both the median and the MAD come out of that histogram: the MAD's
-// order statistics of |2x - 2*median| are found by walking outwards from the median over the bins.  Two vectorised
-// passes (one from HBM, one from L2) instead of four scalar ones; reads with a wider value range take stats_kernel.
+// Fast path of the statistics: ONE histogram per read.  Raw DAC samples span a few thousand distinct values, so the
+// whole read is histogrammed into shared memory (kHistBins bins) with 128-bit loads in one pass, and both the median
+// and the MAD come out of that histogram: the MAD's order statistics of |2x - 2*median| are found by walking outwards
+// from the median over the bins.  One vectorised pass instead of four scalar ones; reads with a wider value range
+// take stats_kernel.
 constexpr int kHistBins = 16384;
 
 // f(v) for every sample of x[0, n): 8 samples per 128-bit load on the 16-byte aligned body, scalars at both ends
@@ -195,29 +195,46 @@ __global__ void __launch_bounds__(kStatThreads) stats_hist_kernel(const int16_t*
     if (tid == 0) { center[r] = 0.0; scale[r] = 1.0; }
     return;
   }
-  // ---- pass A: value range
-  int lo = 32767, hi = -32768;
-  for_each_sample(x, n, [&](int v) { lo = min(lo, v); hi = max(hi, v); });
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lo = min(lo, __shfl_xor_sync(ND_FULL, lo, o));
-    hi = max(hi, __shfl_xor_sync(ND_FULL, hi, o));
+  // ---- optimistic single pass: a window of kHistBins values centred on the first sample holds every sample of a real
+  // read (a few thousand DAC levels); any sample outside sets the overflow flag and the read is redone with its true
+  // minimum as the origin (or left to the radix-select kernel when its range exceeds the histogram)
+  __shared__ int s_over;
+  int lo = (int)x[0] - kHistBins / 2, hi = lo + kHistBins - 1;
+  if (tid == 0) s_over = 0;
+  for (int i = tid; i < kHistBins; i += kStatThreads) hist_s[i] = 0u;
+  __syncthreads();
+  {
+    bool over = false;
+    for_each_sample(x, n, [&](int v) {
+      const unsigned b = (unsigned)(v - lo);
+      if (b < (unsigned)kHistBins) atomicAdd(&hist_s[b], 1u); else over = true;
+    });
+    if (over) s_over = 1;
   }
-  if ((tid & 31) == 0) { s_red[0][tid >> 5] = lo; s_red[1][tid >> 5] = hi; }
   __syncthreads();
-  lo = s_red[0][0]; hi = s_red[1][0];
+  if (s_over) {
+    lo = 32767; hi = -32768;
+    for_each_sample(x, n, [&](int v) { lo = min(lo, v); hi = max(hi, v); });
 #pragma unroll
-  for (int w = 1; w < kStatThreads / 32; ++w) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); }
-  const int range = hi - lo + 1;
-  if (range > kHistBins) {                            // wide value range: the radix-select kernel takes this read
-    if (tid == 0) todo[r] = 1;
-    return;
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = min(lo, __shfl_xor_sync(ND_FULL, lo, o));
+      hi = max(hi, __shfl_xor_sync(ND_FULL, hi, o));
+    }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = lo; s_red[1][tid >> 5] = hi; }
+    __syncthreads();
+    lo = s_red[0][0]; hi = s_red[1][0];
+#pragma unroll
+    for (int w = 1; w < kStatThreads / 32; ++w) { lo = min(lo, s_red[0][w]); hi = max(hi, s_red[1][w]); }
+    if (hi - lo + 1 > kHistBins) {                    // wide value range: the radix-select kernel takes this read
+      if (tid == 0) todo[r] = 1;
+      return;
+    }
+    for (int i = tid; i < kHistBins; i += kStatThreads) hist_s[i] = 0u;
+    __syncthreads();
+    for_each_sample(x, n, [&](int v) { atomicAdd(&hist_s[v - lo], 1u); });
+    __syncthreads();
   }
-  // ---- pass B: histogram
-  for (int i = tid; i < range; i += kStatThreads) hist_s[i] = 0u;
-  __syncthreads();
-  for_each_sample(x, n, [&](int v) { atomicAdd(&hist_s[v - lo], 1u); });
-  __syncthreads();
+  const int range = min(hi, 32767) - lo + 1 > kHistBins ? kHistBins : (s_over ? hi - lo + 1 : kHistBins);
   // ---- the two middle order statistics: per-thread bin groups, block scan of the group counts, local walk
   const int64_t k1 = (n - 1) / 2, k2 = n / 2;
   const int bpt = (range + kStatThreads - 1) / kStatThreads;
@@ -279,21 +296,28 @@ __global__ void __launch_bounds__(kStatThreads) stats_hist_kernel(const int16_t*
   scale[r] = s;
 }
 
-// Chunk gather, 8 samples per thread: the chunk's samples are staged in shared memory with 128-bit loads of the aligned
-// segments that cover them (reads start at arbitrary sample offsets), normalised in fp64 and stored as two 128-bit
-// vectors.  (x - center) * (1 / scale) replaces the fp64 division (20+ instructions per sample, the kernel's former
+// Chunk gather, one warp per chunk and 8 chunks per CTA: the chunk's samples are staged in shared memory with 128-bit
+// loads of the aligned segments that cover them (reads start at arbitrary sample offsets), normalised in fp64 and stored
+// as 128-bit vectors.  (x - center) * (1 / scale) replaces the fp64 division (20+ instructions per sample, the kernel's former
 // bound) wherever that is provably the same float: the true quotient and its fp64 rounding both lie within 2^-52
 // relative of the product, so if the product's neighbours at +-2^-50 round to the same float, so does the reference's
 // float(float64 quotient); otherwise (about one sample in 10^8) the division is done.
-__global__ void __launch_bounds__(128) chunks_vec_kernel(const int16_t* __restrict__ signal,
-                                                         const int64_t* __restrict__ offsets,
-                                                         const double* __restrict__ center,
-                                                         const double* __restrict__ scale,
-                                                         const int32_t* __restrict__ chunk_read,
-                                                         const int64_t* __restrict__ chunk_start, int chunk_len,
-                                                         float* __restrict__ out, int64_t* __restrict__ out_len) {
-  extern __shared__ __align__(16) int16_t stage[];    // [chunk_len + 16]
-  const int c = blockIdx.x;
+constexpr int kChunkWarps = 8;                       // chunks per CTA: one warp each (a CTA per 1 KB chunk is launch bound)
+
+__global__ void __launch_bounds__(kChunkWarps * 32) chunks_vec_kernel(const int16_t* __restrict__ signal,
+                                                                      const int64_t* __restrict__ offsets,
+                                                                      const double* __restrict__ center,
+                                                                      const double* __restrict__ scale,
+                                                                      const int32_t* __restrict__ chunk_read,
+                                                                      const int64_t* __restrict__ chunk_start,
+                                                                      int n_chunks, int chunk_len,
+                                                                      float* __restrict__ out,
+                                                                      int64_t* __restrict__ out_len) {
+  extern __shared__ __align__(16) int16_t stage_all[]; // [kChunkWarps][chunk_len + 16 rounded up to 8]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kChunkWarps + warp;
+  if (c >= n_chunks) return;
+  int16_t* stage = stage_all + (size_t)warp * ((chunk_len + 23) & ~7);       // 16-byte aligned pitch
   const int r = chunk_read[c];
   const int64_t start = chunk_start[c];
   const int64_t n = offsets[r + 1] - offsets[r];
@@ -301,14 +325,14 @@ __global__ void __launch_bounds__(128) chunks_vec_kernel(const int16_t* __restri
   if (len64 > chunk_len) len64 = chunk_len;
   if (len64 < 0) len64 = 0;
   const int len = (int)len64;
-  if (threadIdx.x == 0) out_len[c] = len;
+  if (lane == 0) out_len[c] = len;
   const int16_t* x = signal + offsets[r] + start;
   const int mis = (int)((reinterpret_cast<uintptr_t>(x) & 15) >> 1);         // samples before x in its 16-byte segment
   const int4* seg = reinterpret_cast<const int4*>(x - mis);
   const int nseg = (mis + len + 7) >> 3;
   // the last segment may reach past the read (and, for the last read, past the buffer): guard it with scalar loads
   const int16_t* buf_end = signal + offsets[r + 1];
-  for (int i = threadIdx.x; i < nseg; i += blockDim.x) {
+  for (int i = lane; i < nseg; i += 32) {
     const int16_t* p = reinterpret_cast<const int16_t*>(seg + i);
     if (p + 8 <= buf_end) {                           // (p >= signal: the buffer base is 16-byte aligned)
       reinterpret_cast<int4*>(stage)[i] = __ldg(seg + i);
@@ -316,14 +340,14 @@ __global__ void __launch_bounds__(128) chunks_vec_kernel(const int16_t* __restri
       for (int k = 0; k < 8; ++k) stage[i * 8 + k] = (p + k < buf_end) ? p[k] : (int16_t)0;
     }
   }
-  __syncthreads();
+  __syncwarp();
   const double ctr = center[r], scl = scale[r];
   const double rcp = 1.0 / scl;
   float* o = out + (int64_t)c * chunk_len;
-  for (int j0 = threadIdx.x * 8; j0 < chunk_len; j0 += blockDim.x * 8) {
-    float v[8];
+  for (int j0 = lane * 4; j0 < chunk_len; j0 += 128) {
+    float v[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const int j = j0 + i;
       float f = 0.f;
       if (j < len) {
@@ -334,12 +358,7 @@ __global__ void __launch_bounds__(128) chunks_vec_kernel(const int16_t* __restri
       }
       v[i] = f;
     }
-    if (j0 + 8 <= chunk_len) {
-      *reinterpret_cast<float4*>(o + j0) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(o + j0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-      for (int i = 0; i < 8 && j0 + i < chunk_len; ++i) o[j0 + i] = v[i];
-    }
+    *reinterpret_cast<float4*>(o + j0) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -541,11 +560,11 @@ cudaError_t frontend_chunks(const int16_t* signal, const int64_t* offsets, const
                             const int32_t* chunk_read, const int64_t* chunk_start, int n_chunks, int chunk_len,
                             float* out, int64_t* out_len, cudaStream_t stream) {
   if (n_chunks <= 0) return cudaSuccess;
-  if (g_frontend_fast && (chunk_len & 7) == 0 && chunk_len <= 8192 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+  if (g_frontend_fast && (chunk_len & 3) == 0 && chunk_len <= 2048 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(signal) & 15) == 0) {
-    chunks_vec_kernel<<<n_chunks, 128, (chunk_len + 16) * sizeof(int16_t), stream>>>(signal, offsets, center, scale,
-                                                                                     chunk_read, chunk_start, chunk_len,
-                                                                                     out, out_len);
+    const size_t smem = (size_t)kChunkWarps * ((chunk_len + 23) & ~7) * sizeof(int16_t);
+    chunks_vec_kernel<<<cdiv(n_chunks, kChunkWarps), kChunkWarps * 32, smem, stream>>>(
+        signal, offsets, center, scale, chunk_read, chunk_start, n_chunks, chunk_len, out, out_len);
     return cudaGetLastError();
   }
   chunks_kernel<<<n_chunks, 128, 0, stream>>>(signal, offsets, center, scale, chunk_read, chunk_start, chunk_len, out,
