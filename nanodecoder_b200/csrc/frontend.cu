@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kStatThreads) stats_hist_kernel(const int16_t*
     for_each_sample(x, n, [&](int v) { atomicAdd(&hist_s[v - lo], 1u); });
     __syncthreads();
   }
-  const int range = hi - lo + 1;                       // <= kHistBins; bins outside the read's values hold 0
+  const int range = min(hi, 32767) - lo + 1 > kHistBins ? kHistBins : (s_over ? hi - lo + 1 : kHistBins);
   // ---- the two middle order statistics: per-thread bin groups, block scan of the group counts, local walk
   const int64_t k1 = (n - 1) / 2, k2 = n / 2;
   const int bpt = (range + kStatThreads - 1) / kStatThreads;
