@@ -57,6 +57,7 @@ typedef enum {
 enum { ND_ENC_NANO = 0, ND_ENC_TRANSFORMER = 1, ND_ENC_CNN = 2, ND_ENC_RNN = 3, ND_ENC_BRNN = 4 };
 enum { ND_DEC_TRANSFORMER = 0, ND_DEC_RNN = 1, ND_DEC_CNN = 2 };
 enum { ND_ATTN_MLP = 0, ND_ATTN_GENERAL = 1, ND_ATTN_DOT = 2 };
+enum { ND_RNN_LSTM = 0, ND_RNN_GRU = 1 };        /* onmt/utils/rnn_factory.py:8-17, onmt/models/stacked_rnn.py */
 /* arithmetic of the dense projections */
 enum {
   ND_GEMM_SIMT_FP32 = 0,   /* fp32 FFMA tiles (bring-up / cross-check path) */
@@ -87,7 +88,8 @@ typedef struct nd_config {
   int32_t max_tgt_len;        /* decode steps (L) */
   int32_t max_beam;           /* largest beam_size that will be requested (>=1) */
   int32_t gemm_mode;          /* ND_GEMM_* */
-  int32_t reserved[8];
+  int32_t rnn_type;           /* ND_RNN_*: cell of the nano / rnn / brnn encoders and of the RNN decoder (took reserved[0]) */
+  int32_t reserved[7];
 } nd_config;
 
 typedef struct nd_engine nd_engine;

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libnanodec.so")
 
 ND_API_VERSION = 1
 ND_OK, ND_ERR_INVALID, ND_ERR_CUDA, ND_ERR_STATE, ND_ERR_WEIGHT, ND_ERR_NOMEM = 0, -1, -2, -3, -4, -5
+RNN = {"LSTM": 0, "GRU": 1}
 ENC = {"nano": 0, "transformer": 1, "cnn": 2, "rnn": 3, "brnn": 4}
 DEC = {"transformer": 0, "rnn": 1, "cnn": 2}
 ATTN = {"mlp": 0, "general": 1, "dot": 2}
@@ -30,7 +31,7 @@ class NdConfig(C.Structure):
         ("cnn_kernel_width", C.c_int32), ("enc_pooling", C.c_int32 * 8), ("input_feed", C.c_int32),
         ("attn_type", C.c_int32), ("position_encoding", C.c_int32), ("max_batch", C.c_int32),
         ("max_src_len", C.c_int32), ("max_tgt_len", C.c_int32), ("max_beam", C.c_int32),
-        ("gemm_mode", C.c_int32), ("reserved", C.c_int32 * 8),
+        ("gemm_mode", C.c_int32), ("rnn_type", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 

@@ -56,8 +56,8 @@ class ModelConfig:
             self.enc_pooling = list(self.enc_pooling) * self.enc_layers
         if len(self.enc_pooling) != self.enc_layers:
             raise ValueError("audio_enc_pooling must have 1 or enc_layers entries")
-        if self.rnn_type != "LSTM":
-            raise ValueError("only rnn_type LSTM is on the supported path (got %r)" % self.rnn_type)
+        if self.rnn_type not in ("LSTM", "GRU"):
+            raise ValueError("rnn_type must be LSTM or GRU (SRU is outside the supported path; got %r)" % self.rnn_type)
         if self.d_model % self.heads:
             raise ValueError("d_model must be divisible by heads")
 

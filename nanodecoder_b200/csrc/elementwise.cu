@@ -103,6 +103,23 @@ __global__ void lstm_cell_kernel(const float* __restrict__ ga, const float* __re
   h_out[i] = og * tanhf(cy);
 }
 
+// nn.GRUCell (onmt/models/stacked_rnn.py:39-65): ga = x W_ih^T + b_ih, gb = h W_hh^T + b_hh, rows of [r | z | n]
+__global__ void gru_cell_kernel(const float* __restrict__ ga, const float* __restrict__ gb,
+                                const float* __restrict__ h_in, float* __restrict__ h_out, int rows, int d) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * d) return;
+  const int64_t r = i / d;
+  const int c = (int)(i - r * d);
+  const float* a = ga + r * 3 * d;
+  const float* b = gb + r * 3 * d;
+  const float rg = sigmoid_acc(a[c] + b[c]);
+  const float zg = sigmoid_acc(a[d + c] + b[d + c]);
+  const float ng = tanhf(a[2 * d + c] + rg * b[2 * d + c]);
+  h_out[i] = ng + zg * (h_in[i] - ng);
+}
+
 __global__ void fill_int_kernel(int* p, int n, int value) {
   pdl_launch_dependents();
   pdl_wait();
@@ -312,6 +329,14 @@ cudaError_t cnn_combine(const float* x, const float* c, const float* o, float s,
                         cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   launch_k(cnn_combine_kernel, dim3((unsigned)cdiv64(n, 256)), dim3(256), 0, stream, x, c, o, s, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t gru_cell_pointwise(const float* gates_a, const float* gates_b, const float* h_in, float* h_out, int rows, int d,
+                               cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  launch_k(gru_cell_kernel, dim3((unsigned)cdiv64((int64_t)rows * d, 256)), dim3(256), 0, stream, gates_a, gates_b, h_in, h_out,
+           rows, d);
   return cudaGetLastError();
 }
 

@@ -393,14 +393,15 @@ int load_ln(nd_engine* e, const std::string& prefix, int d, LnW* out) {
 // one (bi)directional LSTM layer: checkpoint keys <prefix>.weight_ih<sfx>[_reverse] ...
 int load_lstm(nd_engine* e, const std::string& prefix, const std::string& sfx, int in, int H, int dirs, LstmW* out,
               const std::vector<float>* in_alpha = nullptr, const std::vector<float>* in_beta = nullptr) {
+  const int NG = e->cfg.rnn_type == ND_RNN_GRU ? 3 : 4;     // gate rows per hidden unit (nn.GRU: r, z, n)
   std::vector<float> Wih, bih, Whh, bhh;
   for (int dir = 0; dir < dirs; ++dir) {
     const std::string s = sfx + (dir ? "_reverse" : "");
     const HostTensor *wi, *wh, *bi, *bh;
-    ND_TRY(need(e, prefix + ".weight_ih" + s, {4 * H, in}, &wi));
-    ND_TRY(need(e, prefix + ".weight_hh" + s, {4 * H, H}, &wh));
-    ND_TRY(need(e, prefix + ".bias_ih" + s, {4 * H}, &bi));
-    ND_TRY(need(e, prefix + ".bias_hh" + s, {4 * H}, &bh));
+    ND_TRY(need(e, prefix + ".weight_ih" + s, {NG * H, in}, &wi));
+    ND_TRY(need(e, prefix + ".weight_hh" + s, {NG * H, H}, &wh));
+    ND_TRY(need(e, prefix + ".bias_ih" + s, {NG * H}, &bi));
+    ND_TRY(need(e, prefix + ".bias_hh" + s, {NG * H}, &bh));
     Wih.insert(Wih.end(), wi->f.begin(), wi->f.end());
     Whh.insert(Whh.end(), wh->f.begin(), wh->f.end());
     bih.insert(bih.end(), bi->f.begin(), bi->f.end());
@@ -411,14 +412,14 @@ int load_lstm(nd_engine* e, const std::string& prefix, const std::string& sfx, i
     out->w_ih0 = upload(e, Wih);
     out->b_ih0 = upload(e, bih);
   } else {
-    out->ih = in_alpha ? make_lin(e, Wih, dirs * 4 * H, in, &bih, 2, in_alpha, in_beta)
-                       : make_lin(e, Wih, dirs * 4 * H, in, &bih);
+    out->ih = in_alpha ? make_lin(e, Wih, dirs * NG * H, in, &bih, 2, in_alpha, in_beta)
+                       : make_lin(e, Wih, dirs * NG * H, in, &bih);
   }
   out->w_hh = upload(e, Whh);
   out->b_hh = upload(e, bhh);
   float wmax = 0.f;
   for (float v : Whh) wmax = std::max(wmax, fabsf(v));
-  out->tc_ok = wmax < 6.0e4f;
+  out->tc_ok = wmax < 6.0e4f && NG == 4;           // the tensor-core recurrence kernel is the LSTM cell
   return ND_OK;
 }
 // weight-normalised conv (onmt/modules/weight_norm.py:153-165, eval: Polyak buffers):
@@ -600,13 +601,14 @@ int finalize(nd_engine* e) {
       const std::string p = c.input_feed ? "decoder.rnn.layers." + std::to_string(l) + "." : "decoder.rnn.";
       const std::string sfx = c.input_feed ? "" : "_l" + std::to_string(l);
       const int in = l == 0 ? (c.input_feed ? 2 * d : d) : d;
+      const int ng = c.rnn_type == ND_RNN_GRU ? 3 : 4;       // StackedGRU / nn.GRU (stacked_rnn.py:39-65)
       const HostTensor *wi, *wh, *bi, *bh;
-      ND_TRY(need(e, p + "weight_ih" + sfx, {4 * d, in}, &wi));
-      ND_TRY(need(e, p + "weight_hh" + sfx, {4 * d, d}, &wh));
-      ND_TRY(need(e, p + "bias_ih" + sfx, {4 * d}, &bi));
-      ND_TRY(need(e, p + "bias_hh" + sfx, {4 * d}, &bh));
-      e->cells[l].ih = make_lin(e, wi->f, 4 * d, in, &bi->f);
-      e->cells[l].hh = make_lin(e, wh->f, 4 * d, d, &bh->f);
+      ND_TRY(need(e, p + "weight_ih" + sfx, {ng * d, in}, &wi));
+      ND_TRY(need(e, p + "weight_hh" + sfx, {ng * d, d}, &wh));
+      ND_TRY(need(e, p + "bias_ih" + sfx, {ng * d}, &bi));
+      ND_TRY(need(e, p + "bias_hh" + sfx, {ng * d}, &bh));
+      e->cells[l].ih = make_lin(e, wi->f, ng * d, in, &bi->f);
+      e->cells[l].hh = make_lin(e, wh->f, ng * d, d, &bh->f);
       if (l == 0 && c.input_feed) {
         e->cells[l].ih_e = col_slice(e->cells[l].ih, 0, d, true);      // embedding columns (+ b_ih)
         e->cells[l].ih_f = col_slice(e->cells[l].ih, d, d, false);     // input-feed columns
@@ -759,17 +761,21 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
     const LstmW& W = e->lstm[l];
     float* out = outs[l & 1];
     LstmParams p;
-    p.B = B; p.T = T; p.dirs = dirs; p.H = H;
+    p.B = B; p.T = T; p.dirs = dirs; p.H = H; p.cell = c.rnn_type == ND_RNN_GRU ? 1 : 0;
     p.w_hh = W.w_hh; p.b_hh = W.b_hh; p.lengths = lens_dev; p.out = out;
     if (l == 0) {
       p.x0 = e->src; p.w_ih0 = W.w_ih0; p.b_ih0 = W.b_ih0;
     } else {
       GemmOpt o;
       if (nano) { o.prologue = PRO_AFFINE; o.pg = e->lstm[l - 1].bn_alpha; o.pb = e->lstm[l - 1].bn_beta; }
-      ND_TRY(run_gemm(e, W.ih, in, d, e->big, (int64_t)dirs * 4 * H, (int64_t)B * T, o, st));
-      p.xg = e->big; p.xg_ld = (int64_t)dirs * 4 * H;
+      const int64_t ng = p.cell ? 3 : 4;
+      ND_TRY(run_gemm(e, W.ih, in, d, e->big, dirs * ng * H, (int64_t)B * T, o, st));
+      p.xg = e->big; p.xg_ld = dirs * ng * H;
     }
-    if (!nano) { p.h_n = e->enc_hn + (int64_t)l * dirs * B * H; p.c_n = e->enc_cn + (int64_t)l * dirs * B * H; }
+    if (!nano) {
+      p.h_n = e->enc_hn + (int64_t)l * dirs * B * H;
+      p.c_n = p.cell ? nullptr : e->enc_cn + (int64_t)l * dirs * B * H;
+    }
     ND_CUDA(e, cudaMemsetAsync(out, 0, (size_t)B * T * d * sizeof(float), st));
     if (tc_mode(e) && lstm_tc_supported(H) && W.tc_ok) ND_LAUNCH_CAT(e, ND_PROF_LSTM, st, lstm_layer_tc(p, st));
     else ND_LAUNCH_CAT(e, ND_PROF_LSTM, st, lstm_layer(p, e->n_sm, st));
@@ -926,9 +932,10 @@ int decoder_init(nd_engine* e, int K, cudaStream_t st, bool cross_mb = false) {
             ND_CUDA(e, cudaMemcpy2DAsync(e->rh[0][l] + (int64_t)k * d + dir * H, (size_t)K * d * sizeof(float), hs,
                                          (size_t)H * sizeof(float), (size_t)H * sizeof(float), B,
                                          cudaMemcpyDeviceToDevice, st));
-            ND_CUDA(e, cudaMemcpy2DAsync(e->rc[0][l] + (int64_t)k * d + dir * H, (size_t)K * d * sizeof(float), cs,
-                                         (size_t)H * sizeof(float), (size_t)H * sizeof(float), B,
-                                         cudaMemcpyDeviceToDevice, st));
+            if (c.rnn_type != ND_RNN_GRU)
+              ND_CUDA(e, cudaMemcpy2DAsync(e->rc[0][l] + (int64_t)k * d + dir * H, (size_t)K * d * sizeof(float), cs,
+                                           (size_t)H * sizeof(float), (size_t)H * sizeof(float), B,
+                                           cudaMemcpyDeviceToDevice, st));
           }
     }
   } else {
@@ -1022,20 +1029,25 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
       ND_CUDA(e, cudaMemcpyAsync(R(e->feed[cur], d), R(e->feed[nxt], d), (size_t)rows * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     const float* below = nullptr;
+    const bool gru = c.rnn_type == ND_RNN_GRU;
+    const int64_t gw = (gru ? 3 : 4) * (int64_t)d;       // gate row width (buffers are sized for 4d)
     for (int l = 0; l < c.dec_layers; ++l) {
       const nd_engine::RnnCell& Rc = e->cells[l];
       GemmOpt oa;
       if (l == 0 && c.input_feed) {
-        ND_TRY(run_gemm(e, Rc.ih_e, R(e->x, d), d, R(e->ga, 4 * d), 4 * d, rows, oa, st));
-        GemmOpt of; of.residual = R(e->ga, 4 * d); of.ldr = 4 * d;
-        ND_TRY(run_gemm(e, Rc.ih_f, R(e->feed[cur], d), d, R(e->ga, 4 * d), 4 * d, rows, of, st));
+        ND_TRY(run_gemm(e, Rc.ih_e, R(e->x, d), d, R(e->ga, 4 * d), gw, rows, oa, st));
+        GemmOpt of; of.residual = R(e->ga, 4 * d); of.ldr = gw;
+        ND_TRY(run_gemm(e, Rc.ih_f, R(e->feed[cur], d), d, R(e->ga, 4 * d), gw, rows, of, st));
       } else {
-        ND_TRY(run_gemm(e, Rc.ih, l == 0 ? R(e->x, d) : below, d, R(e->ga, 4 * d), 4 * d, rows, oa, st));
+        ND_TRY(run_gemm(e, Rc.ih, l == 0 ? R(e->x, d) : below, d, R(e->ga, 4 * d), gw, rows, oa, st));
       }
       GemmOpt ob;
-      ND_TRY(run_gemm(e, Rc.hh, R(e->rh[cur][l], d), d, R(e->gb, 4 * d), 4 * d, rows, ob, st));
-      ND_LAUNCH(e, lstm_cell_pointwise(R(e->ga, 4 * d), R(e->gb, 4 * d), R(e->rc[cur][l], d), R(e->rh[nxt][l], d),
-                                       R(e->rc[nxt][l], d), rows, d, st));
+      ND_TRY(run_gemm(e, Rc.hh, R(e->rh[cur][l], d), d, R(e->gb, 4 * d), gw, rows, ob, st));
+      if (gru)
+        ND_LAUNCH(e, gru_cell_pointwise(R(e->ga, 4 * d), R(e->gb, 4 * d), R(e->rh[cur][l], d), R(e->rh[nxt][l], d), rows, d, st));
+      else
+        ND_LAUNCH(e, lstm_cell_pointwise(R(e->ga, 4 * d), R(e->gb, 4 * d), R(e->rc[cur][l], d), R(e->rh[nxt][l], d),
+                                         R(e->rc[nxt][l], d), rows, d, st));
       below = R(e->rh[nxt][l], d);
     }
     MlpAttnParams ma;
@@ -1247,6 +1259,7 @@ int nd_create(const nd_config* cfg, nd_engine** out) {
     return fail(nullptr, ND_ERR_INVALID, "d_model must be a multiple of 32 and heads a power of two <= 32");
   if (cfg->vocab_size > 16 || cfg->vocab_size < 5) return fail(nullptr, ND_ERR_INVALID, "vocab_size must be in [5,16]");
   if (cfg->max_beam < 1 || cfg->max_beam > 8) return fail(nullptr, ND_ERR_INVALID, "max_beam must be in [1,8]");
+  if (cfg->rnn_type != ND_RNN_LSTM && cfg->rnn_type != ND_RNN_GRU) return fail(nullptr, ND_ERR_INVALID, "rnn_type must be ND_RNN_LSTM or ND_RNN_GRU");
   if (cfg->max_batch < 1 || cfg->max_src_len < 1 || cfg->max_tgt_len < 1) return fail(nullptr, ND_ERR_INVALID, "bad max sizes");
   int ndev = 0;
   cudaError_t err = cudaGetDeviceCount(&ndev);

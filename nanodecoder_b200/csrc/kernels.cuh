@@ -199,6 +199,9 @@ cudaError_t tanh_inplace(float* x, int64_t n, cudaStream_t stream);
 // LSTMCell pointwise (onmt/models/stacked_rnn.py:25-31): gates [rows,4d] (= x.W_ih^T+b_ih + h.W_hh^T+b_hh)
 cudaError_t lstm_cell_pointwise(const float* gates_a, const float* gates_b, const float* c_in,
                                 float* h_out, float* c_out, int rows, int d, cudaStream_t stream);
+// GRUCell pointwise: gates [rows,3d] as [r | z | n]; h_out = n + z * (h_in - n), n = tanh(a_n + r * b_n)
+cudaError_t gru_cell_pointwise(const float* gates_a, const float* gates_b, const float* h_in, float* h_out, int rows,
+                               int d, cudaStream_t stream);
 // out = (x + a * sigmoid(g)) * sqrt(0.5) with y = [a | g] rows of 2d   (onmt/utils/cnn_factory.py:31-34,52-53)
 cudaError_t glu_residual(const float* y, const float* x, float* out, float* glu_out, int64_t rows, int d,
                          cudaStream_t stream);

@@ -38,7 +38,9 @@ __device__ __forceinline__ void rs_stage(float* v, int kq) {
 }
 
 // KSPL = K slices per hidden unit (4; 8 for H = 256, where a quarter of W_hh's four gate rows would be 256 registers)
-template <int H, int C, int BT, int KSPL = 4>
+// NG = gate rows per hidden unit: 4 = LSTM (i, f, g, o), 3 = GRU (r, z, n; nn.GRU / nn.GRUCell:
+//      r = sig(x_r + h_r), z = sig(x_z + h_z), n = tanh(x_n + r * h_n), h' = n + z * (h - n) with h_* = W_h* h + b_h*)
+template <int H, int C, int BT, int KSPL = 4, int NG = 4>
 __global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
   constexpr int UPC = H / C;          // hidden units owned by this CTA
   constexpr int NT = KSPL * UPC;
@@ -59,19 +61,19 @@ __global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
   const int b0 = tile * BT;
   const int u = tid / KSPL, kq = tid % KSPL;
   const int ucol = rank * UPC + u;                       // hidden unit index in [0, H)
-  const int64_t gbase = (int64_t)dir * 4 * H + ucol;     // + g*H = row of gate g in the [dirs*4H] dimension
+  const int64_t gbase = (int64_t)dir * NG * H + ucol;    // + g*H = row of gate g in the [dirs*NG*H] dimension
 
-  float w[4][KQ];
+  float w[NG][KQ];
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
+  for (int g = 0; g < NG; ++g)
 #pragma unroll
     for (int k = 0; k < KQ; k += 4) {
       const float4 v = *reinterpret_cast<const float4*>(p.w_hh + (gbase + g * H) * H + kq * KQ + k);
       w[g][k] = v.x; w[g][k + 1] = v.y; w[g][k + 2] = v.z; w[g][k + 3] = v.w;
     }
-  float bhh[4], wi0[4], bi0[4];
+  float bhh[NG], wi0[NG], bi0[NG];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < NG; ++g) {
     bhh[g] = p.b_hh[gbase + g * H];
     wi0[g] = p.x0 ? p.w_ih0[gbase + g * H] : 0.f;
     bi0[g] = p.x0 ? p.b_ih0[gbase + g * H] : 0.f;
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
   for (int s = 0; s < maxlen; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
     // ---- input-side gate terms of the chunks this lane finishes (latency hides behind the FMAs)
-    float xin[4][PPT];
+    float xin[NG][PPT];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       const int b = kq * PPT + j;
@@ -107,17 +109,17 @@ __global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
       if (p.x0) {
         const float xv = p.x0[(int64_t)bb * p.T + t];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) xin[g][j] = xv * wi0[g] + bi0[g];
+        for (int g = 0; g < NG; ++g) xin[g][j] = xv * wi0[g] + bi0[g];
       } else {
         const float* xr = p.xg + ((int64_t)bb * p.T + t) * p.xg_ld + gbase;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) xin[g][j] = xr[g * H];
+        for (int g = 0; g < NG; ++g) xin[g][j] = xr[g * H];
       }
     }
     // ---- partial recurrent products over this thread's K-quarter, all BT chunks
-    float acc[4][BT];
+    float acc[NG][BT];
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
+    for (int g = 0; g < NG; ++g)
 #pragma unroll
       for (int b = 0; b < BT; ++b) acc[g][b] = 0.f;
 #pragma unroll
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
       for (int b = 0; b < BT; ++b) {
         const float4 hv = *reinterpret_cast<const float4*>(&h_buf[cur][b][kq * KS + k]);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < NG; ++g) {
           acc[g][b] = fmaf(w[g][k], hv.x, acc[g][b]);
           acc[g][b] = fmaf(w[g][k + 1], hv.y, acc[g][b]);
           acc[g][b] = fmaf(w[g][k + 2], hv.z, acc[g][b]);
@@ -136,9 +138,9 @@ __global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
     }
     // ---- reduce-scatter over the KSPL K slices: lane kq ends up with chunks [kq*PPT, (kq+1)*PPT).  Every stage
     // halves the chunk range a lane keeps (upper half when its kq bit is set) and adds the partner's partial sums.
-    float fin[4][PPT];
+    float fin[NG][PPT];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
       if constexpr (KSPL == 8) rs_stage<4 * PPT, 4>(acc[g], kq);
       rs_stage<2 * PPT, 2>(acc[g], kq);
       rs_stage<PPT, 1>(acc[g], kq);
@@ -151,12 +153,19 @@ __global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
       const int b = kq * PPT + j;
       const int len = s_len[b];
       if (s < len) {
-        const float ig = sigmoid_acc(xin[0][j] + (fin[0][j] + bhh[0]));
-        const float fg = sigmoid_acc(xin[1][j] + (fin[1][j] + bhh[1]));
-        const float gg = tanhf(xin[2][j] + (fin[2][j] + bhh[2]));
-        const float og = sigmoid_acc(xin[3][j] + (fin[3][j] + bhh[3]));
-        c_state[j] = fg * c_state[j] + ig * gg;
-        h_state[j] = og * tanhf(c_state[j]);
+        if constexpr (NG == 4) {
+          const float ig = sigmoid_acc(xin[0][j] + (fin[0][j] + bhh[0]));
+          const float fg = sigmoid_acc(xin[1][j] + (fin[1][j] + bhh[1]));
+          const float gg = tanhf(xin[2][j] + (fin[2][j] + bhh[2]));
+          const float og = sigmoid_acc(xin[3][j] + (fin[3][j] + bhh[3]));
+          c_state[j] = fg * c_state[j] + ig * gg;
+          h_state[j] = og * tanhf(c_state[j]);
+        } else {
+          const float rg = sigmoid_acc(xin[0][j] + (fin[0][j] + bhh[0]));
+          const float zg = sigmoid_acc(xin[1][j] + (fin[1][j] + bhh[1]));
+          const float ng = tanhf(xin[2][j] + rg * (fin[2][j] + bhh[2]));
+          h_state[j] = ng + zg * (h_state[j] - ng);
+        }
         const int t = dir == 0 ? s : len - 1 - s;
         p.out[((int64_t)(b0 + b) * p.T + t) * out_ld + dir * H + ucol] = h_state[j];
       }
@@ -179,14 +188,14 @@ __global__ void __launch_bounds__(KSPL * (H / C), 1) lstm_kernel(LstmParams p) {
       if (b0 + b < p.B) {
         const int64_t o = ((int64_t)dir * p.B + b0 + b) * H + ucol;
         p.h_n[o] = h_state[j];
-        p.c_n[o] = c_state[j];
+        if (p.c_n) p.c_n[o] = c_state[j];
       }
     }
   }
   if constexpr (C > 1) cg::this_cluster().sync();     // no CTA may exit while peers still write its smem
 }
 
-template <int H, int C, int BT, int KSPL = 4>
+template <int H, int C, int BT, int KSPL = 4, int NG = 4>
 cudaError_t launch(const LstmParams& p, cudaStream_t stream) {
   const int tiles = cdiv(p.B, BT);
   cudaLaunchConfig_t cfg = {};
@@ -201,10 +210,10 @@ cudaError_t launch(const LstmParams& p, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, lstm_kernel<H, C, BT, KSPL>, p);
+  return cudaLaunchKernelEx(&cfg, lstm_kernel<H, C, BT, KSPL, NG>, p);
 }
 
-template <int H, int C>
+template <int H, int C, int NG = 4>
 cudaError_t pick_bt(const LstmParams& p, int n_sm, cudaStream_t stream) {
   // cost model: waves x per-step cycles (FMA issue ~ 2.5*H*BT per SMSP pair, ~700 cycles of sync)
   int best = 4;
@@ -218,10 +227,10 @@ cudaError_t pick_bt(const LstmParams& p, int n_sm, cudaStream_t stream) {
     if (cost < best_cost) { best_cost = cost; best = bt; }
   }
   switch (best) {
-    case 4: return launch<H, C, 4>(p, stream);
-    case 8: return launch<H, C, 8>(p, stream);
-    case 12: return launch<H, C, 12>(p, stream);
-    default: return launch<H, C, 16>(p, stream);
+    case 4: return launch<H, C, 4, 4, NG>(p, stream);
+    case 8: return launch<H, C, 8, 4, NG>(p, stream);
+    case 12: return launch<H, C, 12, 4, NG>(p, stream);
+    default: return launch<H, C, 16, 4, NG>(p, stream);
   }
 }
 
@@ -233,6 +242,7 @@ cudaError_t launch_h256(const LstmParams& p, int n_sm, cudaStream_t stream) {
   const int64_t c8 = (int64_t)cdiv(p.B, 8) * p.dirs * 8, c16 = (int64_t)cdiv(p.B, 16) * p.dirs * 8;
   const double cost8 = (double)cdiv64(c8, n_sm) * (2.5 * 256 * 8 + 700.0);
   const double cost16 = (double)cdiv64(c16, n_sm) * (2.5 * 256 * 16 + 700.0);
+  if (p.cell == 1) return cost8 <= cost16 ? launch<256, 8, 8, 8, 3>(p, stream) : launch<256, 8, 16, 8, 3>(p, stream);
   return cost8 <= cost16 ? launch<256, 8, 8, 8>(p, stream) : launch<256, 8, 16, 8>(p, stream);
 }
 
@@ -240,6 +250,16 @@ bool lstm_supported(int H) { return H == 16 || H == 32 || H == 64 || H == 128 ||
 
 cudaError_t lstm_layer(const LstmParams& p, int n_sm, cudaStream_t stream) {
   if (p.B <= 0) return cudaSuccess;
+  if (p.cell == 1) {                                   // GRU
+    switch (p.H) {
+      case 16: return pick_bt<16, 1, 3>(p, n_sm, stream);
+      case 32: return pick_bt<32, 1, 3>(p, n_sm, stream);
+      case 64: return pick_bt<64, 1, 3>(p, n_sm, stream);
+      case 128: return pick_bt<128, 2, 3>(p, n_sm, stream);
+      case 256: return launch_h256(p, n_sm, stream);
+      default: return cudaErrorNotSupported;
+    }
+  }
   switch (p.H) {
     case 16: return pick_bt<16, 1>(p, n_sm, stream);
     case 32: return pick_bt<32, 1>(p, n_sm, stream);

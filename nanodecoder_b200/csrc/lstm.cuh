@@ -18,6 +18,7 @@ struct LstmParams {
   float* h_n = nullptr;           // optional [dirs, B, H]
   float* c_n = nullptr;
   int B = 0, T = 0, dirs = 2, H = 0;
+  int cell = 0;                   // 0 LSTM (4 gate rows per unit: xg / w_* are [dirs*4H]), 1 GRU (3 gate rows, no c_n)
   long long* dbg = nullptr;       // optional [32] clock64() stamps of step 100 of CTA 0 (tuning aid)
 };
 

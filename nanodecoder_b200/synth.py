@@ -52,11 +52,12 @@ class _Builder:
         if bias:
             self.bias(prefix + ".bias", out_f)
 
-    def lstm(self, prefix, suffix, in_f, hidden, gain_ih=1.0):
-        self.matrix("%s.weight_ih%s" % (prefix, suffix), 4 * hidden, in_f, gain_ih)
-        self.matrix("%s.weight_hh%s" % (prefix, suffix), 4 * hidden, hidden, 1.0)
-        self.bias("%s.bias_ih%s" % (prefix, suffix), 4 * hidden)
-        self.bias("%s.bias_hh%s" % (prefix, suffix), 4 * hidden)
+    def lstm(self, prefix, suffix, in_f, hidden, gain_ih=1.0, gates=4):
+        """nn.LSTM (gates 4) / nn.GRU (gates 3) parameters of one direction of one layer"""
+        self.matrix("%s.weight_ih%s" % (prefix, suffix), gates * hidden, in_f, gain_ih)
+        self.matrix("%s.weight_hh%s" % (prefix, suffix), gates * hidden, hidden, 1.0)
+        self.bias("%s.bias_ih%s" % (prefix, suffix), gates * hidden)
+        self.bias("%s.bias_hh%s" % (prefix, suffix), gates * hidden)
 
     def mha(self, prefix, d, qk_gain=1.0, out_gain=1.0):
         self.linear(prefix + ".linear_keys", d, d, gain=qk_gain)
@@ -134,6 +135,7 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
     G.update(gains or {})
     d, V = cfg.d_model, cfg.vocab_size
     h = d // 2
+    ng = 3 if cfg.rnn_type == "GRU" else 4       # gate rows per hidden unit
 
     # ---------------- encoder
     if cfg.encoder_type == "nano":              # encoder/nano_encoder.py:26-77
@@ -141,7 +143,7 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
         for l in range(cfg.enc_layers):
             in_f = 1 if l == 0 else d
             for sfx in ("_l0", "_l0_reverse"):
-                b.lstm("encoder.rnn_%d" % l, sfx, in_f, h, gain_ih=1.0)
+                b.lstm("encoder.rnn_%d" % l, sfx, in_f, h, gain_ih=1.0, gates=ng)
             p = "encoder.batchnorm_%d" % l
             b.affine(p, d)
             b.normal(p + ".running_mean", (d,), 0.05)
@@ -153,9 +155,9 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
         hh = d // dirs
         for l in range(cfg.enc_layers):
             in_f = 1 if l == 0 else d
-            b.lstm("encoder.rnn", "_l%d" % l, in_f, hh)
+            b.lstm("encoder.rnn", "_l%d" % l, in_f, hh, gates=ng)
             if dirs == 2:
-                b.lstm("encoder.rnn", "_l%d_reverse" % l, in_f, hh)
+                b.lstm("encoder.rnn", "_l%d_reverse" % l, in_f, hh, gates=ng)
     elif cfg.encoder_type == "transformer":     # encoder/transformer.py:87-104
         b.linear("encoder.linear", d, 1)
         for l in range(cfg.enc_layers):
@@ -188,10 +190,10 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
             # InputFeedRNNDecoder: StackedLSTM of LSTMCells (stacked_rnn.py:15-20); StdRNNDecoder (-input_feed 0):
             # one multi-layer nn.LSTM (decoder.py:264-266 via rnn_factory) -- same arithmetic, other parameter names
             names = rnn_decoder_keys(l, cfg.input_feed)
-            b.matrix(names[0], 4 * d, in_f)
-            b.matrix(names[1], 4 * d, d)
-            b.bias(names[2], 4 * d)
-            b.bias(names[3], 4 * d)
+            b.matrix(names[0], ng * d, in_f)
+            b.matrix(names[1], ng * d, d)
+            b.bias(names[2], ng * d)
+            b.bias(names[3], ng * d)
         # onmt/modules/global_attention.py:71-93
         if cfg.global_attention == "mlp":
             b.linear("decoder.attn.linear_context", d, d, bias=False)

@@ -65,6 +65,11 @@ CASES = {
     # unidirectional rnn encoder (encoder/rnn_encoder.py:64-84): hidden size = d (256: the 8-slice recurrence kernel)
     "rnn2rnn_d256": ("rnn2rnn", dict()),
     "rnn2rnn_d64": ("rnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2)),
+    # -rnn_type GRU (onmt/utils/rnn_factory.py:8-17: nn.GRU encoders; onmt/models/stacked_rnn.py:39-65: StackedGRU decoder)
+    "nano2rnn_gru_d64": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, rnn_type="GRU")),
+    "brnn2rnn_gru_d256": ("brnn2rnn", dict(rnn_type="GRU")),
+    "l2t_gru_d64": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2, rnn_type="GRU")),
+    "rnn2rnn_gru_std_d64": ("rnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, rnn_type="GRU", input_feed=0)),
 }
 
 
@@ -75,6 +80,8 @@ def ref_extra(cfg):
         extra.append("-position_encoding")
     if cfg.decoder_type == "rnn":
         extra += ["-input_feed", str(int(cfg.input_feed))]
+    if cfg.rnn_type != "LSTM":
+        extra += ["-rnn_type", cfg.rnn_type]
     return extra
 
 

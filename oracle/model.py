@@ -26,11 +26,11 @@ def _ln(sd, prefix, x):
 
 
 # ======================================================================================= LSTM
-def _make_lstm(sd, prefix, in_f, hidden, layers, bidirectional):
-    """torch.nn.LSTM carrying the checkpoint weights: the same third-party op the reference calls
-    (onmt/utils/rnn_factory.py:16)."""
-    m = torch.nn.LSTM(input_size=in_f, hidden_size=hidden, num_layers=layers,
-                      bidirectional=bidirectional)
+def _make_lstm(sd, prefix, in_f, hidden, layers, bidirectional, rnn_type="LSTM"):
+    """torch.nn.LSTM / torch.nn.GRU carrying the checkpoint weights: the same third-party op the reference calls
+    (onmt/utils/rnn_factory.py:8-17: getattr(nn, rnn_type))."""
+    m = getattr(torch.nn, rnn_type)(input_size=in_f, hidden_size=hidden, num_layers=layers,
+                                    bidirectional=bidirectional)
     own = m.state_dict()
     m.load_state_dict({k: sd[prefix + "." + k] for k in own})
     return m.eval()
@@ -70,7 +70,7 @@ def nano_encoder(sd, cfg, src, lengths):
     memory_bank = None
     for l in range(cfg.enc_layers):
         stride = cfg.enc_pooling[l]
-        rnn = _make_lstm(sd, "encoder.rnn_%d" % l, 1 if l == 0 else d, hdim, 1, True)
+        rnn = _make_lstm(sd, "encoder.rnn_%d" % l, 1 if l == 0 else d, hdim, 1, True, cfg.rnn_type)
         packed = pack_padded_sequence(src, lens, enforce_sorted=False)   # :97
         memory_bank = pad_packed_sequence(rnn(packed)[0])[0]         # :98-99  [t,B,2h]
         memory_bank = memory_bank.transpose(0, 2)                   # :101
@@ -86,7 +86,7 @@ def nano_encoder(sd, cfg, src, lengths):
     mb = F.linear(memory_bank.contiguous().view(-1, memory_bank.size(2)), sd["encoder.W.weight"])
     mb = mb.view(-1, B, d)
     state = mb.new_zeros(cfg.dec_layers * 2, B, hdim)               # :117-121
-    return (state, state), mb, lengths.new_tensor(lens)
+    return ((state, state) if cfg.rnn_type == "LSTM" else state), mb, lengths.new_tensor(lens)
 
 
 def multi_head_attention(sd, prefix, key, value, query, heads, mask=None, cache=None, kind=None):
@@ -182,7 +182,7 @@ def rnn_encoder(sd, cfg, src, lengths):
     """encoder/rnn_encoder.py:64-84 (no bridge).  -> ((h_n,c_n) [Le*dirs,B,hh], memory_bank, lengths)"""
     bi = cfg.encoder_type == "brnn"
     hh = cfg.d_model // (2 if bi else 1)
-    rnn = _make_lstm(sd, "encoder.rnn", 1, hh, cfg.enc_layers, bi)
+    rnn = _make_lstm(sd, "encoder.rnn", 1, hh, cfg.enc_layers, bi, cfg.rnn_type)
     packed = pack_padded_sequence(src, lengths.view(-1).tolist(), enforce_sorted=False)
     mb, final = rnn(packed)
     return final, pad_packed_sequence(mb)[0], lengths
@@ -287,7 +287,8 @@ class InputFeedRNNDecoder(object):
             if self.cfg.brnn:
                 hid = torch.cat([hid[0:hid.size(0):2], hid[1:hid.size(0):2]], 2)
             return hid
-        hidden = tuple(fix(e) for e in enc_final)
+        # LSTM: (h, c); GRU: the final hidden alone, wrapped in a 1-tuple (decoder.py:118-122)
+        hidden = tuple(fix(e) for e in enc_final) if isinstance(enc_final, tuple) else (fix(enc_final),)
         B = hidden[0].size(1)
         self.state = {"hidden": hidden,
                       "input_feed": hidden[0].new_zeros(1, B, self.cfg.d_model)}
@@ -303,9 +304,11 @@ class InputFeedRNNDecoder(object):
             emb_t = emb_t * math.sqrt(cfg.d_model) + _positional_encoding(
                 cfg.d_model, 0, emb_t, sd.get("decoder.embeddings.make_embedding.pe.pe")).view(1, -1)
         x = torch.cat([emb_t, self.state["input_feed"].squeeze(0)], 1) if cfg.input_feed else emb_t
-        h0, c0 = self.state["hidden"]
+        gru = cfg.rnn_type == "GRU"
+        h0 = self.state["hidden"][0]
+        c0 = None if gru else self.state["hidden"][1]
         h1, c1 = [], []
-        for l in range(cfg.dec_layers):                             # stacked_rnn.py:25-31
+        for l in range(cfg.dec_layers):                             # stacked_rnn.py:25-31 (LSTM), :56-65 (GRU)
             # InputFeedRNNDecoder: StackedLSTM of LSTMCells; StdRNNDecoder (decoder.py:203-262, -input_feed 0): one
             # multi-layer nn.LSTM fed one token -- the same cell arithmetic under nn.LSTM's parameter names
             if cfg.input_feed:
@@ -313,6 +316,17 @@ class InputFeedRNNDecoder(object):
                 wi, wh, bi, bh = p + ".weight_ih", p + ".weight_hh", p + ".bias_ih", p + ".bias_hh"
             else:
                 wi, wh, bi, bh = ("decoder.rnn.%s_l%d" % (n, l) for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+            if gru:                                                 # nn.GRUCell: gates r, z, n
+                gi, gh = F.linear(x, sd[wi], sd[bi]), F.linear(h0[l], sd[wh], sd[bh])
+                i_r, i_z, i_n = gi.chunk(3, 1)
+                h_r, h_z, h_n = gh.chunk(3, 1)
+                r = torch.sigmoid(i_r + h_r)
+                z = torch.sigmoid(i_z + h_z)
+                n = torch.tanh(i_n + r * h_n)
+                h = n + z * (h0[l] - n)
+                h1.append(h)
+                x = h
+                continue
             g = F.linear(x, sd[wi], sd[bi]) + F.linear(h0[l], sd[wh], sd[bh])
             i, f, gg, o = g.chunk(4, 1)
             c = torch.sigmoid(f) * c0[l] + torch.sigmoid(i) * torch.tanh(gg)
@@ -322,7 +336,7 @@ class InputFeedRNNDecoder(object):
             x = h
         out, align = global_attention_mlp(sd, "decoder.attn", x, memory_bank.transpose(0, 1),
                                           memory_lengths, cfg.global_attention)   # :336-339
-        self.state["hidden"] = (torch.stack(h1), torch.stack(c1))
+        self.state["hidden"] = (torch.stack(h1),) if gru else (torch.stack(h1), torch.stack(c1))
         self.state["input_feed"] = out.unsqueeze(0)                 # :347, :171
         return out.unsqueeze(0), align.unsqueeze(0)
 

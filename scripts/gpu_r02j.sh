@@ -6,6 +6,9 @@ cap() {  # name, regex, skip, count, env-prefixed command...
   local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -o $O/r02j_$name -f "$@" > $O/ncu_j_$name.log 2>&1
   echo "ncu $name exit $?"
+  # only the metric tables travel back (gpurun_out is capped at 64 MiB): raw page as CSV, then drop the report
+  ncu -i $O/r02j_$name.ncu-rep --page raw --csv > $O/r02j_$name.raw.csv 2>/dev/null; gzip -f $O/r02j_$name.raw.csv
+  rm -f $O/r02j_$name.ncu-rep
 }
 ND_KW="$C5" python scripts/profile_step.py t2t 1 > $O/r02j_plain.log 2>&1; echo "plain exit $?"
 ND_KW="$C5" cap self_attn_d512 self_attn_kernel 1210 2 python scripts/profile_step.py t2t 1

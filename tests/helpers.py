@@ -12,7 +12,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["l2t_d256", "t2t_d256", "nano2rnn_d256", "brnn2rnn_d256", "cnn2cnn_d256", "l2t_d64", "t2t_d64",
                 "t2t_d512_6x6", "nano2rnn_general_d64", "brnn2rnn_dot_d64", "t2t_pe_d64", "nano2rnn_pe_d64",
                 "cnn2cnn_pe_d64", "brnn2rnn_std_d256", "brnn2rnn_std_general_d64",
-               "rnn2rnn_d256", "rnn2rnn_d64"]
+               "rnn2rnn_d256", "rnn2rnn_d64", "nano2rnn_gru_d64", "brnn2rnn_gru_d256", "l2t_gru_d64",
+               "rnn2rnn_gru_std_d64"]
 
 
 def load_golden(name):

@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 IMPLEMENTED = ["l2t_d256", "t2t_d256", "nano2rnn_d256", "brnn2rnn_d256", "cnn2cnn_d256", "l2t_d64", "t2t_d64",
                "t2t_d512_6x6", "nano2rnn_general_d64", "brnn2rnn_dot_d64", "t2t_pe_d64", "nano2rnn_pe_d64",
                "cnn2cnn_pe_d64", "brnn2rnn_std_d256", "brnn2rnn_std_general_d64",
-               "rnn2rnn_d256", "rnn2rnn_d64"]
+               "rnn2rnn_d256", "rnn2rnn_d64", "nano2rnn_gru_d64", "brnn2rnn_gru_d256", "l2t_gru_d64",
+               "rnn2rnn_gru_std_d64"]
 TOL = 1e-3
 
 
@@ -61,7 +62,8 @@ def test_greedy_matches_reference_golden(name, mode):
 @pytest.mark.parametrize("name", ["l2t_d256", "t2t_d64", "nano2rnn_d256", "brnn2rnn_d256", "l2t_d64", "t2t_d256",
                                   "cnn2cnn_d256", "nano2rnn_general_d64", "brnn2rnn_dot_d64", "t2t_pe_d64",
                                   "nano2rnn_pe_d64", "cnn2cnn_pe_d64", "brnn2rnn_std_d256",
-                                  "brnn2rnn_std_general_d64", "rnn2rnn_d256", "rnn2rnn_d64"])
+                                  "brnn2rnn_std_general_d64", "rnn2rnn_d256", "rnn2rnn_d64", "nano2rnn_gru_d64", "brnn2rnn_gru_d256", "l2t_gru_d64",
+               "rnn2rnn_gru_std_d64"])
 def test_beam_matches_reference_golden(name):
     g, cfg, sd, src, lengths = load_golden(name)
     B, T, L, K = src.shape[0], src.shape[1], int(g["max_length"]), int(g["beam_size"])

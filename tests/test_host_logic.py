@@ -56,7 +56,8 @@ def test_unsupported_configs_fail_loudly():
     with pytest.raises(ValueError):
         ModelConfig(encoder_type="resnet")
     with pytest.raises(ValueError):
-        ModelConfig(rnn_type="GRU")
+        ModelConfig(rnn_type="SRU")
+    assert ModelConfig(rnn_type="GRU").rnn_type == "GRU"
     opt = ModelConfig.family("l2t").to_opt()
     opt.copy_attn = True
     with pytest.raises(ValueError):
