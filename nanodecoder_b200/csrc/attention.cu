@@ -775,18 +775,21 @@ namespace {
 
 // Cache layout: [slot][head][pos][dh] so that one head's keys / values of consecutive positions are
 // contiguous: dh/4 lanes cover one position with 128-bit loads, 32/(dh/4) positions per warp access.
-// U = independent 128-bit loads in flight per lane (the kernel is latency bound)
-template <int U>
+// U = independent 128-bit loads in flight per lane (the kernel is latency bound); DH = head size: with run-time lanes per
+// position the shuffle reductions were loops and 2/3 of the executed instructions were address and control work
+// (ncu source page, profiles/r02l_*: IMAD / BRA / LEA / ISETP 48 %, FFMA 6 %)
+template <int U, int DH>
 __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   extern __shared__ __align__(16) float smem_f[];
   const int row = p.row0 + blockIdx.x;
   pdl_launch_dependents();
   pdl_wait();
   if (p.retired && p.retired[row / p.rows_per_chunk]) return;
-  const int d = p.d, H = p.H, dh = d / H, L = p.step + 1;
+  constexpr int dh = DH;
+  const int d = p.d, H = p.H, L = p.step + 1;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int LPP = dh >> 2;                         // lanes per position (dh = 8/16/32/64 -> 2/4/8/16)
-  const int PPI = 32 / LPP;                        // positions per warp iteration
+  constexpr int LPP = DH >> 2;                     // lanes per position (dh = 8/16/32/64 -> 2/4/8/16)
+  constexpr int PPI = 32 / LPP;                    // positions per warp iteration
   const int sub = lane % LPP, grp = lane / LPP;
   float* q_s = smem_f;                             // [d]
   float* p_s = smem_f + d;                         // [nwarps][Lmax]
@@ -804,6 +807,7 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
   for (int h = warp; h < H; h += nwarps) {
     float* ps = p_s + warp * p.Lmax;
     const float4 qq = *reinterpret_cast<const float4*>(q_s + h * dh + sub * 4);
+    const int64_t own = (((int64_t)row * H + h) * p.Lmax) * dh + sub * 4;       // this row's own cache slot (greedy)
     // ---- scores: U independent 128-bit loads in flight per lane (the kernel is latency bound)
     float m = -FLT_MAX;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -814,16 +818,17 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
         const int j = j0 + u * PPI + grp;
         kk[u] = zero4;
         if (j < L) {
-          const float* kr = (j == p.step)
-                                ? qkv + d + h * dh
-                                : p.Kc + (((int64_t)(anc ? anc[j] : row) * H + h) * p.Lmax + j) * dh;
-          kk[u] = *reinterpret_cast<const float4*>(kr + sub * 4);
+          const float* kr = (j == p.step) ? qkv + d + h * dh + sub * 4
+                            : anc     ? p.Kc + (((int64_t)anc[j] * H + h) * p.Lmax + j) * dh + sub * 4
+                                      : p.Kc + own + j * dh;
+          kk[u] = *reinterpret_cast<const float4*>(kr);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int j = j0 + u * PPI + grp;
         float sc = fmaf(qq.x, kk[u].x, fmaf(qq.y, kk[u].y, fmaf(qq.z, kk[u].z, qq.w * kk[u].w)));
+#pragma unroll
         for (int o = LPP >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(ND_FULL, sc, o);
         if (j < L) {
           if (sub == 0) ps[j] = sc;
@@ -849,10 +854,10 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
         vv[u] = zero4;
         pj[u] = 0.f;
         if (j < L) {
-          const float* vr = (j == p.step)
-                                ? qkv + 2 * d + h * dh
-                                : p.Vc + (((int64_t)(anc ? anc[j] : row) * H + h) * p.Lmax + j) * dh;
-          vv[u] = *reinterpret_cast<const float4*>(vr + sub * 4);
+          const float* vr = (j == p.step) ? qkv + 2 * d + h * dh + sub * 4
+                            : anc     ? p.Vc + (((int64_t)anc[j] * H + h) * p.Lmax + j) * dh + sub * 4
+                                      : p.Vc + own + j * dh;
+          vv[u] = *reinterpret_cast<const float4*>(vr);
           pj[u] = ps[j];
         }
       }
@@ -862,6 +867,7 @@ __global__ void __launch_bounds__(256) self_attn_kernel(SelfAttnParams p) {
         acc.z = fmaf(pj[u], vv[u].z, acc.z); acc.w = fmaf(pj[u], vv[u].w, acc.w);
       }
     }
+#pragma unroll
     for (int o = LPP; o < 32; o <<= 1) {
       acc.x += __shfl_xor_sync(ND_FULL, acc.x, o); acc.y += __shfl_xor_sync(ND_FULL, acc.y, o);
       acc.z += __shfl_xor_sync(ND_FULL, acc.z, o); acc.w += __shfl_xor_sync(ND_FULL, acc.w, o);
@@ -880,7 +886,12 @@ cudaError_t self_attention_step(const SelfAttnParams& p, cudaStream_t stream) {
   const int nw = p.H < 8 ? p.H : 8;
   const size_t smem = ((size_t)p.d + (size_t)nw * p.Lmax) * sizeof(float);
   // U = 8 at head size 64 measured slower (64.7 vs 56.1 us per launch at d = 512, B = 1024, call r02f): 4 everywhere
-  launch_k(self_attn_kernel<4>, dim3(p.rows), dim3(nw * 32), smem, stream, p);
+  switch (dh) {
+    case 8: launch_k(self_attn_kernel<4, 8>, dim3(p.rows), dim3(nw * 32), smem, stream, p); break;
+    case 16: launch_k(self_attn_kernel<4, 16>, dim3(p.rows), dim3(nw * 32), smem, stream, p); break;
+    case 32: launch_k(self_attn_kernel<4, 32>, dim3(p.rows), dim3(nw * 32), smem, stream, p); break;
+    default: launch_k(self_attn_kernel<4, 64>, dim3(p.rows), dim3(nw * 32), smem, stream, p); break;
+  }
   return cudaGetLastError();
 }
 
