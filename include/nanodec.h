@@ -229,7 +229,9 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *                    sequences and identity rates to fp32 storage, profiles/r02_identity_rates.md);
  *                    4 = 15-bit fixed point (2 bytes per element; the reduced-precision mode, never the default);
  *                    5 = the top 24 bits of the fp32 value; 1 / 2 = 24 / 16-bit fixed point decoded with conversion
- *                    instructions (cross-checks).  Beam search always reads fp32 rows.
+ *                    instructions (cross-checks);
+ *   "kv_beam_packed" (default 1): beam search reads the fixed-point planes as well (d = 256 / 512, up to 5 beams at
+ *                    T = 512); 0 = fp32 rows through the TMA-ring kernel.
  * Any nd_set_int call drops the engine's captured CUDA graphs (they are re-captured on the following calls).  */
 ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);
 

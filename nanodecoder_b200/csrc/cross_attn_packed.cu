@@ -508,6 +508,214 @@ cudaError_t launch_fast(const CrossAttnParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+
+// =============================================================================================
+// Several queries per chunk (beam search: the K beams of a chunk share its keys / values).  Same slice layout as
+// fast_body; the queries stay in shared memory (NQ x 8 registers per lane plus 48 row registers would spill at two CTAs
+// per SM), each row is decoded ONCE and used by all NQ queries, scores and probabilities are [NQ][heads][T].
+template <int VPL, int LPH, int FMT, int NQT>
+__device__ __forceinline__ void fast_body_mq(const CrossAttnParams& p, const int chunk, const int part) {
+  constexpr int DS = 32 * VPL, HP = 32 / LPH, RB = 64 / VPL;
+  extern __shared__ __align__(16) float smem_f[];
+  if (p.retired && p.retired[chunk]) return;
+  const int T = p.T, d = p.d, NQ = p.NQ;
+  const int Tup = (T + RB - 1) & ~(RB - 1);
+  const int TS = Tup + LPH;
+  const int sc_f = NQ * HP * TS, red_f = kWarps * NQ * DS;
+  float* sc = smem_f;                            // [NQ][HP][TS]   (later red[warps][NQ][DS])
+  float* kstep = sc + (sc_f > red_f ? sc_f : red_f);
+  float* vstep = kstep + Tup;
+  float* q_s = vstep + Tup;                      // [NQ][DS]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = lane / LPH, j = lane % LPH;
+  const int64_t row0 = (int64_t)chunk * T;
+
+  for (int i = threadIdx.x; i < NQ * DS; i += kThreads) {
+    const int qi = i / DS, c = i - qi * DS;
+    q_s[i] = p.q[((int64_t)chunk * NQ + qi) * p.q_ld + part * DS + c] / p.q_div;
+  }
+  {
+    const float* stp = p.kv_scale + row0 * 2;
+    const float* srow = p.src ? p.src + (int64_t)chunk * p.src_ld : nullptr;
+    for (int t = threadIdx.x; t < Tup; t += kThreads) {
+      float ks = 1.0f, vs = 1.0f;
+      if (t < T) {
+        if (fmt_scaled(FMT)) { ks = stp[2 * t]; vs = stp[2 * t + 1]; }
+        if (srow && srow[t] == p.mask_value) ks = -ks;
+      }
+      kstep[t] = ks;
+      vstep[t] = vs;
+    }
+  }
+  __syncthreads();
+
+  const uint32_t hi_pitch = 4u * d, lo_pitch = 2u * d;
+  const uint8_t* hiK = reinterpret_cast<const uint8_t*>(p.kv_hi) + row0 * hi_pitch + part * (2 * DS) + lane * (2 * VPL);
+  const uint8_t* loK = reinterpret_cast<const uint8_t*>(p.kv_lo) + row0 * lo_pitch + part * DS + lane * VPL;
+  const int nit = Tup / RB;
+
+  // ---------------- phase 1: scores
+  for (int it = warp; it < nit; it += kWarps) {
+    const int t0 = it * RB;
+    RowRegs<VPL, FMT> rr[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (t0 + r < T) {
+        rr[r].load(hiK + (uint32_t)(t0 + r) * hi_pitch, loK + (uint32_t)(t0 + r) * lo_pitch);
+      } else {
+#pragma unroll
+        for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[r].hi[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[r].lo[i] = 0u;
+      }
+    }
+#pragma unroll
+    for (int b0 = 0; b0 < RB; b0 += LPH) {
+      float v[NQT][LPH];
+#pragma unroll
+      for (int r = 0; r < LPH; ++r) {
+        float kf[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) kf[i] = rr[b0 + r].get(i);
+#pragma unroll
+        for (int qi = 0; qi < NQT; ++qi) {
+          float s = 0.f;
+          if (qi < NQ) {
+            const float4 qa = *reinterpret_cast<const float4*>(q_s + qi * DS + lane * VPL);
+            const float4 qb = *reinterpret_cast<const float4*>(q_s + qi * DS + lane * VPL + 4);
+            s = fmaf(qa.x, kf[0], fmaf(qa.y, kf[1], fmaf(qa.z, kf[2], fmaf(qa.w, kf[3],
+                fmaf(qb.x, kf[4], fmaf(qb.y, kf[5], fmaf(qb.z, kf[6], qb.w * kf[7])))))));
+          }
+          v[qi][r] = s;
+        }
+      }
+      const int t = t0 + b0 + j;
+      const float ks = kstep[t];
+#pragma unroll
+      for (int qi = 0; qi < NQT; ++qi) {
+        if (qi < NQ) {                             // warp-uniform
+          if constexpr (LPH >= 8) rs_stage<4, 4>(v[qi], lane);
+          rs_stage<2, 2>(v[qi], lane);
+          rs_stage<1, 1>(v[qi], lane);
+          sc[(qi * HP + head) * TS + t] = ks < 0.f ? -1e18f : v[qi][0] * ks;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: softmax rows; afterwards probability * value step, zero beyond T
+  for (int row = warp; row < NQ * HP; row += kWarps) {
+    float* s = sc + row * TS;
+    float m = -FLT_MAX;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, s[t]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) { const float e = expf(s[t] - m); s[t] = e; sum += e; }
+    sum = warp_sum(sum);
+    float* a = (p.attn && part == 0 && (row % HP) == 0) ? p.attn + ((int64_t)chunk * NQ + row / HP) * T : nullptr;
+    for (int t = lane; t < Tup; t += 32) {
+      float pr = 0.f;
+      if (t < T) {
+        pr = s[t] / sum;
+        if (a) a[t] = pr;
+        pr *= vstep[t];
+      }
+      s[t] = pr;
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3: context
+  float acc[NQT][VPL];
+#pragma unroll
+  for (int qi = 0; qi < NQT; ++qi)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[qi][i] = 0.f;
+  const uint8_t* hiV = hiK + 2 * d;
+  const uint8_t* loV = loK + d;
+  for (int it = warp; it < nit; it += kWarps) {
+    const int t0 = it * RB;
+    RowRegs<VPL, FMT> rr[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (t0 + r < T) {
+        rr[r].load(hiV + (uint32_t)(t0 + r) * hi_pitch, loV + (uint32_t)(t0 + r) * lo_pitch);
+      } else {
+#pragma unroll
+        for (int i = 0; i < RowRegs<VPL, FMT>::NHI; ++i) rr[r].hi[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < (fmt_has_lo(FMT) ? RowRegs<VPL, FMT>::NLO : 1); ++i) rr[r].lo[i] = 0u;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float vf[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) vf[i] = rr[r].get(i);
+#pragma unroll
+      for (int qi = 0; qi < NQT; ++qi) {
+        if (qi < NQ) {
+          const float pr = sc[(qi * HP + head) * TS + t0 + r];
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) acc[qi][i] = fmaf(pr, vf[i], acc[qi][i]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* red = sc;                                 // [warps][NQ][DS]
+#pragma unroll
+  for (int qi = 0; qi < NQT; ++qi)
+    if (qi < NQ) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) red[(warp * NQ + qi) * DS + lane * VPL + i] = acc[qi][i];
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * DS; i += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w * NQ * DS + i];
+    const int qi = i / DS, c = i - qi * DS;
+    p.ctx[((int64_t)chunk * NQ + qi) * p.ctx_ld + part * DS + c] = s;
+  }
+}
+
+template <int LPH, int FMT, int NQT>
+__global__ void __launch_bounds__(kThreads, 2) cross_attn_packed_mq_kernel(CrossAttnParams p, int split) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int chunk = blockIdx.x / split;
+  fast_body_mq<8, LPH, FMT, NQT>(p, chunk, blockIdx.x - chunk * split);
+}
+
+template <int LPH, int FMT, int NQT>
+cudaError_t launch_mq(const CrossAttnParams& p, cudaStream_t stream) {
+  constexpr int DS = 256, RB = 8, HP = 32 / LPH;
+  const int split = p.d / DS;
+  const int Tup = (p.T + RB - 1) & ~(RB - 1);
+  const size_t sc_f = (size_t)p.NQ * HP * (Tup + LPH), red_f = (size_t)kWarps * p.NQ * DS;
+  const size_t smem = ((sc_f > red_f ? sc_f : red_f) + 2 * (size_t)Tup + (size_t)p.NQ * DS) * sizeof(float);
+  if (smem > 110 * 1024) return cudaErrorInvalidValue;         // two CTAs per SM
+  static PerDeviceFlag attr_set;
+  bool& set = attr_set.cur();
+  if (!set) {
+    cudaError_t err = cudaFuncSetAttribute(cross_attn_packed_mq_kernel<LPH, FMT, NQT>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    if (err != cudaSuccess) return err;
+    set = true;
+  }
+  launch_k_heavy(cross_attn_packed_mq_kernel<LPH, FMT, NQT>, dim3(p.n_chunks * split), dim3(kThreads), smem, stream, p, split);
+  return cudaGetLastError();
+}
+
+template <int LPH>
+cudaError_t launch_mq_any(const CrossAttnParams& p, cudaStream_t stream) {
+  if (p.kv_fmt == KV_Q23M) return p.NQ <= 5 ? launch_mq<LPH, KV_Q23M, 5>(p, stream) : launch_mq<LPH, KV_Q23M, 8>(p, stream);
+  if (p.kv_fmt == KV_Q15M) return p.NQ <= 5 ? launch_mq<LPH, KV_Q15M, 5>(p, stream) : launch_mq<LPH, KV_Q15M, 8>(p, stream);
+  return cudaErrorInvalidValue;
+}
+
 // one query per chunk, 8 heads, d = 256 or 512, planes 32-byte aligned
 bool fast_supported(const CrossAttnParams& p) {
   return p.NQ == 1 && p.H == 8 && (p.d == 256 || p.d == 512) && p.kv_fmt >= KV_Q23M && p.kv_fmt <= KV_FP24 &&
@@ -671,6 +879,25 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
 
 void cross_attention_packed_set_fast(int on) { g_packed_fast = on; }
 
+bool cross_attention_packed_beams_ok(int NQ, int d, int H, int T, int fmt) {
+  if (!(NQ > 1 && NQ <= 8 && H == 8 && (d == 256 || d == 512) && (fmt == KV_Q23M || fmt == KV_Q15M) && g_packed_fast)) return false;
+  const int LPH = d == 256 ? 4 : 8, HP = 32 / LPH, Tup = (T + 7) & ~7;
+  const size_t sc_f = (size_t)NQ * HP * (Tup + LPH), red_f = (size_t)kWarps * NQ * 256;
+  return ((sc_f > red_f ? sc_f : red_f) + 2 * (size_t)Tup + (size_t)NQ * 256) * sizeof(float) <= 110 * 1024 &&
+         (int64_t)T * 4 * d < (int64_t)1 << 31;
+}
+
+// several queries per chunk over fixed-point planes: the slice kernel with the queries in shared memory
+bool cross_attention_packed_mq_supported(const CrossAttnParams& p) {
+  if (!(p.NQ > 1 && p.NQ <= 8 && p.H == 8 && (p.d == 256 || p.d == 512) && (p.kv_fmt == KV_Q23M || p.kv_fmt == KV_Q15M) &&
+        (reinterpret_cast<uintptr_t>(p.kv_hi) & 31) == 0 && (reinterpret_cast<uintptr_t>(p.kv_lo) & 15) == 0 &&
+        (int64_t)p.T * 4 * p.d < (int64_t)1 << 31))
+    return false;
+  const int LPH = p.d == 256 ? 4 : 8, HP = 32 / LPH, Tup = (p.T + 7) & ~7;
+  const size_t sc_f = (size_t)p.NQ * HP * (Tup + LPH), red_f = (size_t)kWarps * p.NQ * 256;
+  return ((sc_f > red_f ? sc_f : red_f) + 2 * (size_t)Tup + (size_t)p.NQ * 256) * sizeof(float) <= 110 * 1024;
+}
+
 bool kv_pack_supported(int d) { return d == 64 || d == 128 || d == 256 || d == 512; }
 
 cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
@@ -693,6 +920,7 @@ cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream
       !p.kv_scale || (fmt_has_lo(p.kv_fmt) && !p.kv_lo))
     return cudaErrorInvalidValue;
   if (g_packed_fast && fast_supported(p)) return launch_fast_any(p, stream);
+  if (g_packed_fast && cross_attention_packed_mq_supported(p)) return p.d == 256 ? launch_mq_any<4>(p, stream) : launch_mq_any<8>(p, stream);
   switch (p.d / 32) {
     case 2: return launch_packed<2>(p, stream);
     case 4: return launch_packed<4>(p, stream);

@@ -138,6 +138,7 @@ struct nd_engine {
   // error <= 2^-23 of the row part's largest element; same greedy sequences and identity rates as fp32 storage),
   // KV_F32, KV_Q15M (reduced precision, half the bytes), others = cross-checks
   int kv_mode = KV_Q23M;
+  int kv_beam_packed = 1;                  // beam search reads the fixed-point planes too where the kernel exists
   bool kv_packed = false;                  // set by decoder_init: this decode reads the packed planes
   int enc_attn_tc = 1;                     // Transformer-encoder self attention on the tensor cores when dh = 32
   int* cur_tok = nullptr;
@@ -896,7 +897,10 @@ int decoder_init(nd_engine* e, int K, cudaStream_t st, bool cross_mb = false) {
     // Packed planes: greedy decode only (the beam kernels of cross_attn_ring.cu read fp32 rows); the GEMM writes the
     // fp32 projection into the encoder's scratch (free once the memory bank exists), the packer re-writes it as
     // [int16 plane | uint8 plane | steps] into the layer's K/V buffer (3/4 or 1/2 of it).
-    e->kv_packed = !cross_mb && e->kv_mode != KV_F32 && K == 1 && kv_pack_supported(d);
+    // (beam search: only where the multi-query slice kernel exists -- d = 256 / 512, the beams' score rows fit two CTAs
+    // per SM -- and the option kv_beam_packed is on; otherwise fp32 rows through the ring kernel)
+    e->kv_packed = !cross_mb && e->kv_mode != KV_F32 && kv_pack_supported(d) &&
+                   (K == 1 || (e->kv_beam_packed && cross_attention_packed_beams_ok(K, d, c.heads, Tp, e->kv_mode)));
     for (int l = 0; l < c.dec_layers && !cross_mb; ++l) {
       GemmOpt o;
       if (!e->kv_packed) {
@@ -1503,7 +1507,7 @@ static int decode_beam_any(nd_engine* e, int32_t beam_size, int32_t n_best, int3
   int32_t alpha_bits;
   memcpy(&alpha_bits, &alpha, sizeof(alpha_bits));
   const std::vector<int64_t> key = {1 + mode * 4 + lp_mode, B, e->T, e->Tp, max_len, min_len, K, n_best, alpha_bits,
-                                    n_groups(e, B), g_pdl};
+                                    n_groups(e, B), g_pdl, e->kv_mode, e->kv_beam_packed};
   ND_TRY(run_cached(e, key, st, [&](cudaStream_t s2) {
     return beam_body(e, K, n_best, max_len, min_len, alpha, mode, lp_mode, e->o_ids, e->o_lens, e->o_scores, s2);
   }));
@@ -1557,6 +1561,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
   if (strcmp(name, "kv_mode") == 0) {        // storage of the memory keys / values: 0 fp32, 1 q24, 2 q16 (kernels.cuh)
     if (value < 0 || value > KV_FP24) return fail(e, ND_ERR_INVALID, "kv_mode must be in [0, 5] (nanodec.h)");
     e->kv_mode = (int)value;
+    return ND_OK;
+  }
+  if (strcmp(name, "kv_beam_packed") == 0) {
+    e->kv_beam_packed = value != 0;
     return ND_OK;
   }
   if (strcmp(name, "cross_packed_fast") == 0) {   // process-wide

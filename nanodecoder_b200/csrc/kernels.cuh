@@ -47,6 +47,8 @@ bool kv_pack_supported(int d);
 cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
                     cudaStream_t stream);
 cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream);   // kv_fmt != 0 (cross_attn_packed.cu)
+bool cross_attention_packed_beams_ok(int NQ, int d, int H, int T, int fmt);   // host-side form of the check below
+bool cross_attention_packed_mq_supported(const CrossAttnParams& p);   // several queries per chunk (beam search) at d = 256 / 512
 void cross_attention_packed_set_fast(int on);   // 1 (default): 256-column-slice kernel for one query per chunk; 0: generic
 // several queries per chunk (beam search) at d = 256, H = 8: 2 (default) persistent CTAs fed by a cp.async.bulk ring
 // (cross_attn_ring.cu), 1 register-prefetch kernel, 0 generic kernel
