@@ -15,6 +15,7 @@
 #include <float.h>
 
 #include "kernels.cuh"
+#include "kv_fixed.cuh"
 
 namespace nd {
 
@@ -42,42 +43,6 @@ __device__ __forceinline__ void load_bytes(const uint8_t* p, uint32_t* r) {
     uint16_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
     r[0] = v;
-  }
-}
-
-__device__ __forceinline__ int prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  int d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-  return d;
-}
-
-// element j of a lane's slice as a float holding the (unscaled) integer.  hi: int16 pairs, lo: uint8 quads.
-// prmt selector nibbles: 0-3 = bytes of a (hi pair register), 4-7 = bytes of b (lo quad register), +8 = replicate
-// the sign bit of the selected byte.
-// Integer -> float without a conversion instruction: for |m| < 2^22 the bit pattern 0x4B400000 + m is the float
-// 1.5 * 2^23 + m exactly (one IADD on the integer pipe), and subtracting 1.5 * 2^23 is exact (one FADD).
-__device__ __forceinline__ float magic_i2f(int m) { return __int_as_float(m + 0x4B400000) - 12582912.0f; }
-
-__host__ __device__ constexpr bool fmt_has_lo(int fmt) { return fmt == KV_Q24 || fmt == KV_Q23M || fmt == KV_FP24; }
-__host__ __device__ constexpr bool fmt_scaled(int fmt) { return fmt != KV_FP24; }
-
-template <int FMT>
-__device__ __forceinline__ float unpack_elem(const uint32_t* hi, const uint32_t* lo, int j) {
-  const uint32_t k = 2u * (j & 1);                                 // byte index of the int16 inside its register
-  if constexpr (FMT == KV_FP24) {
-    // the top 24 bits of an fp32: [hi_b1 | hi_b0 | lo | (byte 0 cleared)]
-    const uint32_t sel = (4u + (j & 3)) | ((4u + (j & 3)) << 4) | (k << 8) | ((k + 1) << 12);
-    return __uint_as_float((uint32_t)prmt(hi[j >> 1], lo[j >> 2], sel) & 0xffffff00u);
-  } else if constexpr (fmt_has_lo(FMT)) {
-    const uint32_t sel = (4u + (j & 3)) | (k << 4) | ((k + 1) << 8) | (((k + 1) | 8u) << 12);
-    const int m = prmt(hi[j >> 1], lo[j >> 2], sel);
-    if constexpr (FMT == KV_Q24) return __int2float_rn(m);
-    return magic_i2f(m);
-  } else {
-    const uint32_t sel = k | ((k + 1) << 4) | (((k + 1) | 8u) << 8) | (((k + 1) | 8u) << 12);
-    const int m = prmt(hi[j >> 1], 0u, sel);
-    if constexpr (FMT == KV_Q16) return __int2float_rn(m);
-    return magic_i2f(m);
   }
 }
 
@@ -881,6 +846,9 @@ void cross_attention_packed_set_fast(int on) { g_packed_fast = on; }
 
 bool cross_attention_packed_beams_ok(int NQ, int d, int H, int T, int fmt) {
   if (!(NQ > 1 && NQ <= 8 && H == 8 && (d == 256 || d == 512) && (fmt == KV_Q23M || fmt == KV_Q15M) && g_packed_fast)) return false;
+  // d = 256: only through the shared-memory-ring kernel (the slice kernel below is arithmetic-bound there and loses to
+  // the ring over fp32 rows: 369 vs 215 us on C3); d = 512: the slice kernel (no ring kernel at that width)
+  if (d == 256) return g_cross_beam_kernel == 2 && cross_attention_ring_shape_ok(NQ, d, H, T, fmt);
   const int LPH = d == 256 ? 4 : 8, HP = 32 / LPH, Tup = (T + 7) & ~7;
   const size_t sc_f = (size_t)NQ * HP * (Tup + LPH), red_f = (size_t)kWarps * NQ * 256;
   return ((sc_f > red_f ? sc_f : red_f) + 2 * (size_t)Tup + (size_t)NQ * 256) * sizeof(float) <= 110 * 1024 &&
@@ -920,6 +888,7 @@ cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream
       !p.kv_scale || (fmt_has_lo(p.kv_fmt) && !p.kv_lo))
     return cudaErrorInvalidValue;
   if (g_packed_fast && fast_supported(p)) return launch_fast_any(p, stream);
+  if (g_packed_fast && g_cross_beam_kernel == 2 && cross_attention_ring_supported(p)) return cross_attention_ring(p, stream);
   if (g_packed_fast && cross_attention_packed_mq_supported(p)) return p.d == 256 ? launch_mq_any<4>(p, stream) : launch_mq_any<8>(p, stream);
   switch (p.d / 32) {
     case 2: return launch_packed<2>(p, stream);

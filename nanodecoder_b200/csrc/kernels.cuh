@@ -54,6 +54,8 @@ void cross_attention_packed_set_fast(int on);   // 1 (default): 256-column-slice
 // (cross_attn_ring.cu), 1 register-prefetch kernel, 0 generic kernel
 void cross_attention_set_beam_kernel(int mode);
 bool cross_attention_ring_supported(const CrossAttnParams& p);
+bool cross_attention_ring_shape_ok(int NQ, int d, int H, int T, int fmt);   // fmt: KV_F32 / KV_Q23M / KV_Q15M
+extern int g_cross_beam_kernel;
 cudaError_t cross_attention_ring(const CrossAttnParams& p, cudaStream_t stream);
 void cross_attention_ring_set_groups(int g);    // consumer warp groups of the ring kernel (2 default, 1 for > 5 queries)
 
