@@ -54,6 +54,9 @@ WORKLOADS = {
                               "mlp_attn", "C4"),
     "brnn2rnn_greedy_b1024": ("brnn2rnn", {}, 1, "brnn enc3 -> InputFeed LSTM dec3, mlp attention, d=256", "mlp_attn", "C4"),
     "cnn2cnn_greedy_b1024": ("cnn2cnn", {}, 1, "Conv2Conv 3+3, kernel width 3, d=256", "mlp_attn", "C4"),
+    # not a BASELINE.json config: the other encoder the authors' pipeline-train.sh trains (resnet -> transformer)
+    "resnet2t_greedy_b1024": ("resnet2t", {}, 1, "ResNet stem (17 width-3 convs, 64-512 channels) -> Transformer dec3, d=256",
+                              "cross_attn", "pipeline-train.sh resnet2transformer"),
 }
 KV_MODES = {"f32": 0, "q23": 3, "q15": 4}           # nd_set_int("kv_mode"), include/nanodec.h
 KV_BYTES = {"f32": 4, "q23": 3, "q15": 2}
@@ -78,12 +81,17 @@ class Workload(object):
         cfg = ModelConfig.family(self.family, **self.kw)
         return cfg, synth.make_state_dict(cfg, seed=2025)
 
+    def kv_packed(self, kv):
+        """The engine's rule (engine.cu decoder_init): Transformer decoders keep the memory keys / values in fixed point
+        for greedy decode and, at d = 256 / 512 with 8 heads, for beam search too (kv_beam_packed, default on)."""
+        return self.roof_cat == "cross_attn" and kv != "f32"
+
     def config(self, n_gpus, kv):
         return {"workload": self.name, "baseline_config": self.baseline_cfg, "model": self.desc,
                 "decode": "greedy" if self.beam == 1 else "--fast beam %d" % self.beam,
                 "chunks_per_step_per_gpu": B_PER_GPU, "chunk_len": T, "max_length": L, "min_length": self.min_length,
                 "global_chunks_per_step": B_PER_GPU * n_gpus, "parallelism": "read-sharded x%d" % n_gpus,
-                "memory_kv_storage": kv if (self.beam == 1 and self.roof_cat == "cross_attn") else "f32",
+                "memory_kv_storage": kv if self.kv_packed(kv) else "f32",
                 "l2_policy": "working set (GBs of attention keys / values per step) >> 126 MB L2; no flush needed"}
 
 
@@ -295,7 +303,7 @@ def roofline_entry(wl, cfg, kv, prof, prof_ms, n_prof_steps):
     peak, peak_src = peak_hbm()
     ms_cat, n_cat = prof.get(wl.roof_cat, (0.0, 0))
     d, B, K = cfg.d_model, B_PER_GPU, wl.beam
-    packed = wl.roof_cat == "cross_attn" and K == 1 and kv != "f32"
+    packed = wl.kv_packed(kv)
     bpe = KV_BYTES[kv] if packed else 4
     # K and V (or uh and H, or keys and values of the conv attention) of every chunk once + (packed) the two steps per
     # memory position + query in and context out per row; the beams of a chunk share the K/V pass
@@ -303,6 +311,10 @@ def roofline_entry(wl, cfg, kv, prof, prof_ms, n_prof_steps):
     achieved = bytes_per_launch / (ms_cat / max(n_cat, 1) * 1e-3) / 1e9 if n_cat else None
     if wl.roof_cat == "mlp_attn":
         kname = "mlp_attn_kernel<%d,1> (decode global / conv attention, fp32)" % (d // 32)
+    elif packed and K > 1:
+        kname = ("cross_attn_ring_kernel<%d,%d,%s>" % ((4, 2, kv) if K <= 4 else (5, 2, kv) if K == 5 else (8, 1, kv))
+                 if d == 256 else "cross_attn_packed_mq_kernel<%s>" % kv) + \
+                " (decode cross-attention, the beams of a chunk share one pass over its fixed-point K/V planes)"
     elif packed:
         kname = "cross_attn_packed_fast_kernel<%s> (decode cross-attention, fixed-point K/V, %d CTAs per chunk)" % (kv, 2)
     elif K == 1:

@@ -54,7 +54,9 @@ typedef enum {
   ND_ERR_NOMEM = -5
 } nd_status;
 
-enum { ND_ENC_NANO = 0, ND_ENC_TRANSFORMER = 1, ND_ENC_CNN = 2, ND_ENC_RNN = 3, ND_ENC_BRNN = 4 };
+enum { ND_ENC_NANO = 0, ND_ENC_TRANSFORMER = 1, ND_ENC_CNN = 2, ND_ENC_RNN = 3, ND_ENC_BRNN = 4,
+       /* ResNet stem (encoder/resnet_encoder.py) alone, before the nano stack, before transformer layers */
+       ND_ENC_RESNET = 5, ND_ENC_CRNN = 6, ND_ENC_CTRANSFORMER = 7 };
 enum { ND_DEC_TRANSFORMER = 0, ND_DEC_RNN = 1, ND_DEC_CNN = 2 };
 enum { ND_ATTN_MLP = 0, ND_ATTN_GENERAL = 1, ND_ATTN_DOT = 2 };
 enum { ND_RNN_LSTM = 0, ND_RNN_GRU = 1 };        /* onmt/utils/rnn_factory.py:8-17, onmt/models/stacked_rnn.py */

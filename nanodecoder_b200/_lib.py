@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libnanodec.so")
 ND_API_VERSION = 1
 ND_OK, ND_ERR_INVALID, ND_ERR_CUDA, ND_ERR_STATE, ND_ERR_WEIGHT, ND_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 RNN = {"LSTM": 0, "GRU": 1}
-ENC = {"nano": 0, "transformer": 1, "cnn": 2, "rnn": 3, "brnn": 4}
+ENC = {"nano": 0, "transformer": 1, "cnn": 2, "rnn": 3, "brnn": 4, "resnet": 5, "crnn": 6, "ctransformer": 7}
 DEC = {"transformer": 0, "rnn": 1, "cnn": 2}
 ATTN = {"mlp": 0, "general": 1, "dot": 2}
 GEMM = {"simt": 0, "3xtf32": 1, "tf32": 2}

@@ -15,7 +15,7 @@ from typing import List
 SPECIALS = ["<unk>", "<blank>", "<s>", "</s>"]
 UNK, PAD, BOS, EOS = 0, 1, 2, 3
 
-ENCODER_TYPES = ("nano", "transformer", "cnn", "rnn", "brnn")
+ENCODER_TYPES = ("nano", "transformer", "cnn", "rnn", "brnn", "resnet", "crnn", "ctransformer")
 DECODER_TYPES = ("transformer", "rnn", "cnn")
 
 # named model families of BASELINE.json / SURVEY.md Appendix A
@@ -26,6 +26,13 @@ FAMILIES = {
     "brnn2rnn": dict(encoder_type="brnn", decoder_type="rnn"),
     "rnn2rnn": dict(encoder_type="rnn", decoder_type="rnn"),         # unidirectional encoder (encoder/rnn_encoder.py)
     "cnn2cnn": dict(encoder_type="cnn", decoder_type="cnn"),
+    # ResNet stem (encoder/resnet_encoder.py) alone, in front of the nano stack, in front of transformer layers;
+    # the authors' pipeline-train.sh trains resnet -> transformer and resnet -> rnn
+    "resnet2t": dict(encoder_type="resnet", decoder_type="transformer"),
+    "resnet2rnn": dict(encoder_type="resnet", decoder_type="rnn"),
+    "crnn2t": dict(encoder_type="crnn", decoder_type="transformer"),
+    "crnn2rnn": dict(encoder_type="crnn", decoder_type="rnn"),
+    "ctrans2t": dict(encoder_type="ctransformer", decoder_type="transformer"),
 }
 
 
@@ -60,6 +67,10 @@ class ModelConfig:
             raise ValueError("rnn_type must be LSTM or GRU (SRU is outside the supported path; got %r)" % self.rnn_type)
         if self.d_model % self.heads:
             raise ValueError("d_model must be divisible by heads")
+        if self.encoder_type in ("resnet", "ctransformer") and self.decoder_type == "cnn":
+            # model_builder.py:133-140 builds ResNetEncoder for the cnn decoder, whose outputs are laid out [d,B,T]
+            # with a [1,1,B,T] "embedding" (resnet_encoder.py:195-199): not a configuration anyone can decode with
+            raise ValueError("%s encoder with the cnn decoder is outside the supported translate path" % self.encoder_type)
 
     @property
     def vocab_size(self) -> int:
@@ -68,7 +79,7 @@ class ModelConfig:
     @property
     def brnn(self) -> bool:
         # models/model_builder.py:190-191: nano/crnn encoders force a bidirectional bridge
-        return self.encoder_type in ("brnn", "nano")
+        return self.encoder_type in ("brnn", "nano", "crnn")
 
     @classmethod
     def family(cls, name: str, **kw) -> "ModelConfig":

@@ -154,6 +154,32 @@ __global__ void glu_residual_kernel(const float* __restrict__ y, const float* __
   if (out) out[i] = (x[i] + glu) * 0.70710678118654757f;   // SCALE_WEIGHT = 0.5 ** 0.5 rounded to fp32
 }
 
+// first conv of the ResNet stem: 1 -> 64 channels, 3 taps, folded BatchNorm, ReLU
+__global__ void resnet_stem_kernel(const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ b,
+                                   float* __restrict__ out, int B, int T) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t pos = i >> 4;
+  if (pos >= (int64_t)B * T) return;
+  const int c0 = (int)(i & 15) * 4;
+  const int t = (int)(pos % T);
+  const float xm = t > 0 ? src[pos - 1] : 0.f, x0 = src[pos], xp = t + 1 < T ? src[pos + 1] : 0.f;
+  float4 o;
+  float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* wc = w + (c0 + j) * 3;
+    // conv2d accumulates the three taps in order; the folded bias is added last
+    const float acc = fmaf(wc[2], xp, fmaf(wc[1], x0, wc[0] * xm)) + b[c0 + j];
+    op[j] = fmaxf(acc, 0.f);
+  }
+  *reinterpret_cast<float4*>(out + pos * 64 + c0) = o;
+}
+
+__global__ void take_column_kernel(const float* __restrict__ x, int ld, int col, float* __restrict__ out, int64_t rows) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) out[r] = x[r * ld + col];
+}
+
 __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ A, int B, int T, int d, int k,
                               int left) {
   const int64_t r = blockIdx.x;                    // (b, t)
@@ -452,6 +478,19 @@ cudaError_t glu_residual(const float* y, const float* x, float* out, float* glu_
                          cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   launch_k(glu_residual_kernel, dim3((unsigned)cdiv64(rows * d, 256)), dim3(256), 0, stream, y, x, out, glu_out, rows, d);
+  return cudaGetLastError();
+}
+
+cudaError_t resnet_stem_conv(const float* src, const float* w, const float* b, float* out, int B, int T, cudaStream_t stream) {
+  const int64_t n = (int64_t)B * T * 16;            // one thread per (position, 4 channels)
+  if (n <= 0) return cudaSuccess;
+  resnet_stem_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(src, w, b, out, B, T);
+  return cudaGetLastError();
+}
+
+cudaError_t take_column(const float* x, int ld, int col, float* out, int64_t rows, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  take_column_kernel<<<(unsigned)cdiv(rows, 256), 256, 0, stream>>>(x, ld, col, out, rows);
   return cudaGetLastError();
 }
 

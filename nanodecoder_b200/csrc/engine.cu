@@ -46,6 +46,21 @@ struct Lin {
 
 struct LnW { const float* g = nullptr; const float* b = nullptr; };
 
+// ResNet stem of the resnet / crnn / ctransformer encoders (encoder/resnet_encoder.py:82-170): every layer is a
+// width-3 convolution along time, packed as a [Cout, 3*Cin] GEMM weight over im2col rows (column j*Cin + c), with the
+// eval BatchNorm that follows folded in (w * alpha, b * alpha + beta)
+struct ResBlockW {
+  Lin conv1, conv2, down;        // down: the 1x1 projection of the residual (first block of layers 2-4)
+  bool has_down = false;
+  int cin = 0, cout = 0;
+};
+struct ResNetW {
+  const float* stem_w = nullptr; // [64][3] (BatchNorm folded)
+  const float* stem_b = nullptr; // [64]
+  std::vector<ResBlockW> blocks;
+  Lin fc;                        // [d, 512]
+};
+
 struct EncLayerT {             // transformer encoder layer
   Lin qkv, out, w1, w2;
   LnW ln, ln_ff;
@@ -94,6 +109,9 @@ struct nd_engine {
   std::vector<EncLayerT> encT;
   LnW enc_ln;
   std::vector<ConvW> enc_conv, dec_conv;
+  ResNetW resnet;
+  float* rbuf[3] = {nullptr, nullptr, nullptr};   // [maxB*maxT, 512] activations of the ResNet stem
+  float* cmask = nullptr;            // ctransformer: channel 0 of the stem output, the encoder's key-mask source [B,T]
   std::vector<DecLayerT> decT;
   LnW dec_ln;
   const float* emb = nullptr;        // [V,d]
@@ -498,12 +516,86 @@ int load_cross_mb(nd_engine* e, const std::string& p, const std::string& ln_pref
   return ND_OK;
 }
 
+// eval BatchNorm as y = x*alpha + beta (ATen batch_norm_cpu_transform_input)
+int load_bn_fold(nd_engine* e, const std::string& bp, int n, std::vector<float>* alpha, std::vector<float>* beta) {
+  const HostTensor *w, *b, *rm, *rv;
+  ND_TRY(need(e, bp + ".weight", {n}, &w));
+  ND_TRY(need(e, bp + ".bias", {n}, &b));
+  ND_TRY(need(e, bp + ".running_mean", {n}, &rm));
+  ND_TRY(need(e, bp + ".running_var", {n}, &rv));
+  alpha->resize(n); beta->resize(n);
+  for (int i = 0; i < n; ++i) {
+    const float invstd = 1.0f / sqrtf(rv->f[i] + 1e-5f);
+    (*alpha)[i] = w->f[i] * invstd;
+    (*beta)[i] = b->f[i] - rm->f[i] * (*alpha)[i];
+  }
+  return ND_OK;
+}
+
+// conv (kh x kw) + BatchNorm of the ResNet stem as a GEMM weight.  The image is [B, C, 1, T]: with kh = 5, padding 2
+// only kernel row 2 meets data (kh = 1: row 0), and the strides act on the height-1 axis only.
+int load_resconv(nd_engine* e, const std::string& conv, const std::string& bn, int cout, int cin, int kh, int kw,
+                 bool bias, Lin* out) {
+  const HostTensor *w, *b = nullptr;
+  ND_TRY(need(e, conv + ".weight", {cout, cin, kh, kw}, &w));
+  if (bias) ND_TRY(need(e, conv + ".bias", {cout}, &b));
+  std::vector<float> alpha, beta;
+  ND_TRY(load_bn_fold(e, bn, cout, &alpha, &beta));
+  const int row = kh / 2;
+  std::vector<float> W((size_t)cout * kw * cin), bb(cout);
+  for (int o = 0; o < cout; ++o) {
+    for (int c = 0; c < cin; ++c)
+      for (int j = 0; j < kw; ++j)
+        W[(size_t)o * kw * cin + (size_t)j * cin + c] = alpha[o] * w->f[(((size_t)o * cin + c) * kh + row) * kw + j];
+    bb[o] = (b ? b->f[o] * alpha[o] : 0.f) + beta[o];
+  }
+  *out = make_lin(e, W, cout, kw * cin, &bb);
+  return ND_OK;
+}
+
+int load_resnet(nd_engine* e, const std::string& p, int d) {
+  ResNetW& R = e->resnet;
+  {
+    const HostTensor* w;
+    ND_TRY(need(e, p + ".conv1.weight", {64, 1, 5, 3}, &w));
+    std::vector<float> alpha, beta, sw(64 * 3);
+    ND_TRY(load_bn_fold(e, p + ".bn1", 64, &alpha, &beta));
+    for (int o = 0; o < 64; ++o)
+      for (int j = 0; j < 3; ++j) sw[o * 3 + j] = alpha[o] * w->f[((size_t)o * 5 + 2) * 3 + j];
+    R.stem_w = upload(e, sw);
+    R.stem_b = upload(e, beta);
+  }
+  static const int planes[4] = {64, 128, 256, 512};
+  int inplanes = 64;
+  for (int li = 0; li < 4; ++li) {
+    for (int bi = 0; bi < 2; ++bi) {
+      const std::string bp = p + ".layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      ResBlockW B;
+      B.cin = bi == 0 ? inplanes : planes[li];
+      B.cout = planes[li];
+      ND_TRY(load_resconv(e, bp + ".conv1", bp + ".bn1", B.cout, B.cin, 5, 3, true, &B.conv1));
+      ND_TRY(load_resconv(e, bp + ".conv2", bp + ".bn2", B.cout, B.cout, 5, 3, true, &B.conv2));
+      B.has_down = bi == 0 && B.cin != B.cout;
+      if (B.has_down) ND_TRY(load_resconv(e, bp + ".downsample.0", bp + ".downsample.1", B.cout, B.cin, 1, 1, false, &B.down));
+      R.blocks.push_back(B);
+    }
+    inplanes = planes[li];
+  }
+  ND_TRY(load_lin(e, p + ".fc", d, 512, true, &R.fc));
+  return ND_OK;
+}
+
 int finalize(nd_engine* e) {
   const nd_config& c = e->cfg;
   const int d = c.d_model, V = c.vocab_size;
   // ---------------- encoder
-  if (c.encoder_type == ND_ENC_NANO) {
+  if (c.encoder_type == ND_ENC_RESNET || c.encoder_type == ND_ENC_CRNN || c.encoder_type == ND_ENC_CTRANSFORMER)
+    ND_TRY(load_resnet(e, "encoder.cnn", d));
+  if (c.encoder_type == ND_ENC_RESNET) {
+    // encoder/resnet_encoder.py:202-251: the stem is the whole encoder
+  } else if (c.encoder_type == ND_ENC_NANO || c.encoder_type == ND_ENC_CRNN) {
     const int H = d / 2;
+    const bool crnn = c.encoder_type == ND_ENC_CRNN;       // crnn_encoder.py:62-68: the first layer reads the d-wide stem
     if (!lstm_supported(H)) return fail(e, ND_ERR_INVALID, "LSTM hidden size " + std::to_string(H) + " unsupported (16/32/64/128/256)");
     e->lstm.resize(c.enc_layers);
     std::vector<std::vector<float>> alphas(c.enc_layers), betas(c.enc_layers);
@@ -524,7 +616,7 @@ int finalize(nd_engine* e) {
     }
     for (int l = 0; l < c.enc_layers; ++l) {
       // layer l >= 1 reads BatchNorm_{l-1}(output of layer l-1): folded into its input projection
-      ND_TRY(load_lstm(e, "encoder.rnn_" + std::to_string(l), "_l0", l == 0 ? 1 : d, H, 2, &e->lstm[l],
+      ND_TRY(load_lstm(e, "encoder.rnn_" + std::to_string(l), "_l0", (l == 0 && !crnn) ? 1 : d, H, 2, &e->lstm[l],
                        l ? &alphas[l - 1] : nullptr, l ? &betas[l - 1] : nullptr));
       e->lstm[l].bn_alpha = upload(e, alphas[l]);
       e->lstm[l].bn_beta = upload(e, betas[l]);
@@ -537,8 +629,8 @@ int finalize(nd_engine* e) {
     e->lstm.resize(c.enc_layers);
     for (int l = 0; l < c.enc_layers; ++l)
       ND_TRY(load_lstm(e, "encoder.rnn", "_l" + std::to_string(l), l == 0 ? 1 : d, H, dirs, &e->lstm[l]));
-  } else if (c.encoder_type == ND_ENC_TRANSFORMER) {
-    ND_TRY(load_lin(e, "encoder.linear", d, 1, true, &e->enc_lin_in));
+  } else if (c.encoder_type == ND_ENC_TRANSFORMER || c.encoder_type == ND_ENC_CTRANSFORMER) {
+    if (c.encoder_type == ND_ENC_TRANSFORMER) ND_TRY(load_lin(e, "encoder.linear", d, 1, true, &e->enc_lin_in));
     e->encT.resize(c.enc_layers);
     for (int l = 0; l < c.enc_layers; ++l) {
       const std::string p = "encoder.transformer." + std::to_string(l);
@@ -684,10 +776,18 @@ int alloc_workspace(nd_engine* e) {
   e->mem_len = dalloc<int64_t>(e, B);
   F(e->bufA, BT * d); F(e->bufB, BT * d); F(e->mb, BT * d);
   int64_t wide = 4 * d;                                    // LSTM input projection (2 dirs * 4 * d/2)
-  if (c.encoder_type == ND_ENC_NANO)
+  if (c.encoder_type == ND_ENC_NANO || c.encoder_type == ND_ENC_CRNN)
     for (int l = 0; l < c.enc_layers; ++l)
       if (c.enc_pooling[l] > 1 && !e->bufC) F(e->bufC, BT * d);
-  if (c.encoder_type == ND_ENC_TRANSFORMER) { wide = std::max<int64_t>(3 * d, c.d_ff); F(e->bufC, BT * d); }
+  if (c.encoder_type == ND_ENC_TRANSFORMER || c.encoder_type == ND_ENC_CTRANSFORMER) {
+    wide = std::max<int64_t>(3 * d, c.d_ff);
+    F(e->bufC, BT * d);
+  }
+  if (c.encoder_type == ND_ENC_RESNET || c.encoder_type == ND_ENC_CRNN || c.encoder_type == ND_ENC_CTRANSFORMER) {
+    wide = std::max<int64_t>(wide, 3 * 512);               // im2col rows of the widest stem layer
+    for (int i = 0; i < 3; ++i) F(e->rbuf[i], BT * 512);
+    if (c.encoder_type == ND_ENC_CTRANSFORMER) F(e->cmask, BT);
+  }
   if (c.encoder_type == ND_ENC_CNN) { wide = (int64_t)c.cnn_kernel_width * d; F(e->big2, BT * 2 * d); F(e->emb_remap, BT * d); }
   F(e->big, BT * wide);
   if (c.encoder_type == ND_ENC_BRNN || c.encoder_type == ND_ENC_RNN) {
@@ -745,10 +845,50 @@ int alloc_workspace(nd_engine* e) {
 }
 
 // ------------------------------------------------------------------------------------------ encoders
+// ResNet stem: src [B,T] -> out [B*T, d].  conv(1 -> 64) + BN + ReLU, 8 BasicBlocks
+// (relu(bn2(conv2(relu(bn1(conv1 x)))) + residual), encoder/resnet_encoder.py:30-47), Linear(512, d).
+int encode_resnet_stem(nd_engine* e, float* out, cudaStream_t st) {
+  const ResNetW& R = e->resnet;
+  const int B = e->B, T = e->T;
+  const int64_t M = (int64_t)B * T;
+  float* cur = e->rbuf[0];
+  float* t1 = e->rbuf[1];
+  float* spare = e->rbuf[2];
+  ND_LAUNCH(e, resnet_stem_conv(e->src, R.stem_w, R.stem_b, cur, B, T, st));
+  for (const ResBlockW& K : R.blocks) {
+    ND_LAUNCH(e, im2col_time(cur, e->big, B, T, K.cin, 3, 1, st));
+    GemmOpt o1; o1.act = 1;
+    ND_TRY(run_gemm(e, K.conv1, e->big, 3 * (int64_t)K.cin, t1, K.cout, M, o1, st));
+    ND_LAUNCH(e, im2col_time(t1, e->big, B, T, K.cout, 3, 1, st));
+    GemmOpt o2; o2.act = 3; o2.ldr = K.cout;             // ReLU after the residual add
+    if (K.has_down) {
+      GemmOpt od;
+      ND_TRY(run_gemm(e, K.down, cur, K.cin, spare, K.cout, M, od, st));
+      o2.residual = spare;
+      ND_TRY(run_gemm(e, K.conv2, e->big, 3 * (int64_t)K.cout, cur, K.cout, M, o2, st));   // cur is free by now
+    } else {
+      o2.residual = cur;
+      ND_TRY(run_gemm(e, K.conv2, e->big, 3 * (int64_t)K.cout, spare, K.cout, M, o2, st));
+      std::swap(cur, spare);
+    }
+  }
+  GemmOpt of;
+  ND_TRY(run_gemm(e, R.fc, cur, 512, out, e->cfg.d_model, M, of, st));
+  return ND_OK;
+}
+
+// encoder/resnet_encoder.py:227-251 (ResNetForRNNEncoder): memory bank = the stem output, lengths unchanged, zero state
+int encode_resnet(nd_engine* e, cudaStream_t st) {
+  ND_TRY(encode_resnet_stem(e, e->mb, st));
+  e->Tp = e->T;
+  ND_CUDA(e, cudaMemcpyAsync(e->mem_len, e->lengths, (size_t)e->B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  return ND_OK;
+}
+
 int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
   const nd_config& c = e->cfg;
   const int d = c.d_model, B = e->B;
-  const bool nano = c.encoder_type == ND_ENC_NANO;
+  const bool nano = c.encoder_type == ND_ENC_NANO || c.encoder_type == ND_ENC_CRNN;   // pool / BatchNorm / W stack
   const int dirs = (c.encoder_type == ND_ENC_RNN) ? 1 : 2;
   const int H = d / dirs;
   int T = e->T;
@@ -756,6 +896,12 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
   // does lengths.tolist() and the arithmetic in Python, nano_encoder.py:90,103-104; here nothing leaves the stream)
   const int64_t* lens_dev = e->lengths;
   const float* in = nullptr;                // previous layer output [B,T,d]
+  if (c.encoder_type == ND_ENC_CRNN) {
+    // crnn_encoder.py:97-98: the ResNet stem's [B,T,d] output feeds the first LSTM layer.  It is parked in the memory
+    // bank buffer, which nothing else touches until the stack's last step writes W . out into it.
+    ND_TRY(encode_resnet_stem(e, e->mb, st));
+    in = e->mb;
+  }
   float* outs[2] = {e->bufA, e->bufB};
   float* last = nullptr;
   for (int l = 0; l < c.enc_layers; ++l) {
@@ -764,11 +910,11 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
     LstmParams p;
     p.B = B; p.T = T; p.dirs = dirs; p.H = H; p.cell = c.rnn_type == ND_RNN_GRU ? 1 : 0;
     p.w_hh = W.w_hh; p.b_hh = W.b_hh; p.lengths = lens_dev; p.out = out;
-    if (l == 0) {
+    if (W.in == 1) {
       p.x0 = e->src; p.w_ih0 = W.w_ih0; p.b_ih0 = W.b_ih0;
     } else {
       GemmOpt o;
-      if (nano) { o.prologue = PRO_AFFINE; o.pg = e->lstm[l - 1].bn_alpha; o.pb = e->lstm[l - 1].bn_beta; }
+      if (nano && l > 0) { o.prologue = PRO_AFFINE; o.pg = e->lstm[l - 1].bn_alpha; o.pb = e->lstm[l - 1].bn_beta; }
       const int64_t ng = p.cell ? 3 : 4;
       ND_TRY(run_gemm(e, W.ih, in, d, e->big, dirs * ng * H, (int64_t)B * T, o, st));
       p.xg = e->big; p.xg_ld = dirs * ng * H;
@@ -815,12 +961,20 @@ int encode_transformer(nd_engine* e, cudaStream_t st) {
   float* x = e->bufA;
   float* x1 = e->bufB;
   float* ctx = e->bufC;
-  ND_LAUNCH(e, linear_in1(e->src, e->enc_lin_in.W, e->enc_lin_in.b, x, M, d, st));       // encoder/transformer.py:113
+  const float* mask_src = e->src;           // key t is masked where this is 0.0 (encoder/transformer.py:117-121)
+  if (c.encoder_type == ND_ENC_CTRANSFORMER) {
+    // encoder/ctransformer.py:75-84: the stem replaces Linear(1,d), and the mask is read from channel 0 of ITS output
+    ND_TRY(encode_resnet_stem(e, x, st));
+    ND_LAUNCH(e, take_column(x, d, 0, e->cmask, M, st));
+    mask_src = e->cmask;
+  } else {
+    ND_LAUNCH(e, linear_in1(e->src, e->enc_lin_in.W, e->enc_lin_in.b, x, M, d, st));     // encoder/transformer.py:113
+  }
   for (int l = 0; l < c.enc_layers; ++l) {
     const EncLayerT& L = e->encT[l];
     GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln.g; o1.pb = L.ln.b;
     ND_TRY(run_gemm(e, L.qkv, x, d, e->big, 3 * d, M, o1, st));
-    EncAttnParams a; a.qkv = e->big; a.q_div = sq; a.src = e->src; a.ctx = ctx; a.B = B; a.T = T; a.d = d; a.H = c.heads;
+    EncAttnParams a; a.qkv = e->big; a.q_div = sq; a.src = mask_src; a.ctx = ctx; a.B = B; a.T = T; a.d = d; a.H = c.heads;
     if (tc_mode(e) && e->enc_attn_tc && encoder_attention_tc_supported(a))
       ND_LAUNCH_CAT(e, ND_PROF_ENC_ATTN, st, encoder_attention_tc(a, st));
     else
@@ -1448,7 +1602,8 @@ int nd_encode(nd_engine* e, const float* src, const int64_t* lengths, int32_t B,
   const nd_config& c = e->cfg;
   int rc;
   NvtxRange nvtx("nd:encode");
-  if (c.encoder_type == ND_ENC_TRANSFORMER) rc = encode_transformer(e, st);
+  if (c.encoder_type == ND_ENC_TRANSFORMER || c.encoder_type == ND_ENC_CTRANSFORMER) rc = encode_transformer(e, st);
+  else if (c.encoder_type == ND_ENC_RESNET) rc = encode_resnet(e, st);
   else if (c.encoder_type == ND_ENC_CNN) rc = encode_cnn(e, st);
   else rc = encode_lstm_stack(e, st);
   if (rc == ND_OK) e->encoded = true;

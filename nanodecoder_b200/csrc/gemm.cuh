@@ -23,7 +23,7 @@ struct GemmParams {
   //   PRO_AFFINE:    a * pg[k] + pb[k]                          (eval BatchNorm1d folded to alpha/beta)
   int prologue = PRO_NONE;
   const float* pg = nullptr; const float* pb = nullptr; float eps = 1e-6f;
-  int relu = 0;                                  // 0 none, 1 ReLU, 2 tanh
+  int relu = 0;                                  // 0 none, 1 ReLU, 2 tanh (SIMT path only), 3 ReLU AFTER the residual add
   // columns [0, div_ncols) are divided by div_by after the bias (q / sqrt(dh), multi_headed_attn.py:167)
   float div_by = 1.0f; int div_ncols = 0;
   // tcgen05 path only — LayerNorm folded around the GEMM instead of applied to A:

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmParams p) {
       if (n < p.div_ncols) v = v / p.div_by;
       if (p.relu == 1) v = fmaxf(v, 0.f); else if (p.relu == 2) v = tanhf(v);
       if (p.residual) v += p.residual[(int64_t)m * p.ldr + n];
+      if (p.relu == 3) v = fmaxf(v, 0.f);
       p.C[(int64_t)m * p.ldc + n] = v;
     }
   }

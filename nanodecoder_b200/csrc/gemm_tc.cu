@@ -178,6 +178,7 @@ __device__ __noinline__ void epilogue_store_slow(const GemmParams& p, float (&v)
       else if (p.bias) x += __ldg(p.bias + n);
       if (p.relu == 1) x = fmaxf(x, 0.f);
       if (rrow) x += rrow[j];
+      if (p.relu == 3) x = fmaxf(x, 0.f);
       crow[j] = x;
     }
   }
@@ -565,6 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int mm = m0 + lg * 32 + r;
             float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
             if (p.residual) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+            if (p.relu == 3) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             if (mm < p.M) *reinterpret_cast<float4*>(p.C + (int64_t)mm * p.ldc + nb + cq * 4) = o;
           }
           __syncwarp();
@@ -661,6 +663,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < CH; j += 4) {
             float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
             if (p.residual) { o.x += res[j / 4].x; o.y += res[j / 4].y; o.z += res[j / 4].z; o.w += res[j / 4].w; }
+            if (p.relu == 3) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(crow + j) = o;
           }
         } else {
@@ -991,6 +994,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const int mm = m0 + lg * 32 + r;
             float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
             if (p.residual) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+            if (p.relu == 3) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             if (mm < p.M) *reinterpret_cast<float4*>(p.C + (int64_t)mm * p.ldc + nb + cq * 4) = o;
           }
           __syncwarp();
@@ -1189,7 +1193,7 @@ cudaError_t gemm_tc(const GemmParams& p, int npass, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0) return cudaSuccess;
   if (!lookup()) return cudaErrorNotSupported;
   // the tensor-core kernel keeps a minimal epilogue; prologues are folded into the weights by the caller
-  if (p.prologue != PRO_NONE || p.div_ncols != 0 || p.relu > 1) return cudaErrorInvalidValue;
+  if (p.prologue != PRO_NONE || p.div_ncols != 0 || p.relu == 2) return cudaErrorInvalidValue;
   // TMA needs 16-byte aligned bases and row pitches
   if ((p.lda & 3) || (p.ldw & 3) || (reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15) ||
       (npass == 3 && (p.W_lo == nullptr || (reinterpret_cast<uintptr_t>(p.W_lo) & 15))))

@@ -133,6 +133,11 @@ cudaError_t embed_rows(const int* tok, const float* emb, float* x, int64_t x_ld,
 cudaError_t linear_in1(const float* x, const float* w, const float* bias, float* y, int64_t n, int d,
                        cudaStream_t stream);
 // MaxPool1d(stride) over time: in [B,T,d] -> out [B,T/stride,d]   (encoder/nano_encoder.py:101-105)
+// ResNet stem, first layer (encoder/resnet_encoder.py:123-126,154-156): width-3 convolution of the one-channel signal
+// with zero padding at the chunk ends, eval BatchNorm folded into w / b, ReLU.  src [B,T] -> out [B*T, 64]
+cudaError_t resnet_stem_conv(const float* src, const float* w, const float* b, float* out, int B, int T, cudaStream_t stream);
+// out[r] = x[r*ld + col]
+cudaError_t take_column(const float* x, int ld, int col, float* out, int64_t rows, cudaStream_t stream);
 cudaError_t maxpool_time(const float* in, float* out, int B, int T, int d, int stride, cudaStream_t stream);
 // lengths after MaxPool1d(stride): out[i] = floor((in[i] - stride) / stride + 1) (in == out allowed)
 cudaError_t pool_lengths(const int64_t* in, int64_t* out, int B, int stride, cudaStream_t stream);

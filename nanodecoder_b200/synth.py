@@ -70,6 +70,39 @@ class _Builder:
         self.linear(prefix + ".w_2", d, ff, gain=out_gain)
         self.affine(prefix + ".layer_norm", d)
 
+    def batchnorm(self, prefix, n, scale=1.0):
+        """eval-mode BatchNorm buffers + affine"""
+        w = scale * (1.0 + 0.1 * _rng(self.seed, prefix + ".weight").standard_normal(n))
+        self.sd[prefix + ".weight"] = torch.from_numpy(w.astype(np.float32))
+        self.bias(prefix + ".bias", n)
+        self.normal(prefix + ".running_mean", (n,), 0.05)
+        rv = 0.8 + 0.2 * np.abs(_rng(self.seed, prefix + ".running_var").standard_normal(n))
+        self.sd[prefix + ".running_var"] = torch.from_numpy(rv.astype(np.float32))
+        self.sd[prefix + ".num_batches_tracked"] = torch.tensor(1000, dtype=torch.int64)
+
+    def resnet(self, prefix, num_classes, fc_gain=1.0):
+        """encoder/resnet_encoder.py:119-152 (ResNet with BasicBlock, layers [2,2,2,2]): (5,3) kernels of which only row
+        2 meets the height-1 signal; He-scaled for the 3 taps that act, second BatchNorm of a block damped so the
+        residual stream keeps its scale over the 8 blocks."""
+        self.normal(prefix + ".conv1.weight", (64, 1, 5, 3), np.sqrt(2.0 / 3))
+        self.batchnorm(prefix + ".bn1", 64)
+        inplanes = 64
+        for li, planes in enumerate((64, 128, 256, 512)):
+            for bi in range(2):
+                bp = "%s.layer%d.%d" % (prefix, li + 1, bi)
+                cin = inplanes if bi == 0 else planes
+                self.normal(bp + ".conv1.weight", (planes, cin, 5, 3), np.sqrt(2.0 / (3 * cin)))
+                self.bias(bp + ".conv1.bias", planes)
+                self.batchnorm(bp + ".bn1", planes)
+                self.normal(bp + ".conv2.weight", (planes, planes, 5, 3), np.sqrt(2.0 / (3 * planes)))
+                self.bias(bp + ".conv2.bias", planes)
+                self.batchnorm(bp + ".bn2", planes, scale=0.5)
+                if bi == 0 and inplanes != planes:
+                    self.normal(bp + ".downsample.0.weight", (planes, inplanes, 1, 1), np.sqrt(1.0 / inplanes))
+                    self.batchnorm(bp + ".downsample.1", planes)
+            inplanes = planes
+        self.linear(prefix + ".fc", num_classes, 512, gain=fc_gain)
+
     def wnconv(self, prefix, d, width):
         """WeightNormConv2d (onmt/modules/weight_norm.py:101-169): weight==V, bias==b aliases and
         the Polyak buffers equal to the live values, as in a trained checkpoint, so the
@@ -104,6 +137,15 @@ FAMILY_GAINS = {
     ("brnn", "rnn"): dict(emb_std=1.0, attn_qk=1.5, ctx_out=2.0, gen=3.0, eos_bias=-1.0),
     ("rnn", "rnn"): dict(emb_std=1.0, attn_qk=1.5, ctx_out=2.0, gen=3.0, eos_bias=-1.0),
     ("cnn", "cnn"): dict(emb_std=1.0, attn_qk=2.5, ctx_out=2.0, gen=2.0, eos_bias=-0.5),
+    # ResNet-stem encoders: random search over the same gains + the stem's output gain (fc), 16 chunks
+    ("resnet", "transformer"): dict(stem_gain=2.95, emb_std=0.1, attn_qk=2.9, ctx_out=3.3, self_qk=2.14, self_out=2.24,
+                                    ffn_out=1.53, gen=2.57, eos_bias=-0.88),
+    ("resnet", "rnn"): dict(stem_gain=0.92, emb_std=0.3, attn_qk=2.41, ctx_out=5.72, gen=1.76, eos_bias=-0.86),
+    ("crnn", "transformer"): dict(stem_gain=0.4, emb_std=1.0, attn_qk=1.4, ctx_out=1.45, self_qk=1.87, self_out=1.55,
+                                  ffn_out=1.67, gen=1.4, eos_bias=-0.09),
+    ("crnn", "rnn"): dict(stem_gain=0.1, emb_std=0.3, attn_qk=2.55, ctx_out=5.89, gen=2.35, eos_bias=-1.21),
+    ("ctransformer", "transformer"): dict(stem_gain=2.41, emb_std=0.1, attn_qk=2.63, ctx_out=1.01, self_qk=2.29,
+                                          self_out=0.62, ffn_out=1.73, gen=1.35, eos_bias=-0.21),
 }
 
 
@@ -170,6 +212,23 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
         b.linear("encoder.linear", d, 1)
         for l in range(cfg.enc_layers):
             b.wnconv("encoder.cnn.layers.%d.conv" % l, d, cfg.cnn_kernel_width)
+    elif cfg.encoder_type == "resnet":          # encoder/resnet_encoder.py:214-216
+        b.resnet("encoder.cnn", d, G.get("stem_gain", 1.0))
+    elif cfg.encoder_type == "crnn":            # encoder/crnn_encoder.py:27-84: stem + nano stack, first layer d wide
+        b.resnet("encoder.cnn", d, G.get("stem_gain", 1.0))
+        b.linear("encoder.W", d, d, bias=False)
+        for l in range(cfg.enc_layers):
+            for sfx in ("_l0", "_l0_reverse"):
+                b.lstm("encoder.rnn_%d" % l, sfx, d, h, gain_ih=1.0, gates=ng)
+            b.batchnorm("encoder.batchnorm_%d" % l, d)
+    elif cfg.encoder_type == "ctransformer":    # encoder/ctransformer.py:45-64
+        b.resnet("encoder.cnn", d, G.get("stem_gain", 1.0))
+        for l in range(cfg.enc_layers):
+            p = "encoder.transformer.%d" % l
+            b.mha(p + ".self_attn", d)
+            b.ffn(p + ".feed_forward", d, cfg.d_ff)
+            b.affine(p + ".layer_norm", d)
+        b.affine("encoder.layer_norm", d)
 
     # ---------------- decoder
     b.normal("decoder.embeddings.make_embedding.emb_luts.0.weight", (V, d), G["emb_std"])

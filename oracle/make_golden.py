@@ -70,6 +70,14 @@ CASES = {
     "brnn2rnn_gru_d256": ("brnn2rnn", dict(rnn_type="GRU")),
     "l2t_gru_d64": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2, rnn_type="GRU")),
     "rnn2rnn_gru_std_d64": ("rnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, rnn_type="GRU", input_feed=0)),
+    # ResNet stem encoders (encoder/resnet_encoder.py, crnn_encoder.py, ctransformer.py); pipeline-train.sh trains
+    # resnet -> transformer and resnet -> rnn at d = 256
+    "resnet2t_d256": ("resnet2t", dict()),
+    "resnet2rnn_d256": ("resnet2rnn", dict()),
+    "resnet2t_d64": ("resnet2t", dict(d_model=64, d_ff=128, dec_layers=2)),
+    "crnn2t_d64": ("crnn2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2)),
+    "crnn2rnn_d64": ("crnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2)),
+    "ctrans2t_d64": ("ctrans2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2)),
 }
 
 

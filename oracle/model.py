@@ -188,8 +188,98 @@ def rnn_encoder(sd, cfg, src, lengths):
     return final, pad_packed_sequence(mb)[0], lengths
 
 
+# --------------------------------------------------------------------------- ResNet stem and the encoders built on it
+RESNET_PLANES = (64, 128, 256, 512)      # encoder/resnet_encoder.py:121-130 (the active ResNet.__init__)
+RESNET_BLOCKS = (2, 2, 2, 2)             # models/model_builder.py:87,120,137,145: layers = [2, 2, 2, 2]
+
+
+def _bn2d(sd, prefix, x):
+    """nn.BatchNorm2d in eval mode (eps 1e-5)."""
+    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
+                        sd[prefix + ".bias"], False, 0.1, 1e-5)
+
+
+def resnet_stem(sd, prefix, src):
+    """encoder/resnet_encoder.py:82-170 (class ResNet with BasicBlock, :19-47) on the signal as the callers shape it
+    (:192, crnn_encoder.py:97, ctransformer.py:75): src [T,B,1] -> image [B, 1, 1, T].  The kernels are (5,3) with
+    padding (2,1) and the strides act on the height-1 axis only, so every layer is a width-3 convolution along time
+    (kernel row 2 is the only one that meets data) and T is never shortened.  -> [T, B, num_classes]."""
+    T, B, nf = src.shape
+    x = src.transpose(0, 1).transpose(1, 2).contiguous().view(B, nf, -1, T)
+    x = F.conv2d(x, sd[prefix + ".conv1.weight"], None, stride=(2, 1), padding=(2, 1))          # :123-124 (no bias)
+    x = torch.relu(_bn2d(sd, prefix + ".bn1", x))
+    inplanes = 64
+    for li, (planes, blocks) in enumerate(zip(RESNET_PLANES, RESNET_BLOCKS)):
+        for bi in range(blocks):
+            bp = "%s.layer%d.%d" % (prefix, li + 1, bi)
+            stride = 2 if (li > 0 and bi == 0) else 1
+            out = F.conv2d(x, sd[bp + ".conv1.weight"], sd[bp + ".conv1.bias"], stride=(stride, 1), padding=(2, 1))
+            out = torch.relu(_bn2d(sd, bp + ".bn1", out))
+            out = F.conv2d(out, sd[bp + ".conv2.weight"], sd[bp + ".conv2.bias"], stride=(1, 1), padding=(2, 1))
+            out = _bn2d(sd, bp + ".bn2", out)
+            residual = x
+            if bi == 0 and (stride != 1 or inplanes != planes):                                 # :137-144
+                residual = F.conv2d(x, sd[bp + ".downsample.0.weight"], None, stride=(stride, 1))
+                residual = _bn2d(sd, bp + ".downsample.1", residual)
+            x = torch.relu(out + residual)                                                      # :41-45
+        inplanes = planes
+    x = x.squeeze(2).transpose(0, 1).transpose(0, 2).contiguous()                               # :165  [T,B,512]
+    return _lin(sd, prefix + ".fc", x)
+
+
+def resnet_encoder(sd, cfg, src, lengths):
+    """encoder/resnet_encoder.py:202-251 (ResNetForRNNEncoder: what model_builder.py:141-150 builds for the rnn and
+    transformer decoders).  -> (zero state, memory_bank [T,B,d], lengths)."""
+    B = src.size(1)
+    mb = resnet_stem(sd, "encoder.cnn", src).view(-1, B, cfg.d_model)
+    state = mb.new_zeros(cfg.dec_layers, B, cfg.d_model)
+    return ((state, state) if cfg.rnn_type == "LSTM" else state), mb, lengths
+
+
+def crnn_encoder(sd, cfg, src, lengths):
+    """encoder/crnn_encoder.py:86-133: ResNet stem, then the NanoEncoder stack with a d-wide first layer."""
+    d = cfg.d_model
+    hdim = d // 2
+    B = src.size(1)
+    src = resnet_stem(sd, "encoder.cnn", src)                       # :97-98
+    lens = [int(v) for v in lengths.view(-1).tolist()]
+    memory_bank = None
+    for l in range(cfg.enc_layers):
+        stride = cfg.enc_pooling[l]
+        rnn = _make_lstm(sd, "encoder.rnn_%d" % l, d, hdim, 1, True, cfg.rnn_type)
+        packed = pack_padded_sequence(src, lens, enforce_sorted=False)
+        memory_bank = pad_packed_sequence(rnn(packed)[0])[0]
+        memory_bank = F.max_pool1d(memory_bank.transpose(0, 2), stride)
+        lens = [int(math.floor((n - stride) / stride + 1)) for n in lens]
+        memory_bank = memory_bank.transpose(0, 2)
+        t, _, nf = memory_bank.shape
+        p = "encoder.batchnorm_%d" % l
+        src = F.batch_norm(memory_bank.contiguous().view(-1, nf), sd[p + ".running_mean"],
+                           sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                           False, 0.1, 1e-5).view(t, -1, nf)
+    mb = F.linear(memory_bank.contiguous().view(-1, memory_bank.size(2)), sd["encoder.W.weight"]).view(-1, B, d)
+    state = mb.new_zeros(cfg.dec_layers * 2, B, hdim)
+    return ((state, state) if cfg.rnn_type == "LSTM" else state), mb, lengths.new_tensor(lens)
+
+
+def ctransformer_encoder(sd, cfg, src, lengths):
+    """encoder/ctransformer.py:66-91: ResNet stem instead of Linear(1,d); the key mask is taken from channel 0 of the
+    STEM OUTPUT (== 0.0, :80-84), i.e. practically never set."""
+    emb = resnet_stem(sd, "encoder.cnn", src)                       # :75-77  [T,B,d]
+    out = emb.transpose(0, 1).contiguous()
+    mask = emb[:, :, 0].transpose(0, 1).eq(0).unsqueeze(1)
+    for l in range(cfg.enc_layers):
+        p = "encoder.transformer.%d" % l
+        xn = _ln(sd, p + ".layer_norm", out)
+        ctx, _ = multi_head_attention(sd, p + ".self_attn", xn, xn, xn, cfg.heads, mask=mask)
+        out = feed_forward(sd, p + ".feed_forward", ctx + out)
+    out = _ln(sd, "encoder.layer_norm", out)
+    return emb, out.transpose(0, 1).contiguous(), lengths
+
+
 ENCODERS = {"nano": nano_encoder, "transformer": transformer_encoder, "cnn": cnn_encoder,
-            "rnn": rnn_encoder, "brnn": rnn_encoder}
+            "rnn": rnn_encoder, "brnn": rnn_encoder, "resnet": resnet_encoder, "crnn": crnn_encoder,
+            "ctransformer": ctransformer_encoder}
 
 
 # ======================================================================================= decoders

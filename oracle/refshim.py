@@ -217,6 +217,11 @@ FAMILY_FLAGS = {
     "brnn2rnn": ["-encoder_type", "brnn", "-decoder_type", "rnn"],
     "rnn2rnn": ["-encoder_type", "rnn", "-decoder_type", "rnn"],
     "cnn2cnn": ["-encoder_type", "cnn", "-decoder_type", "cnn"],
+    "resnet2t": ["-encoder_type", "resnet", "-decoder_type", "transformer"],
+    "resnet2rnn": ["-encoder_type", "resnet", "-decoder_type", "rnn"],
+    "crnn2t": ["-encoder_type", "crnn", "-decoder_type", "transformer", "-audio_enc_pooling", "1"],
+    "crnn2rnn": ["-encoder_type", "crnn", "-decoder_type", "rnn", "-audio_enc_pooling", "1"],
+    "ctrans2t": ["-encoder_type", "ctransformer", "-decoder_type", "transformer"],
 }
 
 

@@ -54,7 +54,9 @@ def test_synthetic_state_dicts_are_seed_deterministic(family):
 
 def test_unsupported_configs_fail_loudly():
     with pytest.raises(ValueError):
-        ModelConfig(encoder_type="resnet")
+        ModelConfig(encoder_type="mean")
+    with pytest.raises(ValueError):
+        ModelConfig(encoder_type="resnet", decoder_type="cnn")          # [d,B,T] outputs + [1,1,B,T] embedding
     with pytest.raises(ValueError):
         ModelConfig(rnn_type="SRU")
     assert ModelConfig(rnn_type="GRU").rnn_type == "GRU"
