@@ -172,6 +172,19 @@ ND_EXPORT int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_b
                           int32_t min_len, int32_t length_penalty, float alpha, int64_t* out_ids,
                           int32_t* out_lens, float* out_scores, void* stream);
 
+/* Attention of the hypotheses the last nd_decode_beam / nd_decode_beam_object returned (the reference's
+ * results["attention"] under -attn_debug: translator.py:806-812 alive_attn, beam.py:135,170-178 Beam.attn / get_hyp):
+ *   out [B, n_best, max_len, T'] fp32: row j of hypothesis (b, n) = head-0 cross attention of the last decoder layer at
+ *   decode step j (global attention for the RNN decoder), zero for j >= the hypothesis length.
+ *   out_widths NULL or [B, n_best] int32: the number of source positions the reference keeps of those rows, namely
+ *   memory_lengths[i] of its TILED length vector indexed by the chunk's position i in the batch (fast mode: among the
+ *   chunks not yet retired when the hypothesis finished): the length of chunk alive[i / beam_size] -- the chunk's own
+ *   length when all lengths are equal, a longer one otherwise (translator.py:776, :905).
+ * Needs the integer option "beam_attention" set to 1 BEFORE the decode (the per-step attention of every beam row is then kept:
+ * max_tgt_len * max_batch * max_beam * max_src_len floats, allocated on first use); n_best and max_len as in that decode. */
+ND_EXPORT int nd_beam_attention(nd_engine* e, int32_t n_best, int32_t max_len, float* out, int32_t* out_widths,
+                                void* stream);
+
 /* Read assembly helpers (host code, no GPU work; utils/labelop.py:320-352).
  * nd_longest_match: difflib.SequenceMatcher(None, a, b).find_longest_match(0, na, 0, nb), i.e. the longest block of
  *   get_matching_blocks() the reference's simple_assembly() selects (CPython's autojunk rule included; the sentinel
@@ -232,8 +245,11 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *                    4 = 15-bit fixed point (2 bytes per element; the reduced-precision mode, never the default);
  *                    5 = the top 24 bits of the fp32 value; 1 / 2 = 24 / 16-bit fixed point decoded with conversion
  *                    instructions (cross-checks);
- *   "kv_beam_packed" (default 1): beam search reads the fixed-point planes as well (d = 256 / 512, up to 5 beams at
- *                    T = 512); 0 = fp32 rows through the TMA-ring kernel.
+ *   "kv_beam_packed" (default 1): beam search reads the fixed-point planes as well (kv_mode 3 / 4; d = 256: the TMA-ring
+ *                    kernel over the int16 + uint8 planes, 2 - 8 beams; d = 512: the multi-query slice kernel while the
+ *                    beams' score rows fit two CTAs per SM); 0 = fp32 rows.
+ *   "beam_attention" (default 0): beam decodes keep the per-step attention of every beam row for nd_beam_attention
+ *                    (runs the loop without CUDA graphs);
  * Any nd_set_int call drops the engine's captured CUDA graphs (they are re-captured on the following calls).  */
 ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);
 

@@ -33,6 +33,7 @@ __global__ void beam_init_kernel(BeamParams p, int bos) {
   }
   if (i < p.B) {
     p.st.retired[i] = 0;
+    p.st.retire_step[i] = 0x7fffffff;
     p.st.top_finished[i] = 0;
     p.st.n_hyp[i] = 0;
     for (int n = 0; n < p.n_best; ++n) {
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     float* hs = p.st.hyp_score + (int64_t)b * nb;
     int* hl = p.st.hyp_len + (int64_t)b * nb;
     int* hq = p.st.hyp_seq + (int64_t)b * nb * p.Lmax;
+    int* ha = p.st.hyp_anc + (int64_t)b * nb * p.Lmax;
     const int len = p.step + 1;
     for (int k = 0; k < K; ++k) {                      // finished beams in beam order (:773-778)
       if (!(fin_mask & (1u << k))) continue;
@@ -159,13 +161,19 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
       __syncwarp();
       if (pos < nb) {
         for (int i = nb - 1; i > pos; --i) {
-          for (int j = lane; j < p.Lmax; j += 32) hq[i * p.Lmax + j] = hq[(i - 1) * p.Lmax + j];
+          for (int j = lane; j < p.Lmax; j += 32) {
+            hq[i * p.Lmax + j] = hq[(i - 1) * p.Lmax + j];
+            ha[i * p.Lmax + j] = ha[(i - 1) * p.Lmax + j];
+          }
           __syncwarp();
           if (lane == 0) { hs[i] = hs[i - 1]; hl[i] = hl[i - 1]; }
           __syncwarp();
         }
         const int nr = b * K + k;
-        for (int j = lane; j < len; j += 32) hq[pos * p.Lmax + j] = seq_nxt[(int64_t)nr * Lp1 + 1 + j];
+        for (int j = lane; j < len; j += 32) {
+          hq[pos * p.Lmax + j] = seq_nxt[(int64_t)nr * Lp1 + 1 + j];
+          ha[pos * p.Lmax + j] = anc_nxt[(int64_t)nr * p.Lmax + j];       // rows that ran steps 0 .. step
+        }
         if (lane == 0) { hs[pos] = sc; hl[pos] = len; }
         __syncwarp();
       }
@@ -175,6 +183,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
       p.st.n_hyp[b] = n_hyp;
       if (!obj && top_fin && n_hyp >= nb) {            // :781
         p.st.retired[b] = 1;
+        p.st.retire_step[b] = p.step;
         atomicSub(p.st.n_alive, 1);
       }
       if (obj && (top_fin & 1) && n_hyp >= nb && !(top_fin & 2)) {      // Beam.done() became true (beam.py:151-152)
@@ -200,6 +209,8 @@ __global__ void __launch_bounds__(32) beam_object_fill_kernel(BeamParams p, floa
   const int steps = min(p.max_len, *p.st.stop_step);   // steps actually executed = len(next_ys) - 1
   const int buf = ((steps - 1) & 1) ^ 1;               // alive_seq buffer written by the last executed step
   const int* seq = p.st.alive_seq + (int64_t)buf * p.B * K * Lp1;
+  const int* anc = p.st.anc + (int64_t)buf * p.B * K * p.Lmax;
+  int* ha = p.st.hyp_anc + (int64_t)b * nb * p.Lmax;
   float div = 1.0f;                                    // global score divisor at len(next_ys) = steps + 1
   if (p.lp_mode == 1) div = (float)(pow(5.0 + (double)(steps + 1), (double)alpha) / pow(6.0, (double)alpha));
   else if (p.lp_mode == 2) div = (float)(steps + 1);
@@ -215,17 +226,62 @@ __global__ void __launch_bounds__(32) beam_object_fill_kernel(BeamParams p, floa
     __syncwarp();
     if (pos < nb) {
       for (int q = nb - 1; q > pos; --q) {
-        for (int j = lane; j < p.Lmax; j += 32) hq[q * p.Lmax + j] = hq[(q - 1) * p.Lmax + j];
+        for (int j = lane; j < p.Lmax; j += 32) {
+          hq[q * p.Lmax + j] = hq[(q - 1) * p.Lmax + j];
+          ha[q * p.Lmax + j] = ha[(q - 1) * p.Lmax + j];
+        }
         __syncwarp();
         if (lane == 0) { hs[q] = hs[q - 1]; hl[q] = hl[q - 1]; }
         __syncwarp();
       }
-      for (int j = lane; j < steps; j += 32) hq[pos * p.Lmax + j] = seq[(int64_t)(b * K + i) * Lp1 + 1 + j];
+      for (int j = lane; j < steps; j += 32) {
+        hq[pos * p.Lmax + j] = seq[(int64_t)(b * K + i) * Lp1 + 1 + j];
+        ha[pos * p.Lmax + j] = anc[(int64_t)(b * K + i) * p.Lmax + j];
+      }
       if (lane == 0) { hs[pos] = sc; hl[pos] = steps; }
       __syncwarp();
     }
   }
   (void)gs_none;
+}
+
+// one CTA per (chunk, hypothesis, step): copy (or zero) one attention row
+__global__ void beam_gather_attention_kernel(BeamState st, const float* __restrict__ hist, int n_best, int Lmax, int max_len,
+                                             int rows, int Tp, float* __restrict__ out) {
+  const int64_t i = blockIdx.x;                        // (b * n_best + n) * max_len + j
+  const int j = (int)(i % max_len);
+  const int64_t bn = i / max_len;
+  const int len = st.hyp_len[bn];
+  float* o = out + i * Tp;
+  if (j < len) {
+    const int row = st.hyp_anc[bn * Lmax + j];
+    const float* h = hist + ((int64_t)j * rows + row) * Tp;
+    for (int t = threadIdx.x; t < Tp; t += blockDim.x) o[t] = h[t];
+  } else {
+    for (int t = threadIdx.x; t < Tp; t += blockDim.x) o[t] = 0.f;
+  }
+}
+
+__global__ void beam_attention_width_kernel(BeamState st, const int64_t* __restrict__ mem_len, int B, int K, int n_best,
+                                            int mode, int* __restrict__ widths) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // b * n_best + n
+  if (i >= B * n_best) return;
+  const int b = i / n_best;
+  int src = b / K;                                           // object mode: all chunks stay in the batch (:905)
+  if (mode == 0) {
+    const int s = st.hyp_len[i] - 1;                         // the step at which the hypothesis finished
+    int pos = 0;                                             // position of the chunk among those still in the batch
+    for (int c = 0; c < b; ++c) pos += st.retire_step[c] >= s;
+    const int want = pos / K;                                // :776 memory_lengths[i] of the tiled vector
+    src = b;
+    for (int c = 0, seen = 0; c < B; ++c) {
+      if (st.retire_step[c] >= s) {
+        if (seen == want) { src = c; break; }
+        ++seen;
+      }
+    }
+  }
+  widths[i] = (int)mem_len[src];
 }
 
 __global__ void beam_finalize_kernel(BeamParams p, int64_t* out_ids, int* out_lens, float* out_scores) {
@@ -265,6 +321,16 @@ cudaError_t beam_finalize(const BeamParams& p, int64_t* out_ids, int* out_lens, 
                           cudaStream_t stream) {
   if (p.mode == 1) beam_object_fill_kernel<<<p.B, 32, 0, stream>>>(p, 1.0f, p.alpha);
   launch_k(beam_finalize_kernel, dim3(p.B * p.n_best), dim3(128), 0, stream, p, out_ids, out_lens, out_scores);
+  return cudaGetLastError();
+}
+
+cudaError_t beam_gather_attention(const BeamState& st, const float* hist, const int64_t* mem_len, int B, int K, int n_best,
+                                  int Lmax, int max_len, int rows, int Tp, int mode, float* out, int* widths,
+                                  cudaStream_t stream) {
+  const int64_t n = (int64_t)B * n_best * max_len;
+  if (n <= 0) return cudaSuccess;
+  beam_gather_attention_kernel<<<(unsigned)n, 128, 0, stream>>>(st, hist, n_best, Lmax, max_len, rows, Tp, out);
+  if (widths) beam_attention_width_kernel<<<cdiv(B * n_best, 128), 128, 0, stream>>>(st, mem_len, B, K, n_best, mode, widths);
   return cudaGetLastError();
 }
 

@@ -156,6 +156,10 @@ struct nd_engine {
   // error <= 2^-23 of the row part's largest element; same greedy sequences and identity rates as fp32 storage),
   // KV_F32, KV_Q15M (reduced precision, half the bytes), others = cross-checks
   int kv_mode = KV_Q23M;
+  int beam_n_best = 1, beam_K = 1, beam_mode = 0;   // of the last beam decode (layout of the hypothesis tables)
+  bool beam_attn = false;                  // option "beam_attention": beam decodes keep the per-step head-0 cross attention
+  float* attn_hist = nullptr;              // [max_tgt_len][max_batch*max_beam][max_src_len], allocated on first use
+  int attn_rows = 0, attn_Tp = 0, attn_steps = 0;   // geometry of the history the last beam decode wrote
   int kv_beam_packed = 1;                  // beam search reads the fixed-point planes too where the kernel exists
   bool kv_packed = false;                  // set by decoder_init: this decode reads the packed planes
   int enc_attn_tc = 1;                     // Transformer-encoder self attention on the tensor cores when dh = 32
@@ -831,16 +835,18 @@ int alloc_workspace(nd_engine* e) {
   b.cur_tok = e->cur_tok;
   b.parent = dalloc<int>(e, rows);
   b.retired = dalloc<int>(e, B);
+  b.retire_step = dalloc<int>(e, B);
   b.top_finished = dalloc<int>(e, B);
   b.n_hyp = dalloc<int>(e, B);
   b.hyp_score = dalloc<float>(e, B * K);
   b.hyp_len = dalloc<int>(e, B * K);
   b.hyp_seq = dalloc<int>(e, B * K * L);
+  b.hyp_anc = dalloc<int>(e, B * K * L);
   b.n_alive = dalloc<int>(e, 1);
   b.n_done = dalloc<int>(e, 1);
   b.stop_step = dalloc<int>(e, 1);
   ok = ok && b.n_done && b.stop_step && e->lengths && e->mem_len && e->cur_tok && b.topk_log_probs && b.alive_seq && b.anc && b.parent &&
-       b.retired && b.top_finished && b.n_hyp && b.hyp_score && b.hyp_len && b.hyp_seq && b.n_alive;
+       b.retired && b.top_finished && b.n_hyp && b.hyp_score && b.hyp_len && b.hyp_seq && b.hyp_anc && b.n_alive && b.retire_step;
   return ok ? ND_OK : ND_ERR_NOMEM;
 }
 
@@ -1331,6 +1337,16 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
   bp.logp = e->logp; bp.st = e->beam; bp.B = B; bp.K = K; bp.V = e->cfg.vocab_size; bp.Lmax = e->cfg.max_tgt_len;
   bp.max_len = max_len; bp.min_len = min_len; bp.n_best = n_best; bp.alpha = alpha; bp.mode = mode; bp.lp_mode = lp_mode;
   ND_LAUNCH(e, beam_init(bp, 2, st));
+  e->attn_steps = 0;
+  if (e->beam_attn) {
+    // translator.py:806-812 (alive_attn) / beam.py:135 (Beam.attn): the head-0 cross attention of every step is kept
+    // per ROW; a hypothesis' rows are found afterwards through its ancestor table (nd_beam_attention)
+    if (!e->attn_hist) {
+      e->attn_hist = dalloc<float>(e, (size_t)e->cfg.max_tgt_len * e->max_rows * e->cfg.max_src_len);
+      if (!e->attn_hist) return fail(e, ND_ERR_NOMEM, "beam_attention: no memory for the attention history");
+    }
+    e->attn_rows = B * K; e->attn_Tp = e->Tp; e->attn_steps = max_len;
+  }
   NvtxRange nvtx(mode == 1 ? "nd:object beam decode loop" : "nd:fast beam decode loop");
   // object mode: stop_step / n_done are shared by all chunks (every Beam advances until ALL are done), so chunk
   // groups on independent streams would see the stop at different steps: one stream
@@ -1344,6 +1360,7 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
       cudaStream_t gs = G > 1 ? e->streams[g] : st;
       DecodeCtx dc;
       dc.K = K; dc.Lmax = e->cfg.max_tgt_len; dc.beam = true; dc.step = step;
+      if (e->beam_attn) dc.attn_out = e->attn_hist + (size_t)step * B * K * e->Tp;
       dc.c0 = (int)((int64_t)B * g / G);
       dc.nc = (int)((int64_t)B * (g + 1) / G) - dc.c0;
       GenParams gp;
@@ -1657,7 +1674,8 @@ static int decode_beam_any(nd_engine* e, int32_t beam_size, int32_t n_best, int3
   if (!out_ids || !out_lens || !out_scores) return fail(e, ND_ERR_INVALID, "null output");
   cudaStream_t st = (cudaStream_t)stream;
   const int B = e->B, K = beam_size;
-  if (e->prof_mask || !e->use_graphs)
+  e->beam_n_best = n_best; e->beam_K = beam_size; e->beam_mode = mode;
+  if (e->prof_mask || !e->use_graphs || e->beam_attn)
     return beam_body(e, K, n_best, max_len, min_len, alpha, mode, lp_mode, out_ids, out_lens, out_scores, st);
   int32_t alpha_bits;
   memcpy(&alpha_bits, &alpha, sizeof(alpha_bits));
@@ -1669,6 +1687,18 @@ static int decode_beam_any(nd_engine* e, int32_t beam_size, int32_t n_best, int3
   ND_CUDA(e, cudaMemcpyAsync(out_ids, e->o_ids, (size_t)B * n_best * max_len * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   ND_CUDA(e, cudaMemcpyAsync(out_lens, e->o_lens, (size_t)B * n_best * sizeof(int), cudaMemcpyDeviceToDevice, st));
   ND_CUDA(e, cudaMemcpyAsync(out_scores, e->o_scores, (size_t)B * n_best * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return ND_OK;
+}
+
+int nd_beam_attention(nd_engine* e, int32_t n_best, int32_t max_len, float* out, int32_t* out_widths, void* stream) {
+  ND_TRY(check_ready(e));
+  if (!e->beam_attn || !e->attn_hist || e->attn_steps == 0)
+    return fail(e, ND_ERR_STATE, "nd_beam_attention: set the option beam_attention before the beam decode");
+  if (n_best != e->beam_n_best || max_len != e->attn_steps || !out)
+    return fail(e, ND_ERR_INVALID, "nd_beam_attention: n_best / max_len differ from the last beam decode");
+  ND_LAUNCH(e, beam_gather_attention(e->beam, e->attn_hist, e->mem_len, e->B, e->beam_K, n_best, e->cfg.max_tgt_len,
+                                     max_len, e->attn_rows, e->attn_Tp, e->beam_mode, out, out_widths,
+                                     (cudaStream_t)stream));
   return ND_OK;
 }
 
@@ -1720,6 +1750,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
   }
   if (strcmp(name, "kv_beam_packed") == 0) {
     e->kv_beam_packed = value != 0;
+    return ND_OK;
+  }
+  if (strcmp(name, "beam_attention") == 0) {
+    e->beam_attn = value != 0;
     return ND_OK;
   }
   if (strcmp(name, "cross_packed_fast") == 0) {   // process-wide

@@ -173,11 +173,13 @@ struct BeamState {
   int* cur_tok = nullptr;                         // [B*K]
   int* parent = nullptr;                          // [B*K] parent row of the current beams
   int* retired = nullptr;                         // [B]
+  int* retire_step = nullptr;                     // [B] fast mode: the step at which the chunk left the batch
   int* top_finished = nullptr;                    // [B]
   int* n_hyp = nullptr;                           // [B] finished hypotheses seen so far
   float* hyp_score = nullptr;                     // [B, n_best]
   int* hyp_len = nullptr;                         // [B, n_best]
   int* hyp_seq = nullptr;                         // [B, n_best, Lmax]
+  int* hyp_anc = nullptr;                         // [B, n_best, Lmax] row that ran step j of the hypothesis (ancestor table)
   int* n_alive = nullptr;                         // [1] chunks not yet retired
   int* n_done = nullptr;                          // [1] object mode: chunks whose Beam.done() is true
   int* stop_step = nullptr;                       // [1] object mode: first step that is NOT executed any more
@@ -198,6 +200,14 @@ cudaError_t beam_init(const BeamParams& p, int bos, cudaStream_t stream);
 cudaError_t beam_step(const BeamParams& p, cudaStream_t stream);
 cudaError_t beam_finalize(const BeamParams& p, int64_t* out_ids, int* out_lens, float* out_scores,
                           cudaStream_t stream);
+// attention rows of the finished hypotheses: out[b, n, j, :] = hist[j][hyp_anc[b,n,j]][:] for j < hyp_len[b,n], else 0
+// (hist [*, rows, Tp] = the head-0 cross attention every decode step wrote per row)
+// widths [B, n_best]: how many source positions the reference keeps of those rows -- memory_lengths[i] of the TILED
+// length vector indexed by the chunk's position i in the (fast mode: not yet retired) batch, i.e. the length of chunk
+// alive[i / K] (translator.py:776 and :905; equal to the chunk's own length whenever the lengths are equal)
+cudaError_t beam_gather_attention(const BeamState& st, const float* hist, const int64_t* mem_len, int B, int K, int n_best,
+                                  int Lmax, int max_len, int rows, int Tp, int mode, float* out, int* widths,
+                                  cudaStream_t stream);
 // reorder per-row recurrent state by parent: dst[r] = src[parent[r]]  (rows of `width` floats)
 cudaError_t gather_rows(const float* src, float* dst, const int* parent, int row0, int rows, int width,
                         cudaStream_t stream);

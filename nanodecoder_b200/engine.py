@@ -144,22 +144,43 @@ class Engine(object):
                                               _ptr(logits), self._stream()))
         return {"ids": ids, "scores": scores, "attn": attn, "logits": logits}
 
+    def _want_beam_attention(self, on: bool):
+        """the option drops the captured graphs, so it is only touched when it changes"""
+        if bool(on) != getattr(self, "_beam_attn", False):
+            self.set_option("beam_attention", int(bool(on)))
+            self._beam_attn = bool(on)
+
+    def _beam_attention(self, n_best: int, max_len: int):
+        """-> ([B, n_best, max_len, T'] attention rows of the hypotheses of the last beam decode (zero past their end),
+        [B, n_best] int32 widths: how many source positions the reference returns of them, see include/nanodec.h)"""
+        tp = C.c_int32(0)
+        self._check(self.lib.nd_get_memory_bank(self._h, C.c_void_p(0), C.c_void_p(0), C.byref(tp), self._stream()))
+        attn = torch.empty((self._B, n_best, max_len, tp.value), dtype=torch.float32, device=self.device)
+        widths = torch.empty((self._B, n_best), dtype=torch.int32, device=self.device)
+        self._check(self.lib.nd_beam_attention(self._h, n_best, max_len, _ptr(attn), _ptr(widths), self._stream()))
+        return attn, widths
+
     def decode_beam(self, beam_size: int = 5, n_best: int = 1, max_len: int = 100, min_len: int = 0,
-                    alpha: float = 0.0):
-        """-> dict(ids [B,n_best,L] int64 (-1 padded), lens [B,n_best] int32, scores [B,n_best])"""
+                    alpha: float = 0.0, return_attn: bool = False):
+        """-> dict(ids [B,n_best,L] int64 (-1 padded), lens [B,n_best] int32, scores [B,n_best],
+        attn None or [B,n_best,L,T'] (translator.py:806-812: the attention history of each returned hypothesis),
+        attn_widths None or [B,n_best])"""
         B = self._B
         ids = torch.empty((B, n_best, max_len), dtype=torch.int64, device=self.device)
         lens = torch.empty((B, n_best), dtype=torch.int32, device=self.device)
         scores = torch.empty((B, n_best), dtype=torch.float32, device=self.device)
+        self._want_beam_attention(return_attn)
         self._check(self.lib.nd_decode_beam(self._h, beam_size, n_best, max_len, min_len, float(alpha),
                                             _ptr(ids), _ptr(lens), _ptr(scores), self._stream()))
-        return {"ids": ids, "lens": lens, "scores": scores}
+        attn, widths = self._beam_attention(n_best, max_len) if return_attn else (None, None)
+        return {"ids": ids, "lens": lens, "scores": scores, "attn": attn, "attn_widths": widths}
 
     LENGTH_PENALTY = {"none": 0, "wu": 1, "avg": 2}
 
     def decode_beam_object(self, beam_size: int = 5, n_best: int = 1, max_len: int = 100, min_len: int = 0,
-                           length_penalty: str = "none", alpha: float = 0.0):
+                           length_penalty: str = "none", alpha: float = 0.0, return_attn: bool = False):
         """Object beam search (the reference's default without --fast).  Same outputs as decode_beam."""
+        self._want_beam_attention(return_attn)
         B = self._B
         ids = torch.empty((B, n_best, max_len), dtype=torch.int64, device=self.device)
         lens = torch.empty((B, n_best), dtype=torch.int32, device=self.device)
@@ -167,7 +188,8 @@ class Engine(object):
         self._check(self.lib.nd_decode_beam_object(self._h, beam_size, n_best, max_len, min_len,
                                                    self.LENGTH_PENALTY[length_penalty], float(alpha), _ptr(ids),
                                                    _ptr(lens), _ptr(scores), self._stream()))
-        return {"ids": ids, "lens": lens, "scores": scores}
+        attn, widths = self._beam_attention(n_best, max_len) if return_attn else (None, None)
+        return {"ids": ids, "lens": lens, "scores": scores, "attn": attn, "attn_widths": widths}
 
     # ------------------------------------------------------------------------------------------
     def frontend_stats(self, signal: torch.Tensor, offsets: torch.Tensor, normalization: str = "median"):

@@ -223,9 +223,6 @@ class Translator(object):
                     out = trans.log(next(counter))
                     (self.logger.info(out) if self.logger else os.write(1, out.encode("utf-8")))
                 if attn_debug:
-                    if self.beam_size > 1:
-                        raise ValueError("-attn_debug with beam search: the engine keeps no per-beam attention history; "
-                                         "use -beam_size 1")
                     if self.out_file_attn is not None:
                         if chunks_host is None:
                             chunks_host = chunks.cpu().numpy()
@@ -263,14 +260,22 @@ class Translator(object):
         if not fast:
             # object beam (translator.py:827-926): ranking by the GNMT global score (length penalty only)
             out = eng.decode_beam_object(self.beam_size, self.n_best, self.max_length, self.min_length,
-                                         self.global_scorer.length_penalty, self.global_scorer.alpha)
+                                         self.global_scorer.length_penalty, self.global_scorer.alpha,
+                                         return_attn=attn_debug)
         else:
             out = eng.decode_beam(self.beam_size, self.n_best, self.max_length, self.min_length,
-                                  self.global_scorer.alpha)
+                                  self.global_scorer.alpha, return_attn=attn_debug)
         ids, lens, scores = out["ids"].cpu(), out["lens"].cpu(), out["scores"].cpu()
         results["predictions"] = [[ids[i, n, : int(lens[i, n])] for n in range(self.n_best)] for i in range(B)]
         results["scores"] = [[scores[i, n] for n in range(self.n_best)] for i in range(B)]
-        results["attention"] = [[[] for _ in range(self.n_best)] for _ in range(B)]
+        if out.get("attn") is not None:
+            # translator.py:776,806-812 / :899-905: one [len, memory_length] attention matrix per returned hypothesis
+            # (their width is memory_lengths[i] of the reference's TILED length vector: include/nanodec.h)
+            attn, widths = out["attn"].cpu(), out["attn_widths"].cpu()
+            results["attention"] = [[attn[i, n, : int(lens[i, n]), : int(widths[i, n])] for n in range(self.n_best)]
+                                    for i in range(B)]
+        else:
+            results["attention"] = [[[] for _ in range(self.n_best)] for _ in range(B)]
         return results
 
     def _launch_arrays(self, src, lengths, slot=0):
