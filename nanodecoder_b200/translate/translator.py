@@ -257,6 +257,10 @@ class Translator(object):
             results["scores"] = [[scores[i]] for i in range(B)]
             results["attention"] = [[attn[:, i, : int(mlen[i])]] if attn is not None else [[]] for i in range(B)]
             return results
+        if attn_debug and getattr(self.model_opt, "decoder_type", None) == "cnn":
+            raise ValueError("-attn_debug with beam search and the CNN decoder: the reference indexes the decoder's "
+                             "[rows, prefix, T] attention with beam indices (translate/translator.py:746,900-905) and "
+                             "returns no usable history; use -beam_size 1")
         if not fast:
             # object beam (translator.py:827-926): ranking by the GNMT global score (length penalty only)
             out = eng.decode_beam_object(self.beam_size, self.n_best, self.max_length, self.min_length,

@@ -58,9 +58,13 @@ def _tile(x, count, dim=0):
 
 
 def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0, n_best=1,
-              alpha=0.0, margins=None):
-    """translate/translator.py:619-825 (``--fast`` batched beam search, no attention return).
-    -> dict(predictions: list[B] of list[n_best] of LongTensor, scores: list[B] of list[float])
+              alpha=0.0, margins=None, return_attention=False, attn_rows_first=False):
+    """translate/translator.py:619-825 (``--fast`` batched beam search).
+    -> dict(predictions: list[B] of list[n_best] of LongTensor, scores: list[B] of list[float],
+            attention: list[B] of list[n_best] of [len, width] tensors when return_attention (:744-750, :776: the width
+            is ``memory_lengths[i]`` of the TILED length vector indexed by the chunk's position among the chunks still in
+            the batch -- i.e. the length of chunk alive[i // beam_size], the reference's own indexing).
+            ``attn_rows_first`` reads a decoder's attention as [1, rows, T] whatever its shape (diagnostics only)))
     ``margins`` (optional list, diagnostics only): filled with one float per chunk = the smallest gap, over all steps
     the chunk was alive, between two neighbouring candidates among the best beam_size + 1 of the step (the pruning
     boundary and the order of the kept beams).  A chunk whose margin is of the order of fp32 rounding (~1e-6) can take
@@ -79,12 +83,14 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
         alive_seq = torch.full([B * K, 1], BOS, dtype=torch.long)
         topk_log_probs = torch.tensor([0.0] + [float("-inf")] * (K - 1)).repeat(B)   # :691-693
         hypotheses = [[] for _ in range(B)]
-        results = {"predictions": [[] for _ in range(B)], "scores": [[] for _ in range(B)]}
+        results = {"predictions": [[] for _ in range(B)], "scores": [[] for _ in range(B)],
+                   "attention": [[] for _ in range(B)]}
+        alive_attn = None
 
         for step in range(max_length):
             decoder_input = alive_seq[:, -1].view(1, -1, 1)
-            log_probs, _ = _decode_and_generate(model, decoder_input, memory_bank,
-                                                memory_lengths, step)
+            log_probs, attn = _decode_and_generate(model, decoder_input, memory_bank,
+                                                   memory_lengths, step)
             V = log_probs.size(-1)
             if step < min_length:
                 log_probs[:, EOS] = -1e20                           # :714-715
@@ -108,6 +114,12 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
             select_indices = batch_index.view(-1)
             alive_seq = torch.cat([alive_seq.index_select(0, select_indices),
                                    topk_ids.view(-1, 1)], -1)       # :742-744
+            if return_attention:                                    # :744-750
+                if attn_rows_first:
+                    attn = attn.reshape(1, -1, attn.size(-1))
+                current_attn = attn.index_select(1, select_indices)
+                alive_attn = current_attn if alive_attn is None else \
+                    torch.cat([alive_attn.index_select(1, select_indices), current_attn], 0)
             is_finished = topk_ids.eq(EOS)
             if step + 1 == max_length:
                 is_finished.fill_(True)                             # :754-755
@@ -115,18 +127,23 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
                 topk_log_probs = topk_log_probs.masked_fill(is_finished, -1e10)   # :760
                 top_beam_finished |= is_finished[:, 0]
                 predictions = alive_seq.view(-1, K, alive_seq.size(-1))
+                attention = alive_attn.view(alive_attn.size(0), -1, K, alive_attn.size(-1)) \
+                    if alive_attn is not None else None             # :764-767
                 non_finished_batch = []
                 for i in range(is_finished.size(0)):
                     b = int(batch_offset[i])
                     for j in is_finished[i].nonzero().view(-1).tolist():
-                        hypotheses[b].append((topk_scores[i, j], predictions[i, j, 1:]))
+                        hypotheses[b].append((topk_scores[i, j], predictions[i, j, 1:],
+                                              attention[:, i, j, :memory_lengths[i]].clone()     # :776 (sic)
+                                              if attention is not None else None))
                     if top_beam_finished[i] and len(hypotheses[b]) >= n_best:   # :781
                         best = sorted(hypotheses[b], key=lambda x: x[0], reverse=True)
-                        for n, (score, pred) in enumerate(best):
+                        for n, (score, pred, hyp_attn) in enumerate(best):
                             if n >= n_best:
                                 break
                             results["scores"][b].append(float(score))
                             results["predictions"][b].append(pred.clone())
+                            results["attention"][b].append(hyp_attn if hyp_attn is not None else [])
                     else:
                         non_finished_batch.append(i)
                 non_finished = torch.tensor(non_finished_batch, dtype=torch.long)
@@ -138,6 +155,9 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
                 batch_index = batch_index.index_select(0, non_finished)
                 select_indices = batch_index.view(-1)
                 alive_seq = predictions.index_select(0, non_finished).view(-1, alive_seq.size(-1))
+                if alive_attn is not None:                          # :806-809
+                    alive_attn = attention.index_select(1, non_finished).view(alive_attn.size(0), -1,
+                                                                              alive_attn.size(-1))
             memory_bank = memory_bank.index_select(1, select_indices)           # :813-817
             memory_lengths = memory_lengths.index_select(0, select_indices)
             model.decoder.map_state(lambda s, dim: s.index_select(dim, select_indices))
@@ -145,7 +165,7 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
 
 
 def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length=0, n_best=1,
-                length_penalty="none", alpha=0.0):
+                length_penalty="none", alpha=0.0, return_attention=False):
     """translate/translator.py:827-926 (``_translate_batch``, the default when ``--fast`` is absent) with
     onmt/translate/beam.py:74-178 (``Beam.advance / done / sort_finished / get_hyp``) and the
     GNMTGlobalScorer of beam.py:181-208 with coverage penalty "none" (penalties.py:59-63), length penalty
@@ -174,13 +194,15 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
             next_ys[b][0][0] = BOS
         eos_top = [False] * B
         finished = [[] for _ in range(B)]
+        beam_attns = [[] for _ in range(B)]                          # Beam.attn (beam.py:135)
 
         for step in range(max_length):
             if all(eos_top[b] and len(finished[b]) >= n_best for b in range(B)):    # :883-884, beam.py:151-152
                 break
             inp = torch.stack([next_ys[b][-1] for b in range(B)]).view(1, -1, 1)
-            out, _ = _decode_and_generate(model, inp, memory_bank, memory_lengths, step)
+            out, step_attn = _decode_and_generate(model, inp, memory_bank, memory_lengths, step)
             out = out.view(B, K, -1)
+            step_attn = step_attn.view(B, K, -1)                    # :900
             select = []
             for b in range(B):
                 word_probs = out[b]
@@ -200,6 +222,8 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
                 prev_k = torch.div(best_id, V, rounding_mode="trunc")
                 prev_ks[b].append(prev_k)
                 next_ys[b].append(best_id - prev_k * V)
+                if return_attention:                                # :904-905 (memory_lengths is the TILED vector, sic)
+                    beam_attns[b].append(step_attn[b, :, :memory_lengths[b]].index_select(0, prev_k))
                 for i in range(K):                                  # :140-144
                     if next_ys[b][-1][i] == EOS:
                         s_i = global_score(scores[b], len(next_ys[b]))[i]
@@ -210,7 +234,7 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
             select = torch.cat(select)
             model.decoder.map_state(lambda s, dim: s.index_select(dim, select))      # :913-914
 
-        results = {"predictions": [], "scores": []}
+        results = {"predictions": [], "scores": [], "attention": []}
         for b in range(B):
             i = 0
             while len(finished[b]) < n_best:                        # sort_finished(minimum=n_best) :157-163
@@ -218,14 +242,18 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
                 finished[b].append((float(s_i), len(next_ys[b]) - 1, i))
                 i += 1
             finished[b].sort(key=lambda a: -a[0])                   # stable
-            hyps = []
+            hyps, atts = [], []
             for (sc, t, k) in finished[b][:n_best]:                 # get_hyp :170-178
-                hyp = []
+                hyp, att = [], []
                 for j in range(t - 1, -1, -1):
                     hyp.append(int(next_ys[b][j + 1][k]))
+                    if return_attention:
+                        att.append(beam_attns[b][j][k])
                     k = int(prev_ks[b][j][k])
                 hyps.append(torch.tensor(hyp[::-1], dtype=torch.long))
+                atts.append(torch.stack(att[::-1]) if att else [])
             results["predictions"].append(hyps)
+            results["attention"].append(atts)
             results["scores"].append([sc for sc, _, _ in finished[b][:n_best]])
         return results
 

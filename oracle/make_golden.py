@@ -306,6 +306,84 @@ def make_beam_case(fname, B=6, T=512, max_length=100, beam_size=5, seed=2025, wr
             beam_scores=ref_scores.numpy())
 
 
+BEAM_ATTN_CASES = {
+    # name -> (family, kwargs): the attention matrices the reference returns per hypothesis under -attn_debug
+    "beam_attn_l2t_d64": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2)),
+    "beam_attn_nano2rnn_d64": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2)),
+    # (not the CNN decoder: its attention comes back as [rows, prefix, T] (onmt/decoders/cnn_decoder.py:123-129), so
+    # the reference's --fast path indexes the PREFIX axis with beam indices (translator.py:746: out of bounds, or silently
+    # the wrong rows) and its object beam flattens prefix x T and keeps the first positions (:900-905): neither is an
+    # attention history one could be asked to match.  The Translator here refuses -attn_debug for that combination.)
+}
+
+
+def make_beam_attn_case(fname, B=5, T=96, max_length=12, min_length=5, beam_size=3, n_best=2, seed=2025, write=True):
+    """results["attention"] of _fast_translate_batch (translator.py:744-750,776,806-809) and of _translate_batch
+    (:899-905, beam.py:135,170-178) with attn_debug on RAGGED chunks: the reference cuts the rows at memory_lengths[i] of
+    the tiled length vector, i.e. at the length of chunk alive[i // beam_size]."""
+    family, kw = BEAM_ATTN_CASES[fname]
+    cfg = ModelConfig.family(family, **kw)
+    sd = synth.make_state_dict(cfg, seed=seed)
+    chunks, lengths = synth.make_chunks(B, T=T, seed=77, ragged=True, read_len=2)
+    lengths = torch.tensor([T, T - 7, T - 20, T - 33, T - 50][:B])          # all different: the widths are visible
+    chunks = chunks * (torch.arange(T)[None, :] < lengths[:, None])
+    src = chunks.t().contiguous().unsqueeze(2)
+    model, fields, mopt = refshim.build_reference_model(
+        family, d=cfg.d_model, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers, heads=cfg.heads, ff=cfg.d_ff,
+        extra=ref_extra(cfg))
+    load_into_reference(model, sd)
+    om = OracleModel(sd, cfg)
+    store = {}
+    for mode, fast in (("fast", True), ("obj", False)):
+        tr = refshim.build_reference_translator(model, fields, mopt, beam_size=beam_size, fast=fast,
+                                                max_length=max_length, min_length=min_length, n_best=n_best)
+        fn = odecode.beam_fast if fast else odecode.beam_object
+        ref_raises = False
+        try:
+            res = tr.translate_batch(refshim.FakeBatch(src.clone(), lengths.clone()), refshim.FakeData(), True, fast=fast)
+        except (RuntimeError, IndexError) as ex:
+            # --fast + -attn_debug with the Transformer decoder: attn is [rows, 1, T] and translator.py:746 indexes dim 1
+            assert fast, ex
+            ref_raises = True
+            try:
+                fn(om, src, lengths, beam_size=beam_size, max_length=max_length, min_length=min_length, n_best=n_best,
+                   return_attention=True)
+                raise AssertionError("the oracle should raise where the reference does")
+            except (RuntimeError, IndexError):
+                pass
+            print("%-24s %-4s the reference raises %s: golden from the oracle with attn read as [1, rows, T]" % (
+                fname, mode, type(ex).__name__))
+        store[mode + "_ref_raises"] = np.int32(ref_raises)
+        kw_o = dict(attn_rows_first=True) if (fast and ref_raises) else {}
+        o = fn(om, src, lengths, beam_size=beam_size, max_length=max_length, min_length=min_length, n_best=n_best,
+               return_attention=True, **kw_o)
+        if ref_raises:
+            res = {"predictions": [[h.tolist() for h in p] for p in o["predictions"]], "attention": o["attention"]}
+        ids = np.full((B, n_best, max_length), -1, dtype=np.int64)
+        attn = np.zeros((B, n_best, max_length, T), dtype=np.float32)
+        widths = np.zeros((B, n_best), dtype=np.int32)
+        err = 0.0
+        for b in range(B):
+            for n in range(n_best):
+                hyp = torch.tensor([int(t) for t in res["predictions"][b][n]], dtype=torch.long)
+                a = res["attention"][b][n]
+                assert a.dim() == 2 and a.size(0) == len(hyp), (a.shape, len(hyp))
+                assert torch.equal(o["predictions"][b][n], hyp), "oracle hypotheses differ from the reference"
+                assert tuple(o["attention"][b][n].shape) == tuple(a.shape), (o["attention"][b][n].shape, a.shape)
+                err = max(err, float((o["attention"][b][n] - a).abs().max()))
+                ids[b, n, : len(hyp)] = hyp.numpy()
+                attn[b, n, : a.size(0), : a.size(1)] = a.numpy()
+                widths[b, n] = a.size(1)
+        assert err < 2e-6, err
+        print("%-24s %-4s widths %s (lengths %s), hyp lengths %s, oracle-vs-ref attention %.1e" % (
+            fname, mode, widths.tolist(), lengths.tolist(), (ids >= 0).sum(2).tolist(), err))
+        store[mode + "_ids"], store[mode + "_attn"], store[mode + "_widths"] = ids, attn, widths
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, fname + ".npz"), family=family, cfg_json=np.array(repr(cfg.asdict())),
+                            weight_seed=seed, src=chunks.numpy(), lengths=lengths.numpy(), max_length=max_length,
+                            min_length=min_length, beam_size=beam_size, n_best=n_best, **store)
+
+
 def make_frontend_golden(write=True):
     """Front end: run the reference's extract_fast5_raw on '.signal' text files.
 
@@ -412,9 +490,14 @@ def main():
     ap.add_argument("--no-write", action="store_true")
     ap.add_argument("--B", type=int, default=6)
     ap.add_argument("--beam-cases", nargs="*", default=None, help="only the non-degenerate --fast beam cases named")
+    ap.add_argument("--beam-attn", action="store_true", help="only the beam attention cases")
     args = ap.parse_args()
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if args.beam_attn:
+        for name in BEAM_ATTN_CASES:
+            make_beam_attn_case(name, write=not args.no_write)
+        return
     if args.beam_cases is not None:
         for name in (args.beam_cases or list(BEAM_CASES)):
             make_beam_case(name, B=args.B, write=not args.no_write)
@@ -423,6 +506,8 @@ def main():
     make_assembly_golden(write=not args.no_write)
     for name in BEAM_CASES:
         make_beam_case(name, B=args.B, write=not args.no_write)
+    for name in BEAM_ATTN_CASES:
+        make_beam_attn_case(name, write=not args.no_write)
     for name in args.cases:
         B = args.B if "d512" not in name else 3
         make_case(name, B=B, write=not args.no_write)

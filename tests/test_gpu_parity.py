@@ -530,3 +530,80 @@ def test_two_devices_in_one_process():
             ids = eng.decode_greedy(L)["ids"]
             torch.cuda.synchronize(dev)
             np.testing.assert_array_equal(ids.cpu().numpy(), g["greedy_ids"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["beam_attn_l2t_d64", "beam_attn_nano2rnn_d64"])
+def test_beam_attention_matches_reference_golden(name):
+    """nd_beam_attention after nd_decode_beam / nd_decode_beam_object vs the attention matrices the unmodified
+    reference returns per hypothesis under -attn_debug, on ragged chunks: rows (one per decode step, found through the
+    hypothesis' ancestor table) and widths (the reference's memory_lengths[i] indexing of the tiled length vector)."""
+    import ast
+    import os
+    from helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    cfg = ModelConfig(**ast.literal_eval(str(g["cfg_json"])))
+    sd = synth.make_state_dict(cfg, seed=int(g["weight_seed"]))
+    src, lengths = torch.from_numpy(g["src"]), torch.from_numpy(g["lengths"])
+    B, T = src.shape
+    K, NB, L, ML = int(g["beam_size"]), int(g["n_best"]), int(g["max_length"]), int(g["min_length"])
+    eng = _engine(cfg, sd, B, T, L, K=K)
+    for mode in ("fast", "obj"):
+        eng.encode(src.cuda(), lengths.cuda())
+        out = (eng.decode_beam(K, NB, L, ML, return_attn=True) if mode == "fast"
+               else eng.decode_beam_object(K, NB, L, ML, return_attn=True))
+        torch.cuda.synchronize()
+        ids, lens = out["ids"].cpu().numpy(), out["lens"].cpu().numpy()
+        attn, widths = out["attn"].cpu().numpy(), out["attn_widths"].cpu().numpy()
+        np.testing.assert_array_equal(widths, g[mode + "_widths"])
+        for b in range(B):
+            for n in range(NB):
+                want = g[mode + "_ids"][b, n]
+                want = want[want >= 0]
+                np.testing.assert_array_equal(ids[b, n, : lens[b, n]], want)
+                w = int(widths[b, n])
+                np.testing.assert_allclose(attn[b, n, : len(want), :w], g[mode + "_attn"][b, n, : len(want), :w], atol=2e-5)
+                assert not attn[b, n, len(want):].any()                  # zero past the hypothesis
+    # the same decodes without the option: graphs back on, identical hypotheses
+    eng.encode(src.cuda(), lengths.cuda())
+    plain = eng.decode_beam(K, NB, L, ML)
+    assert plain["attn"] is None
+    np.testing.assert_array_equal(plain["ids"].cpu().numpy()[:, 0, :], np.where(g["fast_ids"][:, 0, :L] >= 0, g["fast_ids"][:, 0, :L], -1))
+
+
+@pytest.mark.gpu
+def test_attn_debug_with_beam_search_writes_one_block_per_chunk():
+    """Translator.translate(attn_debug=True) with --fast beam search: the block of the BEST hypothesis per chunk
+    (translate/translator.py:284-335 prints trans.attns[0]); the CNN decoder is refused (its beam attention in the
+    reference is not an attention history: see oracle/make_golden.py BEAM_ATTN_CASES)."""
+    import io
+    from nanodecoder_b200.checkpoint import Vocab
+    from nanodecoder_b200.engine import Engine
+    from nanodecoder_b200.opts import default_translate_opt
+    from nanodecoder_b200.translate.translator import Translator, _Field
+    cfg = ModelConfig.family("l2t", d_model=64, d_ff=128, enc_layers=2, dec_layers=2)
+    sd = synth.make_state_dict(cfg, seed=3)
+    L = 7
+    opt = default_translate_opt(beam_size=3, fast=True, batch_size=4, max_length=L, min_length=3, src_seq_length=40, gpu=0)
+    eng = Engine(cfg, sd, max_batch=4, max_src_len=40, max_tgt_len=L, max_beam=3)
+    tr = Translator(eng, {"tgt": _Field(Vocab(cfg.vocab))}, opt, cfg)
+    chunks, lengths = synth.make_chunks(6, T=40, seed=4, ragged=False)
+    buf = io.StringIO()
+    tr.setAttnFile(buf)
+    _, preds = tr.translate(src=(chunks, lengths), batch_size=4, attn_debug=True)
+    lines = buf.getvalue().splitlines()
+    heads = [k for k, ln in enumerate(lines) if ln.startswith("       > ")]
+    assert len(heads) == 6
+    for i, h in enumerate(heads):
+        assert lines[h].rstrip().endswith("</s>")
+        end = heads[i + 1] if i + 1 < 6 else len(lines)
+        rows = np.array([[float(x) for x in ln.split()] for ln in lines[h + 1: end]])
+        n_tok = len(preds[i][0].split())
+        # one row per decode step of the best hypothesis: its tokens + the </s> step (none if it ran into max_length)
+        assert rows.shape[0] in (n_tok, n_tok + 1) and rows.shape[0] <= L
+        assert rows.shape[1] == 40 and np.allclose(rows.sum(1), 1.0, atol=1e-4)
+    cfg2 = ModelConfig.family("cnn2cnn", d_model=64, enc_layers=2, dec_layers=2)
+    eng2 = Engine(cfg2, synth.make_state_dict(cfg2, seed=3), max_batch=4, max_src_len=40, max_tgt_len=L, max_beam=3)
+    tr2 = Translator(eng2, {"tgt": _Field(Vocab(cfg2.vocab))}, opt, cfg2)
+    with pytest.raises(ValueError, match="CNN decoder"):
+        tr2.translate(src=(chunks, lengths), batch_size=4, attn_debug=True)

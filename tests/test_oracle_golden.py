@@ -133,3 +133,33 @@ def test_nano_encoder_ignores_last_batchnorm_and_decoder_masks_value_one():
     one = s[:, :, 0].t().eq(1.0)                  # [B,T]
     assert one.any()
     assert float(attn[:, one].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name", ["beam_attn_l2t_d64", "beam_attn_nano2rnn_d64"])
+def test_oracle_beam_attention_matches_reference_golden(name):
+    """results["attention"] of both beam searches under -attn_debug (translator.py:744-750,776,806-809 and :899-905 +
+    beam.py:135,170-178), made by the unmodified reference on ragged chunks: one [len, width] matrix per hypothesis, the
+    width being memory_lengths[i] of the reference's TILED length vector."""
+    import os
+    from helpers import GOLDEN
+    import ast
+    from nanodecoder_b200 import synth
+    from nanodecoder_b200.config import ModelConfig
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    cfg = ModelConfig(**ast.literal_eval(str(g["cfg_json"])))
+    sd = synth.make_state_dict(cfg, seed=int(g["weight_seed"]))
+    src = torch.from_numpy(g["src"]).t().contiguous().unsqueeze(2)
+    lengths = torch.from_numpy(g["lengths"])
+    om = OracleModel(sd, cfg)
+    K, NB, L, ML = int(g["beam_size"]), int(g["n_best"]), int(g["max_length"]), int(g["min_length"])
+    for mode, fn in (("fast", odecode.beam_fast), ("obj", odecode.beam_object)):
+        o = fn(om, src, lengths, beam_size=K, max_length=L, min_length=ML, n_best=NB, return_attention=True)
+        for b in range(src.size(1)):
+            for n in range(NB):
+                want = g[mode + "_ids"][b, n]
+                want = want[want >= 0]
+                np.testing.assert_array_equal(o["predictions"][b][n].numpy(), want)
+                a = o["attention"][b][n]
+                w = int(g[mode + "_widths"][b, n])
+                assert tuple(a.shape) == (len(want), w)
+                np.testing.assert_allclose(a.numpy(), g[mode + "_attn"][b, n, : len(want), :w], atol=2e-6)

@@ -51,7 +51,7 @@ class RecordingEngine(object):
         ids = self._ids()
         return {"ids": torch.from_numpy(ids), "scores": torch.from_numpy(-ids.sum(1).astype(np.float32)), "attn": None}
 
-    def decode_beam(self, K, n_best, max_length, min_length=0, alpha=0.0):
+    def decode_beam(self, K, n_best, max_length, min_length=0, alpha=0.0, return_attn=False):
         ids = self._ids()
         B, L = ids.shape
         out = np.full((B, n_best, L), -1, dtype=np.int64)
