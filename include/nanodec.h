@@ -166,7 +166,8 @@ ND_EXPORT int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, in
  * finished) or max_len steps ran; finished hypotheses are ranked by the GNMT global score = beam score /
  * length penalty (length_penalty: 0 none, 1 wu ((5+len)^alpha / 6^alpha), 2 avg; penalties.py:65-88), stable in
  * arrival order; chunks with fewer than n_best finished hypotheses are topped up from the live beam
- * (beam.py:154-168).  Coverage penalty, stepwise penalty and n-gram blocking are not supported.
+ * (beam.py:154-168).  Coverage penalty and n-gram blocking: integer options "coverage_penalty", "block_ngram_repeat",
+ * "block_ngram_exclude" and the float option "beta"; the stepwise penalty is not supported.
  * Outputs as nd_decode_beam.                                                                                 */
 ND_EXPORT int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len,
                           int32_t min_len, int32_t length_penalty, float alpha, int64_t* out_ids,
@@ -248,10 +249,20 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *   "kv_beam_packed" (default 1): beam search reads the fixed-point planes as well (kv_mode 3 / 4; d = 256: the TMA-ring
  *                    kernel over the int16 + uint8 planes, 2 - 8 beams; d = 512: the multi-query slice kernel while the
  *                    beams' score rows fit two CTAs per SM); 0 = fp32 rows.
+ *   "block_ngram_repeat" (default 0): object beam: n > 0 gives a beam whose hypothesis repeats an n-gram -10e20
+ *                    children (beam.py:101-124);
+ *   "block_ngram_exclude" (default 0): bit v set = n-grams containing vocabulary id v are never blocked
+ *                    (-ignore_when_blocking);
+ *   "coverage_penalty" (default 0): object beam: 1 = wu, 2 = summary (penalties.py:39-57), weighted by the float
+ *                    option beta (nd_set_float) and subtracted from the global score of finished hypotheses
+ *                    (beam.py:203-216; with the length penalty "none" the reference subtracts it IN PLACE from the
+ *                    running scores -- reproduced);
  *   "beam_attention" (default 0): beam decodes keep the per-step attention of every beam row for nd_beam_attention
  *                    (runs the loop without CUDA graphs);
  * Any nd_set_int call drops the engine's captured CUDA graphs (they are re-captured on the following calls).  */
 ND_EXPORT int nd_set_int(nd_engine* e, const char* name, int64_t value);
+/* float options: "beta" (default 0): weight of the object beam's coverage penalty (GNMTGlobalScorer, beam.py:190-193). */
+ND_EXPORT int nd_set_float(nd_engine* e, const char* name, double value);
 
 /* per-kernel-category device timing for bench.py's roofline figures: while a category bit is set,
  * every launch of that category is bracketed by CUDA events on the launching stream;

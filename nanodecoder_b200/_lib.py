@@ -69,6 +69,7 @@ SIGNATURES = {
                                         _P, _P]),
     "nd_beam_attention": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     "nd_set_int": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "nd_set_float": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "nd_profile_enable": (C.c_int, [_P, C.c_uint32]),
     "nd_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "nd_launch_count": (C.c_int64, [_P]),

@@ -76,6 +76,31 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
   const int* anc_cur = p.st.anc + (int64_t)cur * rows * p.Lmax;
   int* anc_nxt = p.st.anc + (int64_t)nxt * rows * p.Lmax;
 
+  // object mode, n-gram blocking (beam.py:101-124): a beam whose hypothesis so far contains the same n-gram twice
+  // (n-grams touching an excluded token are neither recorded nor checked) has ALL its children set to -10e20
+  unsigned ngram_fail = 0;                             // bit k: beam k is blocked
+  if (obj && p.block_ngram > 0 && p.step > 0) {
+    const int n = p.block_ngram, len = p.step;         // hypothesis tokens: seq_cur[row][1 .. step]
+    for (int k = 0; k < K; ++k) {
+      const int* hyp = seq_cur + (int64_t)(b * K + k) * Lp1 + 1;
+      bool fail = false;
+      for (int i = n - 1 + lane; i < len && !fail; i += 32) {        // n-gram ending at i (full length only can repeat)
+        bool excl = false;
+        for (int q = 0; q < n; ++q) excl |= ((p.excl_mask >> hyp[i - q]) & 1u) != 0;
+        if (excl) continue;
+        for (int i1 = n - 1; i1 < i && !fail; ++i1) {
+          bool same = true, ex1 = false;
+          for (int q = 0; q < n; ++q) {
+            same &= hyp[i1 - q] == hyp[i - q];
+            ex1 |= ((p.excl_mask >> hyp[i1 - q]) & 1u) != 0;
+          }
+          fail = same && !ex1;
+        }
+      }
+      if (__any_sync(ND_FULL, fail)) ngram_fail |= 1u << k;
+    }
+  }
+
   // candidate scores: (log_probs + beam score) / length_penalty            translator.py:718-725
   float cand[kMaxCandPerLane];
   unsigned used = 0;
@@ -86,7 +111,10 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     if (c < NC) {
       const int k = c / V;
       const float lpv = p.logp[((int64_t)b * K + k) * V + (c - k * V)] + p.st.topk_log_probs[b * K + k];
-      if (obj) cand[i] = (p.step > 0 && p.st.cur_tok[b * K + k] == p.eos) ? -1e20f : lpv;   // beam.py:94-100
+      if (obj) {
+        cand[i] = (p.step > 0 && p.st.cur_tok[b * K + k] == p.eos) ? -1e20f : lpv;         // beam.py:94-100
+        if ((ngram_fail >> k) & 1u) cand[i] = -10e20f;                                      // beam.py:123-124
+      }
       else cand[i] = lpv / length_penalty;
     } else {
       used |= 1u << i;
@@ -136,6 +164,33 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
   }
   __syncwarp();
 
+  // object mode, coverage penalty (beam.py:229-243 update_global_state; penalties.py:39-57): coverage of new beam k =
+  // coverage of its parent + this step's attention of the parent row, over the columns the reference passes to
+  // Beam.advance (memory_lengths[j] of the TILED vector: translator.py:905); penalty = beta * (wu: -sum log min(cov, 1),
+  // summary: sum max(cov, 1) - width)
+  float my_pen = 0.f;                                  // lane k: penalty of new beam k
+  if (obj && p.cov_mode != 0) {
+    const int width = (int)p.mem_len[b / K];
+    const float* cov_cur = p.cov + (int64_t)cur * rows * p.Tp;
+    float* cov_nxt = p.cov + (int64_t)nxt * rows * p.Tp;
+    for (int k = 0; k < K; ++k) {
+      const int pr = __shfl_sync(ND_FULL, prow, k);
+      const float* a = p.attn_step + (int64_t)pr * p.Tp;
+      const float* cc = cov_cur + (int64_t)pr * p.Tp;
+      float* cn = cov_nxt + (int64_t)(b * K + k) * p.Tp;
+      float acc = 0.f;
+      for (int t = lane; t < width; t += 32) {
+        const float c = (p.step > 0 ? cc[t] : 0.f) + a[t];
+        cn[t] = c;
+        acc += p.cov_mode == 1 ? -logf(fminf(c, 1.0f)) : fmaxf(c, 1.0f);
+      }
+      acc = warp_sum(acc);
+      if (p.cov_mode == 2) acc -= (float)width;
+      if (lane == k) my_pen = p.beta * acc;
+    }
+    if (mine) p.cov_pen[nrow] = my_pen;
+  }
+
   if (fin_mask) {
     if (finished && !obj) new_lp = -1e10f;             // :760 (object mode keeps the score: beam.py:97-100 blocks the children)
     int top_fin = p.st.top_finished[b] | ((fin_mask & 1u) ? 1 : 0);            // :762
@@ -145,11 +200,24 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     int* hl = p.st.hyp_len + (int64_t)b * nb;
     int* hq = p.st.hyp_seq + (int64_t)b * nb * p.Lmax;
     int* ha = p.st.hyp_anc + (int64_t)b * nb * p.Lmax;
+    int* hm = p.st.hyp_meta + (int64_t)b * nb;
     const int len = p.step + 1;
+    // GNMTGlobalScorer.score with the length penalty "none" and a coverage penalty (beam.py:203-216): length_none
+    // returns the beam's score tensor ITSELF and `normalized_probs -= penalty` is in place, so each of the step's
+    // finished hypotheses lowers the RUNNING scores of all K beams by their coverage penalties -- and the scores stored
+    // in Beam.finished are views of that tensor, so every one of them reads the value after ALL of the step's calls
+    const bool alias_scores = obj && p.cov_mode != 0 && p.lp_mode == 0;
+    if (alias_scores)
+      for (int c = __popc(fin_mask); c > 0; --c) new_lp -= my_pen;
     for (int k = 0; k < K; ++k) {                      // finished beams in beam order (:773-778)
       if (!(fin_mask & (1u << k))) continue;
       float sc = __shfl_sync(ND_FULL, sel_score, k);
-      if (obj) sc = sc / length_penalty;               // global score (length penalty none / wu / avg)
+      const float pen_k = __shfl_sync(ND_FULL, my_pen, k);
+      if (alias_scores) {
+        sc = __shfl_sync(ND_FULL, new_lp, k);
+      } else if (obj) {
+        sc = sc / length_penalty - pen_k;              // global score: length penalty (a new tensor), then coverage
+      }
       ++n_hyp;
       // stable insertion into the best-n_best list (descending score, earlier first on ties)
       int pos = nb;
@@ -166,7 +234,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
             ha[i * p.Lmax + j] = ha[(i - 1) * p.Lmax + j];
           }
           __syncwarp();
-          if (lane == 0) { hs[i] = hs[i - 1]; hl[i] = hl[i - 1]; }
+          if (lane == 0) { hs[i] = hs[i - 1]; hl[i] = hl[i - 1]; hm[i] = hm[i - 1]; }
           __syncwarp();
         }
         const int nr = b * K + k;
@@ -174,7 +242,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
           hq[pos * p.Lmax + j] = seq_nxt[(int64_t)nr * Lp1 + 1 + j];
           ha[pos * p.Lmax + j] = anc_nxt[(int64_t)nr * p.Lmax + j];       // rows that ran steps 0 .. step
         }
-        if (lane == 0) { hs[pos] = sc; hl[pos] = len; }
+        if (lane == 0) { hs[pos] = sc; hl[pos] = len; hm[pos] = ((n_hyp - 1) << 8) | k; }
         __syncwarp();
       }
     }
@@ -217,29 +285,49 @@ __global__ void __launch_bounds__(32) beam_object_fill_kernel(BeamParams p, floa
   float* hs = p.st.hyp_score + (int64_t)b * nb;
   int* hl = p.st.hyp_len + (int64_t)b * nb;
   int* hq = p.st.hyp_seq + (int64_t)b * nb * p.Lmax;
-  for (int i = 0; n_hyp < nb && i < K; ++i, ++n_hyp) {
-    const float sc = p.st.topk_log_probs[b * K + i] / div;
-    int pos = nb;
-    for (int q = 0; q < nb; ++q) {
-      if (hl[q] == 0 || sc > hs[q]) { pos = q; break; }
-    }
+  int* hm = p.st.hyp_meta + (int64_t)b * nb;
+  const bool alias_scores = p.cov_mode != 0 && p.lp_mode == 0;
+  if (alias_scores) {
+    // the in-place subtraction of the coverage penalty (see beam_step_kernel) once per topped-up hypothesis; the views
+    // stored for hypotheses that finished at the LAST step point into the same tensor and move with it
+    const int m = min(nb - n_hyp, K);
+    if (lane < K)
+      for (int c = 0; c < m; ++c) p.st.topk_log_probs[b * K + lane] -= p.cov_pen[b * K + lane];
     __syncwarp();
-    if (pos < nb) {
-      for (int q = nb - 1; q > pos; --q) {
+    if (lane == 0)
+      for (int q = 0; q < n_hyp; ++q)
+        if (hl[q] == steps) hs[q] = p.st.topk_log_probs[b * K + (hm[q] & 255)];
+    __syncwarp();
+  }
+  for (int i = 0; n_hyp < nb && i < K; ++i, ++n_hyp) {
+    const float sc = alias_scores ? p.st.topk_log_probs[b * K + i]
+                                  : p.st.topk_log_probs[b * K + i] / div - (p.cov_mode != 0 ? p.cov_pen[b * K + i] : 0.f);
+    const int pos = n_hyp;                             // appended; the list is sorted below
+    for (int j = lane; j < steps; j += 32) {
+      hq[pos * p.Lmax + j] = seq[(int64_t)(b * K + i) * Lp1 + 1 + j];
+      ha[pos * p.Lmax + j] = anc[(int64_t)(b * K + i) * p.Lmax + j];
+    }
+    if (lane == 0) { hs[pos] = sc; hl[pos] = steps; hm[pos] = (n_hyp << 8) | i; }
+    __syncwarp();
+  }
+  // finished.sort(key=lambda a: -a[0]) (beam.py:165): descending score, stable in arrival order
+  for (int pass = 0; pass < n_hyp; ++pass) {
+    for (int q = 0; q + 1 < n_hyp - pass; ++q) {
+      const bool swap = hs[q + 1] > hs[q] || (hs[q + 1] == hs[q] && (hm[q + 1] >> 8) < (hm[q] >> 8));
+      __syncwarp();
+      if (swap) {
         for (int j = lane; j < p.Lmax; j += 32) {
-          hq[q * p.Lmax + j] = hq[(q - 1) * p.Lmax + j];
-          ha[q * p.Lmax + j] = ha[(q - 1) * p.Lmax + j];
+          const int t0 = hq[q * p.Lmax + j]; hq[q * p.Lmax + j] = hq[(q + 1) * p.Lmax + j]; hq[(q + 1) * p.Lmax + j] = t0;
+          const int t1 = ha[q * p.Lmax + j]; ha[q * p.Lmax + j] = ha[(q + 1) * p.Lmax + j]; ha[(q + 1) * p.Lmax + j] = t1;
         }
         __syncwarp();
-        if (lane == 0) { hs[q] = hs[q - 1]; hl[q] = hl[q - 1]; }
+        if (lane == 0) {
+          const float ts = hs[q]; hs[q] = hs[q + 1]; hs[q + 1] = ts;
+          const int tl = hl[q]; hl[q] = hl[q + 1]; hl[q + 1] = tl;
+          const int tm = hm[q]; hm[q] = hm[q + 1]; hm[q + 1] = tm;
+        }
         __syncwarp();
       }
-      for (int j = lane; j < steps; j += 32) {
-        hq[pos * p.Lmax + j] = seq[(int64_t)(b * K + i) * Lp1 + 1 + j];
-        ha[pos * p.Lmax + j] = anc[(int64_t)(b * K + i) * p.Lmax + j];
-      }
-      if (lane == 0) { hs[pos] = sc; hl[pos] = steps; }
-      __syncwarp();
     }
   }
   (void)gs_none;

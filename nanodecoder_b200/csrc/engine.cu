@@ -157,6 +157,9 @@ struct nd_engine {
   // KV_F32, KV_Q15M (reduced precision, half the bytes), others = cross-checks
   int kv_mode = KV_Q23M;
   int beam_n_best = 1, beam_K = 1, beam_mode = 0;   // of the last beam decode (layout of the hypothesis tables)
+  // object beam extras (options block_ngram_repeat / block_ngram_exclude / coverage_penalty, nd_set_float "beta")
+  int block_ngram = 0; unsigned excl_mask = 0; int cov_mode = 0; float beta = 0.f;
+  float* cov = nullptr; float* cov_pen = nullptr; float* cov_attn = nullptr;   // allocated on first use
   bool beam_attn = false;                  // option "beam_attention": beam decodes keep the per-step head-0 cross attention
   float* attn_hist = nullptr;              // [max_tgt_len][max_batch*max_beam][max_src_len], allocated on first use
   int attn_rows = 0, attn_Tp = 0, attn_steps = 0;   // geometry of the history the last beam decode wrote
@@ -842,11 +845,12 @@ int alloc_workspace(nd_engine* e) {
   b.hyp_len = dalloc<int>(e, B * K);
   b.hyp_seq = dalloc<int>(e, B * K * L);
   b.hyp_anc = dalloc<int>(e, B * K * L);
+  b.hyp_meta = dalloc<int>(e, B * K);
   b.n_alive = dalloc<int>(e, 1);
   b.n_done = dalloc<int>(e, 1);
   b.stop_step = dalloc<int>(e, 1);
   ok = ok && b.n_done && b.stop_step && e->lengths && e->mem_len && e->cur_tok && b.topk_log_probs && b.alive_seq && b.anc && b.parent &&
-       b.retired && b.top_finished && b.n_hyp && b.hyp_score && b.hyp_len && b.hyp_seq && b.hyp_anc && b.n_alive && b.retire_step;
+       b.retired && b.top_finished && b.n_hyp && b.hyp_score && b.hyp_len && b.hyp_seq && b.hyp_anc && b.hyp_meta && b.n_alive && b.retire_step;
   return ok ? ND_OK : ND_ERR_NOMEM;
 }
 
@@ -1347,6 +1351,19 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
     }
     e->attn_rows = B * K; e->attn_Tp = e->Tp; e->attn_steps = max_len;
   }
+  const bool cov_on = mode == 1 && e->cov_mode != 0;
+  if (mode == 1) { bp.block_ngram = e->block_ngram; bp.excl_mask = e->excl_mask; }
+  if (cov_on) {
+    const size_t n = (size_t)e->max_rows * e->cfg.max_src_len;
+    if (!e->cov) {
+      e->cov = dalloc<float>(e, 2 * n);
+      e->cov_pen = dalloc<float>(e, (size_t)e->max_rows);
+      e->cov_attn = dalloc<float>(e, n);
+      if (!e->cov || !e->cov_pen || !e->cov_attn) return fail(e, ND_ERR_NOMEM, "coverage penalty: no memory for the coverage vectors");
+    }
+    bp.cov_mode = e->cov_mode; bp.beta = e->beta; bp.cov = e->cov; bp.cov_pen = e->cov_pen;
+    bp.mem_len = e->mem_len; bp.Tp = e->Tp;
+  }
   NvtxRange nvtx(mode == 1 ? "nd:object beam decode loop" : "nd:fast beam decode loop");
   // object mode: stop_step / n_done are shared by all chunks (every Beam advances until ALL are done), so chunk
   // groups on independent streams would see the stop at different steps: one stream
@@ -1361,6 +1378,8 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
       DecodeCtx dc;
       dc.K = K; dc.Lmax = e->cfg.max_tgt_len; dc.beam = true; dc.step = step;
       if (e->beam_attn) dc.attn_out = e->attn_hist + (size_t)step * B * K * e->Tp;
+      else if (cov_on) dc.attn_out = e->cov_attn;
+      bp.attn_step = dc.attn_out;
       dc.c0 = (int)((int64_t)B * g / G);
       dc.nc = (int)((int64_t)B * (g + 1) / G) - dc.c0;
       GenParams gp;
@@ -1675,7 +1694,7 @@ static int decode_beam_any(nd_engine* e, int32_t beam_size, int32_t n_best, int3
   cudaStream_t st = (cudaStream_t)stream;
   const int B = e->B, K = beam_size;
   e->beam_n_best = n_best; e->beam_K = beam_size; e->beam_mode = mode;
-  if (e->prof_mask || !e->use_graphs || e->beam_attn)
+  if (e->prof_mask || !e->use_graphs || e->beam_attn || (mode == 1 && (e->block_ngram || e->cov_mode)))
     return beam_body(e, K, n_best, max_len, min_len, alpha, mode, lp_mode, out_ids, out_lens, out_scores, st);
   int32_t alpha_bits;
   memcpy(&alpha_bits, &alpha, sizeof(alpha_bits));
@@ -1756,6 +1775,20 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     e->beam_attn = value != 0;
     return ND_OK;
   }
+  if (strcmp(name, "block_ngram_repeat") == 0) {
+    if (value < 0 || value > 16) return fail(e, ND_ERR_INVALID, "block_ngram_repeat must be in [0, 16]");
+    e->block_ngram = (int)value;
+    return ND_OK;
+  }
+  if (strcmp(name, "block_ngram_exclude") == 0) {
+    e->excl_mask = (unsigned)value;
+    return ND_OK;
+  }
+  if (strcmp(name, "coverage_penalty") == 0) {
+    if (value < 0 || value > 2) return fail(e, ND_ERR_INVALID, "coverage_penalty must be 0 (none), 1 (wu) or 2 (summary)");
+    e->cov_mode = (int)value;
+    return ND_OK;
+  }
   if (strcmp(name, "cross_packed_fast") == 0) {   // process-wide
     cross_attention_packed_set_fast((int)value);
     return ND_OK;
@@ -1806,6 +1839,15 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
     return ND_OK;
   }
   return fail(e, ND_ERR_INVALID, std::string("unknown option '") + name + "'");
+}
+
+int nd_set_float(nd_engine* e, const char* name, double value) {
+  if (!e || !name) return ND_ERR_INVALID;
+  if (strcmp(name, "beta") == 0) {                // GNMTGlobalScorer beta (coverage penalty weight), object beam
+    e->beta = (float)value;
+    return ND_OK;
+  }
+  return fail(e, ND_ERR_INVALID, std::string("unknown float option ") + name);
 }
 
 int nd_debug_gemm_timeline(int64_t* dev_buf32) {

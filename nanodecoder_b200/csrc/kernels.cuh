@@ -180,6 +180,7 @@ struct BeamState {
   int* hyp_len = nullptr;                         // [B, n_best]
   int* hyp_seq = nullptr;                         // [B, n_best, Lmax]
   int* hyp_anc = nullptr;                         // [B, n_best, Lmax] row that ran step j of the hypothesis (ancestor table)
+  int* hyp_meta = nullptr;                        // [B, n_best] (arrival number << 8) | beam index of the hypothesis
   int* n_alive = nullptr;                         // [1] chunks not yet retired
   int* n_done = nullptr;                          // [1] object mode: chunks whose Beam.done() is true
   int* stop_step = nullptr;                       // [1] object mode: first step that is NOT executed any more
@@ -195,6 +196,16 @@ struct BeamParams {
   // = beam score / gs_div (length penalty none / wu / avg)
   int mode = 0;
   int lp_mode = 0;                                // 0 none, 1 wu, 2 avg
+  // object mode extras (onmt/translate/beam.py:101-124, penalties.py:39-57, beam.py:203-243):
+  int block_ngram = 0;                            // n > 0: a beam whose hypothesis repeats an n-gram gets -10e20 children
+  unsigned excl_mask = 0;                         // vocabulary ids (bit v) whose n-grams are never blocked
+  int cov_mode = 0;                               // coverage penalty: 0 none, 1 wu, 2 summary
+  float beta = 0.f;
+  const float* attn_step = nullptr;               // [B*K, Tp] this step's attention per row (cov_mode != 0)
+  float* cov = nullptr;                           // [2][B*K, Tp] coverage = sum of the attention along the hypothesis
+  float* cov_pen = nullptr;                       // [B*K] coverage penalty of the current beams
+  const int64_t* mem_len = nullptr;               // [B]
+  int Tp = 0;
 };
 cudaError_t beam_init(const BeamParams& p, int bos, cudaStream_t stream);
 cudaError_t beam_step(const BeamParams& p, cudaStream_t stream);

@@ -50,7 +50,8 @@ class _Data(object):
 
 class GNMTGlobalScorer(object):
     """alpha / beta / penalty names (onmt/translate/beam.py:181-242).  --fast only uses alpha; the object beam
-    ranks finished hypotheses with the length penalty (none | wu | avg); coverage penalties are unsupported."""
+    ranks finished hypotheses with the length penalty (none | wu | avg) and subtracts the coverage penalty (none | wu |
+    summary, weight beta)."""
 
     def __init__(self, opt):
         self.alpha = opt.alpha
@@ -124,10 +125,15 @@ class Translator(object):
         self.model_opt = model_opt
         if opt.random_sampling_topk != 1:
             raise ValueError("random sampling (topk != 1) is outside the supported translate path")
-        if opt.block_ngram_repeat != 0 or opt.dump_beam or opt.replace_unk:
-            raise ValueError("block_ngram_repeat / dump_beam / replace_unk are outside the supported translate path")
-        if self.beam_size > 1 and (self.global_scorer.beta != 0 or self.global_scorer.coverage_penalty != "none"):
-            raise ValueError("coverage penalty is outside the supported translate path")
+        if opt.dump_beam or opt.replace_unk:
+            raise ValueError("dump_beam / replace_unk are outside the supported translate path")
+        self.block_ngram_repeat = int(opt.block_ngram_repeat)
+        self.ignore_when_blocking = set(getattr(opt, "ignore_when_blocking", []) or [])
+        if self.block_ngram_repeat != 0 and (self.beam_size == 1 or self.fast):
+            # the reference asserts this in its greedy and --fast paths (translate/translator.py:411, 633)
+            raise ValueError("block_ngram_repeat is only implemented by the object beam search (no -fast, beam_size > 1)")
+        if self.global_scorer.coverage_penalty not in ("none", "wu", "summary"):
+            raise ValueError("unknown coverage penalty %r" % (self.global_scorer.coverage_penalty,))
         if self.beam_size > 1 and getattr(opt, "stepwise_penalty", False):
             raise ValueError("stepwise_penalty is outside the supported translate path")
 
@@ -238,6 +244,13 @@ class Translator(object):
         return all_scores, all_predictions
 
     # --------------------------------------------------------------------------------------
+    def _object_beam_extras(self):
+        """translator.py:836-848: n-gram blocking with its exclusion ids, GNMTGlobalScorer's coverage penalty"""
+        vocab = self.fields["tgt"].vocab
+        return dict(block_ngram_repeat=self.block_ngram_repeat,
+                    exclude_ids=[vocab.stoi[t] for t in self.ignore_when_blocking],
+                    coverage_penalty=self.global_scorer.coverage_penalty, beta=self.global_scorer.beta)
+
     def translate_batch(self, batch, data, attn_debug, fast=False):
         """translator.py:505-540.  batch.src [T,B,1] (any device), batch.src_lengths [B].
         -> {"predictions": [[LongTensor]*n_best]*B, "scores", "attention", "batch", "gold_score"}"""
@@ -265,7 +278,7 @@ class Translator(object):
             # object beam (translator.py:827-926): ranking by the GNMT global score (length penalty only)
             out = eng.decode_beam_object(self.beam_size, self.n_best, self.max_length, self.min_length,
                                          self.global_scorer.length_penalty, self.global_scorer.alpha,
-                                         return_attn=attn_debug)
+                                         return_attn=attn_debug, **self._object_beam_extras())
         else:
             out = eng.decode_beam(self.beam_size, self.n_best, self.max_length, self.min_length,
                                   self.global_scorer.alpha, return_attn=attn_debug)
@@ -297,7 +310,8 @@ class Translator(object):
                                       self.global_scorer.alpha)
             else:
                 out = eng.decode_beam_object(self.beam_size, self.n_best, self.max_length, self.min_length,
-                                             self.global_scorer.length_penalty, self.global_scorer.alpha)
+                                             self.global_scorer.length_penalty, self.global_scorer.alpha,
+                                             **self._object_beam_extras())
             dev_t = {"ids": out["ids"], "lens": out["lens"], "scores": out["scores"]}
         if not dev_t["ids"].is_cuda:
             # only reachable with the recording stub of tests/test_translator_host.py (host-logic tests without a GPU);

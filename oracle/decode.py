@@ -165,11 +165,13 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
 
 
 def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length=0, n_best=1,
-                length_penalty="none", alpha=0.0, return_attention=False):
+                length_penalty="none", alpha=0.0, return_attention=False, block_ngram_repeat=0,
+                exclusion_tokens=(), coverage_penalty="none", beta=0.0):
     """translate/translator.py:827-926 (``_translate_batch``, the default when ``--fast`` is absent) with
     onmt/translate/beam.py:74-178 (``Beam.advance / done / sort_finished / get_hyp``) and the
     GNMTGlobalScorer of beam.py:181-208 with coverage penalty "none" (penalties.py:59-63), length penalty
-    none / wu / avg (penalties.py:65-88), no stepwise penalty, no n-gram blocking.
+    none / wu / avg (penalties.py:65-88), coverage penalty none / wu / summary weighted by beta (penalties.py:39-57,
+    beam.py:203-243), n-gram blocking (beam.py:101-124); no stepwise penalty.
     -> dict(predictions: list[B] of list[n_best] of LongTensor, scores: list[B] of list[n_best] of float)"""
     with torch.no_grad():
         B, K = src.size(1), beam_size
@@ -179,12 +181,30 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
         memory_bank = _tile(memory_bank, K, 1)                      # :878
         memory_lengths = _tile(src_lengths, K)                      # :879
 
-        def global_score(scores, n_ys):                             # beam.py:200-208, penalties.py:65-88
+        coverage = [None] * B                                        # beam.global_state["coverage"] [K, width]
+
+        def cov_pen(cov):                                           # penalties.py:39-57
+            if coverage_penalty == "wu":
+                return beta * (-torch.min(cov, cov.clone().fill_(1.0)).log().sum(1))
+            if coverage_penalty == "summary":
+                return beta * (torch.max(cov, cov.clone().fill_(1.0)).sum(1) - cov.size(1))
+            return torch.zeros(cov.size(0))
+
+        def global_score(scores, n_ys, b=None):                     # beam.py:200-216, penalties.py:65-94
             if length_penalty == "wu":
-                return scores / (((5 + n_ys) ** alpha) / ((5 + 1) ** alpha))
-            if length_penalty == "avg":
-                return scores / n_ys
-            return scores
+                out = scores / (((5 + n_ys) ** alpha) / ((5 + 1) ** alpha))
+            elif length_penalty == "avg":
+                out = scores / n_ys
+            else:
+                out = scores                                        # length_none returns ITS ARGUMENT (penalties.py:90-94)
+            if b is not None and coverage_penalty != "none":
+                # beam.py:214 `normalized_probs -= penalty` is IN PLACE: with the length penalty "none" it subtracts the
+                # coverage penalty from the beam's RUNNING scores, once per call (= once per finished hypothesis, and once
+                # per hypothesis topped up by sort_finished), and the search goes on from the lowered scores
+                out.sub_(cov_pen(coverage[b]))
+            return out
+        exclusion = set(int(t) for t in exclusion_tokens)
+        track_attn = return_attention or coverage_penalty != "none"
 
         # per chunk Beam state (beam.py:20-60)
         scores = [torch.zeros(K) for _ in range(B)]
@@ -215,6 +235,24 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
                     for i in range(K):                              # "Don't let EOS have children" :97-100
                         if next_ys[b][-1][i] == EOS:
                             beam_scores[i] = -1e20
+                    if block_ngram_repeat > 0:                      # :101-124
+                        le = len(next_ys[b])
+                        for j in range(K):
+                            hyp, kk = [], j                         # get_hyp(le - 1, j)
+                            for q in range(le - 2, -1, -1):
+                                hyp.append(int(next_ys[b][q + 1][kk]))
+                                kk = int(prev_ks[b][q][kk])
+                            hyp = hyp[::-1]
+                            ngrams, fail, gram = set(), False, []
+                            for i in range(le - 1):
+                                gram = (gram + [hyp[i]])[-block_ngram_repeat:]
+                                if set(gram) & exclusion:
+                                    continue
+                                if tuple(gram) in ngrams:
+                                    fail = True
+                                ngrams.add(tuple(gram))
+                            if fail:
+                                beam_scores[j] = -10e20
                 else:
                     beam_scores = word_probs[0]
                 best_scores, best_id = beam_scores.reshape(-1).topk(K, 0, True, True)
@@ -222,12 +260,16 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
                 prev_k = torch.div(best_id, V, rounding_mode="trunc")
                 prev_ks[b].append(prev_k)
                 next_ys[b].append(best_id - prev_k * V)
-                if return_attention:                                # :904-905 (memory_lengths is the TILED vector, sic)
+                if track_attn:                                      # :904-905 (memory_lengths is the TILED vector, sic)
                     beam_attns[b].append(step_attn[b, :, :memory_lengths[b]].index_select(0, prev_k))
+                    if len(prev_ks[b]) == 1:                        # update_global_state, beam.py:229-243
+                        coverage[b] = beam_attns[b][-1]
+                    else:
+                        coverage[b] = coverage[b].index_select(0, prev_k).add(beam_attns[b][-1])
                 for i in range(K):                                  # :140-144
                     if next_ys[b][-1][i] == EOS:
-                        s_i = global_score(scores[b], len(next_ys[b]))[i]
-                        finished[b].append((float(s_i), len(next_ys[b]) - 1, i))
+                        s_i = global_score(scores[b], len(next_ys[b]), b)[i]     # a VIEW, like the reference's
+                        finished[b].append((s_i, len(next_ys[b]) - 1, i))
                 if next_ys[b][-1][0] == EOS:                        # :147-149
                     eos_top[b] = True
                 select.append(prev_k + b * K)
@@ -238,9 +280,10 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
         for b in range(B):
             i = 0
             while len(finished[b]) < n_best:                        # sort_finished(minimum=n_best) :157-163
-                s_i = global_score(scores[b], len(next_ys[b]))[i]
-                finished[b].append((float(s_i), len(next_ys[b]) - 1, i))
+                s_i = global_score(scores[b], len(next_ys[b]), b)[i]
+                finished[b].append((s_i, len(next_ys[b]) - 1, i))
                 i += 1
+            finished[b] = [(float(sc), t, k) for sc, t, k in finished[b]]      # the views are read here, after all calls
             finished[b].sort(key=lambda a: -a[0])                   # stable
             hyps, atts = [], []
             for (sc, t, k) in finished[b][:n_best]:                 # get_hyp :170-178

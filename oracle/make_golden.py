@@ -384,6 +384,80 @@ def make_beam_attn_case(fname, B=5, T=96, max_length=12, min_length=5, beam_size
                             min_length=min_length, beam_size=beam_size, n_best=n_best, **store)
 
 
+OBJ_EXTRA_CASES = {
+    # name -> (family, kwargs, ragged, reference flags, oracle kwargs): the object beam's optional scoring rules
+    "objx_l2t_d64_ngram3": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2), True,
+                            ["-block_ngram_repeat", "3"], dict(block_ngram_repeat=3)),
+    "objx_l2t_d64_ngram3_ignoreA": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2), True,
+                                    ["-block_ngram_repeat", "3", "-ignore_when_blocking", "A"],
+                                    dict(block_ngram_repeat=3, exclusion_tokens=(4,))),
+    # (wu takes log(min(coverage, 1)): a source position no beam ever attended gives -inf, which ragged chunks hit at
+    # once through the reference's tiled-length widths, so the wu cases use full chunks)
+    "objx_l2t_d64_covwu": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2), False,
+                           ["-coverage_penalty", "wu", "-beta", "0.4", "-length_penalty", "wu", "-alpha", "0.5"],
+                           dict(coverage_penalty="wu", beta=0.4, length_penalty="wu", alpha=0.5)),
+    "objx_nano2rnn_d64_covsummary": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2), True,
+                                     ["-coverage_penalty", "summary", "-beta", "0.3"],
+                                     dict(coverage_penalty="summary", beta=0.3)),
+    "objx_nano2rnn_d64_covwu": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2), False,
+                                ["-coverage_penalty", "wu", "-beta", "0.2", "-block_ngram_repeat", "5"],
+                                dict(coverage_penalty="wu", beta=0.2, block_ngram_repeat=5)),
+}
+
+
+def make_obj_extras_case(fname, B=5, T=96, max_length=16, min_length=12, beam_size=4, n_best=2, seed=2025, write=True):
+    """_translate_batch + Beam.advance with n-gram blocking (beam.py:101-124) / GNMTGlobalScorer with a coverage penalty
+    (beam.py:203-243, penalties.py:39-57), run by the unmodified reference."""
+    family, kw, ragged, flags, okw = OBJ_EXTRA_CASES[fname]
+    cfg = ModelConfig.family(family, **kw)
+    sd = synth.make_state_dict(cfg, seed=seed)
+    chunks, lengths = synth.make_chunks(B, T=T, seed=78, ragged=False)
+    if okw.get("coverage_penalty") == "wu":
+        # a key the decoder masks (signal value == 1.0, decoder/transformer.py:219-221) is never attended: coverage 0,
+        # log 0 = -inf, every score -inf.  That is the reference's behaviour, but a golden of -inf pins nothing.
+        chunks = torch.where(chunks == 1.0, torch.full_like(chunks, 1.0 + 1.0 / 64), chunks)
+    if ragged:
+        lengths = torch.tensor([T, T - 7, T - 20, T - 33, T - 50][:B])
+        chunks = chunks * (torch.arange(T)[None, :] < lengths[:, None])
+    src = chunks.t().contiguous().unsqueeze(2)
+    model, fields, mopt = refshim.build_reference_model(
+        family, d=cfg.d_model, enc_layers=cfg.enc_layers, dec_layers=cfg.dec_layers, heads=cfg.heads, ff=cfg.d_ff,
+        extra=ref_extra(cfg))
+    load_into_reference(model, sd)
+    tr = refshim.build_reference_translator(model, fields, mopt, beam_size=beam_size, fast=False, max_length=max_length,
+                                            min_length=min_length, n_best=n_best, extra=flags)
+    res = tr.translate_batch(refshim.FakeBatch(src.clone(), lengths.clone()), refshim.FakeData(), False, fast=False)
+    plain = refshim.build_reference_translator(model, fields, mopt, beam_size=beam_size, fast=False,
+                                               max_length=max_length, min_length=min_length, n_best=n_best,
+                                               extra=[f for f in flags if False])
+    res0 = plain.translate_batch(refshim.FakeBatch(src.clone(), lengths.clone()), refshim.FakeData(), False, fast=False)
+    o = odecode.beam_object(OracleModel(sd, cfg), src, lengths, beam_size=beam_size, max_length=max_length,
+                            min_length=min_length, n_best=n_best, **okw)
+    ids = np.full((B, n_best, max_length), -1, dtype=np.int64)
+    scores = np.zeros((B, n_best), dtype=np.float32)
+    changed = 0
+    for b in range(B):
+        for n in range(n_best):
+            hyp = [int(t) for t in res["predictions"][b][n]]
+            assert o["predictions"][b][n].tolist() == hyp, ("oracle hypotheses differ from the reference", b, n,
+                                                             o["predictions"][b][n].tolist(), hyp)
+            assert np.isfinite(float(res["scores"][b][n])), (b, n, float(res["scores"][b][n]))
+            assert abs(float(o["scores"][b][n]) - float(res["scores"][b][n])) < 1e-3 * max(1.0, abs(float(res["scores"][b][n]))), \
+                (b, n, float(o["scores"][b][n]), float(res["scores"][b][n]))
+            ids[b, n, : len(hyp)] = hyp
+            scores[b, n] = float(res["scores"][b][n])
+            changed += hyp != [int(t) for t in res0["predictions"][b][n]] or \
+                abs(float(res["scores"][b][n]) - float(res0["scores"][b][n])) > 1e-4
+    print("%-30s %d of %d hypotheses / scores differ from the plain object beam; scores %s" % (
+        fname, changed, B * n_best, np.round(scores, 3).tolist()))
+    assert changed > 0, "the option did not change anything: pick another case"
+    if write:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, fname + ".npz"), family=family, cfg_json=np.array(repr(cfg.asdict())),
+                            weight_seed=seed, src=chunks.numpy(), lengths=lengths.numpy(), max_length=max_length,
+                            min_length=min_length, beam_size=beam_size, n_best=n_best, ids=ids, scores=scores,
+                            okw=np.array(repr(okw)))
+
+
 def make_frontend_golden(write=True):
     """Front end: run the reference's extract_fast5_raw on '.signal' text files.
 
@@ -497,6 +571,8 @@ def main():
     if args.beam_attn:
         for name in BEAM_ATTN_CASES:
             make_beam_attn_case(name, write=not args.no_write)
+        for name in OBJ_EXTRA_CASES:
+            make_obj_extras_case(name, write=not args.no_write)
         return
     if args.beam_cases is not None:
         for name in (args.beam_cases or list(BEAM_CASES)):
@@ -508,6 +584,8 @@ def main():
         make_beam_case(name, B=args.B, write=not args.no_write)
     for name in BEAM_ATTN_CASES:
         make_beam_attn_case(name, write=not args.no_write)
+    for name in OBJ_EXTRA_CASES:
+        make_obj_extras_case(name, write=not args.no_write)
     for name in args.cases:
         B = args.B if "d512" not in name else 3
         make_case(name, B=B, write=not args.no_write)

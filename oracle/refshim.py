@@ -255,7 +255,7 @@ def build_reference_model(family, **kw):
 
 
 def build_reference_translator(model, fields, model_opt, beam_size=1, fast=False, max_length=100,
-                               min_length=0, n_best=1, alpha=0.0):
+                               min_length=0, n_best=1, alpha=0.0, extra=()):
     install()
     import configargparse
     import models.opts as opts
@@ -269,6 +269,7 @@ def build_reference_translator(model, fields, model_opt, beam_size=1, fast=False
             "-n_best", str(n_best), "-alpha", str(alpha)]
     if fast:
         argv.append("-fast")
+    argv += list(extra)
     topt = parser.parse_args(argv)
     topt.data_type = "nano"
     scorer = onmt.translate.GNMTGlobalScorer(topt)

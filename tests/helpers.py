@@ -60,3 +60,14 @@ def check_beam_against_golden(g, ids, lens, scores, atol=5e-3, tie=1e-3):
     np.testing.assert_allclose(scores[:, :NB], g["beam_scores"], atol=atol)
     assert swaps <= max(1, (B * NB) // 10), "%d of %d hypotheses are tie swaps" % (swaps, B * NB)
     return swaps
+
+
+OBJ_EXTRA_CASES = ["objx_l2t_d64_ngram3", "objx_l2t_d64_ngram3_ignoreA", "objx_l2t_d64_covwu", "objx_nano2rnn_d64_covsummary", "objx_nano2rnn_d64_covwu"]
+
+
+def load_case_npz(name):
+    """goldens that carry their own inputs (beam_attn_*, objx_*): -> (g, cfg, sd, src [B,T], lengths)"""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    cfg = ModelConfig(**ast.literal_eval(str(g["cfg_json"])))
+    sd = synth.make_state_dict(cfg, seed=int(g["weight_seed"]))
+    return g, cfg, sd, torch.from_numpy(g["src"]), torch.from_numpy(g["lengths"])

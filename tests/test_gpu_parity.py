@@ -607,3 +607,36 @@ def test_attn_debug_with_beam_search_writes_one_block_per_chunk():
     tr2 = Translator(eng2, {"tgt": _Field(Vocab(cfg2.vocab))}, opt, cfg2)
     with pytest.raises(ValueError, match="CNN decoder"):
         tr2.translate(src=(chunks, lengths), batch_size=4, attn_debug=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["objx_l2t_d64_ngram3", "objx_l2t_d64_ngram3_ignoreA", "objx_l2t_d64_covwu",
+                                  "objx_nano2rnn_d64_covsummary", "objx_nano2rnn_d64_covwu"])
+def test_object_beam_extras_match_reference_golden(name):
+    """nd_decode_beam_object with the options block_ngram_repeat / block_ngram_exclude / coverage_penalty / beta vs the
+    unmodified reference's _translate_batch with -block_ngram_repeat, -ignore_when_blocking, -coverage_penalty, -beta
+    (goldens: oracle/make_golden.py OBJ_EXTRA_CASES), incl. the in-place score update the reference performs when the
+    length penalty is "none"."""
+    import ast
+    from helpers import load_case_npz
+    g, cfg, sd, src, lengths = load_case_npz(name)
+    okw = ast.literal_eval(str(g["okw"]))
+    B, T = src.shape
+    K, NB, L, ML = int(g["beam_size"]), int(g["n_best"]), int(g["max_length"]), int(g["min_length"])
+    eng = _engine(cfg, sd, B, T, L, K=K)
+    eng.encode(src.cuda(), lengths.cuda())
+    out = eng.decode_beam_object(K, NB, L, ML, length_penalty=okw.get("length_penalty", "none"), alpha=okw.get("alpha", 0.0),
+                                 block_ngram_repeat=okw.get("block_ngram_repeat", 0),
+                                 exclude_ids=okw.get("exclusion_tokens", ()),
+                                 coverage_penalty=okw.get("coverage_penalty", "none"), beta=okw.get("beta", 0.0))
+    torch.cuda.synchronize()
+    ids, lens, scores = out["ids"].cpu().numpy(), out["lens"].cpu().numpy(), out["scores"].cpu().numpy()
+    for b in range(B):
+        for n in range(NB):
+            want = g["ids"][b, n]
+            np.testing.assert_array_equal(ids[b, n, : lens[b, n]], want[want >= 0])
+    np.testing.assert_allclose(scores, g["scores"], rtol=2e-3)
+    # and the plain object beam afterwards: the options are per call, not sticky
+    eng.encode(src.cuda(), lengths.cuda())
+    plain = eng.decode_beam_object(K, NB, L, ML)
+    assert not np.array_equal(plain["scores"].cpu().numpy(), scores)

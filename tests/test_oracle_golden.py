@@ -163,3 +163,22 @@ def test_oracle_beam_attention_matches_reference_golden(name):
                 w = int(g[mode + "_widths"][b, n])
                 assert tuple(a.shape) == (len(want), w)
                 np.testing.assert_allclose(a.numpy(), g[mode + "_attn"][b, n, : len(want), :w], atol=2e-6)
+
+
+def test_oracle_object_beam_extras_match_reference_golden():
+    """n-gram blocking (beam.py:101-124, incl. -ignore_when_blocking) and the coverage penalties of GNMTGlobalScorer
+    (beam.py:203-243, penalties.py:39-57) -- incl. what the length penalty "none" makes of them: `normalized_probs -=
+    penalty` runs IN PLACE on the beam's running scores and Beam.finished keeps views of them."""
+    import ast
+    from helpers import OBJ_EXTRA_CASES, load_case_npz
+    for name in OBJ_EXTRA_CASES:
+        g, cfg, sd, src, lengths = load_case_npz(name)
+        okw = ast.literal_eval(str(g["okw"]))
+        o = odecode.beam_object(OracleModel(sd, cfg), src.t().contiguous().unsqueeze(2), lengths,
+                                beam_size=int(g["beam_size"]), max_length=int(g["max_length"]),
+                                min_length=int(g["min_length"]), n_best=int(g["n_best"]), **okw)
+        for b in range(src.size(0)):
+            for n in range(int(g["n_best"])):
+                want = g["ids"][b, n]
+                np.testing.assert_array_equal(o["predictions"][b][n].numpy(), want[want >= 0], err_msg=name)
+        np.testing.assert_allclose(np.array(o["scores"], dtype=np.float32), g["scores"], rtol=1e-3, err_msg=name)
