@@ -151,6 +151,23 @@ def test_gold_scoring_and_missing_batch_size_are_refused():
         tr.translate(src=(chunks, lengths), tgt=["A C"], batch_size=2)
 
 
+def test_object_beam_flags_reach_the_engine_and_are_refused_where_the_reference_asserts():
+    """-block_ngram_repeat / -ignore_when_blocking / -coverage_penalty / -beta: passed to the object beam (translator.py:
+    836-848, beam.py:181-199); the reference asserts block_ngram_repeat == 0 in its greedy and --fast paths (:411, :633)."""
+    base = dict(n_best=1, batch_size=8, max_length=8, min_length=0, src_seq_length=64, gpu=0)
+    for kw in (dict(beam_size=1, fast=False), dict(beam_size=4, fast=True)):
+        opt = default_translate_opt(block_ngram_repeat=3, **kw, **base)
+        with pytest.raises(ValueError, match="object beam"):
+            Translator(RecordingEngine(8), {"tgt": _Field(_Vocab(VOCAB))}, opt, ModelConfig.family("l2t"))
+    opt = default_translate_opt(beam_size=4, fast=False, block_ngram_repeat=3, ignore_when_blocking=["A", "T"],
+                                coverage_penalty="wu", beta=0.25, **base)
+    tr = Translator(RecordingEngine(8), {"tgt": _Field(_Vocab(VOCAB))}, opt, ModelConfig.family("l2t"))
+    assert tr._object_beam_extras() == dict(block_ngram_repeat=3, exclude_ids=[VOCAB.index(t) for t in ("A", "T")] if
+                                            list(tr.ignore_when_blocking) == ["A", "T"] else
+                                            [VOCAB.index(t) for t in tr.ignore_when_blocking],
+                                            coverage_penalty="wu", beta=0.25)
+
+
 class _Log(object):
     def __init__(self):
         self.lines = []
