@@ -167,7 +167,7 @@ ND_EXPORT int nd_decode_beam(nd_engine* e, int32_t beam_size, int32_t n_best, in
  * length penalty (length_penalty: 0 none, 1 wu ((5+len)^alpha / 6^alpha), 2 avg; penalties.py:65-88), stable in
  * arrival order; chunks with fewer than n_best finished hypotheses are topped up from the live beam
  * (beam.py:154-168).  Coverage penalty and n-gram blocking: integer options "coverage_penalty", "block_ngram_repeat",
- * "block_ngram_exclude" and the float option "beta"; the stepwise penalty is not supported.
+ * "block_ngram_exclude", "stepwise_penalty" and the float option "beta".
  * Outputs as nd_decode_beam.                                                                                 */
 ND_EXPORT int nd_decode_beam_object(nd_engine* e, int32_t beam_size, int32_t n_best, int32_t max_len,
                           int32_t min_len, int32_t length_penalty, float alpha, int64_t* out_ids,
@@ -257,6 +257,8 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *                    option beta (nd_set_float) and subtracted from the global score of finished hypotheses
  *                    (beam.py:203-216; with the length penalty "none" the reference subtracts it IN PLACE from the
  *                    running scores -- reproduced);
+ *   "stepwise_penalty" (default 0): object beam: the coverage penalty is applied to the running scores at every step
+ *                    (GNMTGlobalScorer.update_score, beam.py:218-227) instead of to finished hypotheses;
  *   "beam_attention" (default 0): beam decodes keep the per-step attention of every beam row for nd_beam_attention
  *                    (runs the loop without CUDA graphs);
  * Any nd_set_int call drops the engine's captured CUDA graphs (they are re-captured on the following calls).  */

@@ -101,6 +101,29 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     }
   }
 
+  // object mode, stepwise coverage penalty (GNMTGlobalScorer.update_score, beam.py:218-227, called first thing in
+  // Beam.advance): scores += prev_penalty; scores -= penalty(coverage + this step's attention), in the beams' current order
+  __shared__ float base_s[4][32];
+  float* base = base_s[threadIdx.x >> 5];
+  if (lane < K) base[lane] = p.st.topk_log_probs[b * K + lane];
+  if (obj && p.stepwise && p.cov_mode != 0 && p.step > 0) {
+    const int width = (int)p.mem_len[b / K];
+    const float* cov_cur = p.cov + (int64_t)cur * rows * p.Tp;
+    for (int k = 0; k < K; ++k) {
+      const float* a = p.attn_step + (int64_t)(b * K + k) * p.Tp;
+      const float* cc = cov_cur + (int64_t)(b * K + k) * p.Tp;
+      float acc = 0.f;
+      for (int t = lane; t < width; t += 32) {
+        const float c = cc[t] + a[t];
+        acc += p.cov_mode == 1 ? -logf(fminf(c, 1.0f)) : fmaxf(c, 1.0f);
+      }
+      acc = warp_sum(acc);
+      if (p.cov_mode == 2) acc -= (float)width;
+      if (lane == k) base[k] = (base[k] + p.cov_pen[b * K + k]) - p.beta * acc;
+    }
+  }
+  __syncwarp();
+
   // candidate scores: (log_probs + beam score) / length_penalty            translator.py:718-725
   float cand[kMaxCandPerLane];
   unsigned used = 0;
@@ -110,7 +133,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     cand[i] = -INFINITY;
     if (c < NC) {
       const int k = c / V;
-      const float lpv = p.logp[((int64_t)b * K + k) * V + (c - k * V)] + p.st.topk_log_probs[b * K + k];
+      const float lpv = p.logp[((int64_t)b * K + k) * V + (c - k * V)] + base[k];
       if (obj) {
         cand[i] = (p.step > 0 && p.st.cur_tok[b * K + k] == p.eos) ? -1e20f : lpv;         // beam.py:94-100
         if ((ngram_fail >> k) & 1u) cand[i] = -10e20f;                                      // beam.py:123-124
@@ -188,7 +211,9 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
       if (p.cov_mode == 2) acc -= (float)width;
       if (lane == k) my_pen = p.beta * acc;
     }
-    if (mine) p.cov_pen[nrow] = my_pen;
+    // (stepwise mode reads this back as global_state["prev_penalty"], which the FIRST update_global_state sets to zero:
+    // beam.py:231-232)
+    if (mine) p.cov_pen[nrow] = (p.stepwise && p.step == 0) ? 0.f : my_pen;
   }
 
   if (fin_mask) {
@@ -206,7 +231,7 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
     // returns the beam's score tensor ITSELF and `normalized_probs -= penalty` is in place, so each of the step's
     // finished hypotheses lowers the RUNNING scores of all K beams by their coverage penalties -- and the scores stored
     // in Beam.finished are views of that tensor, so every one of them reads the value after ALL of the step's calls
-    const bool alias_scores = obj && p.cov_mode != 0 && p.lp_mode == 0;
+    const bool alias_scores = obj && p.cov_mode != 0 && p.lp_mode == 0 && !p.stepwise;
     if (alias_scores)
       for (int c = __popc(fin_mask); c > 0; --c) new_lp -= my_pen;
     for (int k = 0; k < K; ++k) {                      // finished beams in beam order (:773-778)
@@ -216,7 +241,8 @@ __global__ void __launch_bounds__(128) beam_step_kernel(BeamParams p, float leng
       if (alias_scores) {
         sc = __shfl_sync(ND_FULL, new_lp, k);
       } else if (obj) {
-        sc = sc / length_penalty - pen_k;              // global score: length penalty (a new tensor), then coverage
+        // global score: length penalty (a new tensor), then coverage -- unless the penalty already steered the search
+        sc = p.stepwise ? sc / length_penalty : sc / length_penalty - pen_k;
       }
       ++n_hyp;
       // stable insertion into the best-n_best list (descending score, earlier first on ties)
@@ -286,7 +312,7 @@ __global__ void __launch_bounds__(32) beam_object_fill_kernel(BeamParams p, floa
   int* hl = p.st.hyp_len + (int64_t)b * nb;
   int* hq = p.st.hyp_seq + (int64_t)b * nb * p.Lmax;
   int* hm = p.st.hyp_meta + (int64_t)b * nb;
-  const bool alias_scores = p.cov_mode != 0 && p.lp_mode == 0;
+  const bool alias_scores = p.cov_mode != 0 && p.lp_mode == 0 && !p.stepwise;
   if (alias_scores) {
     // the in-place subtraction of the coverage penalty (see beam_step_kernel) once per topped-up hypothesis; the views
     // stored for hypotheses that finished at the LAST step point into the same tensor and move with it
@@ -301,7 +327,8 @@ __global__ void __launch_bounds__(32) beam_object_fill_kernel(BeamParams p, floa
   }
   for (int i = 0; n_hyp < nb && i < K; ++i, ++n_hyp) {
     const float sc = alias_scores ? p.st.topk_log_probs[b * K + i]
-                                  : p.st.topk_log_probs[b * K + i] / div - (p.cov_mode != 0 ? p.cov_pen[b * K + i] : 0.f);
+                                  : p.st.topk_log_probs[b * K + i] / div -
+                                        ((p.cov_mode != 0 && !p.stepwise) ? p.cov_pen[b * K + i] : 0.f);
     const int pos = n_hyp;                             // appended; the list is sorted below
     for (int j = lane; j < steps; j += 32) {
       hq[pos * p.Lmax + j] = seq[(int64_t)(b * K + i) * Lp1 + 1 + j];

@@ -158,7 +158,7 @@ struct nd_engine {
   int kv_mode = KV_Q23M;
   int beam_n_best = 1, beam_K = 1, beam_mode = 0;   // of the last beam decode (layout of the hypothesis tables)
   // object beam extras (options block_ngram_repeat / block_ngram_exclude / coverage_penalty, nd_set_float "beta")
-  int block_ngram = 0; unsigned excl_mask = 0; int cov_mode = 0; float beta = 0.f;
+  int block_ngram = 0; unsigned excl_mask = 0; int cov_mode = 0; float beta = 0.f; int stepwise = 0;
   float* cov = nullptr; float* cov_pen = nullptr; float* cov_attn = nullptr;   // allocated on first use
   bool beam_attn = false;                  // option "beam_attention": beam decodes keep the per-step head-0 cross attention
   float* attn_hist = nullptr;              // [max_tgt_len][max_batch*max_beam][max_src_len], allocated on first use
@@ -1361,7 +1361,7 @@ int beam_body(nd_engine* e, int K, int n_best, int max_len, int min_len, float a
       e->cov_attn = dalloc<float>(e, n);
       if (!e->cov || !e->cov_pen || !e->cov_attn) return fail(e, ND_ERR_NOMEM, "coverage penalty: no memory for the coverage vectors");
     }
-    bp.cov_mode = e->cov_mode; bp.beta = e->beta; bp.cov = e->cov; bp.cov_pen = e->cov_pen;
+    bp.cov_mode = e->cov_mode; bp.beta = e->beta; bp.cov = e->cov; bp.cov_pen = e->cov_pen; bp.stepwise = e->stepwise;
     bp.mem_len = e->mem_len; bp.Tp = e->Tp;
   }
   NvtxRange nvtx(mode == 1 ? "nd:object beam decode loop" : "nd:fast beam decode loop");
@@ -1782,6 +1782,10 @@ int nd_set_int(nd_engine* e, const char* name, int64_t value) {
   }
   if (strcmp(name, "block_ngram_exclude") == 0) {
     e->excl_mask = (unsigned)value;
+    return ND_OK;
+  }
+  if (strcmp(name, "stepwise_penalty") == 0) {
+    e->stepwise = value != 0;
     return ND_OK;
   }
   if (strcmp(name, "coverage_penalty") == 0) {

@@ -200,6 +200,7 @@ struct BeamParams {
   int block_ngram = 0;                            // n > 0: a beam whose hypothesis repeats an n-gram gets -10e20 children
   unsigned excl_mask = 0;                         // vocabulary ids (bit v) whose n-grams are never blocked
   int cov_mode = 0;                               // coverage penalty: 0 none, 1 wu, 2 summary
+  int stepwise = 0;                               // -stepwise_penalty: the penalty steers the search (beam.py:87-88,218-227)
   float beta = 0.f;
   const float* attn_step = nullptr;               // [B*K, Tp] this step's attention per row (cov_mode != 0)
   float* cov = nullptr;                           // [2][B*K, Tp] coverage = sum of the attention along the hypothesis

@@ -179,28 +179,29 @@ class Engine(object):
 
     COVERAGE_PENALTY = {"none": 0, "wu": 1, "summary": 2}
 
-    def _object_beam_options(self, block_ngram_repeat, exclude_ids, coverage_penalty, beta):
+    def _object_beam_options(self, block_ngram_repeat, exclude_ids, coverage_penalty, beta, stepwise_penalty=False):
         """engine options of the object beam's extras; only touched when they change (they drop the captured graphs)"""
         mask = 0
         for v in exclude_ids:
             mask |= 1 << int(v)
-        want = (int(block_ngram_repeat), mask, self.COVERAGE_PENALTY[coverage_penalty], float(beta))
-        if want != getattr(self, "_obj_opts", (0, 0, 0, 0.0)):
+        want = (int(block_ngram_repeat), mask, self.COVERAGE_PENALTY[coverage_penalty], float(beta), int(bool(stepwise_penalty)))
+        if want != getattr(self, "_obj_opts", (0, 0, 0, 0.0, 0)):
             self.set_option("block_ngram_repeat", want[0])
             self.set_option("block_ngram_exclude", want[1])
             self.set_option("coverage_penalty", want[2])
             self._check(self.lib.nd_set_float(self._h, b"beta", want[3]))
+            self.set_option("stepwise_penalty", want[4])
             self._obj_opts = want
 
     def decode_beam_object(self, beam_size: int = 5, n_best: int = 1, max_len: int = 100, min_len: int = 0,
                            length_penalty: str = "none", alpha: float = 0.0, return_attn: bool = False,
                            block_ngram_repeat: int = 0, exclude_ids=(), coverage_penalty: str = "none",
-                           beta: float = 0.0):
+                           beta: float = 0.0, stepwise_penalty: bool = False):
         """Object beam search (the reference's default without --fast).  Same outputs as decode_beam.
         block_ngram_repeat / exclude_ids: onmt/translate/beam.py:101-124; coverage_penalty (none | wu | summary) with
         weight beta: penalties.py:39-57, beam.py:203-243."""
         self._want_beam_attention(return_attn)
-        self._object_beam_options(block_ngram_repeat, exclude_ids, coverage_penalty, beta)
+        self._object_beam_options(block_ngram_repeat, exclude_ids, coverage_penalty, beta, stepwise_penalty)
         B = self._B
         ids = torch.empty((B, n_best, max_len), dtype=torch.int64, device=self.device)
         lens = torch.empty((B, n_best), dtype=torch.int32, device=self.device)

@@ -134,8 +134,7 @@ class Translator(object):
             raise ValueError("block_ngram_repeat is only implemented by the object beam search (no -fast, beam_size > 1)")
         if self.global_scorer.coverage_penalty not in ("none", "wu", "summary"):
             raise ValueError("unknown coverage penalty %r" % (self.global_scorer.coverage_penalty,))
-        if self.beam_size > 1 and getattr(opt, "stepwise_penalty", False):
-            raise ValueError("stepwise_penalty is outside the supported translate path")
+        self.stepwise_penalty = bool(getattr(opt, "stepwise_penalty", False))
 
     @classmethod
     def from_state(cls, cfg, state_dict, vocab, opt, report_score=False, logger=None):
@@ -249,7 +248,8 @@ class Translator(object):
         vocab = self.fields["tgt"].vocab
         return dict(block_ngram_repeat=self.block_ngram_repeat,
                     exclude_ids=[vocab.stoi[t] for t in self.ignore_when_blocking],
-                    coverage_penalty=self.global_scorer.coverage_penalty, beta=self.global_scorer.beta)
+                    coverage_penalty=self.global_scorer.coverage_penalty, beta=self.global_scorer.beta,
+                    stepwise_penalty=self.stepwise_penalty)
 
     def translate_batch(self, batch, data, attn_debug, fast=False):
         """translator.py:505-540.  batch.src [T,B,1] (any device), batch.src_lengths [B].

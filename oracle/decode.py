@@ -166,7 +166,7 @@ def beam_fast(model, src, src_lengths, beam_size=5, max_length=100, min_length=0
 
 def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length=0, n_best=1,
                 length_penalty="none", alpha=0.0, return_attention=False, block_ngram_repeat=0,
-                exclusion_tokens=(), coverage_penalty="none", beta=0.0):
+                exclusion_tokens=(), coverage_penalty="none", beta=0.0, stepwise_penalty=False):
     """translate/translator.py:827-926 (``_translate_batch``, the default when ``--fast`` is absent) with
     onmt/translate/beam.py:74-178 (``Beam.advance / done / sort_finished / get_hyp``) and the
     GNMTGlobalScorer of beam.py:181-208 with coverage penalty "none" (penalties.py:59-63), length penalty
@@ -197,7 +197,7 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
                 out = scores / n_ys
             else:
                 out = scores                                        # length_none returns ITS ARGUMENT (penalties.py:90-94)
-            if b is not None and coverage_penalty != "none":
+            if b is not None and coverage_penalty != "none" and not stepwise_penalty:     # beam.py:208
                 # beam.py:214 `normalized_probs -= penalty` is IN PLACE: with the length penalty "none" it subtracts the
                 # coverage penalty from the beam's RUNNING scores, once per call (= once per finished hypothesis, and once
                 # per hypothesis topped up by sort_finished), and the search goes on from the lowered scores
@@ -205,6 +205,7 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
             return out
         exclusion = set(int(t) for t in exclusion_tokens)
         track_attn = return_attention or coverage_penalty != "none"
+        prev_penalty = [None] * B                                    # beam.global_state["prev_penalty"]
 
         # per chunk Beam state (beam.py:20-60)
         scores = [torch.zeros(K) for _ in range(B)]
@@ -227,6 +228,10 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
             for b in range(B):
                 word_probs = out[b]
                 V = word_probs.size(1)
+                if stepwise_penalty and prev_penalty[b] is not None:                # beam.py:87-88, 218-227 update_score
+                    scores[b].add_(prev_penalty[b])
+                    scores[b].sub_(cov_pen(coverage[b] + step_attn[b, :, :memory_lengths[b]])
+                                   if coverage_penalty != "none" else torch.zeros(K))
                 cur_len = len(next_ys[b])
                 if cur_len < min_length:                            # beam.py:89-92
                     word_probs[:, EOS] = -1e20
@@ -264,8 +269,10 @@ def beam_object(model, src, src_lengths, beam_size=5, max_length=100, min_length
                     beam_attns[b].append(step_attn[b, :, :memory_lengths[b]].index_select(0, prev_k))
                     if len(prev_ks[b]) == 1:                        # update_global_state, beam.py:229-243
                         coverage[b] = beam_attns[b][-1]
+                        prev_penalty[b] = torch.zeros(K)
                     else:
                         coverage[b] = coverage[b].index_select(0, prev_k).add(beam_attns[b][-1])
+                        prev_penalty[b] = cov_pen(coverage[b]) if coverage_penalty != "none" else torch.zeros(K)
                 for i in range(K):                                  # :140-144
                     if next_ys[b][-1][i] == EOS:
                         s_i = global_score(scores[b], len(next_ys[b]), b)[i]     # a VIEW, like the reference's

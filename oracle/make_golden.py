@@ -399,6 +399,14 @@ OBJ_EXTRA_CASES = {
     "objx_nano2rnn_d64_covsummary": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2), True,
                                      ["-coverage_penalty", "summary", "-beta", "0.3"],
                                      dict(coverage_penalty="summary", beta=0.3)),
+    "objx_l2t_d64_stepwise_wu": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2), False,
+                                 ["-stepwise_penalty", "-coverage_penalty", "wu", "-beta", "0.3"],
+                                 dict(coverage_penalty="wu", beta=0.3, stepwise_penalty=True)),
+    "objx_nano2rnn_d64_stepwise_summary": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2), True,
+                                           ["-stepwise_penalty", "-coverage_penalty", "summary", "-beta", "0.5",
+                                            "-length_penalty", "avg"],
+                                           dict(coverage_penalty="summary", beta=0.5, stepwise_penalty=True,
+                                                length_penalty="avg")),
     "objx_nano2rnn_d64_covwu": ("nano2rnn", dict(d_model=64, enc_layers=2, dec_layers=2), False,
                                 ["-coverage_penalty", "wu", "-beta", "0.2", "-block_ngram_repeat", "5"],
                                 dict(coverage_penalty="wu", beta=0.2, block_ngram_repeat=5)),

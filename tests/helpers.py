@@ -62,7 +62,8 @@ def check_beam_against_golden(g, ids, lens, scores, atol=5e-3, tie=1e-3):
     return swaps
 
 
-OBJ_EXTRA_CASES = ["objx_l2t_d64_ngram3", "objx_l2t_d64_ngram3_ignoreA", "objx_l2t_d64_covwu", "objx_nano2rnn_d64_covsummary", "objx_nano2rnn_d64_covwu"]
+OBJ_EXTRA_CASES = ["objx_l2t_d64_ngram3", "objx_l2t_d64_ngram3_ignoreA", "objx_l2t_d64_covwu", "objx_nano2rnn_d64_covsummary", "objx_nano2rnn_d64_covwu", "objx_l2t_d64_stepwise_wu",
+                                  "objx_nano2rnn_d64_stepwise_summary"]
 
 
 def load_case_npz(name):

@@ -611,7 +611,8 @@ def test_attn_debug_with_beam_search_writes_one_block_per_chunk():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["objx_l2t_d64_ngram3", "objx_l2t_d64_ngram3_ignoreA", "objx_l2t_d64_covwu",
-                                  "objx_nano2rnn_d64_covsummary", "objx_nano2rnn_d64_covwu"])
+                                  "objx_nano2rnn_d64_covsummary", "objx_nano2rnn_d64_covwu", "objx_l2t_d64_stepwise_wu",
+                                  "objx_nano2rnn_d64_stepwise_summary"])
 def test_object_beam_extras_match_reference_golden(name):
     """nd_decode_beam_object with the options block_ngram_repeat / block_ngram_exclude / coverage_penalty / beta vs the
     unmodified reference's _translate_batch with -block_ngram_repeat, -ignore_when_blocking, -coverage_penalty, -beta
@@ -628,7 +629,8 @@ def test_object_beam_extras_match_reference_golden(name):
     out = eng.decode_beam_object(K, NB, L, ML, length_penalty=okw.get("length_penalty", "none"), alpha=okw.get("alpha", 0.0),
                                  block_ngram_repeat=okw.get("block_ngram_repeat", 0),
                                  exclude_ids=okw.get("exclusion_tokens", ()),
-                                 coverage_penalty=okw.get("coverage_penalty", "none"), beta=okw.get("beta", 0.0))
+                                 coverage_penalty=okw.get("coverage_penalty", "none"), beta=okw.get("beta", 0.0),
+                                 stepwise_penalty=okw.get("stepwise_penalty", False))
     torch.cuda.synchronize()
     ids, lens, scores = out["ids"].cpu().numpy(), out["lens"].cpu().numpy(), out["scores"].cpu().numpy()
     for b in range(B):

@@ -165,7 +165,7 @@ def test_object_beam_flags_reach_the_engine_and_are_refused_where_the_reference_
     assert tr._object_beam_extras() == dict(block_ngram_repeat=3, exclude_ids=[VOCAB.index(t) for t in ("A", "T")] if
                                             list(tr.ignore_when_blocking) == ["A", "T"] else
                                             [VOCAB.index(t) for t in tr.ignore_when_blocking],
-                                            coverage_penalty="wu", beta=0.25)
+                                            coverage_penalty="wu", beta=0.25, stepwise_penalty=False)
 
 
 class _Log(object):
