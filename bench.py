@@ -82,9 +82,10 @@ class Workload(object):
         return cfg, synth.make_state_dict(cfg, seed=2025)
 
     def kv_packed(self, kv):
-        """The engine's rule (engine.cu decoder_init): Transformer decoders keep the memory keys / values in fixed point
-        for greedy decode and, at d = 256 / 512 with 8 heads, for beam search too (kv_beam_packed, default on)."""
-        return self.roof_cat == "cross_attn" and kv != "f32"
+        """The engine's rule (engine.cu decoder_init): every decoder keeps what its attention re-reads at each step in
+        fixed point -- the Transformer decoder's memory keys / values (greedy, and beam search at d = 256 / 512), the RNN
+        decoder's uh | H, the CNN decoder's encoder top | combined state."""
+        return kv != "f32"        # round 2: the RNN decoder's (uh | H) and the CNN decoder's (keys | values) as well
 
     def config(self, n_gpus, kv):
         return {"workload": self.name, "baseline_config": self.baseline_cfg, "model": self.desc,
@@ -309,7 +310,10 @@ def roofline_entry(wl, cfg, kv, prof, prof_ms, n_prof_steps):
     # memory position + query in and context out per row; the beams of a chunk share the K/V pass
     bytes_per_launch = B * (2 * T * d * bpe + (2 * T * 4 if packed else 0) + 2 * K * d * 4)
     achieved = bytes_per_launch / (ms_cat / max(n_cat, 1) * 1e-3) / 1e9 if n_cat else None
-    if wl.roof_cat == "mlp_attn":
+    if wl.roof_cat == "mlp_attn" and packed:
+        kname = "mlp_attn_packed_kernel<%d,%d,%s> (decode global / conv attention over fixed-point planes)" % (
+            d // 32, 1 if K == 1 else 8, kv)
+    elif wl.roof_cat == "mlp_attn":
         kname = "mlp_attn_kernel<%d,1> (decode global / conv attention, fp32)" % (d // 32)
     elif packed and K > 1:
         kname = ("cross_attn_ring_kernel<%d,%d,%s>" % ((4, 2, kv) if K <= 4 else (5, 2, kv) if K == 5 else (8, 1, kv))

@@ -245,7 +245,9 @@ ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32
  *                    sequences and identity rates to fp32 storage, profiles/r02_identity_rates.md);
  *                    4 = 15-bit fixed point (2 bytes per element; the reduced-precision mode, never the default);
  *                    5 = the top 24 bits of the fp32 value; 1 / 2 = 24 / 16-bit fixed point decoded with conversion
- *                    instructions (cross-checks);
+ *                    instructions (cross-checks).  Modes 3 / 4 also apply to what the other decoders' attention
+ *                    re-reads at every step: the RNN decoder's uh | H (global_attention.py:123-136) and the CNN
+ *                    decoder's encoder top | combined state (conv_multi_step_attention.py:38-82; always 3 bytes);
  *   "kv_beam_packed" (default 1): beam search reads the fixed-point planes as well (kv_mode 3 / 4; d = 256: the TMA-ring
  *                    kernel over the int16 + uint8 planes, 2 - 8 beams; d = 512: the multi-query slice kernel while the
  *                    beams' score rows fit two CTAs per SM); 0 = fp32 rows.

@@ -1129,6 +1129,7 @@ cudaError_t launch_mlp(const MlpAttnParams& p, cudaStream_t stream) {
 
 cudaError_t mlp_attention(const MlpAttnParams& p, cudaStream_t stream) {
   if (p.n_chunks <= 0) return cudaSuccess;
+  if (p.kv_fmt != KV_F32) return mlp_attention_packed(p, stream);
   if (p.d % 32 || p.NQ > 8 || p.NQ < 1) return cudaErrorInvalidValue;
   switch (p.d / 32) {
     case 1: return launch_mlp<1>(p, stream);

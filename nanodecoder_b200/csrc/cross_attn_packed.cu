@@ -776,7 +776,8 @@ __device__ __forceinline__ void store_bytes(uint8_t* p, const uint32_t* r) {
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ kv, int64_t rows, int fmt,
+__global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ kmat, int64_t ldk,
+                                                      const float* __restrict__ vmat, int64_t ldv, int64_t rows, int fmt,
                                                       int16_t* __restrict__ hi, uint8_t* __restrict__ lo,
                                                       float* __restrict__ scale) {
   constexpr int d = 32 * VPL;
@@ -785,7 +786,7 @@ __global__ void __launch_bounds__(256) kv_pack_kernel(const float* __restrict__ 
   if (item >= rows * 2) return;
   const int64_t row = item >> 1;
   const int part = (int)(item & 1);
-  const float* src = kv + row * (2 * d) + part * d + lane * VPL;
+  const float* src = (part ? vmat + row * ldv : kmat + row * ldk) + lane * VPL;
   float x[VPL];
   if constexpr (VPL % 4 == 0) {
 #pragma unroll
@@ -868,18 +869,205 @@ bool cross_attention_packed_mq_supported(const CrossAttnParams& p) {
 
 bool kv_pack_supported(int d) { return d == 64 || d == 128 || d == 256 || d == 512; }
 
-cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
-                    cudaStream_t stream) {
+cudaError_t kv_pack2(const float* k, int64_t ldk, const float* v, int64_t ldv, int64_t rows, int d, int fmt, int16_t* hi,
+                     uint8_t* lo, float* scale, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   if (!kv_pack_supported(d) || fmt < KV_Q24 || fmt > KV_FP24 || (fmt_has_lo(fmt) && !lo)) return cudaErrorInvalidValue;
+  if ((ldk & 3) || (ldv & 3) || (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15))
+    return cudaErrorInvalidValue;
   const unsigned grid = (unsigned)cdiv64(rows * 2, 8);
   switch (d / 32) {
-    case 2: kv_pack_kernel<2><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
-    case 4: kv_pack_kernel<4><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
-    case 8: kv_pack_kernel<8><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
-    default: kv_pack_kernel<16><<<grid, 256, 0, stream>>>(kv, rows, fmt, hi, lo, scale); break;
+    case 2: kv_pack_kernel<2><<<grid, 256, 0, stream>>>(k, ldk, v, ldv, rows, fmt, hi, lo, scale); break;
+    case 4: kv_pack_kernel<4><<<grid, 256, 0, stream>>>(k, ldk, v, ldv, rows, fmt, hi, lo, scale); break;
+    case 8: kv_pack_kernel<8><<<grid, 256, 0, stream>>>(k, ldk, v, ldv, rows, fmt, hi, lo, scale); break;
+    default: kv_pack_kernel<16><<<grid, 256, 0, stream>>>(k, ldk, v, ldv, rows, fmt, hi, lo, scale); break;
   }
   return cudaGetLastError();
+}
+
+cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
+                    cudaStream_t stream) {
+  return kv_pack2(kv, 2 * (int64_t)d, kv + d, 2 * (int64_t)d, rows, d, fmt, hi, lo, scale, stream);
+}
+
+// =============================================================================================
+// Global attention of the RNN decoder (onmt/modules/global_attention.py:95-227; mlp: score = v . tanh(wq + uh),
+// general / dot: score = q . H) and the conv attention of the CNN decoder (conv_multi_step_attention.py:38-82) over
+// fixed-point planes: the same kernel shape as mlp_attn_kernel (attention.cu), rows decoded from int16 + uint8 planes.
+// The key step cannot leave the tanh, but it costs nothing: tanh(fma(m, step, wq)) replaces tanh(wq + uh), and
+// m * step is exact (power-of-two step).  The value step multiplies the probability once per row.
+__device__ __forceinline__ float tanh_fast_p(float x) {          // 1 - 2 / (e^(2x) + 1), as attention.cu's tanh_fast
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
+// (one query: 4 rows in flight and 64 registers, 4 CTAs per SM -- the first version, 8 rows / 106 registers / 2 CTAs, ran
+// at 44 % issue-active with 23 % of the warp slots filled and LOST to fp32 rows: 207 vs 181 us)
+template <int VPL, int NQMAX, int FMT>
+__global__ void __launch_bounds__(kThreads, (NQMAX == 1 && VPL <= 8) ? 4 : 1) mlp_attn_packed_kernel(MlpAttnParams p) {
+  constexpr int R = 4;                             // rows in flight per warp iteration
+  extern __shared__ __align__(16) float smem_f[];
+  const int chunk = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (p.retired && p.retired[chunk]) return;
+  constexpr int d = 32 * VPL;
+  const int T = p.T, NQ = p.NQ;
+  float* q_s = smem_f;                            // [NQ][d]
+  float* sc = q_s + NQ * d;                       // [NQ][T]  (later red[warps][NQ*d])
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NQ * d; i += kThreads) q_s[i] = p.wq[((int64_t)chunk * NQ + i / d) * d + (i % d)];
+  float vreg[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) vreg[i] = p.dot ? 0.f : p.v[lane * VPL + i];
+  __syncthreads();
+  const int len = p.lengths ? (int)p.lengths[chunk] : T;
+  const int64_t row0 = (int64_t)chunk * T;
+  const uint32_t hi_pitch = 4u * d, lo_pitch = 2u * d;
+  const uint8_t* hiK = reinterpret_cast<const uint8_t*>(p.kv_hi) + row0 * hi_pitch + lane * (2 * VPL);
+  const uint8_t* loK = reinterpret_cast<const uint8_t*>(p.kv_lo) + row0 * lo_pitch + lane * VPL;
+  const float* stp = p.kv_scale + row0 * 2;
+
+  // ---------------- scores
+  for (int t0 = warp * R; t0 < T; t0 += kWarps * R) {
+    RowRegs<VPL, FMT> rr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (t0 + r < T) rr[r].load(hiK + (uint32_t)(t0 + r) * hi_pitch, loK + (uint32_t)(t0 + r) * lo_pitch);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = t0 + r;
+      if (t < T) {
+        const float ks = __ldg(stp + 2 * t);
+        float u[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) u[i] = rr[r].get(i);
+#pragma unroll
+        for (int qi = 0; qi < NQMAX; ++qi) {
+          if (qi < NQ) {
+            const float* qq = q_s + qi * d + lane * VPL;
+            float s = 0.f;
+            if (p.dot) {
+#pragma unroll
+              for (int i = 0; i < VPL; ++i) s = fmaf(qq[i], u[i], s);
+              s *= ks;
+            } else {
+#pragma unroll
+              for (int i = 0; i < VPL; ++i) s = fmaf(vreg[i], tanh_fast_p(fmaf(u[i], ks, qq[i])), s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) sc[qi * T + t] = (t < len) ? s : -INFINITY;     // sequence_mask, -inf
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- softmax (the probability leaves with the value step folded in)
+  for (int row = warp; row < NQ; row += kWarps) {
+    float* s = sc + row * T;
+    float m = -FLT_MAX;
+    for (int t = lane; t < T; t += 32) m = fmaxf(m, s[t]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int t = lane; t < T; t += 32) { const float e = expf(s[t] - m); s[t] = e; sum += e; }
+    sum = warp_sum(sum);
+    float* a = p.attn ? p.attn + ((int64_t)chunk * NQ + row) * T : nullptr;
+    for (int t = lane; t < T; t += 32) {
+      const float pr = s[t] / sum;
+      if (a) a[t] = pr;
+      s[t] = pr * __ldg(stp + 2 * t + 1);
+    }
+  }
+  __syncthreads();
+  // ---------------- context
+  float acc[NQMAX][VPL];
+#pragma unroll
+  for (int qi = 0; qi < NQMAX; ++qi)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[qi][i] = 0.f;
+  const int tmax = len < T ? len : T;             // weights beyond the length are exactly 0
+  const uint8_t* hiV = hiK + 2 * d;
+  const uint8_t* loV = loK + d;
+  for (int t0 = warp * R; t0 < tmax; t0 += kWarps * R) {
+    RowRegs<VPL, FMT> rr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (t0 + r < tmax) rr[r].load(hiV + (uint32_t)(t0 + r) * hi_pitch, loV + (uint32_t)(t0 + r) * lo_pitch);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = t0 + r;
+      if (t < tmax) {
+        float vf[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) vf[i] = rr[r].get(i);
+#pragma unroll
+        for (int qi = 0; qi < NQMAX; ++qi) {
+          if (qi < NQ) {
+            const float pr = sc[qi * T + t];
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) acc[qi][i] = fmaf(pr, vf[i], acc[qi][i]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float* red = sc;
+#pragma unroll
+  for (int qi = 0; qi < NQMAX; ++qi) {
+    if (qi < NQ) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) red[(warp * NQ + qi) * d + lane * VPL + i] = acc[qi][i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * d; i += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w * NQ * d + i];
+    p.ctx[((int64_t)chunk * NQ + i / d) * p.ctx_ld + (i % d)] = s;
+  }
+}
+
+template <int VPL, int NQMAX, int FMT>
+cudaError_t launch_mlp_packed_one(const MlpAttnParams& p, cudaStream_t stream) {
+  constexpr int d = 32 * VPL;
+  const size_t sc_f = (size_t)p.NQ * p.T, red_f = (size_t)kWarps * p.NQ * d;
+  const size_t smem = ((size_t)p.NQ * d + (sc_f > red_f ? sc_f : red_f)) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static PerDeviceFlag attr_set;
+  bool& set = attr_set.cur();
+  if (!set) {
+    cudaError_t err = cudaFuncSetAttribute(mlp_attn_packed_kernel<VPL, NQMAX, FMT>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (err != cudaSuccess) return err;
+    set = true;
+  }
+  launch_k_heavy(mlp_attn_packed_kernel<VPL, NQMAX, FMT>, dim3(p.n_chunks), dim3(kThreads), smem, stream, p);
+  return cudaGetLastError();
+}
+
+template <int VPL>
+cudaError_t launch_mlp_packed(const MlpAttnParams& p, cudaStream_t stream) {
+  if (p.kv_fmt == KV_Q23M)
+    return p.NQ == 1 ? launch_mlp_packed_one<VPL, 1, KV_Q23M>(p, stream) : launch_mlp_packed_one<VPL, 8, KV_Q23M>(p, stream);
+  return p.NQ == 1 ? launch_mlp_packed_one<VPL, 1, KV_Q15M>(p, stream) : launch_mlp_packed_one<VPL, 8, KV_Q15M>(p, stream);
+}
+
+cudaError_t mlp_attention_packed(const MlpAttnParams& p, cudaStream_t stream) {
+  if (p.n_chunks <= 0) return cudaSuccess;
+  if (!kv_pack_supported(p.d) || p.NQ > 8 || p.NQ < 1 || !p.kv_hi || !p.kv_scale || (p.kv_fmt != KV_Q23M && p.kv_fmt != KV_Q15M) ||
+      (p.kv_fmt == KV_Q23M && !p.kv_lo) || (int64_t)p.T * 4 * p.d >= (int64_t)1 << 31)
+    return cudaErrorInvalidValue;
+  switch (p.d / 32) {
+    case 2: return launch_mlp_packed<2>(p, stream);
+    case 4: return launch_mlp_packed<4>(p, stream);
+    case 8: return launch_mlp_packed<8>(p, stream);
+    default: return launch_mlp_packed<16>(p, stream);
+  }
 }
 
 cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream) {

@@ -169,6 +169,8 @@ struct nd_engine {
   int* cur_tok = nullptr;
   // rnn decoder
   float* uh = nullptr;               // [B, T', d]
+  int pk_fmt = KV_Q23M;              // format of the planes in pk (the CNN decoder always takes q23)
+  float* pk = nullptr;               // RNN / CNN decoders: fixed-point planes of (uh | H) or (enc top | enc combined), sized like fp32 [B*T', 2d]
   std::vector<float*> rh[2], rc[2];  // ping-pong recurrent state [rows,d] per layer
   float* feed[2] = {nullptr, nullptr};
   float *ga = nullptr, *gb = nullptr, *wq = nullptr, *actx = nullptr;
@@ -811,6 +813,7 @@ int alloc_workspace(nd_engine* e) {
     if (cross_attention_mb_supported((int)d, c.heads)) { F(e->qt, B * c.heads * d); F(e->cctxt, B * c.heads * d); }
   } else if (c.decoder_type == ND_DEC_RNN) {
     F(e->uh, BT * d);
+    if (kv_pack_supported((int)d)) F(e->pk, BT * 2 * d);
     for (int s = 0; s < 2; ++s) {
       e->rh[s].resize(c.dec_layers); e->rc[s].resize(c.dec_layers);
       for (int l = 0; l < c.dec_layers; ++l) { F(e->rh[s][l], rows * d); F(e->rc[s][l], rows * d); }
@@ -819,6 +822,7 @@ int alloc_workspace(nd_engine* e) {
     F(e->x, rows * d); F(e->ga, rows * 4 * d); F(e->gb, rows * 4 * d); F(e->wq, rows * d); F(e->actx, rows * d);
   } else {
     F(e->enc_comb, BT * d);
+    if (kv_pack_supported((int)d)) F(e->pk, BT * 2 * d);
     for (int s = 0; s < 2; ++s) {
       e->chist[s].resize(c.dec_layers);
       for (int l = 0; l < c.dec_layers; ++l) F(e->chist[s][l], rows * L * d);
@@ -1043,6 +1047,17 @@ KvPlanes kv_planes(const nd_engine* e, int l) {
   return p;
 }
 
+// RNN / CNN decoders: the same plane layout inside e->pk
+KvPlanes pk_planes(const nd_engine* e) {
+  const size_t n = (size_t)e->B * e->Tp * 2 * e->cfg.d_model;
+  uint8_t* base = reinterpret_cast<uint8_t*>(e->pk);
+  KvPlanes p;
+  p.hi = reinterpret_cast<int16_t*>(base);
+  p.lo = base + 2 * n;
+  p.scale = reinterpret_cast<float*>(base + 3 * n);
+  return p;
+}
+
 bool use_cross_mb(const nd_engine* e, int K, bool want_attn) {
   return e->cross_mode == 1 && K == 1 && !want_attn && e->cfg.decoder_type == ND_DEC_TRANSFORMER && e->qt != nullptr;
 }
@@ -1081,6 +1096,14 @@ int decoder_init(nd_engine* e, int K, cudaStream_t st, bool cross_mb = false) {
       GemmOpt o;                     // uh = Uk . H, exact same product the reference recomputes every step
       ND_TRY(run_gemm(e, e->attn_ctx, e->mb, d, e->uh, d, M, o, st));
     }
+    // The global attention re-reads uh and H (mlp) or H twice (general / dot) at every step: same fixed-point storage
+    // as the Transformer decoder's memory keys / values, part "K" = what the scores read, part "V" = H
+    e->kv_packed = e->kv_mode != KV_F32 && e->pk != nullptr && (e->kv_mode == KV_Q23M || e->kv_mode == KV_Q15M);
+    e->pk_fmt = e->kv_mode;
+    if (e->kv_packed) {
+      const KvPlanes pl = pk_planes(e);
+      ND_LAUNCH(e, kv_pack2(c.attn_type == ND_ATTN_MLP ? e->uh : e->mb, d, e->mb, d, M, d, e->pk_fmt, pl.hi, pl.lo, pl.scale, st));
+    }
     // decoder.py:108-129: hidden from the encoder final state ([fwd;bwd] per layer), input_feed = 0
     for (int l = 0; l < c.dec_layers; ++l) {
       ND_CUDA(e, cudaMemsetAsync(e->rh[0][l], 0, (size_t)rows * d * sizeof(float), st));
@@ -1112,6 +1135,16 @@ int decoder_init(nd_engine* e, int K, cudaStream_t st, bool cross_mb = false) {
                                      "input projection, onmt/decoders/cnn_decoder.py:59-64)");
     // state["src"] = (memory_bank + enc_hidden) * SCALE_WEIGHT                      cnn_decoder.py:63
     ND_LAUNCH(e, add_scale(e->mb, e->emb_remap, 0.70710678118654757f, e->enc_comb, M * d, st));
+    // conv attention: keys = encoder top, values = the combined state; read by every layer at every step.  Always the
+    // 3-byte format: the conv attention's scores are raw dot products of un-normalised states and its softmax is peaked;
+    // 2-byte keys moved one logit in 1024 chunks by 4e-3 (profiles/r02x_identity_rnn_cnn.json), which no stated bound
+    // worth having covers, so kv_mode q15 means q23 for this decoder
+    e->kv_packed = e->kv_mode != KV_F32 && e->pk != nullptr && (e->kv_mode == KV_Q23M || e->kv_mode == KV_Q15M);
+    e->pk_fmt = KV_Q23M;
+    if (e->kv_packed) {
+      const KvPlanes pl = pk_planes(e);
+      ND_LAUNCH(e, kv_pack2(e->mb, d, e->enc_comb, d, M, d, e->pk_fmt, pl.hi, pl.lo, pl.scale, st));
+    }
   }
   return ND_OK;
 }
@@ -1239,6 +1272,11 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
       }
       ma.uh = e->mb + (int64_t)dc.c0 * Tp * d;
     }
+    if (e->kv_packed) {
+      const KvPlanes pl = pk_planes(e);
+      const int64_t r0k = (int64_t)dc.c0 * Tp;
+      ma.kv_fmt = e->pk_fmt; ma.kv_hi = pl.hi + r0k * 2 * d; ma.kv_lo = pl.lo + r0k * 2 * d; ma.kv_scale = pl.scale + r0k * 2;
+    }
     ND_LAUNCH_CAT(e, ND_PROF_MLP_ATTN, st, mlp_attention(ma, st));
     // attn_h = W_out [c ; h] (+ b, no tanh, for mlp; tanh, no bias, for general / dot)   global_attention.py:197-203
     GemmOpt oc;
@@ -1270,6 +1308,11 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
       ma.lengths = nullptr; ma.retired = retired ? retired + dc.c0 : nullptr; ma.ctx = R(e->cctx2, d); ma.ctx_ld = d;
       ma.n_chunks = dc.nc; ma.NQ = K; ma.T = Tp; ma.d = d;
       ma.attn = (l + 1 == c.dec_layers && dc.attn_out) ? dc.attn_out + (int64_t)r0 * Tp : nullptr;
+      if (e->kv_packed) {
+        const KvPlanes pl = pk_planes(e);
+        const int64_t r0k = (int64_t)dc.c0 * Tp;
+        ma.kv_fmt = e->pk_fmt; ma.kv_hi = pl.hi + r0k * 2 * d; ma.kv_lo = pl.lo + r0k * 2 * d; ma.kv_scale = pl.scale + r0k * 2;
+      }
       ND_LAUNCH_CAT(e, ND_PROF_MLP_ATTN, st, mlp_attention(ma, st));
       float* xn = xbuf[l & 1];
       ND_LAUNCH(e, cnn_combine(xl, R(e->cctx2, d), R(e->cout, d), s2, xn, (int64_t)rows * d, st));      // :116

@@ -44,6 +44,9 @@ cudaError_t cross_attention(const CrossAttnParams& p, cudaStream_t stream);
 enum { KV_F32 = 0, KV_Q24 = 1, KV_Q16 = 2, KV_Q23M = 3, KV_Q15M = 4, KV_FP24 = 5 };
 bool kv_pack_supported(int d);
 // kv [rows, 2d] fp32 (row pitch 2d) -> planes as described in CrossAttnParams
+// the two parts of a row from separate matrices: part "K" = k[row*ldk .. +d), part "V" = v[row*ldv .. +d)
+cudaError_t kv_pack2(const float* k, int64_t ldk, const float* v, int64_t ldv, int64_t rows, int d, int fmt, int16_t* hi,
+                     uint8_t* lo, float* scale, cudaStream_t stream);
 cudaError_t kv_pack(const float* kv, int64_t rows, int d, int fmt, int16_t* hi, uint8_t* lo, float* scale,
                     cudaStream_t stream);
 cudaError_t cross_attention_packed(const CrossAttnParams& p, cudaStream_t stream);   // kv_fmt != 0 (cross_attn_packed.cu)
@@ -120,8 +123,15 @@ struct MlpAttnParams {
   float* attn = nullptr;                          // optional [n_chunks*NQ, T]
   int n_chunks = 0, NQ = 1, T = 0, d = 0;
   int dot = 0;                                    // 1: score = q . mem[t] (general / dot attention)
+  // Fixed-point planes (kv_fmt != 0; uh / mem are then unused): the "K" part of a row holds uh (dot: the keys), the "V"
+  // part mem, packed by kv_pack2 exactly like the Transformer decoder's memory keys / values (CrossAttnParams)
+  int kv_fmt = 0;
+  const int16_t* kv_hi = nullptr;
+  const uint8_t* kv_lo = nullptr;
+  const float* kv_scale = nullptr;
 };
 cudaError_t mlp_attention(const MlpAttnParams& p, cudaStream_t stream);
+cudaError_t mlp_attention_packed(const MlpAttnParams& p, cudaStream_t stream);   // kv_fmt KV_Q23M / KV_Q15M, d 64 - 512
 
 // ---------------------------------------------------------------------------------------------
 cudaError_t layernorm_rows(const float* x, const float* g, const float* b, float eps, float* y,

@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--greedy-opts", default="kv_mode=0;kv_mode=3;kv_mode=4",
                     help="';'-separated engine option sets compared against ONE oracle run per family")
     ap.add_argument("--only", default="", help="greedy | beam")
+    ap.add_argument("--families", default="", help="comma-separated family names to keep (default: all)")
     args = ap.parse_args()
     parse = lambda txt: {k: int(v) for k, v in (kv.split("=") for kv in txt.split(",") if kv)}
     opts = parse(args.opts)
@@ -149,12 +150,16 @@ def main():
     rows = []
     if args.only in ("", "greedy"):
         for family, kw in GREEDY:
+            if args.families and family not in args.families.split(","):
+                continue
             n = args.n_big if kw.get("d_model", 256) > 256 else args.n
             for row in greedy_case(family, kw, n, args.slice, greedy_opts):
                 rows.append(row)
                 print(json.dumps(row), flush=True)
     if args.only in ("", "beam"):
         for family, kw, ml in BEAMS:
+            if args.families and family not in args.families.split(","):
+                continue
             rows.append(beam_case(family, kw, ml, args.n, args.slice, opts))
             print(json.dumps(rows[-1]), flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
