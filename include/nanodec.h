@@ -91,7 +91,9 @@ typedef struct nd_config {
   int32_t max_beam;           /* largest beam_size that will be requested (>=1) */
   int32_t gemm_mode;          /* ND_GEMM_* */
   int32_t rnn_type;           /* ND_RNN_*: cell of the nano / rnn / brnn encoders and of the RNN decoder (took reserved[0]) */
-  int32_t reserved[7];
+  int32_t bridge;             /* 1: rnn / brnn encoder with -bridge: Linear + ReLU on the final states (encoder/rnn_encoder.py:82-118;
+                                 took reserved[1]) */
+  int32_t reserved[6];
 } nd_config;
 
 typedef struct nd_engine nd_engine;

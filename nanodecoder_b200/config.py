@@ -52,6 +52,7 @@ class ModelConfig:
     input_feed: int = 1
     global_attention: str = "mlp"
     position_encoding: bool = False
+    bridge: bool = False            # -bridge: Linear + ReLU on the rnn / brnn encoder's final states (rnn_encoder.py:82-118)
 
     def __post_init__(self):
         if self.encoder_type not in ENCODER_TYPES:
@@ -96,7 +97,7 @@ class ModelConfig:
             src_word_vec_size=self.d_model, tgt_word_vec_size=self.d_model, word_vec_size=-1,
             heads=self.heads, transformer_ff=self.d_ff, cnn_kernel_width=self.cnn_kernel_width,
             audio_enc_pooling=",".join(str(p) for p in self.enc_pooling),
-            rnn_type=self.rnn_type, input_feed=self.input_feed, bridge=False,
+            rnn_type=self.rnn_type, input_feed=self.input_feed, bridge=self.bridge,
             brnn=self.encoder_type == "brnn",
             global_attention=self.global_attention, global_attention_function="softmax",
             self_attn_type="scaled-dot", position_encoding=self.position_encoding,
@@ -122,9 +123,6 @@ class ModelConfig:
         if g("self_attn_type", "scaled-dot") != "scaled-dot":
             raise ValueError("-self_attn_type average is outside the supported translate path")
         # flags that change the arithmetic and would otherwise load and decode to wrong bases without an error
-        if g("bridge", False):
-            raise ValueError("-bridge (Linear+ReLU on the encoder final state, encoder/rnn_encoder.py:82-83) is "
-                             "outside the supported translate path")
         for flag in ("global_attention_function", "generator_function"):
             if g(flag, "softmax") not in ("softmax", None):
                 raise ValueError("-%s %s is outside the supported translate path (softmax only)" % (flag, g(flag)))
@@ -143,6 +141,8 @@ class ModelConfig:
             rnn_type=g("rnn_type", "LSTM"), input_feed=g("input_feed", 1),
             global_attention=g("global_attention", "general"),
             position_encoding=bool(g("position_encoding", False)),
+            # models/model_builder.py:78-83: only RNNEncoder takes the flag; the other encoders never see it
+            bridge=bool(g("bridge", False)) and enc in ("rnn", "brnn"),
         )
 
     def asdict(self):

@@ -137,6 +137,8 @@ struct nd_engine {
   float* mb = nullptr;               // memory bank [B, T', d]
   float* emb_remap = nullptr;        // cnn encoder: Linear(1,d) output (decoder init_state needs it)
   float* enc_hn = nullptr; float* enc_cn = nullptr;   // rnn encoders: [Le*dirs, B, hh]
+  float* enc_hb = nullptr; float* enc_cb = nullptr;   // the same after -bridge (Linear + ReLU over rows of hh*Le floats)
+  Lin bridge_h, bridge_c;
   int* fe_todo = nullptr; int fe_todo_cap = 0;     // front end: reads left for the radix-select kernel
   int B = 0, T = 0, Tp = 0;          // last encode
   bool encoded = false;
@@ -638,6 +640,12 @@ int finalize(nd_engine* e) {
     e->lstm.resize(c.enc_layers);
     for (int l = 0; l < c.enc_layers; ++l)
       ND_TRY(load_lstm(e, "encoder.rnn", "_l" + std::to_string(l), l == 0 ? 1 : d, H, dirs, &e->lstm[l]));
+    if (c.bridge) {
+      // encoder/rnn_encoder.py:86-99: nn.Linear(hh * layers, hh * layers) per state (h; c for LSTM)
+      const int tot = H * c.enc_layers;
+      ND_TRY(load_lin(e, "encoder.bridge.0", tot, tot, true, &e->bridge_h));
+      if (c.rnn_type != ND_RNN_GRU) ND_TRY(load_lin(e, "encoder.bridge.1", tot, tot, true, &e->bridge_c));
+    }
   } else if (c.encoder_type == ND_ENC_TRANSFORMER || c.encoder_type == ND_ENC_CTRANSFORMER) {
     if (c.encoder_type == ND_ENC_TRANSFORMER) ND_TRY(load_lin(e, "encoder.linear", d, 1, true, &e->enc_lin_in));
     e->encT.resize(c.enc_layers);
@@ -801,6 +809,7 @@ int alloc_workspace(nd_engine* e) {
   F(e->big, BT * wide);
   if (c.encoder_type == ND_ENC_BRNN || c.encoder_type == ND_ENC_RNN) {
     F(e->enc_hn, (int64_t)c.enc_layers * B * d); F(e->enc_cn, (int64_t)c.enc_layers * B * d);
+    if (c.bridge) { F(e->enc_hb, (int64_t)c.enc_layers * B * d); F(e->enc_cb, (int64_t)c.enc_layers * B * d); }
   }
   // decoder
   F(e->logp, rows * c.vocab_size); F(e->gscore, rows);
@@ -961,6 +970,15 @@ int encode_lstm_stack(nd_engine* e, cudaStream_t st) {
     ND_TRY(run_gemm(e, e->encW, last, d, e->mb, d, (int64_t)B * T, o, st));
   } else {
     ND_CUDA(e, cudaMemcpyAsync(e->mb, last, (size_t)B * T * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (c.bridge) {
+      // encoder/rnn_encoder.py:101-118: relu(Linear(states.view(-1, hh * layers))).view(size) -- the view runs over the
+      // flat [layers*dirs, B, hh] array, so one row is `layers` consecutive (layer-dir, chunk) vectors: reproduced as is
+      const int tot = H * c.enc_layers;
+      const int64_t rows_b = (int64_t)dirs * B;
+      GemmOpt ob; ob.act = 1;
+      ND_TRY(run_gemm(e, e->bridge_h, e->enc_hn, tot, e->enc_hb, tot, rows_b, ob, st));
+      if (c.rnn_type != ND_RNN_GRU) ND_TRY(run_gemm(e, e->bridge_c, e->enc_cn, tot, e->enc_cb, tot, rows_b, ob, st));
+    }
   }
   if (lens_dev != e->mem_len)
     ND_CUDA(e, cudaMemcpyAsync(e->mem_len, e->lengths, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
@@ -1118,8 +1136,8 @@ int decoder_init(nd_engine* e, int K, cudaStream_t st, bool cross_mb = false) {
         for (int dir = 0; dir < dirs; ++dir)
           for (int k = 0; k < K; ++k) {
             // rows are chunk-major: row = b*K + k; copy with a strided 2-D memcpy (width H floats)
-            const float* hs = e->enc_hn + ((int64_t)l * dirs + dir) * B * H;
-            const float* cs = e->enc_cn + ((int64_t)l * dirs + dir) * B * H;
+            const float* hs = (c.bridge ? e->enc_hb : e->enc_hn) + ((int64_t)l * dirs + dir) * B * H;
+            const float* cs = (c.bridge ? e->enc_cb : e->enc_cn) + ((int64_t)l * dirs + dir) * B * H;
             ND_CUDA(e, cudaMemcpy2DAsync(e->rh[0][l] + (int64_t)k * d + dir * H, (size_t)K * d * sizeof(float), hs,
                                          (size_t)H * sizeof(float), (size_t)H * sizeof(float), B,
                                          cudaMemcpyDeviceToDevice, st));

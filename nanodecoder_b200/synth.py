@@ -200,6 +200,10 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
             b.lstm("encoder.rnn", "_l%d" % l, in_f, hh, gates=ng)
             if dirs == 2:
                 b.lstm("encoder.rnn", "_l%d_reverse" % l, in_f, hh, gates=ng)
+        if cfg.bridge:                          # encoder/rnn_encoder.py:86-99: one Linear per state (h, c)
+            tot = hh * cfg.enc_layers
+            for i in range(2 if cfg.rnn_type == "LSTM" else 1):
+                b.linear("encoder.bridge.%d" % i, tot, tot, gain=2.0)
     elif cfg.encoder_type == "transformer":     # encoder/transformer.py:87-104
         b.linear("encoder.linear", d, 1)
         for l in range(cfg.enc_layers):

@@ -70,6 +70,9 @@ CASES = {
     "brnn2rnn_gru_d256": ("brnn2rnn", dict(rnn_type="GRU")),
     "l2t_gru_d64": ("l2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2, rnn_type="GRU")),
     "rnn2rnn_gru_std_d64": ("rnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, rnn_type="GRU", input_feed=0)),
+    # -bridge (encoder/rnn_encoder.py:82-118): Linear + ReLU on the final states, over rows of `layers` batch neighbours
+    "brnn2rnn_bridge_d64": ("brnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, bridge=True)),
+    "rnn2rnn_gru_bridge_d64": ("rnn2rnn", dict(d_model=64, enc_layers=3, dec_layers=3, rnn_type="GRU", bridge=True)),
     # ResNet stem encoders (encoder/resnet_encoder.py, crnn_encoder.py, ctransformer.py); pipeline-train.sh trains
     # resnet -> transformer and resnet -> rnn at d = 256
     "resnet2t_d256": ("resnet2t", dict()),
@@ -90,6 +93,8 @@ def ref_extra(cfg):
         extra += ["-input_feed", str(int(cfg.input_feed))]
     if cfg.rnn_type != "LSTM":
         extra += ["-rnn_type", cfg.rnn_type]
+    if getattr(cfg, "bridge", False):
+        extra.append("-bridge")
     return extra
 
 

@@ -185,6 +185,13 @@ def rnn_encoder(sd, cfg, src, lengths):
     rnn = _make_lstm(sd, "encoder.rnn", 1, hh, cfg.enc_layers, bi, cfg.rnn_type)
     packed = pack_padded_sequence(src, lengths.view(-1).tolist(), enforce_sorted=False)
     mb, final = rnn(packed)
+    if getattr(cfg, "bridge", False):                               # :82-83, 101-118
+        tot = hh * cfg.enc_layers
+
+        def bottle(i, states):      # NB: view(-1, hh * layers) of [layers*dirs, B, hh] mixes `layers` batch neighbours per row
+            return torch.relu(_lin(sd, "encoder.bridge.%d" % i, states.contiguous().view(-1, tot))).view(states.size())
+
+        final = tuple(bottle(i, st) for i, st in enumerate(final)) if isinstance(final, tuple) else bottle(0, final)
     return final, pad_packed_sequence(mb)[0], lengths
 
 

@@ -158,7 +158,13 @@ def test_model_flags_that_change_the_arithmetic_are_refused():
     vocab = SPECIALS + ["A", "C", "G", "T"]
     base = ModelConfig.family("brnn2rnn").to_opt()
     assert ModelConfig.from_opt(base, vocab).encoder_type == "brnn"
-    for flag, value in (("bridge", True), ("global_attention_function", "sparsemax"), ("generator_function", "sparsemax"),
+    opt = ModelConfig.family("brnn2rnn").to_opt()
+    opt.bridge = True
+    assert ModelConfig.from_opt(opt, vocab).bridge                       # -bridge is run (rnn / brnn encoders)
+    opt = ModelConfig.family("l2t").to_opt()
+    opt.bridge = True
+    assert not ModelConfig.from_opt(opt, vocab).bridge                   # model_builder.py: the other encoders never see it
+    for flag, value in (("global_attention_function", "sparsemax"), ("generator_function", "sparsemax"),
                         ("copy_attn", True), ("context_gate", "both"), ("self_attn_type", "average")):
         opt = ModelConfig.family("brnn2rnn").to_opt()
         setattr(opt, flag, value)
