@@ -93,7 +93,8 @@ typedef struct nd_config {
   int32_t rnn_type;           /* ND_RNN_*: cell of the nano / rnn / brnn encoders and of the RNN decoder (took reserved[0]) */
   int32_t bridge;             /* 1: rnn / brnn encoder with -bridge: Linear + ReLU on the final states (encoder/rnn_encoder.py:82-118;
                                  took reserved[1]) */
-  int32_t reserved[6];
+  int32_t self_attn_average;  /* 1: Transformer decoder with -self_attn_type average (onmt/modules/average_attn.py; took reserved[2]) */
+  int32_t reserved[5];
 } nd_config;
 
 typedef struct nd_engine nd_engine;

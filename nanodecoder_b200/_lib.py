@@ -31,7 +31,7 @@ class NdConfig(C.Structure):
         ("cnn_kernel_width", C.c_int32), ("enc_pooling", C.c_int32 * 8), ("input_feed", C.c_int32),
         ("attn_type", C.c_int32), ("position_encoding", C.c_int32), ("max_batch", C.c_int32),
         ("max_src_len", C.c_int32), ("max_tgt_len", C.c_int32), ("max_beam", C.c_int32),
-        ("gemm_mode", C.c_int32), ("rnn_type", C.c_int32), ("bridge", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("gemm_mode", C.c_int32), ("rnn_type", C.c_int32), ("bridge", C.c_int32), ("self_attn_average", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 

@@ -52,6 +52,7 @@ class ModelConfig:
     input_feed: int = 1
     global_attention: str = "mlp"
     position_encoding: bool = False
+    self_attn_type: str = "scaled-dot"   # Transformer decoder: "average" = AverageAttention (onmt/modules/average_attn.py)
     bridge: bool = False            # -bridge: Linear + ReLU on the rnn / brnn encoder's final states (rnn_encoder.py:82-118)
 
     def __post_init__(self):
@@ -68,6 +69,8 @@ class ModelConfig:
             raise ValueError("rnn_type must be LSTM or GRU (SRU is outside the supported path; got %r)" % self.rnn_type)
         if self.d_model % self.heads:
             raise ValueError("d_model must be divisible by heads")
+        if self.self_attn_type not in ("scaled-dot", "average"):
+            raise ValueError("self_attn_type must be scaled-dot or average")
         if self.encoder_type in ("resnet", "ctransformer") and self.decoder_type == "cnn":
             # model_builder.py:133-140 builds ResNetEncoder for the cnn decoder, whose outputs are laid out [d,B,T]
             # with a [1,1,B,T] "embedding" (resnet_encoder.py:195-199): not a configuration anyone can decode with
@@ -100,7 +103,7 @@ class ModelConfig:
             rnn_type=self.rnn_type, input_feed=self.input_feed, bridge=self.bridge,
             brnn=self.encoder_type == "brnn",
             global_attention=self.global_attention, global_attention_function="softmax",
-            self_attn_type="scaled-dot", position_encoding=self.position_encoding,
+            self_attn_type=self.self_attn_type, position_encoding=self.position_encoding,
             copy_attn=False, coverage_attn=False, context_gate=None, reuse_copy_attn=False,
             generator_function="softmax", dropout=0.0, feat_merge="concat",
             feat_vec_exponent=0.7, feat_vec_size=-1, optim="sgd", model_type="nano",
@@ -120,8 +123,8 @@ class ModelConfig:
                 raise ValueError("-%s is outside the supported translate path" % flag)
         if g("context_gate") is not None:
             raise ValueError("-context_gate is outside the supported translate path")
-        if g("self_attn_type", "scaled-dot") != "scaled-dot":
-            raise ValueError("-self_attn_type average is outside the supported translate path")
+        if g("self_attn_type", "scaled-dot") not in ("scaled-dot", "average"):
+            raise ValueError("unknown -self_attn_type %r" % (g("self_attn_type"),))
         # flags that change the arithmetic and would otherwise load and decode to wrong bases without an error
         for flag in ("global_attention_function", "generator_function"):
             if g(flag, "softmax") not in ("softmax", None):
@@ -143,6 +146,8 @@ class ModelConfig:
             position_encoding=bool(g("position_encoding", False)),
             # models/model_builder.py:78-83: only RNNEncoder takes the flag; the other encoders never see it
             bridge=bool(g("bridge", False)) and enc in ("rnn", "brnn"),
+            # decoder/transformer.py:33-38: only the Transformer decoder's self attention has the two types
+            self_attn_type=g("self_attn_type", "scaled-dot") if g("decoder_type", "rnn") == "transformer" else "scaled-dot",
         )
 
     def asdict(self):

@@ -154,6 +154,31 @@ __global__ void glu_residual_kernel(const float* __restrict__ y, const float* __
   if (out) out[i] = (x[i] + glu) * 0.70710678118654757f;   // SCALE_WEIGHT = 0.5 ** 0.5 rounded to fp32
 }
 
+// all pointers are row-range views starting at row0, except prev (whole buffer: parents are global rows)
+__global__ void avg_cumulate_kernel(const float* __restrict__ xn, const float* __restrict__ prev, const int* __restrict__ parent,
+                                    int row0, int rows, int d, int step, float* __restrict__ g) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * d) return;
+  const int r = (int)(i / d), c = (int)(i - (int64_t)r * d);
+  float v = xn[i];
+  if (step > 0) {
+    const int pr = parent ? parent[row0 + r] : row0 + r;
+    v = (v + (float)step * prev[(int64_t)pr * d + c]) / (float)(step + 1);
+  }
+  g[i] = v;
+}
+
+__global__ void avg_gate_kernel(const float* __restrict__ gate, const float* __restrict__ xn, const float* __restrict__ a,
+                                const float* __restrict__ x, float* __restrict__ out, int64_t rows, int d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * d) return;
+  const int64_t r = i / d;
+  const int c = (int)(i - r * d);
+  const float ig = gate[r * 2 * d + c], fg = gate[r * 2 * d + d + c];
+  const float si = 1.0f / (1.0f + expf(-ig)), sf = 1.0f / (1.0f + expf(-fg));
+  out[i] = (si * xn[i] + sf * a[i]) + x[i];
+}
+
 // first conv of the ResNet stem: 1 -> 64 channels, 3 taps, folded BatchNorm, ReLU
 __global__ void resnet_stem_kernel(const float* __restrict__ src, const float* __restrict__ w, const float* __restrict__ b,
                                    float* __restrict__ out, int B, int T) {
@@ -478,6 +503,22 @@ cudaError_t glu_residual(const float* y, const float* x, float* out, float* glu_
                          cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   launch_k(glu_residual_kernel, dim3((unsigned)cdiv64(rows * d, 256)), dim3(256), 0, stream, y, x, out, glu_out, rows, d);
+  return cudaGetLastError();
+}
+
+cudaError_t avg_attn_cumulate(const float* xn, const float* prev, const int* parent, int row0, int rows, int d, int step,
+                              float* g, cudaStream_t stream) {
+  const int64_t n = (int64_t)rows * d;
+  if (n <= 0) return cudaSuccess;
+  avg_cumulate_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(xn, prev, parent, row0, rows, d, step, g);
+  return cudaGetLastError();
+}
+
+cudaError_t avg_attn_gate(const float* gate, const float* xn, const float* a, const float* x, float* out, int64_t rows, int d,
+                          cudaStream_t stream) {
+  const int64_t n = rows * d;
+  if (n <= 0) return cudaSuccess;
+  avg_gate_kernel<<<(unsigned)cdiv(n, 256), 256, 0, stream>>>(gate, xn, a, x, out, rows, d);
   return cudaGetLastError();
 }
 

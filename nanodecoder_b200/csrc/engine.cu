@@ -67,8 +67,9 @@ struct EncLayerT {             // transformer encoder layer
 };
 struct DecLayerT {             // transformer decoder layer
   Lin qkv, self_out, cq, ckv, ctx_out, w1, w2;
+  Lin avg_w1, avg_w2, gate_x, gate_a;   // -self_attn_type average: average_layer (FFN d -> d -> d), gating_layer split by input
   Lin cqt, cm;                 // memory-bank-space cross attention (kernels.cuh CrossMbParams): P [H*d, d], Mcat [d, H*d]
-  LnW ln1, ln2, ln_ff;
+  LnW ln1, ln2, ln_ff, ln_avg;
 };
 struct LstmW {                 // one bidirectional (or unidirectional) LSTM layer
   Lin ih;                      // [dirs*4H, in] with b_ih (input projection GEMM), in > 1
@@ -689,8 +690,19 @@ int finalize(nd_engine* e) {
     for (int l = 0; l < c.dec_layers; ++l) {
       const std::string p = "decoder.transformer_layers." + std::to_string(l);
       DecLayerT& L = e->decT[l];
-      ND_TRY(load_cat_lin(e, {p + ".self_attn.linear_query", p + ".self_attn.linear_keys", p + ".self_attn.linear_values"}, d, d, &L.qkv, p + ".layer_norm_1"));
-      ND_TRY(load_lin(e, p + ".self_attn.final_linear", d, d, true, &L.self_out));
+      if (c.self_attn_average) {
+        // onmt/modules/average_attn.py:22-30: PositionwiseFeedForward(d, d) + Linear(2d, 2d) over cat(inputs, average)
+        const std::string a = p + ".self_attn.average_layer";
+        ND_TRY(load_lin(e, a + ".w_1", d, d, true, &L.avg_w1, a + ".layer_norm"));
+        ND_TRY(load_lin(e, a + ".w_2", d, d, true, &L.avg_w2));
+        Lin gate;
+        ND_TRY(load_lin(e, p + ".self_attn.gating_layer", 2 * d, 2 * d, true, &gate));
+        L.gate_x = col_slice(gate, 0, d, true);
+        L.gate_a = col_slice(gate, d, d, false);
+      } else {
+        ND_TRY(load_cat_lin(e, {p + ".self_attn.linear_query", p + ".self_attn.linear_keys", p + ".self_attn.linear_values"}, d, d, &L.qkv, p + ".layer_norm_1"));
+        ND_TRY(load_lin(e, p + ".self_attn.final_linear", d, d, true, &L.self_out));
+      }
       ND_TRY(load_lin(e, p + ".context_attn.linear_query", d, d, true, &L.cq, p + ".layer_norm_2"));
       ND_TRY(load_cat_lin(e, {p + ".context_attn.linear_keys", p + ".context_attn.linear_values"}, d, d, &L.ckv));
       ND_TRY(load_lin(e, p + ".context_attn.final_linear", d, d, true, &L.ctx_out));
@@ -701,6 +713,7 @@ int finalize(nd_engine* e) {
       ND_TRY(load_ln(e, p + ".layer_norm_1", d, &L.ln1));
       ND_TRY(load_ln(e, p + ".layer_norm_2", d, &L.ln2));
       ND_TRY(load_ln(e, p + ".feed_forward.layer_norm", d, &L.ln_ff));
+      if (c.self_attn_average) ND_TRY(load_ln(e, p + ".self_attn.average_layer.layer_norm", d, &L.ln_avg));
     }
     ND_TRY(load_ln(e, "decoder.layer_norm", d, &e->dec_ln));
   } else if (c.decoder_type == ND_DEC_RNN) {
@@ -1187,6 +1200,26 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
     float* x = R(e->x, d);
     for (int l = 0; l < c.dec_layers; ++l) {
       const DecLayerT& L = e->decT[l];
+      if (c.self_attn_average) {
+        // AverageAttention (onmt/modules/average_attn.py:77-106, decoder/transformer.py:82-85): cumulative average of the
+        // normalised inputs along the hypothesis (state prev_g per row, followed through the beams' parents), FFN, gates
+        float* xn = R(e->sctx, d);
+        float* g_cur = e->selfK[l] + (int64_t)(dc.step & 1) * e->max_rows * d;          // [2][rows, d] inside the (unused) cache
+        const float* g_prev = e->selfK[l] + (int64_t)((dc.step & 1) ^ 1) * e->max_rows * d;
+        ND_LAUNCH(e, layernorm_rows(x, L.ln1.g, L.ln1.b, 1e-6f, xn, rows, d, st));
+        ND_LAUNCH(e, avg_attn_cumulate(xn, g_prev, dc.beam ? e->beam.parent : nullptr, r0, rows, d, dc.step,
+                                       g_cur + (int64_t)r0 * d, st));
+        GemmOpt oa1; oa1.prologue = PRO_LAYERNORM; oa1.pg = L.ln_avg.g; oa1.pb = L.ln_avg.b; oa1.act = 1;
+        ND_TRY(run_gemm(e, L.avg_w1, g_cur + (int64_t)r0 * d, d, R(e->qc, d), d, rows, oa1, st));
+        GemmOpt oa2; oa2.residual = g_cur + (int64_t)r0 * d; oa2.ldr = d;
+        ND_TRY(run_gemm(e, L.avg_w2, R(e->qc, d), d, R(e->cctx, d), d, rows, oa2, st));     // a = FFN(g)
+        float* gate = R(e->qkv, 3 * d);                                                  // [rows, 2d] view, pitch 2d
+        GemmOpt og1;
+        ND_TRY(run_gemm(e, L.gate_x, xn, d, gate, 2 * d, rows, og1, st));
+        GemmOpt og2; og2.residual = gate; og2.ldr = 2 * d;
+        ND_TRY(run_gemm(e, L.gate_a, R(e->cctx, d), d, gate, 2 * d, rows, og2, st));
+        ND_LAUNCH(e, avg_attn_gate(gate, xn, R(e->cctx, d), x, R(e->x1, d), rows, d, st));
+      } else {
       GemmOpt o1; o1.prologue = PRO_LAYERNORM; o1.pg = L.ln1.g; o1.pb = L.ln1.b;
       ND_TRY(run_gemm(e, L.qkv, x, d, R(e->qkv, 3 * d), 3 * d, rows, o1, st));
       SelfAttnParams sa;
@@ -1196,6 +1229,7 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
       ND_LAUNCH_CAT(e, ND_PROF_SELF_ATTN, st, self_attention_step(sa, st));
       GemmOpt o2; o2.residual = x; o2.ldr = d;
       ND_TRY(run_gemm(e, L.self_out, R(e->sctx, d), d, R(e->x1, d), d, rows, o2, st));
+      }
       if (dc.cross_mb) {
         // cross attention in memory-bank space: QT = LN2(x1) P^T + pb -> attention over mb -> x2 = x1 + ctxt Mcat^T + mo
         const int64_t HD = (int64_t)c.heads * d;

@@ -234,6 +234,13 @@ cudaError_t beam_gather_attention(const BeamState& st, const float* hist, const 
 cudaError_t gather_rows(const float* src, float* dst, const int* parent, int row0, int rows, int width,
                         cudaStream_t stream);
 
+// AverageAttention at one decode step (onmt/modules/average_attn.py:52-75):
+//   g[r] = (xn[r] + step * prev[parent ? parent[r] : r]) / (step + 1)      (prev ignored at step 0)
+cudaError_t avg_attn_cumulate(const float* xn, const float* prev, const int* parent, int row0, int rows, int d, int step,
+                              float* g, cudaStream_t stream);
+//   out[r] = sigmoid(gate[r, :d]) * xn[r] + sigmoid(gate[r, d:]) * a[r] + x[r]   (:100-104 + the layer's residual)
+cudaError_t avg_attn_gate(const float* gate, const float* xn, const float* a, const float* x, float* out, int64_t rows, int d,
+                          cudaStream_t stream);
 // x = tanh(x) (accurate tanhf): output stage of the general / dot global attention (global_attention.py:201-203)
 cudaError_t tanh_inplace(float* x, int64_t n, cudaStream_t stream);
 

@@ -44,6 +44,7 @@ class Engine(object):
         c.attn_type = _lib.ATTN[cfg.global_attention]
         c.position_encoding = int(cfg.position_encoding)
         c.rnn_type = _lib.RNN[cfg.rnn_type]
+        c.self_attn_average = int(getattr(cfg, "self_attn_type", "scaled-dot") == "average" and cfg.decoder_type == "transformer")
         c.bridge = int(bool(getattr(cfg, "bridge", False)) and cfg.encoder_type in ("rnn", "brnn"))
         c.max_batch, c.max_src_len, c.max_tgt_len, c.max_beam = max_batch, max_src_len, max_tgt_len, max_beam
         c.gemm_mode = _lib.GEMM[gemm_mode]

@@ -241,7 +241,11 @@ def make_state_dict(cfg: ModelConfig, seed: int = 2025, gains: dict = None) -> D
     if cfg.decoder_type == "transformer":       # decoder/transformer.py:145-171
         for l in range(cfg.dec_layers):
             p = "decoder.transformer_layers.%d" % l
-            b.mha(p + ".self_attn", d, qk_gain=G["self_qk"], out_gain=G["self_out"])
+            if cfg.self_attn_type == "average":  # onmt/modules/average_attn.py:22-30
+                b.ffn(p + ".self_attn.average_layer", d, d, out_gain=G["self_out"])
+                b.linear(p + ".self_attn.gating_layer", 2 * d, 2 * d)
+            else:
+                b.mha(p + ".self_attn", d, qk_gain=G["self_qk"], out_gain=G["self_out"])
             b.mha(p + ".context_attn", d, qk_gain=G["attn_qk"], out_gain=G["ctx_out"])
             b.ffn(p + ".feed_forward", d, cfg.d_ff, out_gain=G["ffn_out"])
             b.affine(p + ".layer_norm_1", d)

@@ -73,6 +73,9 @@ CASES = {
     # -bridge (encoder/rnn_encoder.py:82-118): Linear + ReLU on the final states, over rows of `layers` batch neighbours
     "brnn2rnn_bridge_d64": ("brnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, bridge=True)),
     "rnn2rnn_gru_bridge_d64": ("rnn2rnn", dict(d_model=64, enc_layers=3, dec_layers=3, rnn_type="GRU", bridge=True)),
+    # -self_attn_type average (onmt/modules/average_attn.py): cumulative average + FFN + gating instead of self attention
+    "t2t_avg_d64": ("t2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2, self_attn_type="average")),
+    "l2t_avg_d256": ("l2t", dict(self_attn_type="average")),
     # ResNet stem encoders (encoder/resnet_encoder.py, crnn_encoder.py, ctransformer.py); pipeline-train.sh trains
     # resnet -> transformer and resnet -> rnn at d = 256
     "resnet2t_d256": ("resnet2t", dict()),
@@ -95,6 +98,8 @@ def ref_extra(cfg):
         extra += ["-rnn_type", cfg.rnn_type]
     if getattr(cfg, "bridge", False):
         extra.append("-bridge")
+    if getattr(cfg, "self_attn_type", "scaled-dot") != "scaled-dot":
+        extra += ["-self_attn_type", cfg.self_attn_type]
     return extra
 
 

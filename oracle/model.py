@@ -314,6 +314,9 @@ class TransformerDecoder(object):
         if step == 0:                                               # :198-199,248-266
             self.state["cache"] = [dict(memory_keys=None, memory_values=None, self_keys=None,
                                         self_values=None) for _ in range(cfg.dec_layers)]
+            if cfg.self_attn_type == "average":                     # :261-262: prev_g [B',1,d] zeros
+                for lc in self.state["cache"]:
+                    lc["prev_g"] = memory_bank.new_zeros(memory_bank.size(1), 1, memory_bank.size(-1))
         emb = F.embedding(tgt[:, :, 0], sd["decoder.embeddings.make_embedding.emb_luts.0.weight"])
         if cfg.position_encoding:                                   # onmt/modules/embeddings.py:36-43
             emb = emb * math.sqrt(cfg.d_model) + _positional_encoding(cfg.d_model, step, emb, sd.get("decoder.embeddings.make_embedding.pe.pe"))
@@ -326,8 +329,16 @@ class TransformerDecoder(object):
             p = "decoder.transformer_layers.%d" % l
             lc = self.state["cache"][l]
             xn = _ln(sd, p + ".layer_norm_1", out)                  # :74
-            q, _ = multi_head_attention(sd, p + ".self_attn", xn, xn, xn, cfg.heads,
-                                        mask=None, cache=lc, kind="self")       # :76-80
+            if cfg.self_attn_type == "average":                     # :82-84, onmt/modules/average_attn.py:52-106
+                g = (xn + step * lc["prev_g"]) / (step + 1)         # cumulative average (:71-75)
+                lc["prev_g"] = g
+                a = feed_forward(sd, p + ".self_attn.average_layer", g)
+                gate = _lin(sd, p + ".self_attn.gating_layer", torch.cat((xn, a), -1))
+                ig, fg = torch.chunk(gate, 2, dim=2)
+                q = torch.sigmoid(ig) * xn + torch.sigmoid(fg) * a
+            else:
+                q, _ = multi_head_attention(sd, p + ".self_attn", xn, xn, xn, cfg.heads,
+                                            mask=None, cache=lc, kind="self")       # :76-80
             q = q + out                                             # :85
             qn = _ln(sd, p + ".layer_norm_2", q)                    # :87
             mid, attn = multi_head_attention(sd, p + ".context_attn", mem, mem, qn, cfg.heads,

@@ -14,7 +14,7 @@ GOLDEN_CASES = ["l2t_d256", "t2t_d256", "nano2rnn_d256", "brnn2rnn_d256", "cnn2c
                 "cnn2cnn_pe_d64", "brnn2rnn_std_d256", "brnn2rnn_std_general_d64",
                "rnn2rnn_d256", "rnn2rnn_d64", "nano2rnn_gru_d64", "brnn2rnn_gru_d256", "l2t_gru_d64",
                "rnn2rnn_gru_std_d64", "resnet2t_d256", "resnet2rnn_d256", "resnet2t_d64", "crnn2t_d64", "crnn2rnn_d64",
-                "ctrans2t_d64", "brnn2rnn_bridge_d64", "rnn2rnn_gru_bridge_d64"]
+                "ctrans2t_d64", "brnn2rnn_bridge_d64", "rnn2rnn_gru_bridge_d64", "t2t_avg_d64", "l2t_avg_d256"]
 
 
 def load_golden(name):

@@ -165,7 +165,7 @@ def test_model_flags_that_change_the_arithmetic_are_refused():
     opt.bridge = True
     assert not ModelConfig.from_opt(opt, vocab).bridge                   # model_builder.py: the other encoders never see it
     for flag, value in (("global_attention_function", "sparsemax"), ("generator_function", "sparsemax"),
-                        ("copy_attn", True), ("context_gate", "both"), ("self_attn_type", "average")):
+                        ("copy_attn", True), ("context_gate", "both"), ("self_attn_type", "sideways")):
         opt = ModelConfig.family("brnn2rnn").to_opt()
         setattr(opt, flag, value)
         with pytest.raises(ValueError):
