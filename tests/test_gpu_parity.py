@@ -354,6 +354,48 @@ def test_nano_encoder_time_pooling_vs_oracle(pooling):
         assert torch.equal(bm["ids"][i, 0, : int(bm["lens"][i, 0])].cpu(), ob["predictions"][i][0])
 
 
+@pytest.mark.parametrize("family,kw,B,T", [
+    ("resnet2rnn", dict(d_model=64, dec_layers=2), 3, 77),
+    ("resnet2t", dict(d_model=128, d_ff=256, dec_layers=2), 1, 69),
+    ("crnn2rnn", dict(d_model=64, enc_layers=2, dec_layers=2, enc_pooling=[2, 1]), 5, 90),
+    ("ctrans2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2), 4, 70),
+    ("brnn2rnn", dict(d_model=64, enc_layers=3, dec_layers=3, bridge=True), 7, 73),     # bridge rows straddle layers: 7 % 3 != 0
+    ("t2t", dict(d_model=64, d_ff=128, enc_layers=2, dec_layers=2, self_attn_type="average"), 5, 81),
+])
+def test_round2_model_variants_vs_oracle_on_odd_shapes(family, kw, B, T):
+    """The ResNet-stem encoders (alone, before the LSTM stack incl. time pooling, before transformer layers), -bridge and
+    the average self-attention against the oracle port on shapes the goldens do not have: T not a multiple of any tile,
+    a single chunk, ragged lengths, a batch that is not a multiple of the layer count (bridge view)."""
+    from oracle import decode as od
+    from oracle.model import OracleModel
+    cfg = ModelConfig.family(family, **kw)
+    sd = synth.make_state_dict(cfg, seed=23)
+    L = 10
+    chunks, lengths = synth.make_chunks(B, T=T, seed=37, ragged=True, read_len=2)
+    order = torch.argsort(lengths, descending=True, stable=True)
+    chunks, lengths = chunks[order], lengths[order]
+    Tmax = int(lengths.max())
+    chunks = chunks[:, :Tmax].contiguous()
+    eng = _engine(cfg, sd, B, Tmax, L, K=3)
+    eng.encode(chunks.cuda(), lengths.cuda())
+    mb, mlen = eng.memory_bank()
+    gr = eng.decode_greedy(L, return_logits=True)
+    bm = eng.decode_beam(3, 1, L, min_len=4)
+    torch.cuda.synchronize()
+    om = OracleModel(sd, cfg)
+    s = chunks.t().contiguous().unsqueeze(2)
+    trace = []
+    og = od.greedy(om, s, lengths, max_length=L, trace_logits=trace)
+    assert list(mb.shape) == list(og["memory_bank"].shape)
+    assert torch.equal(mlen.cpu(), og["memory_lengths"])
+    assert rel_err(mb.cpu(), og["memory_bank"]) < TOL
+    assert rel_err(gr["logits"].cpu(), torch.stack(trace)) < TOL
+    assert torch.equal(gr["ids"].cpu(), og["predictions"])
+    ob = od.beam_fast(om, s, lengths, beam_size=3, max_length=L, min_length=4)
+    for i in range(B):
+        assert torch.equal(bm["ids"][i, 0, : int(bm["lens"][i, 0])].cpu(), ob["predictions"][i][0])
+
+
 def test_decode_streams_and_graphs_do_not_change_results():
     """Chunk groups on several streams and CUDA-graph replay are scheduling choices only: eager call,
     graph capture (2nd call) and graph replays (3rd, 4th call) must all return identical results."""
