@@ -172,3 +172,39 @@ def test_model_flags_that_change_the_arithmetic_are_refused():
             ModelConfig.from_opt(opt, vocab)
     with pytest.raises(ValueError):
         ModelConfig.from_opt(base, ["<unk>", "<s>", "<blank>", "</s>", "A", "C", "G", "T"])     # specials out of order
+
+
+def test_nd_config_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of nd_config (nanodecoder_b200/_lib.py) against the C struct of include/nanodec.h, field by
+    field, as a C compiler lays it out: a field added to one side only would shift every later field silently."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    header = open(os.path.join(ROOT, "include", "nanodec.h")).read()
+    body = header[header.index("typedef struct nd_config {"): header.index("} nd_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"int32_t\s+(\w+)\s*(?:\[\d+\])?\s*;", body)
+    assert fields == [f[0] for f in _lib.NdConfig._fields_], (fields, [f[0] for f in _lib.NdConfig._fields_])
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nanodec.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(nd_config));\n' +
+                   "".join('  printf("%%zu\\n", offsetof(nd_config, %s));\n' % f for f in fields) + "  return 0;\n}\n")
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    out = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.NdConfig)
+    assert out[1:] == [getattr(_lib.NdConfig, f).offset for f in fields]
+
+
+def test_ctypes_signatures_have_the_header_parameter_counts():
+    """Every prototype of include/nanodec.h against the ctypes argtypes in _lib.SIGNATURES: same number of parameters
+    (a parameter added to one side only corrupts the call frame without any error)."""
+    header = open(os.path.join(ROOT, "include", "nanodec.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = dict(re.findall(r"ND_EXPORT\s+[\w\s\*]+?\b(nd_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
