@@ -1204,8 +1204,9 @@ int decoder_step(nd_engine* e, const DecodeCtx& dc, GenParams gp, cudaStream_t s
         // AverageAttention (onmt/modules/average_attn.py:77-106, decoder/transformer.py:82-85): cumulative average of the
         // normalised inputs along the hypothesis (state prev_g per row, followed through the beams' parents), FFN, gates
         float* xn = R(e->sctx, d);
-        float* g_cur = e->selfK[l] + (int64_t)(dc.step & 1) * e->max_rows * d;          // [2][rows, d] inside the (unused) cache
-        const float* g_prev = e->selfK[l] + (int64_t)((dc.step & 1) ^ 1) * e->max_rows * d;
+        // the state of even / odd steps lives in the (otherwise unused) self-attention K / V cache buffers of the layer
+        float* g_cur = (dc.step & 1) ? e->selfV[l] : e->selfK[l];                        // [rows, d]
+        const float* g_prev = (dc.step & 1) ? e->selfK[l] : e->selfV[l];
         ND_LAUNCH(e, layernorm_rows(x, L.ln1.g, L.ln1.b, 1e-6f, xn, rows, d, st));
         ND_LAUNCH(e, avg_attn_cumulate(xn, g_prev, dc.beam ? e->beam.parent : nullptr, r0, rows, d, dc.step,
                                        g_cur + (int64_t)r0 * d, st));
