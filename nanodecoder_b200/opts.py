@@ -44,8 +44,9 @@ def translate_opts(parser: argparse.ArgumentParser) -> None:
     g.add_argument("--gemm_mode", "-gemm_mode", default="3xtf32", choices=["3xtf32", "tf32", "simt"],
                    help="arithmetic of the dense projections: 3xtf32 = fp32-parity tcgen05, tf32 = fast")
     g.add_argument("--kv_mode", "-kv_mode", default="q23", choices=["f32", "q23", "q15"],
-                   help="storage of the Transformer decoder's memory keys / values during greedy decode: q23 = 3-byte "
-                        "fixed point (parity mode, 3/4 of the bytes), f32, q15 = reduced precision (half the bytes)")
+                   help="storage of what the decoder's attention re-reads at every step (Transformer: memory keys / "
+                        "values; RNN: uh | H; CNN: encoder top | combined state): q23 = 3-byte fixed point (parity mode, "
+                        "3/4 of the bytes), f32, q15 = reduced precision (half the bytes; the CNN decoder keeps q23)")
     g = parser.add_argument_group("SpeechLike")
     g.add_argument("--fft", "-fft", type=bool, default=False)
     g.add_argument("--sample_rate", "-sample_rate", type=int, default=4000)
