@@ -182,3 +182,31 @@ def test_oracle_object_beam_extras_match_reference_golden():
                 want = g["ids"][b, n]
                 np.testing.assert_array_equal(o["predictions"][b][n].numpy(), want[want >= 0], err_msg=name)
         np.testing.assert_allclose(np.array(o["scores"], dtype=np.float32), g["scores"], rtol=1e-3, err_msg=name)
+
+
+def test_resnet_stem_is_a_stack_of_width3_time_convolutions():
+    """What the engine's ResNet stem relies on: on the [B, 1, 1, T] image the reference builds, the (5,3)
+    kernels with padding (2,1) only ever meet data through kernel row 2, and the (stride, 1) strides act on the height-1
+    axis, so T is never shortened.  Checked by re-running the oracle's conv2d stem with every other kernel row zeroed and
+    against a conv1d formulation of the first block."""
+    import torch.nn.functional as F
+    from nanodecoder_b200 import synth
+    from nanodecoder_b200.config import ModelConfig
+    from oracle.model import resnet_stem
+    cfg = ModelConfig.family("resnet2rnn", d_model=64, dec_layers=2)
+    sd = synth.make_state_dict(cfg, seed=5)
+    src = torch.randn(37, 3, 1)
+    full = resnet_stem(sd, "encoder.cnn", src)
+    assert list(full.shape) == [37, 3, 64]                      # T unchanged by the "stride 2" layers
+    sd2 = dict(sd)
+    for k, v in sd.items():
+        if k.startswith("encoder.cnn.") and v.dim() == 4 and v.size(2) == 5:
+            w = torch.zeros_like(v)
+            w[:, :, 2, :] = v[:, :, 2, :]
+            sd2[k] = w
+    assert torch.equal(resnet_stem(sd2, "encoder.cnn", src), full)
+    # first layer as a plain conv1d over time with kernel row 2
+    x = src[:, :, 0].t().unsqueeze(1)                           # [B, 1, T]
+    y1 = F.conv1d(x, sd["encoder.cnn.conv1.weight"][:, :, 2, :], None, padding=1)
+    y2 = F.conv2d(x.unsqueeze(2), sd["encoder.cnn.conv1.weight"], None, stride=(2, 1), padding=(2, 1)).squeeze(2)
+    assert torch.allclose(y1, y2, atol=1e-6)
