@@ -208,6 +208,20 @@ ND_EXPORT int nd_assembly_offsets(const char* text, const int64_t* offsets, int3
  *   int16, 3 = more than cap samples; *count = samples written so far.                                            */
 ND_EXPORT int nd_parse_signal_text(const char* text, int64_t nbytes, int16_t* out, int64_t cap, int64_t* count,
                                    int32_t* status);
+/* nd_fast5_read_signal: the raw samples of a single-read .fast5 file, i.e. what the reference's
+ *   h5py.File(path)['/Raw/Reads/'] -> first member (name order) -> ['Signal'].value reads (utils/labelop.py:199-214),
+ *   from an in-memory copy of the file (host pointers; no GPU involved).  *count = samples in the dataset; they are
+ *   written to out when cap >= *count (call with cap = 0 to size the buffer).  read_name receives the member's name
+ *   ("Read_1234").  A file that is not HDF5, lacks the path, or uses a feature outside the subset named in
+ *   csrc/fast5.cu (VBZ compression, dense groups, libver='latest' chunk indexes) returns ND_ERR_INVALID with the reason
+ *   in err (NUL terminated, cut at errcap).
+ * nd_h5_read_dataset: the same reader for any fixed- or floating-point dataset at `path` ("/a/b/c"): raw little/big
+ *   endian element bytes as stored.  info[8] = {type class (0 fixed, 1 float), element bytes, signed, big endian, rank,
+ *   total bytes, dim 0, dim 1}; bytes are written when cap >= info[5].                                            */
+ND_EXPORT int nd_fast5_read_signal(const uint8_t* file, int64_t nbytes, int16_t* out, int64_t cap, int64_t* count,
+                                   char* read_name, int32_t name_cap, char* err, int32_t errcap);
+ND_EXPORT int nd_h5_read_dataset(const uint8_t* file, int64_t nbytes, const char* path, uint8_t* out, int64_t cap,
+                                 int64_t* info, char* err, int32_t errcap);
 ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32_t n, const int8_t* lut,
                                  int32_t* counts, int64_t cap, int64_t* length, int32_t* err, int64_t* err_args);
 

@@ -49,6 +49,10 @@ SIGNATURES = {
     "nd_assembly_offsets": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32)]),
     "nd_parse_signal_text": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_int16), C.c_int64, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int32)]),
+    "nd_fast5_read_signal": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_int16), C.c_int64, C.POINTER(C.c_int64),
+                                       C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]),
+    "nd_h5_read_dataset": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.POINTER(C.c_uint8), C.c_int64,
+                                     C.POINTER(C.c_int64), C.c_char_p, C.c_int32]),
     "nd_simple_assembly": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int8),
                                      C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int64)]),

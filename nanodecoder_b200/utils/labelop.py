@@ -90,18 +90,35 @@ def simple_assembly(bpreads, flag_intersection=True):
     return counts[:, : length.value].astype(np.float64)
 
 
+def read_fast5_signal(path):
+    """(read name, int16 samples) of a single-read .fast5 file: the reference's
+    `list(h5py.File(path)['/Raw/Reads/'].values())[0]['Signal'].value` (utils/labelop.py:199-214), read by libnanodec's own
+    HDF5 reader (nd_fast5_read_signal, csrc/fast5.cu: h5py / libhdf5 are not needed).  Errors keep the reference's types
+    and texts: a file that is not HDF5 -> IOError('Error opening file. Likely a corrupted file.') (:203-204), anything wrong
+    below the root -> RuntimeError('Raw data is not stored in Raw/Reads/Read_[read#] ...') (:236-239), each with the
+    reader's reason appended."""
+    raw = open(path, "rb").read()
+    lib = _lib.load()
+    count, name, err = C.c_int64(0), C.create_string_buffer(256), C.create_string_buffer(512)
+    rc = lib.nd_fast5_read_signal(raw, len(raw), None, 0, C.byref(count), name, 256, err, 512)
+    out = np.empty(max(1, count.value), dtype=np.int16)
+    if rc == 0:
+        rc = lib.nd_fast5_read_signal(raw, len(raw), out.ctypes.data_as(C.POINTER(C.c_int16)), out.size, C.byref(count),
+                                      name, 256, err, 512)
+    if rc != 0:
+        why = err.value.decode("latin-1")
+        if "signature not found" in why or "superblock" in why:
+            raise IOError("Error opening file. Likely a corrupted file. (%s)" % why)
+        raise RuntimeError("Raw data is not stored in Raw/Reads/Read_[read#] so new segments cannot be identified. (%s)"
+                           % why)
+    return name.value.decode("latin-1"), out[: count.value]
+
+
 def read_raw_signal(path, suffix):
     """Raw samples of one read (utils/labelop.py:199-219 without the normalisation): int16 for DAC values (fast5 `Signal`
     datasets, integer `.signal` files), float64 for a `.signal` file with non-integer values."""
     if suffix == "fast5":
-        try:
-            import h5py
-        except ImportError as e:       # pragma: no cover - h5py is not part of this image
-            raise ImportError("reading .fast5 files needs h5py (not installed here); "
-                              "export reads as .signal text files instead") from e
-        with h5py.File(path, "r") as f:
-            raw = list(f["/Raw/Reads/"].values())[0]["Signal"][()]
-        return np.asarray(raw, dtype=np.int16)
+        return read_fast5_signal(path)[1]
     raw = open(path, "rb").read()
     out = np.empty(len(raw) // 2 + 1, dtype=np.int16)           # every sample takes at least a digit and a separator
     count, status = C.c_int64(0), C.c_int32(0)

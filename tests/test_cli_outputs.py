@@ -100,12 +100,20 @@ def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path, threads):
     rng = np.random.default_rng(11)
     sizes = [200, 0, 64, 333, 65, 700, 1, 129, 500, 90, 260]            # one empty read, several ragged tails
     raws = []
+    import h5_writer
+    fast5 = {3: "old", 5: "new", 8: "old"}                               # three reads arrive as .fast5 (HDF5) files
     for i, n in enumerate(sizes):
         x = rng.integers(300, 900, size=n)
-        (src / ("r%02d.signal" % i)).write_text(" ".join(map(str, x)))
+        if i in fast5:
+            (src / ("r%02d.fast5" % i)).write_bytes(h5_writer.make_fast5(
+                x.astype(np.int16), read_name="Read_%d" % (100 + i), flavour=fast5[i], chunk=128 if fast5[i] == "old" else None))
+        else:
+            (src / ("r%02d.signal" % i)).write_text(" ".join(map(str, x)))
         raws.append(x.astype(np.int16))
     (src / "r11.signal").write_text("512 garbage 7")                     # a corrupt read: reported and skipped, per read
-    sizes.append(0)
+    (src / "r12.fast5").write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(200))     # a truncated HDF5 file: same
+    sizes += [0, 0]
+    suffix = {i: ("fast5" if i in fast5 or i == 12 else "signal") for i in range(len(sizes))}
     opt = _opt(str(tmp_path / "out"), stride=T, length=T)
     opt.src_dir, opt.thread, opt.batch_size, opt.attn_debug = str(src), threads, B, False   # groups of 8 * threads reads
 
@@ -120,7 +128,8 @@ def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path, threads):
         return torch.from_numpy(chunks), torch.from_numpy(lens), cr
 
     tr, eng = _translator(L, batch_size=B)
-    todo = [(i, ("r%02d.signal" % i, "signal", "r%02d.txt" % i)) for i in range(len(sizes))]
+    todo = [(i, ("r%02d.%s" % (i, suffix[i]), suffix[i], "r%02d.txt" % i)) for i in range(len(sizes))]
+    assert [(t[0], t[1]) for t in cli.list_reads(opt)[0]] == [t[1][:2] for t in todo]
     lines = cli.run_reads(opt, todo, read_raw_signal, frontend, tr)
     cli.finish_lines(opt, lines)
 

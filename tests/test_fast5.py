@@ -1,0 +1,189 @@
+"""CPU: .fast5 ingestion (utils/labelop.py:199-214: h5py.File(path)['/Raw/Reads/'] -> first member -> ['Signal'].value)
+through libnanodec's own HDF5 reader (nd_fast5_read_signal / nd_h5_read_dataset, csrc/fast5.cu; host code, no GPU).
+
+Pinning: (1) a file written by libhdf5 itself (MATLAB 7.3 = HDF5 with a 512-byte user block; scipy ships it as a test
+fixture, copied to tests/golden/libhdf5_matlab73.mat) pins superblock, symbol-table group, B-tree, SNOD, local heap,
+object header, dataspace, datatype and contiguous layout; (2) single-read fast5 skeletons laid out by tests/h5_writer.py
+from the format specification pin the chunk B-tree and the filter pipeline; (3) the inflate implementation is checked
+against Python's zlib over every deflate block type."""
+import ctypes as C
+import os
+import sys
+import zlib
+
+import numpy as np
+import pytest
+
+from nanodecoder_b200 import _lib
+from nanodecoder_b200.utils import labelop
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import h5_writer as hw  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def read_dataset(raw, path):
+    lib = _lib.load()
+    info, err = (C.c_int64 * 8)(), C.create_string_buffer(512)
+    rc = lib.nd_h5_read_dataset(raw, len(raw), path.encode(), None, 0, info, err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    buf = (C.c_uint8 * max(1, info[5]))()
+    rc = lib.nd_h5_read_dataset(raw, len(raw), path.encode(), buf, info[5], info, err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return list(info), bytes(buf)[: info[5]]
+
+
+def read_signal(raw, tmp_path, name="r.fast5"):
+    p = tmp_path / name
+    p.write_bytes(raw)
+    return labelop.read_fast5_signal(str(p))
+
+
+def dac(n, seed=0):
+    """DAC-like samples: a slow level sequence plus noise, so deflate finds matches and literals"""
+    rng = np.random.default_rng(seed)
+    levels = np.repeat(rng.integers(350, 700, n // 9 + 1), 9)[:n]
+    return (levels + rng.integers(-12, 13, n)).astype(np.int16)
+
+
+def test_file_written_by_libhdf5():
+    raw = open(os.path.join(GOLDEN, "libhdf5_matlab73.mat"), "rb").read()
+    assert raw[512:520] == b"\x89HDF\r\n\x1a\n"                    # superblock behind MATLAB's 512-byte user block
+    info, data = read_dataset(raw, "/testdouble")
+    assert info[:5] == [1, 8, 1, 0, 2] and info[6:8] == [9, 1]     # float, 8 bytes, little endian, rank 2, 9 x 1
+    got = np.frombuffer(data, "<f8")
+    assert np.array_equal(got, np.arange(0, 2 * np.pi + 1e-9, np.pi / 4))   # scipy's `testdouble` vector, bit for bit
+    with pytest.raises(RuntimeError, match="no object named 'nope'"):
+        read_dataset(raw, "/nope")
+    with pytest.raises(RuntimeError, match="Raw"):                # a valid HDF5 file without /Raw/Reads
+        p = os.path.join(GOLDEN, "libhdf5_matlab73.mat")
+        labelop.read_fast5_signal(p)
+
+
+@pytest.mark.parametrize("flavour,chunk,filters", [
+    ("old", 4096, (2, 1)),            # MinKNOW's layout: chunked, shuffle + gzip
+    ("old", 1000, (1,)),              # gzip only, ragged last chunk
+    ("old", 777, (3, 2, 1)),          # fletcher32 below shuffle + gzip
+    ("old", 512, (1, 3)),             # fletcher32 on top of gzip
+    ("old", 300, ()),                 # chunked, no filter
+    ("old", "contiguous", ()),
+    ("old", "compact", ()),
+    ("old_sb1", 2048, (2, 1)),        # superblock version 1
+    ("new", None, (2, 1)),            # libver latest: superblock 2, OHDR v2, link messages, single-chunk index
+    ("new", None, ()),
+    ("new", "implicit", ()),
+    ("new", 640, (2, 1)),             # new-style groups around a v3 chunked layout
+])
+def test_signal_round_trip(tmp_path, flavour, chunk, filters):
+    n = 3000 if chunk == "compact" else 20011
+    sig = dac(n, seed=len(filters) + n)
+    raw = hw.make_fast5(sig, read_name="Read_271", chunk=chunk, filters=filters, flavour=flavour)
+    name, got = read_signal(raw, tmp_path)
+    assert name == "Read_271"
+    assert got.dtype == np.int16 and np.array_equal(got, sig)
+
+
+def test_first_read_in_name_order_and_user_block(tmp_path):
+    sig = dac(5000, 3)
+    for flavour in ("old", "new"):
+        # h5py's values() iterates by name: "Read_1000" < "Read_999" < "read_5" bytewise
+        raw = hw.make_fast5(sig, read_name="Read_1000", chunk=1024 if flavour == "old" else None, flavour=flavour,
+                            other_reads=("Read_999", "read_5", "Read_10000"), userblock=1024)
+        name, got = read_signal(raw, tmp_path)
+        assert name == "Read_1000" and np.array_equal(got, sig)
+
+
+def test_wide_groups_and_deep_trees(tmp_path):
+    sig = dac(70000, 5)
+    decoys = tuple("Read_%05d" % i for i in range(20000, 20060))      # 61 members: 8 SNODs under a 3-level B-tree
+    raw = hw.make_fast5(sig, read_name="Read_00042", chunk=256, filters=(2, 1), other_reads=decoys, group_levels=3,
+                        fan=5, cache_root=False)                       # 274 chunks under a 4-level chunk B-tree
+    name, got = read_signal(raw, tmp_path)
+    assert name == "Read_00042" and np.array_equal(got, sig)
+
+
+def test_filter_mask_missing_chunks_continuation_and_types(tmp_path):
+    sig = dac(10000, 7)
+    w = hw.H5Writer()
+    raw = hw.make_fast5(sig, chunk=1000, filters=(2, 1), skip_filter_on=(2, 9), missing=(4,),
+                        extra_messages=[w.msg_attribute_stub(), w.msg_attribute_stub()], split_at=3)
+    want = sig.copy()
+    want[4000:5000] = 0                                                # a chunk that was never written reads as fill value 0
+    assert np.array_equal(read_signal(raw, tmp_path)[1], want)
+    # other integer types h5py would hand back are accepted while they fit the int16 DAC range
+    for dt in ("<u2", ">i2", "<i4", "<u1", ">i8"):
+        vals = (np.abs(sig[:3000]) % (200 if dt == "<u1" else 30000)).astype(dt)
+        got = read_signal(hw.make_fast5(vals, chunk=700, filters=(2, 1)), tmp_path)[1]
+        assert np.array_equal(got, vals.astype(np.int16))
+    big = np.array([1, 40000, 2], "<i4")
+    with pytest.raises(RuntimeError, match="outside the int16 DAC range"):
+        read_signal(hw.make_fast5(big, chunk="contiguous"), tmp_path)
+    assert read_signal(hw.make_fast5(np.zeros(0, np.int16), chunk="contiguous"), tmp_path)[1].size == 0
+    v1 = hw.make_fast5(sig, chunk="contiguous", layout_version=1)      # layout message version 1 (HDF5 1.4 / 1.6 files)
+    assert np.array_equal(read_signal(v1, tmp_path)[1], sig)
+    v2 = hw.make_fast5(sig, chunk=999, filters=(1,), layout_version=2)
+    assert np.array_equal(read_signal(v2, tmp_path)[1], sig)
+
+
+@pytest.mark.parametrize("level,strategy", [(0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY),
+                                            (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                                            (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE)])
+def test_inflate_against_zlib(tmp_path, level, strategy):
+    """stored, fixed-Huffman and dynamic-Huffman blocks; long matches, maximal distances, incompressible input"""
+    rng = np.random.default_rng(level * 10 + strategy)
+    cases = [dac(50000, 1),
+             rng.integers(-32768, 32768, 40000).astype(np.int16),                  # incompressible: stored / literal blocks
+             np.zeros(70000, np.int16),                                             # length-258 matches at distance 1
+             np.tile(rng.integers(0, 900, 16500).astype(np.int16), 3),              # distances beyond 32 000 bytes
+             np.array([5], np.int16),
+             np.arange(40000, dtype=np.int16)]
+    for sig in cases:
+        raw = hw.make_fast5(sig, chunk=len(sig), filters=(1,), level=level, strategy=strategy)
+        assert np.array_equal(read_signal(raw, tmp_path)[1], sig)
+
+
+def test_errors_keep_the_reference_types(tmp_path):
+    sig = dac(4000, 9)
+    good = hw.make_fast5(sig, chunk=1000, filters=(2, 1))
+    with pytest.raises(IOError, match="Likely a corrupted file"):                   # labelop.py:203-204
+        read_signal(b"not an hdf5 file" * 100, tmp_path)
+    with pytest.raises(IOError, match="Likely a corrupted file"):
+        read_signal(b"", tmp_path)
+    # VBZ (ONT's zstd + streamvbyte filter) is named in the message
+    vbz = hw.make_fast5(sig, chunk=1000, filters=(32020,))
+    with pytest.raises(RuntimeError, match="VBZ filter"):
+        read_signal(vbz, tmp_path)
+    # truncation and bit flips anywhere never crash: they either read (flip in padding) or raise one of the two errors
+    for cut in (len(good) // 7, len(good) // 2, len(good) - 9):
+        with pytest.raises((RuntimeError, IOError)):
+            read_signal(good[:cut], tmp_path)
+    rng = np.random.default_rng(0)
+    outcomes = {"ok": 0, "same": 0, "raised": 0}
+    for _ in range(400):
+        bad = bytearray(good)
+        for pos in rng.integers(0, len(bad), 3):
+            bad[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            got = read_signal(bytes(bad), tmp_path)[1]
+            outcomes["same" if np.array_equal(got, sig) else "ok"] += 1
+        except (RuntimeError, IOError):
+            outcomes["raised"] += 1
+    assert sum(outcomes.values()) == 400 and outcomes["raised"] > 50, outcomes
+    # a corrupted deflate stream is caught by the adler32 check or the length check, not returned as samples
+    start = good.index(zlib.compress(hw.H5Writer.encode_chunk(sig[:1000].tobytes(), 2, (2,)), 1)[:8])
+    bad = bytearray(good)
+    bad[start + 40] ^= 0x10
+    with pytest.raises(RuntimeError):
+        read_signal(bytes(bad), tmp_path)
+
+
+def test_read_raw_signal_and_cli_loader(tmp_path):
+    """the reference's worker: suffix 'fast5' -> the Signal dataset, the same samples a .signal export of the read holds"""
+    sig = dac(12345, 11)
+    (tmp_path / "a.fast5").write_bytes(hw.make_fast5(sig, chunk=4096))
+    (tmp_path / "a.signal").write_text(" ".join(str(int(x)) for x in sig))
+    a = labelop.read_raw_signal(str(tmp_path / "a.fast5"), "fast5")
+    b = labelop.read_raw_signal(str(tmp_path / "a.signal"), "signal")
+    assert a.dtype == b.dtype == np.int16 and np.array_equal(a, b)
