@@ -32,30 +32,41 @@ struct H5Error {
 [[noreturn]] void fail(const std::string& m) { throw H5Error{m}; }
 
 // ---------------------------------------------------------------- inflate (RFC 1951) + zlib container (RFC 1950)
+// Bits are consumed from the low end of a 64-bit window that is topped up a byte at a time.
 struct BitReader {
   const uint8_t* p;
   size_t n, pos = 0;
-  uint32_t acc = 0;
+  uint64_t acc = 0;
   int cnt = 0;
   BitReader(const uint8_t* p_, size_t n_) : p(p_), n(n_) {}
-  uint32_t bits(int need) {
-    while (cnt < need) {
-      if (pos >= n) fail("deflate stream ends early");
-      acc |= (uint32_t)p[pos++] << cnt;
+  inline void refill() {
+    while (cnt <= 56 && pos < n) {
+      acc |= (uint64_t)p[pos++] << cnt;
       cnt += 8;
     }
-    const uint32_t v = need == 32 ? acc : (acc & ((1u << need) - 1u));
-    acc = need >= 32 ? 0 : acc >> need;
+  }
+  inline uint32_t bits(int need) {                    // need <= 16
+    if (cnt < need) {
+      refill();
+      if (cnt < need) fail("deflate stream ends early");
+    }
+    const uint32_t v = (uint32_t)(acc & ((1ull << need) - 1ull));
+    acc >>= need;
     cnt -= need;
     return v;
   }
-  void align() { acc = 0; cnt = 0; }
+  inline void drop(int k) { acc >>= k; cnt -= k; }
+  void align() { drop(cnt & 7); }                      // to the next byte boundary; whole bytes stay in the window
+  size_t byte_pos() const { return pos - (size_t)(cnt >> 3); }
 };
 
-// canonical Huffman code: count[len] codes of each length, symbols ordered by (length, value)
+// canonical Huffman code: count[len] codes of each length, symbols ordered by (length, value); codes of up to kFastBits
+// bits are decoded with one lookup in `fast` (entry = length << 9 | symbol, 0 = longer code: canonical walk).
+const int kFastBits = 10;
 struct Huffman {
   uint16_t count[16];
   uint16_t symbol[288];
+  uint16_t fast[1 << kFastBits];
   bool build(const uint8_t* lens, int n) {
     memset(count, 0, sizeof(count));
     for (int i = 0; i < n; ++i) ++count[lens[i]];
@@ -66,13 +77,36 @@ struct Huffman {
       if (left < 0) return false;                     // over-subscribed
     }
     uint16_t offs[16];
+    uint32_t next_code[16];
     offs[1] = 0;
-    for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + count[l];
-    for (int i = 0; i < n; ++i)
-      if (lens[i]) symbol[offs[lens[i]]++] = (uint16_t)i;
+    next_code[1] = 0;
+    for (int l = 1; l < 15; ++l) {
+      offs[l + 1] = offs[l] + count[l];
+      next_code[l + 1] = (next_code[l] + count[l]) << 1;
+    }
+    memset(fast, 0, sizeof(fast));
+    for (int i = 0; i < n; ++i) {
+      const int l = lens[i];
+      if (!l) continue;
+      symbol[offs[l]++] = (uint16_t)i;
+      const uint32_t code = next_code[l]++;
+      if (l <= kFastBits) {
+        uint32_t rev = 0;                             // codes enter the stream most significant bit first
+        for (int b = 0; b < l; ++b) rev |= ((code >> b) & 1u) << (l - 1 - b);
+        for (uint32_t idx = rev; idx < (1u << kFastBits); idx += 1u << l) fast[idx] = (uint16_t)((l << 9) | i);
+      }
+    }
     return true;
   }
-  int decode(BitReader& br) const {
+  inline int decode(BitReader& br) const {
+    if (br.cnt < 15) br.refill();
+    const uint16_t e = fast[br.acc & ((1u << kFastBits) - 1u)];
+    if (e) {
+      const int l = e >> 9;
+      if (l > br.cnt) fail("deflate stream ends early");
+      br.drop(l);
+      return e & 511;
+    }
     int code = 0, first = 0, index = 0;
     for (int l = 1; l < 16; ++l) {
       code |= (int)br.bits(1);
@@ -94,12 +128,13 @@ const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97,
 const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12,
                                 13, 13};
 
-void inflate_codes(BitReader& br, const Huffman& lit, const Huffman& dist, std::vector<uint8_t>& out, size_t limit) {
+// `out` is sized to `limit` up front; `have` counts the bytes produced so far.
+void inflate_codes(BitReader& br, const Huffman& lit, const Huffman& dist, uint8_t* out, size_t& have, size_t limit) {
   for (;;) {
     const int sym = lit.decode(br);
     if (sym < 256) {
-      if (out.size() >= limit) fail("deflate stream is longer than the chunk it fills");
-      out.push_back((uint8_t)sym);
+      if (have >= limit) fail("deflate stream is longer than the chunk it fills");
+      out[have++] = (uint8_t)sym;
     } else if (sym == 256) {
       return;
     } else {
@@ -108,16 +143,19 @@ void inflate_codes(BitReader& br, const Huffman& lit, const Huffman& dist, std::
       const int ds = dist.decode(br);
       if (ds > 29) fail("invalid distance symbol in deflate stream");
       const size_t d = kDistBase[ds] + br.bits(kDistExtra[ds]);
-      if (d > out.size()) fail("deflate distance reaches before the start of the output");
-      if (out.size() + len > limit) fail("deflate stream is longer than the chunk it fills");
-      size_t from = out.size() - d;
-      for (size_t i = 0; i < len; ++i) out.push_back(out[from + i]);     // overlapping copies repeat, byte by byte
+      if (d > have) fail("deflate distance reaches before the start of the output");
+      if (have + len > limit) fail("deflate stream is longer than the chunk it fills");
+      uint8_t* dst = out + have;
+      const uint8_t* src = dst - d;
+      for (size_t i = 0; i < len; ++i) dst[i] = src[i];                   // overlapping copies repeat, byte by byte
+      have += len;
     }
   }
 }
 
-void inflate_raw(BitReader& br, std::vector<uint8_t>& out, size_t limit) {
+void inflate_raw(BitReader& br, uint8_t* out, size_t& have, size_t limit) {
   static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  Huffman lit, dist;
   for (;;) {
     const uint32_t last = br.bits(1);
     const uint32_t type = br.bits(2);
@@ -125,22 +163,24 @@ void inflate_raw(BitReader& br, std::vector<uint8_t>& out, size_t limit) {
       br.align();
       const uint32_t len = br.bits(16), nlen = br.bits(16);
       if ((len ^ 0xffffu) != nlen) fail("stored deflate block with inconsistent length");
-      if (br.pos + len > br.n) fail("deflate stream ends early");
-      if (out.size() + len > limit) fail("deflate stream is longer than the chunk it fills");
-      out.insert(out.end(), br.p + br.pos, br.p + br.pos + len);
-      br.pos += len;
+      if (have + len > limit) fail("deflate stream is longer than the chunk it fills");
+      uint32_t todo = len;
+      while (todo && br.cnt) { out[have++] = (uint8_t)br.bits(8); --todo; }   // bytes already in the window
+      if (br.pos + todo > br.n) fail("deflate stream ends early");
+      memcpy(out + have, br.p + br.pos, todo);
+      have += todo;
+      br.pos += todo;
     } else if (type == 1) {
       uint8_t lens[288];
       for (int i = 0; i < 144; ++i) lens[i] = 8;
       for (int i = 144; i < 256; ++i) lens[i] = 9;
       for (int i = 256; i < 280; ++i) lens[i] = 7;
       for (int i = 280; i < 288; ++i) lens[i] = 8;
-      Huffman lit, dist;
       lit.build(lens, 288);
       uint8_t dl[30];
       for (int i = 0; i < 30; ++i) dl[i] = 5;
       dist.build(dl, 30);
-      inflate_codes(br, lit, dist, out, limit);
+      inflate_codes(br, lit, dist, out, have, limit);
     } else if (type == 2) {
       const int nlen = (int)br.bits(5) + 257, ndist = (int)br.bits(5) + 1, ncode = (int)br.bits(4) + 4;
       if (nlen > 286 || ndist > 30) fail("deflate block with too many codes");
@@ -172,10 +212,9 @@ void inflate_raw(BitReader& br, std::vector<uint8_t>& out, size_t limit) {
         }
       }
       if (all[256] == 0) fail("deflate block without an end code");
-      Huffman lit, dist;
       if (!lit.build(all, nlen)) fail("deflate literal code is over-subscribed");
       if (!dist.build(all + nlen, ndist)) fail("deflate distance code is over-subscribed");
-      inflate_codes(br, lit, dist, out, limit);
+      inflate_codes(br, lit, dist, out, have, limit);
     } else {
       fail("reserved deflate block type");
     }
@@ -200,10 +239,14 @@ void zlib_decompress(const uint8_t* p, size_t n, std::vector<uint8_t>& out, size
   if ((cmf & 15u) != 8u || (cmf >> 4) > 7u || ((cmf << 8) | flg) % 31u != 0u) fail("not a zlib (deflate) stream");
   if (flg & 0x20u) fail("zlib stream with a preset dictionary");
   BitReader br(p + 2, n - 2);
-  out.clear();
-  inflate_raw(br, out, limit);
-  if (br.pos + 4 > br.n) fail("zlib stream without its adler32 checksum");
-  const uint8_t* c = br.p + br.pos;
+  out.resize(limit);
+  size_t have = 0;
+  inflate_raw(br, out.data(), have, limit);
+  out.resize(have);
+  br.align();
+  const size_t at = br.byte_pos();
+  if (at + 4 > br.n) fail("zlib stream without its adler32 checksum");
+  const uint8_t* c = br.p + at;
   const uint32_t want = ((uint32_t)c[0] << 24) | ((uint32_t)c[1] << 16) | ((uint32_t)c[2] << 8) | c[3];
   if (adler32(out.data(), out.size()) != want) fail("zlib adler32 checksum mismatch");
 }
@@ -683,8 +726,9 @@ class H5File {
   // One stored chunk -> elements [elem_off, elem_off + chunk) of the dataset (edge chunks are stored whole).
   void place_chunk(const Dataset& d, uint64_t abs_addr, uint64_t stored, uint32_t mask, uint64_t elem_off, std::vector<uint8_t>& out) {
     const uint64_t cbytes = d.chunk[0] * d.elem;
-    if (cbytes > (1ull << 32)) fail("chunk larger than 4 GiB");
     need_abs(abs_addr, stored);
+    // deflate expands at most ~1032 x: a larger chunk shape is a corrupt layout message, not something to allocate
+    if (cbytes > (1ull << 32) || cbytes > stored * 1100 + 65536) fail("chunk shape larger than its stored bytes can fill");
     std::vector<uint8_t> a(p_ + abs_addr, p_ + abs_addr + stored), b;
     for (int f = (int)d.filters.size() - 1; f >= 0; --f) {                  // undo the pipeline back to front
       if (mask & (1u << f)) continue;                                       // the writer skipped this filter for this chunk
