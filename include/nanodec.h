@@ -212,9 +212,9 @@ ND_EXPORT int nd_parse_signal_text(const char* text, int64_t nbytes, int16_t* ou
  *   h5py.File(path)['/Raw/Reads/'] -> first member (name order) -> ['Signal'].value reads (utils/labelop.py:199-214),
  *   from an in-memory copy of the file (host pointers; no GPU involved).  *count = samples in the dataset; they are
  *   written to out when cap >= *count (call with cap = 0 to size the buffer).  read_name receives the member's name
- *   ("Read_1234").  A file that is not HDF5, lacks the path, or uses a feature outside the subset named in
- *   csrc/fast5.cu (VBZ compression, dense groups, libver='latest' chunk indexes) returns ND_ERR_INVALID with the reason
- *   in err (NUL terminated, cut at errcap).
+ *   ("Read_1234").  Gzip, shuffle, fletcher32 and VBZ (zstd + streamvbyte) chunks are decoded.  A file that is not
+ *   HDF5, lacks the path, or uses a feature outside the subset named in csrc/fast5.cu (dense groups, libver='latest'
+ *   chunk indexes, VBZ version 1) returns ND_ERR_INVALID with the reason in err (NUL terminated, cut at errcap).
  * nd_h5_read_dataset: the same reader for any fixed- or floating-point dataset at `path` ("/a/b/c"): raw little/big
  *   endian element bytes as stored.  info[8] = {type class (0 fixed, 1 float), element bytes, signed, big endian, rank,
  *   total bytes, dim 0, dim 1}; bytes are written when cap >= info[5].                                            */
@@ -222,6 +222,10 @@ ND_EXPORT int nd_fast5_read_signal(const uint8_t* file, int64_t nbytes, int16_t*
                                    char* read_name, int32_t name_cap, char* err, int32_t errcap);
 ND_EXPORT int nd_h5_read_dataset(const uint8_t* file, int64_t nbytes, const char* path, uint8_t* out, int64_t cap,
                                  int64_t* info, char* err, int32_t errcap);
+/* nd_zstd_decompress: the Zstandard decoder (RFC 8878, no dictionaries) behind the VBZ filter of .fast5 chunks, exposed
+ *   so that it can be checked against libzstd-written frames: src -> out (at most cap bytes), *count = bytes written. */
+ND_EXPORT int nd_zstd_decompress(const uint8_t* src, int64_t nbytes, uint8_t* out, int64_t cap, int64_t* count, char* err,
+                                 int32_t errcap);
 ND_EXPORT int nd_simple_assembly(const char* text, const int64_t* offsets, int32_t n, const int8_t* lut,
                                  int32_t* counts, int64_t cap, int64_t* length, int32_t* err, int64_t* err_args);
 

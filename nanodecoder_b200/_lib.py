@@ -53,6 +53,8 @@ SIGNATURES = {
                                        C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]),
     "nd_h5_read_dataset": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.POINTER(C.c_uint8), C.c_int64,
                                      C.POINTER(C.c_int64), C.c_char_p, C.c_int32]),
+    "nd_zstd_decompress": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_int64),
+                                     C.c_char_p, C.c_int32]),
     "nd_simple_assembly": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int8),
                                      C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int64)]),

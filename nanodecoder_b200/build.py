@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnanodec.so")
 SOURCES = ["engine.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm.cu", "lstm_tc.cu", "attention.cu", "cross_attn_packed.cu", "cross_attn_ring.cu", "enc_attn_tc.cu", "elementwise.cu",
-           "beam.cu", "frontend.cu", "assembly.cu", "fast5.cu"]
+           "beam.cu", "frontend.cu", "assembly.cu", "fast5.cu", "vbz.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("ND_EXTRA_NVCC_FLAGS", "").split()

@@ -7,9 +7,10 @@
 //   (symbol-table message -> v1 B-tree + SNOD nodes + local heap) and new-style groups with compact link messages,
 //   dataspace v1/v2, fixed-point / floating-point datatypes, data layout v1-v3 (compact, contiguous, chunked through the
 //   v1 chunk B-tree) and v4 (single-chunk / implicit index), filter pipeline v1/v2 with deflate (own inflate, RFC 1950 /
-//   1951), shuffle and fletcher32.
+//   1951),
+//   shuffle, fletcher32 and ONT's VBZ (id 32020: zstd over streamvbyte, own decoders in vbz.cu).
 // Refused with the reason in the message: dense link storage (fractal heap), the v4 fixed / extensible array and v2
-// B-tree chunk indexes, and the VBZ filter (id 32020: zstd + streamvbyte, needs a zstd decoder).
+// B-tree chunk indexes, VBZ version 1 chunks.
 // h5py iterates a group's members in NAME order (H5_INDEX_NAME, increasing), which is what "the first read" means above:
 // the B-tree of an old-style group is already sorted by name; link messages are sorted here.
 // Every offset read from the file is bounds-checked: a corrupt file gives an error, never a wild read.
@@ -22,14 +23,12 @@
 #include <vector>
 
 #include "../../include/nanodec.h"
+#include "host_io.h"
 
 namespace {
 
-struct H5Error {
-  std::string msg;
-};
-
-[[noreturn]] void fail(const std::string& m) { throw H5Error{m}; }
+typedef ndhost::Error H5Error;
+using ndhost::fail;
 
 // ---------------------------------------------------------------- inflate (RFC 1951) + zlib container (RFC 1950)
 // Bits are consumed from the low end of a 64-bit window that is topped up a byte at a time.
@@ -749,9 +748,9 @@ class H5File {
       } else if (flt.id == 3) {
         if (a.size() < 4) fail("chunk shorter than its fletcher32 checksum");
         a.resize(a.size() - 4);
-      } else if (flt.id == 32020) {
-        fail("Signal is compressed with the VBZ filter (id 32020: zstd + streamvbyte), which is not supported; "
-             "recompress the file with gzip (ont_fast5_api compress_fast5 -c gzip) or export .signal text");
+      } else if (flt.id == 32020) {                                          // ONT's VBZ: zstd over streamvbyte (vbz.cu)
+        ndhost::vbz_decompress(a.data(), a.size(), flt.client.data(), (int)flt.client.size(), b, cbytes + 4);
+        a.swap(b);
       } else {
         fail("unsupported HDF5 filter id " + std::to_string(flt.id));
       }

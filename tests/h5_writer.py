@@ -188,12 +188,15 @@ class H5Writer:
                 raw = c.compress(raw) + c.flush()
             elif fid == 3:
                 raw = raw + b"\xde\xad\xbe\xef"                        # the reader strips, does not verify
-            else:                                                      # unknown / VBZ: stored as is, the reader must refuse
+            elif fid == 32020:
+                raw = vbz_encode(raw, elem, level)
+            else:                                                      # unknown filter: stored as is, the reader must refuse
                 pass
         return raw
 
     def dataset_chunked(self, arr, type_msg, chunk, filters=(2, 1), level=1, strategy=zlib.Z_DEFAULT_STRATEGY, fan=64,
-                        skip_filter_on=(), missing=(), extra_messages=(), split_at=None, layout_version=3):
+                        skip_filter_on=(), missing=(), extra_messages=(), split_at=None, layout_version=3,
+                        kw_vbz_version=0):
         """1-D chunked dataset.  skip_filter_on: chunk numbers stored with every filter skipped (filter mask set);
         missing: chunk numbers never written (read back as zeros)."""
         n, elem = arr.shape[0], arr.dtype.itemsize
@@ -230,7 +233,7 @@ class H5Writer:
                 break
         btree = children[0][3] if entries else UNDEF
         names = {1: "deflate", 2: "shuffle", 3: "fletcher32", 32020: "vbz"}
-        cds = {1: [level], 2: [elem], 3: [], 32020: [0, 2, 1, 1]}
+        cds = {1: [level], 2: [elem], 3: [], 32020: [kw_vbz_version, elem, 1, level]}
         if layout_version == 3:
             lay = struct.pack("<BBBQ", 3, 2, 2, btree) + struct.pack("<II", chunk, elem)
         else:                                                          # v1 / v2: dimensionality, class, reserved, address, dims
@@ -284,6 +287,77 @@ class H5Writer:
         assert len(sb) <= self.sb_size, (len(sb), self.sb_size)
         self.buf[self.base:self.base + len(sb)] = sb
         return bytes(self.buf)
+
+
+def zstd_compress(raw, level=1):
+    """libzstd itself (the copy bundled with pyarrow)"""
+    import pyarrow as pa
+    return pa.Codec("zstd", compression_level=level).compress(raw, asbytes=True)
+
+
+def zstd_frame_features(blob, found=None):
+    """Which parts of the format one libzstd-written frame uses (block types, literal section types, stream counts,
+    Huffman weight encodings, sequence table modes): the decoder test asserts its corpus covers all of them."""
+    from collections import Counter
+    found = Counter() if found is None else found
+    o = 4
+    fhd = blob[o]
+    single, fcs = (fhd >> 5) & 1, fhd >> 6
+    o += 1 + (0 if single else 1) + [0, 1, 2, 4][fhd & 3] + ((1 if single else 0) if fcs == 0 else [0, 2, 4, 8][fcs])
+    while True:
+        bh = int.from_bytes(blob[o:o + 3], "little")
+        o += 3
+        last, kind, size = bh & 1, (bh >> 1) & 3, bh >> 3
+        found["block_" + ("raw", "rle", "compressed")[kind]] += 1
+        if kind == 2:
+            p = blob[o:o + size]
+            lt, fmt = p[0] & 3, (p[0] >> 2) & 3
+            found["literals_" + ("raw", "rle", "huffman", "treeless")[lt]] += 1
+            if lt < 2:
+                regen, q = ((p[0] >> 3, 1) if fmt & 1 == 0 else ((p[0] >> 4) | (p[1] << 4), 2) if fmt == 1 else
+                            ((p[0] >> 4) | (p[1] << 4) | (p[2] << 12), 3))
+                q += regen if lt == 0 else 1
+            else:
+                h = int.from_bytes(p[:5], "little")
+                hdr, comp = ((3, (h >> 14) & 0x3FF) if fmt < 2 else (4, (h >> 18) & 0x3FFF) if fmt == 2 else
+                             (5, (h >> 22) & 0x3FFFF))
+                found["streams_%d" % (1 if fmt == 0 else 4)] += 1
+                if lt == 2:
+                    found["weights_fse" if p[hdr] < 128 else "weights_direct"] += 1
+                q = hdr + comp
+            ns = p[q]
+            if ns == 0:
+                found["no_sequences"] += 1
+            else:
+                q += 1 if ns < 128 else 2 if ns < 255 else 3
+                found["nseq_%d_byte" % (1 if ns < 128 else 2 if ns < 255 else 3)] += 1
+                for name, sh in (("ll", 6), ("of", 4), ("ml", 2)):
+                    found[name + "_" + ("predefined", "rle", "fse", "repeat")[(p[q] >> sh) & 3]] += 1
+        o += 1 if kind == 1 else size
+        if last:
+            return found
+
+
+def vbz_encode(raw, elem, level=1, zigzag=True):
+    """ONT's VBZ chunk, version 0: uint32 size | zstd(streamvbyte(zig-zag(delta(x)))) with 32-bit streamvbyte: one 2-bit
+    key per value (bytes - 1, four values per key byte, low bits first), all keys, then all data bytes little endian"""
+    x = np.frombuffer(raw, {1: "<i1", 2: "<i2", 4: "<i4"}[elem]).astype(np.int64)
+    if zigzag:
+        d = np.diff(x, prepend=0)
+        d = ((d + 2 ** 31) % 2 ** 32 - 2 ** 31).astype(np.int64)     # the filter works in 32-bit arithmetic
+        u = ((d << 1) ^ (d >> 31)) & 0xFFFFFFFF
+    else:
+        u = x & 0xFFFFFFFF
+    nbytes = np.where(u < 1 << 8, 1, np.where(u < 1 << 16, 2, np.where(u < 1 << 24, 3, 4)))
+    keys = np.zeros((len(u) + 3) // 4 * 4, np.uint8)
+    keys[:len(u)] = nbytes - 1
+    keys = keys.reshape(-1, 4)
+    key_bytes = (keys[:, 0] | (keys[:, 1] << 2) | (keys[:, 2] << 4) | (keys[:, 3] << 6)).astype(np.uint8).tobytes()
+    data = b"".join(int(v).to_bytes(int(k), "little") for v, k in zip(u, nbytes))
+    body = key_bytes + data
+    if level:
+        body = zstd_compress(body, level)
+    return struct.pack("<I", len(raw)) + body
 
 
 def make_fast5(signal, read_name="Read_17", chunk=None, filters=(2, 1), level=1, flavour="old", userblock=0,

@@ -144,6 +144,92 @@ def test_inflate_against_zlib(tmp_path, level, strategy):
         assert np.array_equal(read_signal(raw, tmp_path)[1], sig)
 
 
+def zstd_decompress(blob, cap):
+    lib = _lib.load()
+    out, count, err = (C.c_uint8 * max(1, cap))(), C.c_int64(0), C.create_string_buffer(512)
+    rc = lib.nd_zstd_decompress(blob, len(blob), out, cap, C.byref(count), err, 512)
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return bytes(out)[: count.value]
+
+
+def zstd_corpus(level):
+    rng = np.random.default_rng(level)
+    text = b" ".join(str(int(x)).encode() for x in dac(60000, 2))                    # the .signal text of a read: ~230 KB
+    r = rng.integers(0, 256, 400000, dtype=np.uint8)
+    first = bytes(r[:131072])
+    return [b"", b"a", b"abc" * 5, bytes(1000), bytes(300000), b"\x07" * 131073,
+            dac(3000, 1).tobytes(), dac(200000, 4).tobytes(), text, text[:700], text[:5000],
+            rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(),                  # incompressible: raw blocks
+            rng.integers(0, 4, 70000, dtype=np.uint8).tobytes(),                     # 2-bit entropy: Huffman heavy, few matches
+            rng.integers(0, 2, 50000, dtype=np.uint8).tobytes() + rng.integers(0, 200, 50000, dtype=np.uint8).tobytes(),
+            np.tile(rng.integers(0, 256, 150000, dtype=np.uint8), 2).tobytes(),      # a match 150 000 bytes back
+            bytes(rng.integers(0, 256, 40, dtype=np.uint8)) * 3000,                  # period-40 repeats: repeat offsets
+            b"".join(bytes([i % 251]) * (i % 37 + 1) for i in range(20000)),
+            bytes(rng.choice([65, 66, 67, 68], 200, p=[.7, .15, .1, .05]).astype(np.uint8)),   # one Huffman stream
+            b"".join(bytes([b]) + b"ABCDEFGH" for b in r[:40000]),                   # identical sequences: RLE code tables
+            first + b"".join(b"x" + first[i * 100:i * 100 + 60] for i in range(1300)),   # a block whose literals are all 'x'
+            b"".join(bytes([b]) + b"ABC" for b in r[:100000]),                       # ~30 000 sequences per block
+            b"".join(bytes([b]) + b"ABCD" for b in r[:100000])]
+
+
+def test_zstd_corpus_covers_the_format():
+    """the libzstd-written frames the decoder is checked on use every construct the decoder implements, except the
+    3-byte sequence count (>= 32 512 sequences in one block, which libzstd does not emit for 128 KiB blocks)"""
+    from collections import Counter
+    found = Counter()
+    for level in (1, 3, 9, 19):
+        for raw in zstd_corpus(level):
+            hw.zstd_frame_features(hw.zstd_compress(raw, level), found)
+    need = ["block_raw", "block_rle", "block_compressed", "literals_raw", "literals_rle", "literals_huffman",
+            "literals_treeless", "streams_1", "streams_4", "weights_direct", "weights_fse", "no_sequences", "nseq_1_byte",
+            "nseq_2_byte"] + [t + m for t in ("ll_", "of_", "ml_") for m in ("predefined", "rle", "fse", "repeat")]
+    assert [k for k in need if not found[k]] == [], found
+
+
+@pytest.mark.parametrize("level", [1, 3, 9, 19])
+def test_zstd_against_libzstd(level):
+    """frames written by libzstd (pyarrow's bundled copy): raw / RLE / compressed blocks, raw / RLE / Huffman / treeless
+    literals in one and four streams, direct and FSE-compressed weights, predefined / RLE / FSE / repeat sequence tables,
+    repeat offsets, frames of several blocks (> 128 KiB), long offsets"""
+    rng = np.random.default_rng(level)
+    cases = zstd_corpus(level)
+    for raw in cases:
+        blob = hw.zstd_compress(raw, level)
+        assert zstd_decompress(blob, len(raw)) == raw
+        assert zstd_decompress(blob + blob, 2 * len(raw)) == raw + raw               # concatenated frames
+        if len(raw) > 10:
+            with pytest.raises(RuntimeError, match="longer than the space"):
+                zstd_decompress(blob, len(raw) - 1)
+            with pytest.raises(RuntimeError):
+                zstd_decompress(blob[:-3], len(raw))
+    # bit flips never crash and are (almost always) caught by the stream-end / size checks
+    raw = dac(30000, 8).tobytes()
+    blob = hw.zstd_compress(raw, level)
+    caught = 0
+    for _ in range(300):
+        bad = bytearray(blob)
+        bad[int(rng.integers(4, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        try:
+            caught += zstd_decompress(bytes(bad), len(raw)) != raw
+        except RuntimeError:
+            caught += 1
+    assert caught >= 295, caught
+
+
+@pytest.mark.parametrize("flavour,chunk,level", [("old", 4096, 1), ("old", 1000, 3), ("old", 70000, 1), ("new", None, 1),
+                                                 ("old", 512, 0)])
+def test_vbz_compressed_signal(tmp_path, flavour, chunk, level):
+    """MinKNOW's default since 2019: filter 32020, client values {0, 2, 1, zstd level}"""
+    sig = dac(50021, 13)
+    sig[1000:1010] = [-32768, 32767, -32768, 0, 32767, 32767, -1, 1, -32768, -32768]   # 3-byte zig-zag deltas
+    raw = hw.make_fast5(sig, read_name="Read_9", chunk=chunk if flavour == "old" else 2048, filters=(32020,), level=level,
+                        flavour=flavour)
+    name, got = read_signal(raw, tmp_path)
+    assert name == "Read_9" and np.array_equal(got, sig)
+    assert len(raw) < sig.nbytes * (0.75 if level else 1.2)                            # it does compress
+
+
 def test_errors_keep_the_reference_types(tmp_path):
     sig = dac(4000, 9)
     good = hw.make_fast5(sig, chunk=1000, filters=(2, 1))
@@ -151,10 +237,11 @@ def test_errors_keep_the_reference_types(tmp_path):
         read_signal(b"not an hdf5 file" * 100, tmp_path)
     with pytest.raises(IOError, match="Likely a corrupted file"):
         read_signal(b"", tmp_path)
-    # VBZ (ONT's zstd + streamvbyte filter) is named in the message
-    vbz = hw.make_fast5(sig, chunk=1000, filters=(32020,))
-    with pytest.raises(RuntimeError, match="VBZ filter"):
-        read_signal(vbz, tmp_path)
+    # VBZ version 1 (16-bit streamvbyte) and unknown filters are named in the message
+    with pytest.raises(RuntimeError, match="VBZ version 1"):
+        read_signal(hw.make_fast5(sig, chunk=1000, filters=(32020,), kw_vbz_version=1), tmp_path)
+    with pytest.raises(RuntimeError, match="unsupported HDF5 filter id 307"):
+        read_signal(hw.make_fast5(sig, chunk=1000, filters=(307,)), tmp_path)
     # truncation and bit flips anywhere never crash: they either read (flip in padding) or raise one of the two errors
     for cut in (len(good) // 7, len(good) // 2, len(good) - 9):
         with pytest.raises((RuntimeError, IOError)):
