@@ -214,7 +214,7 @@ ND_EXPORT int nd_parse_signal_text(const char* text, int64_t nbytes, int16_t* ou
  *   written to out when cap >= *count (call with cap = 0 to size the buffer).  read_name receives the member's name
  *   ("Read_1234").  Gzip, shuffle, fletcher32 and VBZ (zstd + streamvbyte) chunks are decoded.  A file that is not
  *   HDF5, lacks the path, or uses a feature outside the subset named in csrc/fast5.cu (dense groups, libver='latest'
- *   chunk indexes, VBZ version 1) returns ND_ERR_INVALID with the reason in err (NUL terminated, cut at errcap).
+ *   chunk indexes) returns ND_ERR_INVALID with the reason in err (NUL terminated, cut at errcap).
  * nd_h5_read_dataset: the same reader for any fixed- or floating-point dataset at `path` ("/a/b/c"): raw little/big
  *   endian element bytes as stored.  info[8] = {type class (0 fixed, 1 float), element bytes, signed, big endian, rank,
  *   total bytes, dim 0, dim 1}; bytes are written when cap >= info[5].                                            */

@@ -10,7 +10,7 @@
 //   1951),
 //   shuffle, fletcher32 and ONT's VBZ (id 32020: zstd over streamvbyte, own decoders in vbz.cu).
 // Refused with the reason in the message: dense link storage (fractal heap), the v4 fixed / extensible array and v2
-// B-tree chunk indexes, VBZ version 1 chunks.
+// B-tree chunk indexes.
 // h5py iterates a group's members in NAME order (H5_INDEX_NAME, increasing), which is what "the first read" means above:
 // the B-tree of an old-style group is already sorted by name; link messages are sorted here.
 // Every offset read from the file is bounds-checked: a corrupt file gives an error, never a wild read.

@@ -4,8 +4,9 @@
 // The reference reads such files through h5py + the hdf5 plugin (third-party, absent here), so the published formats are
 // restated: Zstandard frames per RFC 8878 (raw / RLE / compressed blocks, Huffman literals in 1 or 4 streams with direct or
 // FSE-compressed weights, treeless literals, FSE sequences in predefined / RLE / compressed / repeat modes, repeat
-// offsets; no dictionaries) and Lemire's streamvbyte (2-bit keys, 1 - 4 data bytes per 32-bit value) with the filter's
-// zig-zag delta.  The zstd decoder is pinned against libzstd itself (frames written by pyarrow's bundled libzstd at
+// offsets; no dictionaries), and the two streamvbyte layouts of the filter: version 0 = Lemire's streamvbyte over values
+// widened to 32 bits (2-bit keys, 1 - 4 data bytes), version 1 = "svb16" for 16-bit samples (1-bit keys, 1 - 2 data
+// bytes), both after a zig-zag delta.  The zstd decoder is pinned against libzstd itself (frames written by pyarrow's bundled libzstd at
 // levels 1 ... 19, tests/test_fast5.py); the streamvbyte layer follows the published format only (no VBZ file or plugin
 // exists in this image: "parity unpinned").  Content checksums are skipped, not verified.
 #include <stdint.h>
@@ -485,8 +486,7 @@ void zstd_decompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out, si
 void vbz_decompress(const uint8_t* src, size_t n, const uint32_t* cd, int ncd, std::vector<uint8_t>& out, size_t limit) {
   const uint32_t version = ncd > 0 ? cd[0] : 0, int_size = ncd > 1 ? cd[1] : 0, zigzag = ncd > 2 ? cd[2] : 0,
                  level = ncd > 3 ? cd[3] : 1;
-  if (version != 0)
-    fail("VBZ version " + std::to_string(version) + " chunks are not supported (version 0 = 32-bit streamvbyte is)");
+  if (version > 1) fail("VBZ version " + std::to_string(version) + " chunks are not supported (versions 0 and 1 are)");
   if (n < 4) fail("VBZ chunk shorter than its size header");
   const size_t orig = (size_t)src[0] | ((size_t)src[1] << 8) | ((size_t)src[2] << 16) | ((size_t)src[3] << 24);
   if (orig > limit) fail("VBZ chunk is longer than the space it fills");
@@ -508,11 +508,39 @@ void vbz_decompress(const uint8_t* src, size_t n, const uint32_t* cd, int ncd, s
   }
   if (int_size != 1 && int_size != 2 && int_size != 4) fail("VBZ integer size must be 1, 2 or 4");
   if (orig % int_size) fail("VBZ chunk size is not a multiple of its integer size");
-  const size_t count = orig / int_size, nkeys = (count + 3) / 4;
+  const size_t count = orig / int_size;
+  out.resize(orig);
+  if (version == 1 && int_size == 2) {
+    // version 1, 16-bit samples ("svb16"): ONE key bit per value (0 = one data byte, 1 = two), eight values per key byte,
+    // low bit first; zig-zag and delta in 16-bit wrapping arithmetic
+    const size_t nkeys = (count + 7) / 8;
+    if (nkeys > sn) fail("streamvbyte keys end early");
+    const uint8_t* data = s + nkeys;
+    const size_t dn = sn - nkeys;
+    size_t dp = 0;
+    uint16_t prev = 0;
+    for (size_t i = 0; i < count; ++i) {
+      const int len = ((s[i >> 3] >> (i & 7)) & 1) + 1;
+      if (dp + len > dn) fail("streamvbyte data end early");
+      uint16_t v = data[dp];
+      if (len == 2) v |= (uint16_t)(data[dp + 1] << 8);
+      dp += len;
+      if (zigzag) {
+        prev = (uint16_t)(prev + (uint16_t)((v >> 1) ^ (uint16_t)(0u - (v & 1u))));
+        v = prev;
+      }
+      out[2 * i] = (uint8_t)v;
+      out[2 * i + 1] = (uint8_t)(v >> 8);
+    }
+    if (dp != dn) fail("streamvbyte data longer than its keys say");
+    return;
+  }
+  if (version == 1 && int_size == 1) fail("VBZ version 1 with 1-byte integers is not supported");
+  // version 0 (and 32-bit values of version 1): values widened to 32 bits, Lemire's streamvbyte with a 2-bit key per value
+  const size_t nkeys = (count + 3) / 4;
   if (nkeys > sn) fail("streamvbyte keys end early");
   const uint8_t* data = s + nkeys;
   size_t dn = sn - nkeys, dp = 0;
-  out.resize(orig);
   uint32_t prev = 0;
   for (size_t i = 0; i < count; ++i) {
     const int len = ((s[i >> 2] >> ((i & 3) * 2)) & 3) + 1;

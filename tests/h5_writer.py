@@ -177,7 +177,7 @@ class H5Writer:
         return self.object_header_v1(msgs)
 
     @staticmethod
-    def encode_chunk(raw, elem, filters, level=1, strategy=zlib.Z_DEFAULT_STRATEGY):
+    def encode_chunk(raw, elem, filters, level=1, strategy=zlib.Z_DEFAULT_STRATEGY, vbz_version=0):
         for fid in filters:
             if fid == 2:                                               # shuffle: byte j of every element together
                 a = np.frombuffer(raw, np.uint8)
@@ -189,7 +189,7 @@ class H5Writer:
             elif fid == 3:
                 raw = raw + b"\xde\xad\xbe\xef"                        # the reader strips, does not verify
             elif fid == 32020:
-                raw = vbz_encode(raw, elem, level)
+                raw = vbz_encode(raw, elem, level, version=vbz_version)
             else:                                                      # unknown filter: stored as is, the reader must refuse
                 pass
         return raw
@@ -210,7 +210,7 @@ class H5Writer:
             if c in skip_filter_on:
                 raw, mask = part.tobytes(), (1 << len(filters)) - 1
             else:
-                raw, mask = self.encode_chunk(part.tobytes(), elem, filters, level, strategy), 0
+                raw, mask = self.encode_chunk(part.tobytes(), elem, filters, level, strategy, kw_vbz_version), 0
             entries.append((len(raw), mask, c * chunk, self.alloc(raw)))
 
         def key(e):
@@ -338,21 +338,31 @@ def zstd_frame_features(blob, found=None):
             return found
 
 
-def vbz_encode(raw, elem, level=1, zigzag=True):
-    """ONT's VBZ chunk, version 0: uint32 size | zstd(streamvbyte(zig-zag(delta(x)))) with 32-bit streamvbyte: one 2-bit
-    key per value (bytes - 1, four values per key byte, low bits first), all keys, then all data bytes little endian"""
+def vbz_encode(raw, elem, level=1, zigzag=True, version=0):
+    """ONT's VBZ chunk: uint32 size | zstd(streamvbyte(zig-zag(delta(x)))).
+    version 0: values widened to 32 bits, Lemire's streamvbyte: one 2-bit key per value (data bytes - 1, four values per
+    key byte, low bits first), all keys, then all data bytes little endian.
+    version 1 with 16-bit samples ("svb16"): 16-bit wrapping delta and zig-zag, ONE key bit per value (0 = one data byte,
+    1 = two), eight values per key byte, low bit first."""
     x = np.frombuffer(raw, {1: "<i1", 2: "<i2", 4: "<i4"}[elem]).astype(np.int64)
+    bits = 16 if (version == 1 and elem == 2) else 32
     if zigzag:
         d = np.diff(x, prepend=0)
-        d = ((d + 2 ** 31) % 2 ** 32 - 2 ** 31).astype(np.int64)     # the filter works in 32-bit arithmetic
-        u = ((d << 1) ^ (d >> 31)) & 0xFFFFFFFF
+        d = ((d + 2 ** (bits - 1)) % 2 ** bits - 2 ** (bits - 1)).astype(np.int64)   # the filter's wrapping arithmetic
+        u = ((d << 1) ^ (d >> (bits - 1))) & (2 ** bits - 1)
     else:
-        u = x & 0xFFFFFFFF
-    nbytes = np.where(u < 1 << 8, 1, np.where(u < 1 << 16, 2, np.where(u < 1 << 24, 3, 4)))
-    keys = np.zeros((len(u) + 3) // 4 * 4, np.uint8)
-    keys[:len(u)] = nbytes - 1
-    keys = keys.reshape(-1, 4)
-    key_bytes = (keys[:, 0] | (keys[:, 1] << 2) | (keys[:, 2] << 4) | (keys[:, 3] << 6)).astype(np.uint8).tobytes()
+        u = x & (2 ** bits - 1)
+    if bits == 16:
+        nbytes = np.where(u < 1 << 8, 1, 2)
+        keys = np.zeros((len(u) + 7) // 8 * 8, np.uint8)
+        keys[:len(u)] = nbytes - 1
+        key_bytes = np.packbits(keys.reshape(-1, 8), axis=1, bitorder="little").tobytes()
+    else:
+        nbytes = np.where(u < 1 << 8, 1, np.where(u < 1 << 16, 2, np.where(u < 1 << 24, 3, 4)))
+        keys = np.zeros((len(u) + 3) // 4 * 4, np.uint8)
+        keys[:len(u)] = nbytes - 1
+        keys = keys.reshape(-1, 4)
+        key_bytes = (keys[:, 0] | (keys[:, 1] << 2) | (keys[:, 2] << 4) | (keys[:, 3] << 6)).astype(np.uint8).tobytes()
     data = b"".join(int(v).to_bytes(int(k), "little") for v, k in zip(u, nbytes))
     body = key_bytes + data
     if level:

@@ -217,14 +217,16 @@ def test_zstd_against_libzstd(level):
     assert caught >= 295, caught
 
 
+@pytest.mark.parametrize("version", [0, 1])
 @pytest.mark.parametrize("flavour,chunk,level", [("old", 4096, 1), ("old", 1000, 3), ("old", 70000, 1), ("new", None, 1),
                                                  ("old", 512, 0)])
-def test_vbz_compressed_signal(tmp_path, flavour, chunk, level):
-    """MinKNOW's default since 2019: filter 32020, client values {0, 2, 1, zstd level}"""
+def test_vbz_compressed_signal(tmp_path, flavour, chunk, level, version):
+    """MinKNOW's default since 2019: filter 32020, client values {vbz version, 2, 1, zstd level}; version 1 ("svb16") is
+    what ont_fast5_api writes today, version 0 its `vbz_legacy_v0`"""
     sig = dac(50021, 13)
     sig[1000:1010] = [-32768, 32767, -32768, 0, 32767, 32767, -1, 1, -32768, -32768]   # 3-byte zig-zag deltas
     raw = hw.make_fast5(sig, read_name="Read_9", chunk=chunk if flavour == "old" else 2048, filters=(32020,), level=level,
-                        flavour=flavour)
+                        flavour=flavour, kw_vbz_version=version)
     name, got = read_signal(raw, tmp_path)
     assert name == "Read_9" and np.array_equal(got, sig)
     assert len(raw) < sig.nbytes * (0.75 if level else 1.2)                            # it does compress
@@ -237,9 +239,9 @@ def test_errors_keep_the_reference_types(tmp_path):
         read_signal(b"not an hdf5 file" * 100, tmp_path)
     with pytest.raises(IOError, match="Likely a corrupted file"):
         read_signal(b"", tmp_path)
-    # VBZ version 1 (16-bit streamvbyte) and unknown filters are named in the message
-    with pytest.raises(RuntimeError, match="VBZ version 1"):
-        read_signal(hw.make_fast5(sig, chunk=1000, filters=(32020,), kw_vbz_version=1), tmp_path)
+    # unknown VBZ versions and unknown filters are named in the message
+    with pytest.raises(RuntimeError, match="VBZ version 2"):
+        read_signal(hw.make_fast5(sig, chunk=1000, filters=(32020,), kw_vbz_version=2), tmp_path)
     with pytest.raises(RuntimeError, match="unsupported HDF5 filter id 307"):
         read_signal(hw.make_fast5(sig, chunk=1000, filters=(307,)), tmp_path)
     # truncation and bit flips anywhere never crash: they either read (flip in padding) or raise one of the two errors
