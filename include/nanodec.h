@@ -220,6 +220,16 @@ ND_EXPORT int nd_parse_signal_text(const char* text, int64_t nbytes, int16_t* ou
  *   total bytes, dim 0, dim 1}; bytes are written when cap >= info[5].                                            */
 ND_EXPORT int nd_fast5_read_signal(const uint8_t* file, int64_t nbytes, int16_t* out, int64_t cap, int64_t* count,
                                    char* read_name, int32_t name_cap, char* err, int32_t errcap);
+/* nd_fast5_list_reads / nd_fast5_read_signal_of: the same by read name, and beyond the reference (whose reader fails on
+ *   them): MULTI-read .fast5 files (/read_<uuid>/Raw/Signal, what MinKNOW and ont_fast5_api write since 2019).
+ *   list: names NUL separated in `names` (written while they fit names_cap; *names_bytes = bytes needed), name order;
+ *   *layout = 1 single-read (members of /Raw/Reads: the reference takes the first), 2 multi-read (root members read_*).
+ *   read_signal_of: `read_name` as listed.  `file` may be a read-only memory map: only the pages of the structures
+ *   visited are touched.                                                                                              */
+ND_EXPORT int nd_fast5_list_reads(const uint8_t* file, int64_t nbytes, char* names, int64_t names_cap, int64_t* names_bytes,
+                                  int32_t* n_reads, int32_t* layout, char* err, int32_t errcap);
+ND_EXPORT int nd_fast5_read_signal_of(const uint8_t* file, int64_t nbytes, const char* read_name, int16_t* out, int64_t cap,
+                                      int64_t* count, char* err, int32_t errcap);
 ND_EXPORT int nd_h5_read_dataset(const uint8_t* file, int64_t nbytes, const char* path, uint8_t* out, int64_t cap,
                                  int64_t* info, char* err, int32_t errcap);
 /* nd_zstd_decompress: the Zstandard decoder (RFC 8878, no dictionaries) behind the VBZ filter of .fast5 chunks, exposed

@@ -801,6 +801,26 @@ int64_t fixed_value(const uint8_t* p, const Dataset& d) {
   return (int64_t)v;
 }
 
+// the Signal dataset below `group` -> int16 samples; *count = samples, written when cap allows (cap < count: size query)
+void read_signal_of(H5File& f, uint64_t group, const std::string& where, int16_t* out, int64_t cap, int64_t* count) {
+  uint64_t sig = kUndef;
+  for (const Link& l : f.links(group))
+    if (l.name == "Signal") sig = l.addr;
+  if (sig == kUndef) fail(where + " has no Signal dataset");
+  const Dataset d = f.dataset(sig);
+  if (d.type_class != 0) fail("Signal is not an integer dataset");
+  const uint64_t n = f.count(d);
+  *count = (int64_t)n;
+  if ((uint64_t)cap < n) return;
+  std::vector<uint8_t> bytes;
+  f.read(d, bytes);
+  for (uint64_t i = 0; i < n; ++i) {
+    const int64_t v = fixed_value(bytes.data() + i * d.elem, d);
+    if (v < -32768 || v > 32767) fail("Signal sample " + std::to_string(v) + " is outside the int16 DAC range");
+    out[i] = (int16_t)v;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -840,22 +860,64 @@ int nd_fast5_read_signal(const uint8_t* file, int64_t nbytes, int16_t* out, int6
     const std::vector<Link> members = f.links(reads);
     if (members.empty()) fail("/Raw/Reads has no members");                 // list(...)[0] raises IndexError
     put_error(read_name, name_cap, members[0].name);
-    uint64_t sig = kUndef;
-    for (const Link& l : f.links(members[0].addr))
-      if (l.name == "Signal") sig = l.addr;
-    if (sig == kUndef) fail("/Raw/Reads/" + members[0].name + " has no Signal dataset");
-    const Dataset d = f.dataset(sig);
-    if (d.type_class != 0) fail("Signal is not an integer dataset");
-    const uint64_t n = f.count(d);
-    *count = (int64_t)n;
-    if ((uint64_t)cap < n) return ND_OK;                                     // size query
-    std::vector<uint8_t> bytes;
-    f.read(d, bytes);
-    for (uint64_t i = 0; i < n; ++i) {
-      const int64_t v = fixed_value(bytes.data() + i * d.elem, d);
-      if (v < -32768 || v > 32767) fail("Signal sample " + std::to_string(v) + " is outside the int16 DAC range");
-      out[i] = (int16_t)v;
+    read_signal_of(f, members[0].addr, "/Raw/Reads/" + members[0].name, out, cap, count);
+    return ND_OK;
+  } catch (const H5Error& e) {
+    put_error(err, errcap, e.msg);
+    return ND_ERR_INVALID;
+  } catch (const std::exception& e) {
+    put_error(err, errcap, e.what());
+    return ND_ERR_NOMEM;
+  }
+}
+
+int nd_fast5_list_reads(const uint8_t* file, int64_t nbytes, char* names, int64_t names_cap, int64_t* names_bytes,
+                        int32_t* n_reads, int32_t* layout, char* err, int32_t errcap) {
+  if (!file || nbytes < 0 || !names_bytes || !n_reads || !layout || names_cap < 0 || (names_cap > 0 && !names)) return ND_ERR_INVALID;
+  *names_bytes = 0; *n_reads = 0; *layout = 0;
+  try {
+    H5File f(file, (uint64_t)nbytes);
+    std::vector<Link> members;
+    bool single = false;
+    for (const Link& l : f.links(f.root())) single = single || l.name == "Raw";
+    if (single) {
+      members = f.links(f.resolve("/Raw/Reads/"));
+      *layout = 1;
+    } else {
+      for (const Link& l : f.links(f.root()))
+        if (l.name.compare(0, 5, "read_") == 0) members.push_back(l);
+      *layout = 2;
+      if (members.empty()) fail("neither /Raw/Reads (single-read) nor /read_* groups (multi-read) in this file");
     }
+    int64_t at = 0;
+    for (const Link& l : members) {
+      const int64_t len = (int64_t)l.name.size() + 1;
+      if (at + len <= names_cap) memcpy(names + at, l.name.c_str(), (size_t)len);
+      at += len;
+    }
+    *names_bytes = at;
+    *n_reads = (int32_t)members.size();
+    return ND_OK;
+  } catch (const H5Error& e) {
+    put_error(err, errcap, e.msg);
+    return ND_ERR_INVALID;
+  } catch (const std::exception& e) {
+    put_error(err, errcap, e.what());
+    return ND_ERR_NOMEM;
+  }
+}
+
+int nd_fast5_read_signal_of(const uint8_t* file, int64_t nbytes, const char* read_name, int16_t* out, int64_t cap,
+                            int64_t* count, char* err, int32_t errcap) {
+  if (!file || nbytes < 0 || !read_name || !count || cap < 0 || (cap > 0 && !out)) return ND_ERR_INVALID;
+  *count = 0;
+  try {
+    H5File f(file, (uint64_t)nbytes);
+    const std::string name(read_name);
+    bool single = false;
+    for (const Link& l : f.links(f.root())) single = single || l.name == "Raw";
+    if (single) read_signal_of(f, f.resolve("/Raw/Reads/" + name), "/Raw/Reads/" + name, out, cap, count);
+    else read_signal_of(f, f.resolve("/" + name + "/Raw"), "/" + name + "/Raw", out, cap, count);
     return ND_OK;
   } catch (const H5Error& e) {
     put_error(err, errcap, e.msg);

@@ -6,6 +6,7 @@ libnanodec (host C++, nd_simple_assembly), as does the parsing of `.signal` text
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -90,35 +91,72 @@ def simple_assembly(bpreads, flag_intersection=True):
     return counts[:, : length.value].astype(np.float64)
 
 
-def read_fast5_signal(path):
-    """(read name, int16 samples) of a single-read .fast5 file: the reference's
+_MAP_ABOVE = 64 << 20          # larger files (multi-read) are memory mapped: only the pages a read needs are touched
+
+
+def _fast5_bytes(path):
+    """(object passed as the `file` argument, size, keep-alive): the file's bytes, or a read-only memory map of them"""
+    size = os.path.getsize(path)
+    if size <= _MAP_ABOVE:
+        raw = open(path, "rb").read()
+        return raw, len(raw), raw
+    m = np.memmap(path, dtype=np.uint8, mode="r")
+    return C.cast(m.ctypes.data, C.c_char_p), m.size, m
+
+
+def _fast5_error(why):
+    if "signature not found" in why or "superblock" in why:
+        return IOError("Error opening file. Likely a corrupted file. (%s)" % why)
+    return RuntimeError("Raw data is not stored in Raw/Reads/Read_[read#] so new segments cannot be identified. (%s)" % why)
+
+
+def list_fast5_reads(path):
+    """-> (layout, [read names]): layout 1 = single-read file (members of /Raw/Reads in h5py's name order; the reference
+    decodes the first), 2 = multi-read file (/read_<uuid>/Raw/Signal), which the reference cannot read and the CLI here
+    expands into one read per member."""
+    buf, n, keep = _fast5_bytes(path)
+    lib = _lib.load()
+    need, count, layout, err = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.create_string_buffer(512)
+    rc = lib.nd_fast5_list_reads(buf, n, None, 0, C.byref(need), C.byref(count), C.byref(layout), err, 512)
+    names = C.create_string_buffer(max(1, need.value))
+    if rc == 0:
+        rc = lib.nd_fast5_list_reads(buf, n, names, need.value, C.byref(need), C.byref(count), C.byref(layout), err, 512)
+    if rc != 0:
+        raise _fast5_error(err.value.decode("latin-1"))
+    return layout.value, [x.decode("latin-1") for x in names.raw[: need.value].split(b"\0")[: count.value]]
+
+
+def read_fast5_signal(path, read_name=None):
+    """(read name, int16 samples) of a .fast5 file: the reference's
     `list(h5py.File(path)['/Raw/Reads/'].values())[0]['Signal'].value` (utils/labelop.py:199-214), read by libnanodec's own
-    HDF5 reader (nd_fast5_read_signal, csrc/fast5.cu: h5py / libhdf5 are not needed).  Errors keep the reference's types
-    and texts: a file that is not HDF5 -> IOError('Error opening file. Likely a corrupted file.') (:203-204), anything wrong
-    below the root -> RuntimeError('Raw data is not stored in Raw/Reads/Read_[read#] ...') (:236-239), each with the
-    reader's reason appended."""
-    raw = open(path, "rb").read()
+    HDF5 reader (nd_fast5_read_signal, csrc/fast5.cu: h5py / libhdf5 are not needed); with `read_name`, that member of a
+    single- or multi-read file.  Errors keep the reference's types and texts: a file that is not HDF5 ->
+    IOError('Error opening file. Likely a corrupted file.') (:203-204), anything wrong below the root ->
+    RuntimeError('Raw data is not stored in Raw/Reads/Read_[read#] ...') (:236-239), each with the reader's reason
+    appended."""
+    buf, n, keep = _fast5_bytes(path)
     lib = _lib.load()
     count, name, err = C.c_int64(0), C.create_string_buffer(256), C.create_string_buffer(512)
-    rc = lib.nd_fast5_read_signal(raw, len(raw), None, 0, C.byref(count), name, 256, err, 512)
+
+    def call(out, cap):
+        if read_name is None:
+            return lib.nd_fast5_read_signal(buf, n, out, cap, C.byref(count), name, 256, err, 512)
+        return lib.nd_fast5_read_signal_of(buf, n, read_name.encode("latin-1"), out, cap, C.byref(count), err, 512)
+
+    rc = call(None, 0)
     out = np.empty(max(1, count.value), dtype=np.int16)
     if rc == 0:
-        rc = lib.nd_fast5_read_signal(raw, len(raw), out.ctypes.data_as(C.POINTER(C.c_int16)), out.size, C.byref(count),
-                                      name, 256, err, 512)
+        rc = call(out.ctypes.data_as(C.POINTER(C.c_int16)), out.size)
     if rc != 0:
-        why = err.value.decode("latin-1")
-        if "signature not found" in why or "superblock" in why:
-            raise IOError("Error opening file. Likely a corrupted file. (%s)" % why)
-        raise RuntimeError("Raw data is not stored in Raw/Reads/Read_[read#] so new segments cannot be identified. (%s)"
-                           % why)
-    return name.value.decode("latin-1"), out[: count.value]
+        raise _fast5_error(err.value.decode("latin-1"))
+    return (read_name if read_name is not None else name.value.decode("latin-1")), out[: count.value]
 
 
 def read_raw_signal(path, suffix):
     """Raw samples of one read (utils/labelop.py:199-219 without the normalisation): int16 for DAC values (fast5 `Signal`
     datasets, integer `.signal` files), float64 for a `.signal` file with non-integer values."""
-    if suffix == "fast5":
-        return read_fast5_signal(path)[1]
+    if suffix.startswith("fast5"):                               # "fast5" or, for one read of a multi-read file, "fast5:<name>"
+        return read_fast5_signal(path, suffix[6:] or None)[1]
     raw = open(path, "rb").read()
     out = np.empty(len(raw) // 2 + 1, dtype=np.int16)           # every sample takes at least a digit and a separator
     count, status = C.c_int64(0), C.c_int32(0)

@@ -412,3 +412,22 @@ def make_fast5(signal, read_name="Read_17", chunk=None, filters=(2, 1), level=1,
         return w.finish(w.group_new(members, order=["UniqueGlobalKey", "Raw", "PreviousReadInfo", "Analyses"]))
     root, btree, heap = w.group_old(members)
     return w.finish(root, btree, heap, cache_root=cache_root)
+
+
+def make_multi_fast5(reads, chunk=4096, filters=(32020,), level=1, vbz_version=1, userblock=0, pad_to=0):
+    """A multi-read fast5 skeleton as ont_fast5_api writes it (default libver: old-style groups):
+    /read_<id>/Raw/Signal per read plus the per-read metadata groups.  reads: {read id: int16 samples}."""
+    w = H5Writer(userblock=userblock)
+    members = {}
+    for rid, signal in reads.items():
+        signal = np.asarray(signal)
+        t = w.msg_fixed(signal.dtype.itemsize, signed=signal.dtype.kind == "i")
+        ds = w.dataset_chunked(signal, t, min(chunk, max(1, len(signal))), filters=filters, level=level,
+                               kw_vbz_version=vbz_version)
+        raw_g = w.group_old({"Signal": ds})[0]
+        members["read_" + rid] = w.group_old({"Raw": raw_g, "channel_id": w.group_old({})[0],
+                                              "context_tags": w.group_old({})[0], "tracking_id": w.group_old({})[0]})[0]
+    if pad_to:
+        w.alloc(bytes(max(0, pad_to - len(w.buf))))
+    root, btree, heap = w.group_old(members, levels=3)
+    return w.finish(root, btree, heap)

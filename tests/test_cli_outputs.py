@@ -149,3 +149,39 @@ def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path, threads):
         fasta = _read(tmp_path / "out" / "result" / ("r%02d.fasta" % i))
         assert fasta == ">r%02d\n%s" % (i, "".join(w.replace(" ", "") for w in want))
         assert int(speed[live.index(i)].split("\t")[2]) == sum(len(w.split()) for w in want)
+
+
+def test_read_table_expands_multi_read_fast5(tmp_path):
+    """list_reads: one entry per file as in the reference (translate.py:136-152); a multi-read .fast5 file (not readable by
+    the reference) becomes one entry per read, named by the read id, with the same resume rule per read"""
+    import numpy as np
+    import h5_writer
+    from nanodecoder_b200.utils.labelop import read_raw_signal
+    cli = _cli()
+    src = tmp_path / "reads"
+    src.mkdir()
+    rng = np.random.default_rng(5)
+    sig = {k: rng.integers(300, 900, size=n).astype(np.int16) for k, n in (("a", 900), ("b", 1500), ("m1", 700), ("m2", 64),
+                                                                          ("m3", 2000))}
+    (src / "a.signal").write_text(" ".join(map(str, sig["a"])))
+    (src / "b.fast5").write_bytes(h5_writer.make_fast5(sig["b"], read_name="Read_4", chunk=512))
+    (src / "c.fast5").write_bytes(h5_writer.make_multi_fast5({"0003-m3": sig["m3"], "0001-m1": sig["m1"], "0002-m2": sig["m2"]},
+                                                             chunk=256))
+    (src / "d.fast5").write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(100))          # corrupt: stays one entry, reported at load time
+    (src / "notes.txt").write_text("ignored")
+    opt = _opt(str(tmp_path / "out"))
+    opt.src_dir = str(src)
+    (tmp_path / "out" / "result" / "0002-m2.fasta").write_text(">0002-m2\nACGT")       # already translated: skipped
+    todo, sizes, done = cli.list_reads(opt)
+    assert done == 1
+    assert todo == [("a.signal", "signal", "a.txt"), ("b.fast5", "fast5", "b.txt"),
+                    ("c.fast5", "fast5:read_0001-m1", "0001-m1.txt"), ("c.fast5", "fast5:read_0003-m3", "0003-m3.txt"),
+                    ("d.fast5", "fast5", "d.txt")]
+    csize = os.path.getsize(src / "c.fast5")
+    assert sizes == [os.path.getsize(src / "a.signal"), os.path.getsize(src / "b.fast5"), csize // 3, csize // 3,
+                     os.path.getsize(src / "d.fast5")]
+    got = [read_raw_signal(str(src / fn), suffix) for fn, suffix, _ in todo[:4]]
+    for g, k in zip(got, ("a", "b", "m1", "m3")):
+        assert g.dtype == np.int16 and np.array_equal(g, sig[k])
+    with pytest.raises((IOError, RuntimeError)):
+        read_raw_signal(str(src / "d.fast5"), "fast5")

@@ -276,3 +276,33 @@ def test_read_raw_signal_and_cli_loader(tmp_path):
     a = labelop.read_raw_signal(str(tmp_path / "a.fast5"), "fast5")
     b = labelop.read_raw_signal(str(tmp_path / "a.signal"), "signal")
     assert a.dtype == b.dtype == np.int16 and np.array_equal(a, b)
+
+
+def test_multi_read_files(tmp_path, monkeypatch):
+    """beyond the reference (its reader needs /Raw/Reads): /read_<uuid>/Raw/Signal members, listed in name order and read
+    by name; files above the mapping threshold go through a read-only memory map"""
+    rng = np.random.default_rng(21)
+    ids = ["%08x-0000-4000-8000-%012x" % (int(rng.integers(0, 2 ** 32)), i) for i in range(23)]
+    reads = {rid: dac(int(rng.integers(1, 9000)), 100 + i) for i, rid in enumerate(ids)}
+    for mapped in (False, True):
+        if mapped:
+            monkeypatch.setattr(labelop, "_MAP_ABOVE", 1 << 16)
+        p = tmp_path / ("multi%d.fast5" % mapped)
+        p.write_bytes(hw.make_multi_fast5(reads, chunk=1024, vbz_version=int(mapped), pad_to=(1 << 18) if mapped else 0))
+        layout, names = labelop.list_fast5_reads(str(p))
+        assert layout == 2 and names == sorted("read_" + r for r in ids)
+        for rid in ids:
+            name, got = labelop.read_fast5_signal(str(p), "read_" + rid)
+            assert name == "read_" + rid and np.array_equal(got, reads[rid])
+            assert np.array_equal(labelop.read_raw_signal(str(p), "fast5:read_" + rid), reads[rid])
+        with pytest.raises(RuntimeError, match="no object named 'read_nope'"):
+            labelop.read_fast5_signal(str(p), "read_nope")
+        with pytest.raises(RuntimeError, match="Raw"):                      # the reference's call on a multi-read file
+            labelop.read_fast5_signal(str(p))
+    # a single-read file lists the members of /Raw/Reads; the first is what the reference decodes
+    sig = dac(3000, 1)
+    q = tmp_path / "single.fast5"
+    q.write_bytes(hw.make_fast5(sig, read_name="Read_12", chunk=700, other_reads=("Read_7",)))
+    assert labelop.list_fast5_reads(str(q)) == (1, ["Read_12", "Read_7"])
+    assert np.array_equal(labelop.read_fast5_signal(str(q), "Read_12")[1], sig)
+    assert np.array_equal(labelop.read_fast5_signal(str(q), "Read_7")[1], np.full(3, -7, np.int16))

@@ -148,17 +148,39 @@ def finish_records(opt, records):
 
 
 def list_reads(opt):
-    """-> (todo [(file name, suffix, out name)], file sizes, number of reads that already have a result)."""
-    todo, done = [], 0
+    """-> (todo [(file name, suffix, out name)], sizes, number of reads that already have a result).
+    One entry per file like the reference (translate.py:136-152), except that a MULTI-read .fast5 file (which the
+    reference cannot read) contributes one entry per read: suffix "fast5:<member name>", outputs named by the read id."""
+    from nanodecoder_b200.utils.labelop import list_fast5_reads
+    todo, sizes, done = [], [], 0
+
+    def add(fn, suffix, out, size):
+        nonlocal done
+        if os.path.exists(os.path.join(opt.save_data, "result", out.split(".txt")[0] + ".fasta")):
+            done += 1                                            # translate.py:152 (resume semantics)
+        else:
+            todo.append((fn, suffix, out))
+            sizes.append(size)
+
     for fn in sorted(os.listdir(opt.src_dir)):
         for suffix in ("fast5", "signal"):
             if fn.endswith(suffix):
-                out = fn[: -len(suffix) - 1] + ".txt"
-                if os.path.exists(os.path.join(opt.save_data, "result", out.split(".txt")[0] + ".fasta")):
-                    done += 1                                    # translate.py:152 (resume semantics)
+                path = os.path.join(opt.src_dir, fn)
+                size = os.path.getsize(path)
+                members = None
+                if suffix == "fast5":
+                    try:
+                        layout, names = list_fast5_reads(path)
+                        members = names if layout == 2 else None
+                    except Exception:                            # noqa: BLE001 -- reported per read when it is loaded
+                        members = None
+                if members:
+                    for name in members:
+                        rid = name[5:] if name.startswith("read_") else name
+                        add(fn, "fast5:" + name, rid + ".txt", size // len(members))
                 else:
-                    todo.append((fn, suffix, out))
-    return todo, [os.path.getsize(os.path.join(opt.src_dir, t[0])) for t in todo], done
+                    add(fn, suffix, fn[: -len(suffix) - 1] + ".txt", size)
+    return todo, sizes, done
 
 
 def main(opt, logger):
