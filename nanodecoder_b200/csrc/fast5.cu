@@ -289,7 +289,7 @@ class H5File {
 
   uint64_t root() const { return root_; }
 
-  std::vector<Link> links(uint64_t header_addr) {
+  std::vector<Link> links(uint64_t header_addr, bool sorted = true) {
     std::vector<Link> out;
     bool is_group = false;
     uint64_t cached_btree = kUndef, cached_heap = kUndef;
@@ -315,13 +315,13 @@ class H5File {
     }
     if (cached_btree != kUndef && out.empty()) { group_btree(cached_btree, cached_heap, out, 0); is_group = true; }
     if (!is_group) fail("object is not a group");
-    std::stable_sort(out.begin(), out.end(), [](const Link& a, const Link& b) { return a.name < b.name; });
+    if (sorted) std::stable_sort(out.begin(), out.end(), [](const Link& a, const Link& b) { return a.name < b.name; });
     return out;
   }
 
   // "/a/b/c" from the root group; an empty component is skipped (h5py accepts a trailing '/')
-  uint64_t resolve(const std::string& path) {
-    uint64_t cur = root_;
+  uint64_t resolve(const std::string& path) { return resolve(path, root_); }
+  uint64_t resolve(const std::string& path, uint64_t cur) {
     size_t i = 0;
     while (i < path.size()) {
       size_t j = path.find('/', i);
@@ -329,7 +329,7 @@ class H5File {
       if (j > i) {
         const std::string name = path.substr(i, j - i);
         bool found = false;
-        for (const Link& l : links(cur))
+        for (const Link& l : links(cur, false))
           if (l.name == name) { cur = l.addr; found = true; break; }
         if (!found) fail("no object named '" + name + "' on the path '" + path + "'");
       }
@@ -804,7 +804,7 @@ int64_t fixed_value(const uint8_t* p, const Dataset& d) {
 // the Signal dataset below `group` -> int16 samples; *count = samples, written when cap allows (cap < count: size query)
 void read_signal_of(H5File& f, uint64_t group, const std::string& where, int16_t* out, int64_t cap, int64_t* count) {
   uint64_t sig = kUndef;
-  for (const Link& l : f.links(group))
+  for (const Link& l : f.links(group, false))
     if (l.name == "Signal") sig = l.addr;
   if (sig == kUndef) fail(where + " has no Signal dataset");
   const Dataset d = f.dataset(sig);
@@ -914,10 +914,14 @@ int nd_fast5_read_signal_of(const uint8_t* file, int64_t nbytes, const char* rea
   try {
     H5File f(file, (uint64_t)nbytes);
     const std::string name(read_name);
-    bool single = false;
-    for (const Link& l : f.links(f.root())) single = single || l.name == "Raw";
-    if (single) read_signal_of(f, f.resolve("/Raw/Reads/" + name), "/Raw/Reads/" + name, out, cap, count);
-    else read_signal_of(f, f.resolve("/" + name + "/Raw"), "/" + name + "/Raw", out, cap, count);
+    uint64_t raw = kUndef, member = kUndef;                                  // one walk over the root group (4000 members
+    for (const Link& l : f.links(f.root(), false)) {                         // in a multi-read file)
+      if (l.name == "Raw") raw = l.addr;
+      if (l.name == name) member = l.addr;
+    }
+    if (raw != kUndef) read_signal_of(f, f.resolve("Reads/" + name, raw), "/Raw/Reads/" + name, out, cap, count);
+    else if (member != kUndef) read_signal_of(f, f.resolve("Raw", member), "/" + name + "/Raw", out, cap, count);
+    else fail("no object named '" + name + "' in the root group");
     return ND_OK;
   } catch (const H5Error& e) {
     put_error(err, errcap, e.msg);

@@ -91,7 +91,7 @@ def simple_assembly(bpreads, flag_intersection=True):
     return counts[:, : length.value].astype(np.float64)
 
 
-_MAP_ABOVE = 64 << 20          # larger files (multi-read) are memory mapped: only the pages a read needs are touched
+_MAP_ABOVE = 8 << 20           # larger files (multi-read) are memory mapped: only the pages a read needs are touched
 
 
 def _fast5_bytes(path):
