@@ -9,3 +9,9 @@ g++ -O1 -g -std=c++17 -fPIC -shared -fsanitize=address,undefined -fno-sanitize-r
 ASAN_OPTIONS=detect_leaks=0:abort_on_error=1 \
 LD_PRELOAD="$(gcc -print-file-name=libasan.so) /usr/lib/x86_64-linux-gnu/libstdc++.so.6" \
     python scripts/host_fuzz.py "${1:-1}" "${2:-3000}" "${3:-4000}"
+# read assembly (difflib restatement, votes) and the .signal text parser, checked against difflib on the way
+g++ -O1 -g -std=c++17 -fPIC -shared -fsanitize=address,undefined -fno-sanitize-recover=undefined \
+    -x c++ nanodecoder_b200/csrc/assembly.cu -o /tmp/libasm_asan.so
+ASAN_OPTIONS=detect_leaks=0:abort_on_error=1 \
+LD_PRELOAD="$(gcc -print-file-name=libasan.so) /usr/lib/x86_64-linux-gnu/libstdc++.so.6" \
+    python scripts/host_fuzz_assembly.py /tmp/libasm_asan.so "${1:-1}" 1500
