@@ -281,6 +281,7 @@ struct Link {
 struct Message {
   int type;
   uint64_t off, size;
+  int flags;                    // bit 1: the body is a reference to a shared message in another object
 };
 
 class H5File {
@@ -341,6 +342,8 @@ class H5File {
   Dataset dataset(uint64_t header_addr) {
     Dataset d;
     for (const Message& m : messages(header_addr)) {
+      if ((m.flags & 2) && (m.type == 0x01 || m.type == 0x03 || m.type == 0x0B))
+        fail("dataset with a shared (committed) dataspace / datatype / filter message is not supported");
       if (m.type == 0x01) dataspace(m, d);
       else if (m.type == 0x03) datatype(m, d);
       else if (m.type == 0x08) layout(m, d);
@@ -491,7 +494,7 @@ class H5File {
             if (cl < 8 || !sig(s, "OCHK")) fail("object header continuation without its signature");
             blocks.push_back({s + 4, s + cl - 4});
           } else if (type != 0) {
-            out.push_back({type, body, size});
+            out.push_back({type, body, size, (int)p_[q + 3]});
           }
           q = body + size;
         }
@@ -520,7 +523,7 @@ class H5File {
           need(base_ + ca, cl);
           blocks.push_back({base_ + ca, base_ + ca + cl});
         } else if (type != 0) {
-          out.push_back({type, body, size});
+          out.push_back({type, body, size, (int)p_[q + 4]});
         }
         q = body + size;                                                    // v1 message sizes are multiples of 8
       }
@@ -617,7 +620,7 @@ class H5File {
     if (d.type_class == 0) d.is_signed = (bits0 & 8) != 0;
     else if (d.type_class == 1) d.is_signed = true;
     else fail("datatype class " + std::to_string(d.type_class) + " is neither fixed nor floating point");
-    if (d.elem == 0 || d.elem > 16) fail("unsupported element size");
+    if (d.elem == 0 || d.elem > 16 || (d.type_class == 0 && d.elem > 8)) fail("unsupported element size");
     d.have_type = true;
   }
 
