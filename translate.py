@@ -222,8 +222,9 @@ def main(opt, logger):
 
 if __name__ == "__main__":
     parser = argparse.ArgumentParser(description="translate.py", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    opts.config_opts(parser)                                     # -config FILE.yml / -save_config FILE.yml
     opts.translate_opts(parser)
-    opt = parser.parse_args()
+    opt = opts.parse_args(parser)
     logging.basicConfig(level=logging.INFO, format="[%(asctime)s %(levelname)s] %(message)s")
     log = logging.getLogger("translate")
     if opt.log_file:
