@@ -179,7 +179,7 @@ def list_reads(opt):
                         rid = name[5:] if name.startswith("read_") else name
                         add(fn, "fast5:" + name, rid + ".txt", size // len(members))
                 else:
-                    add(fn, suffix, fn[: -len(suffix) - 1] + ".txt", size)
+                    add(fn, suffix, fn.split("." + suffix)[0] + ".txt", size)     # translate.py:138-142 of the reference
     return todo, sizes, done
 
 
