@@ -94,10 +94,10 @@ def simple_assembly(bpreads, flag_intersection=True):
 _MAP_ABOVE = 8 << 20           # larger files (multi-read) are memory mapped: only the pages a read needs are touched
 
 
-def _fast5_bytes(path):
+def _fast5_bytes(path, always_map=False):
     """(object passed as the `file` argument, size, keep-alive): the file's bytes, or a read-only memory map of them"""
     size = os.path.getsize(path)
-    if size <= _MAP_ABOVE:
+    if size <= _MAP_ABOVE and not (always_map and size > 0):
         raw = open(path, "rb").read()
         return raw, len(raw), raw
     m = np.memmap(path, dtype=np.uint8, mode="r")
@@ -114,7 +114,7 @@ def list_fast5_reads(path):
     """-> (layout, [read names]): layout 1 = single-read file (members of /Raw/Reads in h5py's name order; the reference
     decodes the first), 2 = multi-read file (/read_<uuid>/Raw/Signal), which the reference cannot read and the CLI here
     expands into one read per member."""
-    buf, n, keep = _fast5_bytes(path)
+    buf, n, keep = _fast5_bytes(path, always_map=True)       # listing touches the root group's pages only
     lib = _lib.load()
     need, count, layout, err = C.c_int64(0), C.c_int32(0), C.c_int32(0), C.create_string_buffer(512)
     rc = lib.nd_fast5_list_reads(buf, n, None, 0, C.byref(need), C.byref(count), C.byref(layout), err, 512)
