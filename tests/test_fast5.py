@@ -306,3 +306,30 @@ def test_multi_read_files(tmp_path, monkeypatch):
     assert labelop.list_fast5_reads(str(q)) == (1, ["Read_12", "Read_7"])
     assert np.array_equal(labelop.read_fast5_signal(str(q), "Read_12")[1], sig)
     assert np.array_equal(labelop.read_fast5_signal(str(q), "Read_7")[1], np.full(3, -7, np.int16))
+
+
+def test_generic_dataset_reader(tmp_path):
+    """nd_h5_read_dataset on layouts other than the Signal's: 2-D contiguous doubles (as in the libhdf5-written file),
+    compact and chunked + deflate datasets in nested old-style groups, big-endian integers"""
+    w = hw.H5Writer(userblock=512)
+    a = np.arange(12, dtype="<f8").reshape(3, 4) / 7.0
+    b = np.arange(-5, 6, dtype="<i2")
+    c = dac(5000, 3)
+    e = (np.arange(40) * 1000 - 7).astype(">i4")
+    inner = w.group_old({"a": w.dataset_contiguous(a, w.msg_float64()), "b": w.dataset_compact(b, w.msg_fixed(2)),
+                         "c": w.dataset_chunked(c, w.msg_fixed(2), 512, filters=(2, 1)),
+                         "e": w.dataset_contiguous(e, w.msg_fixed(4, big_endian=True))})[0]
+    root, btree, heap = w.group_old({"grp": w.group_old({"inner": inner})[0]})
+    raw = w.finish(root, btree, heap)
+    info, data = read_dataset(raw, "/grp/inner/a")
+    assert info[:5] == [1, 8, 1, 0, 2] and info[6:8] == [3, 4] and np.array_equal(np.frombuffer(data, "<f8").reshape(3, 4), a)
+    info, data = read_dataset(raw, "grp/inner/b/")
+    assert info[:5] == [0, 2, 1, 0, 1] and np.array_equal(np.frombuffer(data, "<i2"), b)
+    info, data = read_dataset(raw, "/grp/inner/c")
+    assert info[5] == c.nbytes and np.array_equal(np.frombuffer(data, "<i2"), c)
+    info, data = read_dataset(raw, "/grp/inner/e")
+    assert info[:4] == [0, 4, 1, 1] and np.array_equal(np.frombuffer(data, ">i4"), e)     # bytes as stored
+    with pytest.raises(RuntimeError, match="not a dataset"):
+        read_dataset(raw, "/grp/inner")
+    with pytest.raises(RuntimeError, match="not a group"):
+        read_dataset(raw, "/grp/inner/a/x")
