@@ -261,7 +261,6 @@ class H5Writer:
         lay += struct.pack("<Q", addr)
         msgs = [(0x01, struct.pack("<BBBB", 2, 1, 0, 1) + struct.pack("<Q", n)), type_msg, (0x08, lay)]
         if filters:
-            names = {1: "", 2: "", 3: ""}
             b = struct.pack("<BB", 2, len(filters))
             for f in filters:
                 cd = {1: [level], 2: [elem], 3: []}[f]
