@@ -14,7 +14,6 @@ from __future__ import annotations
 import pickle
 from typing import List, Optional, Sequence, Tuple
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -1,8 +1,6 @@
 """ids -> tokens (reference: translate/translation.py:7-105, 108-156)."""
 from __future__ import annotations
 
-import torch
-
 
 class Translation(object):
     """Container for one translated chunk (translate/translation.py:108-156)."""

@@ -11,7 +11,7 @@ from __future__ import annotations
 import math
 import os
 from itertools import count
-from typing import List, Optional, Sequence
+from typing import List
 
 import numpy as np
 import torch

@@ -3,8 +3,6 @@
 """
 from __future__ import annotations
 
-from typing import Dict, List
-
 import torch
 
 UNK, PAD, BOS, EOS = 0, 1, 2, 3

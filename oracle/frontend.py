@@ -12,7 +12,7 @@ Third-party arithmetic restated here (absent from /root/reference and from this 
 from __future__ import annotations
 
 import math
-from typing import List, Tuple
+from typing import List
 
 import numpy as np
 

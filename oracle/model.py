@@ -6,7 +6,7 @@ Citations are relative to /root/reference.  Nothing here is used by the product 
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict
 
 import torch
 import torch.nn.functional as F

@@ -1,6 +1,6 @@
 """Mutation fuzzing of the host-side file readers (csrc/fast5.cu, csrc/vbz.cu) built with AddressSanitizer + UBSan
 (scripts/host_fuzz_asan.sh builds /tmp/libh5asan.so and runs this).  usage: host_fuzz.py SEED N_HDF5 N_ZSTD"""
-import ctypes as C, sys, zlib
+import ctypes as C, sys
 import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
