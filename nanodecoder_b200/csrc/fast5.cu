@@ -353,6 +353,12 @@ class H5File {
     return d;
   }
 
+  static bool has_vbz(const Dataset& d) {
+    for (const Filter& f : d.filters)
+      if (f.id == 32020) return true;
+    return false;
+  }
+
   uint64_t count(const Dataset& d) const {
     uint64_t c = 1;
     for (uint64_t x : d.dims) {
@@ -360,7 +366,9 @@ class H5File {
       c *= x;
     }
     // deflate expands at most ~1032 x: a dataspace far beyond what the file could hold is a corrupt header, not a read
-    if (c * d.elem > n_ * 1100 + (1ull << 20)) fail("dataspace larger than the file can hold");
+    // (zstd has no such bound - a constant chunk is one RLE block - so VBZ datasets get an absolute cap instead)
+    if (has_vbz(d) ? c * d.elem > (1ull << 31) : c * d.elem > n_ * 1100 + (1ull << 20))
+      fail("dataspace larger than the file can hold");
     return c;
   }
 
@@ -730,7 +738,8 @@ class H5File {
     const uint64_t cbytes = d.chunk[0] * d.elem;
     need_abs(abs_addr, stored);
     // deflate expands at most ~1032 x: a larger chunk shape is a corrupt layout message, not something to allocate
-    if (cbytes > (1ull << 32) || cbytes > stored * 1100 + 65536) fail("chunk shape larger than its stored bytes can fill");
+    if (cbytes > (1ull << 32) || (has_vbz(d) ? cbytes > (1ull << 28) : cbytes > stored * 1100 + 65536))
+      fail("chunk shape larger than its stored bytes can fill");
     std::vector<uint8_t> a(p_ + abs_addr, p_ + abs_addr + stored), b;
     for (int f = (int)d.filters.size() - 1; f >= 0; --f) {                  // undo the pipeline back to front
       if (mask & (1u << f)) continue;                                       // the writer skipped this filter for this chunk

@@ -230,6 +230,11 @@ def test_vbz_compressed_signal(tmp_path, flavour, chunk, level, version):
     name, got = read_signal(raw, tmp_path)
     assert name == "Read_9" and np.array_equal(got, sig)
     assert len(raw) < sig.nbytes * (0.75 if level else 1.2)                            # it does compress
+    if level and flavour == "old" and chunk == 70000:
+        # a constant chunk is a couple of zstd RLE blocks: far beyond deflate's 1032 x expansion, still a valid read
+        flat = np.full(300000, 517, np.int16)
+        raw = hw.make_fast5(flat, chunk=150000, filters=(32020,), level=level, kw_vbz_version=version)
+        assert len(raw) < 8000 and np.array_equal(read_signal(raw, tmp_path)[1], flat)
 
 
 def test_errors_keep_the_reference_types(tmp_path):
