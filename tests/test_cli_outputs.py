@@ -114,6 +114,15 @@ def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path, threads):
     (src / "r12.fast5").write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(200))     # a truncated HDF5 file: same
     sizes += [0, 0]
     suffix = {i: ("fast5" if i in fast5 or i == 12 else "signal") for i in range(len(sizes))}
+    raws += [np.zeros(0, np.int16)] * 2                                  # the two corrupt reads
+    multi = {}                                                           # two more reads inside ONE multi-read file
+    for i, n in ((13, 150), (14, 410)):
+        x = rng.integers(300, 900, size=n).astype(np.int16)
+        multi["r%02d" % i] = x
+        raws.append(x)
+        sizes.append(n)
+        suffix[i] = "fast5:read_r%02d" % i
+    (src / "zz_multi.fast5").write_bytes(h5_writer.make_multi_fast5(multi, chunk=100))
     opt = _opt(str(tmp_path / "out"), stride=T, length=T)
     opt.src_dir, opt.thread, opt.batch_size, opt.attn_debug = str(src), threads, B, False   # groups of 8 * threads reads
 
@@ -128,7 +137,8 @@ def test_read_loop_with_prefetch_and_write_behind_threads(tmp_path, threads):
         return torch.from_numpy(chunks), torch.from_numpy(lens), cr
 
     tr, eng = _translator(L, batch_size=B)
-    todo = [(i, ("r%02d.%s" % (i, suffix[i]), suffix[i], "r%02d.txt" % i)) for i in range(len(sizes))]
+    todo = [(i, ("zz_multi.fast5" if ":" in suffix[i] else "r%02d.%s" % (i, suffix[i]), suffix[i], "r%02d.txt" % i))
+            for i in range(len(sizes))]
     assert [(t[0], t[1]) for t in cli.list_reads(opt)[0]] == [t[1][:2] for t in todo]
     lines = cli.run_reads(opt, todo, read_raw_signal, frontend, tr)
     cli.finish_lines(opt, lines)
