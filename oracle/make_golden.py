@@ -523,6 +523,91 @@ def make_frontend_golden(write=True):
         np.savez_compressed(os.path.join(GOLDEN_DIR, "frontend.npz"), n_reads=len(reads), **store)
 
 
+def check_fast5_branch():
+    """The reference's own '.fast5' branch (utils/labelop.py:199-214), run UNMODIFIED over an `h5py` stand-in that serves
+    `File(path)['/Raw/Reads/'].values()` / `['Signal'].value` from libnanodec's reader (nd_fast5_list_reads /
+    nd_fast5_read_signal_of): its chunk strings must equal those of its '.signal' branch on the same samples (an int16
+    array instead of a list of floats enters the normalisation).  Files are laid out by tests/h5_writer.py."""
+    refshim.install()
+    import tempfile
+    import statsmodels.robust as robust
+    if not hasattr(robust, "mad"):
+        robust.mad = ofrontend.mad
+    import numpy
+    if not hasattr(numpy, "float"):
+        numpy.float = float
+    import h5py
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import h5_writer
+    from nanodecoder_b200.utils import labelop
+
+    class _Dataset(object):
+        def __init__(self, path, name):
+            self.value = labelop.read_fast5_signal(path, name)[1]
+
+    class _Read(object):
+        def __init__(self, path, name):
+            self.path, self.name = path, name
+
+        def __getitem__(self, key):
+            assert key == "Signal", key
+            return _Dataset(self.path, self.name)
+
+    class _Reads(object):
+        def __init__(self, path):
+            self.path = path
+
+        def values(self):
+            return [_Read(self.path, n) for n in labelop.list_fast5_reads(self.path)[1]]
+
+    class _File(object):
+        def __init__(self, path, mode="r"):
+            try:
+                labelop.list_fast5_reads(path)
+            except IOError:
+                raise
+            except RuntimeError:
+                pass                                             # an HDF5 file without /Raw/Reads opens; the lookup fails
+            self.path = path
+
+        def __getitem__(self, key):
+            assert key == "/Raw/Reads/", key
+            return _Reads(self.path)
+
+        def close(self):
+            pass
+
+    h5py.File = _File
+    from utils.labelop import extract_fast5_raw
+    reads = synth.make_raw_reads(2, seed=41, min_len=900, max_len=4000)
+    layouts = [dict(chunk=512, filters=(2, 1), other_reads=("Read_99", "read_1")),
+               dict(chunk=1000, filters=(32020,), kw_vbz_version=1)]
+    n = 0
+    with tempfile.TemporaryDirectory() as tmp:
+        for ri, (raw, kw) in enumerate(zip(reads, layouts)):
+            p5, ps = os.path.join(tmp, "r%d.fast5" % ri), os.path.join(tmp, "r%d.signal" % ri)
+            with open(p5, "wb") as f:
+                f.write(h5_writer.make_fast5(raw, read_name="Read_%d" % (10 + ri), **kw))
+            with open(ps, "w") as f:
+                f.write(" ".join(str(int(v)) for v in raw))
+            for norm in ("median", "mean"):
+                for (L, S) in ((512, 512), (300, 60)):
+                    a = extract_fast5_raw(p5, "r.txt", norm, L, S, "fast5")
+                    b = extract_fast5_raw(ps, "r.txt", norm, L, S, "signal")
+                    assert a == b and len(a) > 1, "the reference's fast5 branch differs from its signal branch"
+                    n += 1
+        bad = os.path.join(tmp, "bad.fast5")
+        with open(bad, "wb") as f:
+            f.write(b"not hdf5")
+        try:
+            extract_fast5_raw(bad, "r.txt", "median", 512, 512, "fast5")
+            raise AssertionError("a file that is not HDF5 must raise")
+        except IOError as e:
+            assert "Likely a corrupted file" in str(e)
+    print("fast5: the reference's '.fast5' branch over libnanodec's reader == its '.signal' branch on %d runs; "
+          "IOError text kept" % n)
+
+
 def assembly_cases():
     """Seeded inputs for the read-assembly golden: overlapping windows of a random genome with substitution / indel
     noise, repeats (longest-block ties), empty chunks, and base strings >= 200 (difflib's autojunk rule)."""
@@ -583,9 +668,13 @@ def main():
     ap.add_argument("--B", type=int, default=6)
     ap.add_argument("--beam-cases", nargs="*", default=None, help="only the non-degenerate --fast beam cases named")
     ap.add_argument("--beam-attn", action="store_true", help="only the beam attention cases")
+    ap.add_argument("--fast5", action="store_true", help="only the check of the reference's '.fast5' branch")
     args = ap.parse_args()
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if args.fast5:
+        check_fast5_branch()
+        return
     if args.beam_attn:
         for name in BEAM_ATTN_CASES:
             make_beam_attn_case(name, write=not args.no_write)
@@ -597,6 +686,7 @@ def main():
             make_beam_case(name, B=args.B, write=not args.no_write)
         return
     make_frontend_golden(write=not args.no_write)
+    check_fast5_branch()
     make_assembly_golden(write=not args.no_write)
     for name in BEAM_CASES:
         make_beam_case(name, B=args.B, write=not args.no_write)

@@ -338,3 +338,16 @@ def test_generic_dataset_reader(tmp_path):
         read_dataset(raw, "/grp/inner")
     with pytest.raises(RuntimeError, match="not a group"):
         read_dataset(raw, "/grp/inner/a/x")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree (build container only)")
+def test_reference_fast5_branch_over_this_reader():
+    """the UNMODIFIED reference's `extract_fast5_raw(..., 'fast5')` (utils/labelop.py:199-214) with `h5py.File` served by
+    libnanodec's reader gives the chunk strings of its '.signal' branch (oracle/make_golden.py::check_fast5_branch; in a
+    subprocess: the harness patches torch for the torch-1.0 reference)"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "oracle", "make_golden.py"), "--fast5"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "== its '.signal' branch on 8 runs" in r.stdout
