@@ -166,8 +166,9 @@ class H5Writer:
         addr = self.alloc(raw)
         if layout_version == 3:
             lay = struct.pack("<BBQQ", 3, 1, addr, len(raw))
-        else:                                                          # v1: dimensionality, class, 5 reserved, address, dims
-            lay = struct.pack("<BBB5xQ", 1, arr.ndim, 1, addr) + b"".join(struct.pack("<I", d) for d in arr.shape)
+        else:                                   # v1 / v2: dimensionality (rank + 1), class, 5 reserved, address, dims + element
+            lay = (struct.pack("<BBB5xQ", layout_version, arr.ndim + 1, 1, addr) +   # size, as libhdf5 writes them (the
+                   b"".join(struct.pack("<I", d) for d in arr.shape + (arr.dtype.itemsize,)))  # MATLAB file's layout message)
         msgs = [self.msg_dataspace(arr.shape), type_msg, (0x08, lay)]
         return (self.object_header_v2 if v2 else self.object_header_v1)(msgs)
 
