@@ -230,6 +230,11 @@ ND_EXPORT int nd_fast5_list_reads(const uint8_t* file, int64_t nbytes, char* nam
                                   int32_t* n_reads, int32_t* layout, char* err, int32_t errcap);
 ND_EXPORT int nd_fast5_read_signal_of(const uint8_t* file, int64_t nbytes, const char* read_name, int16_t* out, int64_t cap,
                                       int64_t* count, char* err, int32_t errcap);
+/* nd_h5_list_group: member names of the group at `path` ("/" = root), NUL separated, in name order (h5py's iteration
+ *   order); written while they fit names_cap, *names_bytes = bytes needed.  With nd_h5_read_dataset this is what
+ *   nanodecoder_b200/utils/h5lite.py builds its h5py-shaped File / Group / Dataset objects from.                     */
+ND_EXPORT int nd_h5_list_group(const uint8_t* file, int64_t nbytes, const char* path, char* names, int64_t names_cap,
+                               int64_t* names_bytes, int32_t* n_members, char* err, int32_t errcap);
 ND_EXPORT int nd_h5_read_dataset(const uint8_t* file, int64_t nbytes, const char* path, uint8_t* out, int64_t cap,
                                  int64_t* info, char* err, int32_t errcap);
 /* nd_zstd_decompress: the Zstandard decoder (RFC 8878, no dictionaries) behind the VBZ filter of .fast5 chunks, exposed

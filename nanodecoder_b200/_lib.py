@@ -55,6 +55,8 @@ SIGNATURES = {
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_char_p, C.c_int32]),
     "nd_fast5_read_signal_of": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.POINTER(C.c_int16), C.c_int64,
                                           C.POINTER(C.c_int64), C.c_char_p, C.c_int32]),
+    "nd_h5_list_group": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int32), C.c_char_p, C.c_int32]),
     "nd_h5_read_dataset": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.POINTER(C.c_uint8), C.c_int64,
                                      C.POINTER(C.c_int64), C.c_char_p, C.c_int32]),
     "nd_zstd_decompress": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_uint8), C.c_int64, C.POINTER(C.c_int64),

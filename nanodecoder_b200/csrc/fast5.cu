@@ -919,6 +919,31 @@ int nd_fast5_list_reads(const uint8_t* file, int64_t nbytes, char* names, int64_
   }
 }
 
+int nd_h5_list_group(const uint8_t* file, int64_t nbytes, const char* path, char* names, int64_t names_cap, int64_t* names_bytes,
+                     int32_t* n_members, char* err, int32_t errcap) {
+  if (!file || nbytes < 0 || !path || !names_bytes || !n_members || names_cap < 0 || (names_cap > 0 && !names)) return ND_ERR_INVALID;
+  *names_bytes = 0; *n_members = 0;
+  try {
+    H5File f(file, (uint64_t)nbytes);
+    const std::vector<Link> members = f.links(f.resolve(path));             // name order, like h5py's iteration
+    int64_t at = 0;
+    for (const Link& l : members) {
+      const int64_t len = (int64_t)l.name.size() + 1;
+      if (at + len <= names_cap) memcpy(names + at, l.name.c_str(), (size_t)len);
+      at += len;
+    }
+    *names_bytes = at;
+    *n_members = (int32_t)members.size();
+    return ND_OK;
+  } catch (const H5Error& e) {
+    put_error(err, errcap, e.msg);
+    return ND_ERR_INVALID;
+  } catch (const std::exception& e) {
+    put_error(err, errcap, e.what());
+    return ND_ERR_NOMEM;
+  }
+}
+
 int nd_fast5_read_signal_of(const uint8_t* file, int64_t nbytes, const char* read_name, int16_t* out, int64_t cap,
                             int64_t* count, char* err, int32_t errcap) {
   if (!file || nbytes < 0 || !read_name || !count || cap < 0 || (cap > 0 && !out)) return ND_ERR_INVALID;

@@ -524,9 +524,9 @@ def make_frontend_golden(write=True):
 
 
 def check_fast5_branch():
-    """The reference's own '.fast5' branch (utils/labelop.py:199-214), run UNMODIFIED over an `h5py` stand-in that serves
-    `File(path)['/Raw/Reads/'].values()` / `['Signal'].value` from libnanodec's reader (nd_fast5_list_reads /
-    nd_fast5_read_signal_of): its chunk strings must equal those of its '.signal' branch on the same samples (an int16
+    """The reference's own '.fast5' branch (utils/labelop.py:199-214), run UNMODIFIED with `h5py.File` replaced by
+    nanodecoder_b200/utils/h5lite.py (File / Group / Dataset objects over libnanodec's reader: nd_h5_list_group,
+    nd_h5_read_dataset): its chunk strings must equal those of its '.signal' branch on the same samples (an int16
     array instead of a list of floats enters the normalisation).  Files are laid out by tests/h5_writer.py."""
     refshim.install()
     import tempfile
@@ -539,45 +539,8 @@ def check_fast5_branch():
     import h5py
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import h5_writer
-    from nanodecoder_b200.utils import labelop
-
-    class _Dataset(object):
-        def __init__(self, path, name):
-            self.value = labelop.read_fast5_signal(path, name)[1]
-
-    class _Read(object):
-        def __init__(self, path, name):
-            self.path, self.name = path, name
-
-        def __getitem__(self, key):
-            assert key == "Signal", key
-            return _Dataset(self.path, self.name)
-
-    class _Reads(object):
-        def __init__(self, path):
-            self.path = path
-
-        def values(self):
-            return [_Read(self.path, n) for n in labelop.list_fast5_reads(self.path)[1]]
-
-    class _File(object):
-        def __init__(self, path, mode="r"):
-            try:
-                labelop.list_fast5_reads(path)
-            except IOError:
-                raise
-            except RuntimeError:
-                pass                                             # an HDF5 file without /Raw/Reads opens; the lookup fails
-            self.path = path
-
-        def __getitem__(self, key):
-            assert key == "/Raw/Reads/", key
-            return _Reads(self.path)
-
-        def close(self):
-            pass
-
-    h5py.File = _File
+    from nanodecoder_b200.utils import h5lite
+    h5py.File = h5lite.File                                  # the h5py-shaped facade over libnanodec's reader
     from utils.labelop import extract_fast5_raw
     reads = synth.make_raw_reads(2, seed=41, min_len=900, max_len=4000)
     layouts = [dict(chunk=512, filters=(2, 1), other_reads=("Read_99", "read_1")),

@@ -351,3 +351,37 @@ def test_reference_fast5_branch_over_this_reader():
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "== its '.signal' branch on 8 runs" in r.stdout
+
+
+def test_h5py_shaped_facade(tmp_path):
+    """nanodecoder_b200/utils/h5lite.py: the File / Group / Dataset surface the reference's reader touches
+    (utils/labelop.py:199-214), over libnanodec's reader"""
+    from nanodecoder_b200.utils import h5lite
+    sig = dac(7000, 17)
+    p = tmp_path / "a.fast5"
+    p.write_bytes(hw.make_fast5(sig, read_name="Read_33", chunk=1024, filters=(32020,), kw_vbz_version=1,
+                                other_reads=("Read_4", "Read_9")))
+    f = h5lite.File(str(p), "r")
+    reads = f["/Raw/Reads/"]
+    assert list(reads.keys()) == ["Read_33", "Read_4", "Read_9"] and len(reads) == 3 and "Read_4" in reads
+    ds = list(reads.values())[0]["Signal"]                                    # the reference's expression
+    assert ds.shape == (7000,) and ds.dtype == np.dtype("<i2") and len(ds) == 7000
+    assert np.array_equal(ds.value, sig) and np.array_equal(ds[()], sig) and np.array_equal(ds[10:20], sig[10:20])
+    assert np.array_equal(np.asarray(ds), sig)
+    assert sorted(f.keys()) == ["Analyses", "PreviousReadInfo", "Raw", "UniqueGlobalKey"]
+    assert np.array_equal(f["Raw"]["Reads"]["Read_9/Signal"][...], np.full(3, -7, np.int16))
+    assert [k for k, _ in f["/UniqueGlobalKey"].items()] == ["channel_id", "context_tags", "tracking_id"]
+    with pytest.raises(KeyError):
+        f["/Raw/Reads/Read_5"]
+    assert "nope" not in f
+    f.close()
+    with h5lite.File(os.path.join(GOLDEN, "libhdf5_matlab73.mat")) as m:      # the libhdf5-written file
+        d = m["testdouble"]
+        assert d.shape == (9, 1) and d.dtype == np.dtype("<f8")
+        assert np.array_equal(d[()][:, 0], np.arange(0, 2 * np.pi + 1e-9, np.pi / 4))
+    bad = tmp_path / "bad.fast5"
+    bad.write_bytes(b"junk" * 50)
+    with pytest.raises(IOError):                                              # what utils/labelop.py:203 catches
+        h5lite.File(str(bad), "r")
+    with pytest.raises(ValueError):
+        h5lite.File(str(p), "w")
