@@ -21,6 +21,14 @@ def read(raw, cap=20000):
 def readof(raw, nm, cap=20000):
     out=(C.c_int16*cap)(); cnt=C.c_int64(0); err=C.create_string_buffer(256)
     return lib.nd_fast5_read_signal_of(raw,len(raw),nm,out,cap,C.byref(cnt),err,256)
+lib.nd_h5_list_group.argtypes=[C.c_char_p,C.c_int64,C.c_char_p,C.c_char_p,C.c_int64,C.POINTER(C.c_int64),C.POINTER(C.c_int32),C.c_char_p,C.c_int32]
+lib.nd_h5_read_dataset.argtypes=[C.c_char_p,C.c_int64,C.c_char_p,C.POINTER(C.c_uint8),C.c_int64,C.POINTER(C.c_int64),C.c_char_p,C.c_int32]
+def generic(raw):
+    names=C.create_string_buffer(4096); need=C.c_int64(0); n=C.c_int32(0); err=C.create_string_buffer(256)
+    for path in (b"/", b"/Raw/Reads", b"/UniqueGlobalKey"):
+        lib.nd_h5_list_group(raw,len(raw),path,names,4096,C.byref(need),C.byref(n),err,256)
+    info=(C.c_int64*8)(); out=(C.c_uint8*40000)()
+    lib.nd_h5_read_dataset(raw,len(raw),b"/Raw/Reads/Read_17/Signal",out,40000,info,err,256)
 def lst(raw):
     names=C.create_string_buffer(4096); need=C.c_int64(0); n=C.c_int32(0); lay=C.c_int32(0); err=C.create_string_buffer(256)
     return lib.nd_fast5_list_reads(raw,len(raw),names,4096,C.byref(need),C.byref(n),C.byref(lay),err,256)
@@ -44,7 +52,7 @@ for it in range(int(sys.argv[2]) if len(sys.argv)>2 else 3000):
         else: f[pos:pos+8]=b"\xff"*8
     if rng.random()<0.1: f=f[:int(rng.integers(0,len(f)))]
     f=bytes(f)
-    r=read(f); lst(f); readof(f,b"read_a"); readof(f,b"Read_17")
+    r=read(f); lst(f); readof(f,b"read_a"); readof(f,b"Read_17"); generic(f)
     ok+= r==0; bad+= r!=0
 print("hdf5 fuzz: ok",ok,"errors",bad)
 # zstd fuzz
