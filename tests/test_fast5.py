@@ -385,3 +385,20 @@ def test_h5py_shaped_facade(tmp_path):
         h5lite.File(str(bad), "r")
     with pytest.raises(ValueError):
         h5lite.File(str(p), "w")
+
+
+def test_committed_fast5_fixtures():
+    """tests/golden/fast5_*.fast5: three small files laid out by tests/h5_writer.py (single-read gzip + shuffle, single-read
+    VBZ v1, multi-read VBZ v1) with their samples in fast5_samples.npz.  They are committed so that anyone with h5py and
+    the VBZ plugin can check the WRITER against libhdf5 (`h5py.File(f)['/Raw/Reads/Read_101/Signal'][()]`) — the one
+    cross-check this image cannot run — and they pin the reader against accidental format drift of the writer."""
+    want = np.load(os.path.join(GOLDEN, "fast5_samples.npz"))
+    name, got = labelop.read_fast5_signal(os.path.join(GOLDEN, "fast5_single_gzip.fast5"))
+    assert name == "Read_101" and np.array_equal(got, want["single_gzip"])
+    name, got = labelop.read_fast5_signal(os.path.join(GOLDEN, "fast5_single_vbz.fast5"))
+    assert name == "Read_102" and np.array_equal(got, want["single_vbz"])
+    multi = os.path.join(GOLDEN, "fast5_multi_vbz.fast5")
+    layout, names = labelop.list_fast5_reads(multi)
+    assert layout == 2 and len(names) == 3
+    for nm in names:
+        assert np.array_equal(labelop.read_fast5_signal(multi, nm)[1], want["multi_" + nm[5:].replace("-", "_")])
