@@ -121,7 +121,7 @@ class H5Writer:
         for nm in names:
             offs[nm] = len(heap_data)
             heap_data += _pad8(nm.encode() + b"\0")
-        heap_data += b"\0" * 16                                        # free block
+        heap_data += struct.pack("<QQ", 1, 16)                         # the one free block: next = 1 (none), 16 bytes
         data_addr = self.alloc(bytes(heap_data))
         heap = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), len(heap_data) - 16, data_addr))
         per = 2 * self.leaf_k
@@ -143,6 +143,7 @@ class H5Writer:
                 for addr, key in part:
                     body += struct.pack("<QQ", addr, key)
                 node = b"TREE" + struct.pack("<BBHQQ", 0, level, len(part), UNDEF, UNDEF) + body
+                node += b"\0" * (24 + (2 * 16 + 1) * 8 + 2 * 16 * 8 - len(node))   # libhdf5 reads whole nodes (K = 16)
                 nodes.append((self.alloc(node), part[-1][1]))
             children = nodes
             level += 1
@@ -226,6 +227,7 @@ class H5Writer:
                     body += key(e) + struct.pack("<Q", e[3])
                 body += struct.pack("<IIQQ", 0, 0, (part[-1][2] + chunk) if part else 0, 0)   # closing key
                 node = b"TREE" + struct.pack("<BBHQQ", 1, level_no, len(part), UNDEF, UNDEF) + body
+                node += b"\0" * max(0, 24 + (2 * 32 + 1) * 24 + 2 * 32 * 8 - len(node))   # whole node at the default K = 32
                 first = part[0] if part else (0, 0, 0, 0)
                 nodes.append((first[0], first[1], first[2], self.alloc(node)))
             children = nodes
@@ -271,7 +273,7 @@ class H5Writer:
 
     # ---- finish
     def finish(self, root, btree=UNDEF, heap=UNDEF, cache_root=True):
-        eof = len(self.buf) - self.base
+        eof = len(self.buf)            # stored as in the libhdf5-written MATLAB file: base address + relative end (= file size)
         if self.sb_version in (0, 1):
             sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBxBBBxHHI", self.sb_version, 0, 0, 0, 8, 8, self.leaf_k, 16, 0)
             if self.sb_version == 1:
