@@ -127,6 +127,9 @@ class Translator(object):
             raise ValueError("random sampling (topk != 1) is outside the supported translate path")
         if opt.dump_beam or opt.replace_unk:
             raise ValueError("dump_beam / replace_unk are outside the supported translate path")
+        if getattr(opt, "fft", False):
+            # translate/translator.py:143,227 -> inputters/nano_dataset.py:64-77: librosa STFT magnitudes as encoder input
+            raise ValueError("-fft (spectrogram input through librosa's STFT) is outside the supported translate path")
         self.block_ngram_repeat = int(opt.block_ngram_repeat)
         self.ignore_when_blocking = set(getattr(opt, "ignore_when_blocking", []) or [])
         if self.block_ngram_repeat != 0 and (self.beam_size == 1 or self.fast):

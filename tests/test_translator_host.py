@@ -199,3 +199,12 @@ def test_attention_dump_has_the_reference_layout():
     txt = format_attention([0.5, -1.234375, 12.0], ["A", "C"], [[0.25, 0.75, 0.0], [1.0, 0.0, 0.0]])
     assert txt == ("       >      0.5  -1.2343     12.0 " "       |        A        C     </s> \n"
                    " 0.25000  0.75000  0.00000 \n" " 1.00000  0.00000  0.00000 \n")
+
+
+def test_flags_outside_the_path_are_refused_with_the_reason():
+    """flags the reference would act on but this engine does not implement must not be ignored silently"""
+    for kw, word in ((dict(fft=True), "-fft"), (dict(dump_beam="beams.json"), "dump_beam"), (dict(replace_unk=True), "replace_unk"),
+                     (dict(random_sampling_topk=5), "random sampling")):
+        opt = default_translate_opt(beam_size=1, max_length=8, src_seq_length=64, gpu=0, **kw)
+        with pytest.raises(ValueError, match=word):
+            Translator(RecordingEngine(8), {"tgt": _Field(_Vocab(VOCAB))}, opt, ModelConfig.family("l2t"))
